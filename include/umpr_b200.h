@@ -1,0 +1,130 @@
+/* umpr_b200 — C-ABI of the B200-native UMPR review-network hot path.
+ *
+ * This is the drop-in boundary: plain C, raw device pointers, explicit sizes, the CUDA stream as
+ * void*.  No torch types.  Every function cites the reference code it replaces (paths relative to the reference
+ * repository iamwinter/UMPR).  The reference ships no native code: each entry point below replaces the stock
+ * PyTorch/ATen/cuDNN/cuBLAS operators that the cited Python lines dispatch to.
+ *
+ * Conventions
+ *   - return value: 0 ok; UMPR_ERR_ARG (<0) bad argument/shape (see umpr_last_error()); >0 a cudaError_t.
+ *   - all tensors are dense row-major fp32 unless stated; token ids and nothing else are int64; plans are int32.
+ *   - launches are asynchronous on `stream`; no hidden synchronisation; the library owns no device memory.
+ *   - fixed hot-path sizes: gru_size 64, self_atte_size 64, conv kernel_size 3, kernel_count <= 128 (config.py:34-37).
+ *   - "d_*" / "*grad*" outputs marked (+=) are accumulated with atomics and must be initialised by the caller.
+ *
+ * Pack plan (int32 device buffer, built on the host from the reference's own torch.sort call, model.py:18):
+ *   [seq_of (Rp) | row_of (Rp) | len_of (Rp) | tile_off (n_tiles+1) | slab_tile (n_slabs)],  Rp = n_tiles*R
+ *   job k (descending length): reads input sequence seq_of[k], fills ImprovedRnn output row row_of[k] (model.py:21),
+ *   has length len_of[k] (0 = padding job).  Tile j = jobs [j*R, (j+1)*R) owns slabs tile_off[j] .. +len_of[j*R].
+ */
+#ifndef UMPR_B200_H
+#define UMPR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UMPR_B200_VERSION 100
+#define UMPR_ERR_ARG (-1)
+
+int umpr_version(void);
+const char* umpr_last_error(void);              /* thread-local message of the last failing call */
+int umpr_sm_count(int device, int* out);
+
+/* ---- ImprovedRnn: src/model.py:12-21 (pack_padded_sequence -> nn.GRU -> pad_packed_sequence -> 2nd un-sort),
+ *      embedding gather src/model.py:262-264.  `w` / `dw` are 8 pointers in nn.GRU order:
+ *      weight_ih_l0 (192,E), weight_hh_l0 (192,64), bias_ih_l0, bias_hh_l0, then the *_reverse four. ---- */
+/* xp[n_slabs][R][64] <- embedding rows (table[ids], or dense (Nseq,L,E) when dense != NULL), a 1.0 bias column, zeros */
+int umpr_gather_pack(const float* table, const int64_t* ids, const float* dense, const int32_t* plan, int n_tiles,
+                     int n_slabs, int R, int L, int E, float* xp, void* stream);
+/* G[n_slabs][2][R][192] = xp · [W_ih | b_ih (+ b_hh for r,z)]^T for both directions */
+int umpr_gru_inproj(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, void* stream);
+/* out (N,L,128) fully written (zeros for t >= length, total_length = L, model.py:17,20); hn (2,N,64) or NULL;
+ * sv[n_slabs][2][R][256] saved gates for backward, or NULL for inference (evaluate.py:8-11) */
+int umpr_gru_recurrence_fwd(const float* G, const float* const* w, const int32_t* plan, int n_tiles, int n_slabs, int R,
+                            int N, int L, float* out, float* hn, float* sv, void* stream);
+/* dG[n_slabs][2][R][256] = d(gate pre-activations) [dr, dz, dn, dn*r]; d_hn may be NULL */
+int umpr_gru_recurrence_bwd(const float* d_out, const float* d_hn, const float* out, const float* sv, const float* const* w,
+                            const int32_t* plan, int n_tiles, int n_slabs, int R, int N, int L, float* dG, void* stream);
+/* dw[8] (+=): gradients of the 8 GRU tensors.  No input gradient: the embedding is frozen (model.py:237). */
+int umpr_gru_wgrad(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int R,
+                   int L, int E, float* const* dw, int n_ctas, void* stream);
+
+/* ---- generic strided fp32 GEMM: gi·M (model.py:50), text matching (model.py:168) and their gradients ----
+ * C[m][n] = act(accumulate*C + sum_k A[m*ars+k*acs] * B[k*brs+n*bcs] + bias[n]); act 0 none, 1 tanh, 2 relu, 3 sigmoid.
+ * splits > 1: split-K with atomic accumulation into C (C must be initialised; bias/act not allowed). */
+int umpr_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc, int M, int N, int K,
+               int splits, int accumulate, const float* bias, int act, void* stream);
+
+/* ---- RNet co-attention: src/model.py:50-55.  gu, gi, giM (=gi·M): (B,P,128).  The (P,P) affinity matrix is never
+ *      materialised.  rowkey/colkey: (B,P) uint64 scratch, colkey zero-initialised.  t_*: tanh of the row/col maxima,
+ *      arg_*: their positions (saved for backward). ---- */
+int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, int P, unsigned long long* rowkey,
+                    unsigned long long* colkey, float* soft_u, float* soft_i, float* t_u, float* t_i, int32_t* arg_u,
+                    int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
+/* dgu, dgi (without the dgiM·M^T term), dgiM: (B,P,128) fully written.  d_* inputs may be NULL. */
+int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i, const float* t_u,
+                    const float* t_i, const int32_t* arg_u, const int32_t* arg_i, const float* d_soft_u, const float* d_soft_i,
+                    const float* d_atte_u, const float* d_atte_i, int B, int P, float* dgu, float* dgi, float* dgiM, void* stream);
+
+/* ---- SNet: src/model.py:71-81.  x = gru_repr viewed (N, L, 128), N = B*S. ---- */
+int umpr_snet_fwd(const float* x, const float* Ms, const float* Ws, int N, int L, float* self_atte /*(N,128)*/,
+                  float* soft /*(N,L) or NULL*/, float* th /*(N,L,64) or NULL*/, int n_ctas, void* stream);
+int umpr_snet_sentiment_fwd(const float* self_atte, const float* word_soft /*(B,S,Wd)*/, int B, int S, int Wd, float* wsum /*(B,S)*/,
+                            float* sentiment /*(B,128)*/, void* stream);
+int umpr_snet_sentiment_bwd(const float* self_atte, const float* wsum, const float* d_sentiment, const float* d_self_atte_up, int B,
+                            int S, float* d_self_atte, float* d_wsum, void* stream);
+int umpr_snet_bwd(const float* x, const float* th, const float* soft, const float* d_self_atte, const float* Ms, const float* Ws, int N,
+                  int L, float* dx /*(N,L,128) written*/, float* dMs /*(+=)*/, float* dWs /*(+=)*/, int n_ctas, void* stream);
+
+/* ---- CNet tail: src/model.py:118-125 ---- */
+int umpr_cnet_prep(const float* conv_w /*(KC,128,3)*/, int KC, int ksize, float* wt /*(384,128)*/, void* stream);
+int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int N, int L, int KC, float* cfeat /*(N,KC)*/,
+                       int32_t* cidx /*(N,KC) arg-max position, -1 if clipped by ReLU*/, int n_ctas, void* stream);
+int umpr_cnet_head_fwd(const float* cfeat, const float* lin_w, const float* lin_b, float threshold, int B, int S, int V, int KC,
+                       float* view_p /*(B,S,V)*/, float* final_repr /*(B,V)*/, void* stream);
+int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* view_p, const float* lin_w, const float* d_view_p,
+                       const float* d_final, int B, int S, int V, int KC, float* dcfeat /*(N,KC) written*/, float* d_lin_w /*(+=)*/,
+                       float* d_lin_b /*(+=)*/, float* d_conv_b /*(+=)*/, void* stream);
+int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC,
+                       float* dx /*(N,L,128) written*/, float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
+
+/* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */
+int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b, float eps,
+                          int B, int Su, int V, float* senti, float* score, float* prefer_pos, float* prefer_neg, void* stream);
+int umpr_control_tail_bwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* senti,
+                          const float* score, const float* d_prefer_pos, const float* d_prefer_neg, float eps, int B, int Su, int V,
+                          float* d_s, float* d_view_p, float* d_c_out, float* d_ss_w /*(+=)*/, float* d_ss_b /*(+=)*/, void* stream);
+
+/* ---- VisualNet tail: src/model.py:219-228 on VGG16 *features* (B,V,Pc,F); the backbone (model.py:204-207,217) is out of scope ---- */
+int umpr_visual_fwd(const float* feat, const float* pos_v_emb, const float* neg_v_emb, const float* w, const float* bias,
+                    const float* c_u, const float* c_i, int B, int V, int Pc, int F, float* emb /*(2,V)*/, float* img_emb,
+                    float* pos_match, float* neg_match, float* final_pos, float* final_neg, void* stream);
+int umpr_visual_bwd(const float* feat, const float* pos_v_emb, const float* neg_v_emb, const float* w, const float* emb,
+                    const float* img_emb, const float* pos_match, const float* neg_match, const float* c_u, const float* c_i,
+                    const float* d_pos_match, const float* d_neg_match, const float* d_final_pos, const float* d_final_neg, int B, int V,
+                    int Pc, int F, float* scratch /*3*B*V*/, float* d_c_u, float* d_c_i, float* d_pos_v_emb, float* d_neg_v_emb,
+                    float* d_w /*(+=)*/, float* d_b /*(+=)*/, void* stream);
+
+/* ---- fusion Linear+ReLU (model.py:242-245,252-255,268,274) and losses (model.py:269,275-277) ---- */
+int umpr_fusion_fwd(const float* repr, const float* final_pos, const float* final_neg, const float* w, const float* bias, int B, int V,
+                    float* pred, void* stream);
+int umpr_fusion_bwd(const float* repr, const float* final_pos, const float* final_neg, const float* w, const float* pred,
+                    const float* d_pred, int B, int V, float* d_repr, float* d_final_pos, float* d_final_neg, float* d_w /*(+=)*/,
+                    float* d_b /*(+=)*/, void* stream);
+int umpr_loss_fwd(const float* pred, const float* labels, const float* prefer_pos, const float* prefer_neg, const float* pos_match,
+                  const float* neg_match, int B, int V, float loss_v_rate, float* loss /*zero-initialised scalar*/, void* stream);
+int umpr_loss_bwd(const float* pred, const float* labels, const float* prefer_pos, const float* prefer_neg, const float* pos_match,
+                  const float* neg_match, const float* d_loss, int B, int V, float loss_v_rate, float* d_pred, float* d_prefer_pos,
+                  float* d_prefer_neg, float* d_pos_match, float* d_neg_match, void* stream);
+int umpr_tanh_bwd(const float* y, const float* dy, long n, float* dx, void* stream);
+
+/* ---- train step tail: main.py:22-26,37 Adam with L2 on non-bias tensors, fused over one flat parameter buffer ---- */
+int umpr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay /*per element*/,
+                   long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

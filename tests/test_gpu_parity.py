@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C-ABI) against the reference's golden outputs and the CPU oracle.
+Bar: bit-exact packing order / zero pattern; max|a-b|/max|b| <= 1e-4 per fp32 tensor."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import assert_close, load_golden, rel_max
+from oracle import umpr_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def _model(c):
+    import umpr_b200
+    params = cases.make_params(c["review_net_only"], c["V"], c["vocab"], c["seed"], c["m_scale"])
+    m = umpr_b200.UMPR(cases.CaseConfig(c), params["embedding.weight"])
+    r = m.load_state_dict(params, strict=True)          # reference state_dict keys load unchanged
+    assert not r.missing_keys and not r.unexpected_keys
+    return m.to(DEV), params
+
+
+@pytest.mark.parametrize("name", list(cases.RNN_CASES))
+@pytest.mark.parametrize("R", [32, 64, 128])
+def test_improved_rnn_vs_reference(name, R, monkeypatch):
+    import umpr_b200
+    from umpr_b200 import plan as plan_mod
+    monkeypatch.setattr(plan_mod, "choose_tile_rows", lambda n, sm: R)
+    g = load_golden(name)
+    data, lens, w, cot_out, cot_hid = cases.make_rnn_case(cases.RNN_CASES[name])
+    rnn = umpr_b200.ImprovedRnn(torch.nn.GRU, input_size=cases.E, hidden_size=cases.H, batch_first=True, bidirectional=True)
+    rnn.load_state_dict(w, strict=True)
+    rnn = rnn.to(DEV)
+    result, hidden = rnn(data.to(DEV), lens)            # lengths stay on the host, as in the reference
+    assert_close(result, g["result"], TOL, "result")
+    assert_close(hidden, g["hidden"], TOL, "hidden")
+    assert np.array_equal((result.detach().cpu().numpy() != 0).any(-1), (g["result"] != 0).any(-1)), "zero pattern"
+    ((result * cot_out.to(DEV)).sum() + (hidden * cot_hid.to(DEV)).sum()).backward()
+    for k, p in rnn.named_parameters():
+        assert_close(p.grad, g["grad:" + k], TOL, k)
+
+
+def test_improved_rnn_accepts_gpu_lengths_and_total_length():
+    import umpr_b200
+    torch.manual_seed(0)
+    rnn = umpr_b200.ImprovedRnn(torch.nn.GRU, input_size=50, hidden_size=64, batch_first=True, bidirectional=True).to(DEV)
+    data = torch.randn(37, 11, 50)
+    lens = torch.randint(1, 6, (37,))                    # longest sequence (5) < padded length (11)
+    out, hid = rnn(data.to(DEV), lens.to(DEV))
+    w = orc.gru_weights({k: v.detach().cpu() for k, v in rnn.state_dict().items()}, "module")
+    ref, hid_ref = orc.improved_rnn(data, lens, w)
+    assert out.shape == (37, 11, 128)
+    assert_close(out, ref, TOL, "out")
+    assert_close(hid, hid_ref, TOL, "hidden")
+    assert float(out[:, 5:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_umpr_vs_reference(name):
+    c = cases.CASES[name]
+    g = load_golden(name)
+    m, _ = _model(c)
+    batch = cases.make_batch(c)
+    m.train()
+    taps = {}
+    m.review_net.r_net.register_forward_hook(lambda mod, i, o: taps.__setitem__("rnet", o))
+    m.review_net.register_forward_hook(lambda mod, i, o: taps.__setitem__("represent", o))
+    if not c["review_net_only"]:
+        m.control_net.register_forward_hook(lambda mod, i, o: taps.__setitem__("control", o))
+        m.visual_net.register_forward_hook(lambda mod, i, o: taps.__setitem__("visual", o))
+    pred, loss = m(*batch)
+    loss = loss.mean()                                    # main.py:34
+    m.zero_grad()
+    loss.backward()
+    for i, nm in enumerate(["gru_u", "gru_i", "soft_u", "soft_i", "atte_u", "atte_i"]):
+        assert_close(taps["rnet"][i], g["rnet:" + nm], TOL, nm)
+    assert np.array_equal((taps["rnet"][0].detach().cpu().numpy() != 0), (g["rnet:gru_u"] != 0)), "gru_u zero pattern"
+    assert_close(taps["represent"], g["represent"], TOL, "represent")
+    if not c["review_net_only"]:
+        for i, nm in enumerate(["c_u", "c_i", "prefer_pos", "prefer_neg"]):
+            assert_close(taps["control"][i], g["control:" + nm], TOL, nm)
+        for i, nm in enumerate(["pos_match", "neg_match", "final_pos", "final_neg"]):
+            assert_close(taps["visual"][i], g["visual:" + nm], TOL, nm)
+    assert_close(pred, g["pred"], TOL, "pred")
+    assert_close(loss, g["loss"], TOL, "loss")
+    for k, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        ref = g["grad:" + k]
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        if np.abs(ref).max() < 1e-7:
+            assert float(got.abs().max()) < 1e-6, k
+        else:
+            assert_close(got, ref, TOL, "grad " + k)
+    m.eval()
+    with torch.no_grad():
+        pe, _ = m(*batch)
+    assert_close(pe, g["eval_pred"], TOL, "eval_pred")
+
+
+@pytest.mark.parametrize("workload,B", [("music_small_r", 16), ("music_full", 12), ("yelp_full", 9)])
+def test_umpr_vs_oracle_amazon_shape(workload, B):
+    """configs[0..2] shapes (S=20, L=20, GloVe-50d; V=1 or 4) at a batch the oracle finishes in seconds."""
+    from umpr_b200 import synthetic as syn
+    table = syn.make_table(5000, seed=2)
+    batch = syn.make_batch(workload, B, vocab=5000, seed=7)
+    m = syn.build_model(workload, table, seed=1, device=DEV)
+    with torch.no_grad():
+        m.review_net.r_net.M.mul_(0.05)                  # un-saturate tanh so grad(M) is measurable
+    m.train()
+    pred, loss = m(*batch)
+    loss.backward()
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    rno = syn.WORKLOADS[workload]["review_net_only"]
+    p_ref, l_ref, g_ref = orc.umpr_loss_and_grads(params, batch, review_net_only=rno, impl="explicit")
+    assert_close(pred, p_ref, TOL, "pred")
+    assert_close(loss, l_ref, TOL, "loss")
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            got = p.grad if p.grad is not None else torch.zeros_like(p)
+            if float(g_ref[k].abs().max()) < 1e-7:
+                assert float(got.abs().max()) < 1e-6, k
+            else:
+                assert_close(got, g_ref[k], TOL, "grad " + k)
+
+
+def test_module_level_api_rnet_snet_cnet():
+    """RNet / SNet / CNet called the way pretrain_rnet.py:165 and model.py:162,182 call them (dense embeddings in)."""
+    import umpr_b200
+    torch.manual_seed(3)
+    B, S, L = 7, 3, 9
+    emb_u, emb_i = torch.randn(B, S, L, 50) * 0.5, torch.randn(B, S, L, 50) * 0.5
+    lu, li = torch.randint(1, L + 1, (B, S)), torch.randint(1, L + 1, (B, S))
+    rnet = umpr_b200.RNet(50, 64).to(DEV)
+    with torch.no_grad():
+        rnet.M.mul_(0.05)
+    out = rnet(emb_u.to(DEV), emb_i.to(DEV), lu, li)
+    p = {"review_net.r_net." + k: v.detach().cpu() for k, v in rnet.state_dict().items()}
+    ref = orc.r_net(emb_u, emb_i, lu, li, p)
+    for a, b, nm in zip(out, ref, ["gru_u", "gru_i", "soft_u", "soft_i", "atte_u", "atte_i"]):
+        assert_close(a, b, TOL, nm)
+    snet = umpr_b200.SNet(64, 128).to(DEV)
+    sa, se = snet(out[0], out[2], L)
+    sa_ref, se_ref = orc.s_net(ref[0], ref[2], L, snet.Ms.detach().cpu(), snet.Ws.detach().cpu())
+    assert_close(sa, sa_ref, TOL, "self_atte")
+    assert_close(se, se_ref, TOL, "sentiment")
+    cnet = umpr_b200.CNet(50, 64, 120, 3, 4, 0.35).to(DEV)
+    g, vp, fr = cnet(emb_u.to(DEV), lu)
+    pc = {"control_net.c_net." + k: v.detach().cpu() for k, v in cnet.state_dict().items()}
+    g_ref, vp_ref, fr_ref = orc.c_net(emb_u, lu, pc, 0.35)
+    assert_close(g, g_ref, TOL, "cnet gru")
+    assert_close(vp, vp_ref, TOL, "view_p")
+    assert_close(fr, fr_ref, TOL, "final_repr")
+
+
+def test_shard_lengths_use_global_total_length():
+    """A data-parallel shard whose own longest sentence is shorter than L must still return (.., L, ..) (readme.md:154-160)."""
+    from umpr_b200 import synthetic as syn
+    table = syn.make_table(3000, seed=4)
+    user, item, ui, ul, il, uil, photos, labels = syn.make_batch("music_small_r", 8, vocab=3000, seed=5)
+    ul = ul.clamp(max=7)
+    il = il.clamp(max=7)
+    user = user * (torch.arange(20)[None, None] < ul[..., None])
+    item = item * (torch.arange(20)[None, None] < il[..., None])
+    m = syn.build_model("music_small_r", table, seed=2, device=DEV)
+    m.eval()
+    with torch.no_grad():
+        out = m.review_net.r_net(umpr_b200_packed(m, user, ul), umpr_b200_packed(m, item, il), ul, il)
+        pred, loss = m(user, item, ui, ul, il, uil, photos, labels)
+    assert out[0].shape == (8, 400, 128)
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    p_ref, l_ref = orc.umpr_forward(params, (user, item, ui, ul, il, uil, photos, labels), review_net_only=True)
+    assert_close(pred, p_ref, TOL, "pred")
+
+
+def umpr_b200_packed(m, ids, lens):
+    from umpr_b200 import PackedReviews
+    return PackedReviews(lens, ids=ids.to(DEV), table=m.embedding.weight)
+
+
+def test_error_behaviour():
+    import umpr_b200
+    rnn = umpr_b200.ImprovedRnn(torch.nn.GRU, input_size=50, hidden_size=64, batch_first=True, bidirectional=True).to(DEV)
+    with pytest.raises(RuntimeError, match="greater than 0"):
+        rnn(torch.randn(3, 4, 50, device=DEV), torch.tensor([2, 0, 1]))
+    from umpr_b200 import synthetic as syn
+    m = syn.build_model("music_small_r", syn.make_table(100), device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(*syn.make_batch("music_small_r", 2, vocab=100))

@@ -1,0 +1,68 @@
+"""Host-side length bookkeeping (umpr_b200/plan.py) against the oracle and the reference's golden permutations."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import load_golden
+from oracle import umpr_oracle as orc
+from umpr_b200.plan import PackPlan, choose_tile_rows
+
+
+@pytest.mark.parametrize("name", list(cases.RNN_CASES))
+@pytest.mark.parametrize("R", [32, 64, 128])
+def test_plan_matches_reference_packing(name, R):
+    g = load_golden(name)
+    data, lens, *_ = cases.make_rnn_case(cases.RNN_CASES[name])
+    p = PackPlan(lens, data.shape[1], "cpu", tile_rows=R)
+    assert np.array_equal(p.sorted_indices.numpy(), g["sorted_indices"])          # bit-exact packing order
+    assert np.array_equal(p.unsorted_indices.numpy(), g["unsorted_indices"])
+    # batch_sizes of the reference PackedSequence == number of jobs alive at each step
+    bs = [(p.sorted_lengths > t).sum().item() for t in range(int(p.sorted_lengths[0]))]
+    assert bs == g["batch_sizes"].tolist()
+    N, Rp = p.N, p.n_tiles * R
+    h = p.host.to(torch.int64)
+    seq_of, row_of, len_of = h[:Rp], h[Rp:2 * Rp], h[2 * Rp:3 * Rp]
+    tile_off = h[3 * Rp:3 * Rp + p.n_tiles + 1]
+    slab_tile = h[3 * Rp + p.n_tiles + 1:]
+    assert slab_tile.numel() == p.n_slabs == int(tile_off[-1])
+    # every output row is produced exactly once, from the sequence the reference's double un-sort selects
+    assert sorted(row_of[:N].tolist()) == list(range(N))
+    assert torch.equal(p.unsorted_indices[row_of[:N]], seq_of[:N])                # result[n] = Y[unsorted[n]]
+    assert torch.equal(len_of[:N], lens[seq_of[:N]])
+    assert (len_of[N:] == 0).all() and (row_of[N:] == -1).all()
+    assert (len_of[:-1] >= len_of[1:]).all()                                      # descending → tiles early-exit
+    for j in range(p.n_tiles):
+        assert tile_off[j + 1] - tile_off[j] == len_of[j * R]
+        assert (slab_tile[tile_off[j]:tile_off[j + 1]] == j).all()
+    # zero pattern of the result: row n non-zero exactly for t < len[unsorted[n]]
+    eff = p.row_lengths()
+    assert np.array_equal((np.abs(g["result"]).sum(-1) > 0), (torch.arange(data.shape[1])[None] < eff[:, None]).numpy())
+
+
+def test_plan_rejects_bad_lengths():
+    with pytest.raises(RuntimeError, match="greater than 0"):
+        PackPlan(torch.tensor([3, 0, 2]), 5, "cpu", tile_rows=32)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        PackPlan(torch.tensor([3, 9, 2]), 5, "cpu", tile_rows=32)
+
+
+def test_total_length_is_the_padded_dim_not_the_shard_max():
+    # readme.md:154-160: a DataParallel shard whose longest sentence is shorter than the padded tensor
+    lens = torch.tensor([2, 1, 3, 1])
+    p = PackPlan(lens, 20, "cpu", tile_rows=32)
+    assert p.L == 20 and p.n_slabs == 3
+
+
+def test_sort_is_the_reference_call():
+    g = load_golden("sort_order")
+    for n in (64, 1280, 5000):
+        p = PackPlan(torch.tensor(g[f"len{n}"]), 20, "cpu", tile_rows=128)
+        assert np.array_equal(p.sorted_indices.numpy(), g[f"idx{n}"])
+        assert torch.equal(p.sorted_indices, orc.sort_plan(torch.tensor(g[f"len{n}"]))[1])
+
+
+def test_tile_rows_heuristic():
+    assert choose_tile_rows(1280, 148) == 32
+    assert choose_tile_rows(20480, 148) == 128
+    assert choose_tile_rows(5000, 148) == 64

@@ -1,0 +1,119 @@
+"""ctypes binding of the C-ABI in ``include/umpr_b200.h`` (``umpr_b200/libumpr_b200.so``).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libumpr_b200.so")
+
+P, I, L, F = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+# name -> argtypes; mirrors include/umpr_b200.h line by line (tests/test_abi.py checks both against the header)
+SIGNATURES = {
+    "umpr_version": [],
+    "umpr_sm_count": [I, P],
+    "umpr_gather_pack": [P, P, P, P, I, I, I, I, I, P, P],
+    "umpr_gru_inproj": [P, P, I, I, I, P, P],
+    "umpr_gru_recurrence_fwd": [P, P, P, I, I, I, I, I, P, P, P, P],
+    "umpr_gru_recurrence_bwd": [P, P, P, P, P, P, I, I, I, I, I, P, P],
+    "umpr_gru_wgrad": [P, P, P, P, I, I, I, I, I, P, I, P],
+    "umpr_sgemm": [P, L, L, P, L, L, P, L, I, I, I, I, I, P, I, P],
+    "umpr_coattn_fwd": [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
+    "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P],
+    "umpr_snet_fwd": [P, P, P, I, I, P, P, P, I, P],
+    "umpr_snet_sentiment_fwd": [P, P, I, I, I, P, P, P],
+    "umpr_snet_sentiment_bwd": [P, P, P, P, I, I, P, P, P],
+    "umpr_snet_bwd": [P, P, P, P, P, P, I, I, P, P, P, I, P],
+    "umpr_cnet_prep": [P, I, I, P, P],
+    "umpr_cnet_conv_fwd": [P, P, P, I, I, I, P, P, I, P],
+    "umpr_cnet_head_fwd": [P, P, P, F, I, I, I, I, P, P, P],
+    "umpr_cnet_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
+    "umpr_cnet_conv_bwd": [P, P, P, P, I, I, I, P, P, I, P],
+    "umpr_control_tail_fwd": [P, P, P, P, P, F, I, I, I, P, P, P, P, P],
+    "umpr_control_tail_bwd": [P, P, P, P, P, P, P, P, F, I, I, I, P, P, P, P, P, P],
+    "umpr_visual_fwd": [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
+    "umpr_visual_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P, P],
+    "umpr_fusion_fwd": [P, P, P, P, P, I, I, P, P],
+    "umpr_fusion_bwd": [P, P, P, P, P, P, I, I, P, P, P, P, P, P],
+    "umpr_loss_fwd": [P, P, P, P, P, P, I, I, F, P, P],
+    "umpr_loss_bwd": [P, P, P, P, P, P, P, I, I, F, P, P, P, P, P, P],
+    "umpr_tanh_bwd": [P, P, L, P, P],
+    "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"umpr_b200: CUDA library not built ({LIB_PATH} missing). Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C umpr_b200/csrc`. "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = I
+    lib.umpr_last_error.argtypes = []
+    lib.umpr_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().umpr_last_error().decode("utf-8", "replace")
+
+
+def ptr(t):
+    """Device pointer of a contiguous tensor, or NULL for None."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "umpr_b200: non-contiguous tensor handed to the C-ABI"
+    return t.data_ptr()
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t)
+    return arr
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on the current CUDA stream (appended as the last argument)."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    if rc != 0:
+        kind = "argument error" if rc < 0 else f"CUDA error {rc}"
+        raise RuntimeError(f"{name}: {kind}: {last_error()}")
+
+
+_SM = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _SM:
+        out = C.c_int(0)
+        rc = load().umpr_sm_count(idx, C.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"umpr_sm_count: {last_error()}")
+        _SM[idx] = out.value
+    return _SM[idx]

@@ -1,0 +1,333 @@
+// C-Net tail (reference src/model.py:118-125): Conv1d(128 -> K, k=3, pad=1) + ReLU + max over L, then
+// Linear(K -> V) + Sigmoid, threshold, sum of squares over sentences.  Forward and backward.
+// The convolution runs over ALL L positions (padding positions see zeros and produce relu(bias), which competes
+// in the max exactly as in the reference); it is computed as an implicit GEMM (K' = 3*128) fused with the max-pool,
+// so the (N, K, L) activation never reaches HBM.  The backward is sparse: one arg-max position per (sentence, filter).
+#include "common.cuh"
+#include "../../include/umpr_b200.h"
+
+namespace umpr {
+
+constexpr int CK = 3;              // kernel_size (config.py:37)
+constexpr int CKP = 128;           // filters padded to 128 columns
+constexpr int CX_LD = D + 4;       // 132
+constexpr int CROWS = 128;         // MAC tile rows (sentences incl. one zero guard row before and after each)
+constexpr int CCH = 32;            // k' chunk streamed through shared memory
+
+// wt[(dt*128 + c)][kf] = W[kf][c][dt]  (kf >= KC -> 0)
+__global__ void cnet_prep_kernel(const float* __restrict__ w, int KC, float* __restrict__ wt) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= CK * D * CKP) return;
+  const int kf = idx & (CKP - 1), kp = idx >> 7;
+  const int dt = kp >> 7, c = kp & 127;
+  wt[idx] = kf < KC ? w[((size_t)kf * D + c) * CK + dt] : 0.f;
+}
+
+__global__ void __launch_bounds__(256, 1) cnet_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                               const float* __restrict__ bias, int N, int L, int KC, int gs,
+                                                               float* __restrict__ cfeat, int* __restrict__ cidx) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                          // [(CROWS + 2)][132]; tile row r lives at xs row r + 1
+  float* ys = xs + (CROWS + 2) * CX_LD;      // [CROWS][132]  relu(conv)
+  float* wc = ys + CROWS * CX_LD;            // [2][CCH][128] weight chunks
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int Lg = L + 2;
+  const int n_groups = (N + gs - 1) / gs;
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+    const int n0 = grp * gs;
+    const int ns = min(gs, N - n0);
+    __syncthreads();
+    // x rows with zero guards
+    for (int idx = tid; idx < (CROWS + 2) * (D / 4); idx += 256) {
+      const int rr = idx >> 5, c4 = idx & 31;          // rr: xs row
+      const int r = rr - 1;                            // tile row
+      const int s = r >= 0 ? r / Lg : -1;
+      const int l = r >= 0 ? r - s * Lg - 1 : -1;      // position inside the sentence, -1 / L are guards
+      if (s >= 0 && s < ns && l >= 0 && l < L)
+        cp_async16(&xs[rr * CX_LD + c4 * 4], x + ((size_t)(n0 + s) * L + l) * D + c4 * 4);
+      else
+        *reinterpret_cast<float4*>(&xs[rr * CX_LD + c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    auto load_w = [&](int ch) {
+      const float4* src = reinterpret_cast<const float4*>(wt + (size_t)ch * CCH * CKP);
+      float* dst = wc + (ch & 1) * CCH * CKP;
+      for (int idx = tid; idx < CCH * CKP / 4; idx += 256) cp_async16(dst + idx * 4, src + idx);
+      cp_async_commit();
+    };
+    load_w(0);
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+    constexpr int NCH = CK * D / CCH;   // 12
+    for (int ch = 0; ch < NCH; ++ch) {
+      cp_async_wait_all();
+      __syncthreads();                  // chunk ch (and, first time, xs) visible; chunk ch-1 fully consumed
+      if (ch + 1 < NCH) load_w(ch + 1);
+      const float* wcur = wc + (ch & 1) * CCH * CKP;
+      const int dt = ch >> 2, c0 = (ch & 3) * CCH;
+#pragma unroll 2
+      for (int k4 = 0; k4 < CCH / 4; ++k4) {
+        float4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)   // tile row r needs x row (r - 1 + dt) -> xs row (r + dt)
+          a[i] = *reinterpret_cast<const float4*>(&xs[(ty * 8 + i + dt) * CX_LD + c0 + k4 * 4]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float4 b0 = *reinterpret_cast<const float4*>(&wcur[(k4 * 4 + kk) * CKP + tx * 4]);
+          const float4 b1 = *reinterpret_cast<const float4*>(&wcur[(k4 * 4 + kk) * CKP + 64 + tx * 4]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+            acc[i][0] += av * b0.x; acc[i][1] += av * b0.y; acc[i][2] += av * b0.z; acc[i][3] += av * b0.w;
+            acc[i][4] += av * b1.x; acc[i][5] += av * b1.y; acc[i][6] += av * b1.z; acc[i][7] += av * b1.w;
+          }
+        }
+      }
+    }
+    float bv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int kf = c < 4 ? tx * 4 + c : 64 + tx * 4 + c - 4;
+      bv[c] = kf < KC ? bias[kf] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float* o = &ys[(ty * 8 + i) * CX_LD];
+      *reinterpret_cast<float4*>(o + tx * 4) = make_float4(fmaxf(acc[i][0] + bv[0], 0.f), fmaxf(acc[i][1] + bv[1], 0.f),
+                                                           fmaxf(acc[i][2] + bv[2], 0.f), fmaxf(acc[i][3] + bv[3], 0.f));
+      *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(fmaxf(acc[i][4] + bv[4], 0.f), fmaxf(acc[i][5] + bv[5], 0.f),
+                                                                fmaxf(acc[i][6] + bv[6], 0.f), fmaxf(acc[i][7] + bv[7], 0.f));
+    }
+    __syncthreads();
+    // max over the L positions of each sentence (model.py:120); first maximum wins, <= 0 carries no gradient
+    for (int idx = tid; idx < ns * KC; idx += 256) {
+      const int s = idx / KC, kf = idx - s * KC;
+      float best = -1.f;
+      int arg = -1;
+      for (int l = 0; l < L; ++l) {
+        const float v = ys[(s * Lg + 1 + l) * CX_LD + kf];
+        if (v > best) { best = v; arg = l; }
+      }
+      cfeat[(size_t)(n0 + s) * KC + kf] = best;
+      cidx[(size_t)(n0 + s) * KC + kf] = best > 0.f ? arg : -1;
+    }
+  }
+}
+
+// view_p = where(sigmoid(Wc cfeat + bc) < thr, 0, .) (model.py:123-124);  final = sum_s view_p^2 (model.py:125)
+__global__ void __launch_bounds__(128) cnet_head_fwd_kernel(const float* __restrict__ cfeat, const float* __restrict__ lw,
+                                                            const float* __restrict__ lb, float thr, int S_, int V, int KC,
+                                                            float* __restrict__ view_p, float* __restrict__ final_) {
+  extern __shared__ float ps[];   // [S_*V]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int pr = warp; pr < S_ * V; pr += 4) {
+    const int s = pr / V, v = pr - s * V;
+    const float* f = cfeat + ((size_t)b * S_ + s) * KC;
+    float a = 0.f;
+    for (int k = lane; k < KC; k += 32) a += f[k] * lw[v * KC + k];
+    a = warp_sum(a);
+    if (lane == 0) {
+      float p = sigmoidf_acc(a + lb[v]);
+      if (p < thr) p = 0.f;
+      ps[pr] = p;
+      view_p[(size_t)b * S_ * V + pr] = p;
+    }
+  }
+  __syncthreads();
+  if (tid < V) {
+    float a = 0.f;
+    for (int s = 0; s < S_; ++s) { const float p = ps[s * V + tid]; a += p * p; }
+    final_[(size_t)b * V + tid] = a;
+  }
+}
+
+__global__ void __launch_bounds__(128) cnet_head_bwd_kernel(const float* __restrict__ cfeat, const int* __restrict__ cidx,
+                                                            const float* __restrict__ view_p, const float* __restrict__ lw,
+                                                            const float* __restrict__ d_view_p, const float* __restrict__ d_final,
+                                                            int S_, int V, int KC, float* __restrict__ dcfeat,
+                                                            float* __restrict__ d_lw, float* __restrict__ d_lb,
+                                                            float* __restrict__ d_cb) {
+  extern __shared__ float sm[];   // dpre [S_*V]
+  float* dpre = sm;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int pr = tid; pr < S_ * V; pr += 128) {
+    const int v = pr % V;
+    const float p = view_p[(size_t)b * S_ * V + pr];
+    float dp = d_view_p ? d_view_p[(size_t)b * S_ * V + pr] : 0.f;
+    if (d_final) dp += 2.f * p * d_final[(size_t)b * V + v];
+    dpre[pr] = p > 0.f ? dp * p * (1.f - p) : 0.f;
+  }
+  __syncthreads();
+  if (tid < KC) {
+    float dcb = 0.f;
+    for (int s = 0; s < S_; ++s) {
+      const size_t n = (size_t)b * S_ + s;
+      float a = 0.f;
+      for (int v = 0; v < V; ++v) a += dpre[s * V + v] * lw[v * KC + tid];
+      if (cidx[n * KC + tid] < 0) a = 0.f;     // ReLU clipped the maximum: no gradient reaches the conv
+      dcfeat[n * KC + tid] = a;
+      dcb += a;
+    }
+    atomicAdd(&d_cb[tid], dcb);
+    for (int v = 0; v < V; ++v) {
+      float a = 0.f;
+      for (int s = 0; s < S_; ++s) a += dpre[s * V + v] * cfeat[((size_t)b * S_ + s) * KC + tid];
+      atomicAdd(&d_lw[v * KC + tid], a);
+    }
+  }
+  if (tid < V) {
+    float a = 0.f;
+    for (int s = 0; s < S_; ++s) a += dpre[s * V + tid];
+    atomicAdd(&d_lb[tid], a);
+  }
+}
+
+// dx[n][l][c] = sum_{kf, dt : arg[kf] + dt - 1 == l} g[kf] W[kf][c][dt].   Thread (q, c) keeps its 32x3 weights in registers.
+__global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dx_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
+                                                                  const float* __restrict__ w, int N, int L, int KC,
+                                                                  float* __restrict__ dx) {
+  extern __shared__ __align__(16) float smem[];
+  float* dxs = smem;                       // [(L+2)][128]
+  float* gsm = dxs + (L + 2) * D;          // [128]
+  int* tsm = reinterpret_cast<int*>(gsm + CKP);
+  const int tid = threadIdx.x, q = tid >> 7, c = tid & 127;
+  float wr[32][CK];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int kf = q * 32 + i;
+#pragma unroll
+    for (int dt = 0; dt < CK; ++dt) wr[i][dt] = kf < KC ? w[((size_t)kf * D + c) * CK + dt] : 0.f;
+  }
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    for (int idx = tid; idx < (L + 2) * D; idx += 512) dxs[idx] = 0.f;
+    if (tid < CKP) {
+      gsm[tid] = tid < KC ? dcfeat[(size_t)n * KC + tid] : 0.f;
+      tsm[tid] = tid < KC ? cidx[(size_t)n * KC + tid] : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float g = gsm[q * 32 + i];
+      const int t = tsm[q * 32 + i];
+      if (g != 0.f && t >= 0) {          // warp-uniform
+#pragma unroll
+        for (int dt = 0; dt < CK; ++dt) atomicAdd(&dxs[(t + dt) * D + c], g * wr[i][dt]);   // x position t+dt-1 -> guard row +1
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < L * (D / 4); idx += 512) {
+      const int l = idx >> 5, c4 = idx & 31;
+      *reinterpret_cast<float4*>(dx + ((size_t)n * L + l) * D + c4 * 4) = *reinterpret_cast<const float4*>(&dxs[(l + 1) * D + c4 * 4]);
+    }
+  }
+}
+
+// dW[kf][c][dt] += sum_n g[n][kf] x[n][arg + dt - 1][c].  Thread (q, c) accumulates its 32x3 slice in registers.
+__global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
+                                                                  const int* __restrict__ cidx, int N, int L, int KC,
+                                                                  float* __restrict__ dw) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                        // [(L+2)][128] with zero guard rows
+  float* gsm = xs + (L + 2) * D;
+  int* tsm = reinterpret_cast<int*>(gsm + CKP);
+  const int tid = threadIdx.x, q = tid >> 7, c = tid & 127;
+  float acc[32][CK];
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+#pragma unroll
+    for (int dt = 0; dt < CK; ++dt) acc[i][dt] = 0.f;
+  for (int idx = tid; idx < D; idx += 512) { xs[idx] = 0.f; xs[(L + 1) * D + idx] = 0.f; }
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)n * L * D);
+    for (int idx = tid; idx < L * (D / 4); idx += 512) cp_async16(&xs[D + idx * 4], src + idx);
+    cp_async_commit();
+    if (tid < CKP) {
+      gsm[tid] = tid < KC ? dcfeat[(size_t)n * KC + tid] : 0.f;
+      tsm[tid] = tid < KC ? cidx[(size_t)n * KC + tid] : -1;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float g = gsm[q * 32 + i];
+      const int t = tsm[q * 32 + i];
+      if (g != 0.f && t >= 0) {
+#pragma unroll
+        for (int dt = 0; dt < CK; ++dt) acc[i][dt] += g * xs[(t + dt) * D + c];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int kf = q * 32 + i;
+    if (kf < KC) {
+#pragma unroll
+      for (int dt = 0; dt < CK; ++dt) atomicAdd(&dw[((size_t)kf * D + c) * CK + dt], acc[i][dt]);
+    }
+  }
+}
+
+}  // namespace umpr
+
+using namespace umpr;
+
+extern "C" int umpr_cnet_prep(const float* conv_w, int KC, int ksize, float* wt, void* stream) {
+  if (ksize != CK) return fail_arg("cnet: kernel_size=%d (only %d is built)", ksize, CK);
+  if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d must be in [1, %d]", KC, CKP);
+  const int n = CK * D * CKP;
+  cnet_prep_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, wt);
+  return check_launch("cnet_prep");
+}
+
+extern "C" int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int N, int L, int KC, float* cfeat,
+                                  int32_t* cidx, int n_ctas, void* stream) {
+  if (N <= 0) return 0;
+  if (L < 1 || L + 2 > CROWS) return fail_arg("cnet_conv_fwd: sentence length L=%d must be in [1, %d]", L, CROWS - 2);
+  if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
+  int gs = CROWS / (L + 2);
+  if (gs > 16) gs = 16;
+  const int n_groups = (N + gs - 1) / gs;
+  const size_t sm = sizeof(float) * ((CROWS + 2) * CX_LD + CROWS * CX_LD + 2 * CCH * CKP);
+  cudaError_t e = cudaFuncSetAttribute(cnet_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (e != cudaSuccess) { set_error("cnet_conv_fwd smem: %s", cudaGetErrorString(e)); return (int)e; }
+  const int grid = n_ctas > 0 && n_ctas < n_groups ? n_ctas : n_groups;
+  cnet_conv_fwd_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(x, wt, conv_b, N, L, KC, gs, cfeat, cidx);
+  return check_launch("cnet_conv_fwd");
+}
+
+extern "C" int umpr_cnet_head_fwd(const float* cfeat, const float* lin_w, const float* lin_b, float threshold, int B, int S_, int V,
+                                  int KC, float* view_p, float* final_, void* stream) {
+  if (B <= 0) return 0;
+  if (V < 1 || V > 128) return fail_arg("cnet_head: view_size=%d must be in [1,128]", V);
+  cnet_head_fwd_kernel<<<B, 128, sizeof(float) * S_ * V, (cudaStream_t)stream>>>(cfeat, lin_w, lin_b, threshold, S_, V, KC, view_p, final_);
+  return check_launch("cnet_head_fwd");
+}
+
+extern "C" int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* view_p, const float* lin_w,
+                                  const float* d_view_p, const float* d_final, int B, int S_, int V, int KC, float* dcfeat,
+                                  float* d_lin_w, float* d_lin_b, float* d_conv_b, void* stream) {
+  if (B <= 0) return 0;
+  if (V < 1 || V > 128 || KC > 128) return fail_arg("cnet_head_bwd: V=%d KC=%d", V, KC);
+  cnet_head_bwd_kernel<<<B, 128, sizeof(float) * S_ * V, (cudaStream_t)stream>>>(cfeat, cidx, view_p, lin_w, d_view_p, d_final, S_, V,
+                                                                               KC, dcfeat, d_lin_w, d_lin_b, d_conv_b);
+  return check_launch("cnet_head_bwd");
+}
+
+extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L,
+                                  int KC, float* dx, float* d_conv_w, int n_ctas, void* stream) {
+  if (N <= 0) return 0;
+  if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
+  const size_t sm = sizeof(float) * ((L + 2) * D + CKP) + sizeof(int) * CKP;
+  if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd: L=%d too large", L);
+  cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaFuncSetAttribute(cnet_conv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  const int grid = n_ctas > 0 && n_ctas < N ? n_ctas : N;
+  cnet_conv_bwd_dx_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
+  if (int e = check_launch("cnet_conv_bwd_dx")) return e;
+  cnet_conv_bwd_dw_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(x, dcfeat, cidx, N, L, KC, d_conv_w);
+  return check_launch("cnet_conv_bwd_dw");
+}

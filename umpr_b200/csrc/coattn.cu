@@ -1,0 +1,282 @@
+// R-Net co-attention (reference src/model.py:50-55), flash-style: the (P x P) affinity matrix
+// A = tanh(gi · M · gu^T) is never written to HBM.  tanh is monotone, so the row/column maxima are taken on
+// the pre-activation and tanh is applied to 2P numbers per sample instead of P^2.
+//   kernel 1: per (sample, 128-row tile of giM): all column tiles of gu -> packed (max, argmax) per row / column
+//   kernel 2: per (sample, side): tanh, softmax over all P (unmasked, model.py:52-53), pooling atte = g^T soft
+//   kernel 3: backward; dA is non-zero at <= 2P arg-max entries per sample, so it is a gather + scatter-add
+#include "common.cuh"
+#include "../../include/umpr_b200.h"
+
+namespace umpr {
+
+constexpr int CT = 128;          // tile edge
+constexpr int CLD = CT + 4;      // 132
+
+// load a [rows<=128][128] row-major tile (k contiguous) into k-major shared memory T[k][row]; rows >= nvalid are zero
+__device__ __forceinline__ void load_tile_kmajor(float* T, const float* __restrict__ src, int nvalid, int tid) {
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int e = tid + i * 256;
+    const int k4lo = e & 3, m = (e >> 2) & 127, k4 = (e >> 9) * 4 + k4lo;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < nvalid) v = *reinterpret_cast<const float4*>(src + (size_t)m * D + k4 * 4);
+    T[(k4 * 4 + 0) * CLD + m] = v.x; T[(k4 * 4 + 1) * CLD + m] = v.y;
+    T[(k4 * 4 + 2) * CLD + m] = v.z; T[(k4 * 4 + 3) * CLD + m] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) coattn_affinity_kernel(const float* __restrict__ giM, const float* __restrict__ gu, int P,
+                                                                 unsigned long long* __restrict__ rowkey,
+                                                                 unsigned long long* __restrict__ colkey) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                 // [128 k][132]  giM tile
+  float* Bs = smem + D * CLD;       // [128 k][132]  gu tile
+  unsigned long long* cred = reinterpret_cast<unsigned long long*>(Bs + D * CLD);   // [8 warps][128]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i0 = blockIdx.x * CT;
+  const int ni = min(CT, P - i0);
+  load_tile_kmajor(As, giM + ((size_t)b * P + i0) * D, ni, tid);
+  float rmax[8];
+  int rarg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { rmax[i] = -INFINITY; rarg[i] = 0; }
+
+  for (int j0 = 0; j0 < P; j0 += CT) {
+    const int nj = min(CT, P - j0);
+    __syncthreads();                       // previous tile's Bs/cred fully consumed
+    load_tile_kmajor(Bs, gu + ((size_t)b * P + j0) * D, nj, tid);
+    __syncthreads();
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k * CLD + ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k * CLD + 64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k * CLD + tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k * CLD + 64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += a[i] * bb[j];
+    }
+    // row maxima (over gu positions j) accumulate in registers across column tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int jj = (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+        if (jj < nj && acc[i][j] > rmax[i]) { rmax[i] = acc[i][j]; rarg[i] = j0 + jj; }
+      }
+    // column maxima (over giM rows i) for this tile: thread -> half-warp pair -> warps -> global atomicMax
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      unsigned long long key = 0ull;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ii = (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (ii < ni) {
+          const unsigned long long k2 = ((unsigned long long)f2ord(acc[i][j]) << 32) | (unsigned)(i0 + ii);
+          key = k2 > key ? k2 : key;
+        }
+      }
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, 16);
+      key = o > key ? o : key;
+      if (lane < 16) cred[warp * CT + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4)] = key;
+    }
+    __syncthreads();
+    if (tid < nj) {
+      unsigned long long key = cred[tid];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) { const unsigned long long o = cred[w * CT + tid]; key = o > key ? o : key; }
+      atomicMax(&colkey[(size_t)b * P + j0 + tid], key);
+    }
+  }
+  // finish the row maxima across the 16 threads that share a row group
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    unsigned long long key = ((unsigned long long)f2ord(rmax[i]) << 32) | (unsigned)rarg[i];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other > key ? other : key;
+    }
+    const int ii = (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (tx == 0 && ii < ni) rowkey[(size_t)b * P + i0 + ii] = key;
+  }
+}
+
+// soft = softmax_P(tanh(max)), atte = sum_p soft[p] g[p]  (model.py:52-55)
+__global__ void __launch_bounds__(256) coattn_pool_kernel(const unsigned long long* __restrict__ colkey,
+                                                          const unsigned long long* __restrict__ rowkey,
+                                                          const float* __restrict__ gu, const float* __restrict__ gi, int P,
+                                                          float* __restrict__ soft_u, float* __restrict__ soft_i,
+                                                          float* __restrict__ t_u, float* __restrict__ t_i,
+                                                          int* __restrict__ arg_u, int* __restrict__ arg_i,
+                                                          float* __restrict__ atte_u, float* __restrict__ atte_i) {
+  extern __shared__ __align__(16) float smem[];
+  const int P4 = (P + 3) & ~3;
+  float* sp = smem;              // [P4]
+  float* red = smem + P4;        // [32]
+  float4* part = reinterpret_cast<float4*>(smem + P4 + 32);  // [8][32]
+  const int b = blockIdx.x, side = blockIdx.y, tid = threadIdx.x;
+  const unsigned long long* key = (side ? rowkey : colkey) + (size_t)b * P;
+  const float* g = (side ? gi : gu) + (size_t)b * P * D;
+  float* soft = (side ? soft_i : soft_u) + (size_t)b * P;
+  float* tv = (side ? t_i : t_u) + (size_t)b * P;
+  int* arg = (side ? arg_i : arg_u) + (size_t)b * P;
+  float mx = -INFINITY;
+  for (int p = tid; p < P; p += 256) {
+    const unsigned long long k = key[p];
+    const float t = tanhf(ord2f((unsigned)(k >> 32)));
+    sp[p] = t; tv[p] = t; arg[p] = (int)(unsigned)(k & 0xffffffffull);
+    mx = fmaxf(mx, t);
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int p = tid; p < P; p += 256) { const float e = expf(sp[p] - mx); sp[p] = e; sum += e; }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int p = tid; p < P; p += 256) { const float s = sp[p] * inv; sp[p] = s; soft[p] = s; }
+  __syncthreads();
+  const int c4 = tid & 31, pg = tid >> 5;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = pg; p < P; p += 8) {
+    const float s = sp[p];
+    const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + c4 * 4);
+    a.x += s * v.x; a.y += s * v.y; a.z += s * v.z; a.w += s * v.w;
+  }
+  part[pg * 32 + c4] = a;
+  __syncthreads();
+  if (tid < 32) {
+    float4 r = part[tid];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) { const float4 v = part[q * 32 + tid]; r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w; }
+    *reinterpret_cast<float4*>((side ? atte_i : atte_u) + (size_t)b * D + tid * 4) = r;
+  }
+}
+
+// backward of model.py:50-55 with respect to gu, gi (through giM = gi·M; the M products are GEMMs outside)
+__global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict__ gu, const float* __restrict__ gi,
+                                                         const float* __restrict__ giM, const float* __restrict__ soft_u,
+                                                         const float* __restrict__ soft_i, const float* __restrict__ t_u,
+                                                         const float* __restrict__ t_i, const int* __restrict__ arg_u,
+                                                         const int* __restrict__ arg_i, const float* __restrict__ d_soft_u,
+                                                         const float* __restrict__ d_soft_i, const float* __restrict__ d_atte_u,
+                                                         const float* __restrict__ d_atte_i, int P, float* __restrict__ dgu,
+                                                         float* __restrict__ dgi, float* __restrict__ dgiM) {
+  extern __shared__ __align__(16) float smem[];
+  const int P4 = (P + 3) & ~3;
+  float* wu = smem;            // [P4] d(pre-activation col max)  -> entries (arg_u[j], j)
+  float* vi = smem + P4;       // [P4] d(pre-activation row max)  -> entries (i, arg_i[i])
+  float* dau = smem + 2 * P4;  // [128]
+  float* dai = dau + D;        // [128]
+  float* red = dai + D;        // [32]
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t bp = (size_t)b * P;
+  if (tid < D) {
+    dau[tid] = d_atte_u ? d_atte_u[(size_t)b * D + tid] : 0.f;
+    dai[tid] = d_atte_i ? d_atte_i[(size_t)b * D + tid] : 0.f;
+  }
+  __syncthreads();
+  // ds[p] = d_soft[p] + <g[p], d_atte>
+  for (int side = 0; side < 2; ++side) {
+    const float* g = (side ? gi : gu) + bp * D;
+    const float* da = side ? dai : dau;
+    const float* dso = side ? d_soft_i : d_soft_u;
+    float* dst = side ? vi : wu;
+    const float4 d4 = *reinterpret_cast<const float4*>(da + lane * 4);
+    for (int p = warp; p < P; p += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4);
+      float s = v.x * d4.x + v.y * d4.y + v.z * d4.z + v.w * d4.w;
+      s = warp_sum(s);
+      if (lane == 0) dst[p] = s + (dso ? dso[bp + p] : 0.f);
+    }
+  }
+  __syncthreads();
+  // softmax backward, then through tanh
+  for (int side = 0; side < 2; ++side) {
+    const float* so = (side ? soft_i : soft_u) + bp;
+    const float* tv = (side ? t_i : t_u) + bp;
+    float* dst = side ? vi : wu;
+    float dot = 0.f;
+    for (int p = tid; p < P; p += 256) dot += so[p] * dst[p];
+    dot = block_sum(dot, red);
+    for (int p = tid; p < P; p += 256) {
+      const float t = tv[p];
+      dst[p] = so[p] * (dst[p] - dot) * (1.f - t * t);
+    }
+    __syncthreads();
+  }
+  // dense part (every row written exactly once)
+  const float4 dau4 = *reinterpret_cast<const float4*>(dau + lane * 4);
+  const float4 dai4 = *reinterpret_cast<const float4*>(dai + lane * 4);
+  for (int p = warp; p < P; p += 8) {
+    const float su = soft_u[bp + p], w = wu[p];
+    const float4 m = *reinterpret_cast<const float4*>(giM + (bp + arg_u[bp + p]) * D + lane * 4);
+    *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) =
+        make_float4(su * dau4.x + w * m.x, su * dau4.y + w * m.y, su * dau4.z + w * m.z, su * dau4.w + w * m.w);
+    const float si = soft_i[bp + p], v = vi[p];
+    const float4 u = *reinterpret_cast<const float4*>(gu + (bp + arg_i[bp + p]) * D + lane * 4);
+    *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = make_float4(v * u.x, v * u.y, v * u.z, v * u.w);
+    *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(si * dai4.x, si * dai4.y, si * dai4.z, si * dai4.w);
+  }
+  __threadfence();
+  __syncthreads();
+  // scatter part
+  for (int p = warp; p < P; p += 8) {
+    const float w = wu[p];
+    if (w != 0.f) {
+      const float4 u = *reinterpret_cast<const float4*>(gu + (bp + p) * D + lane * 4);
+      float* d = dgiM + (bp + arg_u[bp + p]) * D + lane * 4;
+      atomicAdd(d, w * u.x); atomicAdd(d + 1, w * u.y); atomicAdd(d + 2, w * u.z); atomicAdd(d + 3, w * u.w);
+    }
+    const float v = vi[p];
+    if (v != 0.f) {
+      const float4 m = *reinterpret_cast<const float4*>(giM + (bp + p) * D + lane * 4);
+      float* d = dgu + (bp + arg_i[bp + p]) * D + lane * 4;
+      atomicAdd(d, v * m.x); atomicAdd(d + 1, v * m.y); atomicAdd(d + 2, v * m.z); atomicAdd(d + 3, v * m.w);
+    }
+  }
+}
+
+}  // namespace umpr
+
+using namespace umpr;
+
+extern "C" int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, int P, unsigned long long* rowkey,
+                               unsigned long long* colkey /* zero-initialised */, float* soft_u, float* soft_i, float* t_u,
+                               float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream) {
+  if (B <= 0 || P <= 0) return 0;
+  if (B > 65535) return fail_arg("coattn_fwd: batch %d > 65535", B);
+  const size_t sm1 = sizeof(float) * 2 * D * CLD + sizeof(unsigned long long) * 8 * CT;
+  {
+    cudaError_t e = cudaFuncSetAttribute(coattn_affinity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    if (e != cudaSuccess) { set_error("coattn smem: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  coattn_affinity_kernel<<<dim3((P + CT - 1) / CT, B), 256, sm1, (cudaStream_t)stream>>>(giM, gu, P, rowkey, colkey);
+  if (int e = check_launch("coattn_affinity")) return e;
+  const size_t sm2 = sizeof(float) * (((P + 3) & ~3) + 32) + sizeof(float4) * 8 * 32;
+  if (sm2 > 200 * 1024) return fail_arg("coattn_fwd: P=%d too large", P);
+  if (sm2 > 48 * 1024) cudaFuncSetAttribute(coattn_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+  coattn_pool_kernel<<<dim3(B, 2), 256, sm2, (cudaStream_t)stream>>>(colkey, rowkey, gu, gi, P, soft_u, soft_i, t_u, t_i, arg_u,
+                                                                    arg_i, atte_u, atte_i);
+  return check_launch("coattn_pool");
+}
+
+extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i,
+                               const float* t_u, const float* t_i, const int32_t* arg_u, const int32_t* arg_i,
+                               const float* d_soft_u, const float* d_soft_i, const float* d_atte_u, const float* d_atte_i, int B,
+                               int P, float* dgu, float* dgi, float* dgiM, void* stream) {
+  if (B <= 0 || P <= 0) return 0;
+  const size_t sm = sizeof(float) * (2 * ((P + 3) & ~3) + 2 * D + 32);
+  if (sm > 200 * 1024) return fail_arg("coattn_bwd: P=%d too large", P);
+  if (sm > 48 * 1024) cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  coattn_bwd_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(gu, gi, giM, soft_u, soft_i, t_u, t_i, arg_u, arg_i, d_soft_u, d_soft_i,
+                                                         d_atte_u, d_atte_i, P, dgu, dgi, dgiM);
+  return check_launch("coattn_bwd");
+}

@@ -1,0 +1,457 @@
+"""autograd Functions over the C-ABI kernels.  PyTorch here only owns memory, streams and the autograd tape.
+
+Each Function cites the reference lines (``src/model.py``) whose forward+backward it replaces.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import call, ptr, ptr_array
+from .plan import PackPlan
+
+H, D, ATT, KP, SV = 64, 128, 64, 64, 256
+
+
+def _f32(t):
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+def _chk(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"umpr_b200: {what} must live on a CUDA device (there is no CPU path)")
+    return t
+
+
+def _n_ctas(device, per_sm=1):
+    return _lib.sm_count(device) * per_sm
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# embedding gather + pack   (model.py:262-264 and the pack half of model.py:18)
+# --------------------------------------------------------------------------------------------------------------------
+def gather_pack(plan: PackPlan, *, table=None, ids=None, dense=None):
+    """Packed GRU input ``xp[n_slabs][R][64]``; either ``table[ids]`` (ids: (Nseq, L) int64) or ``dense`` (Nseq, L, E)."""
+    if dense is not None:
+        dense = _f32(_chk(dense, "GRU input"))
+        E = dense.shape[-1]
+        dev = dense.device
+    else:
+        table = _f32(_chk(table, "embedding table"))
+        ids = _chk(ids, "token ids").contiguous()
+        assert ids.dtype == torch.int64
+        E = table.shape[1]
+        dev = table.device
+    xp = torch.empty(plan.n_slabs * plan.R * KP, dtype=torch.float32, device=dev)
+    call("umpr_gather_pack", ptr(table), ptr(ids), ptr(dense), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.R, plan.L, E, ptr(xp))
+    return xp, E
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ImprovedRnn   (model.py:12-21)
+# --------------------------------------------------------------------------------------------------------------------
+class _GruFn(Function):
+    @staticmethod
+    def forward(ctx, plan: PackPlan, xp, E, want_hidden, *w):
+        w = [_f32(t) for t in w]
+        dev = xp.device
+        N, L, R = plan.N, plan.L, plan.R
+        G = torch.empty(plan.n_slabs * 2 * R * 3 * H, dtype=torch.float32, device=dev)
+        wp = ptr_array(w)
+        call("umpr_gru_inproj", ptr(xp), wp, plan.n_slabs, R, E, ptr(G))
+        out = torch.empty(N, L, D, dtype=torch.float32, device=dev)
+        hn = torch.empty(2, N, H, dtype=torch.float32, device=dev) if want_hidden else None
+        need_grad = any(ctx.needs_input_grad[4:])
+        sv = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev) if need_grad else None
+        call("umpr_gru_recurrence_fwd", ptr(G), wp, ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, N, L, ptr(out), ptr(hn), ptr(sv))
+        del G
+        ctx.plan, ctx.E = plan, E
+        ctx.save_for_backward(xp, out, sv, *w)
+        if hn is None:
+            hn = out.new_zeros(0)
+            ctx.mark_non_differentiable(hn)
+        return out, hn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_out, d_hn):
+        plan, E = ctx.plan, ctx.E
+        xp, out, sv, *w = ctx.saved_tensors
+        dev = out.device
+        N, L, R = plan.N, plan.L, plan.R
+        d_out = _f32(d_out) if d_out is not None else torch.zeros_like(out)
+        d_hn = _f32(d_hn) if (d_hn is not None and d_hn.numel()) else None
+        dG = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev)
+        wp = ptr_array(w)
+        call("umpr_gru_recurrence_bwd", ptr(d_out), ptr(d_hn), ptr(out), ptr(sv), wp, ptr(plan.buf), plan.n_tiles, plan.n_slabs, R,
+             N, L, ptr(dG))
+        flat = torch.zeros(sum(t.numel() for t in w), dtype=torch.float32, device=dev)
+        grads, o = [], 0
+        for t in w:
+            grads.append(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+        call("umpr_gru_wgrad", ptr(dG), ptr(xp), ptr(out), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, ptr_array(grads),
+             _n_ctas(dev, 2))
+        return (None, None, None, None, *grads)
+
+
+def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True):
+    """weights: 8 tensors in nn.GRU order (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then *_reverse)."""
+    return _GruFn.apply(plan, xp, E, want_hidden, *weights)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# strided GEMM helper
+# --------------------------------------------------------------------------------------------------------------------
+def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=False, bias=None, act=0):
+    call("umpr_sgemm", A if isinstance(A, int) else ptr(A), a_strides[0], a_strides[1], B if isinstance(B, int) else ptr(B),
+         b_strides[0], b_strides[1], C if isinstance(C, int) else ptr(C), ldc, M, N, K, splits, int(accumulate), ptr(bias), act)
+
+
+def _splits_for(K, device):
+    return max(1, min(_lib.sm_count(device), K // 256))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# RNet co-attention   (model.py:50-55)
+# --------------------------------------------------------------------------------------------------------------------
+class _CoAttnFn(Function):
+    @staticmethod
+    def forward(ctx, gu, gi, M):
+        gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
+        B, P, _ = gu.shape
+        dev = gu.device
+        giM = torch.empty_like(gi)
+        sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D)
+        rowkey = torch.empty(B * P, dtype=torch.int64, device=dev)
+        colkey = torch.zeros(B * P, dtype=torch.int64, device=dev)
+        soft = torch.empty(4, B, P, dtype=torch.float32, device=dev)       # soft_u, soft_i, t_u, t_i
+        arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
+        atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
+        call("umpr_coattn_fwd", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(rowkey), ptr(colkey), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
+             ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]))
+        ctx.save_for_backward(gu, gi, giM, M, soft, arg)
+        return soft[0], soft[1], atte[0], atte[1]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_soft_u, d_soft_i, d_atte_u, d_atte_i):
+        gu, gi, giM, M, soft, arg = ctx.saved_tensors
+        B, P, _ = gu.shape
+        dev = gu.device
+        c = lambda t: None if t is None else _f32(t)
+        dgu = torch.empty_like(gu)
+        dgi = torch.empty_like(gi)
+        dgiM = torch.empty_like(gi)
+        call("umpr_coattn_bwd", ptr(gu), ptr(gi), ptr(giM), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]),
+             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, ptr(dgu), ptr(dgi), ptr(dgiM))
+        # dgi += dgiM · M^T ;  dM = gi^T · dgiM
+        sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
+        dM = torch.zeros_like(M)
+        sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
+        return dgu, dgi, dM
+
+
+def co_attention(gu, gi, M):
+    """→ soft_u, soft_i (B,P), atte_u, atte_i (B,128)."""
+    return _CoAttnFn.apply(gu, gi, M)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# SNet   (model.py:71-81)
+# --------------------------------------------------------------------------------------------------------------------
+class _SNetFn(Function):
+    @staticmethod
+    def forward(ctx, gru_repr, word_soft, sent_length, Ms, Ws):
+        x = _f32(_chk(gru_repr, "gru_repr"))
+        Ms, Ws = _f32(Ms), _f32(Ws)
+        word_soft = _f32(word_soft)
+        B = x.shape[0]
+        L = int(sent_length)
+        S = x.shape[1] // L
+        N = B * S
+        dev = x.device
+        if Ms.shape != (ATT, D) or x.shape[2] != D:
+            raise RuntimeError("umpr_b200: SNet is built for self_atte_size=64, repr_size=128")
+        train = any(ctx.needs_input_grad)
+        self_atte = torch.empty(B, S, D, dtype=torch.float32, device=dev)
+        soft = torch.empty(N, L, dtype=torch.float32, device=dev) if train else None
+        th = torch.empty(N, L, ATT, dtype=torch.float32, device=dev) if train else None
+        call("umpr_snet_fwd", ptr(x), ptr(Ms), ptr(Ws), N, L, ptr(self_atte), ptr(soft), ptr(th), _n_ctas(dev))
+        Wd = word_soft.numel() // N
+        wsum = torch.empty(N, dtype=torch.float32, device=dev)
+        sentiment = torch.empty(B, D, dtype=torch.float32, device=dev)
+        call("umpr_snet_sentiment_fwd", ptr(self_atte), ptr(word_soft), B, S, Wd, ptr(wsum), ptr(sentiment))
+        ctx.dims = (B, S, L, Wd, tuple(word_soft.shape))
+        ctx.save_for_backward(x, soft, th, self_atte, wsum, Ms, Ws)
+        return self_atte, sentiment
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_self_atte, d_sentiment):
+        x, soft, th, self_atte, wsum, Ms, Ws = ctx.saved_tensors
+        B, S, L, Wd, ws_shape = ctx.dims
+        N = B * S
+        dev = x.device
+        d_sa = torch.empty(N, D, dtype=torch.float32, device=dev)
+        want_ws = ctx.needs_input_grad[1] and d_sentiment is not None
+        d_wsum = torch.empty(N, dtype=torch.float32, device=dev) if want_ws else None
+        call("umpr_snet_sentiment_bwd", ptr(self_atte), ptr(wsum), ptr(None if d_sentiment is None else _f32(d_sentiment)),
+             ptr(None if d_self_atte is None else _f32(d_self_atte)), B, S, ptr(d_sa), ptr(d_wsum))
+        dx = torch.empty_like(x)
+        dW = torch.zeros(ATT * D + ATT, dtype=torch.float32, device=dev)
+        dMs, dWs = dW[:ATT * D].view(ATT, D), dW[ATT * D:].view(1, ATT)
+        call("umpr_snet_bwd", ptr(x), ptr(th), ptr(soft), ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev))
+        d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
+        return dx, d_word_soft, None, dMs, dWs
+
+
+def s_net(gru_repr, word_soft, sent_length, Ms, Ws):
+    """→ self_atte (B,S,128), sentiment (B,128)."""
+    return _SNetFn.apply(gru_repr, word_soft, sent_length, Ms, Ws)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# text matching   (model.py:166-168): tanh(linear_u([atte_u ‖ senti_u]) + linear_i([atte_i ‖ senti_i])), bias-free
+# --------------------------------------------------------------------------------------------------------------------
+class _TextMatchFn(Function):
+    @staticmethod
+    def forward(ctx, atte_u, senti_u, atte_i, senti_i, Wu, Wi):
+        ins = [_f32(t) for t in (atte_u, senti_u, atte_i, senti_i)]
+        Wu, Wi = _f32(Wu), _f32(Wi)
+        B = ins[0].shape[0]
+        y = torch.empty(B, D, dtype=torch.float32, device=ins[0].device)
+        # y = sum_j in_j · W[:, j-th half]^T ; B(k,n) = W[n][off+k] -> strides (1, 2D)
+        for j, (x, W, off) in enumerate(((ins[0], Wu, 0), (ins[1], Wu, D), (ins[2], Wi, 0), (ins[3], Wi, D))):
+            sgemm(x, (D, 1), W.data_ptr() + 4 * off, (1, 2 * D), y, D, B, D, D, accumulate=j > 0, act=1 if j == 3 else 0)
+        ctx.save_for_backward(*ins, Wu, Wi, y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        a_u, s_u, a_i, s_i, Wu, Wi, y = ctx.saved_tensors
+        B = y.shape[0]
+        dev = y.device
+        dpre = torch.empty_like(y)
+        call("umpr_tanh_bwd", ptr(y), ptr(_f32(dy)), y.numel(), ptr(dpre))
+        dins = torch.empty(4, B, D, dtype=torch.float32, device=dev)
+        dW = torch.zeros(2, D, 2 * D, dtype=torch.float32, device=dev)
+        sp = _splits_for(B, dev)
+        for j, (x, W, wi, off) in enumerate(((a_u, Wu, 0, 0), (s_u, Wu, 0, D), (a_i, Wi, 1, 0), (s_i, Wi, 1, D))):
+            # d in_j = dpre · W[:, half]        (B(k,n) = W[k][off+n])
+            sgemm(dpre, (D, 1), W.data_ptr() + 4 * off, (2 * D, 1), dins[j], D, B, D, D)
+            # dW[:, half] = dpre^T · in_j       (A(m,k) = dpre[k][m])
+            sgemm(dpre, (1, D), x, (D, 1), dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, splits=sp, accumulate=True)
+        return dins[0], dins[1], dins[2], dins[3], dW[0], dW[1]
+
+
+def text_match(atte_u, senti_u, atte_i, senti_i, Wu, Wi):
+    return _TextMatchFn.apply(atte_u, senti_u, atte_i, senti_i, Wu, Wi)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# CNet tail   (model.py:118-125)
+# --------------------------------------------------------------------------------------------------------------------
+class _CNetTailFn(Function):
+    @staticmethod
+    def forward(ctx, gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
+        x = _f32(_chk(gru_repr, "gru_repr"))
+        conv_w, conv_b, lin_w, lin_b = _f32(conv_w), _f32(conv_b), _f32(lin_w), _f32(lin_b)
+        B = x.shape[0]
+        S, L = int(sent_count), int(sent_length)
+        N = B * S
+        KC, cin, ks = conv_w.shape
+        V = lin_w.shape[0]
+        dev = x.device
+        if cin != D:
+            raise RuntimeError("umpr_b200: CNet conv is built for in_channels=128")
+        wt = torch.empty(3 * D * 128, dtype=torch.float32, device=dev)
+        call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
+        cfeat = torch.empty(N, KC, dtype=torch.float32, device=dev)
+        cidx = torch.empty(N, KC, dtype=torch.int32, device=dev)
+        call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev))
+        view_p = torch.empty(B, S, V, dtype=torch.float32, device=dev)
+        final = torch.empty(B, V, dtype=torch.float32, device=dev)
+        call("umpr_cnet_head_fwd", ptr(cfeat), ptr(lin_w), ptr(lin_b), float(threshold), B, S, V, KC, ptr(view_p), ptr(final))
+        ctx.dims = (B, S, L, KC, V)
+        ctx.save_for_backward(x, cfeat, cidx, view_p, conv_w, lin_w)
+        return view_p, final
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_view_p, d_final):
+        x, cfeat, cidx, view_p, conv_w, lin_w = ctx.saved_tensors
+        B, S, L, KC, V = ctx.dims
+        N = B * S
+        dev = x.device
+        dcfeat = torch.empty(N, KC, dtype=torch.float32, device=dev)
+        flat = torch.zeros(conv_w.numel() + KC + V * KC + V, dtype=torch.float32, device=dev)
+        o = 0
+        d_conv_w = flat[o:o + conv_w.numel()].view_as(conv_w); o += conv_w.numel()
+        d_conv_b = flat[o:o + KC]; o += KC
+        d_lin_w = flat[o:o + V * KC].view(V, KC); o += V * KC
+        d_lin_b = flat[o:o + V]
+        call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
+             ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
+        dx = torch.empty_like(x)
+        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(dx), ptr(d_conv_w), _n_ctas(dev))
+        return dx, None, None, d_conv_w, d_conv_b, d_lin_w, d_lin_b, None
+
+
+def c_net_tail(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
+    """→ view_p (B,S,V), final_repr (B,V)."""
+    return _CNetTailFn.apply(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ControlNet tail   (model.py:186-197; SSNet model.py:142-143)
+# --------------------------------------------------------------------------------------------------------------------
+class _ControlTailFn(Function):
+    @staticmethod
+    def forward(ctx, s, view_p, c_out, ss_w, ss_b, eps):
+        s, view_p, c_out, ss_w, ss_b = (_f32(t) for t in (s, view_p, c_out, ss_w, ss_b))
+        B, Su, _ = s.shape
+        V = view_p.shape[-1]
+        dev = s.device
+        senti = torch.empty(B, Su, dtype=torch.float32, device=dev)
+        out = torch.empty(3, B, V, dtype=torch.float32, device=dev)       # score, prefer_pos, prefer_neg
+        call("umpr_control_tail_fwd", ptr(s), ptr(view_p), ptr(c_out), ptr(ss_w), ptr(ss_b), float(eps), B, Su, V, ptr(senti), ptr(out[0]),
+             ptr(out[1]), ptr(out[2]))
+        ctx.eps = float(eps)
+        ctx.save_for_backward(s, view_p, c_out, ss_w, senti, out)
+        return out[1], out[2]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_pp, d_pn):
+        s, view_p, c_out, ss_w, senti, out = ctx.saved_tensors
+        B, Su, _ = s.shape
+        V = view_p.shape[-1]
+        dev = s.device
+        z = lambda t: torch.zeros(B, V, dtype=torch.float32, device=dev) if t is None else _f32(t)
+        d_s = torch.empty_like(s)
+        d_vp = torch.empty_like(view_p)
+        d_co = torch.empty_like(c_out)
+        dW = torch.zeros(D + 1, dtype=torch.float32, device=dev)
+        call("umpr_control_tail_bwd", ptr(s), ptr(view_p), ptr(c_out), ptr(ss_w), ptr(senti), ptr(out[0]), ptr(z(d_pp)), ptr(z(d_pn)),
+             ctx.eps, B, Su, V, ptr(d_s), ptr(d_vp), ptr(d_co), ptr(dW[:D]), ptr(dW[D:]))
+        return d_s, d_vp, d_co, dW[:D].view(1, D), dW[D:], None
+
+
+def control_tail(s, view_p, c_out, ss_w, ss_b, eps):
+    """→ prefer_pos, prefer_neg (B,V)."""
+    return _ControlTailFn.apply(s, view_p, c_out, ss_w, ss_b, eps)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# VisualNet tail   (model.py:219-228)
+# --------------------------------------------------------------------------------------------------------------------
+class _VisualFn(Function):
+    @staticmethod
+    def forward(ctx, feat, c_u, c_i, pos_e, neg_e, w, b):
+        feat, c_u, c_i, pos_e, neg_e, w, b = (_f32(t) for t in (feat, c_u, c_i, pos_e, neg_e, w, b))
+        _chk(feat, "photo features")
+        B, V, Pc, Fd = feat.shape
+        dev = feat.device
+        emb = torch.empty(2, V, dtype=torch.float32, device=dev)
+        out = torch.empty(5, B, V, dtype=torch.float32, device=dev)       # img_emb, pos_match, neg_match, final_pos, final_neg
+        call("umpr_visual_fwd", ptr(feat), ptr(pos_e), ptr(neg_e), ptr(w), ptr(b), ptr(c_u), ptr(c_i), B, V, Pc, Fd, ptr(emb), ptr(out[0]),
+             ptr(out[1]), ptr(out[2]), ptr(out[3]), ptr(out[4]))
+        ctx.save_for_backward(feat, c_u, c_i, pos_e, neg_e, w, emb, out)
+        return out[1], out[2], out[3], out[4]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_pm, d_nm, d_fp, d_fn):
+        feat, c_u, c_i, pos_e, neg_e, w, emb, out = ctx.saved_tensors
+        B, V, Pc, Fd = feat.shape
+        dev = feat.device
+        c = lambda t: None if t is None else _f32(t)
+        scratch = torch.empty(3 * B * V, dtype=torch.float32, device=dev)
+        d_c = torch.empty(2, B, V, dtype=torch.float32, device=dev)
+        d_e = torch.empty(2, V, Fd, dtype=torch.float32, device=dev)
+        dW = torch.zeros(Fd + 1, dtype=torch.float32, device=dev)
+        call("umpr_visual_bwd", ptr(feat), ptr(pos_e), ptr(neg_e), ptr(w), ptr(emb), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(c_u),
+             ptr(c_i), ptr(c(d_pm)), ptr(c(d_nm)), ptr(c(d_fp)), ptr(c(d_fn)), B, V, Pc, Fd, ptr(scratch), ptr(d_c[0]), ptr(d_c[1]),
+             ptr(d_e[0]), ptr(d_e[1]), ptr(dW[:Fd]), ptr(dW[Fd:]))
+        return None, d_c[0], d_c[1], d_e[0], d_e[1], dW[:Fd].view(1, Fd), dW[Fd:]
+
+
+def visual_tail(feat, c_u, c_i, pos_e, neg_e, w, b):
+    """→ pos_match, neg_match, final_pos, final_neg (B,V)."""
+    return _VisualFn.apply(feat, c_u, c_i, pos_e, neg_e, w, b)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# fusion + losses   (model.py:268-277)
+# --------------------------------------------------------------------------------------------------------------------
+class _FusionFn(Function):
+    @staticmethod
+    def forward(ctx, repr_, fpos, fneg, w, b):
+        repr_, w, b = _f32(_chk(repr_, "review_net_repr")), _f32(w), _f32(b)
+        fpos = None if fpos is None else _f32(fpos)
+        fneg = None if fneg is None else _f32(fneg)
+        B = repr_.shape[0]
+        V = 0 if fpos is None else fpos.shape[1]
+        pred = torch.empty(B, dtype=torch.float32, device=repr_.device)
+        call("umpr_fusion_fwd", ptr(repr_), ptr(fpos), ptr(fneg), ptr(w), ptr(b), B, V, ptr(pred))
+        ctx.V = V
+        ctx.save_for_backward(repr_, fpos, fneg, w, pred)
+        return pred
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_pred):
+        repr_, fpos, fneg, w, pred = ctx.saved_tensors
+        B, V = repr_.shape[0], ctx.V
+        dev = repr_.device
+        d_repr = torch.empty_like(repr_)
+        d_f = torch.empty(2, B, V, dtype=torch.float32, device=dev) if V else None
+        dW = torch.zeros(w.numel() + 1, dtype=torch.float32, device=dev)
+        call("umpr_fusion_bwd", ptr(repr_), ptr(fpos), ptr(fneg), ptr(w), ptr(pred), ptr(_f32(d_pred)), B, V, ptr(d_repr),
+             ptr(d_f[0]) if V else None, ptr(d_f[1]) if V else None, ptr(dW[:-1]), ptr(dW[-1:]))
+        return d_repr, (d_f[0] if V else None), (d_f[1] if V else None), dW[:-1].view_as(w), dW[-1:]
+
+
+def fusion(repr_, fpos, fneg, w, b):
+    """relu(Linear(cat[repr, final_pos, final_neg])).squeeze(-1) → (B,)"""
+    return _FusionFn.apply(repr_, fpos, fneg, w, b)
+
+
+class _LossFn(Function):
+    @staticmethod
+    def forward(ctx, pred, labels, pp, pn, pm, nm, rate):
+        pred, labels = _f32(_chk(pred, "prediction")), _f32(labels)
+        full = pp is not None
+        if full:
+            pp, pn, pm, nm = (_f32(t) for t in (pp, pn, pm, nm))
+        B = pred.shape[0]
+        V = pp.shape[1] if full else 0
+        loss = torch.zeros(1, dtype=torch.float32, device=pred.device)
+        call("umpr_loss_fwd", ptr(pred), ptr(labels), ptr(pp), ptr(pn), ptr(pm), ptr(nm), B, V, float(rate), ptr(loss))
+        ctx.rate, ctx.V = float(rate), V
+        ctx.save_for_backward(pred, labels, pp, pn, pm, nm)
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_loss):
+        pred, labels, pp, pn, pm, nm = ctx.saved_tensors
+        B, V = pred.shape[0], ctx.V
+        dev = pred.device
+        d_pred = torch.empty_like(pred)
+        g = torch.empty(4, B, V, dtype=torch.float32, device=dev) if V else None
+        gp = (lambda i: ptr(g[i])) if V else (lambda i: None)
+        call("umpr_loss_bwd", ptr(pred), ptr(labels), ptr(pp), ptr(pn), ptr(pm), ptr(nm), ptr(_f32(d_loss).reshape(1)), B, V, ctx.rate,
+             ptr(d_pred), gp(0), gp(1), gp(2), gp(3))
+        if V:
+            return d_pred, None, g[0], g[1], g[2], g[3], None
+        return d_pred, None, None, None, None, None, None
+
+
+def umpr_loss(pred, labels, pp=None, pn=None, pm=None, nm=None, rate=0.0):
+    """mse_loss(pred, labels, 'mean') [+ rate * mean(pp^T @ pm + pn^T @ nm)]  (model.py:269,275-277)"""
+    return _LossFn.apply(pred, labels, pp, pn, pm, nm, rate)

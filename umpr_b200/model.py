@@ -1,0 +1,253 @@
+"""Drop-in mirror of the reference ``src/model.py`` module tree on the B200 kernels.
+
+Same class names, constructor arguments, ``forward`` signatures, return tuples and ``state_dict`` keys
+(SURVEY.md §8b), so ``main.py:33`` / ``evaluate.py:11`` / ``pretrain_rnet.py:165`` style host code and reference
+checkpoints work unchanged.  The ``nn`` sub-modules (``nn.GRU``, ``nn.Conv1d``, ``nn.Linear``) are kept ONLY as
+parameter containers with the reference's initialisation; their ``forward`` is never called — every operator runs
+through ``umpr_b200.functional`` → ``libumpr_b200.so``.  There is no CPU path: parameters must be on a CUDA device.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import functional as F
+from .plan import PackPlan
+
+EQ18_EPS = 1e-4   # model.py:188 (the code, not the readme's 1e-6, is the oracle)
+
+
+class PackedReviews:
+    """One review side (user, item or user→item) ready for the GRU kernels: plan + packed inputs, built once and
+    shared by every ImprovedRnn that reads the same tokens (R-Net's and C-Net's GRUs, model.py:45-46,182-184)."""
+
+    def __init__(self, lengths, *, ids=None, table=None, emb=None):
+        src = ids if ids is not None else emb
+        self.B, self.S, self.L = src.shape[0], src.shape[1], src.shape[2]
+        dev = table.device if table is not None else emb.device
+        if emb is not None and emb.requires_grad:
+            raise RuntimeError("umpr_b200: the embedding is frozen on this path (model.py:237); no input gradient is produced")
+        self.plan = PackPlan(lengths.reshape(-1), self.L, dev)               # model.py:42-43 flatten + model.py:18
+        if ids is not None:
+            self.xp, self.E = F.gather_pack(self.plan, table=table, ids=ids.reshape(self.B * self.S, self.L))
+        else:
+            self.xp, self.E = F.gather_pack(self.plan, dense=emb.reshape(self.B * self.S, self.L, emb.shape[-1]))
+
+
+def _gru_weights(gru: nn.GRU):
+    return [gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
+            gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse, gru.bias_hh_l0_reverse]
+
+
+class ImprovedRnn(nn.Module):
+    """model.py:6-21.  ``forward(data (N,L,E), lengths (N,)) -> (result (N,L,128), hidden (2,N,64))`` with
+    ``result[n] = GRU(data[unsorted_indices[n]])`` zero-padded to ``total_length = data.shape[1]``."""
+
+    def __init__(self, module, *args, **kwargs):
+        assert module in (nn.RNN, nn.LSTM, nn.GRU)
+        super().__init__()
+        self.module = module(*args, **kwargs)
+        m = self.module
+        if not (isinstance(m, nn.GRU) and m.batch_first and m.bidirectional and m.num_layers == 1 and m.hidden_size == F.H
+                and m.bias and m.input_size < F.KP):
+            raise NotImplementedError("umpr_b200 builds the reference's configuration only: nn.GRU, batch_first, "
+                                      "bidirectional, 1 layer, hidden_size=64, input_size<64")
+
+    def forward(self, data, lengths):
+        if isinstance(data, PackedReviews):
+            pk = data
+        else:
+            pk = PackedReviews(lengths, emb=data.unsqueeze(0))
+        return self.run(pk)
+
+    def run(self, pk: PackedReviews, want_hidden=True):
+        return F.gru_forward(pk.plan, pk.xp, pk.E, _gru_weights(self.module), want_hidden)
+
+
+class RNet(nn.Module):
+    """model.py:24-56."""
+
+    def __init__(self, gru_in, gru_out, pretrained: str = None):
+        super().__init__()
+        self.gru = ImprovedRnn(nn.GRU, input_size=gru_in, hidden_size=gru_out, batch_first=True, bidirectional=True)
+        self.M = nn.Parameter(torch.randn(2 * gru_out, 2 * gru_out))
+        if pretrained is not None:
+            try:
+                self.load_state_dict(torch.load(pretrained).state_dict())
+            except Exception:
+                print(f'Failed to load R-Net pre-trained weights from "{pretrained}"')
+
+    def forward(self, user_emb, item_emb, u_lengths, i_lengths):
+        pu = user_emb if isinstance(user_emb, PackedReviews) else PackedReviews(u_lengths, emb=user_emb)
+        pi = item_emb if isinstance(item_emb, PackedReviews) else PackedReviews(i_lengths, emb=item_emb)
+        gru_u, _ = self.gru.run(pu, want_hidden=False)
+        gru_i, _ = self.gru.run(pi, want_hidden=False)
+        gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
+        gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
+        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M)
+        return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
+
+
+class SNet(nn.Module):
+    """model.py:59-81."""
+
+    def __init__(self, self_atte_size, repr_size, pretrained: str = None):
+        super().__init__()
+        self.Ms = nn.Parameter(torch.randn(self_atte_size, repr_size))
+        self.Ws = nn.Parameter(torch.randn(1, self_atte_size))
+        if pretrained is not None:
+            try:
+                self.load_state_dict(torch.load(pretrained).state_dict())
+            except Exception:
+                print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
+
+    def forward(self, gru_repr, word_soft, sent_length):
+        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws)
+
+
+class CNet(nn.Module):
+    """model.py:84-126."""
+
+    def __init__(self, gru_in, gru_out, k_count, k_size, view_size, threshold=0.35, pretrained: str = None):
+        super().__init__()
+        self.threshold = threshold
+        self.gru = ImprovedRnn(nn.GRU, input_size=gru_in, hidden_size=gru_out, batch_first=True, bidirectional=True)
+        self.cnn = nn.Sequential(
+            nn.Conv1d(in_channels=2 * gru_out, out_channels=k_count, kernel_size=k_size, padding=(k_size - 1) // 2),
+            nn.ReLU(),
+        )
+        self.linear = nn.Sequential(nn.Linear(k_count, view_size), nn.Sigmoid())
+        if pretrained is not None:
+            try:
+                self.load_state_dict(torch.load(pretrained).state_dict())
+            except Exception:
+                print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
+
+    def forward(self, review_emb, lengths):
+        pk = review_emb if isinstance(review_emb, PackedReviews) else PackedReviews(lengths, emb=review_emb)
+        gru_repr, _ = self.gru.run(pk, want_hidden=False)
+        gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
+        view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
+                                          self.linear[0].weight, self.linear[0].bias, self.threshold)
+        return gru_repr, view_p, final_repr
+
+
+class SSNet(nn.Module):
+    """model.py:129-143.  Used through ``ControlNet`` (fused with Eq.18); standalone forward kept for API parity."""
+
+    def __init__(self, input_size, pretrained: str = None):
+        super().__init__()
+        self.linear = nn.Sequential(nn.Linear(input_size, 1), nn.Sigmoid())
+        if pretrained is not None:
+            try:
+                self.load_state_dict(torch.load(pretrained).state_dict())
+            except Exception:
+                print(f'Failed to load SS-Net pre-trained weights from "{pretrained}"')
+
+    def forward(self, sentiment_emb):
+        x = sentiment_emb
+        y = torch.empty(*x.shape[:-1], 1, dtype=torch.float32, device=x.device)
+        w, b = self.linear[0].weight, self.linear[0].bias
+        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+            raise NotImplementedError("umpr_b200: SSNet trains through ControlNet's fused tail; standalone SSNet is inference-only")
+        rows = x.numel() // x.shape[-1]
+        F.sgemm(x.contiguous(), (x.shape[-1], 1), w.detach(), (1, x.shape[-1]), y, 1, rows, 1, x.shape[-1], bias=b.detach(), act=3)
+        return y
+
+
+class ReviewNet(nn.Module):
+    """model.py:146-169."""
+
+    def __init__(self, emb_size, gru_size, atte_size):
+        super().__init__()
+        self.r_net = RNet(emb_size, gru_size)
+        self.s_net_u = SNet(atte_size, gru_size * 2)
+        self.s_net_i = SNet(atte_size, gru_size * 2)
+        self.linear_u = nn.Linear(gru_size * 4, gru_size * 2, bias=False)
+        self.linear_i = nn.Linear(gru_size * 4, gru_size * 2, bias=False)
+
+    def forward(self, user_emb, item_emb, u_lengths, i_lengths):
+        u_s_length = user_emb.L if isinstance(user_emb, PackedReviews) else user_emb.shape[-2]
+        i_s_length = item_emb.L if isinstance(item_emb, PackedReviews) else item_emb.shape[-2]
+        gru_u, gru_i, soft_u, soft_i, atte_u, atte_i = self.r_net(user_emb, item_emb, u_lengths, i_lengths)
+        _, sentiment_u = self.s_net_u(gru_u, soft_u, u_s_length)
+        _, sentiment_i = self.s_net_i(gru_i, soft_i, i_s_length)
+        return F.text_match(atte_u, sentiment_u, atte_i, sentiment_i, self.linear_u.weight, self.linear_i.weight)
+
+
+class ControlNet(nn.Module):
+    """model.py:172-198."""
+
+    def __init__(self, emb_size, gru_size, k_count, k_size, view_size, threshold, atte_size):
+        super().__init__()
+        self.c_net = CNet(emb_size, gru_size, k_count, k_size, view_size, threshold)
+        self.s_net = SNet(atte_size, repr_size=gru_size * 2)
+        self.ss_net = SSNet(input_size=gru_size * 2)
+
+    def forward(self, user_emb, item_emb, ui_emb, u_lengths, i_lengths, ui_lengths):
+        ui_s_length = ui_emb.L if isinstance(ui_emb, PackedReviews) else ui_emb.shape[-2]
+        gru_repr, view_p, c_net_out = self.c_net(ui_emb, ui_lengths)
+        _, _, c_u = self.c_net(user_emb, u_lengths)
+        _, _, c_i = self.c_net(item_emb, i_lengths)
+        s, _ = self.s_net(gru_repr, view_p, ui_s_length)
+        lin = self.ss_net.linear[0]
+        prefer_pos, prefer_neg = F.control_tail(s, view_p, c_net_out, lin.weight, lin.bias, EQ18_EPS)
+        return c_u, c_i, prefer_pos, prefer_neg
+
+
+class VisualNet(nn.Module):
+    """model.py:201-229 without the VGG16 backbone (out of scope): ``images`` are the backbone's
+    output features ``(B, V, Pc, vgg_out[, 1, 1])``, i.e. what ``self.vgg16(images).view(...)`` yields at model.py:218."""
+
+    def __init__(self, view_size, vgg_out=1000):
+        super().__init__()
+        self.pos_v_emb = nn.Parameter(torch.randn(view_size, vgg_out))
+        self.neg_v_emb = nn.Parameter(torch.randn(view_size, vgg_out))
+        self.linear = nn.Linear(vgg_out, 1)
+
+    def forward(self, images, c_u, c_i):
+        feat = images.reshape(images.shape[0], images.shape[1], images.shape[2], -1)
+        return F.visual_tail(feat, c_u, c_i, self.pos_v_emb, self.neg_v_emb, self.linear.weight, self.linear.bias)
+
+
+class UMPR(nn.Module):
+    """model.py:232-278.  ``forward`` takes the 8-tuple of ``dataset.py:173-182`` and returns ``(prediction, loss)``."""
+
+    def __init__(self, config, word_emb):
+        super().__init__()
+        self.review_net_only = config.review_net_only
+        self.loss_v_rate = config.loss_v_rate
+        self.embedding = nn.Embedding.from_pretrained(torch.as_tensor(word_emb, dtype=torch.float32).clone())
+        self.review_net = ReviewNet(self.embedding.embedding_dim, config.gru_size, config.self_atte_size)
+        if config.review_net_only:
+            self.linear_fusion = nn.Sequential(nn.Linear(config.gru_size * 2, 1), nn.ReLU())
+        else:
+            view_size = len(config.views)
+            self.control_net = ControlNet(self.embedding.embedding_dim, config.gru_size, config.kernel_count,
+                                          config.kernel_size, view_size, config.threshold, config.self_atte_size)
+            self.visual_net = VisualNet(view_size)
+            self.linear_fusion = nn.Sequential(nn.Linear(config.gru_size * 2 + view_size + view_size, 1), nn.ReLU())
+
+    def forward(self, user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels):
+        table = self.embedding.weight
+        device = table.device
+        if device.type != "cuda":
+            raise RuntimeError("umpr_b200: move the model to a CUDA device first (there is no CPU path)")
+        to = lambda v: v.to(device, non_blocking=True)
+        user_reviews, item_reviews = to(user_reviews), to(item_reviews)
+        labels = to(labels)
+        pu = PackedReviews(u_lengths, ids=user_reviews, table=table)          # model.py:262-263 fused into the pack
+        pi = PackedReviews(i_lengths, ids=item_reviews, table=table)
+        review_net_repr = self.review_net(pu, pi, u_lengths, i_lengths)
+        lf = self.linear_fusion[0]
+        if self.review_net_only:
+            prediction = F.fusion(review_net_repr, None, None, lf.weight, lf.bias)
+            loss = F.umpr_loss(prediction, labels)
+        else:
+            photos = to(photos)
+            pui = PackedReviews(ui_lengths, ids=to(ui_reviews), table=table)
+            c_u, c_i, prefer_pos, prefer_neg = self.control_net(pu, pi, pui, u_lengths, i_lengths, ui_lengths)
+            pos_match, neg_match, final_pos, final_neg = self.visual_net(photos, c_u, c_i)
+            prediction = F.fusion(review_net_repr, final_pos, final_neg, lf.weight, lf.bias)
+            loss = F.umpr_loss(prediction, labels, prefer_pos, prefer_neg, pos_match, neg_match, self.loss_v_rate)
+        return prediction, loss
