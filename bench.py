@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — UMPR train-step samples/sec on N B200s (one process per GPU), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--workload music_full]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+A "step" = main.py:32-37 on one synthetic batch: zero_grad, forward, backward, gradient all-reduce (N>1), fused Adam.
+``value``: inputs already resident in HBM.  ``e2e``: the same step through the public API (``UMPR.forward`` of the
+drop-in module) with HOST (pinned) input buffers, the H2D copies and the D2H read of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "UMPR train samples/sec (device-timed, fwd+bwd+allreduce+Adam)"
+UNIT = "samples/s"
+
+# which roofline bounds each entry point: dense contractions -> tensor pipe, the rest -> HBM
+TENSOR_BOUND = {"umpr_gru_inproj", "umpr_gru_recurrence_fwd", "umpr_gru_recurrence_bwd", "umpr_gru_wgrad", "umpr_sgemm",
+                "umpr_coattn_fwd", "umpr_snet_fwd", "umpr_snet_bwd", "umpr_cnet_conv_fwd"}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled during the timed region (B200_PROFILING.md 'clocks' line)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_port_run(workload, batch, steps, warmup, seed=0):
+    """The reference's CPU path for this workload: oracle port with the library GRU calls of model.py:18-20,
+    forward + backward + torch.optim.Adam (main.py:22-25,32-37), all host threads."""
+    from oracle import umpr_oracle as orc     # the one place bench.py executes oracle/: the CPU baseline
+    from umpr_b200 import synthetic as syn
+    table = syn.make_table(400003, seed=0)
+    model = syn.build_model(workload, table, seed=0, device="cpu")
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    for k, v in params.items():
+        v.requires_grad_(k != "embedding.weight")
+    named = [(k, v) for k, v in params.items() if v.requires_grad]
+    opt = torch.optim.Adam([{"params": [v for k, v in named if "bias" not in k]},
+                            {"params": [v for k, v in named if "bias" in k], "weight_decay": 0.0}], 1e-6, weight_decay=1e-3)
+    rno = syn.WORKLOADS[workload]["review_net_only"]
+    batches = [syn.make_batch(workload, batch, seed=seed + i) for i in range(2)]
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        pred, loss = orc.umpr_forward(params, batches[i % 2], review_net_only=rno, impl="lib")
+        opt.zero_grad()
+        loss.mean().backward()
+        opt.step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    val, ms = cpu_port_run(args.workload, B, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "per_step_sample_batch": B, "device": "cpu", "host_threads": cores,
+                       "os_cpu_count": os.cpu_count()},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} train steps of batch {B} ({args.workload}), oracle port with torch's CPU GRU"},
+            "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def tensor_bytes(ts):
+    return int(sum(t.numel() * t.element_size() for t in ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="umpr_b200", choices=["umpr_b200", "reference"])
+    ap.add_argument("--workload", default="music_full")
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--ref-batch", type=int, default=64, help="batch of one CPU reference step (config.py:12)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batch64", action="store_true")
+    ap.add_argument("--kernel-table", action="store_true", help="print the per-entry-point time table to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import umpr_b200
+    from umpr_b200 import _lib, synthetic as syn
+    from umpr_b200.train import FlatTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    umpr_b200.require_lib()
+    peaks = load_peaks()
+    B, K, W = args.batch, args.steps, args.warmup
+
+    table = syn.make_table(400003, seed=0)
+    model = syn.build_model(args.workload, table, seed=0, device=dev)       # identical replicas: same seed on every rank
+    trainer = FlatTrainer(model, lr=1e-6, weight_decay=1e-3)
+    n_params = trainer.n_params
+    NB = 4
+    host = [syn.make_batch(args.workload, B, seed=1000 * rank + i) for i in range(NB)]
+    pin = lambda t: t.pin_memory() if t.numel() else t
+    host = [tuple(pin(t) for t in b) for b in host]
+
+    def resident(b):     # reviews / photos / labels in HBM; lengths stay on the host as the reference's collate leaves them
+        u, it, ui, ul, il, uil, ph, lab = b
+        return (u.to(dev), it.to(dev), ui.to(dev), ul, il, uil, ph.to(dev), lab.to(dev))
+
+    devb = [resident(b) for b in host]
+    tokens = [int(b[3].sum() + b[4].sum() + b[5].sum()) for b in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms), clocks
+
+    def step_resident(i):
+        trainer.train_step(devb[i % NB])
+
+    sink = []
+
+    def step_e2e(i):
+        pred, loss = trainer.train_step(host[i % NB])          # H2D of ids/photos/labels happens inside UMPR.forward
+        sink.append(loss.item())                               # main.py:39: D2H read of the loss every step
+
+    # ---- warm-up, with every entry point timed once to find the dominant kernel
+    for i in range(W - 1):
+        step_resident(i)
+    _lib.start_timing()
+    step_resident(W - 1)
+    table_ms = _lib.stop_timing()
+    top = max(table_ms, key=lambda k: table_ms[k]["ms"])
+    step_ms_profiled = sum(v["ms"] for v in table_ms.values())
+    if args.kernel_table and rank == 0:
+        for k, v in sorted(table_ms.items(), key=lambda kv: -kv[1]["ms"]):
+            print(f"  {k:28s} calls {v['calls']:3d}  {v['ms']:9.3f} ms  {100 * v['ms'] / step_ms_profiled:5.1f}%  "
+                  f"{v['flops'] / 1e9:10.2f} GFLOP {v['bytes'] / 1e6:10.1f} MB", file=sys.stderr)
+
+    # ---- timed region: K steps, inputs resident; only the dominant entry point carries event pairs
+    launches0 = _lib.launch_count
+    _lib.start_timing(only=[top])
+    ms, clocks = timed(step_resident, K, ClockSampler(local))
+    launches = _lib.launch_count - launches0
+    kt = _lib.stop_timing()[top]
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, K)
+    e2e_val = world * B * K / (ms_e2e / 1e3)
+    h2d = tensor_bytes([host[0][j] for j in (0, 1, 2, 6, 7)])
+    # plus the int32 pack plans built from the host lengths (3 or 5 GRU plans share 3 buffers)
+    from umpr_b200.plan import PackPlan
+    h2d += sum(PackPlan(host[0][j], host[0][j - 3].shape[2], "cpu", tile_rows=128).host.numel() * 4
+               for j in ((3, 4) if syn.WORKLOADS[args.workload]["review_net_only"] else (3, 4, 5)))
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: full UMPR, Amazon Digital Music shape (S=20, L=20, S_ui=5, V=1, Pc=1, GloVe-50d table "
+                               f"400003x50, VGG16 features)" if args.workload == "music_full" else args.workload,
+                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "tokens_per_step_per_gpu": int(sum(tokens) / NB), "trainable_params": n_params,
+                   "step": "zero_grad+fwd+bwd+allreduce+adam",
+                   "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; 4 rotating input batches"},
+        "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 4), "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    # ---- roofline of the dominant kernel (event-timed on the launching stream inside the timed region)
+    bound = "tensor" if top in TENSOR_BOUND else "hbm"
+    per_launch_ms = kt["ms"] / max(1, kt["calls"])
+    if bound == "tensor":
+        achieved = kt["flops"] / max(1, kt["calls"]) / (per_launch_ms * 1e-3) / 1e12
+        peak, unit = peaks["tf_sust"], "TFLOP/s"
+    else:
+        achieved = kt["bytes"] / max(1, kt["calls"]) / (per_launch_ms * 1e-3) / 1e9
+        peak, unit = peaks["hbm"], "GB/s"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top)
+    line["roofline"] = {"kernel": top, "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit,
+                        "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peaks["src"] + (" bf16 dense sustained" if bound == "tensor" else " copy"),
+                        "launch_ms": round(per_launch_ms, 4), "share_of_step": round(kt["ms"] / ms, 4),
+                        "math": "fp32 CUDA cores (round 1); algorithmic FLOPs per SURVEY.md §8d"}
+    line["kernel_table_ms"] = {k: round(v["ms"], 3) for k, v in sorted(table_ms.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+
+    if world == 1 and rank == 0:
+        if not args.no_batch64:
+            small = [resident(syn.make_batch(args.workload, 64, seed=77 + i)) for i in range(NB)]
+            for i in range(3):
+                trainer.train_step(small[i % NB])
+            ms64, _ = timed(lambda i: trainer.train_step(small[i % NB]), K)
+            line["batch64"] = {"value": round(64 * K / (ms64 / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms64 / K, 4),
+                               "note": "reference default batch_size=64 (config.py:12), inputs resident"}
+        if not args.no_cpu_baseline:
+            steps_cpu = 12
+            v, msc = cpu_port_run(args.workload, args.ref_batch, steps_cpu, 2)
+            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "ms_per_step": round(msc, 2),
+                                    "sample": f"{steps_cpu} train steps of batch {args.ref_batch} of the same workload "
+                                              f"(oracle port, torch CPU GRU, fwd+bwd+Adam), os.cpu_count={os.cpu_count()}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

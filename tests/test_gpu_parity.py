@@ -13,6 +13,18 @@ TOL = 1e-4
 DEV = "cuda:0"
 
 
+def _check_grad(k, got, ref):
+    ref = torch.as_tensor(ref)
+    if k == "visual_net.linear.bias":
+        # the bias cancels in (pos_emb - img_emb): the analytic gradient is exactly 0 and both sides hold only fp32
+        # cancellation noise of O(1e-7) -> absolute comparison
+        assert float(got.abs().max()) < 1e-5 and float(ref.abs().max()) < 1e-5, k
+    elif float(ref.abs().max()) < 1e-7:
+        assert float(got.abs().max()) < 1e-6, k
+    else:
+        assert_close(got, ref, TOL, "grad " + k)
+
+
 def _model(c):
     import umpr_b200
     params = cases.make_params(c["review_net_only"], c["V"], c["vocab"], c["seed"], c["m_scale"])
@@ -54,7 +66,7 @@ def test_improved_rnn_accepts_gpu_lengths_and_total_length():
     assert out.shape == (37, 11, 128)
     assert_close(out, ref, TOL, "out")
     assert_close(hid, hid_ref, TOL, "hidden")
-    assert float(out[:, 5:].abs().max()) == 0.0
+    assert float(out.detach()[:, 5:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("name", list(cases.CASES))
@@ -90,10 +102,7 @@ def test_umpr_vs_reference(name):
             continue
         ref = g["grad:" + k]
         got = p.grad if p.grad is not None else torch.zeros_like(p)
-        if np.abs(ref).max() < 1e-7:
-            assert float(got.abs().max()) < 1e-6, k
-        else:
-            assert_close(got, ref, TOL, "grad " + k)
+        _check_grad(k, got, ref)
     m.eval()
     with torch.no_grad():
         pe, _ = m(*batch)
@@ -120,10 +129,7 @@ def test_umpr_vs_oracle_amazon_shape(workload, B):
     for k, p in m.named_parameters():
         if p.requires_grad:
             got = p.grad if p.grad is not None else torch.zeros_like(p)
-            if float(g_ref[k].abs().max()) < 1e-7:
-                assert float(got.abs().max()) < 1e-6, k
-            else:
-                assert_close(got, g_ref[k], TOL, "grad " + k)
+            _check_grad(k, got, g_ref[k])
 
 
 def test_module_level_api_rnet_snet_cnet():

@@ -94,13 +94,51 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
-    """Invoke a C-ABI entry point on the current CUDA stream (appended as the last argument)."""
+# kernels launched per C-ABI call (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"umpr_coattn_fwd": 2, "umpr_cnet_conv_bwd": 2, "umpr_visual_fwd": 2, "umpr_visual_bwd": 3}
+launch_count = 0          # kernels launched by this process through the C-ABI
+_timer = None             # optional {"only": set|None, "events": {name: [(start, end), ...]}}
+
+
+def start_timing(only=None):
+    """Record a CUDA-event pair around every call (or only the named entry points) on the launching stream."""
+    global _timer
+    _timer = {"only": set(only) if only else None, "events": {}, "work": {}}
+
+
+def stop_timing():
+    """→ {name: dict(calls, ms, flops, bytes)}; synchronises the device."""
+    global _timer
+    t, _timer = _timer, None
+    torch.cuda.synchronize()
+    out = {}
+    for k, v in (t["events"] if t else {}).items():
+        w = t["work"].get(k, [0.0, 0.0])
+        out[k] = dict(calls=len(v), ms=sum(a.elapsed_time(b) for a, b in v), flops=w[0], bytes=w[1])
+    return out
+
+
+def call(name, *args, work=None):
+    """Invoke a C-ABI entry point on the current CUDA stream (appended as the last argument).
+    ``work`` = (algorithmic FLOPs, algorithmic bytes) of this launch, recorded only while timing (bench.py roofline)."""
+    global launch_count
     lib = load()
+    timed = _timer is not None and (_timer["only"] is None or name in _timer["only"])
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args, stream())
+    if timed:
+        e1.record()
+        _timer["events"].setdefault(name, []).append((e0, e1))
+        if work is not None:
+            w = _timer["work"].setdefault(name, [0.0, 0.0])
+            w[0] += work[0]
+            w[1] += work[1]
     if rc != 0:
         kind = "argument error" if rc < 0 else f"CUDA error {rc}"
         raise RuntimeError(f"{name}: {kind}: {last_error()}")
+    launch_count += KERNELS_PER_CALL.get(name, 1)
 
 
 _SM = {}

@@ -45,7 +45,8 @@ def gather_pack(plan: PackPlan, *, table=None, ids=None, dense=None):
         E = table.shape[1]
         dev = table.device
     xp = torch.empty(plan.n_slabs * plan.R * KP, dtype=torch.float32, device=dev)
-    call("umpr_gather_pack", ptr(table), ptr(ids), ptr(dense), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.R, plan.L, E, ptr(xp))
+    call("umpr_gather_pack", ptr(table), ptr(ids), ptr(dense), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.R, plan.L, E, ptr(xp),
+         work=(0.0, plan.tokens * (8 + 4 * E + 4 * KP)))
     return xp, E
 
 
@@ -60,12 +61,13 @@ class _GruFn(Function):
         N, L, R = plan.N, plan.L, plan.R
         G = torch.empty(plan.n_slabs * 2 * R * 3 * H, dtype=torch.float32, device=dev)
         wp = ptr_array(w)
-        call("umpr_gru_inproj", ptr(xp), wp, plan.n_slabs, R, E, ptr(G))
+        call("umpr_gru_inproj", ptr(xp), wp, plan.n_slabs, R, E, ptr(G), work=(2.0 * plan.tokens * E * 6 * H, 0.0))
         out = torch.empty(N, L, D, dtype=torch.float32, device=dev)
         hn = torch.empty(2, N, H, dtype=torch.float32, device=dev) if want_hidden else None
         need_grad = any(ctx.needs_input_grad[4:])
         sv = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev) if need_grad else None
-        call("umpr_gru_recurrence_fwd", ptr(G), wp, ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, N, L, ptr(out), ptr(hn), ptr(sv))
+        call("umpr_gru_recurrence_fwd", ptr(G), wp, ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, N, L, ptr(out), ptr(hn), ptr(sv),
+             work=(2.0 * plan.tokens * 2 * H * 3 * H, 0.0))
         del G
         ctx.plan, ctx.E = plan, E
         ctx.save_for_backward(xp, out, sv, *w)
@@ -86,14 +88,14 @@ class _GruFn(Function):
         dG = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev)
         wp = ptr_array(w)
         call("umpr_gru_recurrence_bwd", ptr(d_out), ptr(d_hn), ptr(out), ptr(sv), wp, ptr(plan.buf), plan.n_tiles, plan.n_slabs, R,
-             N, L, ptr(dG))
+             N, L, ptr(dG), work=(2.0 * plan.tokens * 2 * H * 3 * H, 0.0))
         flat = torch.zeros(sum(t.numel() for t in w), dtype=torch.float32, device=dev)
         grads, o = [], 0
         for t in w:
             grads.append(flat[o:o + t.numel()].view_as(t))
             o += t.numel()
         call("umpr_gru_wgrad", ptr(dG), ptr(xp), ptr(out), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, ptr_array(grads),
-             _n_ctas(dev, 2))
+             _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
         return (None, None, None, None, *grads)
 
 
@@ -107,7 +109,8 @@ def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True):
 # --------------------------------------------------------------------------------------------------------------------
 def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=False, bias=None, act=0):
     call("umpr_sgemm", A if isinstance(A, int) else ptr(A), a_strides[0], a_strides[1], B if isinstance(B, int) else ptr(B),
-         b_strides[0], b_strides[1], C if isinstance(C, int) else ptr(C), ldc, M, N, K, splits, int(accumulate), ptr(bias), act)
+         b_strides[0], b_strides[1], C if isinstance(C, int) else ptr(C), ldc, M, N, K, splits, int(accumulate), ptr(bias), act,
+         work=(2.0 * M * N * K, 0.0))
 
 
 def _splits_for(K, device):
@@ -131,7 +134,7 @@ class _CoAttnFn(Function):
         arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
         atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
         call("umpr_coattn_fwd", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(rowkey), ptr(colkey), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
-             ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]))
+             ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=(2.0 * B * P * P * D, 2.0 * B * P * D * 4))
         ctx.save_for_backward(gu, gi, giM, M, soft, arg)
         return soft[0], soft[1], atte[0], atte[1]
 
@@ -146,7 +149,8 @@ class _CoAttnFn(Function):
         dgi = torch.empty_like(gi)
         dgiM = torch.empty_like(gi)
         call("umpr_coattn_bwd", ptr(gu), ptr(gi), ptr(giM), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]),
-             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, ptr(dgu), ptr(dgi), ptr(dgiM))
+             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, ptr(dgu), ptr(dgi), ptr(dgiM),
+             work=(0.0, 6.0 * B * P * D * 4))
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
         sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
         dM = torch.zeros_like(M)
@@ -179,7 +183,8 @@ class _SNetFn(Function):
         self_atte = torch.empty(B, S, D, dtype=torch.float32, device=dev)
         soft = torch.empty(N, L, dtype=torch.float32, device=dev) if train else None
         th = torch.empty(N, L, ATT, dtype=torch.float32, device=dev) if train else None
-        call("umpr_snet_fwd", ptr(x), ptr(Ms), ptr(Ws), N, L, ptr(self_atte), ptr(soft), ptr(th), _n_ctas(dev))
+        call("umpr_snet_fwd", ptr(x), ptr(Ms), ptr(Ws), N, L, ptr(self_atte), ptr(soft), ptr(th), _n_ctas(dev),
+             work=(2.0 * N * L * D * ATT, N * L * 4.0 * (D + (ATT if train else 0))))
         Wd = word_soft.numel() // N
         wsum = torch.empty(N, dtype=torch.float32, device=dev)
         sentiment = torch.empty(B, D, dtype=torch.float32, device=dev)
@@ -203,7 +208,8 @@ class _SNetFn(Function):
         dx = torch.empty_like(x)
         dW = torch.zeros(ATT * D + ATT, dtype=torch.float32, device=dev)
         dMs, dWs = dW[:ATT * D].view(ATT, D), dW[ATT * D:].view(1, ATT)
-        call("umpr_snet_bwd", ptr(x), ptr(th), ptr(soft), ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev))
+        call("umpr_snet_bwd", ptr(x), ptr(th), ptr(soft), ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev),
+             work=(4.0 * N * L * D * ATT, N * L * 4.0 * (2 * D + ATT)))
         d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
         return dx, d_word_soft, None, dMs, dWs
 
@@ -272,7 +278,8 @@ class _CNetTailFn(Function):
         call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
         cfeat = torch.empty(N, KC, dtype=torch.float32, device=dev)
         cidx = torch.empty(N, KC, dtype=torch.int32, device=dev)
-        call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev))
+        call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev),
+             work=(2.0 * N * L * 3 * D * KC, N * L * D * 4.0))
         view_p = torch.empty(B, S, V, dtype=torch.float32, device=dev)
         final = torch.empty(B, V, dtype=torch.float32, device=dev)
         call("umpr_cnet_head_fwd", ptr(cfeat), ptr(lin_w), ptr(lin_b), float(threshold), B, S, V, KC, ptr(view_p), ptr(final))
@@ -297,7 +304,8 @@ class _CNetTailFn(Function):
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
         dx = torch.empty_like(x)
-        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(dx), ptr(d_conv_w), _n_ctas(dev))
+        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(dx), ptr(d_conv_w), _n_ctas(dev),
+             work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
         return dx, None, None, d_conv_w, d_conv_b, d_lin_w, d_lin_b, None
 
 

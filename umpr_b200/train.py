@@ -1,0 +1,94 @@
+"""Train-step body (reference main.py:22-26,32-37) and its data-parallel form (main.py:81-82).
+
+The reference wraps the model in ``torch.nn.DataParallel`` (single process, parameters re-broadcast every step,
+gradients reduced onto GPU 0, Adam on GPU 0).  Here every GPU is its own process holding an identical replica:
+all trainable parameters live in ONE flat fp32 buffer, their gradients in another; a step is
+
+    flat_grad.zero_()  →  forward/backward on this rank's shard  →  all-reduce(flat_grad) over NCCL/NVLink
+    →  fused Adam(+L2 on non-bias tensors) with the 1/world scale folded in  (same update on every rank).
+
+``loss.mean()`` over DataParallel's k replica losses (main.py:34) weights each shard's mean loss by 1/k, which is
+exactly ``sum of shard gradients / k``.  Shards are the ``torch.chunk`` pieces DataParallel's scatter would produce.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import call, ptr
+
+
+class FlatTrainer:
+    def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise RuntimeError("nothing to train")
+        dev = named[0][1].device
+        ALIGN = 64                                                  # floats: every tensor starts on a 256-byte boundary
+        up = lambda k: (k + ALIGN - 1) // ALIGN * ALIGN             # (the kernels use 128-bit loads on some weights)
+        total = sum(up(p.numel()) for _, p in named)
+        self.model, self.names = model, [n for n, _ in named]
+        self.n_params = sum(p.numel() for _, p in named)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.wd = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        o = 0
+        with torch.no_grad():
+            for n, p in named:
+                k = p.numel()
+                self.flat[o:o + k].copy_(p.reshape(-1))
+                p.data = self.flat[o:o + k].view_as(p)          # parameters become views of the flat buffer
+                p.grad = self.grad[o:o + k].view_as(p)          # autograd accumulates straight into the bucket
+                self.wd[o:o + k] = 0.0 if "bias" in n else weight_decay      # main.py:23-24
+                o += up(k)
+        self.lr, self.betas, self.eps, self.lr_decay = lr, betas, eps, lr_decay
+        self.step_no = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def reduce_gradients(self):
+        """One flat bucket (0.57–1.0 MB): latency-bound, so a single NCCL all-reduce is the whole exchange."""
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        self.step_no += 1
+        if self.flat.is_cuda:
+            call("umpr_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.wd), self.flat.numel(),
+                 float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_no, 1.0 / self.world)
+        else:
+            raise RuntimeError("umpr_b200: optimizer runs on the GPU only")
+
+    def end_epoch(self):
+        self.lr *= self.lr_decay                                   # ExponentialLR, main.py:26,54
+
+    def train_step(self, batch):
+        """main.py:32-37 on this rank's shard.  Returns (prediction, loss) of the shard."""
+        self.model.train()
+        self.zero_grad()
+        pred, loss = self.model(*batch)
+        loss.mean().backward()
+        self.reduce_gradients()
+        self.optimizer_step()
+        return pred, loss
+
+
+def shard_batch(batch, rank: int, world: int):
+    """The chunk ``torch.nn.DataParallel``'s scatter hands to replica ``rank`` (``torch.chunk`` along dim 0).
+    Returns None when there are fewer chunks than ranks (e.g. B=9, world=8 → 5 chunks)."""
+    out = []
+    for t in batch:
+        if t.dim() == 0 or t.numel() == 0:
+            out.append(t)
+            continue
+        chunks = torch.chunk(t, world, dim=0)
+        if rank >= len(chunks):
+            return None
+        out.append(chunks[rank])
+    return tuple(out)
