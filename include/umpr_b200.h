@@ -57,6 +57,14 @@ int umpr_gru_wgrad(const float* dG, const float* xp, const float* out, const int
 int umpr_sgemm(const float* A, long ars, long acs, const float* B, long brs, long bcs, float* C, long ldc, int M, int N, int K,
                int splits, int accumulate, const float* bias, int act, void* stream);
 
+/* ---- tcgen05 (5th-gen tensor core) variants: fp32 operands split into 3xBF16 on the fly, fp32 accumulation in TMEM ----
+ * C[m][n] = act(accumulate*C + sum_k A[m*lda+k] * B[n*ldb+k] + bias[n])  ("NT": both operands K-contiguous); act 0|1 tanh|2 relu.
+ * Pointers 16-byte aligned, leading dimensions multiples of 4. */
+int umpr_tc_gemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, int accumulate,
+                    const float* bias, int act, void* stream);
+/* same contract as umpr_gru_inproj, on the tensor cores: one GEMM over every packed token (model.py:19, input half) */
+int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, void* stream);
+
 /* ---- RNet co-attention: src/model.py:50-55.  gu, gi, giM (=gi·M): (B,P,128).  The (P,P) affinity matrix is never
  *      materialised.  rowkey/colkey: (B,P) uint64 scratch, colkey zero-initialised.  t_*: tanh of the row/col maxima,
  *      arg_*: their positions (saved for backward). ---- */
