@@ -61,9 +61,12 @@ int umpr_sgemm(const float* A, long ars, long acs, const float* B, long brs, lon
  * C[m][n] = act(accumulate*C + sum_k A[m*lda+k] * B[n*ldb+k] + bias[n])  ("NT": both operands K-contiguous); act 0|1 tanh|2 relu.
  * Pointers 16-byte aligned, leading dimensions multiples of 4. */
 int umpr_tc_gemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, int accumulate,
-                    const float* bias, int act, void* stream);
+                    const float* bias, int act, int b_kn /* B stored [K][N] instead of [N][K] */, void* stream);
 /* same contract as umpr_gru_inproj, on the tensor cores: one GEMM over every packed token (model.py:19, input half) */
-int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, void* stream);
+int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, int n_ctas, void* stream);
+/* persistent weight-stationary form of umpr_tc_gemm_nt for N <= 128, K <= 128 (B stays in shared memory, A streams) */
+int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, int accumulate,
+                    const float* bias, int act, int b_kn, int n_ctas, void* stream);
 
 /* ---- RNet co-attention: src/model.py:50-55.  gu, gi, giM (=gi·M): (B,P,128).  The (P,P) affinity matrix is never
  *      materialised.  rowkey/colkey: (B,P) uint64 scratch, colkey zero-initialised.  t_*: tanh of the row/col maxima,

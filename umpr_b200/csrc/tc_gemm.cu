@@ -21,6 +21,7 @@ struct TcGemmArgs {
   float* C; long ldc;
   int M, N, K;
   int accumulate, act;
+  int b_kn;              // B given as [K][N] row-major (element (n,k) at B[k*ldb + n]) instead of [N][K]
   const float* bias;
   // INPROJ
   const float* w_ih[2]; const float* b_ih[2]; const float* b_hh[2];
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_nt_kernel(const TcGemmA
         float4 vb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int idx = (h * 8 + i) * 128 + tid, r = idx >> 4, k = (idx & 15) * 4;
+          int idx = (h * 8 + i) * 128 + tid, r = idx >> 4, k = (idx & 15) * 4;
+          if (MODE == 0 && a.b_kn) { r = h * 64 + (tid & 63); k = ((tid >> 6) * 8 + i) * 4; }   // lanes along n: coalesced
           const int n = n0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (n < a.N) {
@@ -107,6 +109,12 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_nt_kernel(const TcGemmA
                 t[q] = kk < a.E ? w[kk] : (kk == a.E ? a.b_ih[dir][n] + (n < 2 * H ? a.b_hh[dir][n] : 0.f) : 0.f);
               }
               v = make_float4(t[0], t[1], t[2], t[3]);
+            } else if (a.b_kn) {
+              const float* p = a.B + (long)(k0 + k) * a.ldb + n;
+              if (k0 + k < a.K) v.x = p[0];
+              if (k0 + k + 1 < a.K) v.y = p[a.ldb];
+              if (k0 + k + 2 < a.K) v.z = p[2 * a.ldb];
+              if (k0 + k + 3 < a.K) v.w = p[3 * a.ldb];
             } else {
               const float* p = a.B + (long)n * a.ldb + k0 + k;
               if (k0 + k + 3 < a.K) v = *reinterpret_cast<const float4*>(p);
@@ -121,8 +129,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_nt_kernel(const TcGemmA
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int idx = (h * 8 + i) * 128 + tid;
-          store_split4(b_hi, b_lo, idx >> 4, (idx & 15) * 4, vb[i]);
+          int idx = (h * 8 + i) * 128 + tid, r = idx >> 4, k = (idx & 15) * 4;
+          if (MODE == 0 && a.b_kn) { r = h * 64 + (tid & 63); k = ((tid >> 6) * 8 + i) * 4; }
+          store_split4(b_hi, b_lo, r, k, vb[i]);
         }
       }
       fence_async_smem();            // make the generic-proxy stores visible to the tensor core (async proxy)
@@ -213,7 +222,7 @@ template <int BN, int MODE> static int launch_tc(const TcGemmArgs& a, dim3 grid,
 using namespace umpr;
 
 extern "C" int umpr_tc_gemm_nt(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K,
-                               int accumulate, const float* bias, int act, void* stream) {
+                               int accumulate, const float* bias, int act, int b_kn, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda & 3) || (ldb & 3) || (ldc & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) ||
       (reinterpret_cast<uintptr_t>(C) & 15))
@@ -221,21 +230,10 @@ extern "C" int umpr_tc_gemm_nt(const float* A, long lda, const float* B, long ld
   if (act < 0 || act > 2) return fail_arg("tc_gemm_nt: act=%d", act);
   TcGemmArgs a{};
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-  a.accumulate = accumulate; a.act = act; a.bias = bias;
+  a.accumulate = accumulate; a.act = act; a.bias = bias; a.b_kn = b_kn;
   const int gm = (M + TG_BM - 1) / TG_BM;
   if (N <= 64) return launch_tc<64, 0>(a, dim3(gm, 1, 1), (cudaStream_t)stream);
   if (N <= 128) return launch_tc<128, 0>(a, dim3(gm, 1, 1), (cudaStream_t)stream);
   return launch_tc<128, 0>(a, dim3(gm, (N + 127) / 128, 1), (cudaStream_t)stream);
 }
 
-// tensor-core variant of umpr_gru_inproj (same arguments, same output layout)
-extern "C" int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, void* stream) {
-  if (E < 1 || E >= KP) return fail_arg("gru_inproj: E=%d", E);
-  if (R != 32 && R != 64 && R != 128) return fail_arg("gru_inproj: R=%d", R);
-  if (n_slabs == 0) return 0;
-  TcGemmArgs a{};
-  a.A = xp; a.lda = KP; a.C = G; a.M = n_slabs * R; a.N = G3; a.K = KP; a.E = E; a.R = R;
-  a.w_ih[0] = w[0]; a.b_ih[0] = w[2]; a.b_hh[0] = w[3];
-  a.w_ih[1] = w[4]; a.b_ih[1] = w[6]; a.b_hh[1] = w[7];
-  return launch_tc<192, 1>(a, dim3((a.M + TG_BM - 1) / TG_BM, 1, 2), (cudaStream_t)stream);
-}

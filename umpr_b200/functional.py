@@ -61,7 +61,7 @@ class _GruFn(Function):
         N, L, R = plan.N, plan.L, plan.R
         G = torch.empty(plan.n_slabs * 2 * R * 3 * H, dtype=torch.float32, device=dev)
         wp = ptr_array(w)
-        call("umpr_gru_inproj", ptr(xp), wp, plan.n_slabs, R, E, ptr(G), work=(2.0 * plan.tokens * E * 6 * H, 0.0))
+        call("umpr_gru_inproj_tc", ptr(xp), wp, plan.n_slabs, R, E, ptr(G), _n_ctas(dev), work=(2.0 * plan.tokens * E * 6 * H, 0.0))
         out = torch.empty(N, L, D, dtype=torch.float32, device=dev)
         hn = torch.empty(2, N, H, dtype=torch.float32, device=dev) if want_hidden else None
         need_grad = any(ctx.needs_input_grad[4:])
@@ -108,9 +108,28 @@ def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True):
 # strided GEMM helper
 # --------------------------------------------------------------------------------------------------------------------
 def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=False, bias=None, act=0):
-    call("umpr_sgemm", A if isinstance(A, int) else ptr(A), a_strides[0], a_strides[1], B if isinstance(B, int) else ptr(B),
-         b_strides[0], b_strides[1], C if isinstance(C, int) else ptr(C), ldc, M, N, K, splits, int(accumulate), ptr(bias), act,
-         work=(2.0 * M * N * K, 0.0))
+    """C = act(acc*C + A·B + bias) with strided operands.  Dense "row-major A times K- or N-contiguous B" products run on
+    the tensor cores (tcgen05, 3xBF16 split); split-K reductions and odd strides use the CUDA-core kernel."""
+    pa = A if isinstance(A, int) else ptr(A)
+    pb = B if isinstance(B, int) else ptr(B)
+    pc = C if isinstance(C, int) else ptr(C)
+    work = (2.0 * M * N * K, 0.0)
+    aligned = not ((pa | pb | pc) & 15) and a_strides[1] == 1 and not (a_strides[0] & 3) and not (ldc & 3)
+    if aligned and splits == 1 and act in (0, 1, 2) and M >= 64:
+        b_kn = -1
+        if b_strides[0] == 1 and not (b_strides[1] & 3):          # B[N][K]
+            b_kn, ldb = 0, b_strides[1]
+        elif b_strides[1] == 1 and not (b_strides[0] & 3):        # B[K][N]
+            b_kn, ldb = 1, b_strides[0]
+        if b_kn >= 0:
+            if N <= 128 and K <= 128 and not (N & 3) and M >= 1024:   # weights stay in shared memory, A streams
+                call("umpr_tc_gemm_ws", pa, a_strides[0], pb, ldb, pc, ldc, M, N, K, int(accumulate), ptr(bias), act, b_kn,
+                     _lib.sm_count(torch.cuda.current_device()), work=work)
+            else:
+                call("umpr_tc_gemm_nt", pa, a_strides[0], pb, ldb, pc, ldc, M, N, K, int(accumulate), ptr(bias), act, b_kn, work=work)
+            return
+    call("umpr_sgemm", pa, a_strides[0], a_strides[1], pb, b_strides[0], b_strides[1], pc, ldc, M, N, K, splits, int(accumulate),
+         ptr(bias), act, work=work)
 
 
 def _splits_for(K, device):
