@@ -74,6 +74,10 @@ int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ldb, float* C
 int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, int P, unsigned long long* rowkey,
                     unsigned long long* colkey, float* soft_u, float* soft_i, float* t_u, float* t_i, int32_t* arg_u,
                     int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
+/* tensor-core form of umpr_coattn_fwd: two tcgen05 products per tile pair (S and S^T) so row and column maxima are per-thread
+ * scans; near-tied maxima are re-scored with exact fp32 dot products.  scratch: 32*B*P*(1+ceil(P/128)) bytes. */
+int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, void* scratch, float* soft_u, float* soft_i,
+                       float* t_u, float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
 /* dgu, dgi (without the dgiM·M^T term), dgiM: (B,P,128) fully written.  d_* inputs may be NULL. */
 int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i, const float* t_u,
                     const float* t_i, const int32_t* arg_u, const int32_t* arg_i, const float* d_soft_u, const float* d_soft_i,

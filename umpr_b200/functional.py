@@ -13,6 +13,7 @@ from ._lib import call, ptr, ptr_array
 from .plan import PackPlan
 
 H, D, ATT, KP, SV = 64, 128, 64, 64, 256
+TENSOR_CORE_COATTN = False     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
 def _f32(t):
@@ -147,13 +148,20 @@ class _CoAttnFn(Function):
         dev = gu.device
         giM = torch.empty_like(gi)
         sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D)
-        rowkey = torch.empty(B * P, dtype=torch.int64, device=dev)
-        colkey = torch.zeros(B * P, dtype=torch.int64, device=dev)
         soft = torch.empty(4, B, P, dtype=torch.float32, device=dev)       # soft_u, soft_i, t_u, t_i
         arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
         atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
-        call("umpr_coattn_fwd", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(rowkey), ptr(colkey), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
-             ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=(2.0 * B * P * P * D, 2.0 * B * P * D * 4))
+        work = (2.0 * B * P * P * D, 2.0 * B * P * D * 4)
+        if TENSOR_CORE_COATTN:
+            n_it = (P + 127) // 128
+            scratch = torch.empty(8 * B * P * (1 + n_it), dtype=torch.float32, device=dev)
+            call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(scratch), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
+                 ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
+        else:
+            rowkey = torch.empty(B * P, dtype=torch.int64, device=dev)
+            colkey = torch.zeros(B * P, dtype=torch.int64, device=dev)
+            call("umpr_coattn_fwd", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(rowkey), ptr(colkey), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
+                 ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
         ctx.save_for_backward(gu, gi, giM, M, soft, arg)
         return soft[0], soft[1], atte[0], atte[1]
 
