@@ -97,6 +97,11 @@ int umpr_snet_bwd(const float* x, const float* th, const float* soft, const floa
 int umpr_cnet_prep(const float* conv_w /*(KC,128,3)*/, int KC, int ksize, float* wt /*(384,128)*/, void* stream);
 int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int N, int L, int KC, float* cfeat /*(N,KC)*/,
                        int32_t* cidx /*(N,KC) arg-max position, -1 if clipped by ReLU*/, int n_ctas, void* stream);
+/* tensor-core form of umpr_cnet_prep + umpr_cnet_conv_fwd (implicit GEMM on tcgen05, weights streamed by bulk copies); maxima
+ * that are near-tied (or next to the ReLU threshold) are re-scored in exact fp32 because the arg-max routes the gradient.
+ * scratch: 197632 + 16*cap bytes, 16-byte aligned; cap = capacity of the re-scoring worklist */
+int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize, void* scratch,
+                          int cap, float* cfeat, int32_t* cidx, int n_ctas, void* stream);
 int umpr_cnet_head_fwd(const float* cfeat, const float* lin_w, const float* lin_b, float threshold, int B, int S, int V, int KC,
                        float* view_p /*(B,S,V)*/, float* final_repr /*(B,V)*/, void* stream);
 int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* view_p, const float* lin_w, const float* d_view_p,

@@ -13,6 +13,7 @@ from ._lib import call, ptr, ptr_array
 from .plan import PackPlan
 
 H, D, ATT, KP, SV = 64, 128, 64, 64, 256
+TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
 TENSOR_CORE_COATTN = False     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
@@ -301,12 +302,18 @@ class _CNetTailFn(Function):
         dev = x.device
         if cin != D:
             raise RuntimeError("umpr_b200: CNet conv is built for in_channels=128")
-        wt = torch.empty(3 * D * 128, dtype=torch.float32, device=dev)
-        call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
         cfeat = torch.empty(N, KC, dtype=torch.float32, device=dev)
         cidx = torch.empty(N, KC, dtype=torch.int32, device=dev)
-        call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev),
-             work=(2.0 * N * L * 3 * D * KC, N * L * D * 4.0))
+        work = (2.0 * N * L * 3 * D * KC, N * L * D * 4.0)
+        if TENSOR_CORE_CONV:
+            cap = max(4096, N * KC // 8)
+            scratch = torch.empty((197632 + 16 * cap) // 4, dtype=torch.float32, device=dev)
+            call("umpr_cnet_conv_fwd_tc", ptr(x), ptr(conv_w), ptr(conv_b), N, L, KC, ks, ptr(scratch), cap, ptr(cfeat), ptr(cidx),
+                 _n_ctas(dev), work=work)
+        else:
+            wt = torch.empty(3 * D * 128, dtype=torch.float32, device=dev)
+            call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
+            call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev), work=work)
         view_p = torch.empty(B, S, V, dtype=torch.float32, device=dev)
         final = torch.empty(B, V, dtype=torch.float32, device=dev)
         call("umpr_cnet_head_fwd", ptr(cfeat), ptr(lin_w), ptr(lin_b), float(threshold), B, S, V, KC, ptr(view_p), ptr(final))
