@@ -51,6 +51,10 @@ int umpr_gru_recurrence_bwd(const float* d_out, const float* d_hn, const float* 
 int umpr_gru_wgrad(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int R,
                    int L, int E, float* const* dw, int n_ctas, void* stream);
 
+/* tensor-core form of umpr_gru_wgrad (tcgen05 with MN-major operands, TMEM accumulation over each CTA's slot range) */
+int umpr_gru_wgrad_tc(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int R,
+                      int L, int E, float* const* dw, int n_ctas, void* stream);
+
 /* ---- generic strided fp32 GEMM: gi·M (model.py:50), text matching (model.py:168) and their gradients ----
  * C[m][n] = act(accumulate*C + sum_k A[m*ars+k*acs] * B[k*brs+n*bcs] + bias[n]); act 0 none, 1 tanh, 2 relu, 3 sigmoid.
  * splits > 1: split-K with atomic accumulation into C (C must be initialised; bias/act not allowed). */

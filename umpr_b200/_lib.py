@@ -23,6 +23,7 @@ SIGNATURES = {
     "umpr_gru_recurrence_fwd": [P, P, P, I, I, I, I, I, P, P, P, P],
     "umpr_gru_recurrence_bwd": [P, P, P, P, P, P, I, I, I, I, I, P, P],
     "umpr_gru_wgrad": [P, P, P, P, I, I, I, I, I, P, I, P],
+    "umpr_gru_wgrad_tc": [P, P, P, P, I, I, I, I, I, P, I, P],
     "umpr_sgemm": [P, L, L, P, L, L, P, L, I, I, I, I, I, P, I, P],
     "umpr_tc_gemm_nt": [P, L, P, L, P, L, I, I, I, I, P, I, I, P],
     "umpr_gru_inproj_tc": [P, P, I, I, I, P, I, P],

@@ -184,43 +184,55 @@ __global__ void __launch_bounds__(128) cnet_head_bwd_kernel(const float* __restr
   }
 }
 
-// dx[n][l][c] = sum_{kf, dt : arg[kf] + dt - 1 == l} g[kf] W[kf][c][dt].   Thread (q, c) keeps its 32x3 weights in registers.
-__global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dx_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
-                                                                  const float* __restrict__ w, int N, int L, int KC,
-                                                                  float* __restrict__ dx) {
+// dx[n][l][c] = sum_{kf, dt : arg[kf] + dt - 1 == l} g[kf] W[kf][c][dt].   Thread (q, c) keeps its 32x3 weights in registers and
+// owns column c of its own shared-memory copy q of the sentence gradient (plain read-modify-write, no atomics: shared-memory
+// float atomics are CAS loops on this architecture); the NQ copies are summed on the way out.
+template <int NQ>
+__global__ void __launch_bounds__(128 * NQ, 1) cnet_conv_bwd_dx_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
+                                                                       const float* __restrict__ w, int N, int L, int KC,
+                                                                       float* __restrict__ dx) {
   extern __shared__ __align__(16) float smem[];
-  float* dxs = smem;                       // [(L+2)][128]
-  float* gsm = dxs + (L + 2) * D;          // [128]
+  constexpr int NT = 128 * NQ, FPQ = 128 / NQ;     // filters per group
+  const int rows = L + 2;
+  float* dxs = smem;                               // [NQ][(L+2)][128]
+  float* gsm = dxs + NQ * rows * D;                // [128]
   int* tsm = reinterpret_cast<int*>(gsm + CKP);
   const int tid = threadIdx.x, q = tid >> 7, c = tid & 127;
-  float wr[32][CK];
+  float wr[FPQ][CK];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int kf = q * 32 + i;
+  for (int i = 0; i < FPQ; ++i) {
+    const int kf = q * FPQ + i;
 #pragma unroll
     for (int dt = 0; dt < CK; ++dt) wr[i][dt] = kf < KC ? w[((size_t)kf * D + c) * CK + dt] : 0.f;
   }
+  float* mine = dxs + q * rows * D + c;
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
     __syncthreads();
-    for (int idx = tid; idx < (L + 2) * D; idx += 512) dxs[idx] = 0.f;
+    for (int r = 0; r < rows; ++r) mine[r * D] = 0.f;
     if (tid < CKP) {
       gsm[tid] = tid < KC ? dcfeat[(size_t)n * KC + tid] : 0.f;
       tsm[tid] = tid < KC ? cidx[(size_t)n * KC + tid] : -1;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float g = gsm[q * 32 + i];
-      const int t = tsm[q * 32 + i];
+    for (int i = 0; i < FPQ; ++i) {
+      const float g = gsm[q * FPQ + i];
+      const int t = tsm[q * FPQ + i];
       if (g != 0.f && t >= 0) {          // warp-uniform
 #pragma unroll
-        for (int dt = 0; dt < CK; ++dt) atomicAdd(&dxs[(t + dt) * D + c], g * wr[i][dt]);   // x position t+dt-1 -> guard row +1
+        for (int dt = 0; dt < CK; ++dt) mine[(t + dt) * D] += g * wr[i][dt];     // x position t+dt-1 -> guard row +1
       }
     }
     __syncthreads();
-    for (int idx = tid; idx < L * (D / 4); idx += 512) {
+    for (int idx = tid; idx < L * (D / 4); idx += NT) {
       const int l = idx >> 5, c4 = idx & 31;
-      *reinterpret_cast<float4*>(dx + ((size_t)n * L + l) * D + c4 * 4) = *reinterpret_cast<const float4*>(&dxs[(l + 1) * D + c4 * 4]);
+      float4 a = *reinterpret_cast<const float4*>(&dxs[(l + 1) * D + c4 * 4]);
+#pragma unroll
+      for (int qq = 1; qq < NQ; ++qq) {
+        const float4 b = *reinterpret_cast<const float4*>(&dxs[(qq * rows + l + 1) * D + c4 * 4]);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      *reinterpret_cast<float4*>(dx + ((size_t)n * L + l) * D + c4 * 4) = a;
     }
   }
 }
@@ -323,11 +335,18 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
   if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
   const size_t sm = sizeof(float) * ((L + 2) * D + CKP) + sizeof(int) * CKP;
   if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd: L=%d too large", L);
-  cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  cudaFuncSetAttribute(cnet_conv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   const int grid = n_ctas > 0 && n_ctas < N ? n_ctas : N;
-  cnet_conv_bwd_dx_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
+  const size_t sm4 = sizeof(float) * (4 * (L + 2) * D + CKP) + sizeof(int) * CKP;
+  const size_t sm2 = sizeof(float) * (2 * (L + 2) * D + CKP) + sizeof(int) * CKP;
+  if (sm4 <= 200 * 1024) {
+    cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+    cnet_conv_bwd_dx_kernel<4><<<grid, 512, sm4, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
+  } else {
+    cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    cnet_conv_bwd_dx_kernel<2><<<grid, 256, sm2, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
+  }
   if (int e = check_launch("cnet_conv_bwd_dx")) return e;
+  cudaFuncSetAttribute(cnet_conv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   cnet_conv_bwd_dw_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(x, dcfeat, cidx, N, L, KC, d_conv_w);
   return check_launch("cnet_conv_bwd_dw");
 }

@@ -1,0 +1,207 @@
+// GRU weight gradients on the tensor cores (backward of reference src/model.py:19; main.py:36):
+//   C[256][128] = sum over all packed token slots of dG[slot][256]^T · [xp[slot][64] | h_prev[slot][64]]
+// Both operands are "MN-major" (the reduction index - the token slot - is the slow index in memory), which tcgen05 consumes
+// directly: shared-memory tiles hold, per slot k, 64 contiguous m (or n) elements per 128-byte row, 8 slots per 1024-byte
+// SWIZZLE_128B atom, atoms of consecutive slots SBO = 1024 B apart, the next 64 elements of m/n LBO = 8192 B apart.
+// Persistent CTAs own a contiguous range of slots; 64 slots per pipeline stage; the two 128-row halves of C accumulate in
+// TMEM over the whole range and are flushed once with atomics into the eight nn.GRU gradient tensors.
+//   warps 0-7 loaders (fp32 -> bf16 hi/lo, h_prev gathered from the GRU output), warp 8 MMA issuer, warps 0-3 epilogue.
+#include "common.cuh"
+#include "tc.cuh"
+#include "../../include/umpr_b200.h"
+
+namespace umpr {
+using namespace tc;
+
+constexpr int WT_THREADS = 288;
+constexpr int WT_TILE = 128 * 128;              // bytes: [2 chunks][8 atoms][8 slots][128 B] = 64 slots x 128 elements of bf16
+constexpr int WT_STAGE = 6 * WT_TILE;           // A_top hi/lo, A_bot hi/lo, B hi/lo
+constexpr int WT_NSTAGE = 2;
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+  // MN-major SWIZZLE_128B: LBO (next 64 elements of M/N) = 8192 B, SBO (next 8 k) = 1024 B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// byte offset of elements (mn..mn+3, k) inside a 64-slot x 128-element MN-major tile
+__device__ __forceinline__ uint32_t mn_off(int mn, int k) {
+  const int i2 = mn >> 6, mi = mn & 63, i1 = mi >> 3, i0 = mi & 7, j1 = k >> 3, j0 = k & 7;
+  return (uint32_t)(i2 * 8192 + j1 * 1024 + j0 * 128 + (((i1 ^ j0) << 4) | (i0 << 1)));
+}
+__device__ __forceinline__ void store_split4_mn(unsigned char* hi, unsigned char* lo, int mn, int k, float4 v) {
+  uint32_t h0, l0, h1, l1;
+  split2(v.x, v.y, h0, l0);
+  split2(v.z, v.w, h1, l1);
+  const uint32_t off = mn_off(mn, k);
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(lo + off) = make_uint2(l0, l1);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float* __restrict__ dG, const float* __restrict__ xp,
+                                                                     const float* __restrict__ out, Plan p, int L, int E, int slots_per_cta,
+                                                                     float* __restrict__ dw_ih_f, float* __restrict__ dw_hh_f,
+                                                                     float* __restrict__ db_ih_f, float* __restrict__ db_hh_f,
+                                                                     float* __restrict__ dw_ih_b, float* __restrict__ dw_hh_b,
+                                                                     float* __restrict__ db_ih_b, float* __restrict__ db_hh_b) {
+  extern __shared__ unsigned char raw[];
+  __shared__ uint64_t full_bar[WT_NSTAGE], empty_bar[WT_NSTAGE], acc_bar;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y, R = p.R;
+  const int n_flat = p.n_slabs * R;
+  const int f_beg = blockIdx.x * slots_per_cta, f_end = min(n_flat, f_beg + slots_per_cta);
+  const int n_steps = (f_end - f_beg + 63) / 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < WT_NSTAGE; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ loaders
+    for (int st = 0; st < n_steps; ++st) {
+      const int s = st % WT_NSTAGE;
+      if (st >= WT_NSTAGE) mbar_wait(&empty_bar[s], ((st / WT_NSTAGE) - 1) & 1);
+      unsigned char* sb = base + s * WT_STAGE;
+      const int f0 = f_beg + st * 64;
+      // dG rows: 64 slots x 256 floats (top half m<128 -> tiles 0/1, bottom half -> tiles 2/3)
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid, k = idx >> 5, m = (idx & 31) * 4;      // 32 float4 per 128-float half row
+          const int f = f0 + k;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < f_end) {
+            const int sl = f / R, r = f - sl * R;
+            v[i] = *reinterpret_cast<const float4*>(dG + (((size_t)sl * 2 + dir) * R + r) * SV + half * 128 + m);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid;
+          store_split4_mn(sb + (half * 2) * WT_TILE, sb + (half * 2 + 1) * WT_TILE, (idx & 31) * 4, idx >> 5, v[i]);
+        }
+      }
+      // B rows: [xp (64) | h_prev (64)]
+      {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid, k = idx >> 5, n = (idx & 31) * 4;
+          const int f = f0 + k;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f < f_end) {
+            const int sl = f / R, r = f - sl * R;
+            if (n < KP) {
+              v[i] = *reinterpret_cast<const float4*>(xp + ((size_t)sl * R + r) * KP + n);
+            } else {
+              const int j = p.slab_tile[sl], t = sl - p.tile_off[j], kj = j * R + r;
+              const int rw = p.row_of[kj], tp = dir ? t + 1 : t - 1;
+              if (rw >= 0 && tp >= 0 && tp < p.len_of[kj])
+                v[i] = *reinterpret_cast<const float4*>(out + ((size_t)rw * L + tp) * D + dir * H + (n - KP));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid;
+          store_split4_mn(sb + 4 * WT_TILE, sb + 5 * WT_TILE, (idx & 31) * 4, idx >> 5, v[i]);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&full_bar[s]);
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);     // A and B are MN-major
+    for (int st = 0; st < n_steps; ++st) {
+      const int s = st % WT_NSTAGE;
+      mbar_wait(&full_bar[s], (st / WT_NSTAGE) & 1);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(base + s * WT_STAGE);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t ko = kk * 2048;           // 16 slots = two 1024-byte atoms
+        const uint64_t bh = smem_desc_mn_sw128(sb + 4 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 5 * WT_TILE + ko);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t ah = smem_desc_mn_sw128(sb + (half * 2) * WT_TILE + ko), al = smem_desc_mn_sw128(sb + (half * 2 + 1) * WT_TILE + ko);
+          const uint32_t d = tmem + half * 128;
+          umma_bf16(d, ah, bh, idesc, (st | kk) != 0);
+          umma_bf16(d, ah, bl, idesc, 1);
+          umma_bf16(d, al, bh, idesc, 1);
+        }
+      }
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(&acc_bar);
+  }
+  __syncwarp();
+  if (warp < 4 && n_steps > 0) {
+    // ------------------------------------------------------------------ epilogue: flush the two accumulator halves
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* dw_ih = dir ? dw_ih_b : dw_ih_f;
+    float* dw_hh = dir ? dw_hh_b : dw_hh_f;
+    float* db_ih = dir ? db_ih_b : db_ih_f;
+    float* db_hh = dir ? db_hh_b : db_hh_f;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int g = half * 128 + warp * 32 + lane;          // 0..255 : dr, dz, dn, dn*r
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 128 + c0, v);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int col = c0 + c;
+          if (col < KP) {
+            if (g < G3) {
+              if (col < E) atomicAdd(&dw_ih[g * E + col], v[c]);
+              else if (col == E) { atomicAdd(&db_ih[g], v[c]); if (g < 2 * H) atomicAdd(&db_hh[g], v[c]); }
+            } else if (col == E) {
+              atomicAdd(&db_hh[g - H], v[c]);
+            }
+          } else {
+            const int hc = col - KP;
+            if (g < 2 * H) atomicAdd(&dw_hh[g * H + hc], v[c]);
+            else if (g >= G3) atomicAdd(&dw_hh[(g - H) * H + hc], v[c]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace umpr
+
+using namespace umpr;
+
+extern "C" int umpr_gru_wgrad_tc(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs,
+                                 int R, int L, int E, float* const* dw, int n_ctas, void* stream) {
+  if (n_slabs == 0) return 0;
+  if (R != 32 && R != 64 && R != 128) return fail_arg("gru_wgrad_tc: R=%d", R);
+  Plan p = make_plan(plan, n_tiles, n_slabs, R);
+  const int n_flat = n_slabs * R;
+  if (n_ctas < 2) n_ctas = 2;
+  int per = (n_flat + n_ctas / 2 - 1) / (n_ctas / 2);
+  per = ((per + 63) / 64) * 64;
+  const int grid = (n_flat + per - 1) / per;
+  const int smem = WT_NSTAGE * WT_STAGE + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gru_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("gru_wgrad_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
+  gru_wgrad_tc_kernel<<<dim3(grid, 2), WT_THREADS, smem, (cudaStream_t)stream>>>(dG, xp, out, p, L, E, per, dw[0], dw[1], dw[2], dw[3], dw[4],
+                                                                                dw[5], dw[6], dw[7]);
+  return check_launch("gru_wgrad_tc");
+}

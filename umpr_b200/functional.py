@@ -13,6 +13,7 @@ from ._lib import call, ptr, ptr_array
 from .plan import PackPlan
 
 H, D, ATT, KP, SV = 64, 128, 64, 64, 256
+TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
 TENSOR_CORE_COATTN = False     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
@@ -96,7 +97,7 @@ class _GruFn(Function):
         for t in w:
             grads.append(flat[o:o + t.numel()].view_as(t))
             o += t.numel()
-        call("umpr_gru_wgrad", ptr(dG), ptr(xp), ptr(out), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, ptr_array(grads),
+        call("umpr_gru_wgrad_tc" if TENSOR_CORE_WGRAD else "umpr_gru_wgrad", ptr(dG), ptr(xp), ptr(out), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, ptr_array(grads),
              _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
         return (None, None, None, None, *grads)
 
