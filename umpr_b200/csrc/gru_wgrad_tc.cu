@@ -70,50 +70,54 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float
       if (st >= WT_NSTAGE) mbar_wait(&empty_bar[s], ((st / WT_NSTAGE) - 1) & 1);
       unsigned char* sb = base + s * WT_STAGE;
       const int f0 = f_beg + st * 64;
-      // dG rows: 64 slots x 256 floats (top half m<128 -> tiles 0/1, bottom half -> tiles 2/3)
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        float4 v[8];
+      // thread (warp w, lane): slots k = i*8 + w (i = 0..7), elements lane*4..+3 of each 128-wide half row; the swizzled
+      // destination is a per-thread constant plus i*1024 (k>>3 == i, k&7 == w)
+      const int m = lane * 4;
+      const uint32_t off0 = mn_off(m, warp);
+      const float* gsrc[8];
+      const float* xsrc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = i * 256 + tid, k = idx >> 5, m = (idx & 31) * 4;      // 32 float4 per 128-float half row
-          const int f = f0 + k;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (f < f_end) {
-            const int sl = f / R, r = f - sl * R;
-            v[i] = *reinterpret_cast<const float4*>(dG + (((size_t)sl * 2 + dir) * R + r) * SV + half * 128 + m);
+      for (int i = 0; i < 8; ++i) {
+        const int f = f0 + i * 8 + warp;
+        gsrc[i] = nullptr; xsrc[i] = nullptr;
+        if (f < f_end) {
+          const int sl = f / R, r = f - sl * R;
+          gsrc[i] = dG + (((size_t)sl * 2 + dir) * R + r) * SV + m;
+          if (m < KP) {
+            xsrc[i] = xp + ((size_t)sl * R + r) * KP + m;
+          } else {
+            const int j = p.slab_tile[sl], t = sl - p.tile_off[j], kj = j * R + r;
+            const int rw = p.row_of[kj], tp = dir ? t + 1 : t - 1;
+            if (rw >= 0 && tp >= 0 && tp < p.len_of[kj]) xsrc[i] = out + ((size_t)rw * L + tp) * D + dir * H + (m - KP);
           }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = i * 256 + tid;
-          store_split4_mn(sb + (half * 2) * WT_TILE, sb + (half * 2 + 1) * WT_TILE, (idx & 31) * 4, idx >> 5, v[i]);
         }
       }
-      // B rows: [xp (64) | h_prev (64)]
-      {
-        float4 v[8];
+      float4 v[8];
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {                 // dG rows: top half (dr, dz) then bottom half (dn, dn*r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gsrc[i] ? *reinterpret_cast<const float4*>(gsrc[i] + half * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char* hi = sb + (half * 2) * WT_TILE + off0, *lo = hi + WT_TILE;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int idx = i * 256 + tid, k = idx >> 5, n = (idx & 31) * 4;
-          const int f = f0 + k;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (f < f_end) {
-            const int sl = f / R, r = f - sl * R;
-            if (n < KP) {
-              v[i] = *reinterpret_cast<const float4*>(xp + ((size_t)sl * R + r) * KP + n);
-            } else {
-              const int j = p.slab_tile[sl], t = sl - p.tile_off[j], kj = j * R + r;
-              const int rw = p.row_of[kj], tp = dir ? t + 1 : t - 1;
-              if (rw >= 0 && tp >= 0 && tp < p.len_of[kj])
-                v[i] = *reinterpret_cast<const float4*>(out + ((size_t)rw * L + tp) * D + dir * H + (n - KP));
-            }
-          }
+          uint32_t h0, l0, h1, l1;
+          split2(v[i].x, v[i].y, h0, l0);
+          split2(v[i].z, v[i].w, h1, l1);
+          *reinterpret_cast<uint2*>(hi + i * 1024) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(lo + i * 1024) = make_uint2(l0, l1);
         }
+      }
+      {                                                       // B rows: [xp (64) | h_prev (64)]
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = xsrc[i] ? *reinterpret_cast<const float4*>(xsrc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char* hi = sb + 4 * WT_TILE + off0, *lo = hi + WT_TILE;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int idx = i * 256 + tid;
-          store_split4_mn(sb + 4 * WT_TILE, sb + 5 * WT_TILE, (idx & 31) * 4, idx >> 5, v[i]);
+          uint32_t h0, l0, h1, l1;
+          split2(v[i].x, v[i].y, h0, l0);
+          split2(v[i].z, v[i].w, h1, l1);
+          *reinterpret_cast<uint2*>(hi + i * 1024) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(lo + i * 1024) = make_uint2(l0, l1);
         }
       }
       fence_async_smem();

@@ -128,10 +128,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 // ---- fp32 -> (bf16 hi, bf16 lo) split and swizzled store -----------------------------------------------
 // pack two floats' hi parts / lo parts into one 32-bit word each (element 0 in the low half)
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+  // one packed convert per pair (cvt.rn.bf16x2.f32), bf16 -> fp32 is a shift / mask
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // byte offset of element k (0..63, multiple of 4 here) of row r inside a [rows][64 bf16] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int k) {
