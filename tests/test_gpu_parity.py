@@ -195,3 +195,50 @@ def test_error_behaviour():
     m = syn.build_model("music_small_r", syn.make_table(100), device="cpu")
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(*syn.make_batch("music_small_r", 2, vocab=100))
+
+
+def test_two_shard_step_matches_chunked_oracle():
+    """SURVEY.md §8e parity check on one GPU: each DataParallel chunk alone == oracle on that chunk (own sort, global L),
+    and the bucket sum / k == mean over chunks of the oracle gradients; then the fused Adam equals torch.optim.Adam."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.train import FlatTrainer, shard_batch
+    table = syn.make_table(3000, seed=9)
+    batch = syn.make_batch("music_small_r", 11, vocab=3000, seed=10)
+    m = syn.build_model("music_small_r", table, seed=4, device=DEV)
+    with torch.no_grad():
+        m.review_net.r_net.M.mul_(0.05)
+    params = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    tr = FlatTrainer(m, lr=1e-2, weight_decay=1e-3)
+    tr.zero_grad()
+    ref = {}
+    k_shards = 2
+    for r in range(k_shards):
+        shard = shard_batch(batch, r, k_shards)
+        assert shard[0].shape[0] == (6 if r == 0 else 5)
+        pred, loss = m(*shard)
+        loss.backward()                                             # accumulates into the flat bucket, like the all-reduce sum
+        p_ref, l_ref, g_ref = orc.umpr_loss_and_grads(params, shard, review_net_only=True)
+        assert_close(pred, p_ref, TOL, f"pred shard {r}")
+        assert_close(loss, l_ref, TOL, f"loss shard {r}")
+        for k, g in g_ref.items():
+            ref[k] = ref.get(k, 0) + g / k_shards
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            _check_grad(k, p.grad / k_shards, ref[k])
+    # one optimizer step on the averaged gradient vs torch.optim.Adam with the reference's parameter groups (main.py:22-25)
+    # (Adam divides by |g|: feed both sides the SAME averaged gradient so the kernel, not the conditioning, is what is tested)
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if p.requires_grad:
+                p.grad.copy_(ref[k].to(DEV) * k_shards)
+    tr.world = k_shards
+    tr.optimizer_step()
+    tp = {k: v.clone().requires_grad_(True) for k, v in params.items() if k != "embedding.weight"}
+    opt = torch.optim.Adam([{"params": [v for k, v in tp.items() if "bias" not in k]},
+                            {"params": [v for k, v in tp.items() if "bias" in k], "weight_decay": 0.0}], 1e-2, weight_decay=1e-3)
+    for k, v in tp.items():
+        v.grad = ref[k].clone()
+    opt.step()
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            assert_close(p.detach(), tp[k].detach(), 2e-5, "adam " + k)
