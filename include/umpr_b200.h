@@ -55,6 +55,23 @@ int umpr_gru_wgrad(const float* dG, const float* xp, const float* out, const int
 int umpr_gru_wgrad_tc(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int R,
                       int L, int E, float* const* dw, int n_ctas, void* stream);
 
+/* ---- fused tensor-core ImprovedRnn forward: input projection + recurrence of model.py:19 in one persistent tcgen05 kernel
+ *      (W_ih, W_hh resident in shared memory, two 128-sequence tiles per CTA ping-ponging through TMEM, rows masked by their
+ *      own length, no G round trip).  Up to 3 calls that share the GRU weights (user+item of model.py:45-46; ui+user+item of
+ *      model.py:182-184) run as segments of one launch.  Plans must use R = 128.  sched (int32, device):
+ *      [q_off (n_queues+1) | q_tile (sum of n_tiles)]: queue q lists global tile ids (segment tile bases are cumulative
+ *      n_tiles in segment order), CTA c walks queues 2c and 2c+1 (plan.py builds it longest-first). ---- */
+typedef struct umpr_gru_seg {
+  const float* xp;        /* [n_slabs][128][64] packed inputs (umpr_gather_pack) */
+  const int32_t* plan;    /* pack plan with R = 128 */
+  float* out;             /* (N,L,128), fully written */
+  float* hn;              /* (2,N,64) or NULL */
+  float* sv;              /* [n_slabs][2][128][256] or NULL (inference) */
+  int32_t n_tiles, n_slabs, N, L;
+} umpr_gru_seg;
+int umpr_gru_fwd_tc(const umpr_gru_seg* segs /*host array*/, int n_seg, const float* const* w, int E, const int32_t* sched,
+                    int n_queues, void* stream);
+
 /* ---- generic strided fp32 GEMM: gi·M (model.py:50), text matching (model.py:168) and their gradients ----
  * C[m][n] = act(accumulate*C + sum_k A[m*ars+k*acs] * B[k*brs+n*bcs] + bias[n]); act 0 none, 1 tanh, 2 relu, 3 sigmoid.
  * splits > 1: split-K with atomic accumulation into C (C must be initialised; bias/act not allowed). */

@@ -65,4 +65,25 @@ def test_sort_is_the_reference_call():
 def test_tile_rows_heuristic():
     assert choose_tile_rows(1280, 148) == 32
     assert choose_tile_rows(20480, 148) == 128
-    assert choose_tile_rows(5000, 148) == 64
+    assert choose_tile_rows(5000, 148) == 128      # >= TC_MIN_SEQS: 128-row tiles for the tensor-core GRU
+    assert choose_tile_rows(2000, 148) == 32
+
+
+@pytest.mark.parametrize("sizes,ctas", [([160], 74), ([160, 160], 74), ([40, 160, 160], 74), ([5], 74), ([1], 1), ([300, 7], 3)])
+def test_schedule_covers_every_tile_once_and_balances(sizes, ctas):
+    from umpr_b200.plan import build_schedule
+    rs = np.random.RandomState(sum(sizes))
+    tile_lens = [np.sort(rs.randint(1, 21, size=n))[::-1] for n in sizes]
+    sched, nq = build_schedule(tile_lens, ctas)
+    sched = sched.numpy()
+    T = sum(sizes)
+    assert nq % 2 == 0 and nq // 2 == min(ctas, T) and sched.size == nq + 1 + T
+    q_off, q_tile = sched[:nq + 1], sched[nq + 1:]
+    assert q_off[0] == 0 and q_off[-1] == T and (np.diff(q_off) >= 0).all()
+    assert sorted(q_tile.tolist()) == list(range(T))                    # every tile of every segment exactly once
+    lens = np.concatenate(tile_lens)
+    for q in range(nq):
+        ql = lens[q_tile[q_off[q]:q_off[q + 1]]]
+        assert (ql[:-1] >= ql[1:]).all()                                # longest first inside a queue
+    per_cta = np.array([lens[q_tile[q_off[2 * c]:q_off[2 * c + 2]]].sum() for c in range(nq // 2)])
+    assert per_cta.max() - per_cta.min() <= 2 * lens.max()              # boustrophedon dealing keeps CTAs level

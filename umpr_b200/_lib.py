@@ -24,6 +24,7 @@ SIGNATURES = {
     "umpr_gru_recurrence_bwd": [P, P, P, P, P, P, I, I, I, I, I, P, P],
     "umpr_gru_wgrad": [P, P, P, P, I, I, I, I, I, P, I, P],
     "umpr_gru_wgrad_tc": [P, P, P, P, I, I, I, I, I, P, I, P],
+    "umpr_gru_fwd_tc": [P, I, P, I, P, I, P],
     "umpr_sgemm": [P, L, L, P, L, L, P, L, I, I, I, I, I, P, I, P],
     "umpr_tc_gemm_nt": [P, L, P, L, P, L, I, I, I, I, P, I, I, P],
     "umpr_gru_inproj_tc": [P, P, I, I, I, P, I, P],
@@ -52,6 +53,14 @@ SIGNATURES = {
     "umpr_tanh_bwd": [P, P, L, P, P],
     "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P],
 }
+
+
+
+class GruSeg(C.Structure):
+    """``umpr_gru_seg`` of include/umpr_b200.h: one ImprovedRnn call inside a fused tensor-core GRU launch."""
+    _fields_ = [("xp", P), ("plan", P), ("out", P), ("hn", P), ("sv", P), ("n_tiles", C.c_int32), ("n_slabs", C.c_int32),
+                ("N", C.c_int32), ("L", C.c_int32)]
+
 
 _lib = None
 

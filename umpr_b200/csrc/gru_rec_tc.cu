@@ -1,0 +1,378 @@
+// ImprovedRnn forward on the tensor cores (reference src/model.py:18-21, nn.GRU cell of model.py:19):
+// input projection AND recurrence of the variable-length bidirectional GRU in ONE persistent tcgen05 kernel.
+//
+//   * one CTA per SM, bound to one direction; W_ih (with the bias column) and W_hh stay resident in shared memory for the
+//     whole launch as bf16 hi/lo images (3xBF16: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM);
+//   * a CTA runs TWO tiles of 128 length-sorted sequences at once ("slots"), each with its own 256 TMEM columns
+//       [0,64) r   [64,128) z   (x-part and h-part accumulated together)   [128,192) W_in x + b_in   [192,256) W_hn h
+//     so that the gate math of one slot (CUDA cores / MUFU) overlaps the MMAs of the other (tensor pipe);
+//   * per time step and slot:  D  = x_t · W_ih^T          (N=192, K=64: 12 MMAs, independent of h)
+//                              D += h_{t-1} · W_hh^T      (N=128 into r,z and N=64 into its own n columns: 24 MMAs)
+//     then 8 gate warps read their TMEM lanes, apply the ATen GRU cell, mask each row by its own length, write the
+//     ImprovedRnn output row in the reference's doubly-permuted order (zeros beyond the length), the saved gates for
+//     backward, and h_t as the next step's bf16 hi/lo A-operand;
+//   * warp roles: 0-7 gates (TMEM lane quarter = warp%4, hidden half = warp/4), 8 MMA issuer, 9-10 x loaders
+//     (fp32 packed tokens -> bf16 hi/lo SWIZZLE_128B); hand-offs are mbarriers, no __syncthreads in the steady state;
+//   * several ImprovedRnn calls that share weights (user+item in R-Net, ui+user+item in C-Net) run as "segments" of one
+//     launch; the host orders tiles longest-first into per-slot queues (plan.py) so slots finish together.
+#include "common.cuh"
+#include "tc.cuh"
+#include "../../include/umpr_b200.h"
+
+namespace umpr {
+using namespace tc;
+
+constexpr int RT_GATE_WARPS = 8;
+constexpr int RT_MMA_WARP = 8;
+constexpr int RT_LOAD_WARP0 = 9;
+constexpr int RT_LOAD_WARPS = 2;
+constexpr int RT_THREADS = (RT_GATE_WARPS + 1 + RT_LOAD_WARPS) * 32;   // 352: at most 3 warps per scheduler -> 168 registers
+constexpr int RT_R = 128;                        // sequences per tile = MMA M
+constexpr int RT_W_BYTES = 2 * G3 * 128;         // hi | lo, [192][64 bf16]
+constexpr int RT_A_BYTES = 2 * RT_R * 128;       // hi | lo, [128][64 bf16]
+constexpr int RT_SMEM = 2 * RT_W_BYTES + 4 * RT_A_BYTES + 1024;
+constexpr int RT_MAX_SEG = 3;
+
+struct RecSeg {
+  const float* xp; const int* plan; float* out; float* hn; float* sv;
+  int n_tiles, n_slabs, N, L, tile_base;
+};
+struct RecArgs {
+  RecSeg seg[RT_MAX_SEG];
+  int n_seg;
+  const int* q_off; const int* q_tile;
+  const float* w[8];
+  int E, kx;
+};
+
+// one slot's position in its tile queue; every warp role walks the same deterministic sequence
+struct Cur {
+  int q, qend, s, Lj, tile, si;
+  bool active;
+};
+__device__ __forceinline__ void cur_tile(const RecArgs& a, Cur& c) {
+  const int g = a.q_tile[c.q];
+  int si = 0;
+  if (a.n_seg > 1 && g >= a.seg[1].tile_base) si = 1;
+  if (a.n_seg > 2 && g >= a.seg[2].tile_base) si = 2;
+  c.si = si;
+  c.tile = g - a.seg[si].tile_base;
+  c.Lj = a.seg[si].plan[2 * a.seg[si].n_tiles * RT_R + c.tile * RT_R];    // len_of[tile*R]: the tile's longest job
+  c.s = 0;
+}
+__device__ __forceinline__ void cur_init(const RecArgs& a, Cur& c, int qi) {
+  c.q = a.q_off[qi]; c.qend = a.q_off[qi + 1];
+  c.active = c.q < c.qend;
+  c.s = 0; c.Lj = 0; c.tile = 0; c.si = 0;
+  if (c.active) cur_tile(a, c);
+}
+__device__ __forceinline__ void cur_next(const RecArgs& a, Cur& c) {
+  if (++c.s == c.Lj) {
+    if (++c.q < c.qend) cur_tile(a, c); else c.active = false;
+  }
+}
+
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+// wait for the outstanding TMEM loads; the registers are listed as in/out operands so no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait8(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+               :: "memory");
+}
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void st_zero8(float* p) {
+  *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// per-slot state of one gate thread: its row of the tile (32 of the 64 hidden units)
+struct GateRow {
+  float h[32];
+  int len, rowo;
+};
+
+template <int X>
+__device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRow& g, int n, int dir, int row, int hf,
+                                          unsigned char* hs, const float* s_bhn, uint64_t* h_ready, uint64_t* acc_full, uint32_t tmem) {
+  const RecSeg& sg = a.seg[c.si];
+  const int u0 = hf * 32;
+  unsigned char* h_hi = hs + X * RT_A_BYTES, *h_lo = h_hi + RT_R * 128;
+  if (c.s == 0) {
+    // tile start: this row's job, h_0 = 0 (registers and the A-operand image)
+    const int Rp = sg.n_tiles * RT_R, k = c.tile * RT_R + row;
+    g.rowo = sg.plan[Rp + k];
+    g.len = sg.plan[2 * Rp + k];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) g.h[i] = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const uint32_t off = (uint32_t)(row * 128 + (((hf * 4 + cc) ^ (row & 7)) << 4));
+      *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_async_smem();
+    tc_fence_before();          // orders this thread's TMEM reads of the slot's previous tile before the next MMAs
+    mbar_arrive(&h_ready[X]);
+  }
+  const int t = dir ? (c.Lj - 1 - c.s) : c.s;
+  const bool live = t < g.len;
+  const int slab0 = sg.plan[3 * sg.n_tiles * RT_R + c.tile];        // tile_off[tile]
+  float* orow = sg.out + ((size_t)(g.rowo < 0 ? 0 : g.rowo) * sg.L + t) * D + dir * H + u0;
+  float* svrow = sg.sv ? sg.sv + (((size_t)(slab0 + t) * 2 + dir) * RT_R + row) * SV + u0 : nullptr;
+  const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16) + X * 256 + u0;
+
+  mbar_wait(&acc_full[X], n & 1);
+  tc_fence_after();
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t v[32];
+    tmem_ld8_issue(trow + cc * 8, v);
+    tmem_ld8_issue(trow + 64 + cc * 8, v + 8);
+    tmem_ld8_issue(trow + 128 + cc * 8, v + 16);
+    tmem_ld8_issue(trow + 192 + cc * 8, v + 24);
+    tmem_wait8(v); tmem_wait8(v + 8); tmem_wait8(v + 16); tmem_wait8(v + 24);
+    if (live) {
+      float rr[8], zz[8], nn[8], hh[8], hv[8];
+      const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8), b1 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8 + 4);
+      const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ar = __uint_as_float(v[i]), az = __uint_as_float(v[8 + i]);
+        const float anx = __uint_as_float(v[16 + i]), anh = __uint_as_float(v[24 + i]);
+        const float er = ex2f(fminf(ar * -1.4426950408889634f, 60.f));
+        const float r = rcpf(1.f + er);                                   // sigmoid
+        const float hcand = anh + bh[i];                                  // W_hn h + b_hn
+        const float xn = fmaf(r, hcand, anx);
+        const float ez = ex2f(fminf(az * -1.4426950408889634f, 60.f));
+        const float en = ex2f(fminf(xn * 2.8853900817779268f, 60.f));    // e^{2 xn}
+        const float dz = 1.f + ez, dn = 1.f + en;
+        const float inv = rcpf(dz * dn);                                  // one reciprocal for z and n
+        const float z = dn * inv;
+        const float nv = fmaf(-2.f * dz, inv, 1.f);                       // tanh(xn) = 1 - 2 / (1 + e^{2 xn})
+        const float hnew = fmaf(g.h[cc * 8 + i] - nv, z, nv);            // ATen GRU cell: (h - n) * z + n
+        rr[i] = r; zz[i] = z; nn[i] = nv; hh[i] = hcand; hv[i] = hnew;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g.h[cc * 8 + i] = hv[i];
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(hv[2 * i], hv[2 * i + 1], hi[i], lo[i]);
+      const uint32_t off = (uint32_t)(row * 128 + (((hf * 4 + cc) ^ (row & 7)) << 4));
+      *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      if (g.rowo >= 0) {
+        *reinterpret_cast<float4*>(orow + cc * 8) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<float4*>(orow + cc * 8 + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      }
+      if (svrow) {
+        float* s8 = svrow + cc * 8;
+        *reinterpret_cast<float4*>(s8) = make_float4(rr[0], rr[1], rr[2], rr[3]);
+        *reinterpret_cast<float4*>(s8 + 4) = make_float4(rr[4], rr[5], rr[6], rr[7]);
+        *reinterpret_cast<float4*>(s8 + H) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+        *reinterpret_cast<float4*>(s8 + H + 4) = make_float4(zz[4], zz[5], zz[6], zz[7]);
+        *reinterpret_cast<float4*>(s8 + 2 * H) = make_float4(nn[0], nn[1], nn[2], nn[3]);
+        *reinterpret_cast<float4*>(s8 + 2 * H + 4) = make_float4(nn[4], nn[5], nn[6], nn[7]);
+        *reinterpret_cast<float4*>(s8 + 3 * H) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<float4*>(s8 + 3 * H + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+      }
+    } else if (g.rowo >= 0) {
+      st_zero8(orow + cc * 8);                      // t >= length: pad_packed_sequence zeros (model.py:20)
+    }
+  }
+  if (c.s + 1 < c.Lj) {
+    fence_async_smem();        // h_t image visible to the tensor core's shared-memory reads
+    tc_fence_before();
+    mbar_arrive(&h_ready[X]);
+  } else {
+    // tile end: zero padding up to total_length (model.py:17,20) and h_n in ORIGINAL sequence order
+    if (g.rowo >= 0) {
+      for (int tt = c.Lj; tt < sg.L; ++tt) {
+        float* z = sg.out + ((size_t)g.rowo * sg.L + tt) * D + dir * H + u0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) st_zero8(z + i * 8);
+      }
+      if (sg.hn) {
+        const int seq = sg.plan[c.tile * RT_R + row];
+        float* hp = sg.hn + ((size_t)dir * sg.N + seq) * H + u0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(hp + i * 4) = make_float4(g.h[i * 4], g.h[i * 4 + 1], g.h[i * 4 + 2], g.h[i * 4 + 3]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_constant__ RecArgs a) {
+  extern __shared__ unsigned char raw[];
+  __shared__ uint64_t x_full[2], x_empty[2], h_ready[2], acc_full[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bhn[H];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wih = base;                              // [hi|lo][192][128 B]
+  unsigned char* whh = base + RT_W_BYTES;
+  unsigned char* hs = base + 2 * RT_W_BYTES;              // [slot][hi|lo][128][128 B]
+  unsigned char* xs = hs + 2 * RT_A_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], RT_LOAD_WARPS * 32);
+      mbar_init(&x_empty[s], 1);
+      mbar_init(&h_ready[s], RT_GATE_WARPS * 32);
+      mbar_init(&acc_full[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == RT_MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  {
+    // resident weights of this direction: W_ih with column E = b_ih (+ b_hh for r,z) (multiplied by xp's 1.0 column), W_hh
+    const float* w_ih = a.w[dir * 4 + 0], *w_hh = a.w[dir * 4 + 1], *b_ih = a.w[dir * 4 + 2], *b_hh = a.w[dir * 4 + 3];
+    for (int idx = tid; idx < G3 * 16; idx += RT_THREADS) {
+      const int n = idx >> 4, k = (idx & 15) * 4;
+      float t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kk = k + q;
+        t[q] = kk < a.E ? w_ih[(size_t)n * a.E + kk] : (kk == a.E ? b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f) : 0.f);
+      }
+      store_split4(wih, wih + G3 * 128, n, k, make_float4(t[0], t[1], t[2], t[3]));
+      store_split4(whh, whh + G3 * 128, n, k, *reinterpret_cast<const float4*>(w_hh + n * H + k));
+    }
+    if (tid < H) s_bhn[tid] = b_hh[2 * H + tid];
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  Cur c[2];
+  cur_init(a, c[0], 2 * blockIdx.x);
+  cur_init(a, c[1], 2 * blockIdx.x + 1);
+  int n[2] = {0, 0};                       // steps done per slot (mbarrier phase bookkeeping)
+
+  if (warp < RT_GATE_WARPS) {
+    // ------------------------------------------------------------------ gate warps
+    const int row = (warp & 3) * 32 + lane, hf = warp >> 2;
+    GateRow g0, g1;
+    g0.len = g1.len = 0; g0.rowo = g1.rowo = -1;
+    while (c[0].active || c[1].active) {
+      if (c[0].active) { gate_step<0>(a, c[0], g0, n[0], dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem); ++n[0]; cur_next(a, c[0]); }
+      if (c[1].active) { gate_step<1>(a, c[1], g1, n[1], dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem); ++n[1]; cur_next(a, c[1]); }
+    }
+  } else if (warp == RT_MMA_WARP) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
+      const uint64_t wih_h = smem_desc_sw128(smem_u32(wih)), wih_l = smem_desc_sw128(smem_u32(wih + G3 * 128));
+      const uint64_t whh_h = smem_desc_sw128(smem_u32(whh)), whh_l = smem_desc_sw128(smem_u32(whh + G3 * 128));
+      const uint64_t whn_h = smem_desc_sw128(smem_u32(whh + 128 * 128)), whn_l = smem_desc_sw128(smem_u32(whh + G3 * 128 + 128 * 128));
+      while (c[0].active || c[1].active) {
+#pragma unroll
+        for (int X = 0; X < 2; ++X) {
+          if (!c[X].active) continue;
+          const uint32_t d = tmem + X * 256;
+          const uint64_t x_h = smem_desc_sw128(smem_u32(xs + X * RT_A_BYTES)), x_l = smem_desc_sw128(smem_u32(xs + X * RT_A_BYTES + RT_R * 128));
+          const uint64_t h_h = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES)), h_l = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES + RT_R * 128));
+          mbar_wait(&x_full[X], n[X] & 1);
+          mbar_wait(&h_ready[X], n[X] & 1);       // h_{t-1} image written AND the slot's accumulator columns drained
+          tc_fence_after();
+          for (int kk = 0; kk < a.kx; ++kk) {     // x_t · W_ih^T  -> r, z, n_x  (overwrites)
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_bf16(d, x_h + o, wih_h + o, id192, kk != 0);
+            umma_bf16(d, x_h + o, wih_l + o, id192, 1);
+            umma_bf16(d, x_l + o, wih_h + o, id192, 1);
+          }
+          umma_commit(&x_empty[X]);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {        // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_bf16(d, h_h + o, whh_h + o, id128, 1);
+            umma_bf16(d, h_h + o, whh_l + o, id128, 1);
+            umma_bf16(d, h_l + o, whh_h + o, id128, 1);
+            umma_bf16(d + 192, h_h + o, whn_h + o, id64, kk != 0);
+            umma_bf16(d + 192, h_h + o, whn_l + o, id64, 1);
+            umma_bf16(d + 192, h_l + o, whn_h + o, id64, 1);
+          }
+          umma_commit(&acc_full[X]);
+          ++n[X];
+          cur_next(a, c[X]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ x loaders (2 warps)
+    const int lt = tid - RT_LOAD_WARP0 * 32;
+    while (c[0].active || c[1].active) {
+#pragma unroll
+      for (int X = 0; X < 2; ++X) {
+        if (!c[X].active) continue;
+        const RecSeg& sg = a.seg[c[X].si];
+        const int t = dir ? (c[X].Lj - 1 - c[X].s) : c[X].s;
+        const int slab = sg.plan[3 * sg.n_tiles * RT_R + c[X].tile] + t;
+        const float4* src = reinterpret_cast<const float4*>(sg.xp + (size_t)slab * RT_R * KP);
+        unsigned char* x_hi = xs + X * RT_A_BYTES, *x_lo = x_hi + RT_R * 128;
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) va[i] = src[i * 64 + lt];
+        if (n[X] > 0) mbar_wait(&x_empty[X], (n[X] - 1) & 1);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {            // 4 batches of 8 float4 per thread, next batch in flight while this one is split
+          if (b < 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vb[i] = src[((b + 1) * 8 + i) * 64 + lt];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = (b * 8 + i) * 64 + lt;
+            store_split4(x_hi, x_lo, idx >> 4, (idx & 15) * 4, va[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) va[i] = vb[i];
+        }
+        fence_async_smem();
+        mbar_arrive(&x_full[X]);
+        ++n[X];
+        cur_next(a, c[X]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RT_MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace umpr
+
+using namespace umpr;
+
+extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float* const* w, int E, const int32_t* sched,
+                               int n_queues, void* stream) {
+  if (n_seg < 1 || n_seg > RT_MAX_SEG) return fail_arg("gru_fwd_tc: n_seg=%d not in [1,%d]", n_seg, RT_MAX_SEG);
+  if (E < 1 || E >= KP) return fail_arg("gru_fwd_tc: E=%d must be in [1,%d)", E, KP);
+  if (n_queues < 2 || (n_queues & 1)) return fail_arg("gru_fwd_tc: n_queues=%d must be even and >= 2", n_queues);
+  RecArgs a{};
+  int base = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    const umpr_gru_seg& s = segs[i];
+    if (s.n_tiles < 1 || s.L < 1 || !s.xp || !s.plan || !s.out) return fail_arg("gru_fwd_tc: segment %d is incomplete", i);
+    a.seg[i] = RecSeg{s.xp, s.plan, s.out, s.hn, s.sv, s.n_tiles, s.n_slabs, s.N, s.L, base};
+    base += s.n_tiles;
+  }
+  a.n_seg = n_seg;
+  a.q_off = sched;
+  a.q_tile = sched + n_queues + 1;
+  for (int i = 0; i < 8; ++i) a.w[i] = w[i];
+  a.E = E;
+  a.kx = (E + 1 + 15) / 16;
+  cudaError_t e = cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM);
+  if (e != cudaSuccess) { set_error("gru_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
+  gru_fwd_tc_kernel<<<dim3(n_queues / 2, 2), RT_THREADS, RT_SMEM, (cudaStream_t)stream>>>(a);
+  return check_launch("gru_fwd_tc");
+}

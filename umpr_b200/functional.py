@@ -4,6 +4,8 @@ Each Function cites the reference lines (``src/model.py``) whose forward+backwar
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -13,6 +15,7 @@ from ._lib import call, ptr, ptr_array
 from .plan import PackPlan
 
 H, D, ATT, KP, SV = 64, 128, 64, 64, 256
+TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
 TENSOR_CORE_COATTN = False     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
@@ -104,7 +107,93 @@ class _GruFn(Function):
 
 def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True):
     """weights: 8 tensors in nn.GRU order (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then *_reverse)."""
+    if TENSOR_CORE_GRU and plan.R == 128:
+        out, hn = gru_forward_multi([plan], [xp], E, weights, want_hidden)[0]
+        return out, hn
     return _GruFn.apply(plan, xp, E, want_hidden, *weights)
+
+
+class _GruTcFn(Function):
+    """Several ImprovedRnn calls that share one nn.GRU (model.py:45-46; model.py:182-184) as ONE fused tensor-core launch:
+    input projection + recurrence, W_ih/W_hh resident in shared memory (gru_rec_tc.cu)."""
+
+    @staticmethod
+    def forward(ctx, plans, xps, E, want_hidden, *w):
+        w = [_f32(t) for t in w]
+        dev = xps[0].device
+        n = len(plans)
+        need_grad = any(ctx.needs_input_grad[4:])
+        segs = (_lib.GruSeg * n)()
+        outs, hns, svs = [], [], []
+        tokens = 0
+        for i, (plan, xp) in enumerate(zip(plans, xps)):
+            if plan.R != 128:
+                raise RuntimeError("umpr_b200: the tensor-core GRU needs pack plans with 128-row tiles")
+            out = torch.empty(plan.N, plan.L, D, dtype=torch.float32, device=dev)
+            hn = torch.empty(2, plan.N, H, dtype=torch.float32, device=dev) if want_hidden else None
+            sv = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev) if need_grad else None
+            segs[i] = _lib.GruSeg(ptr(xp), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
+            outs.append(out); hns.append(hn); svs.append(sv)
+            tokens += plan.tokens
+        from .plan import build_schedule
+        sched, nq = build_schedule([p.tile_len for p in plans], max(1, _n_ctas(dev) // 2))
+        sched = sched.pin_memory().to(dev, non_blocking=True)
+        call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
+             work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
+        ctx.plans, ctx.E, ctx.n = plans, E, n
+        ctx.save_for_backward(*xps, *outs, *[t for t in svs if t is not None], *w)
+        ctx.has_sv = need_grad
+        res = list(outs)
+        for hn in hns:
+            if hn is None:
+                hn = outs[0].new_zeros(0)
+            res.append(hn)
+        if not want_hidden:
+            ctx.mark_non_differentiable(*res[n:])
+        return tuple(res)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads_in):
+        plans, E, n = ctx.plans, ctx.E, ctx.n
+        saved = ctx.saved_tensors
+        xps, outs, svs, w = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], list(saved[3 * n:])
+        dev = outs[0].device
+        flat = torch.zeros(sum(t.numel() for t in w), dtype=torch.float32, device=dev)
+        grads, o = [], 0
+        for t in w:
+            grads.append(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+        wp, gp = ptr_array(w), ptr_array(grads)
+        for i, plan in enumerate(plans):
+            d_out, d_hn = grads_in[i], grads_in[n + i]
+            if d_out is None and (d_hn is None or not d_hn.numel()):
+                continue
+            N, L, R = plan.N, plan.L, plan.R
+            d_out = _f32(d_out) if d_out is not None else torch.zeros_like(outs[i])
+            d_hn = _f32(d_hn) if (d_hn is not None and d_hn.numel()) else None
+            dG = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev)
+            call("umpr_gru_recurrence_bwd", ptr(d_out), ptr(d_hn), ptr(outs[i]), ptr(svs[i]), wp, ptr(plan.buf), plan.n_tiles,
+                 plan.n_slabs, R, N, L, ptr(dG), work=(2.0 * plan.tokens * 2 * H * 3 * H, 0.0))
+            call("umpr_gru_wgrad_tc", ptr(dG), ptr(xps[i]), ptr(outs[i]), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, gp,
+                 _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
+        return (None, None, None, None, *grads)
+
+
+def gru_forward_multi(plans, xps, E, weights, want_hidden=False):
+    """ImprovedRnn over several review sides with shared GRU weights → [(out, hn), ...] in the order given.
+    Sides whose plan has 128-row tiles share one fused tensor-core launch; small sides run the CUDA-core kernels."""
+    res = [None] * len(plans)
+    tc = [i for i, p in enumerate(plans) if TENSOR_CORE_GRU and p.R == 128]
+    for i0 in range(0, len(tc), 3):
+        grp = tc[i0:i0 + 3]
+        r = _GruTcFn.apply(tuple(plans[i] for i in grp), tuple(xps[i] for i in grp), E, want_hidden, *weights)
+        for j, i in enumerate(grp):
+            res[i] = (r[j], r[len(grp) + j])
+    for i, p in enumerate(plans):
+        if res[i] is None:
+            res[i] = _GruFn.apply(p, xps[i], E, want_hidden, *weights)
+    return res
 
 
 # --------------------------------------------------------------------------------------------------------------------

@@ -63,6 +63,10 @@ class ImprovedRnn(nn.Module):
     def run(self, pk: PackedReviews, want_hidden=True):
         return F.gru_forward(pk.plan, pk.xp, pk.E, _gru_weights(self.module), want_hidden)
 
+    def run_many(self, pks, want_hidden=False):
+        """Several review sides through this GRU (the reference calls it once per side with the same weights)."""
+        return F.gru_forward_multi([pk.plan for pk in pks], [pk.xp for pk in pks], pks[0].E, _gru_weights(self.module), want_hidden)
+
 
 class RNet(nn.Module):
     """model.py:24-56."""
@@ -80,8 +84,7 @@ class RNet(nn.Module):
     def forward(self, user_emb, item_emb, u_lengths, i_lengths):
         pu = user_emb if isinstance(user_emb, PackedReviews) else PackedReviews(u_lengths, emb=user_emb)
         pi = item_emb if isinstance(item_emb, PackedReviews) else PackedReviews(i_lengths, emb=item_emb)
-        gru_u, _ = self.gru.run(pu, want_hidden=False)
-        gru_i, _ = self.gru.run(pi, want_hidden=False)
+        (gru_u, _), (gru_i, _) = self.gru.run_many([pu, pi])           # model.py:45-46: shared weights, one fused launch
         gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
         gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
         soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M)
@@ -125,11 +128,18 @@ class CNet(nn.Module):
 
     def forward(self, review_emb, lengths):
         pk = review_emb if isinstance(review_emb, PackedReviews) else PackedReviews(lengths, emb=review_emb)
-        gru_repr, _ = self.gru.run(pk, want_hidden=False)
-        gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
-        view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
-                                          self.linear[0].weight, self.linear[0].bias, self.threshold)
-        return gru_repr, view_p, final_repr
+        return self.forward_many([pk])[0]
+
+    def forward_many(self, pks):
+        """``forward`` for several review sides (model.py:182-184 calls C-Net on ui, user and item with shared weights):
+        their GRUs run as one fused launch, the convolution tails per side."""
+        res = []
+        for pk, (gru_repr, _) in zip(pks, self.gru.run_many(pks)):
+            gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
+            view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
+                                              self.linear[0].weight, self.linear[0].bias, self.threshold)
+            res.append((gru_repr, view_p, final_repr))
+        return res
 
 
 class SSNet(nn.Module):
@@ -186,9 +196,9 @@ class ControlNet(nn.Module):
 
     def forward(self, user_emb, item_emb, ui_emb, u_lengths, i_lengths, ui_lengths):
         ui_s_length = ui_emb.L if isinstance(ui_emb, PackedReviews) else ui_emb.shape[-2]
-        gru_repr, view_p, c_net_out = self.c_net(ui_emb, ui_lengths)
-        _, _, c_u = self.c_net(user_emb, u_lengths)
-        _, _, c_i = self.c_net(item_emb, i_lengths)
+        pks = [e if isinstance(e, PackedReviews) else PackedReviews(l, emb=e)
+               for e, l in ((ui_emb, ui_lengths), (user_emb, u_lengths), (item_emb, i_lengths))]
+        (gru_repr, view_p, c_net_out), (_, _, c_u), (_, _, c_i) = self.c_net.forward_many(pks)      # model.py:182-184
         s, _ = self.s_net(gru_repr, view_p, ui_s_length)
         lin = self.ss_net.linear[0]
         prefer_pos, prefer_neg = F.control_tail(s, view_p, c_net_out, lin.weight, lin.bias, EQ18_EPS)

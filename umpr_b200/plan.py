@@ -14,12 +14,45 @@ from . import _lib
 TILE_ROWS = (32, 64, 128)
 
 
+TC_MIN_SEQS = 2048     # from this many sequences on, a call runs on the fused tensor-core GRU kernel (tiles of 128)
+
+
 def choose_tile_rows(n_seq: int, n_sm: int) -> int:
-    """Largest tile whose (tile, direction) grid still covers every SM; small batches get small tiles."""
+    """128-row tiles (the tcgen05 MMA's M) once there are enough sequences to feed the tensor-core kernel; below that the
+    CUDA-core kernels with the largest tile whose (tile, direction) grid still covers every SM."""
+    if n_seq >= TC_MIN_SEQS:
+        return 128
     for r in (128, 64):
         if 2 * ((n_seq + r - 1) // r) >= n_sm:
             return r
     return 32
+
+
+def build_schedule(tile_lens, n_ctas: int):
+    """Tile queues of one fused GRU launch (umpr_gru_fwd_tc / umpr_gru_bwd_tc).
+
+    ``tile_lens``: one int sequence per segment (steps of every 128-row tile, already descending inside a segment).
+    Tiles of all segments get global ids (segment bases are cumulative tile counts) and are dealt longest-first to
+    ``n_ctas`` CTAs in boustrophedon order, pass p filling slot p % 2 of each CTA, so the two slots of a CTA — which
+    ping-pong between tensor pipe and gate math — and all CTAs finish at about the same step.
+    → (int32 tensor ``[q_off (2*G+1) | q_tile (T)]``, n_queues = 2*G); CTA c owns queues 2c and 2c+1.
+    """
+    import numpy as np
+    lens = np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tile_lens])
+    T = int(lens.size)
+    if T == 0:
+        raise RuntimeError("umpr_b200: empty GRU launch")
+    G = max(1, min(int(n_ctas), T))
+    order = np.argsort(-lens, kind="stable")
+    i = np.arange(T)
+    p, pos = i // G, i % G
+    cta = np.where(p % 2 == 0, pos, G - 1 - pos)
+    queue = 2 * cta + (p % 2)
+    by_q = np.argsort(queue, kind="stable")                 # stable: tiles stay longest-first inside a queue
+    q_tile = order[by_q]
+    counts = np.bincount(queue, minlength=2 * G)
+    q_off = np.concatenate([[0], np.cumsum(counts)])
+    return torch.from_numpy(np.concatenate([q_off, q_tile]).astype(np.int32)), 2 * G
 
 
 class PackPlan:
@@ -58,6 +91,7 @@ class PackPlan:
         row_of = torch.cat([sorted_idx[sorted_idx], z - 1])                  # output row fed by job k
         len_of = torch.cat([sorted_len, z])
         tile_len = len_of[::R]
+        self.tile_len = tile_len
         tile_off = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(tile_len, 0)])
         self.n_slabs = int(tile_off[-1])
         slab_tile = torch.repeat_interleave(torch.arange(self.n_tiles, dtype=torch.int64), tile_len)
