@@ -62,13 +62,16 @@ int umpr_gru_wgrad_tc(const float* dG, const float* xp, const float* out, const 
  *      [q_off (n_queues+1) | q_tile (sum of n_tiles)]: queue q lists global tile ids (segment tile bases are cumulative
  *      n_tiles in segment order), CTA c walks queues 2c and 2c+1 (plan.py builds it longest-first). ---- */
 typedef struct umpr_gru_seg {
-  const float* xp;        /* [n_slabs][128][64] packed inputs (umpr_gather_pack) */
+  const void* xq;         /* [n_slabs][hi|lo][128][64 bf16] packed token images (umpr_gather_pack_tc) */
   const int32_t* plan;    /* pack plan with R = 128 */
   float* out;             /* (N,L,128), fully written */
   float* hn;              /* (2,N,64) or NULL */
   float* sv;              /* [n_slabs][2][128][256] or NULL (inference) */
   int32_t n_tiles, n_slabs, N, L;
 } umpr_gru_seg;
+/* xq[n_slabs][hi|lo][128][64 bf16]: gathered + packed tokens as SWIZZLE_128B bf16 hi/lo operand images (E values, 1.0, zeros) */
+int umpr_gather_pack_tc(const float* table, const int64_t* ids, const float* dense, const int32_t* plan, int n_tiles, int n_slabs,
+                        int L, int E, void* xq, void* stream);
 int umpr_gru_fwd_tc(const umpr_gru_seg* segs /*host array*/, int n_seg, const float* const* w, int E, const int32_t* sched,
                     int n_queues, void* stream);
 

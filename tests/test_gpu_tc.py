@@ -105,13 +105,14 @@ def test_fused_gru_forward_matches_cuda_core_path(sides, E, ctas):
         data = torch.randn(N, L, E, device=DEV) * 0.5
         plan = PackPlan(lens, L, DEV, tile_rows=128)
         xp, _ = F.gather_pack(plan, dense=data)
+        xq, _ = F.gather_pack_tc(plan, dense=data)
         G = torch.empty(plan.n_slabs * 2 * 128 * 192, device=DEV)
         call("umpr_gru_inproj", ptr(xp), ptr_array(w), plan.n_slabs, 128, E, ptr(G))
         out = torch.full((N, L, 128), 7.0, device=DEV)
         hn = torch.full((2, N, 64), 7.0, device=DEV)
         sv = torch.zeros(plan.n_slabs * 2 * 128 * 256, device=DEV)
         call("umpr_gru_recurrence_fwd", ptr(G), ptr_array(w), ptr(plan.buf), plan.n_tiles, plan.n_slabs, 128, N, L, ptr(out), ptr(hn), ptr(sv))
-        plans.append(plan); xps.append(xp); refs.append((out, hn, sv))
+        plans.append(plan); xps.append(xq); refs.append((out, hn, sv))
     n = len(sides)
     segs = (_lib.GruSeg * n)()
     got = []
@@ -131,6 +132,7 @@ def test_fused_gru_forward_matches_cuda_core_path(sides, E, ctas):
         assert_close(o1, o0, 2e-5, f"side {i} out")
         assert_close(h1, h0, 2e-5, f"side {i} hn")
         # saved gates are only defined for live (row, t) pairs; compare where the reference wrote something
+        s0 = s0.view(-1, 128, 256).transpose(1, 2).reshape(-1)        # the fused kernel keeps sv column-major inside a tile
         m = s0 != 0
         assert_close(torch.where(m, s1, s0), s0, 2e-5, f"side {i} sv")
 
@@ -145,12 +147,13 @@ def test_fused_gru_autograd_matches_cuda_core_path():
     data = torch.randn(N, L, E, device=DEV) * 0.5
     plan = PackPlan(lens, L, DEV, tile_rows=128)
     xp, _ = F.gather_pack(plan, dense=data)
+    xq, _ = F.gather_pack_tc(plan, dense=data)
     gy = torch.randn(N, L, 128, device=DEV)
     res = []
     for flag in (False, True):
         F.TENSOR_CORE_GRU = flag
         w = [t.clone().requires_grad_(True) for t in w0]
-        out, _ = F.gru_forward(plan, xp, E, w, want_hidden=False)
+        out, _ = F.gru_forward(plan, xp, E, w, want_hidden=False, xq=xq)
         (out * gy).sum().backward()
         res.append((out.detach(), [t.grad.clone() for t in w]))
     F.TENSOR_CORE_GRU = True

@@ -46,16 +46,6 @@ __global__ void cnet_tc_prep_kernel(const float* __restrict__ w, int KC, unsigne
   }
 }
 
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// register pending transaction bytes WITHOUT arriving (the thread arrives later, after its own stores)
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
 __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wimg,
                                                                          const float* __restrict__ bias, int N, int L, int KC, int gs,
                                                                          float* __restrict__ cfeat, int* __restrict__ cidx,

@@ -11,8 +11,8 @@
 //     then 8 gate warps read their TMEM lanes, apply the ATen GRU cell, mask each row by its own length, write the
 //     ImprovedRnn output row in the reference's doubly-permuted order (zeros beyond the length), the saved gates for
 //     backward, and h_t as the next step's bf16 hi/lo A-operand;
-//   * warp roles: 0-7 gates (TMEM lane quarter = warp%4, hidden half = warp/4), 8 MMA issuer, 9-10 x loaders
-//     (fp32 packed tokens -> bf16 hi/lo SWIZZLE_128B); hand-offs are mbarriers, no __syncthreads in the steady state;
+//   * warp roles: 0-7 gates (TMEM lane quarter = warp%4, hidden half = warp/4), 8 MMA issuer, 9 x producer (one TMA bulk copy
+//     of the pre-split bf16 hi/lo token image per step); hand-offs are mbarriers, no __syncthreads in the steady state;
 //   * several ImprovedRnn calls that share weights (user+item in R-Net, ui+user+item in C-Net) run as "segments" of one
 //     launch; the host orders tiles longest-first into per-slot queues (plan.py) so slots finish together.
 #include "common.cuh"
@@ -25,8 +25,8 @@ using namespace tc;
 constexpr int RT_GATE_WARPS = 8;
 constexpr int RT_MMA_WARP = 8;
 constexpr int RT_LOAD_WARP0 = 9;
-constexpr int RT_LOAD_WARPS = 2;
-constexpr int RT_THREADS = (RT_GATE_WARPS + 1 + RT_LOAD_WARPS) * 32;   // 352: at most 3 warps per scheduler -> 168 registers
+constexpr int RT_LOAD_WARPS = 1;
+constexpr int RT_THREADS = (RT_GATE_WARPS + 1 + RT_LOAD_WARPS) * 32;   // 320: at most 3 warps per scheduler -> 168 registers
 constexpr int RT_R = 128;                        // sequences per tile = MMA M
 constexpr int RT_W_BYTES = 2 * G3 * 128;         // hi | lo, [192][64 bf16]
 constexpr int RT_A_BYTES = 2 * RT_R * 128;       // hi | lo, [128][64 bf16]
@@ -34,7 +34,7 @@ constexpr int RT_SMEM = 2 * RT_W_BYTES + 4 * RT_A_BYTES + 1024;
 constexpr int RT_MAX_SEG = 3;
 
 struct RecSeg {
-  const float* xp; const int* plan; float* out; float* hn; float* sv;
+  const unsigned char* xq; const int* plan; float* out; float* hn; float* sv;
   int n_tiles, n_slabs, N, L, tile_base;
 };
 struct RecArgs {
@@ -90,6 +90,28 @@ __device__ __forceinline__ void st_zero8(float* p) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+
+// In-warp transpose of an 8x8 matrix of float4 inside each group of 8 lanes: before, lane j of a group holds a[k] = float4 #k of
+// ITS row; after, lane j holds a[i] = float4 #j of the group's row i.  A warp-wide 128-bit store of a[i] then writes 4 rows x
+// 128 contiguous bytes (full lines) instead of 32 rows x 16 bytes.  3 butterfly stages, 16 shuffles each.
+__device__ __forceinline__ void transpose8x8_f4(float4 (&a)[8], int lane) {
+#pragma unroll
+  for (int s = 1; s < 8; s <<= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k & s) continue;
+      float4 snd = up ? a[k] : a[k | s];
+      float4 rcv;
+      rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, s);
+      rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, s);
+      rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, s);
+      rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, s);
+      if (up) a[k] = rcv; else a[k | s] = rcv;
+    }
+  }
+}
+
 // per-slot state of one gate thread: its row of the tile (32 of the 64 hidden units)
 struct GateRow {
   float h[32];
@@ -122,8 +144,8 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
   const int t = dir ? (c.Lj - 1 - c.s) : c.s;
   const bool live = t < g.len;
   const int slab0 = sg.plan[3 * sg.n_tiles * RT_R + c.tile];        // tile_off[tile]
-  float* orow = sg.out + ((size_t)(g.rowo < 0 ? 0 : g.rowo) * sg.L + t) * D + dir * H + u0;
-  float* svrow = sg.sv ? sg.sv + (((size_t)(slab0 + t) * 2 + dir) * RT_R + row) * SV + u0 : nullptr;
+  // saved gates, column-major inside the (slab, direction) tile: svT[col = gate*64 + unit][row] -> lanes (= rows) are contiguous
+  float* svcol = sg.sv ? sg.sv + (((size_t)(slab0 + t) * 2 + dir) * SV + u0) * RT_R + row : nullptr;
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16) + X * 256 + u0;
 
   mbar_wait(&acc_full[X], n & 1);
@@ -165,37 +187,54 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
       const uint32_t off = (uint32_t)(row * 128 + (((hf * 4 + cc) ^ (row & 7)) << 4));
       *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      if (g.rowo >= 0) {
-        *reinterpret_cast<float4*>(orow + cc * 8) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        *reinterpret_cast<float4*>(orow + cc * 8 + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+      if (svcol) {
+        float* s8 = svcol + (size_t)(cc * 8) * RT_R;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s8[(size_t)i * RT_R] = rr[i];
+          s8[(size_t)(H + i) * RT_R] = zz[i];
+          s8[(size_t)(2 * H + i) * RT_R] = nn[i];
+          s8[(size_t)(3 * H + i) * RT_R] = hh[i];
+        }
       }
-      if (svrow) {
-        float* s8 = svrow + cc * 8;
-        *reinterpret_cast<float4*>(s8) = make_float4(rr[0], rr[1], rr[2], rr[3]);
-        *reinterpret_cast<float4*>(s8 + 4) = make_float4(rr[4], rr[5], rr[6], rr[7]);
-        *reinterpret_cast<float4*>(s8 + H) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-        *reinterpret_cast<float4*>(s8 + H + 4) = make_float4(zz[4], zz[5], zz[6], zz[7]);
-        *reinterpret_cast<float4*>(s8 + 2 * H) = make_float4(nn[0], nn[1], nn[2], nn[3]);
-        *reinterpret_cast<float4*>(s8 + 2 * H + 4) = make_float4(nn[4], nn[5], nn[6], nn[7]);
-        *reinterpret_cast<float4*>(s8 + 3 * H) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<float4*>(s8 + 3 * H + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
-      }
-    } else if (g.rowo >= 0) {
-      st_zero8(orow + cc * 8);                      // t >= length: pad_packed_sequence zeros (model.py:20)
     }
   }
   if (c.s + 1 < c.Lj) {
     fence_async_smem();        // h_t image visible to the tensor core's shared-memory reads
     tc_fence_before();
     mbar_arrive(&h_ready[X]);
-  } else {
-    // tile end: zero padding up to total_length (model.py:17,20) and h_n in ORIGINAL sequence order
-    if (g.rowo >= 0) {
-      for (int tt = c.Lj; tt < sg.L; ++tt) {
-        float* z = sg.out + ((size_t)g.rowo * sg.L + tt) * D + dir * H + u0;
+  }
+  {
+    // ImprovedRnn output row (row_of[job], t): h_t for live rows, zeros for t >= length (pad_packed_sequence, model.py:20).
+    // Transposed inside groups of 8 lanes so that every store instruction writes 4 rows x 128 contiguous bytes.
+    float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st_zero8(z + i * 8);
+    for (int k = 0; k < 8; ++k)
+      o[k] = live ? make_float4(g.h[4 * k], g.h[4 * k + 1], g.h[4 * k + 2], g.h[4 * k + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int lane = row & 31;
+    transpose8x8_f4(o, lane);
+    const int my = g.rowo < 0 ? -1 : g.rowo * sg.L + t;
+    float* obase = sg.out + dir * H + u0 + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ri = __shfl_sync(0xffffffffu, my, (lane & 24) + i);
+      if (ri >= 0) *reinterpret_cast<float4*>(obase + (size_t)ri * D) = o[i];
+    }
+  }
+  if (c.s + 1 == c.Lj) {
+    // tile end: zero padding up to total_length (model.py:17,20) and h_n in ORIGINAL sequence order
+    {
+      const int lane = row & 31;
+      float* obase = sg.out + dir * H + u0 + (lane & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ro = __shfl_sync(0xffffffffu, g.rowo, (lane & 24) + i);
+        if (ro < 0) continue;
+        for (int tt = c.Lj; tt < sg.L; ++tt)
+          *reinterpret_cast<float4*>(obase + ((size_t)ro * sg.L + tt) * D) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    }
+    if (g.rowo >= 0) {
       if (sg.hn) {
         const int seq = sg.plan[c.tile * RT_R + row];
         float* hp = sg.hn + ((size_t)dir * sg.N + seq) * H + u0;
@@ -204,6 +243,44 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
           *reinterpret_cast<float4*>(hp + i * 4) = make_float4(g.h[i * 4], g.h[i * 4 + 1], g.h[i * 4 + 2], g.h[i * 4 + 3]);
       }
     }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather + length-aware pack straight into tensor-core operand images (model.py:262-264 + the pack half of :18):
+//   xq[slab][hi|lo][128 rows][64 bf16]   K-major, SWIZZLE_128B: row r at byte r*128, its 16-byte chunk c at chunk c ^ (r & 7)
+// columns: E embedding values, a 1.0 (bias column), zeros.  fp32 = hi + lo (bf16 each, "3xBF16" operands).  The same image is
+// the A operand of the recurrence's x-part MMA and the (token-major) B operand of the weight-gradient MMA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                                                             const float* __restrict__ dense, Plan p, int L, int E,
+                                                             unsigned char* __restrict__ xq) {
+  const int sl = blockIdx.x;
+  const int j = p.slab_tile[sl];
+  const int t = sl - p.tile_off[j];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec2 = (E & 1) == 0;
+  unsigned char* img = xq + (size_t)sl * RT_A_BYTES;
+  for (int r = warp; r < RT_R; r += 8) {
+    const int k = j * RT_R + r;
+    float2 v = make_float2(0.f, 0.f);
+    if (t < p.len_of[k]) {
+      const size_t tok = (size_t)p.seq_of[k] * L + t;
+      const float* src = dense ? dense + tok * E : table + (size_t)ids[tok] * E;
+      const int e0 = 2 * lane;
+      if (vec2 && e0 + 1 < E) {
+        v = *reinterpret_cast<const float2*>(src + e0);
+      } else {
+        if (e0 < E) v.x = src[e0]; else if (e0 == E) v.x = 1.f;
+        if (e0 + 1 < E) v.y = src[e0 + 1]; else if (e0 + 1 == E) v.y = 1.f;
+      }
+    }
+    uint32_t hi, lo;
+    split2(v.x, v.y, hi, lo);
+    const uint32_t off = sw128_off(r, 2 * lane);
+    *reinterpret_cast<uint32_t*>(img + off) = hi;
+    *reinterpret_cast<uint32_t*>(img + RT_R * 128 + off) = lo;
   }
 }
 
@@ -222,7 +299,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], RT_LOAD_WARPS * 32);
+      mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
       mbar_init(&h_ready[s], RT_GATE_WARPS * 32);
       mbar_init(&acc_full[s], 1);
@@ -307,39 +384,22 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
       }
     }
   } else {
-    // ------------------------------------------------------------------ x loaders (2 warps)
-    const int lt = tid - RT_LOAD_WARP0 * 32;
-    while (c[0].active || c[1].active) {
+    // ------------------------------------------------------------------ x producer: one TMA bulk copy per (slot, step)
+    // the packed token image is already bf16 hi|lo, SWIZZLE_128B (gather_pack_tc_kernel): 32 KB land in the A-operand buffer as is
+    if (lane == 0) {
+      while (c[0].active || c[1].active) {
 #pragma unroll
-      for (int X = 0; X < 2; ++X) {
-        if (!c[X].active) continue;
-        const RecSeg& sg = a.seg[c[X].si];
-        const int t = dir ? (c[X].Lj - 1 - c[X].s) : c[X].s;
-        const int slab = sg.plan[3 * sg.n_tiles * RT_R + c[X].tile] + t;
-        const float4* src = reinterpret_cast<const float4*>(sg.xp + (size_t)slab * RT_R * KP);
-        unsigned char* x_hi = xs + X * RT_A_BYTES, *x_lo = x_hi + RT_R * 128;
-        float4 va[8], vb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) va[i] = src[i * 64 + lt];
-        if (n[X] > 0) mbar_wait(&x_empty[X], (n[X] - 1) & 1);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {            // 4 batches of 8 float4 per thread, next batch in flight while this one is split
-          if (b < 3) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vb[i] = src[((b + 1) * 8 + i) * 64 + lt];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = (b * 8 + i) * 64 + lt;
-            store_split4(x_hi, x_lo, idx >> 4, (idx & 15) * 4, va[i]);
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) va[i] = vb[i];
+        for (int X = 0; X < 2; ++X) {
+          if (!c[X].active) continue;
+          const RecSeg& sg = a.seg[c[X].si];
+          const int t = dir ? (c[X].Lj - 1 - c[X].s) : c[X].s;
+          const int slab = sg.plan[3 * sg.n_tiles * RT_R + c[X].tile] + t;
+          if (n[X] > 0) mbar_wait(&x_empty[X], (n[X] - 1) & 1);
+          mbar_arrive_expect_tx(&x_full[X], RT_A_BYTES);
+          bulk_copy_g2s(xs + X * RT_A_BYTES, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
+          ++n[X];
+          cur_next(a, c[X]);
         }
-        fence_async_smem();
-        mbar_arrive(&x_full[X]);
-        ++n[X];
-        cur_next(a, c[X]);
       }
     }
   }
@@ -352,6 +412,16 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
 
 using namespace umpr;
 
+extern "C" int umpr_gather_pack_tc(const float* table, const int64_t* ids, const float* dense, const int32_t* plan, int n_tiles,
+                                   int n_slabs, int L, int E, void* xq, void* stream) {
+  if ((!table || !ids) && !dense) return fail_arg("gather_pack_tc: need (table, ids) or dense");
+  if (E < 1 || E >= KP) return fail_arg("gather_pack_tc: embedding width E=%d must be in [1, %d)", E, KP);
+  if (n_slabs == 0) return 0;
+  Plan p = make_plan(plan, n_tiles, n_slabs, RT_R);
+  gather_pack_tc_kernel<<<n_slabs, 256, 0, (cudaStream_t)stream>>>(table, ids, dense, p, L, E, reinterpret_cast<unsigned char*>(xq));
+  return check_launch("gather_pack_tc");
+}
+
 extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float* const* w, int E, const int32_t* sched,
                                int n_queues, void* stream) {
   if (n_seg < 1 || n_seg > RT_MAX_SEG) return fail_arg("gru_fwd_tc: n_seg=%d not in [1,%d]", n_seg, RT_MAX_SEG);
@@ -361,8 +431,8 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
   int base = 0;
   for (int i = 0; i < n_seg; ++i) {
     const umpr_gru_seg& s = segs[i];
-    if (s.n_tiles < 1 || s.L < 1 || !s.xp || !s.plan || !s.out) return fail_arg("gru_fwd_tc: segment %d is incomplete", i);
-    a.seg[i] = RecSeg{s.xp, s.plan, s.out, s.hn, s.sv, s.n_tiles, s.n_slabs, s.N, s.L, base};
+    if (s.n_tiles < 1 || s.L < 1 || !s.xq || !s.plan || !s.out) return fail_arg("gru_fwd_tc: segment %d is incomplete", i);
+    a.seg[i] = RecSeg{reinterpret_cast<const unsigned char*>(s.xq), s.plan, s.out, s.hn, s.sv, s.n_tiles, s.n_slabs, s.N, s.L, base};
     base += s.n_tiles;
   }
   a.n_seg = n_seg;

@@ -56,6 +56,24 @@ def gather_pack(plan: PackPlan, *, table=None, ids=None, dense=None):
     return xp, E
 
 
+def gather_pack_tc(plan: PackPlan, *, table=None, ids=None, dense=None):
+    """Packed GRU input as tensor-core operand images ``xq[n_slabs][hi|lo][128][64 bf16]`` (plans with 128-row tiles)."""
+    if plan.R != 128:
+        raise RuntimeError("umpr_b200: operand images need a pack plan with 128-row tiles")
+    if dense is not None:
+        dense = _f32(_chk(dense, "GRU input"))
+        E, dev = dense.shape[-1], dense.device
+    else:
+        table = _f32(_chk(table, "embedding table"))
+        ids = _chk(ids, "token ids").contiguous()
+        assert ids.dtype == torch.int64
+        E, dev = table.shape[1], table.device
+    xq = torch.empty(plan.n_slabs * 2 * 128 * 128, dtype=torch.uint8, device=dev)
+    call("umpr_gather_pack_tc", ptr(table), ptr(ids), ptr(dense), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.L, E, ptr(xq),
+         work=(0.0, plan.tokens * (8 + 4 * E + 4 * KP)))
+    return xq, E
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # ImprovedRnn   (model.py:12-21)
 # --------------------------------------------------------------------------------------------------------------------
@@ -105,10 +123,10 @@ class _GruFn(Function):
         return (None, None, None, None, *grads)
 
 
-def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True):
+def gru_forward(plan: PackPlan, xp, E, weights, want_hidden=True, xq=None):
     """weights: 8 tensors in nn.GRU order (weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0, then *_reverse)."""
-    if TENSOR_CORE_GRU and plan.R == 128:
-        out, hn = gru_forward_multi([plan], [xp], E, weights, want_hidden)[0]
+    if TENSOR_CORE_GRU and plan.R == 128 and xq is not None:
+        out, hn = gru_forward_multi([plan], [xp], [xq], E, weights, want_hidden)[0]
         return out, hn
     return _GruFn.apply(plan, xp, E, want_hidden, *weights)
 
@@ -118,21 +136,21 @@ class _GruTcFn(Function):
     input projection + recurrence, W_ih/W_hh resident in shared memory (gru_rec_tc.cu)."""
 
     @staticmethod
-    def forward(ctx, plans, xps, E, want_hidden, *w):
+    def forward(ctx, plans, xps, xqs, E, want_hidden, *w):
         w = [_f32(t) for t in w]
-        dev = xps[0].device
+        dev = xqs[0].device
         n = len(plans)
-        need_grad = any(ctx.needs_input_grad[4:])
+        need_grad = any(ctx.needs_input_grad[5:])
         segs = (_lib.GruSeg * n)()
         outs, hns, svs = [], [], []
         tokens = 0
-        for i, (plan, xp) in enumerate(zip(plans, xps)):
+        for i, (plan, xq) in enumerate(zip(plans, xqs)):
             if plan.R != 128:
                 raise RuntimeError("umpr_b200: the tensor-core GRU needs pack plans with 128-row tiles")
             out = torch.empty(plan.N, plan.L, D, dtype=torch.float32, device=dev)
             hn = torch.empty(2, plan.N, H, dtype=torch.float32, device=dev) if want_hidden else None
             sv = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev) if need_grad else None
-            segs[i] = _lib.GruSeg(ptr(xp), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
+            segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
             outs.append(out); hns.append(hn); svs.append(sv)
             tokens += plan.tokens
         from .plan import build_schedule
@@ -177,17 +195,17 @@ class _GruTcFn(Function):
                  plan.n_slabs, R, N, L, ptr(dG), work=(2.0 * plan.tokens * 2 * H * 3 * H, 0.0))
             call("umpr_gru_wgrad_tc", ptr(dG), ptr(xps[i]), ptr(outs[i]), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, gp,
                  _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
-def gru_forward_multi(plans, xps, E, weights, want_hidden=False):
+def gru_forward_multi(plans, xps, xqs, E, weights, want_hidden=False):
     """ImprovedRnn over several review sides with shared GRU weights → [(out, hn), ...] in the order given.
     Sides whose plan has 128-row tiles share one fused tensor-core launch; small sides run the CUDA-core kernels."""
     res = [None] * len(plans)
-    tc = [i for i, p in enumerate(plans) if TENSOR_CORE_GRU and p.R == 128]
+    tc = [i for i, p in enumerate(plans) if TENSOR_CORE_GRU and p.R == 128 and xqs[i] is not None]
     for i0 in range(0, len(tc), 3):
         grp = tc[i0:i0 + 3]
-        r = _GruTcFn.apply(tuple(plans[i] for i in grp), tuple(xps[i] for i in grp), E, want_hidden, *weights)
+        r = _GruTcFn.apply(tuple(plans[i] for i in grp), tuple(xps[i] for i in grp), tuple(xqs[i] for i in grp), E, want_hidden, *weights)
         for j, i in enumerate(grp):
             res[i] = (r[j], r[len(grp) + j])
     for i, p in enumerate(plans):
