@@ -75,6 +75,24 @@ int umpr_gather_pack_tc(const float* table, const int64_t* ids, const float* den
 int umpr_gru_fwd_tc(const umpr_gru_seg* segs /*host array*/, int n_seg, const float* const* w, int E, const int32_t* sched,
                     int n_queues, void* stream);
 
+/* backward of umpr_gru_fwd_tc's recurrence (same tiles, queues and segments, reverse time): the carry product
+ * [dr, dz, dn*r]·W_hh runs on tcgen05 with its A operand written into tensor memory; sv = the forward's saved gates,
+ * dG[n_slabs][2][256][128] = [dr, dz, dn, dn*r] pre-activation gradients, both column-major inside a (slab, direction) tile. */
+typedef struct umpr_gru_bwd_seg {
+  const float* d_out;     /* (N,L,128) gradient of the ImprovedRnn result */
+  const float* d_hn;      /* (2,N,64) or NULL */
+  const float* out;       /* (N,L,128) forward result (h_{t-1} is read from it) */
+  const float* sv;        /* forward's saved gates */
+  float* dG;              /* [n_slabs][2][256][128], fully written */
+  const int32_t* plan;
+  int32_t n_tiles, n_slabs, N, L;
+} umpr_gru_bwd_seg;
+int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs /*host array*/, int n_seg, const float* const* w, const int32_t* sched, int n_queues,
+                    void* stream);
+/* dw[8] (+=) from dG in the layout above (R = 128): tcgen05 with K-major dG^T and token-major [xp | h_prev] operands */
+int umpr_gru_wgrad_tc2(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int L, int E,
+                       float* const* dw, int n_ctas, void* stream);
+
 /* ---- generic strided fp32 GEMM: gi·M (model.py:50), text matching (model.py:168) and their gradients ----
  * C[m][n] = act(accumulate*C + sum_k A[m*ars+k*acs] * B[k*brs+n*bcs] + bias[n]); act 0 none, 1 tanh, 2 relu, 3 sigmoid.
  * splits > 1: split-K with atomic accumulation into C (C must be initialised; bias/act not allowed). */

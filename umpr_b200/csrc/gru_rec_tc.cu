@@ -11,27 +11,32 @@
 //     then 8 gate warps read their TMEM lanes, apply the ATen GRU cell, mask each row by its own length, write the
 //     ImprovedRnn output row in the reference's doubly-permuted order (zeros beyond the length), the saved gates for
 //     backward, and h_t as the next step's bf16 hi/lo A-operand;
-//   * warp roles: 0-7 gates (TMEM lane quarter = warp%4, hidden half = warp/4), 8 MMA issuer, 9 x producer (one TMA bulk copy
-//     of the pre-split bf16 hi/lo token image per step); hand-offs are mbarriers, no __syncthreads in the steady state;
+//   * warp roles: 0-7 gates of slot 0, 8-15 gates of slot 1 (TMEM lane quarter = warp%4, hidden half = (warp/4)%2); warps 16, 17:
+//     one driver thread per slot (TMA bulk copy of the pre-split bf16 hi/lo token image, then the step's tcgen05.mma);
+//     hand-offs are mbarriers, no __syncthreads in the steady state, the two slots never wait for each other;
 //   * several ImprovedRnn calls that share weights (user+item in R-Net, ui+user+item in C-Net) run as "segments" of one
 //     launch; the host orders tiles longest-first into per-slot queues (plan.py) so slots finish together.
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc.cuh"
+#include "gru_tc.cuh"
 #include "../../include/umpr_b200.h"
 
 namespace umpr {
 using namespace tc;
 
-constexpr int RT_GATE_WARPS = 8;
-constexpr int RT_MMA_WARP = 8;
-constexpr int RT_LOAD_WARP0 = 9;
-constexpr int RT_LOAD_WARPS = 1;
-constexpr int RT_THREADS = (RT_GATE_WARPS + 1 + RT_LOAD_WARPS) * 32;   // 320: at most 3 warps per scheduler -> 168 registers
-constexpr int RT_R = 128;                        // sequences per tile = MMA M
+constexpr int RT_GATE_WARPS = 16;                // 8 per slot
+constexpr int RT_THREADS = (RT_GATE_WARPS + 2) * 32;   // 576 (18 warps are allocated as 20: 96 registers per thread)
 constexpr int RT_W_BYTES = 2 * G3 * 128;         // hi | lo, [192][64 bf16]
 constexpr int RT_A_BYTES = 2 * RT_R * 128;       // hi | lo, [128][64 bf16]
 constexpr int RT_SMEM = 2 * RT_W_BYTES + 4 * RT_A_BYTES + 1024;
-constexpr int RT_MAX_SEG = 3;
+
+#ifdef UMPR_TRACE
+#define TRACE(role, X, n, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (n) < 64) a.trace[(((role) * 2 + (X)) * 64 + (n)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(role, X, n, ev) do {} while (0)
+#endif
 
 struct RecSeg {
   const unsigned char* xq; const int* plan; float* out; float* hn; float* sv;
@@ -43,74 +48,8 @@ struct RecArgs {
   const int* q_off; const int* q_tile;
   const float* w[8];
   int E, kx;
+  long long* trace;
 };
-
-// one slot's position in its tile queue; every warp role walks the same deterministic sequence
-struct Cur {
-  int q, qend, s, Lj, tile, si;
-  bool active;
-};
-__device__ __forceinline__ void cur_tile(const RecArgs& a, Cur& c) {
-  const int g = a.q_tile[c.q];
-  int si = 0;
-  if (a.n_seg > 1 && g >= a.seg[1].tile_base) si = 1;
-  if (a.n_seg > 2 && g >= a.seg[2].tile_base) si = 2;
-  c.si = si;
-  c.tile = g - a.seg[si].tile_base;
-  c.Lj = a.seg[si].plan[2 * a.seg[si].n_tiles * RT_R + c.tile * RT_R];    // len_of[tile*R]: the tile's longest job
-  c.s = 0;
-}
-__device__ __forceinline__ void cur_init(const RecArgs& a, Cur& c, int qi) {
-  c.q = a.q_off[qi]; c.qend = a.q_off[qi + 1];
-  c.active = c.q < c.qend;
-  c.s = 0; c.Lj = 0; c.tile = 0; c.si = 0;
-  if (c.active) cur_tile(a, c);
-}
-__device__ __forceinline__ void cur_next(const RecArgs& a, Cur& c) {
-  if (++c.s == c.Lj) {
-    if (++c.q < c.qend) cur_tile(a, c); else c.active = false;
-  }
-}
-
-__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-// wait for the outstanding TMEM loads; the registers are listed as in/out operands so no use can be scheduled above the wait
-__device__ __forceinline__ void tmem_wait8(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-               :: "memory");
-}
-__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void st_zero8(float* p) {
-  *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-
-// In-warp transpose of an 8x8 matrix of float4 inside each group of 8 lanes: before, lane j of a group holds a[k] = float4 #k of
-// ITS row; after, lane j holds a[i] = float4 #j of the group's row i.  A warp-wide 128-bit store of a[i] then writes 4 rows x
-// 128 contiguous bytes (full lines) instead of 32 rows x 16 bytes.  3 butterfly stages, 16 shuffles each.
-__device__ __forceinline__ void transpose8x8_f4(float4 (&a)[8], int lane) {
-#pragma unroll
-  for (int s = 1; s < 8; s <<= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (k & s) continue;
-      float4 snd = up ? a[k] : a[k | s];
-      float4 rcv;
-      rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, s);
-      rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, s);
-      rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, s);
-      rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, s);
-      if (up) a[k] = rcv; else a[k | s] = rcv;
-    }
-  }
-}
 
 // per-slot state of one gate thread: its row of the tile (32 of the 64 hidden units)
 struct GateRow {
@@ -118,11 +57,17 @@ struct GateRow {
   int len, rowo;
 };
 
-template <int X>
-__device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRow& g, int n, int dir, int row, int hf,
+constexpr float K_RZ = -1.4426950408889634f;    // -log2(e): sigmoid(a) = 1 / (1 + 2^(K_RZ a))
+constexpr float K_N = 2.8853900817779268f;      // 2 log2(e): tanh(a) = 1 - 2 / (1 + 2^(K_N a))
+
+// One time step of one slot for one gate thread.  The resident weights are pre-scaled (r,z rows by K_RZ, n rows and b_hn by
+// K_N), so the accumulator columns already hold the exponents.  Straight-line code: every row is computed, rows beyond their
+// length keep their state through one select (their accumulator rows are garbage but never observed).
+__device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const Cur& c, GateRow& g, int n, int dir, int row, int hf,
                                           unsigned char* hs, const float* s_bhn, uint64_t* h_ready, uint64_t* acc_full, uint32_t tmem) {
   const RecSeg& sg = a.seg[c.si];
   const int u0 = hf * 32;
+  const int lane = row & 31;
   unsigned char* h_hi = hs + X * RT_A_BYTES, *h_lo = h_hi + RT_R * 128;
   if (c.s == 0) {
     // tile start: this row's job, h_0 = 0 (registers and the A-operand image)
@@ -143,13 +88,15 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
   }
   const int t = dir ? (c.Lj - 1 - c.s) : c.s;
   const bool live = t < g.len;
-  const int slab0 = sg.plan[3 * sg.n_tiles * RT_R + c.tile];        // tile_off[tile]
   // saved gates, column-major inside the (slab, direction) tile: svT[col = gate*64 + unit][row] -> lanes (= rows) are contiguous
-  float* svcol = sg.sv ? sg.sv + (((size_t)(slab0 + t) * 2 + dir) * SV + u0) * RT_R + row : nullptr;
+  float* svcol = nullptr;
+  if (sg.sv) svcol = sg.sv + (((size_t)(sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t) * 2 + dir) * SV + u0) * RT_R + row;
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16) + X * 256 + u0;
 
+  if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 0);
   mbar_wait(&acc_full[X], n & 1);
   tc_fence_after();
+  if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 1);
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     uint32_t v[32];
@@ -157,48 +104,43 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
     tmem_ld8_issue(trow + 64 + cc * 8, v + 8);
     tmem_ld8_issue(trow + 128 + cc * 8, v + 16);
     tmem_ld8_issue(trow + 192 + cc * 8, v + 24);
-    tmem_wait8(v); tmem_wait8(v + 8); tmem_wait8(v + 16); tmem_wait8(v + 24);
-    if (live) {
-      float rr[8], zz[8], nn[8], hh[8], hv[8];
-      const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8), b1 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8 + 4);
-      const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8), b1 = *reinterpret_cast<const float4*>(s_bhn + u0 + cc * 8 + 4);
+    const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    tmem_ld_wait();
+    float hv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float ar = __uint_as_float(v[i]), az = __uint_as_float(v[8 + i]);
-        const float anx = __uint_as_float(v[16 + i]), anh = __uint_as_float(v[24 + i]);
-        const float er = ex2f(fminf(ar * -1.4426950408889634f, 60.f));
-        const float r = rcpf(1.f + er);                                   // sigmoid
-        const float hcand = anh + bh[i];                                  // W_hn h + b_hn
-        const float xn = fmaf(r, hcand, anx);
-        const float ez = ex2f(fminf(az * -1.4426950408889634f, 60.f));
-        const float en = ex2f(fminf(xn * 2.8853900817779268f, 60.f));    // e^{2 xn}
-        const float dz = 1.f + ez, dn = 1.f + en;
-        const float inv = rcpf(dz * dn);                                  // one reciprocal for z and n
-        const float z = dn * inv;
-        const float nv = fmaf(-2.f * dz, inv, 1.f);                       // tanh(xn) = 1 - 2 / (1 + e^{2 xn})
-        const float hnew = fmaf(g.h[cc * 8 + i] - nv, z, nv);            // ATen GRU cell: (h - n) * z + n
-        rr[i] = r; zz[i] = z; nn[i] = nv; hh[i] = hcand; hv[i] = hnew;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g.h[cc * 8 + i] = hv[i];
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split2(hv[2 * i], hv[2 * i + 1], hi[i], lo[i]);
-      const uint32_t off = (uint32_t)(row * 128 + (((hf * 4 + cc) ^ (row & 7)) << 4));
-      *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    for (int i = 0; i < 8; ++i) {
+      const float er = ex2f(__uint_as_float(v[i]));                     // e^{-a_r}
+      const float r = rcpf(1.f + er);                                   // sigmoid
+      const float hcand = __uint_as_float(v[24 + i]) + bh[i];           // K_N (W_hn h + b_hn)
+      const float xn = fmaf(r, hcand, __uint_as_float(v[16 + i]));      // K_N (n pre-activation)
+      const float ez = ex2f(fminf(__uint_as_float(v[8 + i]), 60.f));    // e^{-a_z}
+      const float en = ex2f(fminf(xn, 60.f));                           // e^{2 a_n}
+      const float dz = 1.f + ez, dn = 1.f + en;
+      const float inv = rcpf(dz * dn);                                  // one reciprocal for z and n
+      const float z = dn * inv;
+      const float nv = fmaf(-2.f * dz, inv, 1.f);                       // tanh(a_n) = 1 - 2 / (1 + e^{2 a_n})
+      const float hold = g.h[cc * 8 + i];
+      const float hnew = fmaf(hold - nv, z, nv);                        // ATen GRU cell: (h - n) * z + n
+      hv[i] = live ? hnew : hold;
       if (svcol) {
-        float* s8 = svcol + (size_t)(cc * 8) * RT_R;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s8[(size_t)i * RT_R] = rr[i];
-          s8[(size_t)(H + i) * RT_R] = zz[i];
-          s8[(size_t)(2 * H + i) * RT_R] = nn[i];
-          s8[(size_t)(3 * H + i) * RT_R] = hh[i];
-        }
+        float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
+        s1[0] = r;
+        s1[(size_t)H * RT_R] = z;
+        s1[(size_t)2 * H * RT_R] = nv;
+        s1[(size_t)3 * H * RT_R] = hcand * (1.f / K_N);
       }
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g.h[cc * 8 + i] = hv[i];
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split2(hv[2 * i], hv[2 * i + 1], hi[i], lo[i]);
+    const uint32_t off = (uint32_t)(row * 128 + (((hf * 4 + cc) ^ (row & 7)) << 4));
+    *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+  if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 2);
   if (c.s + 1 < c.Lj) {
     fence_async_smem();        // h_t image visible to the tensor core's shared-memory reads
     tc_fence_before();
@@ -211,7 +153,6 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       o[k] = live ? make_float4(g.h[4 * k], g.h[4 * k + 1], g.h[4 * k + 2], g.h[4 * k + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int lane = row & 31;
     transpose8x8_f4(o, lane);
     const int my = g.rowo < 0 ? -1 : g.rowo * sg.L + t;
     float* obase = sg.out + dir * H + u0 + (lane & 7) * 4;
@@ -221,31 +162,26 @@ __device__ __forceinline__ void gate_step(const RecArgs& a, const Cur& c, GateRo
       if (ri >= 0) *reinterpret_cast<float4*>(obase + (size_t)ri * D) = o[i];
     }
   }
+  if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 3);
   if (c.s + 1 == c.Lj) {
     // tile end: zero padding up to total_length (model.py:17,20) and h_n in ORIGINAL sequence order
-    {
-      const int lane = row & 31;
-      float* obase = sg.out + dir * H + u0 + (lane & 7) * 4;
+    float* obase = sg.out + dir * H + u0 + (lane & 7) * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int ro = __shfl_sync(0xffffffffu, g.rowo, (lane & 24) + i);
-        if (ro < 0) continue;
-        for (int tt = c.Lj; tt < sg.L; ++tt)
-          *reinterpret_cast<float4*>(obase + ((size_t)ro * sg.L + tt) * D) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int ro = __shfl_sync(0xffffffffu, g.rowo, (lane & 24) + i);
+      if (ro < 0) continue;
+      for (int tt = c.Lj; tt < sg.L; ++tt)
+        *reinterpret_cast<float4*>(obase + ((size_t)ro * sg.L + tt) * D) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (g.rowo >= 0) {
-      if (sg.hn) {
-        const int seq = sg.plan[c.tile * RT_R + row];
-        float* hp = sg.hn + ((size_t)dir * sg.N + seq) * H + u0;
+    if (g.rowo >= 0 && sg.hn) {
+      const int seq = sg.plan[c.tile * RT_R + row];
+      float* hp = sg.hn + ((size_t)dir * sg.N + seq) * H + u0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(hp + i * 4) = make_float4(g.h[i * 4], g.h[i * 4 + 1], g.h[i * 4 + 2], g.h[i * 4 + 3]);
-      }
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(hp + i * 4) = make_float4(g.h[i * 4], g.h[i * 4 + 1], g.h[i * 4 + 2], g.h[i * 4 + 3]);
     }
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // embedding gather + length-aware pack straight into tensor-core operand images (model.py:262-264 + the pack half of :18):
@@ -286,7 +222,7 @@ __global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __rest
 
 __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_constant__ RecArgs a) {
   extern __shared__ unsigned char raw[];
-  __shared__ uint64_t x_full[2], x_empty[2], h_ready[2], acc_full[2];
+  __shared__ uint64_t x_full[2], x_empty[2], h_ready[2], acc_full[2], stagger;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bhn[H];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
@@ -301,27 +237,31 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
-      mbar_init(&h_ready[s], RT_GATE_WARPS * 32);
+      mbar_init(&h_ready[s], RT_GATE_WARPS * 16);
       mbar_init(&acc_full[s], 1);
     }
+    mbar_init(&stagger, RT_GATE_WARPS * 16);
     mbar_fence_init();
   }
-  if (warp == RT_MMA_WARP) tmem_alloc(&tmem_slot, 512);
+  if (warp == RT_GATE_WARPS) tmem_alloc(&tmem_slot, 512);
   {
-    // resident weights of this direction: W_ih with column E = b_ih (+ b_hh for r,z) (multiplied by xp's 1.0 column), W_hh
+    // resident weights of this direction, pre-scaled so the accumulators are base-2 exponents (see gate_step):
+    // W_ih with column E = b_ih (+ b_hh for r,z) (multiplied by the packed tokens' 1.0 column), W_hh, b_hn
     const float* w_ih = a.w[dir * 4 + 0], *w_hh = a.w[dir * 4 + 1], *b_ih = a.w[dir * 4 + 2], *b_hh = a.w[dir * 4 + 3];
     for (int idx = tid; idx < G3 * 16; idx += RT_THREADS) {
       const int n = idx >> 4, k = (idx & 15) * 4;
+      const float sc = n < 2 * H ? K_RZ : K_N;
       float t[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int kk = k + q;
-        t[q] = kk < a.E ? w_ih[(size_t)n * a.E + kk] : (kk == a.E ? b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f) : 0.f);
+        t[q] = sc * (kk < a.E ? w_ih[(size_t)n * a.E + kk] : (kk == a.E ? b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f) : 0.f));
       }
       store_split4(wih, wih + G3 * 128, n, k, make_float4(t[0], t[1], t[2], t[3]));
-      store_split4(whh, whh + G3 * 128, n, k, *reinterpret_cast<const float4*>(w_hh + n * H + k));
+      const float4 wh = *reinterpret_cast<const float4*>(w_hh + n * H + k);
+      store_split4(whh, whh + G3 * 128, n, k, make_float4(sc * wh.x, sc * wh.y, sc * wh.z, sc * wh.w));
     }
-    if (tid < H) s_bhn[tid] = b_hh[2 * H + tid];
+    if (tid < H) s_bhn[tid] = K_N * b_hh[2 * H + tid];
   }
   fence_async_smem();
   tc_fence_before();
@@ -329,83 +269,79 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  Cur c[2];
-  cur_init(a, c[0], 2 * blockIdx.x);
-  cur_init(a, c[1], 2 * blockIdx.x + 1);
-  int n[2] = {0, 0};                       // steps done per slot (mbarrier phase bookkeeping)
-
   if (warp < RT_GATE_WARPS) {
-    // ------------------------------------------------------------------ gate warps
-    const int row = (warp & 3) * 32 + lane, hf = warp >> 2;
-    GateRow g0, g1;
-    g0.len = g1.len = 0; g0.rowo = g1.rowo = -1;
-    while (c[0].active || c[1].active) {
-      if (c[0].active) { gate_step<0>(a, c[0], g0, n[0], dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem); ++n[0]; cur_next(a, c[0]); }
-      if (c[1].active) { gate_step<1>(a, c[1], g1, n[1], dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem); ++n[1]; cur_next(a, c[1]); }
+    // ------------------------------------------------------------------ gate warps: warps 0-7 serve slot 0, warps 8-15 slot 1
+    const int X = warp >> 3;
+    const int row = (warp & 3) * 32 + lane, hf = (warp >> 2) & 1;
+    GateRow g;
+    g.len = 0; g.rowo = -1;
+    Cur c;
+    cur_init(a, c, 2 * blockIdx.x + X);
+    for (int n = 0; c.active; ++n) {
+      gate_step(X, a, c, g, n, dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem);
+      if (X == 0 && n == 0) mbar_arrive(&stagger);
+      cur_next(a, c);
     }
-  } else if (warp == RT_MMA_WARP) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
-      const uint64_t wih_h = smem_desc_sw128(smem_u32(wih)), wih_l = smem_desc_sw128(smem_u32(wih + G3 * 128));
-      const uint64_t whh_h = smem_desc_sw128(smem_u32(whh)), whh_l = smem_desc_sw128(smem_u32(whh + G3 * 128));
-      const uint64_t whn_h = smem_desc_sw128(smem_u32(whh + 128 * 128)), whn_l = smem_desc_sw128(smem_u32(whh + G3 * 128 + 128 * 128));
-      while (c[0].active || c[1].active) {
-#pragma unroll
-        for (int X = 0; X < 2; ++X) {
-          if (!c[X].active) continue;
-          const uint32_t d = tmem + X * 256;
-          const uint64_t x_h = smem_desc_sw128(smem_u32(xs + X * RT_A_BYTES)), x_l = smem_desc_sw128(smem_u32(xs + X * RT_A_BYTES + RT_R * 128));
-          const uint64_t h_h = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES)), h_l = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES + RT_R * 128));
-          mbar_wait(&x_full[X], n[X] & 1);
-          mbar_wait(&h_ready[X], n[X] & 1);       // h_{t-1} image written AND the slot's accumulator columns drained
-          tc_fence_after();
-          for (int kk = 0; kk < a.kx; ++kk) {     // x_t · W_ih^T  -> r, z, n_x  (overwrites)
-            const uint64_t o = (uint64_t)(kk * 2);
-            umma_bf16(d, x_h + o, wih_h + o, id192, kk != 0);
-            umma_bf16(d, x_h + o, wih_l + o, id192, 1);
-            umma_bf16(d, x_l + o, wih_h + o, id192, 1);
-          }
-          umma_commit(&x_empty[X]);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {        // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
-            const uint64_t o = (uint64_t)(kk * 2);
-            umma_bf16(d, h_h + o, whh_h + o, id128, 1);
-            umma_bf16(d, h_h + o, whh_l + o, id128, 1);
-            umma_bf16(d, h_l + o, whh_h + o, id128, 1);
-            umma_bf16(d + 192, h_h + o, whn_h + o, id64, kk != 0);
-            umma_bf16(d + 192, h_h + o, whn_l + o, id64, 1);
-            umma_bf16(d + 192, h_l + o, whn_h + o, id64, 1);
-          }
-          umma_commit(&acc_full[X]);
-          ++n[X];
-          cur_next(a, c[X]);
-        }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ slot drivers (warp 16: slot 0, warp 17: slot 1), one thread each:
+    // TMA producer of the packed-token image AND tcgen05.mma issuer of its slot
+    const int X = warp - RT_GATE_WARPS;
+    constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
+    const uint64_t wih_h = smem_desc_sw128(smem_u32(wih)), wih_l = smem_desc_sw128(smem_u32(wih + G3 * 128));
+    const uint64_t whh_h = smem_desc_sw128(smem_u32(whh)), whh_l = smem_desc_sw128(smem_u32(whh + G3 * 128));
+    const uint64_t whn_h = smem_desc_sw128(smem_u32(whh + 128 * 128)), whn_l = smem_desc_sw128(smem_u32(whh + G3 * 128 + 128 * 128));
+    unsigned char* xbuf = xs + X * RT_A_BYTES;
+    const uint64_t x_h = smem_desc_sw128(smem_u32(xbuf)), x_l = smem_desc_sw128(smem_u32(xbuf + RT_R * 128));
+    const uint64_t h_h = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES)), h_l = smem_desc_sw128(smem_u32(hs + X * RT_A_BYTES + RT_R * 128));
+    const uint32_t d = tmem + X * 256;
+    Cur c;
+    cur_init(a, c, 2 * blockIdx.x + X);
+    auto load_x = [&]() {       // the token image is already bf16 hi|lo, SWIZZLE_128B (gather_pack_tc_kernel): 32 KB land as they are
+      const RecSeg& sg = a.seg[c.si];
+      const int t = dir ? (c.Lj - 1 - c.s) : c.s;
+      const int slab = sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t;
+      mbar_arrive_expect_tx(&x_full[X], RT_A_BYTES);
+      bulk_copy_g2s(xbuf, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
+    };
+    if (c.active) load_x();
+    // start slot 1 half a period late: its MMAs then run under slot 0's gate math and vice versa (anti-phase is self-sustaining)
+    if (X == 1 && c.active) mbar_wait(&stagger, 0);
+    for (int n = 0; c.active; ++n) {
+      TRACE(1, X, n, 0);
+      mbar_wait(&x_full[X], n & 1);
+      TRACE(1, X, n, 1);
+      mbar_wait(&h_ready[X], n & 1);            // h_{t-1} image written AND the slot's accumulator columns drained
+      tc_fence_after();
+      TRACE(1, X, n, 2);
+      for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16(d, x_h + o, wih_h + o, id192, kk != 0);
+        umma_bf16(d, x_h + o, wih_l + o, id192, 1);
+        umma_bf16(d, x_l + o, wih_h + o, id192, 1);
       }
-    }
-  } else {
-    // ------------------------------------------------------------------ x producer: one TMA bulk copy per (slot, step)
-    // the packed token image is already bf16 hi|lo, SWIZZLE_128B (gather_pack_tc_kernel): 32 KB land in the A-operand buffer as is
-    if (lane == 0) {
-      while (c[0].active || c[1].active) {
+      umma_commit(&x_empty[X]);
 #pragma unroll
-        for (int X = 0; X < 2; ++X) {
-          if (!c[X].active) continue;
-          const RecSeg& sg = a.seg[c[X].si];
-          const int t = dir ? (c[X].Lj - 1 - c[X].s) : c[X].s;
-          const int slab = sg.plan[3 * sg.n_tiles * RT_R + c[X].tile] + t;
-          if (n[X] > 0) mbar_wait(&x_empty[X], (n[X] - 1) & 1);
-          mbar_arrive_expect_tx(&x_full[X], RT_A_BYTES);
-          bulk_copy_g2s(xs + X * RT_A_BYTES, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
-          ++n[X];
-          cur_next(a, c[X]);
-        }
+      for (int kk = 0; kk < 4; ++kk) {          // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16(d, h_h + o, whh_h + o, id128, 1);
+        umma_bf16(d, h_h + o, whh_l + o, id128, 1);
+        umma_bf16(d, h_l + o, whh_h + o, id128, 1);
+        umma_bf16(d + 192, h_h + o, whn_h + o, id64, kk != 0);
+        umma_bf16(d + 192, h_h + o, whn_l + o, id64, 1);
+        umma_bf16(d + 192, h_l + o, whn_h + o, id64, 1);
+      }
+      umma_commit(&acc_full[X]);
+      TRACE(1, X, n, 3);
+      cur_next(a, c);
+      if (c.active) {
+        mbar_wait(&x_empty[X], n & 1);          // the x-part MMAs of this step have consumed the buffer
+        load_x();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == RT_MMA_WARP) tmem_dealloc(tmem, 512);
+  if (warp == RT_GATE_WARPS) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace umpr
@@ -441,8 +377,33 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
   for (int i = 0; i < 8; ++i) a.w[i] = w[i];
   a.E = E;
   a.kx = (E + 1 + 15) / 16;
+#ifdef UMPR_TRACE
+  static long long* tr = nullptr;
+  if (!tr) cudaMalloc(&tr, 3 * 2 * 64 * 4 * sizeof(long long));
+  cudaMemsetAsync(tr, 0, 3 * 2 * 64 * 4 * sizeof(long long), (cudaStream_t)stream);
+  a.trace = tr;
+#else
+  a.trace = nullptr;
+#endif
   cudaError_t e = cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM);
   if (e != cudaSuccess) { set_error("gru_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   gru_fwd_tc_kernel<<<dim3(n_queues / 2, 2), RT_THREADS, RT_SMEM, (cudaStream_t)stream>>>(a);
+#ifdef UMPR_TRACE
+  {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    static long long host[3 * 2 * 64 * 4];
+    cudaMemcpy(host, tr, sizeof(host), cudaMemcpyDeviceToHost);
+    FILE* f = fopen("gpurun_out/gru_trace.txt", "w");
+    if (f) {
+      long long t0 = host[(1 * 2 + 0) * 64 * 4];
+      for (int role = 0; role < 3; ++role) for (int X = 0; X < 2; ++X) for (int n = 0; n < 24; ++n) {
+        fprintf(f, "role %d slot %d step %2d:", role, X, n);
+        for (int ev = 0; ev < 4; ++ev) fprintf(f, " %8lld", host[((role * 2 + X) * 64 + n) * 4 + ev] ? host[((role * 2 + X) * 64 + n) * 4 + ev] - t0 : -1);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+#endif
   return check_launch("gru_fwd_tc");
 }

@@ -158,9 +158,8 @@ class _GruTcFn(Function):
         sched = sched.pin_memory().to(dev, non_blocking=True)
         call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
              work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
-        ctx.plans, ctx.E, ctx.n = plans, E, n
+        ctx.plans, ctx.E, ctx.n, ctx.sched, ctx.nq = plans, E, n, sched, nq
         ctx.save_for_backward(*xps, *outs, *[t for t in svs if t is not None], *w)
-        ctx.has_sv = need_grad
         res = list(outs)
         for hn in hns:
             if hn is None:
@@ -183,17 +182,22 @@ class _GruTcFn(Function):
             grads.append(flat[o:o + t.numel()].view_as(t))
             o += t.numel()
         wp, gp = ptr_array(w), ptr_array(grads)
+        segs = (_lib.GruBwdSeg * n)()
+        keep, dGs, tokens = [], [], 0
         for i, plan in enumerate(plans):
             d_out, d_hn = grads_in[i], grads_in[n + i]
-            if d_out is None and (d_hn is None or not d_hn.numel()):
-                continue
-            N, L, R = plan.N, plan.L, plan.R
             d_out = _f32(d_out) if d_out is not None else torch.zeros_like(outs[i])
             d_hn = _f32(d_hn) if (d_hn is not None and d_hn.numel()) else None
-            dG = torch.empty(plan.n_slabs * 2 * R * SV, dtype=torch.float32, device=dev)
-            call("umpr_gru_recurrence_bwd", ptr(d_out), ptr(d_hn), ptr(outs[i]), ptr(svs[i]), wp, ptr(plan.buf), plan.n_tiles,
-                 plan.n_slabs, R, N, L, ptr(dG), work=(2.0 * plan.tokens * 2 * H * 3 * H, 0.0))
-            call("umpr_gru_wgrad_tc", ptr(dG), ptr(xps[i]), ptr(outs[i]), ptr(plan.buf), plan.n_tiles, plan.n_slabs, R, L, E, gp,
+            dG = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev)
+            segs[i] = _lib.GruBwdSeg(ptr(d_out), ptr(d_hn), ptr(outs[i]), ptr(svs[i]), ptr(dG), ptr(plan.buf), plan.n_tiles,
+                                     plan.n_slabs, plan.N, plan.L)
+            keep += [d_out, d_hn]
+            dGs.append(dG)
+            tokens += plan.tokens
+        # one reverse-time launch over every side (same tile queues as the forward), then the weight gradients per side
+        call("umpr_gru_bwd_tc", C.addressof(segs), n, wp, ptr(ctx.sched), ctx.nq, work=(2.0 * tokens * 2 * H * 3 * H, 0.0))
+        for i, plan in enumerate(plans):
+            call("umpr_gru_wgrad_tc2", ptr(dGs[i]), ptr(xps[i]), ptr(outs[i]), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.L, E, gp,
                  _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
         return (None, None, None, None, None, *grads)
 

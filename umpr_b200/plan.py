@@ -32,9 +32,10 @@ def build_schedule(tile_lens, n_ctas: int):
     """Tile queues of one fused GRU launch (umpr_gru_fwd_tc / umpr_gru_bwd_tc).
 
     ``tile_lens``: one int sequence per segment (steps of every 128-row tile, already descending inside a segment).
-    Tiles of all segments get global ids (segment bases are cumulative tile counts) and are dealt longest-first to
-    ``n_ctas`` CTAs in boustrophedon order, pass p filling slot p % 2 of each CTA, so the two slots of a CTA — which
-    ping-pong between tensor pipe and gate math — and all CTAs finish at about the same step.
+    Tiles of all segments get global ids (segment bases are cumulative tile counts) and are dealt longest-first, in
+    boustrophedon order, to the 2*G slot queues of G = min(n_ctas, T) CTAs (queue order: slot 0 of every CTA, then slot 1 of
+    every CTA, so few tiles spread over CTAs first).  A CTA's run time is its longer slot's step count, so it is the SLOT
+    queues that are levelled; the two slots of a CTA ping-pong between tensor pipe and gate math.
     → (int32 tensor ``[q_off (2*G+1) | q_tile (T)]``, n_queues = 2*G); CTA c owns queues 2c and 2c+1.
     """
     import numpy as np
@@ -43,14 +44,15 @@ def build_schedule(tile_lens, n_ctas: int):
     if T == 0:
         raise RuntimeError("umpr_b200: empty GRU launch")
     G = max(1, min(int(n_ctas), T))
+    Q = 2 * G
     order = np.argsort(-lens, kind="stable")
     i = np.arange(T)
-    p, pos = i // G, i % G
-    cta = np.where(p % 2 == 0, pos, G - 1 - pos)
-    queue = 2 * cta + (p % 2)
+    p, pos = i // Q, i % Q
+    sq = np.where(p % 2 == 0, pos, Q - 1 - pos)             # slot queue in dealing order: [slot 0 of CTA 0..G-1 | slot 1 of CTA 0..G-1]
+    queue = 2 * (sq % G) + sq // G                          # kernel order: CTA c reads queues 2c (slot 0) and 2c+1 (slot 1)
     by_q = np.argsort(queue, kind="stable")                 # stable: tiles stay longest-first inside a queue
     q_tile = order[by_q]
-    counts = np.bincount(queue, minlength=2 * G)
+    counts = np.bincount(queue, minlength=Q)
     q_off = np.concatenate([[0], np.cumsum(counts)])
     return torch.from_numpy(np.concatenate([q_off, q_tile]).astype(np.int32)), 2 * G
 
