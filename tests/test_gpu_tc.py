@@ -124,7 +124,7 @@ def test_fused_gru_forward_matches_cuda_core_path(sides, E, ctas):
         segs[i] = _lib.GruSeg(ptr(xp), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, N, L)
         got.append((out, hn, sv))
     sched, nq = build_schedule([p.tile_len for p in plans], ctas)
-    sched = sched.to(DEV)
+    sched = torch.from_numpy(sched).to(DEV)
     call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq)
     torch.cuda.synchronize()
     for i, ((o0, h0, s0), (o1, h1, s1)) in enumerate(zip(refs, got)):

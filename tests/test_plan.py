@@ -75,7 +75,6 @@ def test_schedule_covers_every_tile_once_and_balances(sizes, ctas):
     rs = np.random.RandomState(sum(sizes))
     tile_lens = [np.sort(rs.randint(1, 21, size=n))[::-1] for n in sizes]
     sched, nq = build_schedule(tile_lens, ctas)
-    sched = sched.numpy()
     T = sum(sizes)
     assert nq % 2 == 0 and nq // 2 == min(ctas, T) and sched.size == nq + 1 + T
     q_off, q_tile = sched[:nq + 1], sched[nq + 1:]

@@ -115,7 +115,7 @@ def ptr_array(tensors):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)

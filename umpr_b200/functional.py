@@ -5,6 +5,7 @@ Each Function cites the reference lines (``src/model.py``) whose forward+backwar
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch.autograd import Function
@@ -18,7 +19,7 @@ H, D, ATT, KP, SV = 64, 128, 64, 64, 256
 TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
-TENSOR_CORE_COATTN = False     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
+TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "0") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
 def _f32(t):
@@ -153,9 +154,9 @@ class _GruTcFn(Function):
             segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
             outs.append(out); hns.append(hn); svs.append(sv)
             tokens += plan.tokens
-        from .plan import build_schedule
+        from .plan import build_schedule, upload_int32
         sched, nq = build_schedule([p.tile_len for p in plans], max(1, _n_ctas(dev) // 2))
-        sched = sched.pin_memory().to(dev, non_blocking=True)
+        sched = upload_int32(sched, dev)
         call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
              work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
         ctx.plans, ctx.E, ctx.n, ctx.sched, ctx.nq = plans, E, n, sched, nq

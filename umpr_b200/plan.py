@@ -36,7 +36,7 @@ def build_schedule(tile_lens, n_ctas: int):
     boustrophedon order, to the 2*G slot queues of G = min(n_ctas, T) CTAs (queue order: slot 0 of every CTA, then slot 1 of
     every CTA, so few tiles spread over CTAs first).  A CTA's run time is its longer slot's step count, so it is the SLOT
     queues that are levelled; the two slots of a CTA ping-pong between tensor pipe and gate math.
-    → (int32 tensor ``[q_off (2*G+1) | q_tile (T)]``, n_queues = 2*G); CTA c owns queues 2c and 2c+1.
+    → (int32 numpy array ``[q_off (2*G+1) | q_tile (T)]``, n_queues = 2*G); CTA c owns queues 2c and 2c+1.
     """
     import numpy as np
     lens = np.concatenate([np.asarray(t, dtype=np.int64).reshape(-1) for t in tile_lens])
@@ -54,7 +54,48 @@ def build_schedule(tile_lens, n_ctas: int):
     q_tile = order[by_q]
     counts = np.bincount(queue, minlength=Q)
     q_off = np.concatenate([[0], np.cumsum(counts)])
-    return torch.from_numpy(np.concatenate([q_off, q_tile]).astype(np.int32)), 2 * G
+    return np.concatenate([q_off, q_tile]).astype(np.int32), 2 * G
+
+
+class _PinnedRing:
+    """Small ring of pinned host buffers for the per-step int32 plan / schedule uploads (cudaHostAlloc per step is far too
+    slow, and a pageable source can stall the host behind queued GPU work).  A slot is reused only after the copy that last
+    read it has completed (event)."""
+
+    def __init__(self, slots=64):
+        self.bufs, self.events, self.i, self.slots = [None] * slots, [None] * slots, 0, slots
+
+    def upload(self, arr, device):
+        import numpy as np
+        i = self.i
+        self.i = (i + 1) % self.slots
+        n = int(arr.size)
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        if self.bufs[i] is None or self.bufs[i].numel() < n:
+            self.bufs[i] = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
+        host = self.bufs[i][:n]
+        host.numpy()[:] = np.asarray(arr, dtype=np.int32).reshape(-1)
+        dev = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+        return dev
+
+
+_RINGS = {}
+
+
+def upload_int32(arr, device):
+    """int32 numpy array → device tensor through the pinned ring of that device (plain copy for CPU 'devices')."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        import numpy as np
+        return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32))
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _RINGS:
+        _RINGS[key] = _PinnedRing()
+    return _RINGS[key].upload(arr, device)
 
 
 class PackPlan:
@@ -66,45 +107,55 @@ class PackPlan:
     """
 
     def __init__(self, lengths: torch.Tensor, total_length: int, device, tile_rows: int | None = None):
+        import numpy as np
         lens = lengths.detach().to("cpu", torch.int64).reshape(-1)          # model.py:18 lengths.cpu()
         n = lens.numel()
         if n == 0:
             raise RuntimeError("umpr_b200: ImprovedRnn needs at least one sequence")
-        if int(lens.min()) < 1:
+        sorted_len, sorted_idx = torch.sort(lens, descending=True)          # the reference's call, not a re-implementation
+        if int(sorted_len[-1]) < 1:
             # same failure as torch.nn.utils.rnn.pack_padded_sequence
             raise RuntimeError("Length of all samples has to be greater than 0, but found an element in 'lengths' that is <= 0")
-        if int(lens.max()) > total_length:
-            raise RuntimeError(f"umpr_b200: a sequence length ({int(lens.max())}) exceeds the padded length ({total_length})")
-        sorted_len, sorted_idx = torch.sort(lens, descending=True)          # the reference's call, not a re-implementation
-        unsorted = torch.empty_like(sorted_idx)
-        unsorted[sorted_idx] = torch.arange(n, dtype=torch.int64)
+        if int(sorted_len[0]) > total_length:
+            raise RuntimeError(f"umpr_b200: a sequence length ({int(sorted_len[0])}) exceeds the padded length ({total_length})")
         self.N, self.L = n, int(total_length)
         self.lengths = lens
-        self.sorted_lengths, self.sorted_indices, self.unsorted_indices = sorted_len, sorted_idx, unsorted
+        self.sorted_lengths, self.sorted_indices = sorted_len, sorted_idx
+        self._unsorted = None
         self.device = torch.device(device)
         self.R = tile_rows or choose_tile_rows(n, _lib.sm_count(self.device) if self.device.type == "cuda" else 148)
         assert self.R in TILE_ROWS
         R = self.R
         self.n_tiles = (n + R - 1) // R
         rp = self.n_tiles * R
-        pad = rp - n
-        z = torch.zeros(pad, dtype=torch.int64)
-        seq_of = torch.cat([sorted_idx, z])
-        row_of = torch.cat([sorted_idx[sorted_idx], z - 1])                  # output row fed by job k
-        len_of = torch.cat([sorted_len, z])
-        tile_len = len_of[::R]
+        # everything below is integer indexing of the reference's permutation, done in numpy (this runs every step)
+        si, sl = sorted_idx.numpy(), sorted_len.numpy()
+        tile_len = np.zeros(self.n_tiles, dtype=np.int64)
+        tile_len[:] = sl[::R]
         self.tile_len = tile_len
-        tile_off = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(tile_len, 0)])
-        self.n_slabs = int(tile_off[-1])
-        slab_tile = torch.repeat_interleave(torch.arange(self.n_tiles, dtype=torch.int64), tile_len)
-        host = torch.cat([seq_of, row_of, len_of, tile_off, slab_tile]).to(torch.int32)
-        self.host = host
-        self.tokens = int(lens.sum())                                        # T_v: valid tokens
+        self.n_slabs = int(tile_len.sum())
+        host = np.empty(3 * rp + self.n_tiles + 1 + self.n_slabs, dtype=np.int32)
+        host[:n] = si                                                        # seq_of
+        host[n:rp] = 0
+        host[rp:rp + n] = si[si]                                             # row_of: output row fed by job k (model.py:21)
+        host[rp + n:2 * rp] = -1
+        host[2 * rp:2 * rp + n] = sl                                         # len_of
+        host[2 * rp + n:3 * rp] = 0
+        host[3 * rp] = 0
+        np.cumsum(tile_len, out=host[3 * rp + 1:3 * rp + 1 + self.n_tiles])  # tile_off
+        host[3 * rp + 1 + self.n_tiles:] = np.repeat(np.arange(self.n_tiles, dtype=np.int32), tile_len)   # slab_tile
+        self.host = torch.from_numpy(host)
+        self.tokens = int(sl.sum())                                          # T_v: valid tokens
         self.slots = self.n_slabs * R                                        # token slots actually computed
-        if self.device.type == "cuda":
-            self.buf = host.pin_memory().to(self.device, non_blocking=True)
-        else:
-            self.buf = host
+        self.buf = upload_int32(host, self.device)
+
+    @property
+    def unsorted_indices(self) -> torch.Tensor:
+        if self._unsorted is None:
+            u = torch.empty_like(self.sorted_indices)
+            u[self.sorted_indices] = torch.arange(self.N, dtype=torch.int64)
+            self._unsorted = u
+        return self._unsorted
 
     @property
     def row_src(self) -> torch.Tensor:
