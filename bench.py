@@ -27,8 +27,19 @@ METRIC = "UMPR train samples/sec (device-timed, fwd+bwd+allreduce+Adam)"
 UNIT = "samples/s"
 
 # which roofline bounds each entry point: dense contractions -> tensor pipe, the rest -> HBM
-TENSOR_BOUND = {"umpr_gru_inproj", "umpr_gru_recurrence_fwd", "umpr_gru_recurrence_bwd", "umpr_gru_wgrad", "umpr_sgemm",
-                "umpr_coattn_fwd", "umpr_snet_fwd", "umpr_snet_bwd", "umpr_cnet_conv_fwd"}
+TENSOR_BOUND = {"umpr_gru_inproj", "umpr_gru_inproj_tc", "umpr_gru_recurrence_fwd", "umpr_gru_recurrence_bwd", "umpr_gru_wgrad",
+                "umpr_gru_wgrad_tc", "umpr_gru_wgrad_tc2", "umpr_gru_fwd_tc", "umpr_gru_bwd_tc", "umpr_sgemm", "umpr_tc_gemm_ws",
+                "umpr_tc_gemm_nt", "umpr_coattn_fwd", "umpr_coattn_fwd_tc", "umpr_snet_fwd", "umpr_snet_bwd", "umpr_cnet_conv_fwd",
+                "umpr_cnet_conv_fwd_tc"}
+# arithmetic each entry point runs in (everything is fp32 in and out; "3xBF16" = fp32 operands split into bf16 hi+lo, fp32 accumulate)
+MATH = {"umpr_gru_fwd_tc": "tcgen05 kind::f16, 3xBF16 split, fp32 accumulation in TMEM; gates fp32 (ex2/rcp approx)",
+        "umpr_gru_bwd_tc": "tcgen05 (A operand in tensor memory), 3xBF16; element-wise fp32",
+        "umpr_gru_wgrad_tc2": "tcgen05 3xBF16, fp32 TMEM accumulation over each CTA's token range",
+        "umpr_tc_gemm_ws": "tcgen05 3xBF16", "umpr_tc_gemm_nt": "tcgen05 3xBF16", "umpr_cnet_conv_fwd_tc": "tcgen05 3xBF16 + exact fp32 re-scoring of near-ties",
+        "umpr_coattn_fwd_tc": "tcgen05 3xBF16 + exact fp32 re-scoring of near-ties"}
+# the kernels BASELINE.json's north_star names: reported next to the dominant one
+NAMED = ["umpr_gru_fwd_tc", "umpr_gru_bwd_tc", "umpr_gru_wgrad_tc2", "umpr_gather_pack_tc", "umpr_gather_pack", "umpr_coattn_fwd", "umpr_coattn_bwd",
+         "umpr_snet_fwd", "umpr_snet_bwd"]
 
 
 def load_peaks():
@@ -268,23 +279,35 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
     }
-    # ---- roofline of the dominant kernel (event-timed on the launching stream inside the timed region)
-    bound = "tensor" if top in TENSOR_BOUND else "hbm"
-    per_launch_ms = kt["ms"] / max(1, kt["calls"])
-    if bound == "tensor":
-        achieved = kt["flops"] / max(1, kt["calls"]) / (per_launch_ms * 1e-3) / 1e12
-        peak, unit = peaks["tf_sust"], "TFLOP/s"
-    else:
-        achieved = kt["bytes"] / max(1, kt["calls"]) / (per_launch_ms * 1e-3) / 1e9
-        peak, unit = peaks["hbm"], "GB/s"
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    # ---- rooflines (algorithmic work per SURVEY.md §8d ÷ CUDA-event time on the launching stream).  `roofline`: the dominant
+    # entry point, event-timed inside the timed region; `rooflines`: the kernels north_star names, from the all-kernel-timed step.
+    ncu = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_metrics.json")      # per-launch ncu counters copied from profiles/ (static evidence)
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(top)
-    line["roofline"] = {"kernel": top, "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit,
-                        "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peaks["src"] + (" bf16 dense sustained" if bound == "tensor" else " copy"),
-                        "launch_ms": round(per_launch_ms, 4), "share_of_step": round(kt["ms"] / ms, 4),
-                        "math": "fp32 CUDA cores (round 1); algorithmic FLOPs per SURVEY.md §8d"}
+        ncu = json.load(open(tp))
+
+    def roof(name, t, in_region):
+        bound = "tensor" if name in TENSOR_BOUND else "hbm"
+        calls = max(1, t["calls"])
+        per_launch_ms = t["ms"] / calls
+        if bound == "tensor":
+            achieved, peak, unit = t["flops"] / calls / (per_launch_ms * 1e-3) / 1e12, peaks["tf_sust"], "TFLOP/s"
+        else:
+            achieved, peak, unit = t["bytes"] / calls / (per_launch_ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+        m = ncu.get(name, {})
+        r = {"kernel": name, "bound": bound, "achieved": round(achieved, 3), "peak": peak, "unit": unit, "frac": round(achieved / peak, 5),
+             "traffic": m.get("dram_bytes_per_launch"), "peak_source": peaks["src"] + (" bf16 dense sustained" if bound == "tensor" else " copy"),
+             "launch_ms": round(per_launch_ms, 4), "launches_per_step": t["calls"] // (K if in_region else 1),
+             "math": MATH.get(name, "fp32 CUDA cores")}
+        if "tensor_pipe_active_pct" in m:
+            r["ncu_tensor_pipe_active_pct"] = m["tensor_pipe_active_pct"]        # sm__pipe_tensor_cycles_active (3 issued MMAs per algorithmic one)
+        if "dram_pct" in m:
+            r["ncu_dram_pct"] = m["dram_pct"]
+        return r
+
+    line["roofline"] = roof(top, kt, True)
+    line["roofline"]["share_of_step"] = round(kt["ms"] / ms, 4)
+    line["rooflines"] = [roof(k, table_ms[k], False) for k in NAMED if k in table_ms]
     line["kernel_table_ms"] = {k: round(v["ms"], 3) for k, v in sorted(table_ms.items(), key=lambda kv: -kv[1]["ms"])[:8]}
 
     if world == 1 and rank == 0:
