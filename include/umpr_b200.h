@@ -66,7 +66,8 @@ typedef struct umpr_gru_seg {
   const int32_t* plan;    /* pack plan with R = 128 */
   float* out;             /* (N,L,128), fully written */
   float* hn;              /* (2,N,64) or NULL */
-  float* sv;              /* [n_slabs][2][128][256] or NULL (inference) */
+  float* sv;              /* [n_slabs][2][256][128] saved gates (column-major inside a tile) or NULL (inference) */
+  void* hq;               /* [n_slabs][2][hi|lo][128][64 bf16] h_t operand images for the backward kernel, or NULL (inference) */
   int32_t n_tiles, n_slabs, N, L;
 } umpr_gru_seg;
 /* xq[n_slabs][hi|lo][128][64 bf16]: gathered + packed tokens as SWIZZLE_128B bf16 hi/lo operand images (E values, 1.0, zeros) */
@@ -75,21 +76,24 @@ int umpr_gather_pack_tc(const float* table, const int64_t* ids, const float* den
 int umpr_gru_fwd_tc(const umpr_gru_seg* segs /*host array*/, int n_seg, const float* const* w, int E, const int32_t* sched,
                     int n_queues, void* stream);
 
-/* backward of umpr_gru_fwd_tc's recurrence (same tiles, queues and segments, reverse time): the carry product
- * [dr, dz, dn*r]·W_hh runs on tcgen05 with its A operand written into tensor memory; sv = the forward's saved gates,
- * dG[n_slabs][2][256][128] = [dr, dz, dn, dn*r] pre-activation gradients, both column-major inside a (slab, direction) tile. */
+/* backward of umpr_gru_fwd_tc (same tiles, queues and segments, reverse time), recurrence AND weight gradients in one kernel:
+ * the carry product [dr, dz, dn*r]·W_hh runs on tcgen05 with its A operand written into tensor memory, the weight-gradient
+ * product [xq | hq]^T·[dr, dz, dn, dn*r] accumulates in tensor memory over each CTA's queue - the gate gradients never reach
+ * HBM.  sv, xq, hq: what the forward launch read / wrote.  dw[8] (+=): gradients of the 8 GRU tensors (nn.GRU order).
+ * zero_img: 32 KB of zeros (h_{t-1} of a sequence's first step). */
 typedef struct umpr_gru_bwd_seg {
   const float* d_out;     /* (N,L,128) gradient of the ImprovedRnn result */
   const float* d_hn;      /* (2,N,64) or NULL */
-  const float* out;       /* (N,L,128) forward result (h_{t-1} is read from it) */
   const float* sv;        /* forward's saved gates */
-  float* dG;              /* [n_slabs][2][256][128], fully written */
+  const void* xq;         /* packed token images (forward input) */
+  const void* hq;         /* h_t operand images written by the forward */
   const int32_t* plan;
   int32_t n_tiles, n_slabs, N, L;
 } umpr_gru_bwd_seg;
-int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs /*host array*/, int n_seg, const float* const* w, const int32_t* sched, int n_queues,
-                    void* stream);
-/* dw[8] (+=) from dG in the layout above (R = 128): tcgen05 with K-major dG^T and token-major [xp | h_prev] operands */
+int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs /*host array*/, int n_seg, const float* const* w, float* const* dw, int E,
+                    const void* zero_img, const int32_t* sched, int n_queues, void* stream);
+/* dw[8] (+=) from dG[n_slabs][2][256][128] (column-major inside a tile, R = 128): tcgen05 with K-major dG^T and token-major
+ * [xp | h_prev] operands (stand-alone weight-gradient kernel; the fused backward above does not need it) */
 int umpr_gru_wgrad_tc2(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int L, int E,
                        float* const* dw, int n_ctas, void* stream);
 

@@ -121,13 +121,14 @@ def test_fused_gru_forward_matches_cuda_core_path(sides, E, ctas):
         out = torch.full((N, L, 128), -3.0, device=DEV)
         hn = torch.full((2, N, 64), -3.0, device=DEV)
         sv = torch.zeros(plan.n_slabs * 2 * 128 * 256, device=DEV)
-        segs[i] = _lib.GruSeg(ptr(xp), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, N, L)
-        got.append((out, hn, sv))
+        hq = torch.zeros(plan.n_slabs * 2 * 2 * 128 * 128, dtype=torch.uint8, device=DEV)
+        segs[i] = _lib.GruSeg(ptr(xp), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), ptr(hq), plan.n_tiles, plan.n_slabs, N, L)
+        got.append((out, hn, sv, hq))
     sched, nq = build_schedule([p.tile_len for p in plans], ctas)
     sched = torch.from_numpy(sched).to(DEV)
     call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq)
     torch.cuda.synchronize()
-    for i, ((o0, h0, s0), (o1, h1, s1)) in enumerate(zip(refs, got)):
+    for i, ((o0, h0, s0), (o1, h1, s1, _)) in enumerate(zip(refs, got)):
         assert torch.equal(o0 == 0, o1 == 0), f"side {i}: zero pattern differs"
         assert_close(o1, o0, 2e-5, f"side {i} out")
         assert_close(h1, h0, 2e-5, f"side {i} hn")

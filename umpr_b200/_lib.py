@@ -26,7 +26,7 @@ SIGNATURES = {
     "umpr_gru_wgrad_tc": [P, P, P, P, I, I, I, I, I, P, I, P],
     "umpr_gather_pack_tc": [P, P, P, P, I, I, I, I, P, P],
     "umpr_gru_fwd_tc": [P, I, P, I, P, I, P],
-    "umpr_gru_bwd_tc": [P, I, P, P, I, P],
+    "umpr_gru_bwd_tc": [P, I, P, P, I, P, P, I, P],
     "umpr_gru_wgrad_tc2": [P, P, P, P, I, I, I, I, P, I, P],
     "umpr_sgemm": [P, L, L, P, L, L, P, L, I, I, I, I, I, P, I, P],
     "umpr_tc_gemm_nt": [P, L, P, L, P, L, I, I, I, I, P, I, I, P],
@@ -61,13 +61,13 @@ SIGNATURES = {
 
 class GruSeg(C.Structure):
     """``umpr_gru_seg`` of include/umpr_b200.h: one ImprovedRnn call inside a fused tensor-core GRU launch."""
-    _fields_ = [("xq", P), ("plan", P), ("out", P), ("hn", P), ("sv", P), ("n_tiles", C.c_int32), ("n_slabs", C.c_int32),
+    _fields_ = [("xq", P), ("plan", P), ("out", P), ("hn", P), ("sv", P), ("hq", P), ("n_tiles", C.c_int32), ("n_slabs", C.c_int32),
                 ("N", C.c_int32), ("L", C.c_int32)]
 
 
 class GruBwdSeg(C.Structure):
     """``umpr_gru_bwd_seg`` of include/umpr_b200.h."""
-    _fields_ = [("d_out", P), ("d_hn", P), ("out", P), ("sv", P), ("dG", P), ("plan", P), ("n_tiles", C.c_int32),
+    _fields_ = [("d_out", P), ("d_hn", P), ("sv", P), ("xq", P), ("hq", P), ("plan", P), ("n_tiles", C.c_int32),
                 ("n_slabs", C.c_int32), ("N", C.c_int32), ("L", C.c_int32)]
 
 

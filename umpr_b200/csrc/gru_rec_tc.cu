@@ -39,7 +39,7 @@ constexpr int RT_SMEM = 2 * RT_W_BYTES + 4 * RT_A_BYTES + 1024;
 #endif
 
 struct RecSeg {
-  const unsigned char* xq; const int* plan; float* out; float* hn; float* sv;
+  const unsigned char* xq; const int* plan; float* out; float* hn; float* sv; unsigned char* hq;
   int n_tiles, n_slabs, N, L, tile_base;
 };
 struct RecArgs {
@@ -63,6 +63,7 @@ constexpr float K_N = 2.8853900817779268f;      // 2 log2(e): tanh(a) = 1 - 2 / 
 // One time step of one slot for one gate thread.  The resident weights are pre-scaled (r,z rows by K_RZ, n rows and b_hn by
 // K_N), so the accumulator columns already hold the exponents.  Straight-line code: every row is computed, rows beyond their
 // length keep their state through one select (their accumulator rows are garbage but never observed).
+template <bool TRAIN>
 __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const Cur& c, GateRow& g, int n, int dir, int row, int hf,
                                           unsigned char* hs, const float* s_bhn, uint64_t* h_ready, uint64_t* acc_full, uint32_t tmem) {
   const RecSeg& sg = a.seg[c.si];
@@ -90,7 +91,7 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
   const bool live = t < g.len;
   // saved gates, column-major inside the (slab, direction) tile: svT[col = gate*64 + unit][row] -> lanes (= rows) are contiguous
   float* svcol = nullptr;
-  if (sg.sv) svcol = sg.sv + (((size_t)(sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t) * 2 + dir) * SV + u0) * RT_R + row;
+  if (TRAIN) svcol = sg.sv + (((size_t)(sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t) * 2 + dir) * SV + u0) * RT_R + row;
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16) + X * 256 + u0;
 
   if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 0);
@@ -123,7 +124,7 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
       const float hold = g.h[cc * 8 + i];
       const float hnew = fmaf(hold - nv, z, nv);                        // ATen GRU cell: (h - n) * z + n
       hv[i] = live ? hnew : hold;
-      if (svcol) {
+      if (TRAIN) {
         float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
         s1[0] = r;
         s1[(size_t)H * RT_R] = z;
@@ -198,28 +199,46 @@ __global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec2 = (E & 1) == 0;
   unsigned char* img = xq + (size_t)sl * RT_A_BYTES;
-  for (int r = warp; r < RT_R; r += 8) {
-    const int k = j * RT_R + r;
-    float2 v = make_float2(0.f, 0.f);
-    if (t < p.len_of[k]) {
-      const size_t tok = (size_t)p.seq_of[k] * L + t;
-      const float* src = dense ? dense + tok * E : table + (size_t)ids[tok] * E;
-      const int e0 = 2 * lane;
-      if (vec2 && e0 + 1 < E) {
-        v = *reinterpret_cast<const float2*>(src + e0);
-      } else {
-        if (e0 < E) v.x = src[e0]; else if (e0 == E) v.x = 1.f;
-        if (e0 + 1 < E) v.y = src[e0 + 1]; else if (e0 + 1 == E) v.y = 1.f;
+  // 4 rows per warp in flight: the dependent chain plan -> token id -> table row is pure latency, so keep 4 of them outstanding
+#pragma unroll 1
+  for (int r0 = warp; r0 < RT_R; r0 += 32) {
+    const float* src[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = j * RT_R + r0 + 8 * q;
+      src[q] = nullptr;
+      if (t < p.len_of[k]) {
+        const size_t tok = (size_t)p.seq_of[k] * L + t;
+        src[q] = dense ? dense + tok * E : table + (size_t)ids[tok] * E;
       }
     }
-    uint32_t hi, lo;
-    split2(v.x, v.y, hi, lo);
-    const uint32_t off = sw128_off(r, 2 * lane);
-    *reinterpret_cast<uint32_t*>(img + off) = hi;
-    *reinterpret_cast<uint32_t*>(img + RT_R * 128 + off) = lo;
+    float2 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = make_float2(0.f, 0.f);
+      if (src[q]) {
+        const int e0 = 2 * lane;
+        if (vec2 && e0 + 1 < E) {
+          v[q] = *reinterpret_cast<const float2*>(src[q] + e0);
+        } else {
+          if (e0 < E) v[q].x = src[q][e0]; else if (e0 == E) v[q].x = 1.f;
+          if (e0 + 1 < E) v[q].y = src[q][e0 + 1]; else if (e0 + 1 == E) v[q].y = 1.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + 8 * q;
+      uint32_t hi, lo;
+      split2(v[q].x, v[q].y, hi, lo);
+      const uint32_t off = sw128_off(r, 2 * lane);
+      *reinterpret_cast<uint32_t*>(img + off) = hi;
+      *reinterpret_cast<uint32_t*>(img + RT_R * 128 + off) = lo;
+    }
   }
 }
 
+template <bool TRAIN>
 __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_constant__ RecArgs a) {
   extern __shared__ unsigned char raw[];
   __shared__ uint64_t x_full[2], x_empty[2], h_ready[2], acc_full[2], stagger;
@@ -278,7 +297,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
     Cur c;
     cur_init(a, c, 2 * blockIdx.x + X);
     for (int n = 0; c.active; ++n) {
-      gate_step(X, a, c, g, n, dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem);
+      gate_step<TRAIN>(X, a, c, g, n, dir, row, hf, hs, s_bhn, h_ready, acc_full, tmem);
       if (X == 0 && n == 0) mbar_arrive(&stagger);
       cur_next(a, c);
     }
@@ -313,6 +332,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
       mbar_wait(&h_ready[X], n & 1);            // h_{t-1} image written AND the slot's accumulator columns drained
       tc_fence_after();
       TRACE(1, X, n, 2);
+      if (TRAIN && c.s > 0) {
+        // training: keep h_{t-1} as an operand image (bf16 hi|lo, 32 KB) for the backward kernel: it is the A operand of this
+        // step's MMAs, the h_prev of the GRU cell's backward and the token-major operand of the weight-gradient MMA
+        const RecSeg& sg = a.seg[c.si];
+        const int tprev = dir ? (c.Lj - c.s) : (c.s - 1);
+        const size_t slab = (size_t)sg.plan[3 * sg.n_tiles * RT_R + c.tile] + tprev;
+        bulk_copy_s2g(sg.hq + (slab * 2 + dir) * RT_A_BYTES, hs + X * RT_A_BYTES, RT_A_BYTES);
+      }
       for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
         const uint64_t o = (uint64_t)(kk * 2);
         umma_bf16(d, x_h + o, wih_h + o, id192, kk != 0);
@@ -330,6 +357,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
         umma_bf16(d + 192, h_h + o, whn_l + o, id64, 1);
         umma_bf16(d + 192, h_l + o, whn_h + o, id64, 1);
       }
+      if (TRAIN) bulk_wait_read();              // the h image has been read out before the gate threads may overwrite it
       umma_commit(&acc_full[X]);
       TRACE(1, X, n, 3);
       cur_next(a, c);
@@ -338,6 +366,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
         load_x();
       }
     }
+    if (TRAIN) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -368,7 +397,7 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
   for (int i = 0; i < n_seg; ++i) {
     const umpr_gru_seg& s = segs[i];
     if (s.n_tiles < 1 || s.L < 1 || !s.xq || !s.plan || !s.out) return fail_arg("gru_fwd_tc: segment %d is incomplete", i);
-    a.seg[i] = RecSeg{reinterpret_cast<const unsigned char*>(s.xq), s.plan, s.out, s.hn, s.sv, s.n_tiles, s.n_slabs, s.N, s.L, base};
+    a.seg[i] = RecSeg{reinterpret_cast<const unsigned char*>(s.xq), s.plan, s.out, s.hn, s.sv, reinterpret_cast<unsigned char*>(s.hq), s.n_tiles, s.n_slabs, s.N, s.L, base};
     base += s.n_tiles;
   }
   a.n_seg = n_seg;
@@ -385,9 +414,14 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
 #else
   a.trace = nullptr;
 #endif
-  cudaError_t e = cudaFuncSetAttribute(gru_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM);
+  bool train = segs[0].sv != nullptr;
+  for (int i = 0; i < n_seg; ++i)
+    if ((segs[i].sv != nullptr) != train || (segs[i].hq != nullptr) != train)
+      return fail_arg("gru_fwd_tc: sv and hq must be given for all segments (training) or for none (inference)");
+  auto kern = train ? gru_fwd_tc_kernel<true> : gru_fwd_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM);
   if (e != cudaSuccess) { set_error("gru_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
-  gru_fwd_tc_kernel<<<dim3(n_queues / 2, 2), RT_THREADS, RT_SMEM, (cudaStream_t)stream>>>(a);
+  kern<<<dim3(n_queues / 2, 2), RT_THREADS, RT_SMEM, (cudaStream_t)stream>>>(a);
 #ifdef UMPR_TRACE
   {
     cudaStreamSynchronize((cudaStream_t)stream);

@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc2_kernel(const floa
     // ------------------------------------------------------------------ loaders
     for (int st = 0; st < n_steps; ++st) {
       const int s = st % WT_NSTAGE;
-      if (st >= WT_NSTAGE) mbar_wait(&empty_bar[s], ((st / WT_NSTAGE) - 1) & 1);
       unsigned char* sb = base + s * WT_STAGE;
       const int f0 = f_beg + st * 64;
       // B operand sources per thread (warp w, lane): slots k = i*8 + w (i = 0..7), elements lane*4..+3 of [xp | h_prev]
@@ -237,31 +236,31 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc2_kernel(const floa
           }
         }
       }
-      float4 v[8];
-      {
-        // A operand: dGT is column-major inside the (slab, direction) tile -> for one gate, the stage's 64 token slots are 256
-        // contiguous bytes: K-major SWIZZLE_128B tiles [128 gates][64 slots], top half (dr, dz) then bottom half (dn, dn*r)
-        const int sl = f0 / R, r0 = f0 - sl * R;
-        const float* gbase = dG + ((size_t)sl * 2 + dir) * SV * R + r0;
-        const int k4 = (tid & 15) * 4, g0 = tid >> 4;           // 16 lanes cover the 64 slots of a gate row; 16 gate rows per pass
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+      // all 24 loads of the stage are issued before anything is consumed (and before the stage buffer is even free): 96 KB in
+      // flight per CTA instead of 32 KB.  A operand: dGT is column-major inside the (slab, direction) tile -> for one gate, the
+      // stage's 64 token slots are 256 contiguous bytes: K-major SWIZZLE_128B tiles [128 gates][64 slots], top half (dr, dz)
+      // then bottom half (dn, dn*r)
+      const int sl0 = f0 / R, r0 = f0 - sl0 * R;
+      const float* gbase = dG + ((size_t)sl0 * 2 + dir) * SV * R + r0;
+      const int k4 = (tid & 15) * 4, g0 = tid >> 4;             // 16 lanes cover the 64 slots of a gate row; 16 gate rows per pass
+      float4 va[16], vb[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(gbase + (size_t)(half * 128 + i * 16 + g0) * R + k4);
-          unsigned char* hi = sb + (half * 2) * WT_TILE, *lo = hi + WT_TILE;
+      for (int i = 0; i < 16; ++i) va[i] = *reinterpret_cast<const float4*>(gbase + (size_t)(i * 16 + g0) * R + k4);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) store_split4(hi, lo, i * 16 + g0, k4, v[i]);
-        }
+      for (int i = 0; i < 8; ++i) vb[i] = xsrc[i] ? *reinterpret_cast<const float4*>(xsrc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (st >= WT_NSTAGE) mbar_wait(&empty_bar[s], ((st / WT_NSTAGE) - 1) & 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        unsigned char* hi = sb + ((i >> 3) * 2) * WT_TILE, *lo = hi + WT_TILE;
+        store_split4(hi, lo, (i & 7) * 16 + g0, k4, va[i]);
       }
       {                                                       // B rows: [xp (64) | h_prev (64)]
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = xsrc[i] ? *reinterpret_cast<const float4*>(xsrc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
         unsigned char* hi = sb + 4 * WT_TILE + off0, *lo = hi + WT_TILE;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint32_t h0, l0, h1, l1;
-          split2(v[i].x, v[i].y, h0, l0);
-          split2(v[i].z, v[i].w, h1, l1);
+          split2(vb[i].x, vb[i].y, h0, l0);
+          split2(vb[i].z, vb[i].w, h1, l1);
           *reinterpret_cast<uint2*>(hi + i * 1024) = make_uint2(h0, h1);
           *reinterpret_cast<uint2*>(lo + i * 1024) = make_uint2(l0, l1);
         }

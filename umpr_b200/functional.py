@@ -143,7 +143,7 @@ class _GruTcFn(Function):
         n = len(plans)
         need_grad = any(ctx.needs_input_grad[5:])
         segs = (_lib.GruSeg * n)()
-        outs, hns, svs = [], [], []
+        outs, hns, svs, hqs = [], [], [], []
         tokens = 0
         for i, (plan, xq) in enumerate(zip(plans, xqs)):
             if plan.R != 128:
@@ -151,8 +151,9 @@ class _GruTcFn(Function):
             out = torch.empty(plan.N, plan.L, D, dtype=torch.float32, device=dev)
             hn = torch.empty(2, plan.N, H, dtype=torch.float32, device=dev) if want_hidden else None
             sv = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev) if need_grad else None
-            segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
-            outs.append(out); hns.append(hn); svs.append(sv)
+            hq = torch.empty(plan.n_slabs * 2 * 2 * 128 * 128, dtype=torch.uint8, device=dev) if need_grad else None
+            segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), ptr(hq), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
+            outs.append(out); hns.append(hn); svs.append(sv); hqs.append(hq)
             tokens += plan.tokens
         from .plan import build_schedule, upload_int32
         sched, nq = build_schedule([p.tile_len for p in plans], max(1, _n_ctas(dev) // 2))
@@ -160,7 +161,8 @@ class _GruTcFn(Function):
         call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
              work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
         ctx.plans, ctx.E, ctx.n, ctx.sched, ctx.nq = plans, E, n, sched, nq
-        ctx.save_for_backward(*xps, *outs, *[t for t in svs if t is not None], *w)
+        ctx.save_for_backward(*xqs, *[t for t in hqs if t is not None], *[t for t in svs if t is not None], *w)
+        ctx.out_shapes = [tuple(o.shape) for o in outs]
         res = list(outs)
         for hn in hns:
             if hn is None:
@@ -175,32 +177,38 @@ class _GruTcFn(Function):
     def backward(ctx, *grads_in):
         plans, E, n = ctx.plans, ctx.E, ctx.n
         saved = ctx.saved_tensors
-        xps, outs, svs, w = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], list(saved[3 * n:])
-        dev = outs[0].device
+        xqs, hqs, svs, w = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], list(saved[3 * n:])
+        dev = xqs[0].device
         flat = torch.zeros(sum(t.numel() for t in w), dtype=torch.float32, device=dev)
         grads, o = [], 0
         for t in w:
             grads.append(flat[o:o + t.numel()].view_as(t))
             o += t.numel()
-        wp, gp = ptr_array(w), ptr_array(grads)
         segs = (_lib.GruBwdSeg * n)()
-        keep, dGs, tokens = [], [], 0
+        keep, tokens = [], 0
         for i, plan in enumerate(plans):
             d_out, d_hn = grads_in[i], grads_in[n + i]
-            d_out = _f32(d_out) if d_out is not None else torch.zeros_like(outs[i])
+            d_out = _f32(d_out) if d_out is not None else torch.zeros(ctx.out_shapes[i], dtype=torch.float32, device=dev)
             d_hn = _f32(d_hn) if (d_hn is not None and d_hn.numel()) else None
-            dG = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev)
-            segs[i] = _lib.GruBwdSeg(ptr(d_out), ptr(d_hn), ptr(outs[i]), ptr(svs[i]), ptr(dG), ptr(plan.buf), plan.n_tiles,
+            segs[i] = _lib.GruBwdSeg(ptr(d_out), ptr(d_hn), ptr(svs[i]), ptr(xqs[i]), ptr(hqs[i]), ptr(plan.buf), plan.n_tiles,
                                      plan.n_slabs, plan.N, plan.L)
             keep += [d_out, d_hn]
-            dGs.append(dG)
             tokens += plan.tokens
-        # one reverse-time launch over every side (same tile queues as the forward), then the weight gradients per side
-        call("umpr_gru_bwd_tc", C.addressof(segs), n, wp, ptr(ctx.sched), ctx.nq, work=(2.0 * tokens * 2 * H * 3 * H, 0.0))
-        for i, plan in enumerate(plans):
-            call("umpr_gru_wgrad_tc2", ptr(dGs[i]), ptr(xps[i]), ptr(outs[i]), ptr(plan.buf), plan.n_tiles, plan.n_slabs, plan.L, E, gp,
-                 _n_ctas(dev, 2), work=(2.0 * plan.tokens * 2 * 3 * H * (E + H), 0.0))
+        # one reverse-time launch over every side (same tile queues as the forward): recurrence + all eight weight gradients
+        call("umpr_gru_bwd_tc", C.addressof(segs), n, ptr_array(w), ptr_array(grads), E, ptr(_zero_image(dev)), ptr(ctx.sched), ctx.nq,
+             work=(2.0 * tokens * 2 * H * 3 * H + 2.0 * tokens * 2 * 3 * H * (E + H), 0.0))
         return (None, None, None, None, None, *grads)
+
+
+_ZERO_IMG = {}
+
+
+def _zero_image(dev):
+    """32 KB of zeros: the h_{t-1} operand image of a sequence's first step (umpr_gru_bwd_tc)."""
+    key = torch.device(dev).index
+    if key not in _ZERO_IMG:
+        _ZERO_IMG[key] = torch.zeros(2 * 128 * 128, dtype=torch.uint8, device=dev)
+    return _ZERO_IMG[key]
 
 
 def gru_forward_multi(plans, xps, xqs, E, weights, want_hidden=False):

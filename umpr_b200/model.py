@@ -28,11 +28,19 @@ class PackedReviews:
         if emb is not None and emb.requires_grad:
             raise RuntimeError("umpr_b200: the embedding is frozen on this path (model.py:237); no input gradient is produced")
         self.plan = PackPlan(lengths.reshape(-1), self.L, dev)               # model.py:42-43 flatten + model.py:18
-        src_kw = (dict(table=table, ids=ids.reshape(self.B * self.S, self.L)) if ids is not None
-                  else dict(dense=emb.reshape(self.B * self.S, self.L, emb.shape[-1])))
-        self.xp, self.E = F.gather_pack(self.plan, **src_kw)
-        # plans with 128-row tiles feed the fused tensor-core GRU: tokens packed straight into bf16 hi/lo operand images
-        self.xq = F.gather_pack_tc(self.plan, **src_kw)[0] if (self.plan.R == 128 and F.TENSOR_CORE_GRU) else None
+        self._src = (dict(table=table, ids=ids.reshape(self.B * self.S, self.L)) if ids is not None
+                     else dict(dense=emb.reshape(self.B * self.S, self.L, emb.shape[-1])))
+        self.E = table.shape[1] if ids is not None else emb.shape[-1]
+        self._xp = None
+        # plans with 128-row tiles feed the fused tensor-core GRU: tokens packed straight into bf16 hi/lo operand images;
+        # the fp32 packing (CUDA-core kernels of small sides) is only materialised if somebody asks for it
+        self.xq = F.gather_pack_tc(self.plan, **self._src)[0] if (self.plan.R == 128 and F.TENSOR_CORE_GRU) else None
+
+    @property
+    def xp(self):
+        if self._xp is None:
+            self._xp = F.gather_pack(self.plan, **self._src)[0]
+        return self._xp
 
 
 def _gru_weights(gru: nn.GRU):
@@ -62,11 +70,11 @@ class ImprovedRnn(nn.Module):
         return self.run(pk)
 
     def run(self, pk: PackedReviews, want_hidden=True):
-        return F.gru_forward(pk.plan, pk.xp, pk.E, _gru_weights(self.module), want_hidden, xq=pk.xq)
+        return F.gru_forward(pk.plan, pk.xp if pk.xq is None else None, pk.E, _gru_weights(self.module), want_hidden, xq=pk.xq)
 
     def run_many(self, pks, want_hidden=False):
         """Several review sides through this GRU (the reference calls it once per side with the same weights)."""
-        return F.gru_forward_multi([pk.plan for pk in pks], [pk.xp for pk in pks], [pk.xq for pk in pks], pks[0].E,
+        return F.gru_forward_multi([pk.plan for pk in pks], [pk.xp if pk.xq is None else None for pk in pks], [pk.xq for pk in pks], pks[0].E,
                                    _gru_weights(self.module), want_hidden)
 
 
