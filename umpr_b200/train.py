@@ -79,6 +79,40 @@ class FlatTrainer:
         return pred, loss
 
 
+class AsyncScalarReader:
+    """Per-step device→host read of a scalar (the loss of main.py:38-39) that does not drain the GPU: the value goes to a
+    pinned slot with an asynchronous copy, and is handed out one step later, when its copy has completed.  Every step's value
+    is still delivered, in order; ``drain()`` returns the ones still in flight."""
+
+    def __init__(self, depth: int = 2):
+        self.depth = depth
+        self.slots = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.head = 0          # next slot to write
+        self.inflight = 0
+
+    def push(self, scalar: torch.Tensor):
+        """Queue the read of ``scalar``; returns the list of values whose reads had to complete to make room (0 or 1)."""
+        out = []
+        if self.inflight == self.depth:
+            out.append(self._pop())
+        i = self.head
+        self.slots[i].copy_(scalar.detach().reshape(1), non_blocking=True)
+        self.events[i].record()
+        self.head = (i + 1) % self.depth
+        self.inflight += 1
+        return out
+
+    def _pop(self):
+        i = (self.head - self.inflight) % self.depth
+        self.events[i].synchronize()
+        self.inflight -= 1
+        return float(self.slots[i])
+
+    def drain(self):
+        return [self._pop() for _ in range(self.inflight)]
+
+
 def shard_batch(batch, rank: int, world: int):
     """The chunk ``torch.nn.DataParallel``'s scatter hands to replica ``rank`` (``torch.chunk`` along dim 0).
     Returns None when there are fewer chunks than ranks (e.g. B=9, world=8 → 5 chunks)."""
