@@ -114,6 +114,10 @@ int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int 
 int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, int accumulate,
                     const float* bias, int act, int b_kn, int n_ctas, void* stream);
 
+/* reduction GEMM over a huge K with both operands row-major in k ("TN"): C[m][n] (+=) sum_k A[k*lda+m] * B[k*ldb+n], M, N <= 128.
+ * dM = gi^T · dgiM of the co-attention backward (model.py:50) runs here.  C must be initialised (atomic accumulation). */
+int umpr_tc_gemm_tn(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, long K, int n_ctas, void* stream);
+
 /* ---- RNet co-attention: src/model.py:50-55.  gu, gi, giM (=gi·M): (B,P,128).  The (P,P) affinity matrix is never
  *      materialised.  rowkey/colkey: (B,P) uint64 scratch, colkey zero-initialised.  t_*: tanh of the row/col maxima,
  *      arg_*: their positions (saved for backward). ---- */

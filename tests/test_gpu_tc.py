@@ -161,3 +161,20 @@ def test_fused_gru_autograd_matches_cuda_core_path():
     assert_close(res[1][0], res[0][0], 2e-5, "out")
     for a, b in zip(res[1][1], res[0][1]):
         assert_close(a, b, 5e-5, "grad")
+
+
+@pytest.mark.parametrize("M,N,K,ctas", [(128, 128, 5000, 148), (128, 128, 64, 3), (64, 100, 777, 7), (128, 128, 409600, 148), (4, 128, 1000, 1)])
+def test_tc_gemm_tn_reduction(M, N, K, ctas):
+    """C += A^T · B with the reduction index slowest in both operands (dM = gi^T · dgiM, model.py:50 backward)."""
+    from umpr_b200._lib import call, ptr
+    torch.manual_seed(M + N + K)
+    lda, ldb, ldc = 128, 128, (N + 3) // 4 * 4
+    A = torch.randn(K, lda, device=DEV) * 0.3
+    B = torch.randn(K, ldb, device=DEV) * 0.3
+    C = torch.randn(M, ldc, device=DEV)
+    C0 = C.clone()
+    call("umpr_tc_gemm_tn", ptr(A), lda, ptr(B), ldb, ptr(C), ldc, M, N, K, ctas)
+    ref = C0[:, :N].double() + A[:, :M].double().t() @ B[:, :N].double()
+    assert_close(C[:, :N], ref, 2e-5, "tc_gemm_tn")
+    if ldc > N:
+        assert torch.equal(C[:, N:], C0[:, N:])

@@ -333,6 +333,111 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc2_kernel(const floa
   if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Generic "TN" reduction GEMM on the tensor cores: C[M][N] += sum_k A[k][M]^T · B[k][N]   (M, N <= 128, K huge; both operands
+// row-major with the reduction index slowest = MN-major for tcgen05, converted fp32 -> bf16 hi/lo on the fly).
+// Used for dM = gi^T · dgiM of the co-attention backward (model.py:50; K = B*P).  Persistent CTAs own contiguous K ranges,
+// accumulate in TMEM and flush once with atomics.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int TN_STAGE = 4 * WT_TILE;            // A hi/lo, B hi/lo (64 k x 128 elements each)
+constexpr int TN_NSTAGE = 3;
+
+__global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
+                                                                   float* __restrict__ C, long ldc, int M, int N, long K, long k_per_cta) {
+  extern __shared__ unsigned char raw[];
+  __shared__ uint64_t full_bar[TN_NSTAGE], empty_bar[TN_NSTAGE], acc_bar;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long k_beg = (long)blockIdx.x * k_per_cta, k_end = min(K, k_beg + k_per_cta);
+  const int n_steps = (int)((k_end - k_beg + 63) / 64);
+
+  if (tid == 0) {
+    for (int s = 0; s < TN_NSTAGE; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 8) {
+    // loaders: thread (warp w, lane) owns k = i*8 + w (i = 0..7) and elements lane*4..+3 of both 128-wide rows
+    const int m = lane * 4;
+    const uint32_t off0 = mn_off(m, warp);
+    const bool a_ok = m < M, b_ok = m < N;          // M, N are multiples of 4
+    for (int st = 0; st < n_steps; ++st) {
+      const int s = st % TN_NSTAGE;
+      const long k0 = k_beg + (long)st * 64 + warp;
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long k = k0 + i * 8;
+        const bool in = k < k_end;
+        va[i] = (in && a_ok) ? *reinterpret_cast<const float4*>(A + k * lda + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = (in && b_ok) ? *reinterpret_cast<const float4*>(B + k * ldb + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (st >= TN_NSTAGE) mbar_wait(&empty_bar[s], ((st / TN_NSTAGE) - 1) & 1);
+      unsigned char* sb = base + s * TN_STAGE + off0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t h0, l0, h1, l1;
+        split2(va[i].x, va[i].y, h0, l0);
+        split2(va[i].z, va[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(sb + i * 1024) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(sb + WT_TILE + i * 1024) = make_uint2(l0, l1);
+        split2(vb[i].x, vb[i].y, h0, l0);
+        split2(vb[i].z, vb[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(sb + 2 * WT_TILE + i * 1024) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(sb + 3 * WT_TILE + i * 1024) = make_uint2(l0, l1);
+      }
+      fence_async_smem();
+      mbar_arrive(&full_bar[s]);
+    }
+  } else if (lane == 0) {
+    constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);     // A and B are MN-major
+    for (int st = 0; st < n_steps; ++st) {
+      const int s = st % TN_NSTAGE;
+      mbar_wait(&full_bar[s], (st / TN_NSTAGE) & 1);
+      tc_fence_after();
+      const uint32_t sb = smem_u32(base + s * TN_STAGE);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t ko = kk * 2048;           // 16 k = two 1024-byte atoms
+        const uint64_t ah = smem_desc_mn_sw128(sb + ko), al = smem_desc_mn_sw128(sb + WT_TILE + ko);
+        const uint64_t bh = smem_desc_mn_sw128(sb + 2 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 3 * WT_TILE + ko);
+        umma_bf16(tmem, ah, bh, idesc, (st | kk) != 0);
+        umma_bf16(tmem, ah, bl, idesc, 1);
+        umma_bf16(tmem, al, bh, idesc, 1);
+      }
+      umma_commit(&empty_bar[s]);
+    }
+    umma_commit(&acc_bar);
+  }
+  __syncwarp();
+  if (warp < 4 && n_steps > 0) {
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const int mrow = warp * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+      if (mrow < M) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c0 + c < N) atomicAdd(&C[(long)mrow * ldc + c0 + c], v[c]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 128);
+}
+
 }  // namespace umpr
 
 using namespace umpr;
@@ -372,4 +477,22 @@ extern "C" int umpr_gru_wgrad_tc2(const float* dGT, const float* xp, const float
   gru_wgrad_tc2_kernel<<<dim3(grid, 2), WT_THREADS, smem, (cudaStream_t)stream>>>(dGT, xp, out, p, L, E, per, dw[0], dw[1], dw[2], dw[3], dw[4],
                                                                                  dw[5], dw[6], dw[7]);
   return check_launch("gru_wgrad_tc2");
+}
+
+// C[M][N] (+=) sum_k A[k*lda + m] * B[k*ldb + n]: tensor-core reduction over a huge K (M, N <= 128, multiples of 4; 16-byte aligned rows)
+extern "C" int umpr_tc_gemm_tn(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, long K, int n_ctas,
+                               void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M > 128 || N > 128 || (M & 3) || (N & 3)) return fail_arg("tc_gemm_tn: M=%d N=%d (need <= 128, multiples of 4)", M, N);
+  if ((lda & 3) || (ldb & 3) || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15))
+    return fail_arg("tc_gemm_tn: A and B must be 16-byte aligned with leading dimensions that are multiples of 4");
+  if (n_ctas < 1) n_ctas = 148;
+  long per = (K + n_ctas - 1) / n_ctas;
+  per = ((per + 63) / 64) * 64;
+  const int grid = (int)((K + per - 1) / per);
+  const int smem = TN_NSTAGE * TN_STAGE + 1024;
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("tc_gemm_tn smem: %s", cudaGetErrorString(e)); return (int)e; }
+  tc_gemm_tn_kernel<<<grid, WT_THREADS, smem, (cudaStream_t)stream>>>(A, lda, B, ldb, C, ldc, M, N, K, per);
+  return check_launch("tc_gemm_tn");
 }

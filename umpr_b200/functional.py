@@ -303,7 +303,10 @@ class _CoAttnFn(Function):
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
         sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
         dM = torch.zeros_like(M)
-        sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
+        if B * P >= 4096:      # reduction over every token of the batch: tensor cores, both operands token-major
+            call("umpr_tc_gemm_tn", ptr(gi), D, ptr(dgiM), D, ptr(dM), D, D, D, B * P, _n_ctas(dev), work=(2.0 * D * D * B * P, 0.0))
+        else:
+            sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
         return dgu, dgi, dM
 
 
