@@ -62,8 +62,11 @@ class _PinnedRing:
     slow, and a pageable source can stall the host behind queued GPU work).  A slot is reused only after the copy that last
     read it has completed (event)."""
 
-    def __init__(self, slots=64):
-        self.bufs, self.events, self.i, self.slots = [None] * slots, [None] * slots, 0, slots
+    def __init__(self, slots=32, slot_ints=1 << 17):
+        # one pinned allocation up front: cudaHostAlloc inside the training loop costs milliseconds and synchronises
+        self.pool = torch.empty(slots * slot_ints, dtype=torch.int32).pin_memory()
+        self.bufs = [self.pool[i * slot_ints:(i + 1) * slot_ints] for i in range(slots)]
+        self.events, self.i, self.slots = [None] * slots, 0, slots
 
     def upload(self, arr, device):
         import numpy as np
@@ -72,14 +75,14 @@ class _PinnedRing:
         n = int(arr.size)
         if self.events[i] is not None:
             self.events[i].synchronize()
-        if self.bufs[i] is None or self.bufs[i].numel() < n:
-            self.bufs[i] = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
+        if self.bufs[i].numel() < n:                     # oversized plan: give this slot its own buffer
+            self.bufs[i] = torch.empty(n, dtype=torch.int32).pin_memory()
         host = self.bufs[i][:n]
         host.numpy()[:] = np.asarray(arr, dtype=np.int32).reshape(-1)
         dev = host.to(device, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self.events[i] = ev
+        if self.events[i] is None:
+            self.events[i] = torch.cuda.Event()
+        self.events[i].record()
         return dev
 
 
