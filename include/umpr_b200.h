@@ -124,8 +124,10 @@ int umpr_tc_gemm_tn(const float* A, long lda, const float* B, long ldb, float* C
 int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, int P, unsigned long long* rowkey,
                     unsigned long long* colkey, float* soft_u, float* soft_i, float* t_u, float* t_i, int32_t* arg_u,
                     int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
-/* tensor-core form of umpr_coattn_fwd: two tcgen05 products per tile pair (S and S^T) so row and column maxima are per-thread
- * scans; near-tied maxima are re-scored with exact fp32 dot products.  scratch: 32*B*P*(1+ceil(P/128)) bytes. */
+/* tensor-core form of umpr_coattn_fwd (P <= 512): operands pre-split into bf16 hi|lo images; one CTA per sample issues two tcgen05
+ * products per tile pair (S and S^T, so row and column maxima are per-thread scans) in two passes - maxima, then every value
+ * within the 3xBF16 error bound of its final maximum - and the surviving near-ties are re-scored with exact fp32 dot products
+ * (the arg-max routes the gradient).  scratch: 2*B*T*65536 + 2*B*P*4 + 4*B*P*16 + 256 bytes, T = ceil(P/128), 16-byte aligned. */
 int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, void* scratch, float* soft_u, float* soft_i,
                        float* t_u, float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
 /* dgu, dgi (without the dgiM·M^T term), dgiM: (B,P,128) fully written.  d_* inputs may be NULL. */

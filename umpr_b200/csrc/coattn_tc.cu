@@ -34,8 +34,8 @@ struct Cand4 {
       if (c < nvalid && x[c] > thr) { push(x[c], idx0 + c); thr = fmaxf(thr, v[0] - tau); }
     }
   }
-  // keep the 4 largest distinct values, sorted descending
-  __device__ __forceinline__ void push(float x, int idx) {
+  // keep the 4 largest distinct values, sorted descending (rare path: kept out of line so the scan loops stay small)
+  __device__ __noinline__ void push(float x, int idx) {
     if (x == v[0] || x == v[1] || x == v[2] || x == v[3]) return;     // exact duplicates (zero padding) carry no information
     if (x > v[3]) {
       v[3] = x; id[3] = idx;
@@ -50,192 +50,218 @@ struct Cand4 {
   }
 };
 
-__global__ void __launch_bounds__(CA_THREADS, 1) coattn_affinity_tc_kernel(const float* __restrict__ giM, const float* __restrict__ gu,
-                                                                           int P, int n_it, float4* __restrict__ rc_v, int4* __restrict__ rc_i,
-                                                                           float4* __restrict__ cc_v, int4* __restrict__ cc_i) {
+// ------------------------------------------------------------------------------------------------------------------------
+// version 2: one CTA per sample, two passes over the sample's tile pairs.
+//   pass 0: maxima only (row maxima per thread of the S tile, column maxima per thread of the S^T tile);
+//   pass 1: the same products again (MMAs are cheap), now every value within the error bound of its FINAL row / column maximum
+//           is kept as a candidate (up to 4 distinct values) for coattn_resolve_kernel's exact fp32 re-scoring.
+// Operands are pre-split bf16 hi|lo images (coattn_images_kernel), loaded by TMA bulk copies: no conversion in the hot loop.
+//   warps 0-3: scan S rows (i), warps 4-7: scan S^T rows (j), warp 8: TMA producer, warp 9: MMA issuer.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int CI_TILE = 128 * 128;          // bytes of one [128][64 bf16] tile
+constexpr int CI_IMG = 4 * CI_TILE;         // [kb 2][hi|lo][128][128 B]: a 128-row, K=128 operand image
+constexpr int C2_THREADS = 320;
+constexpr int C2_MAXP = 512;
+
+// fp32 rows (giM and gu of every sample, zero-padded to 128-row tiles) -> operand images + squared row norms
+__global__ void __launch_bounds__(256) coattn_images_kernel(const float* __restrict__ giM, const float* __restrict__ gu, int P, int T,
+                                                            unsigned char* __restrict__ imgA, unsigned char* __restrict__ imgB,
+                                                            float* __restrict__ n2a, float* __restrict__ n2b) {
+  const int t = blockIdx.x, b = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+  const float* src = (which ? gu : giM) + (size_t)b * P * D;
+  unsigned char* img = (which ? imgB : imgA) + ((size_t)b * T + t) * CI_IMG;
+  float* n2 = (which ? n2b : n2a) + (size_t)b * P;
+  const int k = (tid & 15) * 4;
+  for (int r = tid >> 4; r < 128; r += 16) {          // half-warp per row, both k-blocks
+    const int p = t * 128 + r;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (p < P) {
+      v0 = *reinterpret_cast<const float4*>(src + (size_t)p * D + k);
+      v1 = *reinterpret_cast<const float4*>(src + (size_t)p * D + 64 + k);
+    }
+    store_split4(img, img + CI_TILE, r, k, v0);
+    store_split4(img + 2 * CI_TILE, img + 3 * CI_TILE, r, k, v1);
+    float q = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+    q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 4);
+    q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 1);
+    if ((tid & 15) == 0 && p < P) n2[p] = q;
+  }
+}
+
+struct C2Bars { uint64_t a_full, a_empty, b_full[2], b_empty[2], acc_full[2], acc_empty[2]; };
+
+__global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
+                                                                            const float* __restrict__ n2a, const float* __restrict__ n2b, int P, int T,
+                                                                            float4* __restrict__ rc_v, int4* __restrict__ rc_i,
+                                                                            float4* __restrict__ cc_v, int4* __restrict__ cc_i) {
   extern __shared__ unsigned char raw[];
-  __shared__ uint64_t b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+  __shared__ C2Bars bars;
   __shared__ uint32_t tmem_slot;
-  __shared__ float a_norm2[128];          // |giM_i|^2 of the resident tile
-  __shared__ float b_norm2[4][128];       // |gu_j|^2 of the staged tiles
-  __shared__ float norm_red[4];
+  __shared__ float s_an[C2_MAXP], s_bn[C2_MAXP], s_rowmax[C2_MAXP], s_colmax[C2_MAXP];
+  __shared__ float4 s_cv[C2_MAXP];
+  __shared__ int4 s_ci[C2_MAXP];
+  __shared__ float red[32];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  constexpr int TILE = 128 * 128;            // bytes of one [128][64 bf16] tile
-  unsigned char* a_res = base;               // [kb 2][hi|lo][128][128 B]  giM tile
-  unsigned char* b_stg = base + 4 * TILE;    // 2 stages of the same shape   gu tiles
+  unsigned char* a_img = base;                  // giM tile of the current i-tile
+  unsigned char* b_img = base + CI_IMG;         // 2 stages of gu tiles
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, it_ = blockIdx.x, i0 = it_ * 128;
-  const int ni = min(128, P - i0);
-  const int n_jt = (P + 127) / 128;
-  const float* giM_b = giM + (size_t)b * P * D;
-  const float* gu_b = gu + (size_t)b * P * D;
+  const int b = blockIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 128); mbar_init(&b_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    mbar_init(&bars.a_full, 1); mbar_init(&bars.a_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars.b_full[s], 1); mbar_init(&bars.b_empty[s], 1); mbar_init(&bars.acc_full[s], 1); mbar_init(&bars.acc_empty[s], 256); }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, 512);
-  if (tid < 256) {
-    for (int r = tid >> 4; r < 128; r += 16) {          // half-warp per row, both k-blocks
-      const int k = (tid & 15) * 4;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (r < ni) {
-        v0 = *reinterpret_cast<const float4*>(giM_b + (size_t)(i0 + r) * D + k);
-        v1 = *reinterpret_cast<const float4*>(giM_b + (size_t)(i0 + r) * D + 64 + k);
-      }
-      store_split4(a_res, a_res + TILE, r, k, v0);
-      store_split4(a_res + 2 * TILE, a_res + 3 * TILE, r, k, v1);
-      float t = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
-      t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 1);
-      if ((tid & 15) == 0) a_norm2[r] = t;
-    }
+  if (warp == 9) tmem_alloc(&tmem_slot, 512);
+  float amax = 0.f;
+  for (int p = tid; p < C2_MAXP; p += C2_THREADS) {
+    const float an = p < P ? sqrtf(n2a[(size_t)b * P + p]) : 0.f;
+    s_an[p] = an;
+    s_bn[p] = p < P ? sqrtf(n2b[(size_t)b * P + p]) : 0.f;
+    s_colmax[p] = -INFINITY;
+    s_cv[p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    s_ci[p] = make_int4(-1, -1, -1, -1);
+    amax = fmaxf(amax, an);
   }
-  fence_async_smem();
+  amax = block_max(amax, red);              // max_i |giM_i| of the sample: bound for the column-side tolerance
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  const int n_pairs = 2 * T * T;
 
-  if (warp < 4) {
-    // ---------------------------------------------------------------- loaders: gu tiles
-    for (int jt = 0; jt < n_jt; ++jt) {
-      const int s = jt & 1;
-      if (jt >= 2) mbar_wait(&b_empty[s], ((jt >> 1) - 1) & 1);
-      unsigned char* st = b_stg + s * 4 * TILE;
-      const int j0 = jt * 128, nj = min(128, P - j0);
-      float n2[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) n2[i] = 0.f;
+  if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue: S rows (warps 0-3) / S^T rows (warps 4-7)
+    const bool is_t = warp >= 4;
+    const int q = warp & 3, r = q * 32 + lane;
+    float m = -INFINITY;
+    Cand4 cd;                 // candidates of this thread's row (S side: lives across the j-tiles) / column (S^T side: parked in shared memory)
+    cd.init();
+    float thr = -INFINITY;    // candidate threshold (final maximum - tau), kept in a register: Cand4 itself lives on the stack for push()
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int it = 0; it < T; ++it)
 #pragma unroll 1
-      for (int kb = 0; kb < 2; ++kb) {
-        float4 va[16];
+        for (int jt = 0; jt < T; ++jt, ++n) {
+          const int s = n & 1;
+          const int own = (is_t ? jt : it) * 128 + r;                // the row (i) / column (j) this thread scans (< 512)
+          const int o0 = (is_t ? it : jt) * 128;                     // first index of the scanned direction
+          const int nv = min(128, P - o0);
+          const float tau = is_t ? CA_EPS * s_bn[own] * amax : CA_EPS * s_an[own] * CA_GNORM;
+          if (pass == 1) {
+            if (is_t) {
+              const float4 v = s_cv[own]; const int4 id = s_ci[own];
+              cd.v[0] = v.x; cd.v[1] = v.y; cd.v[2] = v.z; cd.v[3] = v.w;
+              cd.id[0] = id.x; cd.id[1] = id.y; cd.id[2] = id.z; cd.id[3] = id.w;
+              thr = s_colmax[own] - tau;
+            } else if (jt == 0) {
+              cd.init();
+              thr = s_rowmax[own] - tau;
+            }
+          } else if (!is_t && jt == 0) {
+            m = -INFINITY;
+          }
+          mbar_wait(&bars.acc_full[s], (n >> 1) & 1);
+          tc_fence_after();
+          const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + s * 256 + (is_t ? 128 : 0);
+          float tm = -INFINITY;
+          const bool scan = pass == 1 && own < P;
+          uint32_t ra[2][16];
+          tmem_ld16_issue(t0, ra[0]);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid, r = idx >> 4, k = (idx & 15) * 4;
-          va[i] = r < nj ? *reinterpret_cast<const float4*>(gu_b + (size_t)(j0 + r) * D + kb * 64 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int ch = 0; ch < 8; ++ch) {
+            tmem_ld_wait();
+            if (ch + 1 < 8) tmem_ld16_issue(t0 + (ch + 1) * 16, ra[(ch + 1) & 1]);
+            const int left = nv - ch * 16;
+            float cm = -INFINITY;                                   // chunk maximum over the valid columns
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid;
-          store_split4(st + kb * 2 * TILE, st + kb * 2 * TILE + TILE, idx >> 4, (idx & 15) * 4, va[i]);
-          n2[i] += va[i].x * va[i].x + va[i].y * va[i].y + va[i].z * va[i].z + va[i].w * va[i].w;
-        }
-      }
+            for (int c = 0; c < 16; ++c) cm = fmaxf(cm, c < left ? __uint_as_float(ra[ch & 1][c]) : -INFINITY);
+            tm = fmaxf(tm, cm);
+            if (scan && cm > thr) {                              // rare: something in this chunk is within tau of the maximum
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {       // the 16 lanes of a half-warp share row (i*128+tid)>>4
-        float t = n2[i];
-        t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 4);
-        t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 1);
-        if ((lane & 15) == 0) b_norm2[jt & 3][(i * 128 + tid) >> 4] = t;
-      }
-      fence_async_smem();
-      mbar_arrive(&b_full[s]);
-    }
-  } else if (warp == 4) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, 128);
-      const uint32_t a0 = smem_u32(a_res);
-      for (int jt = 0; jt < n_jt; ++jt) {
-        const int s = jt & 1;
-        if (jt >= 2) mbar_wait(&acc_empty[s], ((jt >> 1) - 1) & 1);
-        mbar_wait(&b_full[s], (jt >> 1) & 1);
-        tc_fence_after();
-        const uint32_t b0 = smem_u32(b_stg + s * 4 * TILE);
-        const uint32_t d1 = tmem + s * 256, d2 = d1 + 128;
+              for (int c = 0; c < 16; ++c) {
+                const float x = __uint_as_float(ra[ch & 1][c]);
+                if (c < left && x > thr) cd.push(x, o0 + ch * 16 + c);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bars.acc_empty[s]);
+          if (pass == 0) {
+            if (is_t) s_colmax[own] = fmaxf(s_colmax[own], tm);
+            else { m = fmaxf(m, tm); if (jt == T - 1) s_rowmax[own] = m; }
+          } else if (own < P) {
+            const bool done = is_t ? (it == T - 1) : (jt == T - 1);
+            if (done) {
+              const size_t o = (size_t)b * P + own;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const uint64_t ah = smem_desc_sw128(a0 + kb * 2 * TILE), al = smem_desc_sw128(a0 + kb * 2 * TILE + TILE);
-          const uint64_t bh = smem_desc_sw128(b0 + kb * 2 * TILE), bl = smem_desc_sw128(b0 + kb * 2 * TILE + TILE);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t o = (uint64_t)(kk * 2);
-            const uint32_t accf = (kb | kk) != 0;
-            umma_bf16(d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
-            umma_bf16(d1, ah + o, bl + o, idesc, 1);
-            umma_bf16(d1, al + o, bh + o, idesc, 1);
-            umma_bf16(d2, bh + o, ah + o, idesc, accf);      // S^T (rows j, cols i)
-            umma_bf16(d2, bh + o, al + o, idesc, 1);
-            umma_bf16(d2, bl + o, ah + o, idesc, 1);
+              for (int k = 1; k < 4; ++k) if (cd.v[k] < cd.v[0] - tau) { cd.v[k] = -INFINITY; cd.id[k] = -1; }
+              (is_t ? cc_v : rc_v)[o] = make_float4(cd.v[0], cd.v[1], cd.v[2], cd.v[3]);
+              (is_t ? cc_i : rc_i)[o] = make_int4(cd.id[0], cd.id[1], cd.id[2], cd.id[3]);
+            } else if (is_t) {
+              s_cv[own] = make_float4(cd.v[0], cd.v[1], cd.v[2], cd.v[3]);
+              s_ci[own] = make_int4(cd.id[0], cd.id[1], cd.id[2], cd.id[3]);
+            }
           }
         }
-        umma_commit(&b_empty[s]);
-        umma_commit(&acc_full[s]);
-      }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int n = 0, na = 0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int it = 0; it < T; ++it, ++na) {
+          if (na > 0) mbar_wait(&bars.a_empty, (na - 1) & 1);
+          mbar_arrive_expect_tx(&bars.a_full, CI_IMG);
+          bulk_copy_g2s(a_img, imgA + ((size_t)b * T + it) * CI_IMG, CI_IMG, &bars.a_full);
+          for (int jt = 0; jt < T; ++jt, ++n) {
+            const int s = n & 1;
+            if (n >= 2) mbar_wait(&bars.b_empty[s], ((n >> 1) - 1) & 1);
+            mbar_arrive_expect_tx(&bars.b_full[s], CI_IMG);
+            bulk_copy_g2s(b_img + s * CI_IMG, imgB + ((size_t)b * T + jt) * CI_IMG, CI_IMG, &bars.b_full[s]);
+          }
+        }
     }
-  } else {
-    // ---------------------------------------------------------------- epilogue: candidate scans
-    const int q = warp & 3, row = q * 32 + lane;
-    // error bounds: tau_i = eps * |giM_i| * max|gu_j| ; tau_j = eps * |gu_j| * max_{i in tile} |giM_i|
-    const float nrm = sqrtf(a_norm2[row]);
-    const float wmax = warp_max(nrm);
-    if (lane == 0) norm_red[q] = wmax;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const float tile_norm = fmaxf(fmaxf(norm_red[0], norm_red[1]), fmaxf(norm_red[2], norm_red[3]));
-    const float tau_i = CA_EPS * nrm * CA_GNORM;
-    Cand4 rc;
-    rc.init();
-    for (int jt = 0; jt < n_jt; ++jt) {
-      const int s = jt & 1, j0 = jt * 128, nj = min(128, P - j0);
-      mbar_wait(&acc_full[s], (jt >> 1) & 1);
-      tc_fence_after();
-      const uint32_t t1 = tmem + ((uint32_t)(q * 32) << 16) + s * 256, t2 = t1 + 128;
-      const float tau_j = CA_EPS * sqrtf(b_norm2[jt & 3][row]) * tile_norm;
-      Cand4 cc;
-      cc.init();
-      // phase A: branch-free tile maxima, so that candidates are judged against an up-to-date head (few slow-path events).
-      // TMEM loads are software-pipelined: the next 16-column chunk of S and S^T is in flight while the current one is scanned.
-      float m1 = -INFINITY, m2 = -INFINITY;
-      uint32_t ra[2][16], rb[2][16];
-      tmem_ld16_issue(t1, ra[0]);
-      tmem_ld16_issue(t2, rb[0]);
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = idesc_bf16(128, 128);
+    const uint32_t a0 = smem_u32(a_img);
+    int n = 0, na = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int it = 0; it < T; ++it, ++na) {
+        mbar_wait(&bars.a_full, na & 1);
+        for (int jt = 0; jt < T; ++jt, ++n) {
+          const int s = n & 1;
+          mbar_wait(&bars.b_full[s], (n >> 1) & 1);
+          if (n >= 2) mbar_wait(&bars.acc_empty[s], ((n >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(b_img + s * CI_IMG);
+          const uint32_t d1 = tmem + s * 256, d2 = d1 + 128;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        tmem_ld_wait();
-        if (ch + 1 < 8) { tmem_ld16_issue(t1 + (ch + 1) * 16, ra[(ch + 1) & 1]); tmem_ld16_issue(t2 + (ch + 1) * 16, rb[(ch + 1) & 1]); }
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t ah = smem_desc_sw128(a0 + kb * 2 * CI_TILE), al = smem_desc_sw128(a0 + kb * 2 * CI_TILE + CI_TILE);
+            const uint64_t bh = smem_desc_sw128(b0 + kb * 2 * CI_TILE), bl = smem_desc_sw128(b0 + kb * 2 * CI_TILE + CI_TILE);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          m1 = fmaxf(m1, ch * 16 + c < nj ? __uint_as_float(ra[ch & 1][c]) : -INFINITY);
-          m2 = fmaxf(m2, ch * 16 + c < ni ? __uint_as_float(rb[ch & 1][c]) : -INFINITY);
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t o = (uint64_t)(kk * 2);
+              const uint32_t accf = (kb | kk) != 0;
+              umma_bf16(d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
+              umma_bf16(d1, ah + o, bl + o, idesc, 1);
+              umma_bf16(d1, al + o, bh + o, idesc, 1);
+              umma_bf16(d2, bh + o, ah + o, idesc, accf);      // S^T (rows j, cols i)
+              umma_bf16(d2, bh + o, al + o, idesc, 1);
+              umma_bf16(d2, bl + o, ah + o, idesc, 1);
+            }
+          }
+          umma_commit(&bars.b_empty[s]);
+          umma_commit(&bars.acc_full[s]);
+          if (jt == T - 1) umma_commit(&bars.a_empty);
         }
       }
-      rc.thr = fmaxf(rc.thr, m1 - tau_i);
-      cc.thr = m2 - tau_j;
-      // phase B: collect the candidates within tau of the head
-      tmem_ld16_issue(t1, ra[0]);
-      tmem_ld16_issue(t2, rb[0]);
-#pragma unroll 1
-      for (int ch = 0; ch < 8; ++ch) {
-        tmem_ld_wait();
-        float v1[16], v2[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { v1[c] = __uint_as_float(ra[0][c]); v2[c] = __uint_as_float(rb[0][c]); }
-        if (ch + 1 < 8) { tmem_ld16_issue(t1 + (ch + 1) * 16, ra[0]); tmem_ld16_issue(t2 + (ch + 1) * 16, rb[0]); }
-        if (row < ni) { rc.scan8(v1, j0 + ch * 16, nj - ch * 16, tau_i); rc.scan8(v1 + 8, j0 + ch * 16 + 8, nj - ch * 16 - 8, tau_i); }
-        if (row < nj) { cc.scan8(v2, i0 + ch * 16, ni - ch * 16, tau_j); cc.scan8(v2 + 8, i0 + ch * 16 + 8, ni - ch * 16 - 8, tau_j); }
-      }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[s]);
-      if (row < nj) {
-        const size_t o = ((size_t)b * n_it + it_) * P + j0 + row;
-#pragma unroll
-        for (int k = 1; k < 4; ++k) if (cc.v[k] < cc.v[0] - tau_j) { cc.v[k] = -INFINITY; cc.id[k] = -1; }
-        cc_v[o] = make_float4(cc.v[0], cc.v[1], cc.v[2], cc.v[3]);
-        cc_i[o] = make_int4(cc.id[0], cc.id[1], cc.id[2], cc.id[3]);
-      }
-    }
-    if (row < ni) {
-      const size_t o = (size_t)b * P + i0 + row;
-#pragma unroll
-      for (int k = 1; k < 4; ++k) if (rc.v[k] < rc.v[0] - tau_i) { rc.v[k] = -INFINITY; rc.id[k] = -1; }
-      rc_v[o] = make_float4(rc.v[0], rc.v[1], rc.v[2], rc.v[3]);
-      rc_i[o] = make_int4(rc.id[0], rc.id[1], rc.id[2], rc.id[3]);
-    }
+    (void)n_pairs;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 // exact fp32 <giM[i], gu[j]> by one warp (lane holds a float4 of each row)
@@ -339,26 +365,35 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
 
 using namespace umpr;
 
-// scratch: float4 rc_v[B*P], int4 rc_i[B*P], float4 cc_v[B*n_it*P], int4 cc_i[B*n_it*P], n_it = ceil(P/128)  -> 32*B*P*(1+n_it) bytes
+// scratch (16-byte aligned): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),
+// T = ceil(P/128): 2*B*T*65536 + 2*B*P*4 + 4*B*P*16 + 256 bytes.  P <= 512.
 extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, void* scratch, float* soft_u,
                                   float* soft_i, float* t_u, float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i,
                                   void* stream) {
   if (B <= 0 || P <= 0) return 0;
   if (B > 65535) return fail_arg("coattn_fwd_tc: batch %d > 65535", B);
-  const int n_it = (P + 127) / 128;
-  float4* rc_v = reinterpret_cast<float4*>(scratch);
+  if (P > C2_MAXP) return fail_arg("coattn_fwd_tc: P=%d > %d (use umpr_coattn_fwd)", P, C2_MAXP);
+  const int T = (P + 127) / 128;
+  unsigned char* imgA = reinterpret_cast<unsigned char*>(scratch);
+  unsigned char* imgB = imgA + (size_t)B * T * CI_IMG;
+  float* n2a = reinterpret_cast<float*>(imgB + (size_t)B * T * CI_IMG);
+  float* n2b = n2a + (size_t)B * P;
+  uintptr_t q = (reinterpret_cast<uintptr_t>(n2b + (size_t)B * P) + 15) & ~uintptr_t(15);
+  float4* rc_v = reinterpret_cast<float4*>(q);
   int4* rc_i = reinterpret_cast<int4*>(rc_v + (size_t)B * P);
   float4* cc_v = reinterpret_cast<float4*>(rc_i + (size_t)B * P);
-  int4* cc_i = reinterpret_cast<int4*>(cc_v + (size_t)B * n_it * P);
-  const int sm1 = 12 * 128 * 128 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(coattn_affinity_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
+  int4* cc_i = reinterpret_cast<int4*>(cc_v + (size_t)B * P);
+  cudaStream_t st = (cudaStream_t)stream;
+  coattn_images_kernel<<<dim3(T, B, 2), 256, 0, st>>>(giM, gu, P, T, imgA, imgB, n2a, n2b);
+  if (int rc = check_launch("coattn_images")) return rc;
+  const int sm1 = 3 * CI_IMG + 1024;
+  cudaError_t e = cudaFuncSetAttribute(coattn_affinity_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
   if (e != cudaSuccess) { set_error("coattn_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
-  coattn_affinity_tc_kernel<<<dim3(n_it, B), CA_THREADS, sm1, (cudaStream_t)stream>>>(giM, gu, P, n_it, rc_v, rc_i, cc_v, cc_i);
-  if (int rc = check_launch("coattn_affinity_tc")) return rc;
+  coattn_affinity_tc2_kernel<<<B, C2_THREADS, sm1, st>>>(imgA, imgB, n2a, n2b, P, T, rc_v, rc_i, cc_v, cc_i);
+  if (int rc = check_launch("coattn_affinity_tc2")) return rc;
   const size_t sm2 = sizeof(float) * (((P + 3) & ~3) + 32) + sizeof(float4) * 8 * 32;
-  if (sm2 > 200 * 1024) return fail_arg("coattn_fwd_tc: P=%d too large", P);
   if (sm2 > 48 * 1024) cudaFuncSetAttribute(coattn_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, (cudaStream_t)stream>>>(giM, gu, gi, P, n_it, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
-                                                                       t_i, arg_u, arg_i, atte_u, atte_i);
+  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, st>>>(giM, gu, gi, P, 1, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
+                                                     t_i, arg_u, arg_i, atte_u, atte_i);
   return check_launch("coattn_resolve");
 }

@@ -19,7 +19,7 @@ H, D, ATT, KP, SV = 64, 128, 64, 64, 256
 TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
-TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "0") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
+TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
 def _f32(t):
@@ -274,9 +274,9 @@ class _CoAttnFn(Function):
         arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
         atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
         work = (2.0 * B * P * P * D, 2.0 * B * P * D * 4)
-        if TENSOR_CORE_COATTN:
+        if TENSOR_CORE_COATTN and P <= 512:
             n_it = (P + 127) // 128
-            scratch = torch.empty(8 * B * P * (1 + n_it), dtype=torch.float32, device=dev)
+            scratch = torch.empty((2 * B * n_it * 65536 + 2 * B * P * 4 + 4 * B * P * 16 + 256 + 3) // 4, dtype=torch.float32, device=dev)
             call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(scratch), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
                  ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
         else:
