@@ -273,7 +273,7 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ giM_b, cons
 
 // resolve the candidates with exact fp32 re-scoring, then tanh / softmax over all P / pooling (model.py:52-55)
 __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __restrict__ giM, const float* __restrict__ gu, const float* __restrict__ gi,
-                                                             int P, int n_it, const float4* __restrict__ rc_v, const int4* __restrict__ rc_i,
+                                                             const float* __restrict__ n2a, const float* __restrict__ n2b, int P, int n_it, const float4* __restrict__ rc_v, const int4* __restrict__ rc_i,
                                                              const float4* __restrict__ cc_v, const int4* __restrict__ cc_i,
                                                              float* __restrict__ soft_u, float* __restrict__ soft_i, float* __restrict__ t_u,
                                                              float* __restrict__ t_i, int* __restrict__ arg_u, int* __restrict__ arg_i,
@@ -290,19 +290,15 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
   float* soft = (side ? soft_i : soft_u) + (size_t)b * P;
   float* tv = (side ? t_i : t_u) + (size_t)b * P;
   int* arg = (side ? arg_i : arg_u) + (size_t)b * P;
-  // max_i |giM_i| of this sample (bound for the column-side tolerance)
+  // max_i |giM_i| of this sample (bound for the column-side tolerance); squared row norms come from coattn_images_kernel
   float gmax = 0.f;
   if (side == 0) {
-    for (int p = warp; p < P; p += 8) {
-      const float4 x = *reinterpret_cast<const float4*>(giM_b + (size_t)p * D + lane * 4);
-      gmax = fmaxf(gmax, warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w));
-    }
+    for (int p = tid; p < P; p += 256) gmax = fmaxf(gmax, n2a[(size_t)b * P + p]);
     gmax = sqrtf(block_max(gmax, red));
   }
   for (int p = warp; p < P; p += 8) {
-    // tolerance of this row (side 1: i = p) / column (side 0: j = p): the same bound the producer used, or looser
-    const float4 own = *reinterpret_cast<const float4*>((side ? giM_b : gu_b) + (size_t)p * D + lane * 4);
-    const float nrm = sqrtf(warp_sum(own.x * own.x + own.y * own.y + own.z * own.z + own.w * own.w));
+    // tolerance of this row (side 1: i = p) / column (side 0: j = p): the same bound the producer used
+    const float nrm = sqrtf((side ? n2a : n2b)[(size_t)b * P + p]);
     const float tau = CA_EPS * nrm * (side ? CA_GNORM : gmax);
     const int nl = side ? 1 : n_it;
     float head = -INFINITY;
@@ -393,7 +389,7 @@ extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float*
   if (int rc = check_launch("coattn_affinity_tc2")) return rc;
   const size_t sm2 = sizeof(float) * (((P + 3) & ~3) + 32) + sizeof(float4) * 8 * 32;
   if (sm2 > 48 * 1024) cudaFuncSetAttribute(coattn_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, st>>>(giM, gu, gi, P, 1, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
+  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, st>>>(giM, gu, gi, n2a, n2b, P, 1, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
                                                      t_i, arg_u, arg_i, atte_u, atte_i);
   return check_launch("coattn_resolve");
 }
