@@ -296,35 +296,56 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
     for (int p = tid; p < P; p += 256) gmax = fmaxf(gmax, n2a[(size_t)b * P + p]);
     gmax = sqrtf(block_max(gmax, red));
   }
-  for (int p = warp; p < P; p += 8) {
-    // tolerance of this row (side 1: i = p) / column (side 0: j = p): the same bound the producer used
-    const float nrm = sqrtf((side ? n2a : n2b)[(size_t)b * P + p]);
-    const float tau = CA_EPS * nrm * (side ? CA_GNORM : gmax);
-    const int nl = side ? 1 : n_it;
+  // (1) one thread per row / column: count the candidates that survive the tolerance; a unique survivor keeps its tensor-core value
+  //     (the common case), the others go to a work list;  (2) one warp per work-list entry: exact fp32 re-scoring
+  __shared__ int s_work[C2_MAXP], s_nwork;
+  if (tid == 0) s_nwork = 0;
+  __syncthreads();
+  const int nl = side ? 1 : n_it;
+  for (int p = tid; p < P; p += 256) {
+    const float tau = CA_EPS * sqrtf((side ? n2a : n2b)[(size_t)b * P + p]) * (side ? CA_GNORM : gmax);
     float head = -INFINITY;
     for (int l = 0; l < nl; ++l) head = fmaxf(head, side ? rc_v[(size_t)b * P + p].x : cc_v[((size_t)b * n_it + l) * P + p].x);
-    float best = -INFINITY, lone_v = 0.f;
-    int besti = 0x7fffffff, lone_i = 0, n_surv = 0;
-    for (int pass = 0; pass < 2; ++pass) {           // pass 0: count survivors; pass 1: exact re-scoring if more than one
-      if (pass == 1 && n_surv <= 1) break;
-      for (int l = 0; l < nl; ++l) {
-        const size_t o = side ? (size_t)b * P + p : ((size_t)b * n_it + l) * P + p;
-        const float4 v = side ? rc_v[o] : cc_v[o];
-        const int4 id = side ? rc_i[o] : cc_i[o];
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        const int ii[4] = {id.x, id.y, id.z, id.w};
+    float lone_v = 0.f;
+    int lone_i = 0, n_surv = 0;
+    for (int l = 0; l < nl; ++l) {
+      const size_t o = side ? (size_t)b * P + p : ((size_t)b * n_it + l) * P + p;
+      const float4 v = side ? rc_v[o] : cc_v[o];
+      const int4 id = side ? rc_i[o] : cc_i[o];
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const int ii[4] = {id.x, id.y, id.z, id.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (ii[k] < 0 || vv[k] < head - tau) continue;
-          if (pass == 0) { ++n_surv; lone_v = vv[k]; lone_i = ii[k]; }
-          else {
-            const float ex = side ? exact_dot(giM_b, gu_b, p, ii[k], lane) : exact_dot(giM_b, gu_b, ii[k], p, lane);
-            if (ex > best || (ex == best && ii[k] < besti)) { best = ex; besti = ii[k]; }
-          }
-        }
+      for (int k = 0; k < 4; ++k)
+        if (ii[k] >= 0 && vv[k] >= head - tau) { ++n_surv; lone_v = vv[k]; lone_i = ii[k]; }
+    }
+    if (n_surv <= 1) {
+      const float t = tanhf(lone_v);
+      sp[p] = t; tv[p] = t; arg[p] = lone_i;
+    } else if (p < C2_MAXP) {
+      s_work[atomicAdd(&s_nwork, 1)] = p;
+    }
+  }
+  __syncthreads();
+  for (int wi = warp; wi < s_nwork; wi += 8) {
+    const int p = s_work[wi];
+    const float tau = CA_EPS * sqrtf((side ? n2a : n2b)[(size_t)b * P + p]) * (side ? CA_GNORM : gmax);
+    float head = -INFINITY;
+    for (int l = 0; l < nl; ++l) head = fmaxf(head, side ? rc_v[(size_t)b * P + p].x : cc_v[((size_t)b * n_it + l) * P + p].x);
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+    for (int l = 0; l < nl; ++l) {
+      const size_t o = side ? (size_t)b * P + p : ((size_t)b * n_it + l) * P + p;
+      const float4 v = side ? rc_v[o] : cc_v[o];
+      const int4 id = side ? rc_i[o] : cc_i[o];
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      const int ii[4] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (ii[k] < 0 || vv[k] < head - tau) continue;
+        const float ex = side ? exact_dot(giM_b, gu_b, p, ii[k], lane) : exact_dot(giM_b, gu_b, ii[k], p, lane);
+        if (ex > best || (ex == best && ii[k] < besti)) { best = ex; besti = ii[k]; }
       }
     }
-    if (n_surv <= 1) { best = lone_v; besti = lone_i; }     // unique candidate: keep the tensor-core value
     if (lane == 0) {
       const float t = tanhf(best);
       sp[p] = t; tv[p] = t; arg[p] = besti;

@@ -286,6 +286,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     if (!c.active) { qi = 1; cur_init(a, c, 2 * blockIdx.x + 1); }
     if (c.active) produce(c);
     for (int n = 0; c.active; ++n) {
+      Cur nx = c;
+      cur_next(a, nx);
+      if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
+      if (nx.active && lane == 0) {
+        // the next step's saved gates (128 KB) and operand images are pulled into L2 while this step computes
+        const BwdSeg& sg = a.seg[nx.si];
+        const int t = dir ? nx.s : (nx.Lj - 1 - nx.s);
+        const int tp = dir ? t + 1 : t - 1;
+        const size_t slab0 = (size_t)sg.plan[3 * sg.n_tiles * RT_R + nx.tile];
+        bulk_prefetch_l2(sg.sv + ((slab0 + t) * 2 + dir) * SV * RT_R, SV * RT_R * 4);
+        bulk_prefetch_l2(sg.xq + (slab0 + t) * RB_IMG, RB_IMG);
+        if (tp >= 0 && tp < nx.Lj) bulk_prefetch_l2(sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG, RB_IMG);
+      }
       if (lane == 0) {
         mbar_wait(&bars.p1_ready, n & 1);
         tc_fence_after();
@@ -314,9 +327,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
         umma_commit(&bars.stage_free);           // (same completion as w2_done: operand images and staging are free again)
       }
       __syncwarp();
-      Cur nx = c;
-      cur_next(a, nx);
-      if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
       if (nx.active) {
         mbar_wait(&bars.stage_free, n & 1);     // all MMAs that read this step's images have retired (the gate threads read theirs before p1_ready)
         produce(nx);
