@@ -12,10 +12,10 @@
 //     bulk copy each), B operand = the gate gradients written by the gate threads as a token-major bf16 hi|lo tile;
 //     accumulated in TMEM over the CTA's whole queue and flushed once with atomics into the eight nn.GRU gradients;
 //   * TMEM (512 columns): [0,64) dh | [64,160) carry A hi | [160,256) carry A lo | [256,512) dW^T accumulator;
-//   * warps 0-7: gate threads (one sequence row x 32 hidden units each); warp 8: driver (32 lanes issue the TMA copies - d_out
-//     rows into a padded staging buffer, the two operand images - lane 0 issues the MMAs);
-//   * h_{t-1} of the cell's backward is read from the hq image (hi + lo), so `out` is not touched; saved gates svT are
-//     column-major inside a (slab, direction) tile (lanes = rows read 128 contiguous bytes).
+//   * warps 0-7: gate threads (one sequence row x 32 hidden units each): saved gates, d_out and h_{t-1} (hq image, hi + lo) are
+//     read straight from global memory (prefetched into L2 one step ahead); warp 8: driver thread (TMA copies of the two
+//     operand images, MMAs);
+//   * `out` is not touched; saved gates svT are column-major inside a (slab, direction) tile (lanes = rows read 128 contiguous bytes).
 #include "common.cuh"
 #include "tc.cuh"
 #include "gru_tc.cuh"
@@ -27,11 +27,9 @@ using namespace tc;
 constexpr int RB_GATE_WARPS = 8;
 constexpr int RB_THREADS = (RB_GATE_WARPS + 1) * 32;      // 288
 constexpr int RB_W_BYTES = 2 * G3 * 128;                  // W_hh hi | lo, [192][64 bf16]
-constexpr int RB_ROW = 272;                               // staged d_out row: 64 floats + 16 B pad (conflict-free 128-bit row reads)
-constexpr int RB_STAGE = RT_R * RB_ROW;
 constexpr int RB_IMG = 2 * RT_R * 128;                    // one operand image: hi | lo, [128][64 bf16] = 32 KB
 constexpr int RB_GT = 4 * RT_R * 128;                     // gate-gradient tile: [hi|lo][2 blocks of 64 gates][128 sequences][128 B] = 64 KB
-constexpr int RB_SMEM = RB_W_BYTES + RB_STAGE + 2 * RB_IMG + RB_GT + 1024;
+constexpr int RB_SMEM = RB_W_BYTES + 2 * RB_IMG + RB_GT + 1024;
 
 struct BwdSeg {
   const float* d_out; const float* d_hn; const float* sv; const unsigned char* xq; const unsigned char* hq; const int* plan;
@@ -66,14 +64,38 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float* v
   }
 }
 
+// Everything a gate thread needs for 8 hidden units of its row that does NOT depend on the carry: saved gates (column-major
+// tile: lanes = rows are contiguous), d_out (the row's own 32 bytes) and h_{t-1} (one 16-byte chunk of the hq image, hi and lo).
+// Loaded straight from global memory (the driver pulls the step's tile into L2 one step ahead).
+struct ChunkIn {
+  float r[8], z[8], n[8], hh[8];
+  float4 y0, y1;
+  uint4 hhi, hlo;
+};
+__device__ __forceinline__ void load_chunk(ChunkIn& in, bool live, const float* svcol, const float* dyrow, const unsigned char* hrow, int cc,
+                                           uint32_t off) {
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
+      in.r[i] = s1[0]; in.z[i] = s1[(size_t)H * RT_R]; in.n[i] = s1[(size_t)2 * H * RT_R]; in.hh[i] = s1[(size_t)3 * H * RT_R];
+    }
+    in.y0 = *reinterpret_cast<const float4*>(dyrow + cc * 8);
+    in.y1 = *reinterpret_cast<const float4*>(dyrow + cc * 8 + 4);
+    in.hhi = make_uint4(0u, 0u, 0u, 0u); in.hlo = in.hhi;
+    if (hrow) {
+      in.hhi = *reinterpret_cast<const uint4*>(hrow + off);
+      in.hlo = *reinterpret_cast<const uint4*>(hrow + RT_R * 128 + off);
+    }
+  }
+}
+
 __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, BwdRow& g, int n, int dir, int row, int hf,
                                               unsigned char* base, BwdBars* bar, uint32_t tmem) {
   const BwdSeg& sg = a.seg[c.si];
   const int u0 = hf * 32;
   const int Rp = sg.n_tiles * RT_R;
-  unsigned char* stage = base + RB_W_BYTES;
-  unsigned char* himg = stage + RB_STAGE + RB_IMG;         // hq image of h_{t-1}: hi | lo
-  unsigned char* gt = stage + RB_STAGE + 2 * RB_IMG;       // gate-gradient tile
+  unsigned char* gt = base + RB_W_BYTES + 2 * RB_IMG;       // gate-gradient tile
   if (c.s == 0) {
     const int k = c.tile * RT_R + row;
     g.rowo = sg.plan[Rp + k];
@@ -90,48 +112,47 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
     }
   }
   const int t = dir ? c.s : (c.Lj - 1 - c.s);          // reverse of the forward kernel's order
+  const int tp = dir ? t + 1 : t - 1;
   const bool live = t < g.len;
-  const float* svcol = sg.sv + (((size_t)(sg.plan[3 * Rp + c.tile] + t) * 2 + dir) * SV + u0) * RT_R + row;
-  const float* dy_s = reinterpret_cast<const float*>(stage + row * RB_ROW) + u0;
+  const size_t slab0 = (size_t)sg.plan[3 * Rp + c.tile];
+  const float* svcol = sg.sv + (((slab0 + t) * 2 + dir) * SV + u0) * RT_R + row;
+  const float* dyrow = sg.d_out + ((size_t)(g.rowo < 0 ? 0 : g.rowo) * sg.L + t) * D + dir * H + u0;
+  const unsigned char* hrow = (tp >= 0 && tp < c.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : nullptr;     // h_{t-1} image (zeros at the first step)
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16);
+  const uint32_t off0 = (uint32_t)(row * 128);
 
+  ChunkIn ci;                                   // chunk 0 is requested before the barrier waits: its latency hides behind them
+  load_chunk(ci, live, svcol, dyrow, hrow, 0, off0 + (((hf * 4) ^ (row & 7)) << 4));
   if (n > 0) {
     mbar_wait(&bar->acc_full, (n - 1) & 1);     // previous carry product retired: dh readable, its TMEM A operand reusable
     mbar_wait(&bar->w2_done, (n - 1) & 1);      // previous weight-gradient MMAs retired: the gate-gradient tile is reusable
     tc_fence_after();
   }
-  mbar_wait(&bar->stage_full, n & 1);           // d_out rows and the two operand images of this step have landed
   uint32_t dn_hi[16], dn_lo[16], dnr_hi[16], dnr_lo[16];          // pass-2 gate gradients, kept packed until pass 1 retires
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
+    const int chunk = hf * 4 + cc;
+    const uint32_t off = off0 + ((chunk ^ (row & 7)) << 4);
+    if (cc > 0) load_chunk(ci, live, svcol, dyrow, hrow, cc, off);
     uint32_t acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0u;
     if (c.s > 0) { tmem_ld8_issue(trow + u0 + cc * 8, acc); tmem_ld_wait(); }     // warp-uniform: outside the per-row branch
     float dr[8], dz[8], dn8[8], dnr[8];
-    const int chunk = hf * 4 + cc;
-    const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
     if (live) {
-      const float4 y0 = *reinterpret_cast<const float4*>(dy_s + cc * 8), y1 = *reinterpret_cast<const float4*>(dy_s + cc * 8 + 4);
-      const float dy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      const float dy[8] = {ci.y0.x, ci.y0.y, ci.y0.z, ci.y0.w, ci.y1.x, ci.y1.y, ci.y1.z, ci.y1.w};
       float hp[8];
-      unpack8(*reinterpret_cast<const uint4*>(himg + off), *reinterpret_cast<const uint4*>(himg + RT_R * 128 + off), hp);
-      float rr[8], zz[8], nn[8], hh[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
-        rr[i] = s1[0]; zz[i] = s1[(size_t)H * RT_R]; nn[i] = s1[(size_t)2 * H * RT_R]; hh[i] = s1[(size_t)3 * H * RT_R];
-      }
+      unpack8(ci.hhi, ci.hlo, hp);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float dh = g.part[cc * 8 + i] + __uint_as_float(acc[i]) + dy[i];
-        const float dnv = dh * (1.f - zz[i]);
-        const float dn_pre = dnv * (1.f - nn[i] * nn[i]);
-        dz[i] = dh * (hp[i] - nn[i]) * zz[i] * (1.f - zz[i]);
-        dr[i] = dn_pre * hh[i] * rr[i] * (1.f - rr[i]);
-        dnr[i] = dn_pre * rr[i];
+        const float dnv = dh * (1.f - ci.z[i]);
+        const float dn_pre = dnv * (1.f - ci.n[i] * ci.n[i]);
+        dz[i] = dh * (hp[i] - ci.n[i]) * ci.z[i] * (1.f - ci.z[i]);
+        dr[i] = dn_pre * ci.hh[i] * ci.r[i] * (1.f - ci.r[i]);
+        dnr[i] = dn_pre * ci.r[i];
         dn8[i] = dn_pre;
-        g.part[cc * 8 + i] = dh * zz[i];
+        g.part[cc * 8 + i] = dh * ci.z[i];
       }
     } else {
       // beyond this row's length: no gradient (zero rows in both products), the carry just passes through
@@ -144,19 +165,20 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
     // carry A operand in tensor memory: k = gate block * 64 + unit, two bf16 per 32-bit column, hi at +64, lo at +160;
     // weight-gradient B operand in shared memory: token-major tile, block 0 = dr (pass 2: dn), block 1 = dz (pass 2: dn*r)
     const uint32_t acol = trow + 64 + (u0 + cc * 8) / 2;
+    const uint32_t goff = off;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(dr[2 * i], dr[2 * i + 1], hi[i], lo[i]);
     tmem_st4(acol, hi[0], hi[1], hi[2], hi[3]);
     tmem_st4(acol + 96, lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(gt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 2 * RT_R * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(gt + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(gt + 2 * RT_R * 128 + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(dz[2 * i], dz[2 * i + 1], hi[i], lo[i]);
     tmem_st4(acol + 32, hi[0], hi[1], hi[2], hi[3]);
     tmem_st4(acol + 96 + 32, lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(gt + RT_R * 128 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 3 * RT_R * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(gt + RT_R * 128 + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(gt + 3 * RT_R * 128 + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], dnr_hi[cc * 4 + i], dnr_lo[cc * 4 + i]);
     tmem_st4(acol + 64, dnr_hi[cc * 4], dnr_hi[cc * 4 + 1], dnr_hi[cc * 4 + 2], dnr_hi[cc * 4 + 3]);
@@ -167,7 +189,7 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
   tmem_st_wait();
   fence_async_smem();
   tc_fence_before();
-  mbar_arrive(&bar->p1_ready);         // carry A operand + pass-1 tile (dr | dz) complete; d_out staging and hq image consumed
+  mbar_arrive(&bar->p1_ready);         // carry A operand + pass-1 tile (dr | dz) complete
   // pass 2: the same tile buffer, once the pass-1 MMAs have read it
   mbar_wait(&bar->w1_done, n & 1);
 #pragma unroll
@@ -189,14 +211,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   __shared__ uint32_t tmem_slot;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   unsigned char* whh = base;                                  // [hi|lo][192][128 B]
-  unsigned char* stage = base + RB_W_BYTES;                   // d_out rows [128][272 B]
-  unsigned char* ximg = stage + RB_STAGE;                     // xq image (hi|lo), then hq image (hi|lo)
+  unsigned char* ximg = base + RB_W_BYTES;                    // xq image (hi|lo), then hq image (hi|lo): operands of the weight-gradient MMAs
   unsigned char* gt = ximg + 2 * RB_IMG;                      // gate-gradient tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
 
   if (tid == 0) {
-    mbar_init(&bars.stage_full, 32);
+    mbar_init(&bars.stage_full, 1);
     mbar_init(&bars.stage_free, 1);
     mbar_init(&bars.p1_ready, RB_GATE_WARPS * 32);
     mbar_init(&bars.p2_ready, RB_GATE_WARPS * 32);
@@ -247,38 +268,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     // weight-gradient A operand: M = 128 features = [64 of xq | 64 of hq]: the second 64-feature block lies one image (32 KB) further
     const uint32_t xa_hi = smem_u32(ximg), xa_lo = smem_u32(ximg + RT_R * 128);
     const uint32_t g_hi = smem_u32(gt), g_lo = smem_u32(gt + 2 * RT_R * 128);
-    int rowo[4], len[4];
-    int cur_tile_id = -1, cur_seg = -1;
-    auto produce = [&](const Cur& cc) {
+    auto produce = [&](const Cur& cc) {      // the step's two operand images, one TMA bulk copy each (lane 0)
+      if (lane != 0) return;
       const BwdSeg& sg = a.seg[cc.si];
-      const int Rp = sg.n_tiles * RT_R;
-      if (cc.tile != cur_tile_id || cc.si != cur_seg) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int k = cc.tile * RT_R + lane + 32 * q;
-          rowo[q] = sg.plan[Rp + k];
-          len[q] = sg.plan[2 * Rp + k];
-        }
-        cur_tile_id = cc.tile; cur_seg = cc.si;
-      }
       const int t = dir ? cc.s : (cc.Lj - 1 - cc.s);
       const int tp = dir ? t + 1 : t - 1;
-      const size_t slab0 = (size_t)sg.plan[3 * Rp + cc.tile];
-      uint32_t bytes = lane == 0 ? 2 * RB_IMG : 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (rowo[q] >= 0 && t < len[q]) bytes += 256;
-      mbar_arrive_expect_tx(&bars.stage_full, bytes);
-      if (lane == 0) {
-        bulk_copy_g2s(ximg, sg.xq + (slab0 + t) * RB_IMG, RB_IMG, &bars.stage_full);
-        const unsigned char* hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
-        bulk_copy_g2s(ximg + RB_IMG, hsrc, RB_IMG, &bars.stage_full);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (rowo[q] >= 0 && t < len[q])
-          bulk_copy_g2s(stage + (lane + 32 * q) * RB_ROW, sg.d_out + ((size_t)rowo[q] * sg.L + t) * D + dir * H, 256, &bars.stage_full);
-      }
+      const size_t slab0 = (size_t)sg.plan[3 * sg.n_tiles * RT_R + cc.tile];
+      mbar_arrive_expect_tx(&bars.stage_full, 2 * RB_IMG);
+      bulk_copy_g2s(ximg, sg.xq + (slab0 + t) * RB_IMG, RB_IMG, &bars.stage_full);
+      const unsigned char* hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
+      bulk_copy_g2s(ximg + RB_IMG, hsrc, RB_IMG, &bars.stage_full);
     };
     Cur c;
     int qi = 0;
@@ -310,6 +309,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
           umma_bf16_ts(d_dh, a_lo + ks * 8, bh, id_carry, 1);
         }
         umma_commit(&bars.acc_full);
+        mbar_wait(&bars.stage_full, n & 1);      // the step's operand images have landed
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {  // dW^T[128 features][pass*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
           if (pass == 1) { mbar_wait(&bars.p2_ready, n & 1); tc_fence_after(); }
