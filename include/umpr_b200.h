@@ -160,6 +160,7 @@ int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* vie
                        const float* d_final, int B, int S, int V, int KC, float* dcfeat /*(N,KC) written*/, float* d_lin_w /*(+=)*/,
                        float* d_lin_b /*(+=)*/, float* d_conv_b /*(+=)*/, void* stream);
 int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC,
+                       float* wt_scratch /*KC*3*128 floats (tap-major weight copy), or NULL for the scatter kernel*/,
                        float* dx /*(N,L,128) written*/, float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
 
 /* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */

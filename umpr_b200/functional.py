@@ -462,7 +462,8 @@ class _CNetTailFn(Function):
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
         dx = torch.empty_like(x)
-        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(dx), ptr(d_conv_w), _n_ctas(dev),
+        wt = torch.empty(KC * 3 * D, dtype=torch.float32, device=dev)
+        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
              work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
         return dx, None, None, d_conv_w, d_conv_b, d_lin_w, d_lin_b, None
 
