@@ -237,13 +237,7 @@ __global__ void __launch_bounds__(128 * NQ, 1) cnet_conv_bwd_dx_kernel(const flo
   }
 }
 
-// dx by a sorted sweep (replaces the shared-memory read-modify-write scatter above for the hot path).  128 threads (one per
-// channel) own one sentence; 4 sentences per CTA.  The sentence's <= 128 (arg-max position, gradient, filter) triples are
-// sorted by position (rank by counting, deterministic: ties in filter order), then one pass over them keeps a sliding window of
-// THREE register accumulators - rows p-1, p, p+1 of this channel - and emits each output row exactly once, in order, as a
-// coalesced 512-byte store.  No atomics, no shared-memory accumulation; the weights are read from a [filter][tap][channel] copy
-// (one line per warp load) that stays in L1/L2 (184 KB, reused by every sentence).
-// w[kf][c][dt] -> wt[kf][dt][c]: a warp's 32 channels of one (filter, tap) become one 128-byte line
+// w[kf][c][dt] -> wt[kf][dt][c]: a warp's 128 channels of one (filter, tap) become one 512-byte row
 __global__ void cnet_wt_kernel(const float* __restrict__ w, int KC, float* __restrict__ wt) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= KC * CK * D) return;
@@ -251,55 +245,69 @@ __global__ void cnet_wt_kernel(const float* __restrict__ w, int KC, float* __res
   wt[idx] = w[((size_t)kf * D + c) * CK + dt];
 }
 
-__global__ void __launch_bounds__(512, 3) cnet_conv_bwd_dx_sweep_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
-                                                                        const float* __restrict__ wt, int N, int L, int KC,
-                                                                        float* __restrict__ dx) {
-  __shared__ int s_key[4][CKP];           // arg-max position of filter kf (0x7fff: no gradient through this filter)
-  __shared__ float4 s_sorted[4][CKP];     // (position, gradient, filter) in sweep order
-  const int tid = threadIdx.x, grp = tid >> 7, c = tid & 127;
-  for (int n0 = blockIdx.x * 4; n0 < N; n0 += gridDim.x * 4) {
-    const int n = n0 + grp;
-    const bool has = n < N;               // uniform inside the group of 128
-    float g = 0.f;
-    int t = -1;
-    if (has && c < KC) { g = dcfeat[(size_t)n * KC + c]; t = cidx[(size_t)n * KC + c]; }
-    const bool valid = g != 0.f && t >= 0;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");          // the previous sentence's sweep is done with the tables
-    s_key[grp][c] = valid ? t : 0x7fff;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-    // rank of (t, kf) among the valid filters; every thread also learns how many there are
-    int rank = 0, nvalid = 0;
-    const int4* keys = reinterpret_cast<const int4*>(s_key[grp]);
-#pragma unroll 4
-    for (int j4 = 0; j4 < CKP / 4; ++j4) {
-      const int4 k = keys[j4];
-      const int j = j4 * 4;
-      rank += (k.x < t || (k.x == t && j < c)) + (k.y < t || (k.y == t && j + 1 < c)) + (k.z < t || (k.z == t && j + 2 < c)) +
-              (k.w < t || (k.w == t && j + 3 < c));
-      nvalid += (k.x != 0x7fff) + (k.y != 0x7fff) + (k.z != 0x7fff) + (k.w != 0x7fff);
+// dx by a sorted sweep (replaces the shared-memory read-modify-write scatter above for the hot path).  ONE WARP per sentence,
+// each lane owns 4 channels (float4).  The sentence's <= 128 (arg-max position, gradient, filter) triples are counting-sorted
+// by position with warp ballots (deterministic: ties in filter order), then one pass over them keeps a sliding window of THREE
+// float4 accumulators per lane - rows p-1, p, p+1 - and emits each output row exactly once, in order, as a 512-byte store.
+// No atomics, no shared-memory accumulation; weights come from the tap-major copy wt[filter][tap][channel] (L1/L2 resident).
+constexpr int SW_WARPS = 8;
+__global__ void __launch_bounds__(SW_WARPS * 32, 4) cnet_conv_bwd_dx_sweep_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
+                                                                                 const float* __restrict__ wt, int N, int L, int KC,
+                                                                                 float* __restrict__ dx) {
+  __shared__ float2 s_sorted[SW_WARPS][CKP];     // (gradient, position | filter << 16) in sweep order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int n = blockIdx.x * SW_WARPS + warp; n < N; n += gridDim.x * SW_WARPS) {
+    // each lane holds filters lane, lane+32, lane+64, lane+96
+    float g[4];
+    int t[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kf = lane + 32 * q;
+      g[q] = kf < KC ? dcfeat[(size_t)n * KC + kf] : 0.f;
+      t[q] = kf < KC ? cidx[(size_t)n * KC + kf] : -1;
+      if (g[q] == 0.f) t[q] = -1;                               // no gradient through this filter
     }
-    if (valid) s_sorted[grp][rank] = make_float4(__int_as_float(t), g, __int_as_float(c), 0.f);
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-    if (!has) continue;
-    float* orow = dx + (size_t)n * L * D + c;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;        // rows cur-1, cur, cur+1
+    __syncwarp();
+    // counting sort by position: start[p] = number of valid filters with a smaller position; rank inside a position = filter order
+    int base = 0;
+    int rank[4] = {0, 0, 0, 0};
+    for (int p = 0; p < L; ++p) {
+      int cnt = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, t[q] == p);
+        if (t[q] == p) rank[q] = base + cnt + __popc(m & lt);
+        cnt += __popc(m);
+      }
+      base += cnt;
+    }
+    const int nvalid = base;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (t[q] >= 0) s_sorted[warp][rank[q]] = make_float2(g[q], __int_as_float(t[q] | ((lane + 32 * q) << 16)));
+    __syncwarp();
+    float* orow = dx + (size_t)n * L * D + lane * 4;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;        // rows cur-1, cur, cur+1
     int cur = 0;
     for (int i = 0; i < nvalid; ++i) {
-      const float4 e = s_sorted[grp][i];
-      const int p = __float_as_int(e.x), kf = __float_as_int(e.z);
+      const float2 e = s_sorted[warp][i];
+      const int pk = __float_as_int(e.y), p = pk & 0xffff, kf = pk >> 16;
       while (cur < p) {                        // slide the window: row cur-1 is complete
-        if (cur >= 1) orow[(size_t)(cur - 1) * D] = a0;
-        a0 = a1; a1 = a2; a2 = 0.f; ++cur;
+        if (cur >= 1) *reinterpret_cast<float4*>(orow + (size_t)(cur - 1) * D) = a0;
+        a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f); ++cur;
       }
-      const float* wk = wt + (size_t)kf * CK * D + c;
-      a0 = fmaf(e.y, wk[0], a0);               // x position p + dt - 1
-      a1 = fmaf(e.y, wk[D], a1);
-      a2 = fmaf(e.y, wk[2 * D], a2);
+      const float4* wk = reinterpret_cast<const float4*>(wt + (size_t)kf * CK * D) + lane;
+      const float4 w0 = wk[0], w1 = wk[D / 4], w2 = wk[2 * D / 4];        // taps 0, 1, 2 -> x positions p-1, p, p+1
+      a0.x = fmaf(e.x, w0.x, a0.x); a0.y = fmaf(e.x, w0.y, a0.y); a0.z = fmaf(e.x, w0.z, a0.z); a0.w = fmaf(e.x, w0.w, a0.w);
+      a1.x = fmaf(e.x, w1.x, a1.x); a1.y = fmaf(e.x, w1.y, a1.y); a1.z = fmaf(e.x, w1.z, a1.z); a1.w = fmaf(e.x, w1.w, a1.w);
+      a2.x = fmaf(e.x, w2.x, a2.x); a2.y = fmaf(e.x, w2.y, a2.y); a2.z = fmaf(e.x, w2.z, a2.z); a2.w = fmaf(e.x, w2.w, a2.w);
     }
     while (cur <= L) {                         // flush: every row of dx is written exactly once (zeros where nothing landed)
-      if (cur >= 1) orow[(size_t)(cur - 1) * D] = a0;
-      a0 = a1; a1 = a2; a2 = 0.f; ++cur;
+      if (cur >= 1) *reinterpret_cast<float4*>(orow + (size_t)(cur - 1) * D) = a0;
+      a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f); ++cur;
     }
+    __syncwarp();
   }
 }
 
@@ -406,9 +414,9 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
   const size_t sm2 = sizeof(float) * (2 * (L + 2) * D + CKP) + sizeof(int) * CKP;
   if (wt_scratch && KC <= CKP && L < 0x7fff) {
     cnet_wt_kernel<<<(KC * CK * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, wt_scratch);
-    const int g4 = (N + 3) / 4;
-    const int want = 3 * (n_ctas > 0 ? n_ctas : 148);
-    cnet_conv_bwd_dx_sweep_kernel<<<g4 < want ? g4 : want, 512, 0, (cudaStream_t)stream>>>(dcfeat, cidx, wt_scratch, N, L, KC, dx);
+    const int g4 = (N + SW_WARPS - 1) / SW_WARPS;
+    const int want = 8 * (n_ctas > 0 ? n_ctas : 148);
+    cnet_conv_bwd_dx_sweep_kernel<<<g4 < want ? g4 : want, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(dcfeat, cidx, wt_scratch, N, L, KC, dx);
   } else if (sm4 <= 200 * 1024) {
     cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
     cnet_conv_bwd_dx_kernel<4><<<grid, 512, sm4, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
