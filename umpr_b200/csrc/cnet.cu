@@ -316,27 +316,44 @@ __global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dw_kernel(const float* _
                                                                   const int* __restrict__ cidx, int N, int L, int KC,
                                                                   float* __restrict__ dw) {
   extern __shared__ __align__(16) float smem[];
-  float* xs = smem;                        // [(L+2)][128] with zero guard rows
-  float* gsm = xs + (L + 2) * D;
-  int* tsm = reinterpret_cast<int*>(gsm + CKP);
+  // two stages of {sentence [(L+2)][128] with zero guard rows, gradients [128], arg-max positions [128]}: the next sentence
+  // streams in (cp.async) while the current one is consumed
+  const int stage_f = (L + 2) * D + 2 * CKP;
   const int tid = threadIdx.x, q = tid >> 7, c = tid & 127;
   float acc[32][CK];
 #pragma unroll
   for (int i = 0; i < 32; ++i)
 #pragma unroll
     for (int dt = 0; dt < CK; ++dt) acc[i][dt] = 0.f;
-  for (int idx = tid; idx < D; idx += 512) { xs[idx] = 0.f; xs[(L + 1) * D + idx] = 0.f; }
-  for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    __syncthreads();
+  for (int s2 = 0; s2 < 2; ++s2)
+    for (int idx = tid; idx < D; idx += 512) { smem[s2 * stage_f + idx] = 0.f; smem[s2 * stage_f + (L + 1) * D + idx] = 0.f; }
+  auto issue = [&](int n, int st) {
+    float* xs = smem + st * stage_f;
     const float4* src = reinterpret_cast<const float4*>(x + (size_t)n * L * D);
     for (int idx = tid; idx < L * (D / 4); idx += 512) cp_async16(&xs[D + idx * 4], src + idx);
-    cp_async_commit();
     if (tid < CKP) {
-      gsm[tid] = tid < KC ? dcfeat[(size_t)n * KC + tid] : 0.f;
-      tsm[tid] = tid < KC ? cidx[(size_t)n * KC + tid] : -1;
+      float* gsm = xs + (L + 2) * D;
+      int* tsm = reinterpret_cast<int*>(gsm + CKP);
+      if (tid < KC) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&gsm[tid])), "l"(dcfeat + (size_t)n * KC + tid));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&tsm[tid])), "l"(cidx + (size_t)n * KC + tid));
+      } else {
+        gsm[tid] = 0.f; tsm[tid] = -1;
+      }
     }
-    cp_async_wait_all();
-    __syncthreads();
+    cp_async_commit();
+  };
+  int it = 0;
+  if ((int)blockIdx.x < N) issue(blockIdx.x, 0);
+  for (int n = blockIdx.x; n < N; n += gridDim.x, ++it) {
+    const int st = it & 1;
+    const int nn = n + gridDim.x;
+    if (nn < N) { issue(nn, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    else cp_async_wait_all();
+    __syncthreads();                         // stage st has landed for every thread
+    const float* xs = smem + st * stage_f;
+    const float* gsm = xs + (L + 2) * D;
+    const int* tsm = reinterpret_cast<const int*>(gsm + CKP);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float g = gsm[q * 32 + i];
@@ -346,6 +363,7 @@ __global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dw_kernel(const float* _
         for (int dt = 0; dt < CK; ++dt) acc[i][dt] += g * xs[(t + dt) * D + c];
       }
     }
+    __syncthreads();                         // stage st may be refilled by the next iteration's prefetch
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
@@ -407,7 +425,7 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
                                   int KC, float* wt_scratch, float* dx, float* d_conv_w, int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
-  const size_t sm = sizeof(float) * ((L + 2) * D + CKP) + sizeof(int) * CKP;
+  const size_t sm = 2 * (sizeof(float) * ((L + 2) * D + CKP) + sizeof(int) * CKP);
   if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd: L=%d too large", L);
   const int grid = n_ctas > 0 && n_ctas < N ? n_ctas : N;
   const size_t sm4 = sizeof(float) * (4 * (L + 2) * D + CKP) + sizeof(int) * CKP;
