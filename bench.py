@@ -223,19 +223,31 @@ def main():
         barrier()
         return float(ms), clocks
 
+    from umpr_b200.train import PlanPrefetcher
+
+    def stream_of(batches, n):            # what a data loader does: the next batch's host-side pack plans are prepared on a worker
+        def gen():                        # thread while the current step runs (fresh plans every step: nothing is cached across steps)
+            for i in range(n):
+                b = batches[i % NB]
+                yield tuple(t.clone() if j in (3, 4, 5) else t for j, t in enumerate(b))     # new lengths tensors, as a loader would emit
+        return PlanPrefetcher(gen(), dev)
+
+    feed = {"it": None}
+
     def step_resident(i):
-        trainer.train_step(devb[i % NB])
+        trainer.train_step(next(feed["it"]))
 
     sink = []
     from umpr_b200.train import AsyncScalarReader
     reader = AsyncScalarReader(depth=2)
 
     def step_e2e(i):
-        pred, loss = trainer.train_step(host[i % NB])          # H2D of ids/photos/labels happens inside UMPR.forward
+        pred, loss = trainer.train_step(next(feed["it"]))      # H2D of ids/photos/labels happens inside UMPR.forward
         sink.extend(reader.push(loss))                         # main.py:39: D2H read of the loss EVERY step (pinned slot, async copy,
                                                                # delivered one step later so the host keeps issuing the next step)
 
     # ---- warm-up, with every entry point timed once to find the dominant kernel
+    feed["it"] = stream_of(devb, W)
     for i in range(W - 1):
         step_resident(i)
     _lib.start_timing()
@@ -251,14 +263,17 @@ def main():
     # ---- timed region: K steps, inputs resident; only the dominant entry point carries event pairs
     launches0 = _lib.launch_count
     _lib.start_timing(only=[top])
+    feed["it"] = stream_of(devb, K)
     ms, clocks = timed(step_resident, K, ClockSampler(local))
     launches = _lib.launch_count - launches0
     kt = _lib.stop_timing()[top]
     value = world * B * K / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers
+    feed["it"] = stream_of(host, 2)
     for i in range(2):
         step_e2e(i)
+    feed["it"] = stream_of(host, K)
     n_before = len(sink) + reader.inflight
     ms_e2e, _ = timed(lambda i: (step_e2e(i), sink.extend(reader.drain()) if i == K - 1 else None), K)
     assert len(sink) + reader.inflight - n_before == K and all(v == v for v in sink), "every step's loss must have been read back"
@@ -278,6 +293,7 @@ def main():
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "tokens_per_step_per_gpu": int(sum(tokens) / NB), "trainable_params": n_params,
                    "step": "zero_grad+fwd+bwd+allreduce+adam",
+                   "host_pipeline": "the next batch's pack plans (torch.sort + int32 plan) are built on a worker thread, like a collate worker; rebuilt every step",
                    "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; 4 rotating input batches"},
         "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "ms_per_step": round(ms_e2e / K, 4), "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
@@ -318,9 +334,11 @@ def main():
     if world == 1 and rank == 0:
         if not args.no_batch64:
             small = [resident(syn.make_batch(args.workload, 64, seed=77 + i)) for i in range(NB)]
+            feed["it"] = stream_of(small, 3)
             for i in range(3):
-                trainer.train_step(small[i % NB])
-            ms64, _ = timed(lambda i: trainer.train_step(small[i % NB]), K)
+                step_resident(i)
+            feed["it"] = stream_of(small, K)
+            ms64, _ = timed(step_resident, K)
             line["batch64"] = {"value": round(64 * K / (ms64 / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms64 / K, 4),
                                "note": "reference default batch_size=64 (config.py:12), inputs resident"}
         if not args.no_cpu_baseline:

@@ -89,3 +89,21 @@ def test_schedule_covers_every_tile_once_and_balances(sizes, ctas):
         assert per_q.max() - per_q.min() <= 2 * lens.max()              # boustrophedon dealing keeps the slot queues level
     else:
         assert (per_q[0::2] > 0).all()                                  # few tiles: every CTA gets one before any gets two
+
+
+def test_plan_prefetcher_prepares_the_same_plans_off_thread():
+    """train.PlanPrefetcher (collate-worker pattern): plans built on the worker thread equal the ones built in place, ride on
+    the lengths tensors of the unchanged 8-tuple, and every batch of the source comes out once, in order."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.train import PlanPrefetcher
+    batches = [syn.make_batch("music_full", 9, vocab=500, seed=s) for s in range(4)]
+    out = list(PlanPrefetcher(iter(batches), "cpu"))
+    assert len(out) == 4
+    for b, o in zip(batches, out):
+        assert all(x is y for x, y in zip(b, o))
+        for ids, lens in ((o[0], o[3]), (o[1], o[4]), (o[2], o[5])):
+            ref = PackPlan(lens.reshape(-1), ids.shape[2], "cpu")
+            got = lens._umpr_plan
+            assert got.L == ids.shape[2] and got.N == lens.numel() and got.R == ref.R
+            assert torch.equal(got.host, ref.host) and torch.equal(got.sorted_indices, ref.sorted_indices)
+            assert got.ensure_uploaded().buf is not None

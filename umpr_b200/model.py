@@ -27,7 +27,13 @@ class PackedReviews:
         dev = table.device if table is not None else emb.device
         if emb is not None and emb.requires_grad:
             raise RuntimeError("umpr_b200: the embedding is frozen on this path (model.py:237); no input gradient is produced")
-        self.plan = PackPlan(lengths.reshape(-1), self.L, dev)               # model.py:42-43 flatten + model.py:18
+        # model.py:42-43 flatten + model.py:18.  A data-pipeline thread may have prepared the plan already (train.PlanPrefetcher
+        # attaches it to the lengths tensor); it is only accepted if it was built for exactly this tensor and padded length.
+        pre = getattr(lengths, "_umpr_plan", None)
+        if pre is not None and pre.L == self.L and pre.N == lengths.numel() and pre.device == torch.device(dev):
+            self.plan = pre.ensure_uploaded()
+        else:
+            self.plan = PackPlan(lengths.reshape(-1), self.L, dev)
         self._src = (dict(table=table, ids=ids.reshape(self.B * self.S, self.L)) if ids is not None
                      else dict(dense=emb.reshape(self.B * self.S, self.L, emb.shape[-1])))
         self.E = table.shape[1] if ids is not None else emb.shape[-1]

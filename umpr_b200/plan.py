@@ -109,7 +109,7 @@ class PackPlan:
     (model.py:21 applies the un-sort permutation a second time).
     """
 
-    def __init__(self, lengths: torch.Tensor, total_length: int, device, tile_rows: int | None = None):
+    def __init__(self, lengths: torch.Tensor, total_length: int, device, tile_rows: int | None = None, upload: bool = True):
         import numpy as np
         lens = lengths.detach().to("cpu", torch.int64).reshape(-1)          # model.py:18 lengths.cpu()
         n = lens.numel()
@@ -150,7 +150,14 @@ class PackPlan:
         self.host = torch.from_numpy(host)
         self.tokens = int(sl.sum())                                          # T_v: valid tokens
         self.slots = self.n_slabs * R                                        # token slots actually computed
-        self.buf = upload_int32(host, self.device)
+        self._host_np = host
+        self.buf = upload_int32(host, self.device) if upload else None      # upload=False: built off-thread, see ensure_uploaded()
+
+    def ensure_uploaded(self):
+        """Plans prepared by a data-pipeline thread (train.PlanPrefetcher) are uploaded here, on the consumer's thread/stream."""
+        if self.buf is None:
+            self.buf = upload_int32(self._host_np, self.device)
+        return self
 
     @property
     def unsorted_indices(self) -> torch.Tensor:

@@ -79,6 +79,52 @@ class FlatTrainer:
         return pred, loss
 
 
+def prepare_batch(batch, device):
+    """Host-side half of ImprovedRnn's packing for one batch (the reference's ``torch.sort`` call and the integer plan derived
+    from it, plan.PackPlan) - what a collate worker would do.  The plans ride on the three ``lengths``
+    tensors of the 8-tuple, so the model's forward signature is unchanged; no CUDA call is made here."""
+    from .plan import PackPlan
+    u, it, ui, ul, il, uil = batch[:6]
+    for ids, lens in ((u, ul), (it, il), (ui, uil)):
+        if lens.numel() and ids.dim() == 3:
+            lens._umpr_plan = PackPlan(lens.reshape(-1), ids.shape[2], device, upload=False)
+    return batch
+
+
+class PlanPrefetcher:
+    """Iterator over batches that prepares the NEXT batch's pack plans on a worker thread while the current step runs
+    (the data-loader pattern; ``torch.sort`` and numpy release the GIL).  ``for batch in PlanPrefetcher(loader, device): ...``"""
+
+    def __init__(self, batches, device, depth: int = 2):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=depth)
+        self._done = object()
+        self._err = None
+
+        def work():
+            try:
+                for b in batches:
+                    self._q.put(prepare_batch(b, device))
+            except BaseException as e:          # surfaced on the consumer's thread
+                self._err = e
+            self._q.put(self._done)
+
+        self._thr = threading.Thread(target=work, daemon=True)
+        self._thr.start()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        b = self._q.get()
+        if b is self._done:
+            if self._err is not None:
+                raise self._err
+            raise StopIteration
+        return b
+
+
 class AsyncScalarReader:
     """Per-step device→host read of a scalar (the loss of main.py:38-39) that does not drain the GPU: the value goes to a
     pinned slot with an asynchronous copy, and is handed out one step later, when its copy has completed.  Every step's value
