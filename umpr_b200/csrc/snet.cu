@@ -9,24 +9,28 @@ namespace umpr {
 
 constexpr int XLD = D + 4;      // 132
 constexpr int TLD = ATT + 4;    // 68
-constexpr int SN_ROWS = 128;
+constexpr int SN_ROWS = 128;    // largest row tile (and the longest sentence supported)
 constexpr int SN_MAXG = 16;     // sentences per CTA tile
 
-struct SnetSmem {
-  float xs[SN_ROWS * XLD];      // x rows, row-major
-  float ths[SN_ROWS * TLD];     // tanh(Ms x) rows (forward: scratch; backward: th then d(pre-tanh))
+// ROWS = rows of one CTA tile: 128, or 64 when the sentences are short enough - half the shared memory, two CTAs per SM, so
+// one CTA's loads and barrier phases overlap the other's math
+template <int ROWS>
+struct SnetSmemT {
+  float xs[ROWS * XLD];         // x rows, row-major
+  float ths[ROWS * TLD];        // tanh(Ms x) rows (forward: scratch; backward: th then d(pre-tanh))
   float ms[D * TLD];            // forward: Ms^T [k][a] ; backward: Ms [a][c] uses [ATT][XLD] (same bytes: 128*68 == 64*132+256)
-  float score[SN_ROWS];
-  float soft[SN_ROWS];
+  float score[ROWS];
+  float soft[ROWS];
   float ws[ATT];
   float red[32];
 };
 static_assert(D * TLD >= ATT * XLD, "ms buffer reuse");
 
+template <int ROWS>
 __device__ __forceinline__ void load_rows(float* dst, int ld, const float* __restrict__ src, int rows, int width, int tid) {
-  // rows x width floats (width % 4 == 0) -> dst[r*ld + c]; rows..SN_ROWS zero-filled
+  // rows x width floats (width % 4 == 0) -> dst[r*ld + c]; rows..ROWS zero-filled
   const int w4 = width >> 2;
-  for (int idx = tid; idx < SN_ROWS * w4; idx += 256) {
+  for (int idx = tid; idx < ROWS * w4; idx += 256) {
     const int r = idx / w4, c4 = idx - r * w4;
     if (r < rows) cp_async16(&dst[r * ld + c4 * 4], src + (size_t)r * width + c4 * 4);
     else *reinterpret_cast<float4*>(&dst[r * ld + c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -34,12 +38,15 @@ __device__ __forceinline__ void load_rows(float* dst, int ld, const float* __res
   cp_async_commit();
 }
 
-__global__ void __launch_bounds__(256, 1) snet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Ms,
+template <int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 64 ? 2 : 1) snet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Ms,
                                                           const float* __restrict__ Ws, int N, int L, int gs,
                                                           float* __restrict__ self_atte, float* __restrict__ soft_out,
                                                           float* __restrict__ th_out) {
   extern __shared__ __align__(16) unsigned char raw[];
-  SnetSmem& S = *reinterpret_cast<SnetSmem*>(raw);
+  using Smem = SnetSmemT<ROWS>;
+  constexpr int RPT = ROWS / 16;           // rows per thread of the 16 x 16 thread grid
+  Smem& S = *reinterpret_cast<Smem*>(raw);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
   for (int idx = tid; idx < ATT * D; idx += 256) {
     const int a = idx >> 7, k = idx & 127;
@@ -52,23 +59,23 @@ __global__ void __launch_bounds__(256, 1) snet_fwd_kernel(const float* __restric
     const int ns = min(gs, N - n0);
     const int rows = ns * L;
     __syncthreads();
-    load_rows(S.xs, XLD, x + (size_t)n0 * L * D, rows, D, tid);
+    load_rows<ROWS>(S.xs, XLD, x + (size_t)n0 * L * D, rows, D, tid);
     cp_async_wait_all();
     __syncthreads();
-    float acc[8][4];
+    float acc[RPT][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
     for (int k4 = 0; k4 < D / 4; ++k4) {
-      float4 a[8];
+      float4 a[RPT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&S.xs[(ty * 8 + i) * XLD + k4 * 4]);
+      for (int i = 0; i < RPT; ++i) a[i] = *reinterpret_cast<const float4*>(&S.xs[(ty * RPT + i) * XLD + k4 * 4]);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const float4 b = *reinterpret_cast<const float4*>(&S.ms[(k4 * 4 + kk) * TLD + tx * 4]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
           acc[i][0] += av * b.x; acc[i][1] += av * b.y; acc[i][2] += av * b.z; acc[i][3] += av * b.w;
         }
@@ -76,8 +83,8 @@ __global__ void __launch_bounds__(256, 1) snet_fwd_kernel(const float* __restric
     }
     const float4 w4 = *reinterpret_cast<const float4*>(&S.ws[tx * 4]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = ty * 8 + i;
+    for (int i = 0; i < RPT; ++i) {
+      const int r = ty * RPT + i;
       const float t0 = tanhf(acc[i][0]), t1 = tanhf(acc[i][1]), t2 = tanhf(acc[i][2]), t3 = tanhf(acc[i][3]);
       float sc = t0 * w4.x + t1 * w4.y + t2 * w4.z + t3 * w4.w;
 #pragma unroll
@@ -154,14 +161,17 @@ __global__ void __launch_bounds__(128) snet_sentiment_bwd_kernel(const float* __
   }
 }
 
-__global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restrict__ x, const float* __restrict__ th,
+template <int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 64 ? 2 : 1) snet_bwd_kernel(const float* __restrict__ x, const float* __restrict__ th,
                                                           const float* __restrict__ soft, const float* __restrict__ d_sa,
                                                           const float* __restrict__ Ms, const float* __restrict__ Ws, int N, int L,
                                                           int gs, float* __restrict__ dx, float* __restrict__ dMs,
                                                           float* __restrict__ dWs) {
   extern __shared__ __align__(16) unsigned char raw[];
-  SnetSmem& S = *reinterpret_cast<SnetSmem*>(raw);
-  float* dsa = reinterpret_cast<float*>(raw + sizeof(SnetSmem));    // [SN_MAXG][128]
+  using Smem = SnetSmemT<ROWS>;
+  constexpr int RPT = ROWS / 16;
+  Smem& S = *reinterpret_cast<Smem*>(raw);
+  float* dsa = reinterpret_cast<float*>(raw + sizeof(Smem));    // [SN_MAXG][128]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   float* msn = S.ms;                                                 // Ms natural layout [a][XLD]
   for (int idx = tid; idx < ATT * D; idx += 256) {
@@ -181,9 +191,9 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
     const int ns = min(gs, N - n0);
     const int rows = ns * L;
     __syncthreads();
-    load_rows(S.xs, XLD, x + (size_t)n0 * L * D, rows, D, tid);
-    load_rows(S.ths, TLD, th + (size_t)n0 * L * ATT, rows, ATT, tid);
-    for (int idx = tid; idx < SN_ROWS; idx += 256) S.soft[idx] = idx < rows ? soft[(size_t)n0 * L + idx] : 0.f;
+    load_rows<ROWS>(S.xs, XLD, x + (size_t)n0 * L * D, rows, D, tid);
+    load_rows<ROWS>(S.ths, TLD, th + (size_t)n0 * L * ATT, rows, ATT, tid);
+    for (int idx = tid; idx < ROWS; idx += 256) S.soft[idx] = idx < rows ? soft[(size_t)n0 * L + idx] : 0.f;
     for (int idx = tid; idx < ns * D; idx += 256) dsa[idx] = d_sa[(size_t)n0 * D + idx];
     cp_async_wait_all();
     __syncthreads();
@@ -204,7 +214,7 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
       dot = warp_sum(dot);
       for (int l = lane; l < L; l += 32) S.score[s * L + l] = S.soft[s * L + l] * (S.score[s * L + l] - dot);
     }
-    for (int r = rows + tid; r < SN_ROWS; r += 256) S.score[r] = 0.f;
+    for (int r = rows + tid; r < ROWS; r += 256) S.score[r] = 0.f;
     __syncthreads();
     // through Ws and tanh: ths <- d(pre-tanh);  dWs += sum_r d_score[r] th[r]
     {
@@ -219,21 +229,21 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
     __syncthreads();
     // dx[r][c] = soft[r] d_sa[s][c] + sum_a dpre[r][a] Ms[a][c]
     {
-      float acc[8][8];
+      float acc[RPT][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < RPT; ++i)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
       for (int k4 = 0; k4 < ATT / 4; ++k4) {
-        float4 a[8];
+        float4 a[RPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&S.ths[(ty * 8 + i) * TLD + k4 * 4]);
+        for (int i = 0; i < RPT; ++i) a[i] = *reinterpret_cast<const float4*>(&S.ths[(ty * RPT + i) * TLD + k4 * 4]);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const float4 b0 = *reinterpret_cast<const float4*>(&msn[(k4 * 4 + kk) * XLD + tx * 4]);
           const float4 b1 = *reinterpret_cast<const float4*>(&msn[(k4 * 4 + kk) * XLD + 64 + tx * 4]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < RPT; ++i) {
             const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
             acc[i][0] += av * b0.x; acc[i][1] += av * b0.y; acc[i][2] += av * b0.z; acc[i][3] += av * b0.w;
             acc[i][4] += av * b1.x; acc[i][5] += av * b1.y; acc[i][6] += av * b1.z; acc[i][7] += av * b1.w;
@@ -241,8 +251,8 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = ty * 8 + i;
+      for (int i = 0; i < RPT; ++i) {
+        const int r = ty * RPT + i;
         if (r >= rows) continue;
         const int s = r / L;
         const float so = S.soft[r];
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
       }
     }
     // dMs[a][c] += sum_r dpre[r][a] x[r][c]   (zero rows beyond `rows` contribute nothing)
-    for (int r = 0; r < SN_ROWS; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       if (r >= rows) break;
       const float4 a4 = *reinterpret_cast<const float4*>(&S.ths[r * TLD + ty * 4]);
       const float4 b0 = *reinterpret_cast<const float4*>(&S.xs[r * XLD + tx * 4]);
@@ -281,23 +291,28 @@ __global__ void __launch_bounds__(256, 1) snet_bwd_kernel(const float* __restric
 
 using namespace umpr;
 
-static int snet_group(int L) {
-  int gs = SN_ROWS / L;
+static int snet_group(int L, int rows) {
+  int gs = rows / L;
   if (gs > SN_MAXG) gs = SN_MAXG;
   return gs;
 }
+// 64-row tiles (two CTAs per SM) when they waste no more rows than 128-row tiles do
+static int snet_rows(int L) { return (L <= 64 && (64 / L) * 2 >= 128 / L) ? 64 : 128; }
 
 extern "C" int umpr_snet_fwd(const float* x, const float* Ms, const float* Ws, int N, int L, float* self_atte, float* soft,
                              float* th, int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (L < 1 || L > SN_ROWS) return fail_arg("snet_fwd: sentence length L=%d must be in [1, %d]", L, SN_ROWS);
-  const int gs = snet_group(L);
+  const int rows = 128;            // the forward has few barrier phases: 128-row tiles measured faster than 2 CTAs of 64 rows
+  const int gs = snet_group(L, rows);
   const int n_groups = (N + gs - 1) / gs;
-  const size_t sm = sizeof(SnetSmem);
-  cudaError_t e = cudaFuncSetAttribute(snet_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  const size_t sm = rows == 64 ? sizeof(SnetSmemT<64>) : sizeof(SnetSmemT<128>);
+  auto kern = rows == 64 ? snet_fwd_kernel<64> : snet_fwd_kernel<128>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) { set_error("snet_fwd smem: %s", cudaGetErrorString(e)); return (int)e; }
+  if (rows == 64) n_ctas *= 2;
   const int grid = n_ctas > 0 && n_ctas < n_groups ? n_ctas : n_groups;
-  snet_fwd_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(x, Ms, Ws, N, L, gs, self_atte, soft, th);
+  kern<<<grid, 256, sm, (cudaStream_t)stream>>>(x, Ms, Ws, N, L, gs, self_atte, soft, th);
   return check_launch("snet_fwd");
 }
 
@@ -319,12 +334,15 @@ extern "C" int umpr_snet_bwd(const float* x, const float* th, const float* soft,
                              int N, int L, float* dx, float* dMs, float* dWs, int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (L < 1 || L > SN_ROWS) return fail_arg("snet_bwd: sentence length L=%d must be in [1, %d]", L, SN_ROWS);
-  const int gs = snet_group(L);
+  const int rows = snet_rows(L);
+  const int gs = snet_group(L, rows);
   const int n_groups = (N + gs - 1) / gs;
-  const size_t sm = sizeof(SnetSmem) + sizeof(float) * SN_MAXG * D;
-  cudaError_t e = cudaFuncSetAttribute(snet_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  const size_t sm = (rows == 64 ? sizeof(SnetSmemT<64>) : sizeof(SnetSmemT<128>)) + sizeof(float) * SN_MAXG * D;
+  auto kern = rows == 64 ? snet_bwd_kernel<64> : snet_bwd_kernel<128>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   if (e != cudaSuccess) { set_error("snet_bwd smem: %s", cudaGetErrorString(e)); return (int)e; }
+  if (rows == 64) n_ctas *= 2;
   const int grid = n_ctas > 0 && n_ctas < n_groups ? n_ctas : n_groups;
-  snet_bwd_kernel<<<grid, 256, sm, (cudaStream_t)stream>>>(x, th, soft, d_sa, Ms, Ws, N, L, gs, dx, dMs, dWs);
+  kern<<<grid, 256, sm, (cudaStream_t)stream>>>(x, th, soft, d_sa, Ms, Ws, N, L, gs, dx, dMs, dWs);
   return check_launch("snet_bwd");
 }
