@@ -92,11 +92,6 @@ typedef struct umpr_gru_bwd_seg {
 } umpr_gru_bwd_seg;
 int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs /*host array*/, int n_seg, const float* const* w, float* const* dw, int E,
                     const void* zero_img, const int32_t* sched, int n_queues, void* stream);
-/* dw[8] (+=) from dG[n_slabs][2][256][128] (column-major inside a tile, R = 128): tcgen05 with K-major dG^T and token-major
- * [xp | h_prev] operands (stand-alone weight-gradient kernel; the fused backward above does not need it) */
-int umpr_gru_wgrad_tc2(const float* dG, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs, int L, int E,
-                       float* const* dw, int n_ctas, void* stream);
-
 /* ---- generic strided fp32 GEMM: gi·M (model.py:50), text matching (model.py:168) and their gradients ----
  * C[m][n] = act(accumulate*C + sum_k A[m*ars+k*acs] * B[k*brs+n*bcs] + bias[n]); act 0 none, 1 tanh, 2 relu, 3 sigmoid.
  * splits > 1: split-K with atomic accumulation into C (C must be initialised; bias/act not allowed). */

@@ -27,7 +27,6 @@ SIGNATURES = {
     "umpr_gather_pack_tc": [P, P, P, P, I, I, I, I, P, P],
     "umpr_gru_fwd_tc": [P, I, P, I, P, I, P],
     "umpr_gru_bwd_tc": [P, I, P, P, I, P, P, I, P],
-    "umpr_gru_wgrad_tc2": [P, P, P, P, I, I, I, I, P, I, P],
     "umpr_sgemm": [P, L, L, P, L, L, P, L, I, I, I, I, I, P, I, P],
     "umpr_tc_gemm_nt": [P, L, P, L, P, L, I, I, I, I, P, I, I, P],
     "umpr_gru_inproj_tc": [P, P, I, I, I, P, I, P],

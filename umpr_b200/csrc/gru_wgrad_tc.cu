@@ -184,156 +184,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float
   if (warp == 8) tmem_dealloc(tmem, 256);
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc2_kernel(const float* __restrict__ dG, const float* __restrict__ xp,
-                                                                     const float* __restrict__ out, Plan p, int L, int E, int slots_per_cta,
-                                                                     float* __restrict__ dw_ih_f, float* __restrict__ dw_hh_f,
-                                                                     float* __restrict__ db_ih_f, float* __restrict__ db_hh_f,
-                                                                     float* __restrict__ dw_ih_b, float* __restrict__ dw_hh_b,
-                                                                     float* __restrict__ db_ih_b, float* __restrict__ db_hh_b) {
-  extern __shared__ unsigned char raw[];
-  __shared__ uint64_t full_bar[WT_NSTAGE], empty_bar[WT_NSTAGE], acc_bar;
-  __shared__ uint32_t tmem_slot;
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int dir = blockIdx.y, R = p.R;
-  const int n_flat = p.n_slabs * R;
-  const int f_beg = blockIdx.x * slots_per_cta, f_end = min(n_flat, f_beg + slots_per_cta);
-  const int n_steps = (f_end - f_beg + 63) / 64;
-
-  if (tid == 0) {
-    for (int s = 0; s < WT_NSTAGE; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&acc_bar, 1);
-    mbar_fence_init();
-  }
-  if (warp == 8) tmem_alloc(&tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-
-  if (warp < 8) {
-    // ------------------------------------------------------------------ loaders
-    for (int st = 0; st < n_steps; ++st) {
-      const int s = st % WT_NSTAGE;
-      unsigned char* sb = base + s * WT_STAGE;
-      const int f0 = f_beg + st * 64;
-      // B operand sources per thread (warp w, lane): slots k = i*8 + w (i = 0..7), elements lane*4..+3 of [xp | h_prev]
-      const int m = lane * 4;
-      const uint32_t off0 = mn_off(m, warp);
-      const float* xsrc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int f = f0 + i * 8 + warp;
-        xsrc[i] = nullptr;
-        if (f < f_end) {
-          const int sl = f / R, r = f - sl * R;
-          if (m < KP) {
-            xsrc[i] = xp + ((size_t)sl * R + r) * KP + m;
-          } else {
-            const int j = p.slab_tile[sl], t = sl - p.tile_off[j], kj = j * R + r;
-            const int rw = p.row_of[kj], tp = dir ? t + 1 : t - 1;
-            if (rw >= 0 && tp >= 0 && tp < p.len_of[kj]) xsrc[i] = out + ((size_t)rw * L + tp) * D + dir * H + (m - KP);
-          }
-        }
-      }
-      // all 24 loads of the stage are issued before anything is consumed (and before the stage buffer is even free): 96 KB in
-      // flight per CTA instead of 32 KB.  A operand: dGT is column-major inside the (slab, direction) tile -> for one gate, the
-      // stage's 64 token slots are 256 contiguous bytes: K-major SWIZZLE_128B tiles [128 gates][64 slots], top half (dr, dz)
-      // then bottom half (dn, dn*r)
-      const int sl0 = f0 / R, r0 = f0 - sl0 * R;
-      const float* gbase = dG + ((size_t)sl0 * 2 + dir) * SV * R + r0;
-      const int k4 = (tid & 15) * 4, g0 = tid >> 4;             // 16 lanes cover the 64 slots of a gate row; 16 gate rows per pass
-      float4 va[16], vb[8];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) va[i] = *reinterpret_cast<const float4*>(gbase + (size_t)(i * 16 + g0) * R + k4);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) vb[i] = xsrc[i] ? *reinterpret_cast<const float4*>(xsrc[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (st >= WT_NSTAGE) mbar_wait(&empty_bar[s], ((st / WT_NSTAGE) - 1) & 1);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        unsigned char* hi = sb + ((i >> 3) * 2) * WT_TILE, *lo = hi + WT_TILE;
-        store_split4(hi, lo, (i & 7) * 16 + g0, k4, va[i]);
-      }
-      {                                                       // B rows: [xp (64) | h_prev (64)]
-        unsigned char* hi = sb + 4 * WT_TILE + off0, *lo = hi + WT_TILE;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint32_t h0, l0, h1, l1;
-          split2(vb[i].x, vb[i].y, h0, l0);
-          split2(vb[i].z, vb[i].w, h1, l1);
-          *reinterpret_cast<uint2*>(hi + i * 1024) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(lo + i * 1024) = make_uint2(l0, l1);
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(&full_bar[s]);
-    }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 16);     // A (dGT) K-major, B ([xp | h_prev]) MN-major
-    for (int st = 0; st < n_steps; ++st) {
-      const int s = st % WT_NSTAGE;
-      mbar_wait(&full_bar[s], (st / WT_NSTAGE) & 1);
-      tc_fence_after();
-      const uint32_t sb = smem_u32(base + s * WT_STAGE);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t ko = kk * 2048;           // 16 slots = two 1024-byte atoms
-        const uint64_t bh = smem_desc_mn_sw128(sb + 4 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 5 * WT_TILE + ko);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t ah = smem_desc_sw128(sb + (half * 2) * WT_TILE) + (uint64_t)(kk * 2), al = smem_desc_sw128(sb + (half * 2 + 1) * WT_TILE) + (uint64_t)(kk * 2);
-          const uint32_t d = tmem + half * 128;
-          umma_bf16(d, ah, bh, idesc, (st | kk) != 0);
-          umma_bf16(d, ah, bl, idesc, 1);
-          umma_bf16(d, al, bh, idesc, 1);
-        }
-      }
-      umma_commit(&empty_bar[s]);
-    }
-    umma_commit(&acc_bar);
-  }
-  __syncwarp();
-  if (warp < 4 && n_steps > 0) {
-    // ------------------------------------------------------------------ epilogue: flush the two accumulator halves
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    float* dw_ih = dir ? dw_ih_b : dw_ih_f;
-    float* dw_hh = dir ? dw_hh_b : dw_hh_f;
-    float* db_ih = dir ? db_ih_b : db_ih_f;
-    float* db_hh = dir ? db_hh_b : db_hh_f;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      const int g = half * 128 + warp * 32 + lane;          // 0..255 : dr, dz, dn, dn*r
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + half * 128 + c0, v);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int col = c0 + c;
-          if (col < KP) {
-            if (g < G3) {
-              if (col < E) atomicAdd(&dw_ih[g * E + col], v[c]);
-              else if (col == E) { atomicAdd(&db_ih[g], v[c]); if (g < 2 * H) atomicAdd(&db_hh[g], v[c]); }
-            } else if (col == E) {
-              atomicAdd(&db_hh[g - H], v[c]);
-            }
-          } else {
-            const int hc = col - KP;
-            if (g < 2 * H) atomicAdd(&dw_hh[g * H + hc], v[c]);
-            else if (g >= G3) atomicAdd(&dw_hh[(g - H) * H + hc], v[c]);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 256);
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------------
 // Generic "TN" reduction GEMM on the tensor cores: C[M][N] += sum_k A[k][M]^T · B[k][N]   (M, N <= 128, K huge; both operands
 // row-major with the reduction index slowest = MN-major for tcgen05, converted fp32 -> bf16 hi/lo on the fly).
@@ -458,25 +308,6 @@ extern "C" int umpr_gru_wgrad_tc(const float* dG, const float* xp, const float* 
   gru_wgrad_tc_kernel<<<dim3(grid, 2), WT_THREADS, smem, (cudaStream_t)stream>>>(dG, xp, out, p, L, E, per, dw[0], dw[1], dw[2], dw[3], dw[4],
                                                                                 dw[5], dw[6], dw[7]);
   return check_launch("gru_wgrad_tc");
-}
-
-// umpr_gru_wgrad_tc for the tensor-core GRU's layout: dGT[n_slabs][2][256][128] (column-major inside a tile, umpr_gru_bwd_tc), R = 128
-extern "C" int umpr_gru_wgrad_tc2(const float* dGT, const float* xp, const float* out, const int32_t* plan, int n_tiles, int n_slabs,
-                                  int L, int E, float* const* dw, int n_ctas, void* stream) {
-  if (n_slabs == 0) return 0;
-  const int R = 128;
-  Plan p = make_plan(plan, n_tiles, n_slabs, R);
-  const int n_flat = n_slabs * R;
-  if (n_ctas < 2) n_ctas = 2;
-  int per = (n_flat + n_ctas / 2 - 1) / (n_ctas / 2);
-  per = ((per + 63) / 64) * 64;
-  const int grid = (n_flat + per - 1) / per;
-  const int smem = WT_NSTAGE * WT_STAGE + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gru_wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) { set_error("gru_wgrad_tc2 smem: %s", cudaGetErrorString(e)); return (int)e; }
-  gru_wgrad_tc2_kernel<<<dim3(grid, 2), WT_THREADS, smem, (cudaStream_t)stream>>>(dGT, xp, out, p, L, E, per, dw[0], dw[1], dw[2], dw[3], dw[4],
-                                                                                 dw[5], dw[6], dw[7]);
-  return check_launch("gru_wgrad_tc2");
 }
 
 // C[M][N] (+=) sum_k A[k*lda + m] * B[k*ldb + n]: tensor-core reduction over a huge K (M, N <= 128, multiples of 4; 16-byte aligned rows)
