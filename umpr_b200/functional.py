@@ -22,6 +22,25 @@ TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
 TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
+DIRECT_GRAD_ACCUM = False      # set by train.FlatTrainer for the duration of its backward pass (see _sinks)
+
+
+def _sinks(params):
+    """Destinations of parameter gradients that the kernels ACCUMULATE (+=) → (buffers to hand to the kernels, tensors to return
+    to autograd).  Under train.FlatTrainer every parameter's ``.grad`` is a view into the flat gradient bucket (zeroed each step), so
+    the kernels add straight into it and autograd gets ``None``: no temporary, no zero-fill kernel, no AccumulateGrad add kernel per
+    parameter.  Anywhere else (``torch.autograd.grad``, plain ``backward`` on a fresh model) fresh zeroed buffers are returned."""
+    if DIRECT_GRAD_ACCUM and all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.shape == p.shape
+                                 for p in params):
+        return [p.grad for p in params], [None] * len(params)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    out, o = [], 0
+    for p in params:
+        out.append(flat[o:o + p.numel()].view(p.shape))
+        o += p.numel()
+    return out, out
+
+
 def _f32(t):
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
@@ -138,6 +157,7 @@ class _GruTcFn(Function):
 
     @staticmethod
     def forward(ctx, plans, xps, xqs, E, want_hidden, *w):
+        ctx.params = w
         w = [_f32(t) for t in w]
         dev = xqs[0].device
         n = len(plans)
@@ -179,11 +199,7 @@ class _GruTcFn(Function):
         saved = ctx.saved_tensors
         xqs, hqs, svs, w = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], list(saved[3 * n:])
         dev = xqs[0].device
-        flat = torch.zeros(sum(t.numel() for t in w), dtype=torch.float32, device=dev)
-        grads, o = [], 0
-        for t in w:
-            grads.append(flat[o:o + t.numel()].view_as(t))
-            o += t.numel()
+        grads, rets = _sinks(ctx.params)
         segs = (_lib.GruBwdSeg * n)()
         keep, tokens = [], 0
         for i, plan in enumerate(plans):
@@ -197,7 +213,7 @@ class _GruTcFn(Function):
         # one reverse-time launch over every side (same tile queues as the forward): recurrence + all eight weight gradients
         call("umpr_gru_bwd_tc", C.addressof(segs), n, ptr_array(w), ptr_array(grads), E, ptr(_zero_image(dev)), ptr(ctx.sched), ctx.nq,
              work=(2.0 * tokens * 2 * H * 3 * H + 2.0 * tokens * 2 * 3 * H * (E + H), 0.0))
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, *rets)
 
 
 _ZERO_IMG = {}
@@ -265,6 +281,7 @@ def _splits_for(K, device):
 class _CoAttnFn(Function):
     @staticmethod
     def forward(ctx, gu, gi, M):
+        ctx.params = (M,)
         gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
         B, P, _ = gu.shape
         dev = gu.device
@@ -302,12 +319,12 @@ class _CoAttnFn(Function):
              work=(0.0, 6.0 * B * P * D * 4))
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
         sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
-        dM = torch.zeros_like(M)
+        (dM,), (rM,) = _sinks(ctx.params)
         if B * P >= 4096:      # reduction over every token of the batch: tensor cores, both operands token-major
             call("umpr_tc_gemm_tn", ptr(gi), D, ptr(dgiM), D, ptr(dM), D, D, D, B * P, _n_ctas(dev), work=(2.0 * D * D * B * P, 0.0))
         else:
             sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
-        return dgu, dgi, dM
+        return dgu, dgi, rM
 
 
 def co_attention(gu, gi, M):
@@ -321,6 +338,7 @@ def co_attention(gu, gi, M):
 class _SNetFn(Function):
     @staticmethod
     def forward(ctx, gru_repr, word_soft, sent_length, Ms, Ws):
+        ctx.params = (Ms, Ws)
         x = _f32(_chk(gru_repr, "gru_repr"))
         Ms, Ws = _f32(Ms), _f32(Ws)
         word_soft = _f32(word_soft)
@@ -358,12 +376,11 @@ class _SNetFn(Function):
         call("umpr_snet_sentiment_bwd", ptr(self_atte), ptr(wsum), ptr(None if d_sentiment is None else _f32(d_sentiment)),
              ptr(None if d_self_atte is None else _f32(d_self_atte)), B, S, ptr(d_sa), ptr(d_wsum))
         dx = torch.empty_like(x)
-        dW = torch.zeros(ATT * D + ATT, dtype=torch.float32, device=dev)
-        dMs, dWs = dW[:ATT * D].view(ATT, D), dW[ATT * D:].view(1, ATT)
+        (dMs, dWs), (rMs, rWs) = _sinks(ctx.params)
         call("umpr_snet_bwd", ptr(x), ptr(th), ptr(soft), ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev),
              work=(4.0 * N * L * D * ATT, N * L * 4.0 * (2 * D + ATT)))
         d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
-        return dx, d_word_soft, None, dMs, dWs
+        return dx, d_word_soft, None, rMs, rWs
 
 
 def s_net(gru_repr, word_soft, sent_length, Ms, Ws):
@@ -377,6 +394,7 @@ def s_net(gru_repr, word_soft, sent_length, Ms, Ws):
 class _TextMatchFn(Function):
     @staticmethod
     def forward(ctx, atte_u, senti_u, atte_i, senti_i, Wu, Wi):
+        ctx.params = (Wu, Wi)
         ins = [_f32(t) for t in (atte_u, senti_u, atte_i, senti_i)]
         Wu, Wi = _f32(Wu), _f32(Wi)
         B = ins[0].shape[0]
@@ -396,14 +414,14 @@ class _TextMatchFn(Function):
         dpre = torch.empty_like(y)
         call("umpr_tanh_bwd", ptr(y), ptr(_f32(dy)), y.numel(), ptr(dpre))
         dins = torch.empty(4, B, D, dtype=torch.float32, device=dev)
-        dW = torch.zeros(2, D, 2 * D, dtype=torch.float32, device=dev)
+        dW, rW = _sinks(ctx.params)
         sp = _splits_for(B, dev)
         for j, (x, W, wi, off) in enumerate(((a_u, Wu, 0, 0), (s_u, Wu, 0, D), (a_i, Wi, 1, 0), (s_i, Wi, 1, D))):
             # d in_j = dpre · W[:, half]        (B(k,n) = W[k][off+n])
             sgemm(dpre, (D, 1), W.data_ptr() + 4 * off, (2 * D, 1), dins[j], D, B, D, D)
             # dW[:, half] = dpre^T · in_j       (A(m,k) = dpre[k][m])
             sgemm(dpre, (1, D), x, (D, 1), dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, splits=sp, accumulate=True)
-        return dins[0], dins[1], dins[2], dins[3], dW[0], dW[1]
+        return dins[0], dins[1], dins[2], dins[3], rW[0], rW[1]
 
 
 def text_match(atte_u, senti_u, atte_i, senti_i, Wu, Wi):
@@ -416,6 +434,7 @@ def text_match(atte_u, senti_u, atte_i, senti_i, Wu, Wi):
 class _CNetTailFn(Function):
     @staticmethod
     def forward(ctx, gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
+        ctx.params = (conv_w, conv_b, lin_w, lin_b)
         x = _f32(_chk(gru_repr, "gru_repr"))
         conv_w, conv_b, lin_w, lin_b = _f32(conv_w), _f32(conv_b), _f32(lin_w), _f32(lin_b)
         B = x.shape[0]
@@ -453,19 +472,14 @@ class _CNetTailFn(Function):
         N = B * S
         dev = x.device
         dcfeat = torch.empty(N, KC, dtype=torch.float32, device=dev)
-        flat = torch.zeros(conv_w.numel() + KC + V * KC + V, dtype=torch.float32, device=dev)
-        o = 0
-        d_conv_w = flat[o:o + conv_w.numel()].view_as(conv_w); o += conv_w.numel()
-        d_conv_b = flat[o:o + KC]; o += KC
-        d_lin_w = flat[o:o + V * KC].view(V, KC); o += V * KC
-        d_lin_b = flat[o:o + V]
+        (d_conv_w, d_conv_b, d_lin_w, d_lin_b), rets = _sinks(ctx.params)
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
         dx = torch.empty_like(x)
         wt = torch.empty(KC * 3 * D, dtype=torch.float32, device=dev)
         call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
              work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
-        return dx, None, None, d_conv_w, d_conv_b, d_lin_w, d_lin_b, None
+        return dx, None, None, rets[0], rets[1], rets[2], rets[3], None
 
 
 def c_net_tail(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
@@ -479,6 +493,7 @@ def c_net_tail(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, 
 class _ControlTailFn(Function):
     @staticmethod
     def forward(ctx, s, view_p, c_out, ss_w, ss_b, eps):
+        ctx.params = (ss_w, ss_b)
         s, view_p, c_out, ss_w, ss_b = (_f32(t) for t in (s, view_p, c_out, ss_w, ss_b))
         B, Su, _ = s.shape
         V = view_p.shape[-1]
@@ -502,10 +517,10 @@ class _ControlTailFn(Function):
         d_s = torch.empty_like(s)
         d_vp = torch.empty_like(view_p)
         d_co = torch.empty_like(c_out)
-        dW = torch.zeros(D + 1, dtype=torch.float32, device=dev)
+        (dw_, db_), (rw_, rb_) = _sinks(ctx.params)
         call("umpr_control_tail_bwd", ptr(s), ptr(view_p), ptr(c_out), ptr(ss_w), ptr(senti), ptr(out[0]), ptr(z(d_pp)), ptr(z(d_pn)),
-             ctx.eps, B, Su, V, ptr(d_s), ptr(d_vp), ptr(d_co), ptr(dW[:D]), ptr(dW[D:]))
-        return d_s, d_vp, d_co, dW[:D].view(1, D), dW[D:], None
+             ctx.eps, B, Su, V, ptr(d_s), ptr(d_vp), ptr(d_co), ptr(dw_), ptr(db_))
+        return d_s, d_vp, d_co, rw_, rb_, None
 
 
 def control_tail(s, view_p, c_out, ss_w, ss_b, eps):
@@ -519,6 +534,7 @@ def control_tail(s, view_p, c_out, ss_w, ss_b, eps):
 class _VisualFn(Function):
     @staticmethod
     def forward(ctx, feat, c_u, c_i, pos_e, neg_e, w, b):
+        ctx.params = (w, b)
         feat, c_u, c_i, pos_e, neg_e, w, b = (_f32(t) for t in (feat, c_u, c_i, pos_e, neg_e, w, b))
         _chk(feat, "photo features")
         B, V, Pc, Fd = feat.shape
@@ -540,11 +556,11 @@ class _VisualFn(Function):
         scratch = torch.empty(3 * B * V, dtype=torch.float32, device=dev)
         d_c = torch.empty(2, B, V, dtype=torch.float32, device=dev)
         d_e = torch.empty(2, V, Fd, dtype=torch.float32, device=dev)
-        dW = torch.zeros(Fd + 1, dtype=torch.float32, device=dev)
+        (dw_, db_), (rw_, rb_) = _sinks(ctx.params)
         call("umpr_visual_bwd", ptr(feat), ptr(pos_e), ptr(neg_e), ptr(w), ptr(emb), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(c_u),
              ptr(c_i), ptr(c(d_pm)), ptr(c(d_nm)), ptr(c(d_fp)), ptr(c(d_fn)), B, V, Pc, Fd, ptr(scratch), ptr(d_c[0]), ptr(d_c[1]),
-             ptr(d_e[0]), ptr(d_e[1]), ptr(dW[:Fd]), ptr(dW[Fd:]))
-        return None, d_c[0], d_c[1], d_e[0], d_e[1], dW[:Fd].view(1, Fd), dW[Fd:]
+             ptr(d_e[0]), ptr(d_e[1]), ptr(dw_), ptr(db_))
+        return None, d_c[0], d_c[1], d_e[0], d_e[1], rw_, rb_
 
 
 def visual_tail(feat, c_u, c_i, pos_e, neg_e, w, b):
@@ -558,6 +574,7 @@ def visual_tail(feat, c_u, c_i, pos_e, neg_e, w, b):
 class _FusionFn(Function):
     @staticmethod
     def forward(ctx, repr_, fpos, fneg, w, b):
+        ctx.params = (w, b)
         repr_, w, b = _f32(_chk(repr_, "review_net_repr")), _f32(w), _f32(b)
         fpos = None if fpos is None else _f32(fpos)
         fneg = None if fneg is None else _f32(fneg)
@@ -577,10 +594,10 @@ class _FusionFn(Function):
         dev = repr_.device
         d_repr = torch.empty_like(repr_)
         d_f = torch.empty(2, B, V, dtype=torch.float32, device=dev) if V else None
-        dW = torch.zeros(w.numel() + 1, dtype=torch.float32, device=dev)
+        (dw_, db_), (rw_, rb_) = _sinks(ctx.params)
         call("umpr_fusion_bwd", ptr(repr_), ptr(fpos), ptr(fneg), ptr(w), ptr(pred), ptr(_f32(d_pred)), B, V, ptr(d_repr),
-             ptr(d_f[0]) if V else None, ptr(d_f[1]) if V else None, ptr(dW[:-1]), ptr(dW[-1:]))
-        return d_repr, (d_f[0] if V else None), (d_f[1] if V else None), dW[:-1].view_as(w), dW[-1:]
+             ptr(d_f[0]) if V else None, ptr(d_f[1]) if V else None, ptr(dw_), ptr(db_))
+        return d_repr, (d_f[0] if V else None), (d_f[1] if V else None), rw_, rb_
 
 
 def fusion(repr_, fpos, fneg, w, b):

@@ -70,10 +70,15 @@ class FlatTrainer:
 
     def train_step(self, batch):
         """main.py:32-37 on this rank's shard.  Returns (prediction, loss) of the shard."""
+        from . import functional as F
         self.model.train()
         self.zero_grad()
         pred, loss = self.model(*batch)
-        loss.mean().backward()
+        F.DIRECT_GRAD_ACCUM = True          # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
+        try:
+            loss.mean().backward()
+        finally:
+            F.DIRECT_GRAD_ACCUM = False
         self.reduce_gradients()
         self.optimizer_step()
         return pred, loss
