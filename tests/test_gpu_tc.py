@@ -178,3 +178,26 @@ def test_tc_gemm_tn_reduction(M, N, K, ctas):
     assert_close(C[:, :N], ref, 2e-5, "tc_gemm_tn")
     if ldc > N:
         assert torch.equal(C[:, N:], C0[:, N:])
+
+
+@pytest.mark.parametrize("B,S,L,KC", [(128, 16, 20, 120), (9, 3, 11, 100)])
+def test_cnet_tail_tensor_core_conv_matches_cuda_core_conv(B, S, L, KC):
+    """C-Net tail (conv + ReLU + max-pool + view head, model.py:105-125) with the tcgen05 implicit-GEMM convolution against the
+    fp32 CUDA-core convolution: same pooled features and the same gradients (the arg-max routing must not differ)."""
+    from umpr_b200 import functional as F
+    torch.manual_seed(B + L)
+    x0 = torch.randn(B, S * L, 128, device=DEV) * 0.5
+    p0 = [torch.randn(KC, 128, 3, device=DEV) * 0.05, torch.randn(KC, device=DEV) * 0.1,
+          torch.randn(4, KC, device=DEV) * 0.1, torch.randn(4, device=DEV) * 0.1]
+    gv, gf = torch.randn(B, S, 4, device=DEV), torch.randn(B, 4, device=DEV)
+    res = []
+    for flag in (False, True):
+        F.TENSOR_CORE_CONV = flag
+        x = x0.clone().requires_grad_(True)
+        p = [t.clone().requires_grad_(True) for t in p0]
+        view_p, final = F.c_net_tail(x, S, L, *p, 0.35)
+        ((view_p * gv).sum() + (final * gf).sum()).backward()
+        res.append([view_p.detach(), final.detach(), x.grad] + [t.grad for t in p])
+    F.TENSOR_CORE_CONV = True
+    for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
+        assert_close(a, b, 2e-5, nm)

@@ -19,6 +19,7 @@ H, D, ATT, KP, SV = 64, 128, 64, 64, 256
 TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
+TENSOR_CORE_GEMM = True        # tcgen05 3xBF16 dense products (gemm_tc.cu); False = fp32 CUDA-core kernel everywhere
 TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
@@ -254,7 +255,7 @@ def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=F
     pc = C if isinstance(C, int) else ptr(C)
     work = (2.0 * M * N * K, 0.0)
     aligned = not ((pa | pb | pc) & 15) and a_strides[1] == 1 and not (a_strides[0] & 3) and not (ldc & 3)
-    if aligned and splits == 1 and act in (0, 1, 2) and M >= 64:
+    if TENSOR_CORE_GEMM and aligned and splits == 1 and act in (0, 1, 2) and M >= 64:
         b_kn = -1
         if b_strides[0] == 1 and not (b_strides[1] & 3):          # B[N][K]
             b_kn, ldb = 0, b_strides[1]
