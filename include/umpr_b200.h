@@ -140,6 +140,15 @@ int umpr_snet_sentiment_bwd(const float* self_atte, const float* wsum, const flo
 int umpr_snet_bwd(const float* x, const float* th, const float* soft, const float* d_self_atte, const float* Ms, const float* Ws, int N,
                   int L, float* dx /*(N,L,128) written*/, float* dMs /*(+=)*/, float* dWs /*(+=)*/, int n_ctas, void* stream);
 
+/* Tensor-core S-Net for inputs produced by ImprovedRnn (rows at or beyond a sentence's length are exactly zero, model.py:20): only the
+ * valid rows are multiplied.  table = [tile_sent_off (n_tiles+1) | cstart (N+1)] (int32, device): sentences tile_sent_off[k] ..
+ * tile_sent_off[k+1]-1 form tile k (<= 128 valid rows), cstart = exclusive prefix sum of the per-sentence lengths.  The backward
+ * recomputes the scores from x (nothing else is saved) and writes dx only for the valid rows. */
+int umpr_snet_fwd_tc(const float* x, const int32_t* table, int n_tiles, const float* Ms, const float* Ws, int N, int L,
+                     float* self_atte /*(N,128)*/, int n_ctas, void* stream);
+int umpr_snet_bwd_tc(const float* x, const int32_t* table, int n_tiles, const float* d_self_atte, const float* Ms, const float* Ws, int N,
+                     int L, float* dx /*(N,L,128): valid rows written*/, float* dMs /*(+=)*/, float* dWs /*(+=)*/, int n_ctas, void* stream);
+
 /* ---- CNet tail: src/model.py:118-125 ---- */
 int umpr_cnet_prep(const float* conv_w /*(KC,128,3)*/, int KC, int ksize, float* wt /*(384,128)*/, void* stream);
 int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int N, int L, int KC, float* cfeat /*(N,KC)*/,

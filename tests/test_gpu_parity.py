@@ -244,42 +244,45 @@ def test_two_shard_step_matches_chunked_oracle():
             assert_close(p.detach(), tp[k].detach(), 2e-5, "adam " + k)
 
 
-# Tensors whose value is a heavily cancelled sum over every token of the batch.  grad(r_net.M) = sum_tokens gi^T d(gi M): its
-# max-norm is ~1e-4 of the sum of the magnitudes of its terms (1e-4 absolute with M scaled down, 1e-7 at the reference's own
-# initialisation where tanh saturates), so the ~1e-5 element error of the 3xBF16 tensor-core GRU outputs it is built from shows
-# up 30-100x amplified.  Measured 3.6e-4 / 8.0e-4 / 1.3e-3 on the three cases below (fp32 GRU path: 2e-5; the TN reduction
-# itself runs with fp32-equivalent operands, see gru_wgrad_tc.cu).  This is the one tensor outside the 1e-4 bar; DESIGN.md
-# section 5 records it as a known deviation.
-CONDITIONED = {"review_net.r_net.M": 2e-3}
-
-
-@pytest.mark.parametrize("workload,batch,m_scale", [("music_full", 128, 1.0), ("music_full", 128, 0.05), ("yelp_full", 112, 0.05)])
-def test_full_model_on_the_tensor_core_path_vs_oracle(workload, batch, m_scale):
+@pytest.mark.parametrize("workload,batch,m_scale,seed", [("music_full", 128, 1.0, 5), ("music_full", 128, 0.05, 5),
+                                                         ("yelp_full", 112, 0.05, 5), ("yelp_full", 120, 0.05, 7), ("music_full", 112, 0.05, 5)])
+def test_full_model_on_the_tensor_core_path_vs_oracle(workload, batch, m_scale, seed):
     """A batch large enough (B*S >= 2048 sentences) that every tensor-core kernel is on the path - fused tcgen05 GRU forward and
-    backward with all sides in one launch, tcgen05 co-attention, TN reduction GEMM, sweep conv backward - against the CPU oracle:
-    prediction, loss and every parameter gradient within the 1e-4 bar, at the reference's own initialisation (m_scale 1: tanh
-    saturated, arg-max gradients ~0) and with M scaled down so that the co-attention gradients are exercised."""
+    backward with all sides in one launch, tcgen05 co-attention and S-Net, TN reduction GEMM, sweep conv backward - against the CPU
+    oracle: prediction, loss and every parameter gradient within the 1e-4 bar, at the reference's own initialisation (m_scale 1:
+    tanh saturated, arg-max gradients ~0) and with M scaled down so that the co-attention gradients are exercised.
+
+    A batch of this size holds ~1e5 co-attention maxima and ~1e6 max-pool maxima; a handful are tied to within the last bits, so
+    two fp32 implementations route those gradients to different (equally maximal) positions and disagree by up to 1e-2 on grad(M)
+    and the conv weights - whatever their precision.  The oracle therefore back-propagates through the positions OUR kernels
+    chose (oracle.routed) and the test asserts separately that every chosen position is a maximum to within 2e-5 of the value
+    range."""
+    from umpr_b200 import functional as F
     from umpr_b200 import synthetic as syn
     from umpr_b200.plan import TC_MIN_SEQS
     table = syn.make_table(3000, seed=2)
-    batch_t = syn.make_batch(workload, batch, vocab=3000, seed=5)
+    batch_t = syn.make_batch(workload, batch, vocab=3000, seed=seed)
     assert batch_t[3].numel() >= TC_MIN_SEQS
     model = syn.build_model(workload, table, seed=1, device=DEV)
     with torch.no_grad():
         model.review_net.r_net.M.mul_(m_scale)
     model.train()
-    pred, loss = model(*batch_t)
+    F.ROUTING_LOG = []
+    try:
+        pred, loss = model(*batch_t)
+        log = F.ROUTING_LOG
+    finally:
+        F.ROUTING_LOG = None
     loss.backward()
+    picks = {"coattn": [(a[0].cpu(), a[1].cpu()) for k, a in log if k == "coattn"], "cnet": [a.cpu() for k, a in log if k == "cnet"]}
+    assert len(picks["coattn"]) == 1 and len(picks["cnet"]) == 3
     params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     rno = syn.WORKLOADS[workload]["review_net_only"]
-    p_ref, l_ref, g_ref = orc.umpr_loss_and_grads(params, batch_t, review_net_only=rno, impl="lib")
+    with orc.routed(picks) as r:
+        p_ref, l_ref, g_ref = orc.umpr_loss_and_grads(params, batch_t, review_net_only=rno, impl="lib")
+    assert r.margin["coattn"] <= 2e-5 and r.margin["cnet"] <= 2e-5, r.margin     # our winners ARE maxima (to the element error)
     assert_close(pred, p_ref, TOL, "prediction")
     assert_close(loss, l_ref, TOL, "loss")
     for k, p in model.named_parameters():
-        if not p.requires_grad:
-            continue
-        got = p.grad if p.grad is not None else torch.zeros_like(p)
-        if k in CONDITIONED and float(g_ref[k].abs().max()) >= 1e-7:
-            assert_close(got, g_ref[k], CONDITIONED[k], "grad " + k)
-        else:
-            _check_grad(k, got, g_ref[k])
+        if p.requires_grad:
+            _check_grad(k, p.grad if p.grad is not None else torch.zeros_like(p), g_ref[k])

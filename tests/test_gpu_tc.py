@@ -201,3 +201,61 @@ def test_cnet_tail_tensor_core_conv_matches_cuda_core_conv(B, S, L, KC):
     F.TENSOR_CORE_CONV = True
     for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
         assert_close(a, b, 2e-5, nm)
+
+
+@pytest.mark.parametrize("B,S,L,short", [(1024, 20, 20, False), (128, 20, 20, False), (300, 5, 20, True), (40, 3, 128, False), (64, 4, 100, True), (7, 2, 1, False)])
+def test_snet_tensor_core_matches_cuda_core_path(B, S, L, short):
+    """S-Net (model.py:71-81) on tcgen05 over the valid positions only against the fp32 kernel over all positions: same outputs,
+    same parameter gradients, same input gradient on every position below a sentence's length (the others are never read)."""
+    from umpr_b200 import functional as F
+    from umpr_b200.plan import PackPlan
+    torch.manual_seed(B + S + L)
+    N = B * S
+    lens = torch.randint(1, (min(4, L) if short else L) + 1, (N,))
+    if short:
+        lens[::7] = L
+    plan = PackPlan(lens, L, DEV, tile_rows=128)
+    eff = plan.row_lengths().to(DEV)                                  # length of the sequence each OUTPUT row holds
+    mask = (torch.arange(L, device=DEV)[None, :] < eff[:, None]).view(B, S * L, 1)
+    x0 = torch.randn(B, S * L, 128, device=DEV) * 0.5 * mask
+    ws0 = torch.softmax(torch.randn(B, S * L, device=DEV), dim=1).view(B, S, L)
+    p0 = [torch.randn(64, 128, device=DEV) * 0.1, torch.randn(1, 64, device=DEV)]
+    g_sa, g_se = torch.randn(B, S, 128, device=DEV), torch.randn(B, 128, device=DEV)
+    res = []
+    for pl in (None, plan):
+        x, ws = x0.clone().requires_grad_(True), ws0.clone().requires_grad_(True)
+        p = [t.clone().requires_grad_(True) for t in p0]
+        sa, se = F.s_net(x, ws, L, *p, plan=pl)
+        ((sa * g_sa).sum() + (se * g_se).sum()).backward()
+        res.append([sa.detach(), se.detach(), torch.where(mask, x.grad, torch.zeros_like(x.grad)), ws.grad, p[0].grad, p[1].grad])
+    assert plan.snet_table()[1] <= (int(lens.sum()) + 128 - L) // (129 - L) + 1
+    for a, b, nm in zip(res[1], res[0], ["self_atte", "sentiment", "dx", "d word_soft", "dMs", "dWs"]):
+        assert_close(a, b, 5e-5, nm)
+
+
+@pytest.mark.parametrize("B,S,L,KC,V", [(112, 20, 20, 120, 4), (128, 20, 20, 120, 1), (37, 5, 20, 120, 4), (9, 3, 11, 100, 2)])
+def test_cnet_tail_vs_fp64_torch(B, S, L, KC, V):
+    """C-Net tail (model.py:118-125) forward and backward against the same ops written with torch in fp64 (conv1d, ReLU, max over
+    positions, Linear+Sigmoid, threshold, sum of squares)."""
+    from umpr_b200 import functional as F
+    torch.manual_seed(B * 7 + V)
+    x0 = torch.randn(B, S * L, 128, device=DEV) * 0.5
+    p0 = [torch.randn(KC, 128, 3, device=DEV) * 0.05, torch.randn(KC, device=DEV) * 0.1,
+          torch.randn(V, KC, device=DEV) * 0.1, torch.randn(V, device=DEV) * 0.1]
+    gv, gf = torch.randn(B, S, V, device=DEV), torch.randn(B, V, device=DEV)
+    x = x0.clone().requires_grad_(True)
+    p = [t.clone().requires_grad_(True) for t in p0]
+    view_p, final = F.c_net_tail(x, S, L, *p, 0.35)
+    ((view_p * gv).sum() + (final * gf).sum()).backward()
+    got = [view_p.detach(), final.detach(), x.grad] + [t.grad for t in p]
+    xd = x0.double().requires_grad_(True)
+    pd = [t.double().requires_grad_(True) for t in p0]
+    conv = torch.relu(torch.nn.functional.conv1d(xd.view(B * S, L, 128).transpose(-1, -2), pd[0], pd[1], padding=1))
+    feat = conv.max(dim=-1)[0].reshape(B, S, -1)
+    vp = torch.sigmoid(feat @ pd[2].t() + pd[3])
+    vp = torch.where(vp < 0.35, torch.zeros_like(vp), vp)
+    fin = (vp ** 2).sum(-2)
+    ((vp * gv.double()).sum() + (fin * gf.double()).sum()).backward()
+    ref = [vp.detach(), fin.detach(), xd.grad] + [t.grad for t in pd]
+    for a, b, nm in zip(got, ref, ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
+        assert_close(a, b.float(), 3e-5, nm)

@@ -107,3 +107,18 @@ def test_plan_prefetcher_prepares_the_same_plans_off_thread():
             assert got.L == ids.shape[2] and got.N == lens.numel() and got.R == ref.R
             assert torch.equal(got.host, ref.host) and torch.equal(got.sorted_indices, ref.sorted_indices)
             assert got.ensure_uploaded().buf is not None
+
+
+@pytest.mark.parametrize("L", [1, 20, 100, 128])
+def test_snet_tile_table_covers_every_sentence_with_at_most_128_rows(L):
+    rs = np.random.RandomState(L)
+    lens = torch.from_numpy(rs.randint(1, L + 1, size=3000))
+    p = PackPlan(lens, L, "cpu", tile_rows=128)
+    tab, nt = p._snet_host()
+    tso, cst = tab[:nt + 1], tab[nt + 1:]
+    assert cst.size == p.N + 1 and tso[0] == 0 and tso[-1] == p.N and (np.diff(tso) >= 1).all()
+    assert np.array_equal(np.diff(cst), p.row_lengths().numpy())            # per OUTPUT row, in output order
+    rows = cst[tso[1:]] - cst[tso[:-1]]
+    assert rows.max() <= 128 and int(rows.sum()) == p.tokens
+    if L <= 20:
+        assert rows[:-1].min() >= 129 - 2 * L                                # tiles are filled to within two sentences

@@ -39,6 +39,8 @@ SIGNATURES = {
     "umpr_snet_sentiment_fwd": [P, P, I, I, I, P, P, P],
     "umpr_snet_sentiment_bwd": [P, P, P, P, I, I, P, P, P],
     "umpr_snet_bwd": [P, P, P, P, P, P, I, I, P, P, P, I, P],
+    "umpr_snet_fwd_tc": [P, P, I, P, P, I, I, P, I, P],
+    "umpr_snet_bwd_tc": [P, P, I, P, P, P, I, I, P, P, P, I, P],
     "umpr_cnet_prep": [P, I, I, P, P],
     "umpr_cnet_conv_fwd": [P, P, P, I, I, I, P, P, I, P],
     "umpr_cnet_conv_fwd_tc": [P, P, P, I, I, I, I, P, I, P, P, I, P],

@@ -190,24 +190,9 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float
 // Used for dM = gi^T · dgiM of the co-attention backward (model.py:50; K = B*P).  Persistent CTAs own contiguous K ranges,
 // accumulate in TMEM and flush once with atomics.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int TN_STAGE = 6 * WT_TILE;            // A hi/mid/lo, B hi/mid/lo (64 k x 128 elements each)
-constexpr int TN_NSTAGE = 2;
+constexpr int TN_STAGE = 4 * WT_TILE;            // A hi/lo, B hi/lo (64 k x 128 elements each)
+constexpr int TN_NSTAGE = 3;
 
-// fp32 pair -> three bf16 pairs (hi, mid, lo): 24 mantissa bits, i.e. the fp32 value exactly
-__device__ __forceinline__ void split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float a1 = a - __uint_as_float(hi << 16), b1 = b - __uint_as_float(hi & 0xffff0000u);
-  const __nv_bfloat162 m = __floats2bfloat162_rn(a1, b1);
-  mid = *reinterpret_cast<const uint32_t*>(&m);
-  const float a2 = a1 - __uint_as_float(mid << 16), b2 = b1 - __uint_as_float(mid & 0xffff0000u);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a2, b2);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-// This reduction runs over every token of the batch and its result (dM) is small against the sum of the magnitudes of its terms,
-// so the usual 3xBF16 operands (16 mantissa bits) are not enough: operands are split three ways and the six products that matter
-// (hh, hm, mh, mm, hl, lh) are issued - fp32-equivalent operands, fp32 accumulation in TMEM.
 __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* __restrict__ A, long lda, const float* __restrict__ B, long ldb,
                                                                    float* __restrict__ C, long ldc, int M, int N, long K, long k_per_cta) {
   extern __shared__ unsigned char raw[];
@@ -249,17 +234,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
       unsigned char* sb = base + s * TN_STAGE + off0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        uint32_t h0, m0, l0, h1, m1, l1;
-        split3(va[i].x, va[i].y, h0, m0, l0);
-        split3(va[i].z, va[i].w, h1, m1, l1);
+        uint32_t h0, l0, h1, l1;
+        split2(va[i].x, va[i].y, h0, l0);
+        split2(va[i].z, va[i].w, h1, l1);
         *reinterpret_cast<uint2*>(sb + i * 1024) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(sb + WT_TILE + i * 1024) = make_uint2(m0, m1);
-        *reinterpret_cast<uint2*>(sb + 2 * WT_TILE + i * 1024) = make_uint2(l0, l1);
-        split3(vb[i].x, vb[i].y, h0, m0, l0);
-        split3(vb[i].z, vb[i].w, h1, m1, l1);
-        *reinterpret_cast<uint2*>(sb + 3 * WT_TILE + i * 1024) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(sb + 4 * WT_TILE + i * 1024) = make_uint2(m0, m1);
-        *reinterpret_cast<uint2*>(sb + 5 * WT_TILE + i * 1024) = make_uint2(l0, l1);
+        *reinterpret_cast<uint2*>(sb + WT_TILE + i * 1024) = make_uint2(l0, l1);
+        split2(vb[i].x, vb[i].y, h0, l0);
+        split2(vb[i].z, vb[i].w, h1, l1);
+        *reinterpret_cast<uint2*>(sb + 2 * WT_TILE + i * 1024) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(sb + 3 * WT_TILE + i * 1024) = make_uint2(l0, l1);
       }
       fence_async_smem();
       mbar_arrive(&full_bar[s]);
@@ -274,14 +257,11 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const uint32_t ko = kk * 2048;           // 16 k = two 1024-byte atoms
-        const uint64_t ah = smem_desc_mn_sw128(sb + ko), am = smem_desc_mn_sw128(sb + WT_TILE + ko), al = smem_desc_mn_sw128(sb + 2 * WT_TILE + ko);
-        const uint64_t bh = smem_desc_mn_sw128(sb + 3 * WT_TILE + ko), bm = smem_desc_mn_sw128(sb + 4 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 5 * WT_TILE + ko);
-        umma_bf16(tmem, al, bh, idesc, (st | kk) != 0);       // smallest terms first
+        const uint64_t ah = smem_desc_mn_sw128(sb + ko), al = smem_desc_mn_sw128(sb + WT_TILE + ko);
+        const uint64_t bh = smem_desc_mn_sw128(sb + 2 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 3 * WT_TILE + ko);
+        umma_bf16(tmem, ah, bh, idesc, (st | kk) != 0);
         umma_bf16(tmem, ah, bl, idesc, 1);
-        umma_bf16(tmem, am, bm, idesc, 1);
-        umma_bf16(tmem, am, bh, idesc, 1);
-        umma_bf16(tmem, ah, bm, idesc, 1);
-        umma_bf16(tmem, ah, bh, idesc, 1);
+        umma_bf16(tmem, al, bh, idesc, 1);
       }
       umma_commit(&empty_bar[s]);
     }

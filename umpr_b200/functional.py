@@ -19,10 +19,12 @@ H, D, ATT, KP, SV = 64, 128, 64, 64, 256
 TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
+TENSOR_CORE_SNET = True        # tcgen05 S-Net over the valid positions only (snet_tc.cu), for inputs that carry their pack plan
 TENSOR_CORE_GEMM = True        # tcgen05 3xBF16 dense products (gemm_tc.cu); False = fp32 CUDA-core kernel everywhere
 TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
+ROUTING_LOG = None             # tests: a list that receives ("coattn", arg (2,B,P)) / ("cnet", cidx (N,KC)) - the arg-max positions the kernels chose
 DIRECT_GRAD_ACCUM = False      # set by train.FlatTrainer for the duration of its backward pass (see _sinks)
 
 
@@ -302,6 +304,8 @@ class _CoAttnFn(Function):
             colkey = torch.zeros(B * P, dtype=torch.int64, device=dev)
             call("umpr_coattn_fwd", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(rowkey), ptr(colkey), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
                  ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
+        if ROUTING_LOG is not None:
+            ROUTING_LOG.append(("coattn", arg.clone()))
         ctx.save_for_backward(gu, gi, giM, M, soft, arg)
         return soft[0], soft[1], atte[0], atte[1]
 
@@ -384,8 +388,62 @@ class _SNetFn(Function):
         return dx, d_word_soft, None, rMs, rWs
 
 
-def s_net(gru_repr, word_soft, sent_length, Ms, Ws):
-    """→ self_atte (B,S,128), sentiment (B,128)."""
+class _SNetTcFn(Function):
+    """S-Net on the tensor cores for a ``gru_repr`` that came out of ImprovedRnn with ``plan``: only the valid positions are
+    multiplied (csrc/snet_tc.cu); the backward recomputes the scores, so nothing but the input is kept."""
+
+    @staticmethod
+    def forward(ctx, plan, gru_repr, word_soft, sent_length, Ms, Ws):
+        ctx.params = (Ms, Ws)
+        x = _f32(_chk(gru_repr, "gru_repr"))
+        Ms, Ws = _f32(Ms), _f32(Ws)
+        word_soft = _f32(word_soft)
+        B, L = x.shape[0], int(sent_length)
+        S = x.shape[1] // L
+        N = B * S
+        dev = x.device
+        table, n_tiles = plan.snet_table()
+        T_v = float(plan.tokens)
+        self_atte = torch.empty(B, S, D, dtype=torch.float32, device=dev)
+        call("umpr_snet_fwd_tc", ptr(x), ptr(table), n_tiles, ptr(Ms), ptr(Ws), N, L, ptr(self_atte), _n_ctas(dev),
+             work=(2.0 * T_v * D * ATT, T_v * D * 8.0))
+        Wd = word_soft.numel() // N
+        wsum = torch.empty(N, dtype=torch.float32, device=dev)
+        sentiment = torch.empty(B, D, dtype=torch.float32, device=dev)
+        call("umpr_snet_sentiment_fwd", ptr(self_atte), ptr(word_soft), B, S, Wd, ptr(wsum), ptr(sentiment))
+        ctx.dims = (B, S, L, Wd, tuple(word_soft.shape))
+        ctx.plan = plan
+        ctx.save_for_backward(x, self_atte, wsum, Ms, Ws)
+        return self_atte, sentiment
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_self_atte, d_sentiment):
+        x, self_atte, wsum, Ms, Ws = ctx.saved_tensors
+        B, S, L, Wd, ws_shape = ctx.dims
+        N = B * S
+        dev = x.device
+        d_sa = torch.empty(N, D, dtype=torch.float32, device=dev)
+        want_ws = ctx.needs_input_grad[2] and d_sentiment is not None
+        d_wsum = torch.empty(N, dtype=torch.float32, device=dev) if want_ws else None
+        call("umpr_snet_sentiment_bwd", ptr(self_atte), ptr(wsum), ptr(None if d_sentiment is None else _f32(d_sentiment)),
+             ptr(None if d_self_atte is None else _f32(d_self_atte)), B, S, ptr(d_sa), ptr(d_wsum))
+        dx = torch.empty_like(x)        # positions beyond a sentence's length stay unwritten: the packed GRU never reads them (model.py:18)
+        (dMs, dWs), (rMs, rWs) = _sinks(ctx.params)
+        table, n_tiles = ctx.plan.snet_table()
+        T_v = float(ctx.plan.tokens)
+        call("umpr_snet_bwd_tc", ptr(x), ptr(table), n_tiles, ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev),
+             work=(6.0 * T_v * D * ATT, T_v * D * 8.0))
+        d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
+        return None, dx, d_word_soft, None, rMs, rWs
+
+
+def s_net(gru_repr, word_soft, sent_length, Ms, Ws, plan=None):
+    """→ self_atte (B,S,128), sentiment (B,128).  ``plan``: the PackPlan of the ImprovedRnn call that produced ``gru_repr`` (its rows
+    beyond each sentence's length are exactly zero) - enables the tensor-core kernels, which skip them."""
+    if (TENSOR_CORE_SNET and plan is not None and plan.R == 128 and plan.L == int(sent_length) and plan.L <= 128
+            and plan.N * plan.L == gru_repr.shape[0] * gru_repr.shape[1] and tuple(Ms.shape) == (ATT, D) and gru_repr.shape[2] == D):
+        return _SNetTcFn.apply(plan, gru_repr, word_soft, sent_length, Ms, Ws)
     return _SNetFn.apply(gru_repr, word_soft, sent_length, Ms, Ws)
 
 
@@ -458,6 +516,8 @@ class _CNetTailFn(Function):
             wt = torch.empty(3 * D * 128, dtype=torch.float32, device=dev)
             call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
             call("umpr_cnet_conv_fwd", ptr(x), ptr(wt), ptr(conv_b), N, L, KC, ptr(cfeat), ptr(cidx), _n_ctas(dev), work=work)
+        if ROUTING_LOG is not None:
+            ROUTING_LOG.append(("cnet", cidx.clone()))
         view_p = torch.empty(B, S, V, dtype=torch.float32, device=dev)
         final = torch.empty(B, V, dtype=torch.float32, device=dev)
         call("umpr_cnet_head_fwd", ptr(cfeat), ptr(lin_w), ptr(lin_b), float(threshold), B, S, V, KC, ptr(view_p), ptr(final))

@@ -104,6 +104,7 @@ class RNet(nn.Module):
         gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
         gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
         soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M)
+        gru_u._umpr_plan, gru_i._umpr_plan = pu.plan, pi.plan          # lets S-Net skip the positions beyond each sentence's length
         return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
 
 
@@ -121,7 +122,7 @@ class SNet(nn.Module):
                 print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
 
     def forward(self, gru_repr, word_soft, sent_length):
-        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws)
+        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws, plan=getattr(gru_repr, "_umpr_plan", None))
 
 
 class CNet(nn.Module):
@@ -152,6 +153,7 @@ class CNet(nn.Module):
         res = []
         for pk, (gru_repr, _) in zip(pks, self.gru.run_many(pks)):
             gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
+            gru_repr._umpr_plan = pk.plan
             view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
                                               self.linear[0].weight, self.linear[0].bias, self.threshold)
             res.append((gru_repr, view_p, final_repr))

@@ -171,6 +171,32 @@ class PackPlan:
     def row_src(self) -> torch.Tensor:
         return self.unsorted_indices
 
+    def snet_table(self):
+        """Tile table of the tensor-core S-Net (csrc/snet_tc.cu): consecutive OUTPUT rows (sentences, in the order ImprovedRnn
+        returns them) are grouped so that a tile holds at most 128 valid positions.  Sentence n goes to tile
+        ``cstart[n] // (129 - L)``: starts inside a window of 129-L rows plus one sentence of at most L rows never exceed 128.
+        → (device int32 ``[tile_sent_off (n_tiles+1) | cstart (N+1)]``, n_tiles); cached."""
+        if getattr(self, "_snet", None) is None:
+            self._snet = (upload_int32(self._snet_host()[0], self.device), self._snet_host()[1])
+        return self._snet
+
+    def _snet_host(self):
+        if getattr(self, "_snet_np", None) is None:
+            import numpy as np
+            if self.L > 128:
+                raise RuntimeError(f"umpr_b200: S-Net sentence length {self.L} exceeds 128")
+            n, rp = self.N, self.n_tiles * self.R
+            h = self._host_np
+            row_len = np.empty(n, dtype=np.int64)
+            row_len[h[rp:rp + n]] = h[2 * rp:2 * rp + n]                     # output row row_of[k] holds a sequence of len_of[k] steps
+            cstart = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(row_len, out=cstart[1:])
+            tid = np.unique(cstart[:-1] // (129 - self.L), return_inverse=True)[1]      # dense ids: no empty tiles when L > 129-L
+            nt = int(tid[-1]) + 1
+            tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
+            self._snet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
+        return self._snet_np
+
     def row_lengths(self) -> torch.Tensor:
         """Effective length of every OUTPUT row: len[unsorted_indices[n]] (the zero pattern of the result)."""
         return self.lengths[self.unsorted_indices]

@@ -93,6 +93,8 @@ def prepare_batch(batch, device):
     for ids, lens in ((u, ul), (it, il), (ui, uil)):
         if lens.numel() and ids.dim() == 3:
             lens._umpr_plan = PackPlan(lens.reshape(-1), ids.shape[2], device, upload=False)
+            if lens._umpr_plan.R == 128 and ids.shape[2] <= 128:
+                lens._umpr_plan._snet_host()                      # S-Net tile table (numpy; uploaded by the consumer)
     return batch
 
 
