@@ -155,18 +155,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int m0 = tile * 128 + q * 32;
+      const int c4 = (lane & 7) * 4;
+      // accumulate mode: the C rows of a 32-column chunk are requested one chunk ahead (the first one before the accumulator
+      // is even ready), so their latency hides behind the TMEM load / staging of the previous chunk
+      float4 cnext[8];
+      const bool acc_c = MODE == 0 && a.accumulate;
+      auto fetch_c = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + j * 4 + (lane >> 3), n = c0 + c4;
+          cnext[j] = (m < a.M && n < a.N) ? *reinterpret_cast<const float4*>(a.C + (long)m * a.ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (acc_c) fetch_c(0);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int m0 = tile * 128 + q * 32;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
+        float4 ccur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ccur[j] = cnext[j];
+        if (acc_c && c0 + 32 < BN) fetch_c(c0 + 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(&sw[lane * WS_STG_LD + j * 4]) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         __syncwarp();
-        const int c4 = (lane & 7) * 4, n = c0 + c4;
+        const int n = c0 + c4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = j * 4 + (lane >> 3), m = m0 + r;
@@ -178,7 +195,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
               crow = a.C + (((long)slab * 2 + dir) * a.R + rr) * G3 + n;
             } else {
               crow = a.C + (long)m * a.ldc + n;
-              if (a.accumulate) { const float4 c = *reinterpret_cast<const float4*>(crow); o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+              if (a.accumulate) { o.x += ccur[j].x; o.y += ccur[j].y; o.z += ccur[j].z; o.w += ccur[j].w; }
               if (a.bias) { o.x += a.bias[n]; o.y += a.bias[n + 1]; o.z += a.bias[n + 2]; o.w += a.bias[n + 3]; }
               if (a.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
               else if (a.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }

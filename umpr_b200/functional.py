@@ -478,8 +478,12 @@ class _TextMatchFn(Function):
         for j, (x, W, wi, off) in enumerate(((a_u, Wu, 0, 0), (s_u, Wu, 0, D), (a_i, Wi, 1, 0), (s_i, Wi, 1, D))):
             # d in_j = dpre · W[:, half]        (B(k,n) = W[k][off+n])
             sgemm(dpre, (D, 1), W.data_ptr() + 4 * off, (2 * D, 1), dins[j], D, B, D, D)
-            # dW[:, half] = dpre^T · in_j       (A(m,k) = dpre[k][m])
-            sgemm(dpre, (1, D), x, (D, 1), dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, splits=sp, accumulate=True)
+            # dW[:, half] += dpre^T · in_j      (A(m,k) = dpre[k][m]): reduction over the batch, both operands sample-major
+            if TENSOR_CORE_GEMM and B >= 256:
+                call("umpr_tc_gemm_tn", ptr(dpre), D, ptr(x), D, dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, _n_ctas(dev),
+                     work=(2.0 * D * D * B, 0.0))
+            else:
+                sgemm(dpre, (1, D), x, (D, 1), dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, splits=sp, accumulate=True)
         return dins[0], dins[1], dins[2], dins[3], rW[0], rW[1]
 
 
