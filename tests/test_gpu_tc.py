@@ -259,3 +259,33 @@ def test_cnet_tail_vs_fp64_torch(B, S, L, KC, V):
     ref = [vp.detach(), fin.detach(), xd.grad] + [t.grad for t in pd]
     for a, b, nm in zip(got, ref, ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
         assert_close(a, b.float(), 3e-5, nm)
+
+
+@pytest.mark.parametrize("B,S,L,short", [(96, 20, 20, False), (33, 5, 20, True), (8, 4, 100, False), (5, 3, 7, True)])
+def test_coattention_over_valid_rows_matches_dense(B, S, L, short):
+    """Co-attention (model.py:50-55) with the pack plans of its inputs - only the valid rows are multiplied, the padded rows' exact 0
+    enters every maximum analytically - against the same kernels run densely over all P rows: same soft-max weights, pooled
+    vectors and gradients (input gradients compared on the valid rows; the others are never read)."""
+    from umpr_b200 import functional as F
+    from umpr_b200.plan import PackPlan
+    torch.manual_seed(B + L)
+    N, P = B * S, S * L
+    plans, xs, masks = [], [], []
+    for side in range(2):
+        lens = torch.randint(1, (min(3, L) if short else L) + 1, (N,))
+        if short:
+            lens[side::5] = L
+        pl = PackPlan(lens, L, DEV, tile_rows=128 if N >= 2048 else 32)
+        m = (torch.arange(L, device=DEV)[None, :] < pl.row_lengths().to(DEV)[:, None]).view(B, P, 1)
+        plans.append(pl); masks.append(m)
+        xs.append(torch.tanh(torch.randn(B, P, 128, device=DEV)) * m)          # GRU outputs lie in (-1, 1)
+    M0 = torch.randn(128, 128, device=DEV) * (-0.02 if short else 0.02)       # negative M: many maxima are the padded rows' 0
+    g = [torch.randn(B, P, device=DEV), torch.randn(B, P, device=DEV), torch.randn(B, 128, device=DEV), torch.randn(B, 128, device=DEV)]
+    res = []
+    for pls in (None, tuple(plans)):
+        gu, gi, M = xs[0].clone().requires_grad_(True), xs[1].clone().requires_grad_(True), M0.clone().requires_grad_(True)
+        out = F.co_attention(gu, gi, M, plans=pls)
+        sum((o * w).sum() for o, w in zip(out, g)).backward()
+        res.append([o.detach() for o in out] + [gu.grad * masks[0], gi.grad * masks[1], M.grad])
+    for a, b, nm in zip(res[1], res[0], ["soft_u", "soft_i", "atte_u", "atte_i", "dgu", "dgi", "dM"]):
+        assert_close(a, b, 2e-5, nm)

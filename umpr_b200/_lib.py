@@ -33,7 +33,7 @@ SIGNATURES = {
     "umpr_tc_gemm_tn": [P, L, P, L, P, L, I, I, L, I, P],
     "umpr_tc_gemm_ws": [P, L, P, L, P, L, I, I, I, I, P, I, I, I, P],
     "umpr_coattn_fwd": [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
-    "umpr_coattn_fwd_tc": [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P],
+    "umpr_coattn_fwd_tc": [P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P, P, P, P, P],
     "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, P, P, P],
     "umpr_snet_fwd": [P, P, P, I, I, P, P, P, I, P],
     "umpr_snet_sentiment_fwd": [P, P, I, I, I, P, P, P],
@@ -121,7 +121,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"umpr_coattn_fwd": 2, "umpr_coattn_fwd_tc": 2, "umpr_cnet_conv_fwd_tc": 3, "umpr_cnet_conv_bwd": 3, "umpr_visual_fwd": 2, "umpr_visual_bwd": 3}
+KERNELS_PER_CALL = {"umpr_coattn_fwd": 2, "umpr_coattn_fwd_tc": 3, "umpr_cnet_conv_fwd_tc": 3, "umpr_cnet_conv_bwd": 3, "umpr_visual_fwd": 2, "umpr_visual_bwd": 3}
 launch_count = 0          # kernels launched by this process through the C-ABI
 _timer = None             # optional {"only": set|None, "events": {name: [(start, end), ...]}}
 

@@ -63,19 +63,49 @@ constexpr int CI_IMG = 4 * CI_TILE;         // [kb 2][hi|lo][128][128 B]: a 128-
 constexpr int C2_THREADS = 320;
 constexpr int C2_MAXP = 512;
 
-// fp32 rows (giM and gu of every sample, zero-padded to 128-row tiles) -> operand images + squared row norms
+// Valid-position bookkeeping of one side of one sample.  Inputs that come out of ImprovedRnn have exactly-zero rows at and beyond each
+// sentence's length (model.py:20); their affinity entries are exactly 0, so only the VALID rows are compacted into the operand
+// images and multiplied, and "0" enters every maximum analytically (coattn_resolve_kernel).
+//   meta[(b*2 + which)*2 + {0,1}] = {number of valid rows, first padded position (or -1)};  pos[b*P + c] = position of compact row c
+// which = 0: giM rows (item side), 1: gu rows (user side).  cst = exclusive prefix sum of the sentence lengths (NULL: all P rows valid).
 __global__ void __launch_bounds__(256) coattn_images_kernel(const float* __restrict__ giM, const float* __restrict__ gu, int P, int T,
-                                                            unsigned char* __restrict__ imgA, unsigned char* __restrict__ imgB,
-                                                            float* __restrict__ n2a, float* __restrict__ n2b) {
+                                                            const int* __restrict__ cst_a, int S_a, int L_a, const int* __restrict__ cst_b,
+                                                            int S_b, int L_b, unsigned char* __restrict__ imgA,
+                                                            unsigned char* __restrict__ imgB, float* __restrict__ n2a, float* __restrict__ n2b,
+                                                            int* __restrict__ posA, int* __restrict__ posB, int* __restrict__ meta) {
+  __shared__ int sb[C2_MAXP + 1];
   const int t = blockIdx.x, b = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
+  const int* cst = which ? cst_b : cst_a;
+  const int S_ = which ? S_b : S_a, L_ = which ? L_b : L_a;
   const float* src = (which ? gu : giM) + (size_t)b * P * D;
   unsigned char* img = (which ? imgB : imgA) + ((size_t)b * T + t) * CI_IMG;
   float* n2 = (which ? n2b : n2a) + (size_t)b * P;
+  int* pos = (which ? posB : posA) + (size_t)b * P;
+  int Pv = P;
+  if (cst) {
+    const int base0 = cst[(size_t)b * S_];
+    for (int s_ = tid; s_ <= S_; s_ += 256) sb[s_] = cst[(size_t)b * S_ + s_] - base0;
+    __syncthreads();
+    Pv = sb[S_];
+  }
+  if (t == 0 && tid == 0) {
+    int fp = -1;
+    if (cst) for (int s_ = 0; s_ < S_; ++s_) { const int len = sb[s_ + 1] - sb[s_]; if (len < L_) { fp = s_ * L_ + len; break; } }
+    meta[(b * 2 + which) * 2] = Pv;
+    meta[(b * 2 + which) * 2 + 1] = fp;
+  }
+  if (t * 128 >= Pv) return;                           // nothing valid in this tile: the affinity kernel never loads it
   const int k = (tid & 15) * 4;
   for (int r = tid >> 4; r < 128; r += 16) {          // half-warp per row, both k-blocks
-    const int p = t * 128 + r;
+    const int c = t * 128 + r;
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (p < P) {
+    int p = c;
+    if (c < Pv) {
+      if (cst) {                                        // sentence of compact row c: largest s with sb[s] <= c
+        int lo = 0, hi = S_;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sb[mid] <= c) lo = mid; else hi = mid; }
+        p = lo * L_ + (c - sb[lo]);
+      }
       v0 = *reinterpret_cast<const float4*>(src + (size_t)p * D + k);
       v1 = *reinterpret_cast<const float4*>(src + (size_t)p * D + 64 + k);
     }
@@ -84,7 +114,7 @@ __global__ void __launch_bounds__(256) coattn_images_kernel(const float* __restr
     float q = v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w + v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
     q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 4);
     q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 1);
-    if ((tid & 15) == 0 && p < P) n2[p] = q;
+    if ((tid & 15) == 0 && c < Pv) { n2[c] = q; pos[c] = p; }
   }
 }
 
@@ -92,7 +122,7 @@ struct C2Bars { uint64_t a_full, a_empty, b_full[2], b_empty[2], acc_full[2], ac
 
 __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                                                                             const float* __restrict__ n2a, const float* __restrict__ n2b, int P, int T,
-                                                                            float4* __restrict__ rc_v, int4* __restrict__ rc_i,
+                                                                            const int* __restrict__ meta, float4* __restrict__ rc_v, int4* __restrict__ rc_i,
                                                                             float4* __restrict__ cc_v, int4* __restrict__ cc_i) {
   extern __shared__ unsigned char raw[];
   __shared__ C2Bars bars;
@@ -106,6 +136,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   unsigned char* b_img = base + CI_IMG;         // 2 stages of gu tiles
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x;
+  const int Pa = meta[b * 4], Pb = meta[b * 4 + 2];               // valid rows of giM (i) / gu (j) of this sample
+  const int Ta = (Pa + 127) >> 7, Tb = (Pb + 127) >> 7;
 
   if (tid == 0) {
     mbar_init(&bars.a_full, 1); mbar_init(&bars.a_empty, 1);
@@ -115,9 +147,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   if (warp == 9) tmem_alloc(&tmem_slot, 512);
   float amax = 0.f;
   for (int p = tid; p < C2_MAXP; p += C2_THREADS) {
-    const float an = p < P ? sqrtf(n2a[(size_t)b * P + p]) : 0.f;
+    const float an = p < Pa ? sqrtf(n2a[(size_t)b * P + p]) : 0.f;
     s_an[p] = an;
-    s_bn[p] = p < P ? sqrtf(n2b[(size_t)b * P + p]) : 0.f;
+    s_bn[p] = p < Pb ? sqrtf(n2b[(size_t)b * P + p]) : 0.f;
     s_colmax[p] = -INFINITY;
     s_cv[p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     s_ci[p] = make_int4(-1, -1, -1, -1);
@@ -128,7 +160,6 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const int n_pairs = 2 * T * T;
 
   if (warp < 8) {
     // ------------------------------------------------------------------ epilogue: S rows (warps 0-3) / S^T rows (warps 4-7)
@@ -139,14 +170,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
     cd.init();
     float thr = -INFINITY;    // candidate threshold (final maximum - tau), kept in a register: Cand4 itself lives on the stack for push()
     int n = 0;
+    const int Pown = is_t ? Pb : Pa;
     for (int pass = 0; pass < 2; ++pass)
-      for (int it = 0; it < T; ++it)
+      for (int it = 0; it < Ta; ++it)
 #pragma unroll 1
-        for (int jt = 0; jt < T; ++jt, ++n) {
+        for (int jt = 0; jt < Tb; ++jt, ++n) {
           const int s = n & 1;
-          const int own = (is_t ? jt : it) * 128 + r;                // the row (i) / column (j) this thread scans (< 512)
+          const int own = (is_t ? jt : it) * 128 + r;                // the (compact) row i / column j this thread scans (< 512)
           const int o0 = (is_t ? it : jt) * 128;                     // first index of the scanned direction
-          const int nv = min(128, P - o0);
+          const int nv = min(128, (is_t ? Pa : Pb) - o0);
           const float tau = is_t ? CA_EPS * s_bn[own] * amax : CA_EPS * s_an[own] * CA_GNORM;
           if (pass == 1) {
             if (is_t) {
@@ -165,7 +197,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           tc_fence_after();
           const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + s * 256 + (is_t ? 128 : 0);
           float tm = -INFINITY;
-          const bool scan = pass == 1 && own < P;
+          const bool scan = pass == 1 && own < Pown;
           uint32_t ra[2][16];
           tmem_ld16_issue(t0, ra[0]);
 #pragma unroll
@@ -189,9 +221,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           mbar_arrive(&bars.acc_empty[s]);
           if (pass == 0) {
             if (is_t) s_colmax[own] = fmaxf(s_colmax[own], tm);
-            else { m = fmaxf(m, tm); if (jt == T - 1) s_rowmax[own] = m; }
-          } else if (own < P) {
-            const bool done = is_t ? (it == T - 1) : (jt == T - 1);
+            else { m = fmaxf(m, tm); if (jt == Tb - 1) s_rowmax[own] = m; }
+          } else if (own < Pown) {
+            const bool done = is_t ? (it == Ta - 1) : (jt == Tb - 1);
             if (done) {
               const size_t o = (size_t)b * P + own;
 #pragma unroll
@@ -209,11 +241,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
     if (lane == 0) {
       int n = 0, na = 0;
       for (int pass = 0; pass < 2; ++pass)
-        for (int it = 0; it < T; ++it, ++na) {
+        for (int it = 0; it < Ta; ++it, ++na) {
           if (na > 0) mbar_wait(&bars.a_empty, (na - 1) & 1);
           mbar_arrive_expect_tx(&bars.a_full, CI_IMG);
           bulk_copy_g2s(a_img, imgA + ((size_t)b * T + it) * CI_IMG, CI_IMG, &bars.a_full);
-          for (int jt = 0; jt < T; ++jt, ++n) {
+          for (int jt = 0; jt < Tb; ++jt, ++n) {
             const int s = n & 1;
             if (n >= 2) mbar_wait(&bars.b_empty[s], ((n >> 1) - 1) & 1);
             mbar_arrive_expect_tx(&bars.b_full[s], CI_IMG);
@@ -227,9 +259,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
     const uint32_t a0 = smem_u32(a_img);
     int n = 0, na = 0;
     for (int pass = 0; pass < 2; ++pass)
-      for (int it = 0; it < T; ++it, ++na) {
+      for (int it = 0; it < Ta; ++it, ++na) {
         mbar_wait(&bars.a_full, na & 1);
-        for (int jt = 0; jt < T; ++jt, ++n) {
+        for (int jt = 0; jt < Tb; ++jt, ++n) {
           const int s = n & 1;
           mbar_wait(&bars.b_full[s], (n >> 1) & 1);
           if (n >= 2) mbar_wait(&bars.acc_empty[s], ((n >> 1) - 1) & 1);
@@ -254,10 +286,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           }
           umma_commit(&bars.b_empty[s]);
           umma_commit(&bars.acc_full[s]);
-          if (jt == T - 1) umma_commit(&bars.a_empty);
+          if (jt == Tb - 1) umma_commit(&bars.a_empty);
         }
       }
-    (void)n_pairs;
   }
   tc_fence_before();
   __syncthreads();
@@ -271,9 +302,15 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ giM_b, cons
   return warp_sum(x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w);
 }
 
-// resolve the candidates with exact fp32 re-scoring, then tanh / softmax over all P / pooling (model.py:52-55)
+// resolve the candidates with exact fp32 re-scoring, then tanh / softmax over all P / pooling (model.py:52-55).
+// Works on the compact (valid-row) index space of the affinity kernel and writes results at the original positions.  When the
+// other side has padded rows, every maximum also competes with their exact 0: a maximum below 0 becomes (0, first padded
+// position) - its gradient lands on a zero row and vanishes, exactly as in the dense computation.  Padded positions of the own
+// side get value tanh(0) = 0 and take part in the softmax.
 __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __restrict__ giM, const float* __restrict__ gu, const float* __restrict__ gi,
-                                                             const float* __restrict__ n2a, const float* __restrict__ n2b, int P, int n_it, const float4* __restrict__ rc_v, const int4* __restrict__ rc_i,
+                                                             const float* __restrict__ n2a, const float* __restrict__ n2b, int P,
+                                                             const int* __restrict__ meta, const int* __restrict__ posA, const int* __restrict__ posB,
+                                                             const float4* __restrict__ rc_v, const int4* __restrict__ rc_i,
                                                              const float4* __restrict__ cc_v, const int4* __restrict__ cc_i,
                                                              float* __restrict__ soft_u, float* __restrict__ soft_i, float* __restrict__ t_u,
                                                              float* __restrict__ t_i, int* __restrict__ arg_u, int* __restrict__ arg_i,
@@ -290,82 +327,94 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
   float* soft = (side ? soft_i : soft_u) + (size_t)b * P;
   float* tv = (side ? t_i : t_u) + (size_t)b * P;
   int* arg = (side ? arg_i : arg_u) + (size_t)b * P;
+  const int Pa = meta[b * 4], Pb = meta[b * 4 + 2];
+  const int Po = side ? Pa : Pb;                                  // own valid count (side 1 = rows i, side 0 = columns j)
+  const int* pos_own = (side ? posA : posB) + (size_t)b * P;
+  const int* pos_oth = (side ? posB : posA) + (size_t)b * P;
+  const int zero_at = meta[b * 4 + (side ? 3 : 1)];               // first padded position of the OTHER side, -1 if it has none
+  const float* n2_own = (side ? n2a : n2b) + (size_t)b * P;
+  const float4* cv = (side ? rc_v : cc_v) + (size_t)b * P;
+  const int4* ci = (side ? rc_i : cc_i) + (size_t)b * P;
   // max_i |giM_i| of this sample (bound for the column-side tolerance); squared row norms come from coattn_images_kernel
   float gmax = 0.f;
   if (side == 0) {
-    for (int p = tid; p < P; p += 256) gmax = fmaxf(gmax, n2a[(size_t)b * P + p]);
+    for (int p = tid; p < Pa; p += 256) gmax = fmaxf(gmax, n2a[(size_t)b * P + p]);
     gmax = sqrtf(block_max(gmax, red));
   }
-  // (1) one thread per row / column: count the candidates that survive the tolerance; a unique survivor keeps its tensor-core value
-  //     (the common case), the others go to a work list;  (2) one warp per work-list entry: exact fp32 re-scoring
   __shared__ int s_work[C2_MAXP], s_nwork;
   if (tid == 0) s_nwork = 0;
+  for (int p = tid; p < P; p += 256) { tv[p] = 0.f; arg[p] = 0; }          // padded positions of the own side (valid ones overwritten below)
   __syncthreads();
-  const int nl = side ? 1 : n_it;
-  for (int p = tid; p < P; p += 256) {
-    const float tau = CA_EPS * sqrtf((side ? n2a : n2b)[(size_t)b * P + p]) * (side ? CA_GNORM : gmax);
-    float head = -INFINITY;
-    for (int l = 0; l < nl; ++l) head = fmaxf(head, side ? rc_v[(size_t)b * P + p].x : cc_v[((size_t)b * n_it + l) * P + p].x);
+  // (1) one thread per row / column: count the candidates that survive the tolerance; a unique survivor keeps its tensor-core value
+  //     (the common case), the others go to a work list;  (2) one warp per work-list entry: exact fp32 re-scoring
+  for (int p = tid; p < Po; p += 256) {
+    const float tau = CA_EPS * sqrtf(n2_own[p]) * (side ? CA_GNORM : gmax);
+    const float4 v = cv[p];
+    const int4 id = ci[p];
+    const float head = v.x;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const int ii[4] = {id.x, id.y, id.z, id.w};
     float lone_v = 0.f;
     int lone_i = 0, n_surv = 0;
-    for (int l = 0; l < nl; ++l) {
-      const size_t o = side ? (size_t)b * P + p : ((size_t)b * n_it + l) * P + p;
-      const float4 v = side ? rc_v[o] : cc_v[o];
-      const int4 id = side ? rc_i[o] : cc_i[o];
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      const int ii[4] = {id.x, id.y, id.z, id.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (ii[k] >= 0 && vv[k] >= head - tau) { ++n_surv; lone_v = vv[k]; lone_i = ii[k]; }
-    }
-    if (n_surv <= 1) {
-      const float t = tanhf(lone_v);
-      sp[p] = t; tv[p] = t; arg[p] = lone_i;
-    } else if (p < C2_MAXP) {
+    for (int k = 0; k < 4; ++k)
+      if (ii[k] >= 0 && vv[k] >= head - tau) { ++n_surv; lone_v = vv[k]; lone_i = ii[k]; }
+    const bool near_zero = zero_at >= 0 && fabsf(lone_v) <= tau;             // undecided against the padded rows' exact 0
+    if (n_surv <= 1 && !near_zero) {
+      const bool zero_wins = zero_at >= 0 && lone_v < 0.f;
+      const float t = zero_wins ? 0.f : tanhf(lone_v);
+      sp[p] = t; tv[pos_own[p]] = t; arg[pos_own[p]] = zero_wins ? zero_at : pos_oth[lone_i];
+    } else {
       s_work[atomicAdd(&s_nwork, 1)] = p;
     }
   }
   __syncthreads();
   for (int wi = warp; wi < s_nwork; wi += 8) {
     const int p = s_work[wi];
-    const float tau = CA_EPS * sqrtf((side ? n2a : n2b)[(size_t)b * P + p]) * (side ? CA_GNORM : gmax);
-    float head = -INFINITY;
-    for (int l = 0; l < nl; ++l) head = fmaxf(head, side ? rc_v[(size_t)b * P + p].x : cc_v[((size_t)b * n_it + l) * P + p].x);
+    const float tau = CA_EPS * sqrtf(n2_own[p]) * (side ? CA_GNORM : gmax);
+    const float4 v = cv[p];
+    const int4 id = ci[p];
+    const float head = v.x;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    const int ii[4] = {id.x, id.y, id.z, id.w};
     float best = -INFINITY;
     int besti = 0x7fffffff;
-    for (int l = 0; l < nl; ++l) {
-      const size_t o = side ? (size_t)b * P + p : ((size_t)b * n_it + l) * P + p;
-      const float4 v = side ? rc_v[o] : cc_v[o];
-      const int4 id = side ? rc_i[o] : cc_i[o];
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      const int ii[4] = {id.x, id.y, id.z, id.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (ii[k] < 0 || vv[k] < head - tau) continue;
-        const float ex = side ? exact_dot(giM_b, gu_b, p, ii[k], lane) : exact_dot(giM_b, gu_b, ii[k], p, lane);
-        if (ex > best || (ex == best && ii[k] < besti)) { best = ex; besti = ii[k]; }
-      }
+    for (int k = 0; k < 4; ++k) {
+      if (ii[k] < 0 || vv[k] < head - tau) continue;
+      const int po = pos_oth[ii[k]];
+      const float ex = side ? exact_dot(giM_b, gu_b, pos_own[p], po, lane) : exact_dot(giM_b, gu_b, po, pos_own[p], lane);
+      if (ex > best || (ex == best && po < besti)) { best = ex; besti = po; }
     }
+    if (zero_at >= 0 && (best < 0.f || (best == 0.f && zero_at < besti))) { best = 0.f; besti = zero_at; }    // first maximum wins
     if (lane == 0) {
       const float t = tanhf(best);
-      sp[p] = t; tv[p] = t; arg[p] = besti;
+      sp[p] = t; tv[pos_own[p]] = t; arg[pos_own[p]] = besti;
     }
   }
   __syncthreads();
-  float mx = -INFINITY;
-  for (int p = tid; p < P; p += 256) mx = fmaxf(mx, sp[p]);
+  const int n_pad = P - Po;                                       // own padded positions: value tanh(0) = 0 each
+  float mx = n_pad > 0 ? 0.f : -INFINITY;
+  for (int p = tid; p < Po; p += 256) mx = fmaxf(mx, sp[p]);
   mx = block_max(mx, red);
   float sum = 0.f;
-  for (int p = tid; p < P; p += 256) { const float e = expf(sp[p] - mx); sp[p] = e; sum += e; }
+  for (int p = tid; p < Po; p += 256) { const float e = expf(sp[p] - mx); sp[p] = e; sum += e; }
   sum = block_sum(sum, red);
+  const float e_pad = expf(-mx);
+  sum += (float)n_pad * e_pad;
   const float inv = 1.f / sum;
-  for (int p = tid; p < P; p += 256) { const float s = sp[p] * inv; sp[p] = s; soft[p] = s; }
+  if (n_pad > 0) {
+    const float s_pad = e_pad * inv;
+    for (int p = tid; p < P; p += 256) soft[p] = s_pad;
+    __syncthreads();
+  }
+  for (int p = tid; p < Po; p += 256) { const float s = sp[p] * inv; sp[p] = s; soft[pos_own[p]] = s; }
   __syncthreads();
   const int c4 = tid & 31, pg = tid >> 5;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = pg; p < P; p += 8) {
+  for (int p = pg; p < Po; p += 8) {
     const float s = sp[p];
-    const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + c4 * 4);
+    const float4 v = *reinterpret_cast<const float4*>(g + (size_t)pos_own[p] * D + c4 * 4);
     acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w;
   }
   part[pg * 32 + c4] = acc;
@@ -382,35 +431,44 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
 
 using namespace umpr;
 
-// scratch (16-byte aligned): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),
-// T = ceil(P/128): 2*B*T*65536 + 2*B*P*4 + 4*B*P*16 + 256 bytes.  P <= 512.
-extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, void* scratch, float* soft_u,
-                                  float* soft_i, float* t_u, float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i,
-                                  void* stream) {
+// scratch (16-byte aligned): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][posA B*P i32][posB B*P i32][meta 4*B i32]
+// [rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),  T = ceil(P/128): 2*B*T*65536 + 4*B*P*4 + 16*B + 4*B*P*16 + 256 bytes.  P <= 512.
+// cst_u / cst_i (optional, both or neither): exclusive prefix sums of the sentence lengths of the user / item side (S_x sentences of
+// L_x positions per sample, S_x*L_x == P) for inputs whose rows beyond each sentence's length are exactly zero - only the valid rows
+// are multiplied.  NULL: every row is treated as valid.
+extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, const int32_t* cst_u, int S_u, int L_u,
+                                  const int32_t* cst_i, int S_i, int L_i, void* scratch, float* soft_u, float* soft_i, float* t_u,
+                                  float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream) {
   if (B <= 0 || P <= 0) return 0;
   if (B > 65535) return fail_arg("coattn_fwd_tc: batch %d > 65535", B);
   if (P > C2_MAXP) return fail_arg("coattn_fwd_tc: P=%d > %d (use umpr_coattn_fwd)", P, C2_MAXP);
+  if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_fwd_tc: length tables must be given for both sides or neither");
+  if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
+    return fail_arg("coattn_fwd_tc: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);
   const int T = (P + 127) / 128;
   unsigned char* imgA = reinterpret_cast<unsigned char*>(scratch);
   unsigned char* imgB = imgA + (size_t)B * T * CI_IMG;
   float* n2a = reinterpret_cast<float*>(imgB + (size_t)B * T * CI_IMG);
   float* n2b = n2a + (size_t)B * P;
-  uintptr_t q = (reinterpret_cast<uintptr_t>(n2b + (size_t)B * P) + 15) & ~uintptr_t(15);
+  int* posA = reinterpret_cast<int*>(n2b + (size_t)B * P);
+  int* posB = posA + (size_t)B * P;
+  int* meta = posB + (size_t)B * P;
+  uintptr_t q = (reinterpret_cast<uintptr_t>(meta + (size_t)4 * B) + 15) & ~uintptr_t(15);
   float4* rc_v = reinterpret_cast<float4*>(q);
   int4* rc_i = reinterpret_cast<int4*>(rc_v + (size_t)B * P);
   float4* cc_v = reinterpret_cast<float4*>(rc_i + (size_t)B * P);
   int4* cc_i = reinterpret_cast<int4*>(cc_v + (size_t)B * P);
   cudaStream_t st = (cudaStream_t)stream;
-  coattn_images_kernel<<<dim3(T, B, 2), 256, 0, st>>>(giM, gu, P, T, imgA, imgB, n2a, n2b);
+  coattn_images_kernel<<<dim3(T, B, 2), 256, 0, st>>>(giM, gu, P, T, cst_i, S_i, L_i, cst_u, S_u, L_u, imgA, imgB, n2a, n2b, posA, posB, meta);
   if (int rc = check_launch("coattn_images")) return rc;
   const int sm1 = 3 * CI_IMG + 1024;
   cudaError_t e = cudaFuncSetAttribute(coattn_affinity_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
   if (e != cudaSuccess) { set_error("coattn_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
-  coattn_affinity_tc2_kernel<<<B, C2_THREADS, sm1, st>>>(imgA, imgB, n2a, n2b, P, T, rc_v, rc_i, cc_v, cc_i);
+  coattn_affinity_tc2_kernel<<<B, C2_THREADS, sm1, st>>>(imgA, imgB, n2a, n2b, P, T, meta, rc_v, rc_i, cc_v, cc_i);
   if (int rc = check_launch("coattn_affinity_tc2")) return rc;
   const size_t sm2 = sizeof(float) * (((P + 3) & ~3) + 32) + sizeof(float4) * 8 * 32;
   if (sm2 > 48 * 1024) cudaFuncSetAttribute(coattn_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
-  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, st>>>(giM, gu, gi, n2a, n2b, P, 1, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
+  coattn_resolve_kernel<<<dim3(B, 2), 256, sm2, st>>>(giM, gu, gi, n2a, n2b, P, meta, posA, posB, rc_v, rc_i, cc_v, cc_i, soft_u, soft_i, t_u,
                                                      t_i, arg_u, arg_i, atte_u, atte_i);
   return check_launch("coattn_resolve");
 }

@@ -283,7 +283,7 @@ def _splits_for(K, device):
 # --------------------------------------------------------------------------------------------------------------------
 class _CoAttnFn(Function):
     @staticmethod
-    def forward(ctx, gu, gi, M):
+    def forward(ctx, plans, gu, gi, M):
         ctx.params = (M,)
         gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
         B, P, _ = gu.shape
@@ -296,9 +296,20 @@ class _CoAttnFn(Function):
         work = (2.0 * B * P * P * D, 2.0 * B * P * D * 4)
         if TENSOR_CORE_COATTN and P <= 512:
             n_it = (P + 127) // 128
-            scratch = torch.empty((2 * B * n_it * 65536 + 2 * B * P * 4 + 4 * B * P * 16 + 256 + 3) // 4, dtype=torch.float32, device=dev)
-            call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, ptr(scratch), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]),
-                 ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
+            scratch = torch.empty((2 * B * n_it * 65536 + 4 * B * P * 4 + 16 * B + 4 * B * P * 16 + 256 + 3) // 4, dtype=torch.float32, device=dev)
+            cst = [None, None]
+            sl = [0, 0, 0, 0]
+            if plans is not None and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans):
+                # both inputs come out of ImprovedRnn with these plans: rows beyond each sentence's length are exactly zero
+                for k, pl in enumerate(plans):
+                    table, n_tiles = pl.snet_table()
+                    cst[k] = table.data_ptr() + 4 * (n_tiles + 1)
+                    sl[2 * k], sl[2 * k + 1] = pl.N // B, pl.L
+                ctx.keep = plans
+                valid = float(plans[0].tokens) * float(plans[1].tokens) / B
+                work = (2.0 * valid * D, 2.0 * (plans[0].tokens + plans[1].tokens) * D * 4)
+            call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, cst[0], sl[0], sl[1], cst[1], sl[2], sl[3], ptr(scratch),
+                 ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
         else:
             rowkey = torch.empty(B * P, dtype=torch.int64, device=dev)
             colkey = torch.zeros(B * P, dtype=torch.int64, device=dev)
@@ -329,12 +340,13 @@ class _CoAttnFn(Function):
             call("umpr_tc_gemm_tn", ptr(gi), D, ptr(dgiM), D, ptr(dM), D, D, D, B * P, _n_ctas(dev), work=(2.0 * D * D * B * P, 0.0))
         else:
             sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
-        return dgu, dgi, rM
+        return None, dgu, dgi, rM
 
 
-def co_attention(gu, gi, M):
-    """→ soft_u, soft_i (B,P), atte_u, atte_i (B,128)."""
-    return _CoAttnFn.apply(gu, gi, M)
+def co_attention(gu, gi, M, plans=None):
+    """→ soft_u, soft_i (B,P), atte_u, atte_i (B,128).  ``plans`` = (plan_u, plan_i): the PackPlans of the ImprovedRnn calls that
+    produced ``gu`` / ``gi`` - their rows beyond each sentence's length are exactly zero and the tensor-core kernels skip them."""
+    return _CoAttnFn.apply(plans, gu, gi, M)
 
 
 # --------------------------------------------------------------------------------------------------------------------

@@ -103,7 +103,7 @@ class RNet(nn.Module):
         (gru_u, _), (gru_i, _) = self.gru.run_many([pu, pi])           # model.py:45-46: shared weights, one fused launch
         gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
         gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
-        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M)
+        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=(pu.plan, pi.plan))
         gru_u._umpr_plan, gru_i._umpr_plan = pu.plan, pi.plan          # lets S-Net skip the positions beyond each sentence's length
         return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
 
