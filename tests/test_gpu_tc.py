@@ -286,6 +286,6 @@ def test_coattention_over_valid_rows_matches_dense(B, S, L, short):
         gu, gi, M = xs[0].clone().requires_grad_(True), xs[1].clone().requires_grad_(True), M0.clone().requires_grad_(True)
         out = F.co_attention(gu, gi, M, plans=pls)
         sum((o * w).sum() for o, w in zip(out, g)).backward()
-        res.append([o.detach() for o in out] + [gu.grad * masks[0], gi.grad * masks[1], M.grad])
+        res.append([o.detach() for o in out] + [torch.where(masks[0], gu.grad, torch.zeros_like(gu.grad)), torch.where(masks[1], gi.grad, torch.zeros_like(gi.grad)), M.grad])
     for a, b, nm in zip(res[1], res[0], ["soft_u", "soft_i", "atte_u", "atte_i", "dgu", "dgi", "dM"]):
         assert_close(a, b, 2e-5, nm)

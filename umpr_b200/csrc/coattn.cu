@@ -167,8 +167,9 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ t_i, const int* __restrict__ arg_u,
                                                          const int* __restrict__ arg_i, const float* __restrict__ d_soft_u,
                                                          const float* __restrict__ d_soft_i, const float* __restrict__ d_atte_u,
-                                                         const float* __restrict__ d_atte_i, int P, float* __restrict__ dgu,
-                                                         float* __restrict__ dgi, float* __restrict__ dgiM) {
+                                                         const float* __restrict__ d_atte_i, int P, const int* __restrict__ cst_u,
+                                                         int S_u, int L_u, const int* __restrict__ cst_i, int S_i, int L_i,
+                                                         float* __restrict__ dgu, float* __restrict__ dgi, float* __restrict__ dgiM) {
   extern __shared__ __align__(16) float smem[];
   const int P4 = (P + 3) & ~3;
   float* wu = smem;            // [P4] d(pre-activation col max)  -> entries (arg_u[j], j)
@@ -176,11 +177,24 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   float* dau = smem + 2 * P4;  // [128]
   float* dai = dau + D;        // [128]
   float* red = dai + D;        // [32]
+  // with length tables: rows at or beyond a sentence's length are exactly zero (model.py:20) and are neither read nor written
+  // (their gradients are never used); dgiM alone gets explicit zeros there because the dM reduction runs over every row
+  unsigned char* mu = reinterpret_cast<unsigned char*>(red + 32);   // [P4] user-side row is valid
+  unsigned char* mi = mu + P4;                                       // [P4] item-side row is valid
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t bp = (size_t)b * P;
   if (tid < D) {
     dau[tid] = d_atte_u ? d_atte_u[(size_t)b * D + tid] : 0.f;
     dai[tid] = d_atte_i ? d_atte_i[(size_t)b * D + tid] : 0.f;
+  }
+  for (int p = tid; p < P; p += 256) {
+    unsigned char a = 1, c = 1;
+    if (cst_u) {
+      const int su = p / L_u, si = p / L_i;
+      a = (p - su * L_u) < cst_u[(size_t)b * S_u + su + 1] - cst_u[(size_t)b * S_u + su];
+      c = (p - si * L_i) < cst_i[(size_t)b * S_i + si + 1] - cst_i[(size_t)b * S_i + si];
+    }
+    mu[p] = a; mi[p] = c;
   }
   __syncthreads();
   // ds[p] = d_soft[p] + <g[p], d_atte>
@@ -190,7 +204,9 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
     const float* dso = side ? d_soft_i : d_soft_u;
     float* dst = side ? vi : wu;
     const float4 d4 = *reinterpret_cast<const float4*>(da + lane * 4);
+    const unsigned char* ok = side ? mi : mu;
     for (int p = warp; p < P; p += 8) {
+      if (!ok[p]) { if (lane == 0) dst[p] = dso ? dso[bp + p] : 0.f; continue; }
       const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4);
       float s = v.x * d4.x + v.y * d4.y + v.z * d4.z + v.w * d4.w;
       s = warp_sum(s);
@@ -215,28 +231,37 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   // dense part (every row written exactly once)
   const float4 dau4 = *reinterpret_cast<const float4*>(dau + lane * 4);
   const float4 dai4 = *reinterpret_cast<const float4*>(dai + lane * 4);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = warp; p < P; p += 8) {
-    const float su = soft_u[bp + p], w = wu[p];
-    const float4 m = *reinterpret_cast<const float4*>(giM + (bp + arg_u[bp + p]) * D + lane * 4);
-    *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) =
-        make_float4(su * dau4.x + w * m.x, su * dau4.y + w * m.y, su * dau4.z + w * m.z, su * dau4.w + w * m.w);
-    const float si = soft_i[bp + p], v = vi[p];
-    const float4 u = *reinterpret_cast<const float4*>(gu + (bp + arg_i[bp + p]) * D + lane * 4);
-    *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = make_float4(v * u.x, v * u.y, v * u.z, v * u.w);
-    *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(si * dai4.x, si * dai4.y, si * dai4.z, si * dai4.w);
+    if (mu[p]) {
+      const float su = soft_u[bp + p], w = wu[p];
+      const int a = arg_u[bp + p];
+      const float4 m = mi[a] ? *reinterpret_cast<const float4*>(giM + (bp + a) * D + lane * 4) : zero4;
+      *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) =
+          make_float4(su * dau4.x + w * m.x, su * dau4.y + w * m.y, su * dau4.z + w * m.z, su * dau4.w + w * m.w);
+    }
+    if (mi[p]) {
+      const float si = soft_i[bp + p], v = vi[p];
+      const int a = arg_i[bp + p];
+      const float4 u = mu[a] ? *reinterpret_cast<const float4*>(gu + (bp + a) * D + lane * 4) : zero4;
+      *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = make_float4(v * u.x, v * u.y, v * u.z, v * u.w);
+      *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(si * dai4.x, si * dai4.y, si * dai4.z, si * dai4.w);
+    } else {
+      *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
+    }
   }
   __threadfence();
   __syncthreads();
   // scatter part
   for (int p = warp; p < P; p += 8) {
     const float w = wu[p];
-    if (w != 0.f) {
+    if (w != 0.f && mu[p] && mi[arg_u[bp + p]]) {
       const float4 u = *reinterpret_cast<const float4*>(gu + (bp + p) * D + lane * 4);
       float* d = dgiM + (bp + arg_u[bp + p]) * D + lane * 4;
       atomicAdd(d, w * u.x); atomicAdd(d + 1, w * u.y); atomicAdd(d + 2, w * u.z); atomicAdd(d + 3, w * u.w);
     }
     const float v = vi[p];
-    if (v != 0.f) {
+    if (v != 0.f && mi[p] && mu[arg_i[bp + p]]) {
       const float4 m = *reinterpret_cast<const float4*>(giM + (bp + p) * D + lane * 4);
       float* d = dgu + (bp + arg_i[bp + p]) * D + lane * 4;
       atomicAdd(d, v * m.x); atomicAdd(d + 1, v * m.y); atomicAdd(d + 2, v * m.z); atomicAdd(d + 3, v * m.w);
@@ -271,12 +296,16 @@ extern "C" int umpr_coattn_fwd(const float* gu, const float* gi, const float* gi
 extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i,
                                const float* t_u, const float* t_i, const int32_t* arg_u, const int32_t* arg_i,
                                const float* d_soft_u, const float* d_soft_i, const float* d_atte_u, const float* d_atte_i, int B,
-                               int P, float* dgu, float* dgi, float* dgiM, void* stream) {
+                               int P, const int32_t* cst_u, int S_u, int L_u, const int32_t* cst_i, int S_i, int L_i, float* dgu,
+                               float* dgi, float* dgiM, void* stream) {
   if (B <= 0 || P <= 0) return 0;
-  const size_t sm = sizeof(float) * (2 * ((P + 3) & ~3) + 2 * D + 32);
+  if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_bwd: length tables must be given for both sides or neither");
+  if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
+    return fail_arg("coattn_bwd: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);
+  const size_t sm = sizeof(float) * (2 * ((P + 3) & ~3) + 2 * D + 32) + 2 * ((P + 3) & ~3);
   if (sm > 200 * 1024) return fail_arg("coattn_bwd: P=%d too large", P);
   if (sm > 48 * 1024) cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   coattn_bwd_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(gu, gi, giM, soft_u, soft_i, t_u, t_i, arg_u, arg_i, d_soft_u, d_soft_i,
-                                                         d_atte_u, d_atte_i, P, dgu, dgi, dgiM);
+                                                         d_atte_u, d_atte_i, P, cst_u, S_u, L_u, cst_i, S_i, L_i, dgu, dgi, dgiM);
   return check_launch("coattn_bwd");
 }

@@ -285,6 +285,7 @@ class _CoAttnFn(Function):
     @staticmethod
     def forward(ctx, plans, gu, gi, M):
         ctx.params = (M,)
+        ctx.cst = (None, 0, 0, None, 0, 0)
         gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
         B, P, _ = gu.shape
         dev = gu.device
@@ -305,7 +306,8 @@ class _CoAttnFn(Function):
                     table, n_tiles = pl.snet_table()
                     cst[k] = table.data_ptr() + 4 * (n_tiles + 1)
                     sl[2 * k], sl[2 * k + 1] = pl.N // B, pl.L
-                ctx.keep = plans
+                ctx.cst = (cst[0], sl[0], sl[1], cst[1], sl[2], sl[3])
+                ctx.keep = plans             # keeps the device tables alive until backward
                 valid = float(plans[0].tokens) * float(plans[1].tokens) / B
                 work = (2.0 * valid * D, 2.0 * (plans[0].tokens + plans[1].tokens) * D * 4)
             call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, cst[0], sl[0], sl[1], cst[1], sl[2], sl[3], ptr(scratch),
@@ -331,7 +333,7 @@ class _CoAttnFn(Function):
         dgi = torch.empty_like(gi)
         dgiM = torch.empty_like(gi)
         call("umpr_coattn_bwd", ptr(gu), ptr(gi), ptr(giM), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]),
-             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, ptr(dgu), ptr(dgi), ptr(dgiM),
+             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, *ctx.cst, ptr(dgu), ptr(dgi), ptr(dgiM),
              work=(0.0, 6.0 * B * P * D * 4))
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
         sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
