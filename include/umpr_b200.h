@@ -162,9 +162,13 @@ int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int
                        int32_t* cidx /*(N,KC) arg-max position, -1 if clipped by ReLU*/, int n_ctas, void* stream);
 /* tensor-core form of umpr_cnet_prep + umpr_cnet_conv_fwd (implicit GEMM on tcgen05, weights streamed by bulk copies); maxima
  * that are near-tied (or next to the ReLU threshold) are re-scored in exact fp32 because the arg-max routes the gradient.
- * scratch: 197632 + 16*cap bytes, 16-byte aligned; cap = capacity of the re-scoring worklist */
-int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize, void* scratch,
-                          int cap, float* cfeat, int32_t* cidx, int n_ctas, void* stream);
+ * scratch: 197632 + 16*cap bytes, 16-byte aligned; cap = capacity of the re-scoring worklist.
+ * table (optional, int32 device) = [tile_sent_off (n_tiles+1) | cstart (N+1)], cstart = exclusive prefix sum of (len+2) per sentence,
+ * for inputs produced by ImprovedRnn (rows at or beyond a sentence's length exactly zero): only the valid rows are laid out and
+ * multiplied, the all-zero windows enter the max as the bias.  NULL: every sentence is processed at its full length L. */
+int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize,
+                          const int32_t* table, int n_tiles, void* scratch, int cap, float* cfeat, int32_t* cidx, int n_ctas,
+                          void* stream);
 int umpr_cnet_head_fwd(const float* cfeat, const float* lin_w, const float* lin_b, float threshold, int B, int S, int V, int KC,
                        float* view_p /*(B,S,V)*/, float* final_repr /*(B,V)*/, void* stream);
 int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* view_p, const float* lin_w, const float* d_view_p,

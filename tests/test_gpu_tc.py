@@ -289,3 +289,31 @@ def test_coattention_over_valid_rows_matches_dense(B, S, L, short):
         res.append([o.detach() for o in out] + [torch.where(masks[0], gu.grad, torch.zeros_like(gu.grad)), torch.where(masks[1], gi.grad, torch.zeros_like(gi.grad)), M.grad])
     for a, b, nm in zip(res[1], res[0], ["soft_u", "soft_i", "atte_u", "atte_i", "dgu", "dgi", "dM"]):
         assert_close(a, b, 2e-5, nm)
+
+
+@pytest.mark.parametrize("B,S,L,short", [(128, 20, 20, False), (200, 5, 20, True), (10, 3, 100, False), (6, 2, 3, True)])
+def test_cnet_tail_over_valid_rows_matches_dense(B, S, L, short):
+    """C-Net tail with the pack plan of its input - the tensor-core convolution lays out the valid rows only, the all-zero windows
+    enter the max as the bias - against the same kernels over every position: same pooled views and gradients."""
+    from umpr_b200 import functional as F
+    from umpr_b200.plan import PackPlan
+    torch.manual_seed(B * 3 + L)
+    N, KC, V = B * S, 120, 4
+    lens = torch.randint(1, (min(3, L) if short else L) + 1, (N,))
+    if short:
+        lens[::4] = L
+    plan = PackPlan(lens, L, DEV, tile_rows=128 if N >= 2048 else 32)
+    mask = (torch.arange(L, device=DEV)[None, :] < plan.row_lengths().to(DEV)[:, None]).view(B, S * L, 1)
+    x0 = torch.tanh(torch.randn(B, S * L, 128, device=DEV)) * mask
+    p0 = [torch.randn(KC, 128, 3, device=DEV) * 0.05, torch.randn(KC, device=DEV) * 0.3,      # biases of both signs: the zero windows win often
+          torch.randn(V, KC, device=DEV) * 0.1, torch.randn(V, device=DEV) * 0.1]
+    gv, gf = torch.randn(B, S, V, device=DEV), torch.randn(B, V, device=DEV)
+    res = []
+    for pl in (None, plan):
+        x = x0.clone().requires_grad_(True)
+        p = [t.clone().requires_grad_(True) for t in p0]
+        view_p, final = F.c_net_tail(x, S, L, *p, 0.35, plan=pl)
+        ((view_p * gv).sum() + (final * gf).sum()).backward()
+        res.append([view_p.detach(), final.detach(), torch.where(mask, x.grad, torch.zeros_like(x.grad))] + [t.grad for t in p])
+    for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
+        assert_close(a, b, 1e-6, nm)

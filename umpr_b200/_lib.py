@@ -43,7 +43,7 @@ SIGNATURES = {
     "umpr_snet_bwd_tc": [P, P, I, P, P, P, I, I, P, P, P, I, P],
     "umpr_cnet_prep": [P, I, I, P, P],
     "umpr_cnet_conv_fwd": [P, P, P, I, I, I, P, P, I, P],
-    "umpr_cnet_conv_fwd_tc": [P, P, P, I, I, I, I, P, I, P, P, I, P],
+    "umpr_cnet_conv_fwd_tc": [P, P, P, I, I, I, I, P, I, P, I, P, P, I, P],
     "umpr_cnet_head_fwd": [P, P, P, F, I, I, I, I, P, P, P],
     "umpr_cnet_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
     "umpr_cnet_conv_bwd": [P, P, P, P, I, I, I, P, P, P, I, P],

@@ -1,6 +1,9 @@
 // C-Net convolution on the tensor cores (reference src/model.py:118-120): Conv1d(128 -> K, k=3, pad=1) + ReLU + max over L
 // as an implicit GEMM, persistent CTAs, 3xBF16 split, accumulators in TMEM.
-//   M tile = gs whole sentences, each with one zero guard row before and after (gs*(L+2) <= 128 rows)
+//   M tile = whole sentences, each with one zero guard row before and after.  Without a length table: gs sentences of L+2 rows.
+//            With one (inputs from ImprovedRnn: rows at or beyond a sentence's length are exactly zero, model.py:20): only the
+//            len valid rows plus the two guards are laid out (positions 0..len are computed; every later position is an all-zero
+//            window whose value is exactly the bias and enters the max analytically), so a tile holds ~2.4x more sentences.
 //   K      = 3*128 = 6 blocks of 64: block kb covers tap dt = kb/2, channels (kb%2)*64..+64; the A rows of tap dt are the
 //            x rows shifted by dt-1 (the im2col happens in the loader's addressing, nothing is materialised)
 //   B      = the weights, pre-split once per step into the exact shared-memory image (bf16 hi/lo, SWIZZLE_128B) by
@@ -46,24 +49,35 @@ __global__ void cnet_tc_prep_kernel(const float* __restrict__ w, int KC, unsigne
   }
 }
 
+constexpr int CT_NMETA = 4;
+constexpr int CT_MAXS = 44;              // sentences per tile: each takes at least 3 rows
+struct CtMeta {
+  int s0, ns;
+  int sb[CT_MAXS];                       // tile row of each sentence's leading guard row
+  int len[CT_MAXS];                      // valid rows of each sentence
+  int rowsrc[128];                       // tile row -> global x row, -1 = zero row
+};
+
 __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const float* __restrict__ x, const unsigned char* __restrict__ wimg,
                                                                          const float* __restrict__ bias, int N, int L, int KC, int gs,
+                                                                         const int* __restrict__ tso, const int* __restrict__ cstc, int n_tiles,
                                                                          float* __restrict__ cfeat, int* __restrict__ cidx,
                                                                          int4* __restrict__ worklist, int cap) {
   extern __shared__ unsigned char raw[];
-  __shared__ uint64_t full_bar[CT_NSTAGE], empty_bar[CT_NSTAGE], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[CT_NSTAGE], empty_bar[CT_NSTAGE], acc_full[2], acc_empty[2], m_full[CT_NMETA];
   __shared__ uint32_t tmem_slot;
+  __shared__ CtMeta meta[CT_NMETA];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   float* stg = reinterpret_cast<float*>(base + CT_NSTAGE * CT_STAGE);      // [128][33]
   const float* wnorm = reinterpret_cast<const float*>(wimg + CT_IMG_BYTES);
   int* counter = reinterpret_cast<int*>(const_cast<unsigned char*>(wimg) + CT_IMG_BYTES + 512);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Lg = L + 2;
-  const int n_tiles = (N + gs - 1) / gs;
 
   if (tid == 0) {
     for (int s = 0; s < CT_NSTAGE; ++s) { mbar_init(&full_bar[s], 256); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < CT_NMETA; ++s) mbar_init(&m_full[s], 256);
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(&tmem_slot, 256);
@@ -75,9 +89,28 @@ __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const f
   if (warp < 8) {
     // ------------------------------------------------------------------ loaders
     int it = 0;       // global k-block counter (ring position)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int n0 = tile * gs;
-      const int ns = min(gs, N - n0);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      // tile bookkeeping (slot t % 4: the epilogue of tile t-4 has finished before the ring lets this tile's stages through)
+      CtMeta& m = meta[t % CT_NMETA];
+      if (t >= CT_NMETA) mbar_wait(&empty_bar[it % CT_NSTAGE], ((it / CT_NSTAGE) - 1) & 1);
+      if (tid < 128) m.rowsrc[tid] = -1;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      {
+        int s0, ns;
+        if (tso) { s0 = tso[tile]; ns = tso[tile + 1] - s0; } else { s0 = tile * gs; ns = min(gs, N - s0); }
+        if (tid < ns) {
+          int base, len;
+          if (tso) { const int c0 = cstc[s0]; base = cstc[s0 + tid] - c0; len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2; }
+          else { base = tid * Lg; len = L; }
+          m.sb[tid] = base; m.len[tid] = len;
+          const int g0 = (s0 + tid) * L;
+          for (int l = 0; l < len; ++l) m.rowsrc[base + 1 + l] = g0 + l;
+        }
+        if (tid == 0) { m.s0 = s0; m.ns = ns; }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mbar_arrive(&m_full[t % CT_NMETA]);
 #pragma unroll 1
       for (int kb = 0; kb < CT_KB; ++kb, ++it) {
         const int s = it % CT_NSTAGE;
@@ -93,12 +126,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const f
         for (int i = 0; i < 8; ++i) {
           const int idx = i * 256 + tid, r = idx >> 4, k = (idx & 15) * 4;
           const int rr = r - 1 + dt;                 // tile row whose x feeds output row r at tap dt
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr >= 0) {
-            const int sn = rr / Lg, l = rr - sn * Lg - 1;
-            if (sn < ns && l >= 0 && l < L) v = *reinterpret_cast<const float4*>(x + ((size_t)(n0 + sn) * L + l) * D + c0 + k);
-          }
-          va[i] = v;
+          const int src = (rr >= 0 && rr < 128) ? m.rowsrc[rr] : -1;
+          va[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + (size_t)src * D + c0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -144,8 +173,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const f
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
-      const int n0 = tile * gs;
-      const int ns = min(gs, N - n0);
+      mbar_wait(&m_full[t % CT_NMETA], (t / CT_NMETA) & 1);
+      const CtMeta& m = meta[t % CT_NMETA];
+      const int n0 = m.s0, ns = m.ns;
       mbar_wait(&acc_full[acc], (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -165,10 +195,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) cnet_conv_fwd_tc_kernel(const f
             float best = -INFINITY, second = -INFINITY;
             int arg = -1, arg2 = -1;
             const float bz = bias[c0 + c];
-            for (int l = 0; l < L; ++l) {
-              const float y = stg[(sn * Lg + 1 + l) * CT_STG_LD + c];
+            const int len = m.len[sn];
+            const int np = min(len + 1, L);            // positions whose window touches a valid row
+            const float* col = stg + (m.sb[sn] + 1) * CT_STG_LD + c;
+            for (int l = 0; l < np; ++l) {
+              const float y = col[l * CT_STG_LD];
               if (y > best) { second = best; arg2 = arg; best = y; arg = l; }
               else if (y > second && !(y == best && y == bz)) { second = y; arg2 = l; }   // all-zero windows give exactly the bias: a true tie, first wins
+            }
+            if (np < L) {                              // the remaining positions are all-zero windows: exactly the bias, first one at np
+              if (bz > best) { second = best; arg2 = arg; best = bz; arg = np; }
+              else if (bz > second && !(bz == best)) { second = bz; arg2 = np; }
             }
             const size_t o = (size_t)(n0 + sn) * KC + c0 + c;
             cfeat[o] = fmaxf(best, 0.f);
@@ -232,9 +269,12 @@ __global__ void __launch_bounds__(256) cnet_conv_fix_kernel(const float* __restr
 
 using namespace umpr;
 
-// scratch: 197632 + 16*cap bytes, 16-byte aligned (weight image, filter norms, worklist of near-tied maxima)
+// scratch: 197632 + 16*cap bytes, 16-byte aligned (weight image, filter norms, worklist of near-tied maxima).
+// table (optional) = [tile_sent_off (n_tiles+1) | cstart (N+1)] with cstart the exclusive prefix sum of (len + 2) per sentence
+// (plan.py:cnet_table): sentences tile_sent_off[k] .. tile_sent_off[k+1]-1 form tile k, at most 128 rows including the guards.
 extern "C" int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize,
-                                     void* wimg, int cap, float* cfeat, int32_t* cidx, int n_ctas, void* stream) {
+                                     const int32_t* table, int table_tiles, void* wimg, int cap, float* cfeat, int32_t* cidx,
+                                     int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (ksize != 3) return fail_arg("cnet: kernel_size=%d (only 3 is built)", ksize);
   if (KC < 1 || KC > 128) return fail_arg("cnet: kernel_count=%d must be in [1, 128]", KC);
@@ -245,14 +285,15 @@ extern "C" int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const 
   if (int e = check_launch("cnet_tc_prep")) return e;
   int gs = 128 / (L + 2);
   if (gs > 16) gs = 16;
-  const int n_tiles = (N + gs - 1) / gs;
+  if (table && (table_tiles < 1 || table_tiles > N)) return fail_arg("cnet_conv_fwd_tc: tile table inconsistent (n_tiles=%d, N=%d)", table_tiles, N);
+  const int n_tiles = table ? table_tiles : (N + gs - 1) / gs;
   const int smem = CT_NSTAGE * CT_STAGE + 128 * CT_STG_LD * 4 + 1024;
   cudaError_t e = cudaFuncSetAttribute(cnet_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("cnet_conv_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
   cnet_conv_fwd_tc_kernel<<<grid, CT_THREADS, smem, (cudaStream_t)stream>>>(x, reinterpret_cast<const unsigned char*>(wimg), conv_b, N, L, KC,
-                                                                          gs, cfeat, cidx, reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(wimg) + CT_HDR_BYTES), cap);
+                                                                          gs, table, table ? table + n_tiles + 1 : nullptr, n_tiles, cfeat, cidx, reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(wimg) + CT_HDR_BYTES), cap);
   if (int rc = check_launch("cnet_conv_fwd_tc")) return rc;
   cnet_conv_fix_kernel<<<n_ctas * 2, 256, 0, (cudaStream_t)stream>>>(x, conv_w, conv_b, reinterpret_cast<const int*>(reinterpret_cast<unsigned char*>(wimg) + CT_IMG_BYTES + 512),
                                                                       reinterpret_cast<const int4*>(reinterpret_cast<unsigned char*>(wimg) + CT_HDR_BYTES), cap, L, KC, cfeat, cidx);

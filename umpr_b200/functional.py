@@ -510,7 +510,7 @@ def text_match(atte_u, senti_u, atte_i, senti_i, Wu, Wi):
 # --------------------------------------------------------------------------------------------------------------------
 class _CNetTailFn(Function):
     @staticmethod
-    def forward(ctx, gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
+    def forward(ctx, plan, gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
         ctx.params = (conv_w, conv_b, lin_w, lin_b)
         x = _f32(_chk(gru_repr, "gru_repr"))
         conv_w, conv_b, lin_w, lin_b = _f32(conv_w), _f32(conv_b), _f32(lin_w), _f32(lin_b)
@@ -528,8 +528,14 @@ class _CNetTailFn(Function):
         if TENSOR_CORE_CONV:
             cap = max(4096, N * KC // 8)
             scratch = torch.empty((197632 + 16 * cap) // 4, dtype=torch.float32, device=dev)
-            call("umpr_cnet_conv_fwd_tc", ptr(x), ptr(conv_w), ptr(conv_b), N, L, KC, ks, ptr(scratch), cap, ptr(cfeat), ptr(cidx),
-                 _n_ctas(dev), work=work)
+            table, n_tiles = None, 0
+            if plan is not None and plan.N == N and plan.L == L and L + 2 <= 128:
+                # gru_repr comes out of ImprovedRnn with this plan: rows beyond each sentence's length are exactly zero
+                table, n_tiles = plan.cnet_table()
+                ctx.keep = plan
+                work = (2.0 * (plan.tokens + N) * 3 * D * KC, plan.tokens * D * 4.0)
+            call("umpr_cnet_conv_fwd_tc", ptr(x), ptr(conv_w), ptr(conv_b), N, L, KC, ks, ptr(table), n_tiles, ptr(scratch), cap,
+                 ptr(cfeat), ptr(cidx), _n_ctas(dev), work=work)
         else:
             wt = torch.empty(3 * D * 128, dtype=torch.float32, device=dev)
             call("umpr_cnet_prep", ptr(conv_w), KC, ks, ptr(wt))
@@ -558,12 +564,13 @@ class _CNetTailFn(Function):
         wt = torch.empty(KC * 3 * D, dtype=torch.float32, device=dev)
         call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
              work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
-        return dx, None, None, rets[0], rets[1], rets[2], rets[3], None
+        return None, dx, None, None, rets[0], rets[1], rets[2], rets[3], None
 
 
-def c_net_tail(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold):
-    """→ view_p (B,S,V), final_repr (B,V)."""
-    return _CNetTailFn.apply(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold)
+def c_net_tail(gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold, plan=None):
+    """→ view_p (B,S,V), final_repr (B,V).  ``plan``: the PackPlan of the ImprovedRnn call that produced ``gru_repr`` (rows beyond
+    each sentence's length exactly zero) - the tensor-core convolution then lays out and multiplies the valid rows only."""
+    return _CNetTailFn.apply(plan, gru_repr, sent_count, sent_length, conv_w, conv_b, lin_w, lin_b, threshold)
 
 
 # --------------------------------------------------------------------------------------------------------------------

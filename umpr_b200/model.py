@@ -155,7 +155,7 @@ class CNet(nn.Module):
             gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
             gru_repr._umpr_plan = pk.plan
             view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
-                                              self.linear[0].weight, self.linear[0].bias, self.threshold)
+                                              self.linear[0].weight, self.linear[0].bias, self.threshold, plan=pk.plan)
             res.append((gru_repr, view_p, final_repr))
         return res
 

@@ -197,6 +197,32 @@ class PackPlan:
             self._snet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
         return self._snet_np
 
+    def cnet_table(self):
+        """Tile table of the tensor-core C-Net convolution (csrc/cnet_tc.cu): like ``snet_table`` with every sentence taking
+        ``len + 2`` tile rows (a zero guard row before and after its valid rows).  → (device int32 ``[tile_sent_off | cstart]``,
+        n_tiles); cached."""
+        if getattr(self, "_cnet", None) is None:
+            host, nt = self._cnet_host()
+            self._cnet = (upload_int32(host, self.device), nt)
+        return self._cnet
+
+    def _cnet_host(self):
+        if getattr(self, "_cnet_np", None) is None:
+            import numpy as np
+            if self.L + 2 > 128:
+                raise RuntimeError(f"umpr_b200: C-Net sentence length {self.L} exceeds 126")
+            n, rp = self.N, self.n_tiles * self.R
+            h = self._host_np
+            rows = np.empty(n, dtype=np.int64)
+            rows[h[rp:rp + n]] = h[2 * rp:2 * rp + n].astype(np.int64) + 2
+            cstart = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(rows, out=cstart[1:])
+            tid = np.unique(cstart[:-1] // (129 - (self.L + 2)), return_inverse=True)[1]
+            nt = int(tid[-1]) + 1
+            tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
+            self._cnet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
+        return self._cnet_np
+
     def row_lengths(self) -> torch.Tensor:
         """Effective length of every OUTPUT row: len[unsorted_indices[n]] (the zero pattern of the result)."""
         return self.lengths[self.unsorted_indices]

@@ -94,7 +94,9 @@ def prepare_batch(batch, device):
         if lens.numel() and ids.dim() == 3:
             lens._umpr_plan = PackPlan(lens.reshape(-1), ids.shape[2], device, upload=False)
             if lens._umpr_plan.R == 128 and ids.shape[2] <= 128:
-                lens._umpr_plan._snet_host()                      # S-Net tile table (numpy; uploaded by the consumer)
+                lens._umpr_plan._snet_host()                      # S-Net / C-Net tile tables (numpy; uploaded by the consumer)
+                if ids.shape[2] <= 126:
+                    lens._umpr_plan._cnet_host()
     return batch
 
 
