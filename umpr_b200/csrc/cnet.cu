@@ -253,7 +253,7 @@ __global__ void cnet_wt_kernel(const float* __restrict__ w, int KC, float* __res
 constexpr int SW_WARPS = 8;
 __global__ void __launch_bounds__(SW_WARPS * 32, 4) cnet_conv_bwd_dx_sweep_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
                                                                                  const float* __restrict__ wt, int N, int L, int KC,
-                                                                                 float* __restrict__ dx) {
+                                                                                 const int* __restrict__ cst, float* __restrict__ dx) {
   __shared__ float2 s_sorted[SW_WARPS][CKP];     // (gradient, position | filter << 16) in sweep order
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -288,11 +288,14 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) cnet_conv_bwd_dx_sweep_kerne
       if (t[q] >= 0) s_sorted[warp][rank[q]] = make_float2(g[q], __int_as_float(t[q] | ((lane + 32 * q) << 16)));
     __syncwarp();
     float* orow = dx + (size_t)n * L * D + lane * 4;
+    // with a length table only the rows below the sentence's length are written (the others are never read: model.py:18)
+    const int len = cst ? min(L, cst[n + 1] - cst[n]) : L;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;        // rows cur-1, cur, cur+1
     int cur = 0;
     for (int i = 0; i < nvalid; ++i) {
       const float2 e = s_sorted[warp][i];
       const int pk = __float_as_int(e.y), p = pk & 0xffff, kf = pk >> 16;
+      if (p > len) break;                      // sorted by position: everything from here on lands on rows >= len
       while (cur < p) {                        // slide the window: row cur-1 is complete
         if (cur >= 1) *reinterpret_cast<float4*>(orow + (size_t)(cur - 1) * D) = a0;
         a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f); ++cur;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) cnet_conv_bwd_dx_sweep_kerne
       a1.x = fmaf(e.x, w1.x, a1.x); a1.y = fmaf(e.x, w1.y, a1.y); a1.z = fmaf(e.x, w1.z, a1.z); a1.w = fmaf(e.x, w1.w, a1.w);
       a2.x = fmaf(e.x, w2.x, a2.x); a2.y = fmaf(e.x, w2.y, a2.y); a2.z = fmaf(e.x, w2.z, a2.z); a2.w = fmaf(e.x, w2.w, a2.w);
     }
-    while (cur <= L) {                         // flush: every row of dx is written exactly once (zeros where nothing landed)
+    while (cur <= len) {                       // flush: every (valid) row of dx is written exactly once (zeros where nothing landed)
       if (cur >= 1) *reinterpret_cast<float4*>(orow + (size_t)(cur - 1) * D) = a0;
       a0 = a1; a1 = a2; a2 = make_float4(0.f, 0.f, 0.f, 0.f); ++cur;
     }
@@ -312,65 +315,87 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 4) cnet_conv_bwd_dx_sweep_kerne
 }
 
 // dW[kf][c][dt] += sum_n g[n][kf] x[n][arg + dt - 1][c].  Thread (q, c) accumulates its 32x3 slice in registers.
+// G sentences per pipeline stage (one barrier pair and one cp.async group per G sentences); with a length table only the rows
+// below each sentence's length are staged - taps that fall on a zero row are skipped.
 __global__ void __launch_bounds__(512, 1) cnet_conv_bwd_dw_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
-                                                                  const int* __restrict__ cidx, int N, int L, int KC,
-                                                                  float* __restrict__ dw) {
+                                                                  const int* __restrict__ cidx, int N, int L, int KC, int G,
+                                                                  const int* __restrict__ cst, float* __restrict__ dw) {
   extern __shared__ __align__(16) float smem[];
-  // two stages of {sentence [(L+2)][128] with zero guard rows, gradients [128], arg-max positions [128]}: the next sentence
-  // streams in (cp.async) while the current one is consumed
-  const int stage_f = (L + 2) * D + 2 * CKP;
-  const int tid = threadIdx.x, q = tid >> 7, c = tid & 127;
-  float acc[32][CK];
+  const int sent_f = L * D + 2 * CKP;          // per sentence: rows [L][128], gradients [128], arg-max positions [128]
+  const int stage_f = G * sent_f;
+  // thread = (warp w: filters 8w..8w+7, lane: channels 4*lane..+3): the filter loop is warp-uniform (no divergence on the
+  // zero-gradient test), every tap is one conflict-free 128-bit shared-memory load feeding four FMAs
+  const int tid = threadIdx.x, fg = tid >> 5, c4 = (tid & 31) * 4;
+  const int n_groups = (N + G - 1) / G;
+  float4 acc[8][CK];
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int dt = 0; dt < CK; ++dt) acc[i][dt] = 0.f;
-  for (int s2 = 0; s2 < 2; ++s2)
-    for (int idx = tid; idx < D; idx += 512) { smem[s2 * stage_f + idx] = 0.f; smem[s2 * stage_f + (L + 1) * D + idx] = 0.f; }
-  auto issue = [&](int n, int st) {
-    float* xs = smem + st * stage_f;
-    const float4* src = reinterpret_cast<const float4*>(x + (size_t)n * L * D);
-    for (int idx = tid; idx < L * (D / 4); idx += 512) cp_async16(&xs[D + idx * 4], src + idx);
-    if (tid < CKP) {
-      float* gsm = xs + (L + 2) * D;
-      int* tsm = reinterpret_cast<int*>(gsm + CKP);
-      if (tid < KC) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&gsm[tid])), "l"(dcfeat + (size_t)n * KC + tid));
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&tsm[tid])), "l"(cidx + (size_t)n * KC + tid));
-      } else {
-        gsm[tid] = 0.f; tsm[tid] = -1;
+    for (int dt = 0; dt < CK; ++dt) acc[i][dt] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto sent_len = [&](int n) { return cst ? min(L, cst[n + 1] - cst[n]) : L; };
+  auto issue = [&](int grp, int st) {
+    for (int j = 0; j < G; ++j) {
+      const int n = grp * G + j;
+      if (n >= N) break;
+      float* xs = smem + st * stage_f + j * sent_f;
+      const int len = sent_len(n);
+      const float4* src = reinterpret_cast<const float4*>(x + (size_t)n * L * D);
+      for (int idx = tid; idx < len * (D / 4); idx += 512) cp_async16(&xs[idx * 4], src + idx);
+      if (tid < CKP) {
+        float* gsm = xs + L * D;
+        int* tsm = reinterpret_cast<int*>(gsm + CKP);
+        if (tid < KC) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&gsm[tid])), "l"(dcfeat + (size_t)n * KC + tid));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&tsm[tid])), "l"(cidx + (size_t)n * KC + tid));
+        } else {
+          gsm[tid] = 0.f; tsm[tid] = -1;
+        }
       }
     }
     cp_async_commit();
   };
   int it = 0;
-  if ((int)blockIdx.x < N) issue(blockIdx.x, 0);
-  for (int n = blockIdx.x; n < N; n += gridDim.x, ++it) {
+  if ((int)blockIdx.x < n_groups) issue(blockIdx.x, 0);
+  for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++it) {
     const int st = it & 1;
-    const int nn = n + gridDim.x;
-    if (nn < N) { issue(nn, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+    const int ng = grp + gridDim.x;
+    if (ng < n_groups) { issue(ng, st ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
     else cp_async_wait_all();
     __syncthreads();                         // stage st has landed for every thread
-    const float* xs = smem + st * stage_f;
-    const float* gsm = xs + (L + 2) * D;
-    const int* tsm = reinterpret_cast<const int*>(gsm + CKP);
+    for (int j = 0; j < G; ++j) {
+      const int n = grp * G + j;
+      if (n >= N) break;
+      const float* xs = smem + st * stage_f + j * sent_f;
+      const float* gsm = xs + L * D;
+      const int* tsm = reinterpret_cast<const int*>(gsm + CKP);
+      const int len = sent_len(n);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float g = gsm[q * 32 + i];
-      const int t = tsm[q * 32 + i];
-      if (g != 0.f && t >= 0) {
+      for (int i = 0; i < 8; ++i) {
+        const float g = gsm[fg * 8 + i];
+        const int t = tsm[fg * 8 + i];
+        if (g != 0.f && t >= 0) {
 #pragma unroll
-        for (int dt = 0; dt < CK; ++dt) acc[i][dt] += g * xs[(t + dt) * D + c];
+          for (int dt = 0; dt < CK; ++dt) {
+            const int row = t + dt - 1;
+            if (row >= 0 && row < len) {
+              const float4 v = *reinterpret_cast<const float4*>(&xs[row * D + c4]);
+              acc[i][dt].x += g * v.x; acc[i][dt].y += g * v.y; acc[i][dt].z += g * v.z; acc[i][dt].w += g * v.w;
+            }
+          }
+        }
       }
     }
     __syncthreads();                         // stage st may be refilled by the next iteration's prefetch
   }
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int kf = q * 32 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int kf = fg * 8 + i;
     if (kf < KC) {
 #pragma unroll
-      for (int dt = 0; dt < CK; ++dt) atomicAdd(&dw[((size_t)kf * D + c) * CK + dt], acc[i][dt]);
+      for (int dt = 0; dt < CK; ++dt) {
+        float* d = dw + ((size_t)kf * D + c4) * CK + dt;
+        atomicAdd(d, acc[i][dt].x); atomicAdd(d + CK, acc[i][dt].y); atomicAdd(d + 2 * CK, acc[i][dt].z); atomicAdd(d + 3 * CK, acc[i][dt].w);
+      }
     }
   }
 }
@@ -421,11 +446,17 @@ extern "C" int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const
   return check_launch("cnet_head_bwd");
 }
 
+// cst (optional): exclusive prefix sum (N+1, int32, device) of the sentence lengths for an x produced by ImprovedRnn - rows at or
+// beyond a sentence's length are exactly zero, are not staged, and their dx rows are not written.
 extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L,
-                                  int KC, float* wt_scratch, float* dx, float* d_conv_w, int n_ctas, void* stream) {
+                                  int KC, const int32_t* cst, float* wt_scratch, float* dx, float* d_conv_w, int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
-  const size_t sm = 2 * (sizeof(float) * ((L + 2) * D + CKP) + sizeof(int) * CKP);
+  const size_t sent_b = sizeof(float) * ((size_t)L * D + 2 * CKP);
+  int G = (int)((90 * 1024) / sent_b);
+  if (G > 2) G = 2;
+  if (G < 1) G = 1;
+  const size_t sm = 2 * G * sent_b;
   if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd: L=%d too large", L);
   const int grid = n_ctas > 0 && n_ctas < N ? n_ctas : N;
   const size_t sm4 = sizeof(float) * (4 * (L + 2) * D + CKP) + sizeof(int) * CKP;
@@ -434,7 +465,7 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
     cnet_wt_kernel<<<(KC * CK * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, wt_scratch);
     const int g4 = (N + SW_WARPS - 1) / SW_WARPS;
     const int want = 8 * (n_ctas > 0 ? n_ctas : 148);
-    cnet_conv_bwd_dx_sweep_kernel<<<g4 < want ? g4 : want, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(dcfeat, cidx, wt_scratch, N, L, KC, dx);
+    cnet_conv_bwd_dx_sweep_kernel<<<g4 < want ? g4 : want, SW_WARPS * 32, 0, (cudaStream_t)stream>>>(dcfeat, cidx, wt_scratch, N, L, KC, cst, dx);
   } else if (sm4 <= 200 * 1024) {
     cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
     cnet_conv_bwd_dx_kernel<4><<<grid, 512, sm4, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
@@ -444,6 +475,8 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
   }
   if (int e = check_launch("cnet_conv_bwd_dx")) return e;
   cudaFuncSetAttribute(cnet_conv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  cnet_conv_bwd_dw_kernel<<<grid, 512, sm, (cudaStream_t)stream>>>(x, dcfeat, cidx, N, L, KC, d_conv_w);
+  const int n_groups = (N + G - 1) / G;
+  const int grid_w = n_ctas > 0 && n_ctas < n_groups ? n_ctas : n_groups;
+  cnet_conv_bwd_dw_kernel<<<grid_w, 512, sm, (cudaStream_t)stream>>>(x, dcfeat, cidx, N, L, KC, G, cst, d_conv_w);
   return check_launch("cnet_conv_bwd_dw");
 }

@@ -529,6 +529,7 @@ class _CNetTailFn(Function):
             cap = max(4096, N * KC // 8)
             scratch = torch.empty((197632 + 16 * cap) // 4, dtype=torch.float32, device=dev)
             table, n_tiles = None, 0
+            ctx.keep = None
             if plan is not None and plan.N == N and plan.L == L and L + 2 <= 128:
                 # gru_repr comes out of ImprovedRnn with this plan: rows beyond each sentence's length are exactly zero
                 table, n_tiles = plan.cnet_table()
@@ -560,9 +561,14 @@ class _CNetTailFn(Function):
         (d_conv_w, d_conv_b, d_lin_w, d_lin_b), rets = _sinks(ctx.params)
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
-        dx = torch.empty_like(x)
+        dx = torch.empty_like(x)        # with a plan: rows beyond a sentence's length stay unwritten (never read, model.py:18)
         wt = torch.empty(KC * 3 * D, dtype=torch.float32, device=dev)
-        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
+        cst = None
+        plan = getattr(ctx, "keep", None)
+        if plan is not None:
+            table, n_tiles = plan.snet_table()
+            cst = table.data_ptr() + 4 * (n_tiles + 1)
+        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
              work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
         return None, dx, None, None, rets[0], rets[1], rets[2], rets[3], None
 
