@@ -30,15 +30,18 @@ UNIT = "samples/s"
 TENSOR_BOUND = {"umpr_gru_inproj", "umpr_gru_inproj_tc", "umpr_gru_recurrence_fwd", "umpr_gru_recurrence_bwd", "umpr_gru_wgrad",
                 "umpr_gru_wgrad_tc", "umpr_gru_fwd_tc", "umpr_gru_bwd_tc", "umpr_sgemm", "umpr_tc_gemm_ws",
                 "umpr_tc_gemm_nt", "umpr_coattn_fwd", "umpr_coattn_fwd_tc", "umpr_snet_fwd", "umpr_snet_bwd", "umpr_cnet_conv_fwd",
-                "umpr_cnet_conv_fwd_tc"}
+                "umpr_cnet_conv_fwd_tc", "umpr_snet_fwd_tc", "umpr_snet_bwd_tc", "umpr_tc_gemm_tn"}
 # arithmetic each entry point runs in (everything is fp32 in and out; "3xBF16" = fp32 operands split into bf16 hi+lo, fp32 accumulate)
 MATH = {"umpr_gru_fwd_tc": "tcgen05 kind::f16, 3xBF16 split, fp32 accumulation in TMEM; gates fp32 (ex2/rcp approx)",
         "umpr_gru_bwd_tc": "tcgen05 (carry A operand in tensor memory; weight gradients accumulated in TMEM), 3xBF16; element-wise fp32",
         "umpr_tc_gemm_ws": "tcgen05 3xBF16", "umpr_tc_gemm_nt": "tcgen05 3xBF16", "umpr_cnet_conv_fwd_tc": "tcgen05 3xBF16 + exact fp32 re-scoring of near-ties",
-        "umpr_coattn_fwd_tc": "tcgen05 3xBF16 + exact fp32 re-scoring of near-ties"}
+        "umpr_coattn_fwd_tc": "tcgen05 3xBF16 over the valid rows only + exact fp32 re-scoring of near-ties",
+        "umpr_snet_fwd_tc": "tcgen05 3xBF16 over the valid rows only; tanh / softmax fp32",
+        "umpr_snet_bwd_tc": "tcgen05 3xBF16 (scores recomputed; dx and dMs^T products, dMs accumulated in TMEM); element-wise fp32",
+        "umpr_tc_gemm_tn": "tcgen05 3xBF16, both operands MN-major"}
 # the kernels BASELINE.json's north_star names: reported next to the dominant one
 NAMED = ["umpr_gru_fwd_tc", "umpr_gru_bwd_tc", "umpr_gather_pack_tc", "umpr_gather_pack", "umpr_coattn_fwd_tc", "umpr_coattn_fwd", "umpr_coattn_bwd",
-         "umpr_snet_fwd", "umpr_snet_bwd"]
+         "umpr_snet_fwd_tc", "umpr_snet_bwd_tc", "umpr_snet_fwd", "umpr_snet_bwd"]
 
 
 def load_peaks():

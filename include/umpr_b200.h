@@ -174,11 +174,14 @@ int umpr_cnet_head_fwd(const float* cfeat, const float* lin_w, const float* lin_
 int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const float* view_p, const float* lin_w, const float* d_view_p,
                        const float* d_final, int B, int S, int V, int KC, float* dcfeat /*(N,KC) written*/, float* d_lin_w /*(+=)*/,
                        float* d_lin_b /*(+=)*/, float* d_conv_b /*(+=)*/, void* stream);
-/* cst (optional): exclusive prefix sum (N+1) of the sentence lengths for an x produced by ImprovedRnn (rows at or beyond a sentence's
+/* Backward of conv + ReLU + max (model.py:118-120): sparse, one arg-max position per (sentence, filter).
+ * cst (optional): exclusive prefix sum (N+1) of the sentence lengths for an x produced by ImprovedRnn (rows at or beyond a sentence's
  * length exactly zero): those rows are not staged and their dx rows are not written.  NULL: all rows. */
-int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC,
-                       const int32_t* cst, float* wt_scratch /*KC*3*128 floats (tap-major weight copy), or NULL for the scatter kernel*/,
-                       float* dx /*(N,L,128): rows below each length written*/, float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
+int umpr_cnet_conv_bwd_dx(const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC, const int32_t* cst,
+                          float* wt_scratch /*KC*3*128 floats (tap-major weight copy), or NULL for the scatter kernel*/,
+                          float* dx /*(N,L,128): rows below each length written*/, int n_ctas, void* stream);
+int umpr_cnet_conv_bwd_dw(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* cst,
+                          float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
 
 /* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */
 int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b, float eps,

@@ -448,16 +448,10 @@ extern "C" int umpr_cnet_head_bwd(const float* cfeat, const int32_t* cidx, const
 
 // cst (optional): exclusive prefix sum (N+1, int32, device) of the sentence lengths for an x produced by ImprovedRnn - rows at or
 // beyond a sentence's length are exactly zero, are not staged, and their dx rows are not written.
-extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L,
-                                  int KC, const int32_t* cst, float* wt_scratch, float* dx, float* d_conv_w, int n_ctas, void* stream) {
+extern "C" int umpr_cnet_conv_bwd_dx(const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC,
+                                     const int32_t* cst, float* wt_scratch, float* dx, int n_ctas, void* stream) {
   if (N <= 0) return 0;
   if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
-  const size_t sent_b = sizeof(float) * ((size_t)L * D + 2 * CKP);
-  int G = (int)((90 * 1024) / sent_b);
-  if (G > 2) G = 2;
-  if (G < 1) G = 1;
-  const size_t sm = 2 * G * sent_b;
-  if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd: L=%d too large", L);
   const int grid = n_ctas > 0 && n_ctas < N ? n_ctas : N;
   const size_t sm4 = sizeof(float) * (4 * (L + 2) * D + CKP) + sizeof(int) * CKP;
   const size_t sm2 = sizeof(float) * (2 * (L + 2) * D + CKP) + sizeof(int) * CKP;
@@ -469,11 +463,25 @@ extern "C" int umpr_cnet_conv_bwd(const float* x, const float* dcfeat, const int
   } else if (sm4 <= 200 * 1024) {
     cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
     cnet_conv_bwd_dx_kernel<4><<<grid, 512, sm4, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
-  } else {
+  } else if (sm2 <= 200 * 1024) {
     cudaFuncSetAttribute(cnet_conv_bwd_dx_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
     cnet_conv_bwd_dx_kernel<2><<<grid, 256, sm2, (cudaStream_t)stream>>>(dcfeat, cidx, conv_w, N, L, KC, dx);
+  } else {
+    return fail_arg("cnet_conv_bwd_dx: L=%d too large", L);
   }
-  if (int e = check_launch("cnet_conv_bwd_dx")) return e;
+  return check_launch("cnet_conv_bwd_dx");
+}
+
+extern "C" int umpr_cnet_conv_bwd_dw(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* cst,
+                                     float* d_conv_w, int n_ctas, void* stream) {
+  if (N <= 0) return 0;
+  if (KC < 1 || KC > CKP) return fail_arg("cnet: kernel_count=%d", KC);
+  const size_t sent_b = sizeof(float) * ((size_t)L * D + 2 * CKP);
+  int G = (int)((90 * 1024) / sent_b);
+  if (G > 2) G = 2;
+  if (G < 1) G = 1;
+  const size_t sm = 2 * G * sent_b;
+  if (sm > 200 * 1024) return fail_arg("cnet_conv_bwd_dw: L=%d too large", L);
   cudaFuncSetAttribute(cnet_conv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   const int n_groups = (N + G - 1) / G;
   const int grid_w = n_ctas > 0 && n_ctas < n_groups ? n_ctas : n_groups;

@@ -41,12 +41,15 @@ __global__ void cnet_tc_prep_kernel(const float* __restrict__ w, int KC, unsigne
   }
   unsigned char* img = wimg + (size_t)kb * 2 * CT_TILE;
   store_split4(img, img + CT_TILE, n, k, make_float4(t[0], t[1], t[2], t[3]));
-  if (idx < 128) {          // |W_kf| for the near-tie tolerance; thread 0 also resets the worklist counter
+  // |W_kf| for the near-tie tolerance: one warp per filter; thread 0 also resets the worklist counter
+  const int f = idx >> 5, lane = idx & 31;
+  if (f < 128) {
     float a = 0.f;
-    if (idx < KC) for (int e = 0; e < D * 3; ++e) { const float v = w[(size_t)idx * D * 3 + e]; a += v * v; }
-    reinterpret_cast<float*>(wimg + CT_IMG_BYTES)[idx] = sqrtf(a);
-    if (idx == 0) *reinterpret_cast<int*>(wimg + CT_IMG_BYTES + 512) = 0;
+    if (f < KC) for (int e = lane; e < D * 3; e += 32) { const float v = w[(size_t)f * D * 3 + e]; a += v * v; }
+    a = warp_sum(a);
+    if (lane == 0) reinterpret_cast<float*>(wimg + CT_IMG_BYTES)[f] = sqrtf(a);
   }
+  if (idx == 0) *reinterpret_cast<int*>(wimg + CT_IMG_BYTES + 512) = 0;
 }
 
 constexpr int CT_NMETA = 4;

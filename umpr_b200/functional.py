@@ -568,8 +568,11 @@ class _CNetTailFn(Function):
         if plan is not None:
             table, n_tiles = plan.snet_table()
             cst = table.data_ptr() + 4 * (n_tiles + 1)
-        call("umpr_cnet_conv_bwd", ptr(x), ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), ptr(d_conv_w), _n_ctas(dev),
-             work=(4.0 * N * KC * 3 * D, 2.0 * N * L * D * 4))
+        rows = plan.tokens if plan is not None else N * L
+        call("umpr_cnet_conv_bwd_dx", ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), _n_ctas(dev),
+             work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
+        call("umpr_cnet_conv_bwd_dw", ptr(x), ptr(dcfeat), ptr(cidx), N, L, KC, cst, ptr(d_conv_w), _n_ctas(dev),
+             work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
         return None, dx, None, None, rets[0], rets[1], rets[2], rets[3], None
 
 
