@@ -105,9 +105,11 @@ int umpr_tc_gemm_nt(const float* A, long lda, const float* B, long ldb, float* C
                     const float* bias, int act, int b_kn /* B stored [K][N] instead of [N][K] */, void* stream);
 /* same contract as umpr_gru_inproj, on the tensor cores: one GEMM over every packed token (model.py:19, input half) */
 int umpr_gru_inproj_tc(const float* xp, const float* const* w, int n_slabs, int R, int E, float* G, int n_ctas, void* stream);
-/* persistent weight-stationary form of umpr_tc_gemm_nt for N <= 128, K <= 128 (B stays in shared memory, A streams) */
+/* persistent weight-stationary form of umpr_tc_gemm_nt for N <= 128, K <= 128 (B stays in shared memory, A streams).
+ * table (optional) = [tile_sent_off (n_row_tiles+1) | cstart (M/L+1)] for an A whose rows are sentences of L positions with
+ * exactly-zero rows at and beyond each sentence's length: only the valid rows are read and written, the others left untouched. */
 int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K, int accumulate,
-                    const float* bias, int act, int b_kn, int n_ctas, void* stream);
+                    const float* bias, int act, int b_kn, const int32_t* table, int n_row_tiles, int L, int n_ctas, void* stream);
 
 /* reduction GEMM over a huge K with both operands row-major in k ("TN"): C[m][n] (+=) sum_k A[k*lda+m] * B[k*ldb+n], M, N <= 128.
  * dM = gi^T · dgiM of the co-attention backward (model.py:50) runs here.  C must be initialised (atomic accumulation). */

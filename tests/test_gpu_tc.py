@@ -53,7 +53,7 @@ def test_tc_gemm_weight_stationary(M, N, K, b_kn, ctas):
     bias = torch.randn(N, device=DEV)
     C = torch.randn(M, ldc, device=DEV) * 0.1
     C0 = C.clone()
-    call("umpr_tc_gemm_ws", ptr(A), lda, ptr(B), B.shape[1], ptr(C), ldc, M, N, K, 1, ptr(bias), 0, b_kn, ctas)
+    call("umpr_tc_gemm_ws", ptr(A), lda, ptr(B), B.shape[1], ptr(C), ldc, M, N, K, 1, ptr(bias), 0, b_kn, None, 0, 0, ctas)
     Bm = B.double() if b_kn else B.double().t()
     assert_close(C[:, :N], C0[:, :N].double() + A[:, :K].double() @ Bm + bias.double(), 2e-5, "tc_gemm_ws")
 
@@ -317,3 +317,25 @@ def test_cnet_tail_over_valid_rows_matches_dense(B, S, L, short):
         res.append([view_p.detach(), final.detach(), torch.where(mask, x.grad, torch.zeros_like(x.grad))] + [t.grad for t in p])
     for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
         assert_close(a, b, 1e-6, nm)
+
+
+@pytest.mark.parametrize("Nsent,L,accumulate,ctas", [(3000, 20, 0, 148), (3000, 20, 1, 148), (5000, 7, 1, 5), (300, 128, 0, 148)])
+def test_tc_gemm_weight_stationary_over_valid_rows(Nsent, L, accumulate, ctas):
+    """umpr_tc_gemm_ws with a sentence-length table: the rows below each sentence's length equal the dense product, every other
+    row of C is left untouched."""
+    from umpr_b200._lib import call, ptr
+    from umpr_b200.plan import PackPlan
+    torch.manual_seed(Nsent + L)
+    lens = torch.randint(1, L + 1, (Nsent,))
+    plan = PackPlan(lens, L, DEV, tile_rows=128)
+    table, n_tiles = plan.snet_table()
+    valid = (torch.arange(L, device=DEV)[None, :] < plan.row_lengths().to(DEV)[:, None]).reshape(-1, 1)
+    M = Nsent * L
+    A = torch.randn(M, 128, device=DEV) * 0.3 * valid
+    W = torch.randn(128, 128, device=DEV) * 0.1
+    C0 = torch.randn(M, 128, device=DEV)
+    C = C0.clone()
+    call("umpr_tc_gemm_ws", ptr(A), 128, ptr(W), 128, ptr(C), 128, M, 128, 128, accumulate, None, 0, 0, ptr(table), n_tiles, L, ctas)
+    ref = (A.double() @ W.double().t() + (C0.double() if accumulate else 0)).float()
+    assert_close(torch.where(valid, C, torch.zeros_like(C)), torch.where(valid, ref, torch.zeros_like(ref)), 2e-5, "valid rows")
+    assert torch.equal(torch.where(valid, torch.zeros_like(C), C), torch.where(valid, torch.zeros_like(C), C0)), "padded rows must stay untouched"

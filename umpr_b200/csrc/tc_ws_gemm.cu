@@ -25,7 +25,13 @@ struct WsArgs {
   const float* bias;
   const float* w_ih[2]; const float* b_ih[2]; const float* b_hh[2];
   int E, R;
+  // valid-row mode (MODE 0): tiles of whole consecutive sentences, <= 128 valid rows each (plan.py:snet_table); row r of sentence n is
+  // global row n*L + r.  tso == NULL: plain 128-row tiles of all M rows
+  const int* tso; const int* cst; int L, n_row_tiles;
 };
+
+constexpr int WS_NMETA = 8;      // deeper than stages + accumulators: the slot of tile it-8 is free for every NSTAGE
+struct WsMeta { int rows; int rowmap[128]; };
 
 template <int BN, int KB, int NSTAGE> struct WsSmem {
   static constexpr int B_BYTES = KB * 2 * BN * 128;            // [kb][hi|lo][BN][128 B]
@@ -37,8 +43,9 @@ template <int BN, int KB, int NSTAGE> struct WsSmem {
 template <int BN, int KB, int NSTAGE, int MODE>
 __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs a) {
   extern __shared__ unsigned char raw[];
-  __shared__ uint64_t a_full[NSTAGE], a_empty[NSTAGE], acc_full[2], acc_empty[2];
+  __shared__ uint64_t a_full[NSTAGE], a_empty[NSTAGE], acc_full[2], acc_empty[2], m_full[WS_NMETA];
   __shared__ uint32_t tmem_slot;
+  __shared__ WsMeta meta[MODE == 0 ? WS_NMETA : 1];
   using SM = WsSmem<BN, KB, NSTAGE>;
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   unsigned char* bsm = base;
@@ -47,11 +54,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
   constexpr uint32_t TCOLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  const int n_tiles = (a.M + 127) / 128;
+  const bool by_rows = MODE == 0 && a.tso != nullptr;
+  const int n_tiles = by_rows ? a.n_row_tiles : (a.M + 127) / 128;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < WS_NMETA; ++s) mbar_init(&m_full[s], 128);
     mbar_fence_init();
   }
   if (warp == 4) tmem_alloc(&tmem_slot, TCOLS);
@@ -90,6 +99,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       if (it >= NSTAGE) mbar_wait(&a_empty[s], ((it / NSTAGE) - 1) & 1);
       unsigned char* st = asm_ + s * SM::A_STAGE;
       const int m0 = tile * 128;
+      const WsMeta& mt = meta[MODE == 0 ? it % WS_NMETA : 0];
+      int rows = 128;
+      if (by_rows) {
+        // slot it % 8 is free: the ring wait above implies the epilogue of tile it-5 has finished (it arrives acc_empty last)
+        WsMeta& mw = meta[MODE == 0 ? it % WS_NMETA : 0];
+        const int s0 = a.tso[tile], ns = a.tso[tile + 1] - s0, c0 = a.cst[s0];
+        if (tid < ns) {
+          const int b = a.cst[s0 + tid] - c0, e = a.cst[s0 + tid + 1] - c0, g0 = (s0 + tid) * a.L - b;
+          for (int r = b; r < e; ++r) mw.rowmap[r] = g0 + r;
+        }
+        rows = a.cst[s0 + ns] - c0;
+        if (tid == 0) mw.rows = rows;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 #pragma unroll 1
       for (int kb = 0; kb < KB; ++kb) {
         unsigned char* a_hi = st + kb * 2 * 128 * 128, *a_lo = a_hi + 128 * 128;
@@ -97,7 +120,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
-          const int m = m0 + r;
+          const int m = by_rows ? (r < rows ? mt.rowmap[r] : a.M) : m0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (m < a.M) {
             const float* p = a.A + (long)m * a.lda + k;
@@ -118,6 +141,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       }
       fence_async_smem();
       mbar_arrive(&a_full[s]);
+      if (by_rows) mbar_arrive(&m_full[it % WS_NMETA]);
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
@@ -157,6 +181,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       const int acc = it & 1;
       const int m0 = tile * 128 + q * 32;
       const int c4 = (lane & 7) * 4;
+      const WsMeta& mt = meta[MODE == 0 ? it % WS_NMETA : 0];
+      if (by_rows) mbar_wait(&m_full[it % WS_NMETA], (it / WS_NMETA) & 1);
+      // global row of tile row rr (a.M = none)
+      auto grow = [&](int rr) { return by_rows ? (q * 32 + rr < mt.rows ? mt.rowmap[q * 32 + rr] : a.M) : m0 + rr; };
       // accumulate mode: the C rows of a 32-column chunk are requested one chunk ahead (the first one before the accumulator
       // is even ready), so their latency hides behind the TMEM load / staging of the previous chunk
       float4 cnext[8];
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       auto fetch_c = [&](int c0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int m = m0 + j * 4 + (lane >> 3), n = c0 + c4;
+          const int m = grow(j * 4 + (lane >> 3)), n = c0 + c4;
           cnext[j] = (m < a.M && n < a.N) ? *reinterpret_cast<const float4*>(a.C + (long)m * a.ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
@@ -186,7 +214,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
         const int n = c0 + c4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = j * 4 + (lane >> 3), m = m0 + r;
+          const int r = j * 4 + (lane >> 3), m = grow(r);
           if (m < a.M && n < a.N) {
             float4 o = *reinterpret_cast<const float4*>(&sw[r * WS_STG_LD + c4]);
             float* crow;
@@ -219,7 +247,7 @@ template <int BN, int KB, int NSTAGE, int MODE> static int launch_ws(const WsArg
   static_assert(smem <= 227 * 1024, "shared memory budget");
   cudaError_t e = cudaFuncSetAttribute(tc_ws_gemm_kernel<BN, KB, NSTAGE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("tc_ws_gemm smem: %s", cudaGetErrorString(e)); return (int)e; }
-  const int n_tiles = (a.M + 127) / 128;
+  const int n_tiles = (MODE == 0 && a.tso) ? a.n_row_tiles : (a.M + 127) / 128;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
   tc_ws_gemm_kernel<BN, KB, NSTAGE, MODE><<<dim3(grid, gy), WS_THREADS, smem, st>>>(a);
   return check_launch("tc_ws_gemm");
@@ -229,9 +257,13 @@ template <int BN, int KB, int NSTAGE, int MODE> static int launch_ws(const WsArg
 
 using namespace umpr;
 
-// C[M][N<=128] = act(acc*C + A[M][K<=128] · B^T + bias): persistent weight-stationary tensor-core GEMM (N multiple of 4)
+// C[M][N<=128] = act(acc*C + A[M][K<=128] · B^T + bias): persistent weight-stationary tensor-core GEMM (N multiple of 4).
+// table (optional) = [tile_sent_off (n_row_tiles+1) | cstart (M/L+1)] (plan.py:snet_table) for an A whose rows are sentences of L
+// positions with exactly-zero rows at and beyond each sentence's length: only the valid rows are read, multiplied and written
+// (the other rows of C are left untouched).
 extern "C" int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ldb, float* C, long ldc, int M, int N, int K,
-                               int accumulate, const float* bias, int act, int b_kn, int n_ctas, void* stream) {
+                               int accumulate, const float* bias, int act, int b_kn, const int32_t* table, int n_row_tiles, int L,
+                               int n_ctas, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (N > 128 || K > 128 || (N & 3)) return fail_arg("tc_gemm_ws: N=%d K=%d (needs N<=128, N%%4==0, K<=128)", N, K);
   if ((lda & 3) || (ldc & 3) || (reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(C) & 15))
@@ -240,6 +272,10 @@ extern "C" int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ld
   WsArgs a{};
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.b_kn = b_kn; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.accumulate = accumulate; a.act = act; a.bias = bias;
+  if (table) {
+    if (n_row_tiles < 1 || L < 1 || L > 128 || M % L) return fail_arg("tc_gemm_ws: row table inconsistent (n_row_tiles=%d, L=%d, M=%d)", n_row_tiles, L, M);
+    a.tso = table; a.cst = table + n_row_tiles + 1; a.L = L; a.n_row_tiles = n_row_tiles;
+  }
   if (n_ctas < 1) n_ctas = 148;
   if (K <= 64) return launch_ws<128, 1, 3, 0>(a, n_ctas, 1, (cudaStream_t)stream);
   return launch_ws<128, 2, 2, 0>(a, n_ctas, 1, (cudaStream_t)stream);

@@ -249,7 +249,7 @@ def gru_forward_multi(plans, xps, xqs, E, weights, want_hidden=False):
 # --------------------------------------------------------------------------------------------------------------------
 # strided GEMM helper
 # --------------------------------------------------------------------------------------------------------------------
-def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=False, bias=None, act=0):
+def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=False, bias=None, act=0, rows=None):
     """C = act(acc*C + A·B + bias) with strided operands.  Dense "row-major A times K- or N-contiguous B" products run on
     the tensor cores (tcgen05, 3xBF16 split); split-K reductions and odd strides use the CUDA-core kernel."""
     pa = A if isinstance(A, int) else ptr(A)
@@ -265,8 +265,14 @@ def sgemm(A, a_strides, B, b_strides, C, ldc, M, N, K, *, splits=1, accumulate=F
             b_kn, ldb = 1, b_strides[0]
         if b_kn >= 0:
             if N <= 128 and K <= 128 and not (N & 3) and M >= 1024:   # weights stay in shared memory, A streams
+                table, n_row_tiles, L = None, 0, 0
+                if rows is not None and rows.N * rows.L == M and rows.L <= 128:
+                    # ``rows``: the pack plan behind A - rows beyond each sentence's length are exactly zero and are skipped
+                    tab, n_row_tiles = rows.snet_table()
+                    table, L = tab.data_ptr(), rows.L
+                    work = (2.0 * rows.tokens * N * K, 0.0)
                 call("umpr_tc_gemm_ws", pa, a_strides[0], pb, ldb, pc, ldc, M, N, K, int(accumulate), ptr(bias), act, b_kn,
-                     _lib.sm_count(torch.cuda.current_device()), work=work)
+                     table, n_row_tiles, L, _lib.sm_count(torch.cuda.current_device()), work=work)
             else:
                 call("umpr_tc_gemm_nt", pa, a_strides[0], pb, ldb, pc, ldc, M, N, K, int(accumulate), ptr(bias), act, b_kn, work=work)
             return
@@ -290,7 +296,10 @@ class _CoAttnFn(Function):
         B, P, _ = gu.shape
         dev = gu.device
         giM = torch.empty_like(gi)
-        sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D)
+        use_rows = (TENSOR_CORE_COATTN and P <= 512 and plans is not None
+                    and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans))
+        ctx.rows_i = plans[1] if use_rows else None       # giM / dgi rows beyond each sentence's length are never read: skip them
+        sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D, rows=ctx.rows_i)
         soft = torch.empty(4, B, P, dtype=torch.float32, device=dev)       # soft_u, soft_i, t_u, t_i
         arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
         atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
@@ -336,7 +345,7 @@ class _CoAttnFn(Function):
              ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, *ctx.cst, ptr(dgu), ptr(dgi), ptr(dgiM),
              work=(0.0, 6.0 * B * P * D * 4))
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
-        sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True)
+        sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True, rows=ctx.rows_i)
         (dM,), (rM,) = _sinks(ctx.params)
         if B * P >= 4096:      # reduction over every token of the batch: tensor cores, both operands token-major
             call("umpr_tc_gemm_tn", ptr(gi), D, ptr(dgiM), D, ptr(dM), D, D, D, B * P, _n_ctas(dev), work=(2.0 * D * D * B * P, 0.0))
