@@ -34,6 +34,14 @@ struct StMeta {
 };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// tanh(x) = 2 / (1 + 2^(-2x log2 e)) - 1 with ex2.approx / rcp.approx (absolute error ~2e-7, the same cell math as the GRU kernels):
+// 6 instructions instead of the ~45 of tanhf, which dominated the row threads' serial chain
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.885390082f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return fmaf(2.f, r, -1.f);
+}
 
 // Ms [64][128] fp32 -> resident images (all threads of the CTA)
 __device__ __forceinline__ void load_ms_images(unsigned char* msi, const float* __restrict__ Ms, int tid) {
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_fwd_tc_kernel(const float*
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * ATT + h * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sc += ws_s[h * 32 + i] * tanhf(v[i]);
+        for (int i = 0; i < 32; ++i) sc += ws_s[h * 32 + i] * tanh_fast(v[i]);
       }
       score[r] = sc;
       tc_fence_before();
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
         float v[32];
         tmem_ld32(trow + T_E + acc * ATT + h * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { th[h * 32 + i] = tanhf(v[i]); sc += ws_s[h * 32 + i] * th[h * 32 + i]; }
+        for (int i = 0; i < 32; ++i) { th[h * 32 + i] = tanh_fast(v[i]); sc += ws_s[h * 32 + i] * th[h * 32 + i]; }
       }
       score[pb][r] = sc;
       tc_fence_before();
