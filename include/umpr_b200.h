@@ -29,6 +29,17 @@ extern "C" {
 #define UMPR_ERR_ARG (-1)
 
 int umpr_version(void);
+/* Scratch bytes of the entry points that take a caller-owned workspace (PyTorch owns every buffer):
+ *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count */
+int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes);
+
+/* ---- data-parallel gradient exchange (replaces nn.DataParallel, main.py:81-82): one process per GPU, one in-place sum all-reduce
+ * of the flat fp32 gradient bucket per step.  NCCL is resolved at run time from the libnccl.so.2 already in the process. ---- */
+int umpr_comm_unique_id(void* id128 /* 128 bytes, created on rank 0 and handed to every rank by the host */);
+int umpr_comm_init(int rank, int world, const void* id128, void** comm);
+int umpr_allreduce(void* comm, float* flat, long n_floats, void* stream);
+int umpr_comm_destroy(void* comm);
+
 const char* umpr_last_error(void);              /* thread-local message of the last failing call */
 int umpr_sm_count(int device, int* out);
 

@@ -286,3 +286,17 @@ def test_full_model_on_the_tensor_core_path_vs_oracle(workload, batch, m_scale, 
     for k, p in model.named_parameters():
         if p.requires_grad:
             _check_grad(k, p.grad if p.grad is not None else torch.zeros_like(p), g_ref[k])
+
+
+def test_abi_allreduce_two_gpus():
+    """C-ABI NCCL helpers (umpr_comm_unique_id / umpr_comm_init / umpr_allreduce, SURVEY.md §8b,e) on two ranks: same sums as
+    torch.distributed, and a FlatTrainer step through them ends with identical parameters.  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(here, "dist_abi_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ABI_ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -19,8 +19,44 @@ from . import _lib
 from ._lib import call, ptr
 
 
+class AbiComm:
+    """The library's NCCL communicator (C-ABI ``umpr_comm_*``): rank 0 creates the unique id, ``torch.distributed`` carries its 128
+    bytes to the other ranks (any backend), every rank joins; ``all_reduce`` sums a flat fp32 CUDA tensor in place on the current stream."""
+
+    def __init__(self, rank, world, device, process_group=None):
+        import ctypes
+        lib = _lib.load()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (ctypes.c_ubyte * 128)()
+            if lib.umpr_comm_unique_id(raw) != 0:
+                raise RuntimeError(f"umpr_comm_unique_id: {_lib.last_error()}")
+            buf = torch.tensor(list(raw), dtype=torch.uint8)
+        backend = dist.get_backend(process_group)
+        t = buf.to(device) if backend == "nccl" else buf
+        dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0, group=process_group)
+        ident = (ctypes.c_ubyte * 128)(*t.cpu().tolist())
+        self._h = ctypes.c_void_p()
+        torch.cuda.set_device(device)
+        if lib.umpr_comm_init(rank, world, ident, ctypes.byref(self._h)) != 0:
+            raise RuntimeError(f"umpr_comm_init: {_lib.last_error()}")
+        self.rank, self.world = rank, world
+
+    def all_reduce(self, flat):
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous()
+        call("umpr_allreduce", self._h, ptr(flat), flat.numel())
+
+    def close(self):
+        if self._h:
+            _lib.load().umpr_comm_destroy(self._h)
+            self._h = None
+
+
 class FlatTrainer:
-    def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None):
+    def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None, comm=None):
+        """``comm``: "torch" = ``torch.distributed.all_reduce`` on ``process_group`` (default), "abi" = the library's own NCCL
+        communicator (``umpr_comm_init`` / ``umpr_allreduce``, include/umpr_b200.h), bootstrapped by broadcasting the NCCL unique
+        id through ``torch.distributed``; default from ``UMPR_COMM``."""
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         if not named:
             raise RuntimeError("nothing to train")
@@ -48,13 +84,19 @@ class FlatTrainer:
         self.step_no = 0
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.comm = None
+        import os
+        if (comm or os.environ.get("UMPR_COMM", "torch")) == "abi" and self.world > 1 and self.flat.is_cuda:
+            self.comm = AbiComm(dist.get_rank(process_group), self.world, dev, process_group)
 
     def zero_grad(self):
         self.grad.zero_()
 
     def reduce_gradients(self):
         """One flat bucket (0.57–1.0 MB): latency-bound, so a single NCCL all-reduce is the whole exchange."""
-        if self.world > 1:
+        if self.comm is not None:
+            self.comm.all_reduce(self.grad)
+        elif self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def optimizer_step(self):
