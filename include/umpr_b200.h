@@ -33,6 +33,13 @@ int umpr_version(void);
  *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count */
 int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes);
 
+/* ---- R-Net pre-training head (pretrain/pretrain_rnet.py:148-168): sigmoid(Linear(256 -> 1)([att_u | att_i])) + BCELoss (mean) ---- */
+int umpr_bce_head_fwd(const float* att_u /*(B,128)*/, const float* att_i, const float* w /*(1,256)*/, const float* bias /*(1)*/,
+                      const float* target /*(B)*/, int B, float* result /*(B)*/, float* loss /*scalar, zero-initialised*/, void* stream);
+int umpr_bce_head_bwd(const float* att_u, const float* att_i, const float* w, const float* result, const float* target,
+                      const float* d_loss /*scalar or NULL*/, const float* d_result /*(B) or NULL*/, int B, float* d_att_u, float* d_att_i,
+                      float* d_w /*(+=)*/, float* d_b /*(+=)*/, void* stream);
+
 /* ---- data-parallel gradient exchange (replaces nn.DataParallel, main.py:81-82): one process per GPU, one in-place sum all-reduce
  * of the flat fp32 gradient bucket per step.  NCCL is resolved at run time from the libnccl.so.2 already in the process. ---- */
 int umpr_comm_unique_id(void* id128 /* 128 bytes, created on rank 0 and handed to every rank by the host */);

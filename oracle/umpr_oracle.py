@@ -329,6 +329,22 @@ def umpr_forward(params: Dict[str, Tensor], batch, *, review_net_only: bool, thr
     return pred, loss_r + loss_v * loss_v_rate
 
 
+# ----------------------------------------------------------------------------
+# R-Net pre-training  (pretrain/pretrain_rnet.py:144-169) – next-row (f3)
+# ----------------------------------------------------------------------------
+def pretrain_rnet_forward(params: Dict[str, Tensor], u: Tensor, u_len: Tensor, i: Tensor, i_len: Tensor, target: Tensor,
+                          impl: str = "explicit"):
+    """``PretrainRNet.forward``: ids (B,L) -> one sentence per sample -> R-Net -> sigmoid(Linear(256->1)) -> BCELoss.
+    Keys: ``embedding.weight``, ``r_net.*``, ``linear.0.{weight,bias}``."""
+    table = params["embedding.weight"]
+    ue = table[u.reshape(u.shape[0], 1, u.shape[1])]                                           # pretrain_rnet.py:158-163
+    ie = table[i.reshape(i.shape[0], 1, i.shape[1])]
+    out = r_net(ue, ie, u_len.reshape(-1, 1), i_len.reshape(-1, 1), params, prefix="r_net", impl=impl)
+    att = torch.cat([out[4], out[5]], dim=-1)                                                  # :165
+    result = torch.sigmoid(att @ params["linear.0.weight"].t() + params["linear.0.bias"]).squeeze(-1)   # :166
+    return result, torch.nn.functional.binary_cross_entropy(result, target)                   # :167
+
+
 def trainable_keys(params: Dict[str, Tensor]):
     """Everything but the frozen embedding (model.py:237 ``from_pretrained`` ⇒ requires_grad=False)."""
     return [k for k in params if k != "embedding.weight"]

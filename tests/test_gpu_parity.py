@@ -300,3 +300,42 @@ def test_abi_allreduce_two_gpus():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", os.path.join(here, "dist_abi_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ABI_ALLREDUCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("B,L", [(40, 20), (2100, 12)])
+def test_pretrain_rnet_vs_oracle(B, L):
+    """the R-Net pre-training module (pretrain_rnet.py:144-169; one sentence per sample, sigmoid head, BCE) through
+    the same kernels - small batch on the CUDA-core path, 2100 sentences on the fused tensor-core path - against the oracle."""
+    from umpr_b200.pretrain import PretrainRNet
+    from umpr_b200 import synthetic as syn
+    torch.manual_seed(B)
+    table = syn.make_table(3000, seed=2)
+    m = PretrainRNet(table, 64).to(DEV)
+    with torch.no_grad():
+        m.r_net.M.mul_(0.05)
+    lens = [torch.randint(1, L + 1, (B,)) for _ in range(2)]
+    ids = [torch.where(torch.arange(L)[None, :] < ln[:, None], torch.randint(3, 3000, (B, L)), torch.zeros(B, L, dtype=torch.int64)) for ln in lens]
+    target = torch.randint(0, 2, (B,)).float()
+    from umpr_b200 import functional as F
+    m.train()
+    F.ROUTING_LOG = []
+    try:
+        result, loss = m(ids[0], lens[0], ids[1], lens[1], target)
+        log = F.ROUTING_LOG
+    finally:
+        F.ROUTING_LOG = None
+    loss.mean().backward()                                                   # pretrain_rnet.py:190-192
+    params = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    p = {k: v.clone().requires_grad_(k != "embedding.weight") for k, v in params.items()}
+    # thousands of co-attention maxima: the oracle back-propagates through the positions our kernels chose (see the large-batch test)
+    with orc.routed({"coattn": [(a[0].cpu(), a[1].cpu()) for k, a in log if k == "coattn"]}) as r:
+        r_ref, l_ref = orc.pretrain_rnet_forward(p, ids[0], lens[0], ids[1], lens[1], target, impl="lib")
+    assert r.margin["coattn"] <= 2e-5, r.margin
+    keys = [k for k in p if k != "embedding.weight"]
+    g_ref = dict(zip(keys, torch.autograd.grad(l_ref, [p[k] for k in keys], allow_unused=True)))
+    assert_close(result, r_ref.detach(), TOL, "result")
+    assert_close(loss, l_ref.detach(), TOL, "loss")
+    for k, prm in m.named_parameters():
+        if prm.requires_grad:
+            ref = g_ref[k] if g_ref[k] is not None else torch.zeros_like(p[k])
+            _check_grad(k, prm.grad if prm.grad is not None else torch.zeros_like(prm), ref)

@@ -28,6 +28,21 @@ ROUTING_LOG = None             # tests: a list that receives ("coattn", arg (2,B
 DIRECT_GRAD_ACCUM = False      # set by train.FlatTrainer for the duration of its backward pass (see _sinks)
 
 
+_WS = {}
+
+
+def _workspace_floats(entry: str, a: int, b: int = 0) -> int:
+    """Scratch size (in fp32 elements) of an entry point that takes a caller-owned workspace, from ``umpr_workspace_bytes``."""
+    key = (entry, a, b)
+    if key not in _WS:
+        import ctypes
+        out = ctypes.c_longlong(0)
+        if _lib.load().umpr_workspace_bytes(entry.encode(), a, b, ctypes.byref(out)) != 0:
+            raise RuntimeError(f"umpr_workspace_bytes: {_lib.last_error()}")
+        _WS[key] = (out.value + 3) // 4
+    return _WS[key]
+
+
 def _sinks(params):
     """Destinations of parameter gradients that the kernels ACCUMULATE (+=) → (buffers to hand to the kernels, tensors to return
     to autograd).  Under train.FlatTrainer every parameter's ``.grad`` is a view into the flat gradient bucket (zeroed each step), so
@@ -306,7 +321,7 @@ class _CoAttnFn(Function):
         work = (2.0 * B * P * P * D, 2.0 * B * P * D * 4)
         if TENSOR_CORE_COATTN and P <= 512:
             n_it = (P + 127) // 128
-            scratch = torch.empty((2 * B * n_it * 65536 + 4 * B * P * 4 + 16 * B + 4 * B * P * 16 + 256 + 3) // 4, dtype=torch.float32, device=dev)
+            scratch = torch.empty(_workspace_floats("coattn_fwd_tc", B, P), dtype=torch.float32, device=dev)
             cst = [None, None]
             sl = [0, 0, 0, 0]
             if plans is not None and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans):
@@ -536,7 +551,7 @@ class _CNetTailFn(Function):
         work = (2.0 * N * L * 3 * D * KC, N * L * D * 4.0)
         if TENSOR_CORE_CONV:
             cap = max(4096, N * KC // 8)
-            scratch = torch.empty((197632 + 16 * cap) // 4, dtype=torch.float32, device=dev)
+            scratch = torch.empty(_workspace_floats("cnet_conv_fwd_tc", cap), dtype=torch.float32, device=dev)
             table, n_tiles = None, 0
             ctx.keep = None
             if plan is not None and plan.N == N and plan.L == L and L + 2 <= 128:
@@ -571,7 +586,7 @@ class _CNetTailFn(Function):
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
         dx = torch.empty_like(x)        # with a plan: rows beyond a sentence's length stay unwritten (never read, model.py:18)
-        wt = torch.empty(KC * 3 * D, dtype=torch.float32, device=dev)
+        wt = torch.empty(_workspace_floats("cnet_conv_bwd_dx", KC), dtype=torch.float32, device=dev)
         cst = None
         plan = getattr(ctx, "keep", None)
         if plan is not None:
@@ -743,3 +758,37 @@ class _LossFn(Function):
 def umpr_loss(pred, labels, pp=None, pn=None, pm=None, nm=None, rate=0.0):
     """mse_loss(pred, labels, 'mean') [+ rate * mean(pp^T @ pm + pn^T @ nm)]  (model.py:269,275-277)"""
     return _LossFn.apply(pred, labels, pp, pn, pm, nm, rate)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# R-Net pre-training head   (pretrain/pretrain_rnet.py:148-168)
+# --------------------------------------------------------------------------------------------------------------------
+class _BceHeadFn(Function):
+    @staticmethod
+    def forward(ctx, att_u, att_i, w, b, target):
+        ctx.params = (w, b)
+        att_u, att_i, w, b, target = (_f32(_chk(t, "bce head input")) for t in (att_u, att_i, w, b, target))
+        B = att_u.shape[0]
+        if att_u.shape[1] != D or w.numel() != 2 * D:
+            raise RuntimeError("umpr_b200: the pre-training head is built for gru_size=64 (256 -> 1)")
+        result = torch.empty(B, dtype=torch.float32, device=att_u.device)
+        loss = torch.zeros((), dtype=torch.float32, device=att_u.device)
+        call("umpr_bce_head_fwd", ptr(att_u), ptr(att_i), ptr(w), ptr(b), ptr(target), B, ptr(result), ptr(loss))
+        ctx.save_for_backward(att_u, att_i, w, result, target)
+        return result, loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_result, d_loss):
+        att_u, att_i, w, result, target = ctx.saved_tensors
+        B = att_u.shape[0]
+        d_u, d_i = torch.empty_like(att_u), torch.empty_like(att_i)
+        (dw, db), (rw, rb) = _sinks(ctx.params)
+        call("umpr_bce_head_bwd", ptr(att_u), ptr(att_i), ptr(w), ptr(result), ptr(target), ptr(None if d_loss is None else _f32(d_loss)),
+             ptr(None if d_result is None else _f32(d_result)), B, ptr(d_u), ptr(d_i), ptr(dw), ptr(db))
+        return d_u, d_i, rw, rb, None
+
+
+def bce_head(att_u, att_i, w, b, target):
+    """→ result (B,), loss scalar."""
+    return _BceHeadFn.apply(att_u, att_i, w, b, target)
