@@ -156,7 +156,20 @@ class PackPlan:
     def ensure_uploaded(self):
         """Plans prepared by a data-pipeline thread (train.PlanPrefetcher) are uploaded here, on the consumer's thread/stream."""
         if self.buf is None:
-            self.buf = upload_int32(self._host_np, self.device)
+            # one H2D copy for the plan and whichever valid-row tables the worker has already built
+            import numpy as np
+            parts, names = [self._host_np], []
+            for name in ("_snet", "_cnet"):
+                t = getattr(self, name + "_np", None)
+                if t is not None and getattr(self, name, None) is None:
+                    parts.append(t[0])
+                    names.append((name, t[1]))
+            dev = upload_int32(np.concatenate(parts) if len(parts) > 1 else parts[0], self.device)
+            o = self._host_np.size
+            self.buf = dev[:o]
+            for (name, nt), part in zip(names, parts[1:]):
+                setattr(self, name, (dev[o:o + part.size], nt))
+                o += part.size
         return self
 
     @property
