@@ -151,11 +151,13 @@ int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B
                        const int32_t* cst_i, int S_i, int L_i, void* scratch, float* soft_u, float* soft_i, float* t_u, float* t_i,
                        int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
 /* dgu, dgi (without the dgiM·M^T term), dgiM: (B,P,128).  d_* inputs may be NULL.  cst_* as in umpr_coattn_fwd_tc: with them, rows
- * at or beyond a sentence's length are neither read nor written (dgiM alone gets explicit zeros there); NULL: all rows written. */
+ * at or beyond a sentence's length are neither read nor written (dgiM alone gets explicit zeros there); NULL: all rows written.
+ * add_u / add_i (optional, (B,P,128)): gradients of gu / gi from their other consumer (S-Net), added into dgu / dgi on the way out. */
 int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i, const float* t_u,
                     const float* t_i, const int32_t* arg_u, const int32_t* arg_i, const float* d_soft_u, const float* d_soft_i,
                     const float* d_atte_u, const float* d_atte_i, int B, int P, const int32_t* cst_u, int S_u, int L_u,
-                    const int32_t* cst_i, int S_i, int L_i, float* dgu, float* dgi, float* dgiM, void* stream);
+                    const int32_t* cst_i, int S_i, int L_i, const float* add_u, const float* add_i, float* dgu, float* dgi, float* dgiM,
+                    void* stream);
 
 /* ---- SNet: src/model.py:71-81.  x = gru_repr viewed (N, L, 128), N = B*S. ---- */
 int umpr_snet_fwd(const float* x, const float* Ms, const float* Ws, int N, int L, float* self_atte /*(N,128)*/,

@@ -34,7 +34,7 @@ SIGNATURES = {
     "umpr_tc_gemm_ws": [P, L, P, L, P, L, I, I, I, I, P, I, I, P, I, I, I, P],
     "umpr_coattn_fwd": [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
     "umpr_coattn_fwd_tc": [P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P, P, P, P, P],
-    "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, P, I, I, P, P, P, P],
+    "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P],
     "umpr_bce_head_fwd": [P, P, P, P, P, I, P, P, P],
     "umpr_bce_head_bwd": [P, P, P, P, P, P, P, I, P, P, P, P, P],
     "umpr_workspace_bytes": [C.c_char_p, L, L, P],

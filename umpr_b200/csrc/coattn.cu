@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ d_soft_i, const float* __restrict__ d_atte_u,
                                                          const float* __restrict__ d_atte_i, int P, const int* __restrict__ cst_u,
                                                          int S_u, int L_u, const int* __restrict__ cst_i, int S_i, int L_i,
+                                                         const float* __restrict__ add_u, const float* __restrict__ add_i,
                                                          float* __restrict__ dgu, float* __restrict__ dgi, float* __restrict__ dgiM) {
   extern __shared__ __align__(16) float smem[];
   const int P4 = (P + 3) & ~3;
@@ -237,15 +238,18 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
       const float su = soft_u[bp + p], w = wu[p];
       const int a = arg_u[bp + p];
       const float4 m = mi[a] ? *reinterpret_cast<const float4*>(giM + (bp + a) * D + lane * 4) : zero4;
+      // add_u / add_i: gradient of the same rows from another consumer of gu / gi (S-Net), folded in here instead of a separate add pass
+      const float4 e = add_u ? *reinterpret_cast<const float4*>(add_u + (bp + p) * D + lane * 4) : zero4;
       *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) =
-          make_float4(su * dau4.x + w * m.x, su * dau4.y + w * m.y, su * dau4.z + w * m.z, su * dau4.w + w * m.w);
+          make_float4(e.x + su * dau4.x + w * m.x, e.y + su * dau4.y + w * m.y, e.z + su * dau4.z + w * m.z, e.w + su * dau4.w + w * m.w);
     }
     if (mi[p]) {
       const float si = soft_i[bp + p], v = vi[p];
       const int a = arg_i[bp + p];
       const float4 u = mu[a] ? *reinterpret_cast<const float4*>(gu + (bp + a) * D + lane * 4) : zero4;
       *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = make_float4(v * u.x, v * u.y, v * u.z, v * u.w);
-      *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(si * dai4.x, si * dai4.y, si * dai4.z, si * dai4.w);
+      const float4 e = add_i ? *reinterpret_cast<const float4*>(add_i + (bp + p) * D + lane * 4) : zero4;
+      *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(e.x + si * dai4.x, e.y + si * dai4.y, e.z + si * dai4.z, e.w + si * dai4.w);
     } else {
       *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
     }
@@ -296,8 +300,8 @@ extern "C" int umpr_coattn_fwd(const float* gu, const float* gi, const float* gi
 extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* giM, const float* soft_u, const float* soft_i,
                                const float* t_u, const float* t_i, const int32_t* arg_u, const int32_t* arg_i,
                                const float* d_soft_u, const float* d_soft_i, const float* d_atte_u, const float* d_atte_i, int B,
-                               int P, const int32_t* cst_u, int S_u, int L_u, const int32_t* cst_i, int S_i, int L_i, float* dgu,
-                               float* dgi, float* dgiM, void* stream) {
+                               int P, const int32_t* cst_u, int S_u, int L_u, const int32_t* cst_i, int S_i, int L_i,
+                               const float* add_u, const float* add_i, float* dgu, float* dgi, float* dgiM, void* stream) {
   if (B <= 0 || P <= 0) return 0;
   if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_bwd: length tables must be given for both sides or neither");
   if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
@@ -306,6 +310,6 @@ extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* gi
   if (sm > 200 * 1024) return fail_arg("coattn_bwd: P=%d too large", P);
   if (sm > 48 * 1024) cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   coattn_bwd_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(gu, gi, giM, soft_u, soft_i, t_u, t_i, arg_u, arg_i, d_soft_u, d_soft_i,
-                                                         d_atte_u, d_atte_i, P, cst_u, S_u, L_u, cst_i, S_i, L_i, dgu, dgi, dgiM);
+                                                         d_atte_u, d_atte_i, P, cst_u, S_u, L_u, cst_i, S_i, L_i, add_u, add_i, dgu, dgi, dgiM);
   return check_launch("coattn_bwd");
 }

@@ -302,9 +302,24 @@ def _splits_for(K, device):
 # --------------------------------------------------------------------------------------------------------------------
 # RNet co-attention   (model.py:50-55)
 # --------------------------------------------------------------------------------------------------------------------
+class GradSink:
+    """Hand-over of one gradient between two autograd Functions that consume the same tensor.  ``gru_u`` feeds the co-attention
+    and S-Net, and S-Net's other input is the co-attention's soft-max - so S-Net's backward always runs first.  Instead of returning
+    its ``dx`` (autograd would then add it to the co-attention's ``dgu`` with one more full pass over both tensors), S-Net parks it
+    here and returns nothing; the co-attention backward folds it into the rows it writes anyway (``add_u`` / ``add_i``)."""
+    __slots__ = ("armed", "dx")
+
+    def __init__(self):
+        self.armed, self.dx = False, None
+
+
 class _CoAttnFn(Function):
     @staticmethod
-    def forward(ctx, plans, gu, gi, M):
+    def forward(ctx, plans, sinks, gu, gi, M):
+        ctx.sinks = sinks
+        if sinks is not None:
+            for sk, t in zip(sinks, (gu, gi)):
+                sk.armed = bool(t.requires_grad)
         ctx.params = (M,)
         ctx.cst = (None, 0, 0, None, 0, 0)
         gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
@@ -356,8 +371,12 @@ class _CoAttnFn(Function):
         dgu = torch.empty_like(gu)
         dgi = torch.empty_like(gi)
         dgiM = torch.empty_like(gi)
+        adds = [None, None]
+        if ctx.sinks is not None:
+            for k, sk in enumerate(ctx.sinks):
+                adds[k], sk.dx, sk.armed = sk.dx, None, False
         call("umpr_coattn_bwd", ptr(gu), ptr(gi), ptr(giM), ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]),
-             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, *ctx.cst, ptr(dgu), ptr(dgi), ptr(dgiM),
+             ptr(arg[1]), ptr(c(d_soft_u)), ptr(c(d_soft_i)), ptr(c(d_atte_u)), ptr(c(d_atte_i)), B, P, *ctx.cst, ptr(adds[0]), ptr(adds[1]), ptr(dgu), ptr(dgi), ptr(dgiM),
              work=(0.0, 6.0 * B * P * D * 4))
         # dgi += dgiM · M^T ;  dM = gi^T · dgiM
         sgemm(dgiM, (D, 1), M, (1, D), dgi, D, B * P, D, D, accumulate=True, rows=ctx.rows_i)
@@ -366,13 +385,13 @@ class _CoAttnFn(Function):
             call("umpr_tc_gemm_tn", ptr(gi), D, ptr(dgiM), D, ptr(dM), D, D, D, B * P, _n_ctas(dev), work=(2.0 * D * D * B * P, 0.0))
         else:
             sgemm(gi, (1, D), dgiM, (D, 1), dM, D, D, D, B * P, splits=_splits_for(B * P, dev), accumulate=True)
-        return None, dgu, dgi, rM
+        return None, None, dgu, dgi, rM
 
 
-def co_attention(gu, gi, M, plans=None):
+def co_attention(gu, gi, M, plans=None, sinks=None):
     """→ soft_u, soft_i (B,P), atte_u, atte_i (B,128).  ``plans`` = (plan_u, plan_i): the PackPlans of the ImprovedRnn calls that
     produced ``gu`` / ``gi`` - their rows beyond each sentence's length are exactly zero and the tensor-core kernels skip them."""
-    return _CoAttnFn.apply(plans, gu, gi, M)
+    return _CoAttnFn.apply(plans, sinks, gu, gi, M)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -431,8 +450,9 @@ class _SNetTcFn(Function):
     multiplied (csrc/snet_tc.cu); the backward recomputes the scores, so nothing but the input is kept."""
 
     @staticmethod
-    def forward(ctx, plan, gru_repr, word_soft, sent_length, Ms, Ws):
+    def forward(ctx, plan, sink, gru_repr, word_soft, sent_length, Ms, Ws):
         ctx.params = (Ms, Ws)
+        ctx.sink = sink
         x = _f32(_chk(gru_repr, "gru_repr"))
         Ms, Ws = _f32(Ms), _f32(Ws)
         word_soft = _f32(word_soft)
@@ -462,7 +482,7 @@ class _SNetTcFn(Function):
         N = B * S
         dev = x.device
         d_sa = torch.empty(N, D, dtype=torch.float32, device=dev)
-        want_ws = ctx.needs_input_grad[2] and d_sentiment is not None
+        want_ws = ctx.needs_input_grad[3] and d_sentiment is not None
         d_wsum = torch.empty(N, dtype=torch.float32, device=dev) if want_ws else None
         call("umpr_snet_sentiment_bwd", ptr(self_atte), ptr(wsum), ptr(None if d_sentiment is None else _f32(d_sentiment)),
              ptr(None if d_self_atte is None else _f32(d_self_atte)), B, S, ptr(d_sa), ptr(d_wsum))
@@ -473,15 +493,17 @@ class _SNetTcFn(Function):
         call("umpr_snet_bwd_tc", ptr(x), ptr(table), n_tiles, ptr(d_sa), ptr(Ms), ptr(Ws), N, L, ptr(dx), ptr(dMs), ptr(dWs), _n_ctas(dev),
              work=(6.0 * T_v * D * ATT, T_v * D * 8.0))
         d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
-        return None, dx, d_word_soft, None, rMs, rWs
+        if ctx.sink is not None and ctx.sink.armed and want_ws:
+            ctx.sink.dx, dx = dx, None            # the co-attention backward (which needs d_word_soft, so it runs after us) adds it in
+        return None, None, dx, d_word_soft, None, rMs, rWs
 
 
-def s_net(gru_repr, word_soft, sent_length, Ms, Ws, plan=None):
+def s_net(gru_repr, word_soft, sent_length, Ms, Ws, plan=None, sink=None):
     """→ self_atte (B,S,128), sentiment (B,128).  ``plan``: the PackPlan of the ImprovedRnn call that produced ``gru_repr`` (its rows
     beyond each sentence's length are exactly zero) - enables the tensor-core kernels, which skip them."""
     if (TENSOR_CORE_SNET and plan is not None and plan.R == 128 and plan.L == int(sent_length) and plan.L <= 128
             and plan.N * plan.L == gru_repr.shape[0] * gru_repr.shape[1] and tuple(Ms.shape) == (ATT, D) and gru_repr.shape[2] == D):
-        return _SNetTcFn.apply(plan, gru_repr, word_soft, sent_length, Ms, Ws)
+        return _SNetTcFn.apply(plan, sink, gru_repr, word_soft, sent_length, Ms, Ws)
     return _SNetFn.apply(gru_repr, word_soft, sent_length, Ms, Ws)
 
 

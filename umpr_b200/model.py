@@ -103,8 +103,10 @@ class RNet(nn.Module):
         (gru_u, _), (gru_i, _) = self.gru.run_many([pu, pi])           # model.py:45-46: shared weights, one fused launch
         gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
         gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
-        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=(pu.plan, pi.plan))
+        sinks = (F.GradSink(), F.GradSink())
+        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=(pu.plan, pi.plan), sinks=sinks)
         gru_u._umpr_plan, gru_i._umpr_plan = pu.plan, pi.plan          # lets S-Net skip the positions beyond each sentence's length
+        gru_u._umpr_sink, gru_i._umpr_sink = sinks                      # and hand its dx to the co-attention backward (F.GradSink)
         return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
 
 
@@ -122,7 +124,8 @@ class SNet(nn.Module):
                 print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
 
     def forward(self, gru_repr, word_soft, sent_length):
-        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws, plan=getattr(gru_repr, "_umpr_plan", None))
+        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws, plan=getattr(gru_repr, "_umpr_plan", None),
+                       sink=getattr(gru_repr, "_umpr_sink", None))
 
 
 class CNet(nn.Module):
