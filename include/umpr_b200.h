@@ -33,6 +33,14 @@ int umpr_version(void);
  *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count */
 int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes);
 
+/* ---- text matching (model.py:166-168): y = tanh(linear_u([atte_u | senti_u]) + linear_i([atte_i | senti_i])), Wu / Wi (128,256),
+ * bias-free; the backward takes dpre = dy * (1 - y^2) (umpr_tanh_bwd) and returns the four input gradients (weight gradients:
+ * umpr_tc_gemm_tn / umpr_sgemm reductions over the batch) ---- */
+int umpr_text_match_fwd(const float* atte_u, const float* senti_u, const float* atte_i, const float* senti_i, const float* Wu,
+                        const float* Wi, int B, float* y /*(B,128)*/, void* stream);
+int umpr_text_match_bwd(const float* dpre, const float* Wu, const float* Wi, int B, float* d_atte_u, float* d_senti_u, float* d_atte_i,
+                        float* d_senti_i, void* stream);
+
 /* ---- R-Net pre-training head (pretrain/pretrain_rnet.py:148-168): sigmoid(Linear(256 -> 1)([att_u | att_i])) + BCELoss (mean) ---- */
 int umpr_bce_head_fwd(const float* att_u /*(B,128)*/, const float* att_i, const float* w /*(1,256)*/, const float* bias /*(1)*/,
                       const float* target /*(B)*/, int B, float* result /*(B)*/, float* loss /*scalar, zero-initialised*/, void* stream);

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
     float* dst = side ? vi : wu;
     const float4 d4 = *reinterpret_cast<const float4*>(da + lane * 4);
     const unsigned char* ok = side ? mi : mu;
+#pragma unroll 4
     for (int p = warp; p < P; p += 8) {
       if (!ok[p]) { if (lane == 0) dst[p] = dso ? dso[bp + p] : 0.f; continue; }
       const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4);
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   const float4 dau4 = *reinterpret_cast<const float4*>(dau + lane * 4);
   const float4 dai4 = *reinterpret_cast<const float4*>(dai + lane * 4);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
   for (int p = warp; p < P; p += 8) {
     if (mu[p]) {
       const float su = soft_u[bp + p], w = wu[p];

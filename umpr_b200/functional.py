@@ -518,9 +518,10 @@ class _TextMatchFn(Function):
         Wu, Wi = _f32(Wu), _f32(Wi)
         B = ins[0].shape[0]
         y = torch.empty(B, D, dtype=torch.float32, device=ins[0].device)
-        # y = sum_j in_j · W[:, j-th half]^T ; B(k,n) = W[n][off+k] -> strides (1, 2D)
-        for j, (x, W, off) in enumerate(((ins[0], Wu, 0), (ins[1], Wu, D), (ins[2], Wi, 0), (ins[3], Wi, D))):
-            sgemm(x, (D, 1), W.data_ptr() + 4 * off, (1, 2 * D), y, D, B, D, D, accumulate=j > 0, act=1 if j == 3 else 0)
+        if tuple(Wu.shape) != (D, 2 * D) or tuple(Wi.shape) != (D, 2 * D) or any(tuple(t.shape) != (B, D) for t in ins):
+            raise RuntimeError("umpr_b200: text matching is built for gru_size=64 (two bias-free 256 -> 128 linears)")
+        call("umpr_text_match_fwd", ptr(ins[0]), ptr(ins[1]), ptr(ins[2]), ptr(ins[3]), ptr(Wu), ptr(Wi), B, ptr(y),
+             work=(2.0 * B * D * 4 * D, 0.0))
         ctx.save_for_backward(*ins, Wu, Wi, y)
         return y
 
@@ -535,9 +536,9 @@ class _TextMatchFn(Function):
         dins = torch.empty(4, B, D, dtype=torch.float32, device=dev)
         dW, rW = _sinks(ctx.params)
         sp = _splits_for(B, dev)
+        call("umpr_text_match_bwd", ptr(dpre), ptr(Wu), ptr(Wi), B, ptr(dins[0]), ptr(dins[1]), ptr(dins[2]), ptr(dins[3]),
+             work=(2.0 * B * D * 4 * D, 0.0))
         for j, (x, W, wi, off) in enumerate(((a_u, Wu, 0, 0), (s_u, Wu, 0, D), (a_i, Wi, 1, 0), (s_i, Wi, 1, D))):
-            # d in_j = dpre · W[:, half]        (B(k,n) = W[k][off+n])
-            sgemm(dpre, (D, 1), W.data_ptr() + 4 * off, (2 * D, 1), dins[j], D, B, D, D)
             # dW[:, half] += dpre^T · in_j      (A(m,k) = dpre[k][m]): reduction over the batch, both operands sample-major
             if TENSOR_CORE_GEMM and B >= 256:
                 call("umpr_tc_gemm_tn", ptr(dpre), D, ptr(x), D, dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, _n_ctas(dev),
