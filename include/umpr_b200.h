@@ -40,6 +40,8 @@ int umpr_text_match_fwd(const float* atte_u, const float* senti_u, const float* 
                         const float* Wi, int B, float* y /*(B,128)*/, void* stream);
 int umpr_text_match_bwd(const float* dpre, const float* Wu, const float* Wi, int B, float* d_atte_u, float* d_senti_u, float* d_atte_i,
                         float* d_senti_i, void* stream);
+int umpr_text_match_wgrad(const float* dpre, const float* atte_u, const float* senti_u, const float* atte_i, const float* senti_i, int B,
+                          float* dWu /*(128,256) +=*/, float* dWi /*(+=)*/, void* stream);
 
 /* ---- R-Net pre-training head (pretrain/pretrain_rnet.py:148-168): sigmoid(Linear(256 -> 1)([att_u | att_i])) + BCELoss (mean) ---- */
 int umpr_bce_head_fwd(const float* att_u /*(B,128)*/, const float* att_i, const float* w /*(1,256)*/, const float* bias /*(1)*/,

@@ -37,6 +37,7 @@ SIGNATURES = {
     "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P],
     "umpr_text_match_fwd": [P, P, P, P, P, P, I, P, P],
     "umpr_text_match_bwd": [P, P, P, I, P, P, P, P, P],
+    "umpr_text_match_wgrad": [P, P, P, P, P, I, P, P, P],
     "umpr_bce_head_fwd": [P, P, P, P, P, I, P, P, P],
     "umpr_bce_head_bwd": [P, P, P, P, P, P, P, I, P, P, P, P, P],
     "umpr_workspace_bytes": [C.c_char_p, L, L, P],

@@ -69,9 +69,57 @@ __global__ void __launch_bounds__(512) text_match_bwd_kernel(const float* __rest
     if (b0 + s < B) dst[(size_t)(b0 + s) * D + (k & 127)] = acc[s];
 }
 
+// dW[n][k] += sum_b dpre[b][n] in[b][k] over [a_u | s_u | a_i | s_i] (k = 0..511; dWu takes k < 256, dWi the rest).
+// grid (8 blocks of 64 columns, batch splits); thread = (32 outputs n, one column k); atomics fold the batch splits
+__global__ void __launch_bounds__(256) text_match_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ a_u,
+                                                               const float* __restrict__ s_u, const float* __restrict__ a_i,
+                                                               const float* __restrict__ s_i, int B, int per_split,
+                                                               float* __restrict__ dWu, float* __restrict__ dWi) {
+  __shared__ float dp[8][D];
+  __shared__ float xin[8][64];
+  const int tid = threadIdx.x, k = tid & 63, n0 = (tid >> 6) * 32;
+  const int kb = blockIdx.x, j = kb >> 1, c0 = (kb & 1) * 64;           // input j, its columns c0..c0+63
+  const float* src = j == 0 ? a_u : j == 1 ? s_u : j == 2 ? a_i : s_i;
+  const int b_beg = blockIdx.y * per_split, b_end = min(B, b_beg + per_split);
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int b0 = b_beg; b0 < b_end; b0 += 8) {
+    __syncthreads();
+    for (int idx = tid; idx < 8 * D; idx += 256) {
+      const int s = idx >> 7, n = idx & 127;
+      dp[s][n] = b0 + s < b_end ? dpre[(size_t)(b0 + s) * D + n] : 0.f;
+    }
+    for (int idx = tid; idx < 8 * 64; idx += 256) {
+      const int s = idx >> 6, c = idx & 63;
+      xin[s][c] = b0 + s < b_end ? src[(size_t)(b0 + s) * D + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const float x = xin[s][k];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += dp[s][n0 + i] * x;
+    }
+  }
+  float* dW = (j < 2 ? dWu : dWi) + (j & 1) * D + c0 + k;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) atomicAdd(dW + (size_t)(n0 + i) * 2 * D, acc[i]);
+}
+
 }  // namespace umpr
 
 using namespace umpr;
+
+extern "C" int umpr_text_match_wgrad(const float* dpre, const float* atte_u, const float* senti_u, const float* atte_i,
+                                     const float* senti_i, int B, float* dWu, float* dWi, void* stream) {
+  if (B <= 0) return 0;
+  int splits = (B + 63) / 64;
+  if (splits > 32) splits = 32;
+  const int per_split = ((B + splits - 1) / splits + 7) / 8 * 8;
+  text_match_wgrad_kernel<<<dim3(8, splits), 256, 0, (cudaStream_t)stream>>>(dpre, atte_u, senti_u, atte_i, senti_i, B, per_split, dWu, dWi);
+  return check_launch("text_match_wgrad");
+}
 
 extern "C" int umpr_text_match_fwd(const float* atte_u, const float* senti_u, const float* atte_i, const float* senti_i, const float* Wu,
                                    const float* Wi, int B, float* y, void* stream) {

@@ -535,16 +535,11 @@ class _TextMatchFn(Function):
         call("umpr_tanh_bwd", ptr(y), ptr(_f32(dy)), y.numel(), ptr(dpre))
         dins = torch.empty(4, B, D, dtype=torch.float32, device=dev)
         dW, rW = _sinks(ctx.params)
-        sp = _splits_for(B, dev)
         call("umpr_text_match_bwd", ptr(dpre), ptr(Wu), ptr(Wi), B, ptr(dins[0]), ptr(dins[1]), ptr(dins[2]), ptr(dins[3]),
              work=(2.0 * B * D * 4 * D, 0.0))
-        for j, (x, W, wi, off) in enumerate(((a_u, Wu, 0, 0), (s_u, Wu, 0, D), (a_i, Wi, 1, 0), (s_i, Wi, 1, D))):
-            # dW[:, half] += dpre^T · in_j      (A(m,k) = dpre[k][m]): reduction over the batch, both operands sample-major
-            if TENSOR_CORE_GEMM and B >= 256:
-                call("umpr_tc_gemm_tn", ptr(dpre), D, ptr(x), D, dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, _n_ctas(dev),
-                     work=(2.0 * D * D * B, 0.0))
-            else:
-                sgemm(dpre, (1, D), x, (D, 1), dW[wi].data_ptr() + 4 * off, 2 * D, D, D, B, splits=sp, accumulate=True)
+        # dW[:, half] += dpre^T · in_j: reduction over the batch for all four halves in one launch
+        call("umpr_text_match_wgrad", ptr(dpre), ptr(a_u), ptr(s_u), ptr(a_i), ptr(s_i), B, ptr(dW[0]), ptr(dW[1]),
+             work=(2.0 * B * D * 4 * D, 0.0))
         return dins[0], dins[1], dins[2], dins[3], rW[0], rW[1]
 
 
