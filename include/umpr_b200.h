@@ -214,6 +214,10 @@ int umpr_cnet_conv_bwd_dx(const float* dcfeat, const int32_t* cidx, const float*
                           float* dx /*(N,L,128): rows below each length written*/, int n_ctas, void* stream);
 int umpr_cnet_conv_bwd_dw(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* cst,
                           float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
+/* the same weight gradient on tcgen05: per tap, dW_j^T = x^T . G_j with the gradients scattered into a one-hot tile G_j (3xBF16);
+ * table = the convolution's tile table of umpr_cnet_conv_fwd_tc (required) */
+int umpr_cnet_conv_bwd_dw_tc(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* table,
+                             int n_tiles, float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
 
 /* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */
 int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b, float eps,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "umpr_cnet_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P],
     "umpr_cnet_conv_bwd_dx": [P, P, P, I, I, I, P, P, P, I, P],
     "umpr_cnet_conv_bwd_dw": [P, P, P, I, I, I, P, P, I, P],
+    "umpr_cnet_conv_bwd_dw_tc": [P, P, P, I, I, I, P, I, P, I, P],
     "umpr_control_tail_fwd": [P, P, P, P, P, F, I, I, I, P, P, P, P, P],
     "umpr_control_tail_bwd": [P, P, P, P, P, P, P, P, F, I, I, I, P, P, P, P, P, P],
     "umpr_visual_fwd": [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],

@@ -1,0 +1,225 @@
+// C-Net convolution weight gradient on tcgen05 (backward of reference src/model.py:118-120).
+//   dW[k][c][j] = sum_n g[n][k] x[n][arg(n,k) + j - 1][c]        (g = gradient of the pooled feature, arg = its max position)
+// is sparse per (sentence, filter) - 1.5 KB of row gathers per pair on CUDA cores - but dense per tap once the gradients are
+// scattered into a one-hot tile:  dW_j^T [c x k] = x^T [c x rows] . G_j [rows x k],  G_j[r][k] = g[n][k] at the row r that tap j of
+// the winning window reads.  Tiles are the convolution's own (plan.py:cnet_table: valid rows of whole sentences between zero guard
+// rows, <= 128 rows); the x image is loaded once per tile and used MN-major; G_j is rebuilt in shared memory for each tap
+// (zero-fill + scatter of <= ns*K bf16 hi/lo pairs); three accumulators (one per tap) live in tensor memory for the CTA's whole
+// queue and are flushed once.  warps 0-3: x loaders, warp 4: MMA issuer, warps 5-8: gradient scatter + flush.
+#include "common.cuh"
+#include "tc.cuh"
+#include "../../include/umpr_b200.h"
+
+namespace umpr {
+using namespace tc;
+
+constexpr int CB_THREADS = 288;
+constexpr int CB_XIMG = 65536;          // [c block 2][hi|lo][128 rows][128 B]
+constexpr int CB_GIMG = 65536;          // [k block 2][hi|lo][128 rows][128 B]
+constexpr int CB_NMETA = 4;
+constexpr int CB_MAXS = 44;
+constexpr int CB_RC = 16;             // (gradient, position) pairs a scatter thread keeps in registers per tile
+
+struct CbMeta {
+  int s0, ns;
+  int sb[CB_MAXS];                      // tile row of each sentence's leading guard row
+  int len[CB_MAXS];
+  int rowsrc[128];                      // tile row -> global x row, -1 = zero row
+};
+struct CbBars { uint64_t a_full[2], a_empty[2], m_full[CB_NMETA], g_ready, g_free, w_full; };
+
+__global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
+                                                                            const int* __restrict__ cidx, const int* __restrict__ tso,
+                                                                            const int* __restrict__ cstc, int n_tiles, int L, int KC,
+                                                                            float* __restrict__ dw) {
+  extern __shared__ unsigned char raw[];
+  __shared__ CbBars bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ CbMeta meta[CB_NMETA];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* xim = base;                     // 2 stages
+  unsigned char* gim = base + 2 * CB_XIMG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int n_mine = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar.a_full[s], 128); mbar_init(&bar.a_empty[s], 1); }
+    for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
+    mbar_init(&bar.g_ready, 128);
+    mbar_init(&bar.g_free, 1);
+    mbar_init(&bar.w_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ loaders: tile bookkeeping + x rows -> bf16 hi/lo image
+    for (int it = 0; it < n_mine; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x, s = it & 1;
+      if (it >= 2) mbar_wait(&bar.a_empty[s], ((it >> 1) - 1) & 1);     // also frees meta slot it % 4 (tile it-4 is long finished)
+      CbMeta& m = meta[it % CB_NMETA];
+      m.rowsrc[tid] = -1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
+      if (tid < ns) {
+        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
+        m.sb[tid] = b; m.len[tid] = len;
+        const int g0 = (s0 + tid) * L;
+        for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
+      }
+      if (tid == 0) { m.s0 = s0; m.ns = ns; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      unsigned char* st = xim + s * CB_XIMG;
+#pragma unroll 1
+      for (int kb = 0; kb < 2; ++kb) {
+        unsigned char* a_hi = st + kb * 32768, *a_lo = a_hi + 16384;
+        float4 va[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
+          const int src = m.rowsrc[r];
+          va[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + (size_t)src * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = i * 128 + tid;
+          store_split4(a_hi, a_lo, idx >> 4, (idx & 15) * 4, va[i]);
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(&bar.a_full[s]);
+      mbar_arrive(&bar.m_full[it % CB_NMETA]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);      // A (x) and B (G) MN-major
+      const uint32_t g0 = smem_u32(gim);
+      int q = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const int s = it & 1;
+        mbar_wait(&bar.a_full[s], (it >> 1) & 1);
+        const uint32_t a0 = smem_u32(xim + s * CB_XIMG);
+        for (int j = 0; j < 3; ++j, ++q) {
+          mbar_wait(&bar.g_ready, q & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
+            const uint64_t gh = desc_mn(g0 + ks * 2048, 32768), gl = desc_mn(g0 + 16384 + ks * 2048, 32768);
+            umma_bf16(tmem + j * 128, xh, gh, idesc, (it | ks) != 0);
+            umma_bf16(tmem + j * 128, xh, gl, idesc, 1);
+            umma_bf16(tmem + j * 128, xl, gh, idesc, 1);
+          }
+          umma_commit(&bar.g_free);
+          if (j == 2) umma_commit(&bar.a_empty[s]);
+        }
+      }
+      umma_commit(&bar.w_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ gradient scatter (one-hot tile per tap), final flush
+    const int et = tid - 160;
+    int q = 0;
+    for (int it = 0; it < n_mine; ++it) {
+      mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
+      const CbMeta& m = meta[it % CB_NMETA];
+      const int ns = m.ns, s0 = m.s0;
+      // the tile's (gradient, position) pairs are fetched ONCE, all loads in flight together, and reused by the three taps;
+      // a thread keeps its first CB_RC items in registers (a tile rarely holds more than 16 sentences), the rest is re-read
+      float gq[CB_RC];
+      int rq[CB_RC];                                              // tile row of the window's centre, or -1000 if nothing to scatter
+#pragma unroll
+      for (int i = 0; i < CB_RC; ++i) {
+        const int idx = et + i * 128, sn = idx >> 7, k = idx & 127;
+        gq[i] = 0.f; rq[i] = -1000;
+        if (sn < ns && k < KC) {
+          const size_t o = (size_t)(s0 + sn) * KC + k;
+          gq[i] = dcfeat[o];
+          rq[i] = cidx[o];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CB_RC; ++i) {
+        const int sn = (et + i * 128) >> 7;
+        if (sn < ns) {
+          const int t = rq[i];
+          // centre row of the winning window in tile coordinates, plus its sentence's valid range packed alongside
+          rq[i] = (gq[i] != 0.f && t >= 0) ? t : -1000;
+        }
+      }
+      for (int j = 0; j < 3; ++j, ++q) {
+        if (q >= 1) mbar_wait(&bar.g_free, (q - 1) & 1);          // the previous tap's MMAs have read the tile
+        for (int i = et; i < CB_GIMG / 16; i += 128) reinterpret_cast<uint4*>(gim)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        auto put = [&](int sn, int k, float g, int t) {
+          const int row_in = t + j - 1;                            // the x row tap j of the winning window reads
+          if (row_in < 0 || row_in >= m.len[sn]) return;
+          const int r = m.sb[sn] + 1 + row_in;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
+          const uint32_t off = (uint32_t)((k >> 6) * 32768 + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+          *reinterpret_cast<__nv_bfloat16*>(gim + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(gim + 16384 + off) = lo;
+        };
+#pragma unroll
+        for (int i = 0; i < CB_RC; ++i)
+          if (rq[i] >= 0) put((et + i * 128) >> 7, et & 127, gq[i], rq[i]);
+        for (int idx = et + CB_RC * 128; idx < ns * 128; idx += 128) {
+          const int sn = idx >> 7, k = idx & 127;
+          if (k >= KC) continue;
+          const size_t o = (size_t)(s0 + sn) * KC + k;
+          const float g = dcfeat[o];
+          const int t = cidx[o];
+          if (g != 0.f && t >= 0) put(sn, k, g, t);
+        }
+        fence_async_smem();
+        mbar_arrive(&bar.g_ready);
+      }
+    }
+    if (n_mine > 0) {
+      mbar_wait(&bar.w_full, 0);
+      tc_fence_after();
+      const int q4 = warp & 3, c = q4 * 32 + lane;                 // TMEM lane = channel
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j)
+#pragma unroll 1
+        for (int k0 = 0; k0 < 128; k0 += 32) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + j * 128 + k0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i < KC) atomicAdd(&dw[((size_t)(k0 + i) * D + c) * 3 + j], v[i]);
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace umpr
+
+using namespace umpr;
+
+// table = the convolution's tile table (plan.py:cnet_table): [tile_sent_off (n_tiles+1) | cstart (N+1)], cstart = prefix sum of len+2
+extern "C" int umpr_cnet_conv_bwd_dw_tc(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* table,
+                                        int n_tiles, float* d_conv_w, int n_ctas, void* stream) {
+  if (N <= 0) return 0;
+  if (KC < 1 || KC > 128) return fail_arg("cnet: kernel_count=%d must be in [1, 128]", KC);
+  if (L < 1 || L + 2 > 128) return fail_arg("cnet_conv_bwd_dw_tc: sentence length L=%d must be in [1, 126]", L);
+  if (!table || n_tiles < 1 || n_tiles > N) return fail_arg("cnet_conv_bwd_dw_tc: tile table missing or inconsistent (n_tiles=%d, N=%d)", n_tiles, N);
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail_arg("cnet_conv_bwd_dw_tc: x must be 16-byte aligned");
+  constexpr int smem = 2 * CB_XIMG + CB_GIMG + 1024;
+  cudaError_t e = cudaFuncSetAttribute(cnet_conv_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("cnet_conv_bwd_dw_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
+  if (n_ctas < 1) n_ctas = 148;
+  const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
+  cnet_conv_bwd_dw_tc_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(x, dcfeat, cidx, table, table + n_tiles + 1, n_tiles, L, KC, d_conv_w);
+  return check_launch("cnet_conv_bwd_dw_tc");
+}

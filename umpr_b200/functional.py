@@ -613,8 +613,13 @@ class _CNetTailFn(Function):
         rows = plan.tokens if plan is not None else N * L
         call("umpr_cnet_conv_bwd_dx", ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), _n_ctas(dev),
              work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
-        call("umpr_cnet_conv_bwd_dw", ptr(x), ptr(dcfeat), ptr(cidx), N, L, KC, cst, ptr(d_conv_w), _n_ctas(dev),
-             work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
+        if plan is not None and TENSOR_CORE_CONV:
+            ctab, c_tiles = plan.cnet_table()
+            call("umpr_cnet_conv_bwd_dw_tc", ptr(x), ptr(dcfeat), ptr(cidx), N, L, KC, ptr(ctab), c_tiles, ptr(d_conv_w), _n_ctas(dev),
+                 work=(2.0 * (rows + 2 * N) * 3 * D * KC, rows * D * 4.0 + N * KC * 8.0))
+        else:
+            call("umpr_cnet_conv_bwd_dw", ptr(x), ptr(dcfeat), ptr(cidx), N, L, KC, cst, ptr(d_conv_w), _n_ctas(dev),
+                 work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
         return None, dx, None, None, rets[0], rets[1], rets[2], rets[3], None
 
 
