@@ -30,7 +30,8 @@ extern "C" {
 
 int umpr_version(void);
 /* Scratch bytes of the entry points that take a caller-owned workspace (PyTorch owns every buffer):
- *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count */
+ *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count
+ *   "cnet_conv_bwd_dx_tc": no size argument */
 int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes);
 
 /* ---- text matching (model.py:166-168): y = tanh(linear_u([atte_u | senti_u]) + linear_i([atte_i | senti_i])), Wu / Wi (128,256),
@@ -218,6 +219,10 @@ int umpr_cnet_conv_bwd_dw(const float* x, const float* dcfeat, const int32_t* ci
  * table = the convolution's tile table of umpr_cnet_conv_fwd_tc (required) */
 int umpr_cnet_conv_bwd_dw_tc(const float* x, const float* dcfeat, const int32_t* cidx, int N, int L, int KC, const int32_t* table,
                              int n_tiles, float* d_conv_w /*(+=)*/, int n_ctas, void* stream);
+/* the input gradient on tcgen05: dX = sum_j G_j . W_j with the same one-hot tiles, the tap weights streamed by TMA bulk copies;
+ * scratch: umpr_workspace_bytes("cnet_conv_bwd_dx_tc") = 196608 bytes, 16-byte aligned; rows below each length written */
+int umpr_cnet_conv_bwd_dx_tc(const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC, const int32_t* table,
+                             int n_tiles, void* scratch, float* dx, int n_ctas, void* stream);
 
 /* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */
 int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b, float eps,

@@ -316,7 +316,7 @@ def test_cnet_tail_over_valid_rows_matches_dense(B, S, L, short):
         ((view_p * gv).sum() + (final * gf).sum()).backward()
         res.append([view_p.detach(), final.detach(), torch.where(mask, x.grad, torch.zeros_like(x.grad))] + [t.grad for t in p])
     for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
-        assert_close(a, b, 2e-5 if nm == "d conv_w" else 1e-6, nm)      # with the plan the weight gradient runs on tcgen05 (3xBF16)
+        assert_close(a, b, 2e-5 if nm in ("d conv_w", "dx") else 1e-6, nm)      # with the plan both conv gradients run on tcgen05 (3xBF16)
 
 
 @pytest.mark.parametrize("Nsent,L,accumulate,ctas", [(3000, 20, 0, 148), (3000, 20, 1, 148), (5000, 7, 1, 5), (300, 128, 0, 148)])

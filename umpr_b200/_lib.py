@@ -59,6 +59,7 @@ SIGNATURES = {
     "umpr_cnet_conv_bwd_dx": [P, P, P, I, I, I, P, P, P, I, P],
     "umpr_cnet_conv_bwd_dw": [P, P, P, I, I, I, P, P, I, P],
     "umpr_cnet_conv_bwd_dw_tc": [P, P, P, I, I, I, P, I, P, I, P],
+    "umpr_cnet_conv_bwd_dx_tc": [P, P, P, I, I, I, P, I, P, P, I, P],
     "umpr_control_tail_fwd": [P, P, P, P, P, F, I, I, I, P, P, P, P, P],
     "umpr_control_tail_bwd": [P, P, P, P, P, P, P, P, F, I, I, I, P, P, P, P, P, P],
     "umpr_visual_fwd": [P, P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
@@ -133,7 +134,7 @@ def stream():
 
 
 # kernels launched per C-ABI call (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"umpr_coattn_fwd": 2, "umpr_coattn_fwd_tc": 3, "umpr_cnet_conv_fwd_tc": 3, "umpr_cnet_conv_bwd_dx": 2, "umpr_visual_fwd": 2, "umpr_visual_bwd": 3}
+KERNELS_PER_CALL = {"umpr_coattn_fwd": 2, "umpr_coattn_fwd_tc": 3, "umpr_cnet_conv_fwd_tc": 3, "umpr_cnet_conv_bwd_dx": 2, "umpr_cnet_conv_bwd_dx_tc": 2, "umpr_visual_fwd": 2, "umpr_visual_bwd": 3}
 launch_count = 0          # kernels launched by this process through the C-ABI
 _timer = None             # optional {"only": set|None, "events": {name: [(start, end), ...]}}
 

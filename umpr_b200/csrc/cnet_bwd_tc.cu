@@ -203,6 +203,199 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
   if (warp == 4) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Input gradient on tcgen05:  dX [rows x c] = sum_j G_j [rows x k] . W_j [k x c]  with the same one-hot gradient tiles (K-major A
+// operand this time) and the tap's weights W_j^T as a K-major image streamed from L2 by one TMA bulk copy per tap.
+//   warps 0-3: scatter, warp 4: MMA issuer + TMA producer, warps 5-8: epilogue (valid rows only, coalesced row stores)
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int CX_WIMG = 65536;          // per tap: [k block 2][hi|lo][128 c rows][128 B]
+constexpr int CX_STG_LD = 36;
+
+// wimg[tap][kb][hi|lo][c][kk] = W[kb*64 + kk][c][tap]
+__global__ void cnet_bwd_wimg_kernel(const float* __restrict__ w, int KC, unsigned char* __restrict__ wimg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // (tap, kb, c, k4)
+  if (idx >= 3 * 2 * 128 * 16) return;
+  const int tap = idx / (2 * 128 * 16), rem = idx - tap * 2 * 128 * 16, kb = rem / (128 * 16), c = (rem >> 4) & 127, kk = (rem & 15) * 4;
+  float t[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const int k = kb * 64 + kk + q; t[q] = k < KC ? w[((size_t)k * D + c) * 3 + tap] : 0.f; }
+  unsigned char* img = wimg + (size_t)tap * CX_WIMG + kb * 32768;
+  store_split4(img, img + 16384, c, kk, make_float4(t[0], t[1], t[2], t[3]));
+}
+
+struct CxBars { uint64_t m_full[CB_NMETA], g_ready, g_free, w_full[2], w_empty[2], acc_full[2], acc_empty[2]; };
+
+__global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
+                                                                            const unsigned char* __restrict__ wimg, const int* __restrict__ tso,
+                                                                            const int* __restrict__ cstc, int n_tiles, int L, int KC,
+                                                                            float* __restrict__ dx) {
+  extern __shared__ unsigned char raw[];
+  __shared__ CxBars bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ CbMeta meta[CB_NMETA];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* gim = base;
+  unsigned char* wsm = base + CB_GIMG;             // 2 stages of one tap's weights
+  float* stg = reinterpret_cast<float*>(base + CB_GIMG + 2 * CX_WIMG);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int n_mine = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
+
+  if (tid == 0) {
+    for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
+    mbar_init(&bar.g_ready, 128);
+    mbar_init(&bar.g_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar.w_full[s], 1); mbar_init(&bar.w_empty[s], 1); mbar_init(&bar.acc_full[s], 1); mbar_init(&bar.acc_empty[s], 128); }
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(&tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ tile bookkeeping + gradient scatter
+    const int et = tid;
+    int q = 0;
+    for (int it = 0; it < n_mine; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      // meta slot it % 4: the epilogue of tile it-4 finished before the accumulator ring let tile it-2's MMAs start, and those
+      // finished (g_free) before this tile's first scatter below - so the slot is free
+      CbMeta& m = meta[it % CB_NMETA];
+      if (q >= 1) mbar_wait(&bar.g_free, (q - 1) & 1);
+      m.rowsrc[tid] = -1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
+      if (tid < ns) {
+        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
+        m.sb[tid] = b; m.len[tid] = len;
+        const int g0 = (s0 + tid) * L;
+        for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
+      }
+      if (tid == 0) { m.s0 = s0; m.ns = ns; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_arrive(&bar.m_full[it % CB_NMETA]);
+      float gq[CB_RC];
+      int rq[CB_RC];
+#pragma unroll
+      for (int i = 0; i < CB_RC; ++i) {
+        const int idx = et + i * 128, sn = idx >> 7, k = idx & 127;
+        gq[i] = 0.f; rq[i] = -1000;
+        if (sn < ns && k < KC) {
+          const size_t o = (size_t)(s0 + sn) * KC + k;
+          gq[i] = dcfeat[o];
+          rq[i] = cidx[o];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CB_RC; ++i) rq[i] = (gq[i] != 0.f && rq[i] >= 0) ? rq[i] : -1000;
+      for (int j = 0; j < 3; ++j, ++q) {
+        if (j > 0) mbar_wait(&bar.g_free, (q - 1) & 1);
+        for (int i = et; i < CB_GIMG / 16; i += 128) reinterpret_cast<uint4*>(gim)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        auto put = [&](int sn, int k, float g, int t) {
+          const int row_out = t + j - 1;                           // the x row tap j of the winning window read: it receives g * W[.][.][j]
+          if (row_out < 0 || row_out >= m.len[sn]) return;
+          const int r = m.sb[sn] + 1 + row_out;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
+          const uint32_t off = (uint32_t)((k >> 6) * 32768 + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
+          *reinterpret_cast<__nv_bfloat16*>(gim + off) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(gim + 16384 + off) = lo;
+        };
+#pragma unroll
+        for (int i = 0; i < CB_RC; ++i)
+          if (rq[i] >= 0) put((et + i * 128) >> 7, et & 127, gq[i], rq[i]);
+        for (int idx = et + CB_RC * 128; idx < ns * 128; idx += 128) {
+          const int sn = idx >> 7, k = idx & 127;
+          if (k >= KC) continue;
+          const size_t o = (size_t)(s0 + sn) * KC + k;
+          const float g = dcfeat[o];
+          const int t = cidx[o];
+          if (g != 0.f && t >= 0) put(sn, k, g, t);
+        }
+        fence_async_smem();
+        mbar_arrive(&bar.g_ready);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer (tap weights) + MMA issuer
+    if (lane == 0 && n_mine > 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, 128);              // A (G) and B (W_j^T) K-major
+      const uint32_t g0 = smem_u32(gim);
+      const int n_taps = 3 * n_mine;
+      auto fetch = [&](int q) {
+        const int ws = q & 1;
+        if (q >= 2) mbar_wait(&bar.w_empty[ws], ((q >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bar.w_full[ws], CX_WIMG);
+        bulk_copy_g2s(wsm + ws * CX_WIMG, wimg + (size_t)(q % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
+      };
+      fetch(0);
+      int q = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const int acc = it & 1;
+        if (it >= 2) mbar_wait(&bar.acc_empty[acc], ((it >> 1) - 1) & 1);
+        for (int j = 0; j < 3; ++j, ++q) {
+          if (q + 1 < n_taps) fetch(q + 1);
+          const int ws = q & 1;
+          mbar_wait(&bar.w_full[ws], (q >> 1) & 1);
+          mbar_wait(&bar.g_ready, q & 1);
+          tc_fence_after();
+          const uint32_t w0 = smem_u32(wsm + ws * CX_WIMG);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint64_t gh = smem_desc_sw128(g0 + kb * 32768), gl = smem_desc_sw128(g0 + kb * 32768 + 16384);
+            const uint64_t wh = smem_desc_sw128(w0 + kb * 32768), wl = smem_desc_sw128(w0 + kb * 32768 + 16384);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t o = (uint64_t)(kk * 2);
+              umma_bf16(tmem + acc * 128, gh + o, wh + o, idesc, (j | kb | kk) != 0);
+              umma_bf16(tmem + acc * 128, gh + o, wl + o, idesc, 1);
+              umma_bf16(tmem + acc * 128, gl + o, wh + o, idesc, 1);
+            }
+          }
+          umma_commit(&bar.g_free);
+          umma_commit(&bar.w_empty[ws]);
+          if (j == 2) umma_commit(&bar.acc_full[acc]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: valid rows of dx, coalesced 128-byte row stores
+    const int q4 = warp & 3;
+    float* sw = stg + q4 * 32 * CX_STG_LD;
+    for (int it = 0; it < n_mine; ++it) {
+      const int acc = it & 1;
+      mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
+      const CbMeta& m = meta[it % CB_NMETA];
+      mbar_wait(&bar.acc_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + acc * 128 + c0, v);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          *reinterpret_cast<float4*>(&sw[lane * CX_STG_LD + jj * 4]) = make_float4(v[jj * 4], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
+        __syncwarp();
+        const int c = c0 + (lane & 7) * 4;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int rr = jj * 4 + (lane >> 3), src = m.rowsrc[q4 * 32 + rr];
+          if (src >= 0) *reinterpret_cast<float4*>(dx + (size_t)src * D + c) = *reinterpret_cast<const float4*>(&sw[rr * CX_STG_LD + (lane & 7) * 4]);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&bar.acc_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace umpr
 
 using namespace umpr;
@@ -222,4 +415,25 @@ extern "C" int umpr_cnet_conv_bwd_dw_tc(const float* x, const float* dcfeat, con
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
   cnet_conv_bwd_dw_tc_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(x, dcfeat, cidx, table, table + n_tiles + 1, n_tiles, L, KC, d_conv_w);
   return check_launch("cnet_conv_bwd_dw_tc");
+}
+
+// wimg_scratch: 3 * 65536 bytes, 16-byte aligned (per-tap weight images, rebuilt every call)
+extern "C" int umpr_cnet_conv_bwd_dx_tc(const float* dcfeat, const int32_t* cidx, const float* conv_w, int N, int L, int KC,
+                                        const int32_t* table, int n_tiles, void* wimg_scratch, float* dx, int n_ctas, void* stream) {
+  if (N <= 0) return 0;
+  if (KC < 1 || KC > 128) return fail_arg("cnet: kernel_count=%d must be in [1, 128]", KC);
+  if (L < 1 || L + 2 > 128) return fail_arg("cnet_conv_bwd_dx_tc: sentence length L=%d must be in [1, 126]", L);
+  if (!table || n_tiles < 1 || n_tiles > N) return fail_arg("cnet_conv_bwd_dx_tc: tile table missing or inconsistent (n_tiles=%d, N=%d)", n_tiles, N);
+  if (!wimg_scratch || (reinterpret_cast<uintptr_t>(wimg_scratch) & 15)) return fail_arg("cnet_conv_bwd_dx_tc: scratch must be 16-byte aligned");
+  cnet_bwd_wimg_kernel<<<(3 * 2 * 128 * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, reinterpret_cast<unsigned char*>(wimg_scratch));
+  if (int e = check_launch("cnet_bwd_wimg")) return e;
+  constexpr int smem = CB_GIMG + 2 * CX_WIMG + 4 * 32 * CX_STG_LD * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  cudaError_t e = cudaFuncSetAttribute(cnet_conv_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("cnet_conv_bwd_dx_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
+  if (n_ctas < 1) n_ctas = 148;
+  const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
+  cnet_conv_bwd_dx_tc_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(dcfeat, cidx, reinterpret_cast<const unsigned char*>(wimg_scratch),
+                                                                              table, table + n_tiles + 1, n_tiles, L, KC, dx);
+  return check_launch("cnet_conv_bwd_dx_tc");
 }

@@ -89,6 +89,7 @@ extern "C" int umpr_comm_destroy(void* comm) {
 
 // Scratch bytes of the entry points that take a caller-owned workspace (PyTorch owns every buffer).
 //   "coattn_fwd_tc": a = B, b = P            "cnet_conv_fwd_tc": a = worklist capacity          "cnet_conv_bwd_dx": a = kernel_count
+//   "cnet_conv_bwd_dx_tc": (none)
 extern "C" int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes) {
   if (!entry || !bytes) return fail_arg("workspace_bytes: NULL argument");
   if (!strcmp(entry, "coattn_fwd_tc")) {
@@ -98,6 +99,8 @@ extern "C" int umpr_workspace_bytes(const char* entry, long a, long b, long long
     *bytes = 197632ll + 16ll * a;
   } else if (!strcmp(entry, "cnet_conv_bwd_dx")) {
     *bytes = 4ll * a * 3 * 128;
+  } else if (!strcmp(entry, "cnet_conv_bwd_dx_tc")) {
+    *bytes = 3ll * 65536;
   } else {
     return fail_arg("workspace_bytes: unknown entry point '%s'", entry);
   }

@@ -19,6 +19,7 @@ H, D, ATT, KP, SV = 64, 128, 64, 64, 256
 TENSOR_CORE_GRU = True         # fused tcgen05 input projection + recurrence (gru_rec_tc.cu) for plans with 128-row tiles
 TENSOR_CORE_WGRAD = True       # tcgen05 GRU weight gradients with MN-major operands (gru_wgrad_tc.cu)
 TENSOR_CORE_CONV = True        # tcgen05 implicit-GEMM convolution (cnet_tc.cu)
+TENSOR_CORE_CONV_DX = True     # conv input gradient on tcgen05 (cnet_bwd_tc.cu) when the input carries its pack plan
 TENSOR_CORE_SNET = True        # tcgen05 S-Net over the valid positions only (snet_tc.cu), for inputs that carry their pack plan
 TENSOR_CORE_GEMM = True        # tcgen05 3xBF16 dense products (gemm_tc.cu); False = fp32 CUDA-core kernel everywhere
 TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
@@ -611,8 +612,14 @@ class _CNetTailFn(Function):
             table, n_tiles = plan.snet_table()
             cst = table.data_ptr() + 4 * (n_tiles + 1)
         rows = plan.tokens if plan is not None else N * L
-        call("umpr_cnet_conv_bwd_dx", ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), _n_ctas(dev),
-             work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
+        if plan is not None and TENSOR_CORE_CONV and TENSOR_CORE_CONV_DX:
+            ctab, c_tiles = plan.cnet_table()
+            wimg = torch.empty(_workspace_floats("cnet_conv_bwd_dx_tc", 0), dtype=torch.float32, device=dev)
+            call("umpr_cnet_conv_bwd_dx_tc", ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, ptr(ctab), c_tiles, ptr(wimg), ptr(dx), _n_ctas(dev),
+                 work=(2.0 * (rows + 2 * N) * 3 * D * KC, rows * D * 4.0 + N * KC * 8.0))
+        else:
+            call("umpr_cnet_conv_bwd_dx", ptr(dcfeat), ptr(cidx), ptr(conv_w), N, L, KC, cst, ptr(wt), ptr(dx), _n_ctas(dev),
+                 work=(2.0 * N * KC * 3 * D, rows * D * 4.0 + N * KC * 8.0))
         if plan is not None and TENSOR_CORE_CONV:
             ctab, c_tiles = plan.cnet_table()
             call("umpr_cnet_conv_bwd_dw_tc", ptr(x), ptr(dcfeat), ptr(cidx), N, L, KC, ptr(ctab), c_tiles, ptr(d_conv_w), _n_ctas(dev),
