@@ -26,7 +26,67 @@ struct CbMeta {
   int len[CB_MAXS];
   int rowsrc[128];                      // tile row -> global x row, -1 = zero row
 };
-struct CbBars { uint64_t a_full[2], a_empty[2], m_full[CB_NMETA], g_ready, g_free, w_full; };
+
+constexpr int CB_GHALF = 32768;         // one half (64 filters) of a one-hot gradient tile: [hi|lo][128 rows][128 B]
+
+// The scatter side of both kernels.  A step = (tap j, filter half h); its one-hot tile G[r][k] (k in that half) holds g[n][k] at the
+// row r that tap j of sentence n's winning window touches.  Two half-tile buffers ping-pong with the MMA issuer, so the scatter of
+// step q+1 runs under the MMAs of step q.  Thread et owns filter column kk = et & 63 of the half and every second sentence.
+struct GradCache {
+  float g[2][CB_RC / 2];
+  int t[2][CB_RC / 2];
+};
+__device__ __forceinline__ void grad_cache_load(GradCache& c, const float* __restrict__ dcfeat, const int* __restrict__ cidx, int s0, int ns,
+                                                int KC, int et) {
+  const int kk = et & 63, sg = et >> 6;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < CB_RC / 2; ++i) {
+      const int sn = 2 * i + sg, k = h * 64 + kk;
+      c.g[h][i] = 0.f; c.t[h][i] = -1;
+      if (sn < ns && k < KC) {
+        const size_t o = (size_t)(s0 + sn) * KC + k;
+        c.g[h][i] = dcfeat[o];
+        c.t[h][i] = cidx[o];
+      }
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < CB_RC / 2; ++i)
+      if (c.g[h][i] == 0.f) c.t[h][i] = -1;
+}
+__device__ __forceinline__ void grad_put(unsigned char* gbuf, const CbMeta& m, int sn, int kk, float g, int row) {
+  if (row < 0 || row >= m.len[sn]) return;
+  const int r = m.sb[sn] + 1 + row;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
+  const uint32_t off = (uint32_t)(r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2);
+  *reinterpret_cast<__nv_bfloat16*>(gbuf + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(gbuf + 16384 + off) = lo;
+}
+// one step: zero the half tile, scatter (register-cached pairs first, the rest re-read), publish
+__device__ __forceinline__ void grad_scatter_step(unsigned char* gbuf, const CbMeta& m, const GradCache& c, const float* __restrict__ dcfeat,
+                                                  const int* __restrict__ cidx, int KC, int j, int h, int et, int bar_id) {
+  for (int i = et; i < CB_GHALF / 16; i += 128) reinterpret_cast<uint4*>(gbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+  const int kk = et & 63, sg = et >> 6, ns = m.ns;
+#pragma unroll
+  for (int i = 0; i < CB_RC / 2; ++i)
+    if (c.t[h][i] >= 0) grad_put(gbuf, m, 2 * i + sg, kk, c.g[h][i], c.t[h][i] + j - 1);
+  const int k = h * 64 + kk;
+  if (k < KC)
+    for (int sn = CB_RC + sg; sn < ns; sn += 2) {
+      const size_t o = (size_t)(m.s0 + sn) * KC + k;
+      const float g = dcfeat[o];
+      const int t = cidx[o];
+      if (g != 0.f && t >= 0) grad_put(gbuf, m, sn, kk, g, t + j - 1);
+    }
+  fence_async_smem();
+}
+
+struct CbBars { uint64_t a_full[2], a_empty[2], m_full[CB_NMETA], g_ready[2], g_free[2], w_full; };
 
 __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
                                                                             const int* __restrict__ cidx, const int* __restrict__ tso,
@@ -46,8 +106,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&bar.a_full[s], 128); mbar_init(&bar.a_empty[s], 1); }
     for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
-    mbar_init(&bar.g_ready, 128);
-    mbar_init(&bar.g_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar.g_ready[s], 128); mbar_init(&bar.g_free[s], 1); }
     mbar_init(&bar.w_full, 1);
     mbar_fence_init();
   }
@@ -98,27 +157,31 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_mine > 0) {
-      constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);      // A (x) and B (G) MN-major
+      constexpr uint32_t idesc = idesc_bf16(128, 64) | (1u << 15) | (1u << 16);       // A (x) and B (G half tile) MN-major
       const uint32_t g0 = smem_u32(gim);
       int q = 0;
       for (int it = 0; it < n_mine; ++it) {
         const int s = it & 1;
         mbar_wait(&bar.a_full[s], (it >> 1) & 1);
         const uint32_t a0 = smem_u32(xim + s * CB_XIMG);
-        for (int j = 0; j < 3; ++j, ++q) {
-          mbar_wait(&bar.g_ready, q & 1);
-          tc_fence_after();
+        for (int j = 0; j < 3; ++j)
+          for (int h = 0; h < 2; ++h, ++q) {
+            const int gb = q & 1;
+            mbar_wait(&bar.g_ready[gb], (q >> 1) & 1);
+            tc_fence_after();
+            const uint32_t gq0 = g0 + gb * CB_GHALF;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
-            const uint64_t gh = desc_mn(g0 + ks * 2048, 32768), gl = desc_mn(g0 + 16384 + ks * 2048, 32768);
-            umma_bf16(tmem + j * 128, xh, gh, idesc, (it | ks) != 0);
-            umma_bf16(tmem + j * 128, xh, gl, idesc, 1);
-            umma_bf16(tmem + j * 128, xl, gh, idesc, 1);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
+              const uint64_t gh = desc_mn(gq0 + ks * 2048, 8192), gl = desc_mn(gq0 + 16384 + ks * 2048, 8192);
+              const uint32_t d = tmem + j * 128 + h * 64;
+              umma_bf16(d, xh, gh, idesc, (it | ks) != 0);
+              umma_bf16(d, xh, gl, idesc, 1);
+              umma_bf16(d, xl, gh, idesc, 1);
+            }
+            umma_commit(&bar.g_free[gb]);
+            if (j == 2 && h == 1) umma_commit(&bar.a_empty[s]);
           }
-          umma_commit(&bar.g_free);
-          if (j == 2) umma_commit(&bar.a_empty[s]);
-        }
       }
       umma_commit(&bar.w_full);
     }
@@ -129,58 +192,16 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
     for (int it = 0; it < n_mine; ++it) {
       mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
       const CbMeta& m = meta[it % CB_NMETA];
-      const int ns = m.ns, s0 = m.s0;
-      // the tile's (gradient, position) pairs are fetched ONCE, all loads in flight together, and reused by the three taps;
-      // a thread keeps its first CB_RC items in registers (a tile rarely holds more than 16 sentences), the rest is re-read
-      float gq[CB_RC];
-      int rq[CB_RC];                                              // tile row of the window's centre, or -1000 if nothing to scatter
-#pragma unroll
-      for (int i = 0; i < CB_RC; ++i) {
-        const int idx = et + i * 128, sn = idx >> 7, k = idx & 127;
-        gq[i] = 0.f; rq[i] = -1000;
-        if (sn < ns && k < KC) {
-          const size_t o = (size_t)(s0 + sn) * KC + k;
-          gq[i] = dcfeat[o];
-          rq[i] = cidx[o];
+      // the tile's (gradient, position) pairs are fetched ONCE, all loads in flight together, and reused by the six steps
+      GradCache gc;
+      grad_cache_load(gc, dcfeat, cidx, m.s0, m.ns, KC, et);
+      for (int j = 0; j < 3; ++j)
+        for (int h = 0; h < 2; ++h, ++q) {
+          const int gb = q & 1;
+          if (q >= 2) mbar_wait(&bar.g_free[gb], ((q >> 1) - 1) & 1);      // the MMAs of step q-2 have read this buffer
+          grad_scatter_step(gim + gb * CB_GHALF, m, gc, dcfeat, cidx, KC, j, h, et, 2);
+          mbar_arrive(&bar.g_ready[gb]);
         }
-      }
-#pragma unroll
-      for (int i = 0; i < CB_RC; ++i) {
-        const int sn = (et + i * 128) >> 7;
-        if (sn < ns) {
-          const int t = rq[i];
-          // centre row of the winning window in tile coordinates, plus its sentence's valid range packed alongside
-          rq[i] = (gq[i] != 0.f && t >= 0) ? t : -1000;
-        }
-      }
-      for (int j = 0; j < 3; ++j, ++q) {
-        if (q >= 1) mbar_wait(&bar.g_free, (q - 1) & 1);          // the previous tap's MMAs have read the tile
-        for (int i = et; i < CB_GIMG / 16; i += 128) reinterpret_cast<uint4*>(gim)[i] = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        auto put = [&](int sn, int k, float g, int t) {
-          const int row_in = t + j - 1;                            // the x row tap j of the winning window reads
-          if (row_in < 0 || row_in >= m.len[sn]) return;
-          const int r = m.sb[sn] + 1 + row_in;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(g);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
-          const uint32_t off = (uint32_t)((k >> 6) * 32768 + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
-          *reinterpret_cast<__nv_bfloat16*>(gim + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(gim + 16384 + off) = lo;
-        };
-#pragma unroll
-        for (int i = 0; i < CB_RC; ++i)
-          if (rq[i] >= 0) put((et + i * 128) >> 7, et & 127, gq[i], rq[i]);
-        for (int idx = et + CB_RC * 128; idx < ns * 128; idx += 128) {
-          const int sn = idx >> 7, k = idx & 127;
-          if (k >= KC) continue;
-          const size_t o = (size_t)(s0 + sn) * KC + k;
-          const float g = dcfeat[o];
-          const int t = cidx[o];
-          if (g != 0.f && t >= 0) put(sn, k, g, t);
-        }
-        fence_async_smem();
-        mbar_arrive(&bar.g_ready);
-      }
     }
     if (n_mine > 0) {
       mbar_wait(&bar.w_full, 0);
@@ -223,7 +244,7 @@ __global__ void cnet_bwd_wimg_kernel(const float* __restrict__ w, int KC, unsign
   store_split4(img, img + 16384, c, kk, make_float4(t[0], t[1], t[2], t[3]));
 }
 
-struct CxBars { uint64_t m_full[CB_NMETA], g_ready, g_free, w_full[2], w_empty[2], acc_full[2], acc_empty[2]; };
+struct CxBars { uint64_t m_full[CB_NMETA], g_ready[2], g_free[2], w_full[2], w_empty[2], acc_full[2], acc_empty[2]; };
 
 __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
                                                                             const unsigned char* __restrict__ wimg, const int* __restrict__ tso,
@@ -243,8 +264,7 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
 
   if (tid == 0) {
     for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
-    mbar_init(&bar.g_ready, 128);
-    mbar_init(&bar.g_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar.g_ready[s], 128); mbar_init(&bar.g_free[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar.w_full[s], 1); mbar_init(&bar.w_empty[s], 1); mbar_init(&bar.acc_full[s], 1); mbar_init(&bar.acc_empty[s], 128); }
     mbar_fence_init();
   }
@@ -260,10 +280,10 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
     int q = 0;
     for (int it = 0; it < n_mine; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
-      // meta slot it % 4: the epilogue of tile it-4 finished before the accumulator ring let tile it-2's MMAs start, and those
-      // finished (g_free) before this tile's first scatter below - so the slot is free
+      // meta slot it % 4: the epilogue of tile it-4 finished before the accumulator ring let tile it-2's MMAs start, and the last of
+      // those has retired (g_free of step q-2) before the bookkeeping below is written - so the slot is free
       CbMeta& m = meta[it % CB_NMETA];
-      if (q >= 1) mbar_wait(&bar.g_free, (q - 1) & 1);
+      if (q >= 2) mbar_wait(&bar.g_free[q & 1], ((q >> 1) - 1) & 1);
       m.rowsrc[tid] = -1;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int s0 = tso[tile], ns = tso[tile + 1] - s0;
@@ -276,48 +296,15 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
       if (tid == 0) { m.s0 = s0; m.ns = ns; }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_arrive(&bar.m_full[it % CB_NMETA]);
-      float gq[CB_RC];
-      int rq[CB_RC];
-#pragma unroll
-      for (int i = 0; i < CB_RC; ++i) {
-        const int idx = et + i * 128, sn = idx >> 7, k = idx & 127;
-        gq[i] = 0.f; rq[i] = -1000;
-        if (sn < ns && k < KC) {
-          const size_t o = (size_t)(s0 + sn) * KC + k;
-          gq[i] = dcfeat[o];
-          rq[i] = cidx[o];
+      GradCache gc;
+      grad_cache_load(gc, dcfeat, cidx, s0, ns, KC, et);
+      for (int j = 0; j < 3; ++j)
+        for (int h = 0; h < 2; ++h, ++q) {
+          const int gb = q & 1;
+          if (q >= 2) mbar_wait(&bar.g_free[gb], ((q >> 1) - 1) & 1);
+          grad_scatter_step(gim + gb * CB_GHALF, m, gc, dcfeat, cidx, KC, j, h, et, 1);
+          mbar_arrive(&bar.g_ready[gb]);
         }
-      }
-#pragma unroll
-      for (int i = 0; i < CB_RC; ++i) rq[i] = (gq[i] != 0.f && rq[i] >= 0) ? rq[i] : -1000;
-      for (int j = 0; j < 3; ++j, ++q) {
-        if (j > 0) mbar_wait(&bar.g_free, (q - 1) & 1);
-        for (int i = et; i < CB_GIMG / 16; i += 128) reinterpret_cast<uint4*>(gim)[i] = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        auto put = [&](int sn, int k, float g, int t) {
-          const int row_out = t + j - 1;                           // the x row tap j of the winning window read: it receives g * W[.][.][j]
-          if (row_out < 0 || row_out >= m.len[sn]) return;
-          const int r = m.sb[sn] + 1 + row_out;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(g);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
-          const uint32_t off = (uint32_t)((k >> 6) * 32768 + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
-          *reinterpret_cast<__nv_bfloat16*>(gim + off) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(gim + 16384 + off) = lo;
-        };
-#pragma unroll
-        for (int i = 0; i < CB_RC; ++i)
-          if (rq[i] >= 0) put((et + i * 128) >> 7, et & 127, gq[i], rq[i]);
-        for (int idx = et + CB_RC * 128; idx < ns * 128; idx += 128) {
-          const int sn = idx >> 7, k = idx & 127;
-          if (k >= KC) continue;
-          const size_t o = (size_t)(s0 + sn) * KC + k;
-          const float g = dcfeat[o];
-          const int t = cidx[o];
-          if (g != 0.f && t >= 0) put(sn, k, g, t);
-        }
-        fence_async_smem();
-        mbar_arrive(&bar.g_ready);
-      }
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer (tap weights) + MMA issuer
@@ -325,37 +312,38 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
       constexpr uint32_t idesc = idesc_bf16(128, 128);              // A (G) and B (W_j^T) K-major
       const uint32_t g0 = smem_u32(gim);
       const int n_taps = 3 * n_mine;
-      auto fetch = [&](int q) {
-        const int ws = q & 1;
-        if (q >= 2) mbar_wait(&bar.w_empty[ws], ((q >> 1) - 1) & 1);
+      auto fetch = [&](int p) {                                     // weights of tap p % 3 into stage p & 1
+        const int ws = p & 1;
+        if (p >= 2) mbar_wait(&bar.w_empty[ws], ((p >> 1) - 1) & 1);
         mbar_arrive_expect_tx(&bar.w_full[ws], CX_WIMG);
-        bulk_copy_g2s(wsm + ws * CX_WIMG, wimg + (size_t)(q % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
+        bulk_copy_g2s(wsm + ws * CX_WIMG, wimg + (size_t)(p % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
       };
       fetch(0);
-      int q = 0;
+      int q = 0, p = 0;
       for (int it = 0; it < n_mine; ++it) {
         const int acc = it & 1;
         if (it >= 2) mbar_wait(&bar.acc_empty[acc], ((it >> 1) - 1) & 1);
-        for (int j = 0; j < 3; ++j, ++q) {
-          if (q + 1 < n_taps) fetch(q + 1);
-          const int ws = q & 1;
-          mbar_wait(&bar.w_full[ws], (q >> 1) & 1);
-          mbar_wait(&bar.g_ready, q & 1);
-          tc_fence_after();
+        for (int j = 0; j < 3; ++j, ++p) {
+          if (p + 1 < n_taps) fetch(p + 1);
+          const int ws = p & 1;
+          mbar_wait(&bar.w_full[ws], (p >> 1) & 1);
           const uint32_t w0 = smem_u32(wsm + ws * CX_WIMG);
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-            const uint64_t gh = smem_desc_sw128(g0 + kb * 32768), gl = smem_desc_sw128(g0 + kb * 32768 + 16384);
-            const uint64_t wh = smem_desc_sw128(w0 + kb * 32768), wl = smem_desc_sw128(w0 + kb * 32768 + 16384);
+          for (int h = 0; h < 2; ++h, ++q) {
+            const int gb = q & 1;
+            mbar_wait(&bar.g_ready[gb], (q >> 1) & 1);
+            tc_fence_after();
+            const uint32_t gq0 = g0 + gb * CB_GHALF;
+            const uint64_t gh = smem_desc_sw128(gq0), gl = smem_desc_sw128(gq0 + 16384);
+            const uint64_t wh = smem_desc_sw128(w0 + h * 32768), wl = smem_desc_sw128(w0 + h * 32768 + 16384);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t o = (uint64_t)(kk * 2);
-              umma_bf16(tmem + acc * 128, gh + o, wh + o, idesc, (j | kb | kk) != 0);
+              umma_bf16(tmem + acc * 128, gh + o, wh + o, idesc, (j | h | kk) != 0);
               umma_bf16(tmem + acc * 128, gh + o, wl + o, idesc, 1);
               umma_bf16(tmem + acc * 128, gl + o, wh + o, idesc, 1);
             }
+            umma_commit(&bar.g_free[gb]);
           }
-          umma_commit(&bar.g_free);
           umma_commit(&bar.w_empty[ws]);
           if (j == 2) umma_commit(&bar.acc_full[acc]);
         }
