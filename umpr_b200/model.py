@@ -104,7 +104,9 @@ class RNet(nn.Module):
         gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
         gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
         sinks = (F.GradSink(), F.GradSink())
-        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=(pu.plan, pi.plan), sinks=sinks)
+        # valid-row tables pay for their host-side cost on large sides only (the small-batch regime is host-bound)
+        plans = (pu.plan, pi.plan) if (pu.plan.R == 128 and pi.plan.R == 128) else None
+        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=plans, sinks=sinks)
         gru_u._umpr_plan, gru_i._umpr_plan = pu.plan, pi.plan          # lets S-Net skip the positions beyond each sentence's length
         gru_u._umpr_sink, gru_i._umpr_sink = sinks                      # and hand its dx to the co-attention backward (F.GradSink)
         return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
@@ -158,7 +160,7 @@ class CNet(nn.Module):
             gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
             gru_repr._umpr_plan = pk.plan
             view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
-                                              self.linear[0].weight, self.linear[0].bias, self.threshold, plan=pk.plan)
+                                              self.linear[0].weight, self.linear[0].bias, self.threshold, plan=pk.plan if pk.plan.R == 128 else None)
             res.append((gru_repr, view_p, final_repr))
         return res
 
