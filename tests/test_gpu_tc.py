@@ -261,11 +261,12 @@ def test_cnet_tail_vs_fp64_torch(B, S, L, KC, V):
         assert_close(a, b.float(), 3e-5, nm)
 
 
-@pytest.mark.parametrize("B,S,L,short", [(96, 20, 20, False), (33, 5, 20, True), (8, 4, 100, False), (5, 3, 7, True)])
+@pytest.mark.parametrize("B,S,L,short", [(96, 20, 20, False), (33, 5, 20, True), (8, 4, 100, False), (5, 3, 7, True), (12, 10, 100, True)])
 def test_coattention_over_valid_rows_matches_dense(B, S, L, short):
     """Co-attention (model.py:50-55) with the pack plans of its inputs - only the valid rows are multiplied, the padded rows' exact 0
     enters every maximum analytically - against the same kernels run densely over all P rows: same soft-max weights, pooled
-    vectors and gradients (input gradients compared on the valid rows; the others are never read)."""
+    vectors and gradients (input gradients compared on the valid rows; the others are never read).  The last case has P = 1000
+    padded positions but fewer than 512 valid ones per sample: with the plans it runs on the tensor cores, without on the fp32 kernels."""
     from umpr_b200 import functional as F
     from umpr_b200.plan import PackPlan
     torch.manual_seed(B + L)

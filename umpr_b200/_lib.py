@@ -33,7 +33,7 @@ SIGNATURES = {
     "umpr_tc_gemm_tn": [P, L, P, L, P, L, I, I, L, I, P],
     "umpr_tc_gemm_ws": [P, L, P, L, P, L, I, I, I, I, P, I, I, P, I, I, I, P],
     "umpr_coattn_fwd": [P, P, P, I, I, P, P, P, P, P, P, P, P, P, P, P],
-    "umpr_coattn_fwd_tc": [P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P, P, P, P, P],
+    "umpr_coattn_fwd_tc": [P, P, P, I, I, P, I, I, P, I, I, I, P, P, P, P, P, P, P, P, P, P],
     "umpr_coattn_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, P, I, I, P, I, I, P, I, I, P, P, P, P, P, P],
     "umpr_text_match_fwd": [P, P, P, P, P, P, I, P, P],
     "umpr_text_match_bwd": [P, P, P, I, P, P, P, P, P],

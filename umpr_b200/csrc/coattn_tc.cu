@@ -432,20 +432,24 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
 using namespace umpr;
 
 // scratch (16-byte aligned): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][posA B*P i32][posB B*P i32][meta 4*B i32]
-// [rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),  T = ceil(P/128): 2*B*T*65536 + 4*B*P*4 + 16*B + 4*B*P*16 + 256 bytes.  P <= 512.
+// [rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),  T = ceil(pv_max/128): 2*B*T*65536 + 4*B*P*4 + 16*B + 4*B*P*16 + 256 bytes.
 // cst_u / cst_i (optional, both or neither): exclusive prefix sums of the sentence lengths of the user / item side (S_x sentences of
 // L_x positions per sample, S_x*L_x == P) for inputs whose rows beyond each sentence's length are exactly zero - only the valid rows
 // are multiplied.  NULL: every row is treated as valid.
+// pv_max (with length tables): the largest number of valid rows any sample has on either side - the limit of 512 then applies to it,
+// not to P (long padded sentences that are mostly padding), and the operand images are sized by it; 0 = P.
 extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, const int32_t* cst_u, int S_u, int L_u,
-                                  const int32_t* cst_i, int S_i, int L_i, void* scratch, float* soft_u, float* soft_i, float* t_u,
+                                  const int32_t* cst_i, int S_i, int L_i, int pv_max, void* scratch, float* soft_u, float* soft_i, float* t_u,
                                   float* t_i, int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream) {
   if (B <= 0 || P <= 0) return 0;
   if (B > 65535) return fail_arg("coattn_fwd_tc: batch %d > 65535", B);
-  if (P > C2_MAXP) return fail_arg("coattn_fwd_tc: P=%d > %d (use umpr_coattn_fwd)", P, C2_MAXP);
+  if (!cst_u || pv_max <= 0 || pv_max > P) pv_max = P;
+  if (pv_max > C2_MAXP) return fail_arg("coattn_fwd_tc: %d valid positions per sample > %d (use umpr_coattn_fwd)", pv_max, C2_MAXP);
+  if (P > 16384 || S_u > C2_MAXP || S_i > C2_MAXP) return fail_arg("coattn_fwd_tc: P=%d / S=%d,%d too large", P, S_u, S_i);
   if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_fwd_tc: length tables must be given for both sides or neither");
   if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
     return fail_arg("coattn_fwd_tc: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);
-  const int T = (P + 127) / 128;
+  const int T = (pv_max + 127) / 128;
   unsigned char* imgA = reinterpret_cast<unsigned char*>(scratch);
   unsigned char* imgB = imgA + (size_t)B * T * CI_IMG;
   float* n2a = reinterpret_cast<float*>(imgB + (size_t)B * T * CI_IMG);

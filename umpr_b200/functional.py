@@ -327,20 +327,22 @@ class _CoAttnFn(Function):
         B, P, _ = gu.shape
         dev = gu.device
         giM = torch.empty_like(gi)
-        use_rows = (TENSOR_CORE_COATTN and P <= 512 and plans is not None
-                    and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans))
+        ok_plans = plans is not None and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans)
+        # the tensor-core kernels handle 512 positions per sample; with the plans the limit applies to the VALID positions
+        pv_max = max(pl.max_valid_per_sample(B) for pl in plans) if ok_plans else P
+        use_tc = TENSOR_CORE_COATTN and pv_max <= 512 and P <= 16384
+        use_rows = use_tc and ok_plans
         ctx.rows_i = plans[1] if use_rows else None       # giM / dgi rows beyond each sentence's length are never read: skip them
         sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D, rows=ctx.rows_i)
         soft = torch.empty(4, B, P, dtype=torch.float32, device=dev)       # soft_u, soft_i, t_u, t_i
         arg = torch.empty(2, B, P, dtype=torch.int32, device=dev)
         atte = torch.empty(2, B, D, dtype=torch.float32, device=dev)
         work = (2.0 * B * P * P * D, 2.0 * B * P * D * 4)
-        if TENSOR_CORE_COATTN and P <= 512:
-            n_it = (P + 127) // 128
+        if use_tc:
             scratch = torch.empty(_workspace_floats("coattn_fwd_tc", B, P), dtype=torch.float32, device=dev)
             cst = [None, None]
             sl = [0, 0, 0, 0]
-            if plans is not None and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans):
+            if ok_plans:
                 # both inputs come out of ImprovedRnn with these plans: rows beyond each sentence's length are exactly zero
                 for k, pl in enumerate(plans):
                     table, n_tiles = pl.snet_table()
@@ -350,7 +352,7 @@ class _CoAttnFn(Function):
                 ctx.keep = plans             # keeps the device tables alive until backward
                 valid = float(plans[0].tokens) * float(plans[1].tokens) / B
                 work = (2.0 * valid * D, 2.0 * (plans[0].tokens + plans[1].tokens) * D * 4)
-            call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, cst[0], sl[0], sl[1], cst[1], sl[2], sl[3], ptr(scratch),
+            call("umpr_coattn_fwd_tc", ptr(gu), ptr(gi), ptr(giM), B, P, cst[0], sl[0], sl[1], cst[1], sl[2], sl[3], pv_max if ok_plans else 0, ptr(scratch),
                  ptr(soft[0]), ptr(soft[1]), ptr(soft[2]), ptr(soft[3]), ptr(arg[0]), ptr(arg[1]), ptr(atte[0]), ptr(atte[1]), work=work)
         else:
             rowkey = torch.empty(B * P, dtype=torch.int64, device=dev)

@@ -193,6 +193,15 @@ class PackPlan:
             self._snet = (upload_int32(self._snet_host()[0], self.device), self._snet_host()[1])
         return self._snet
 
+    def max_valid_per_sample(self, B: int) -> int:
+        """Largest number of valid positions any of the ``B`` samples has (its sentences are consecutive output rows)."""
+        key = "_pvmax%d" % B
+        if getattr(self, key, None) is None:
+            cs = self._snet_host()[0][self._snet_host()[1] + 1:]
+            S = self.N // B
+            setattr(self, key, int((cs[S::S] - cs[:-1:S]).max()))
+        return getattr(self, key)
+
     def _snet_host(self):
         if getattr(self, "_snet_np", None) is None:
             import numpy as np
