@@ -338,4 +338,11 @@ def test_pretrain_rnet_vs_oracle(B, L):
     for k, prm in m.named_parameters():
         if prm.requires_grad:
             ref = g_ref[k] if g_ref[k] is not None else torch.zeros_like(p[k])
-            _check_grad(k, prm.grad if prm.grad is not None else torch.zeros_like(prm), ref)
+            got = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+            if k == "linear.0.bias":
+                # a single number: mean(p - t) over the batch, ~1e-2 of the mean magnitude of its terms - both fp32 sums (ours and the
+                # oracle's) are only good to ~1e-6 of THAT scale, so the bar is applied to it, not to the cancelled result
+                scale = float((r_ref.detach() - target).abs().mean())
+                assert float((got.cpu() - ref).abs().max()) <= TOL * scale, (k, float(got), float(ref), scale)
+            else:
+                _check_grad(k, got, ref)
