@@ -289,7 +289,7 @@ def test_coattention_over_valid_rows_matches_dense(B, S, L, short):
         sum((o * w).sum() for o, w in zip(out, g)).backward()
         res.append([o.detach() for o in out] + [torch.where(masks[0], gu.grad, torch.zeros_like(gu.grad)), torch.where(masks[1], gi.grad, torch.zeros_like(gi.grad)), M.grad])
     for a, b, nm in zip(res[1], res[0], ["soft_u", "soft_i", "atte_u", "atte_i", "dgu", "dgi", "dM"]):
-        assert_close(a, b, 2e-5, nm)
+        assert_close(a, b, 5e-5 if P > 512 else 2e-5, nm)        # P > 512: the dense side is the fp32 kernel, not the same 3xBF16 arithmetic
 
 
 @pytest.mark.parametrize("B,S,L,short", [(128, 20, 20, False), (200, 5, 20, True), (10, 3, 100, False), (6, 2, 3, True)])
@@ -317,7 +317,7 @@ def test_cnet_tail_over_valid_rows_matches_dense(B, S, L, short):
         ((view_p * gv).sum() + (final * gf).sum()).backward()
         res.append([view_p.detach(), final.detach(), torch.where(mask, x.grad, torch.zeros_like(x.grad))] + [t.grad for t in p])
     for a, b, nm in zip(res[1], res[0], ["view_p", "final", "dx", "d conv_w", "d conv_b", "d lin_w", "d lin_b"]):
-        assert_close(a, b, 2e-5 if nm in ("d conv_w", "dx") else 1e-6, nm)      # with the plan both conv gradients run on tcgen05 (3xBF16)
+        assert_close(a, b, 5e-5 if nm in ("d conv_w", "dx") else 1e-6, nm)      # with the plan both conv gradients run on tcgen05 (3xBF16)
 
 
 @pytest.mark.parametrize("Nsent,L,accumulate,ctas", [(3000, 20, 0, 148), (3000, 20, 1, 148), (5000, 7, 1, 5), (300, 128, 0, 148)])
