@@ -157,16 +157,23 @@ def stop_timing():
     return out
 
 
+_FN = {}
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_current_device = torch.cuda.current_device
+
+
 def call(name, *args, work=None):
     """Invoke a C-ABI entry point on the current CUDA stream (appended as the last argument).
     ``work`` = (algorithmic FLOPs, algorithmic bytes) of this launch, recorded only while timing (bench.py roofline)."""
     global launch_count
-    lib = load()
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
     timed = _timer is not None and (_timer["only"] is None or name in _timer["only"])
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = getattr(lib, name)(*args, stream())
+    rc = fn(*args, _raw_stream(_current_device()))
     if timed:
         e1.record()
         _timer["events"].setdefault(name, []).append((e0, e1))
