@@ -122,3 +122,27 @@ def test_snet_tile_table_covers_every_sentence_with_at_most_128_rows(L):
     assert rows.max() <= 128 and int(rows.sum()) == p.tokens
     if L <= 20:
         assert rows[:-1].min() >= 129 - 2 * L                                # tiles are filled to within two sentences
+
+
+@pytest.mark.parametrize("L", [1, 20, 100, 126])
+def test_cnet_tile_table_has_guard_rows_and_at_most_128_rows(L):
+    """The convolution's tile table: every sentence takes len + 2 tile rows (zero guard row before and after its valid rows)."""
+    rs = np.random.RandomState(100 + L)
+    lens = torch.from_numpy(rs.randint(1, L + 1, size=2500))
+    p = PackPlan(lens, L, "cpu", tile_rows=128)
+    tab, nt = p._cnet_host()
+    tso, cst = tab[:nt + 1], tab[nt + 1:]
+    assert cst.size == p.N + 1 and tso[0] == 0 and tso[-1] == p.N and (np.diff(tso) >= 1).all()
+    assert np.array_equal(np.diff(cst), p.row_lengths().numpy() + 2)
+    rows = cst[tso[1:]] - cst[tso[:-1]]
+    assert rows.max() <= 128 and int(rows.sum()) == p.tokens + 2 * p.N
+    assert np.diff(tso).max() <= 44                                          # CT_MAXS / CB_MAXS of the kernels: >= 3 rows per sentence
+
+
+def test_max_valid_positions_per_sample():
+    rs = np.random.RandomState(3)
+    B, S, L = 50, 8, 30
+    lens = torch.from_numpy(rs.randint(1, L + 1, size=B * S))
+    p = PackPlan(lens, L, "cpu", tile_rows=128)
+    eff = p.row_lengths().numpy().reshape(B, S)                              # lengths in OUTPUT-row order (the double un-sort)
+    assert p.max_valid_per_sample(B) == int(eff.sum(1).max())
