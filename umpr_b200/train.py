@@ -119,7 +119,7 @@ class FlatTrainer:
         pred, loss = self.model(*batch)
         F.DIRECT_GRAD_ACCUM = True          # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
         try:
-            loss.mean().backward()
+            (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
         finally:
             F.DIRECT_GRAD_ACCUM = False
         self.reduce_gradients()
