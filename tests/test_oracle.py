@@ -96,3 +96,64 @@ def test_adam_restatement_matches_torch():
         opt.step()
         orc.adam_step(p, g, m, v, step, 1e-3, 1e-3)
     assert_close(p, p_ref.detach(), 1e-6, "adam")
+
+
+@pytest.mark.parametrize("name", [n for n in cases.CASES if not cases.CASES[n]["review_net_only"]][:1] + [n for n in cases.CASES if cases.CASES[n]["review_net_only"]][:1])
+def test_routed_oracle_with_its_own_argmax_is_the_plain_oracle(name):
+    """``oracle.routed`` (the arg-max routing hand-over used by the large-batch GPU parity tests): fed with the oracle's OWN winners
+    it reproduces the unrouted prediction, loss and gradients exactly and reports zero margin; fed with a runner-up it reports how
+    far below the maximum that choice lies."""
+    c = cases.CASES[name]
+    params = cases.make_params(c["review_net_only"], c["V"], c["vocab"], c["seed"], c["m_scale"])
+    batch = cases.make_batch(c)
+    user, item, ui, ul, il, uil, photos, labels = batch
+    t = params["embedding.weight"]
+    gru_u, gru_i, *_ = orc.r_net(t[user], t[item], ul, il, params)
+    A = torch.tanh(gru_i @ params["review_net.r_net.M"] @ gru_u.transpose(-1, -2))
+    picks = {"coattn": [(A.argmax(dim=-2), A.argmax(dim=-1))]}
+    if not c["review_net_only"]:
+        picks["cnet"] = []
+        for emb, ln in ((t[ui], uil), (t[user], ul), (t[item], il)):          # the order control_net calls c_net in
+            B, S, L, E = emb.shape
+            g, _ = orc.improved_rnn(emb.reshape(B * S, L, E), ln.reshape(-1), orc.gru_weights(params, "control_net.c_net.gru.module"))
+            pre = torch.nn.functional.conv1d(g.transpose(-1, -2), params["control_net.c_net.cnn.0.weight"],
+                                             params["control_net.c_net.cnn.0.bias"], padding=1)
+            idx = pre.argmax(dim=-1)
+            picks["cnet"].append(torch.where(pre.max(dim=-1).values > 0, idx, torch.full_like(idx, -1)))
+    ref = orc.umpr_loss_and_grads(params, batch, review_net_only=c["review_net_only"])
+    with orc.routed(picks) as r:
+        got = orc.umpr_loss_and_grads(params, batch, review_net_only=c["review_net_only"])
+    assert r.margin["coattn"] == 0.0 and r.margin["cnet"] == 0.0
+    assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+    for k in ref[2]:
+        assert_close(got[2][k], ref[2][k], 1e-6, "grad " + k) if float(ref[2][k].abs().max()) > 1e-9 else None
+    # a runner-up for one column: the margin reports its distance from the maximum
+    second = A.topk(2, dim=-2).indices[..., 1, :]
+    worse = (torch.where(torch.arange(A.shape[-1])[None, :] == 0, second, picks["coattn"][0][0]), picks["coattn"][0][1])
+    with orc.routed({"coattn": [worse]}) as r2:
+        orc.r_net(t[user], t[item], ul, il, params)
+    top2 = A.topk(2, dim=-2).values[..., :, 0]
+    assert r2.margin["coattn"] > 0.0
+    assert abs(r2.margin["coattn"] - float(((top2[:, 0] - top2[:, 1]).max()) / A.max(dim=-2).values.abs().max())) < 1e-6
+
+
+def test_pretrain_rnet_restatement_is_rnet_plus_torch_head():
+    """``oracle.pretrain_rnet_forward`` (pretrain_rnet.py:144-169; the reference module itself cannot be imported here - it needs
+    gensim): it is the pinned ``r_net`` restatement with S = 1 followed by Linear + Sigmoid + BCELoss of torch."""
+    torch.manual_seed(4)
+    B, L, V = 6, 9, 50
+    p = {"embedding.weight": torch.randn(V, 50) * 0.5, "r_net.M": torch.randn(128, 128) * 0.05,
+         "linear.0.weight": torch.randn(1, 256) * 0.1, "linear.0.bias": torch.randn(1) * 0.1}
+    gru = torch.nn.GRU(50, 64, batch_first=True, bidirectional=True)
+    p.update({"r_net.gru.module." + k: v.detach() for k, v in gru.state_dict().items()})
+    lens = [torch.randint(1, L + 1, (B,)) for _ in range(2)]
+    ids = [torch.randint(3, V, (B, L)) * (torch.arange(L)[None, :] < ln[:, None]) for ln in lens]
+    target = torch.randint(0, 2, (B,)).float()
+    result, loss = orc.pretrain_rnet_forward(p, ids[0], lens[0], ids[1], lens[1], target)
+    t = p["embedding.weight"]
+    out = orc.r_net(t[ids[0]].unsqueeze(1), t[ids[1]].unsqueeze(1), lens[0].view(-1, 1), lens[1].view(-1, 1), p, prefix="r_net")
+    head = torch.nn.Sequential(torch.nn.Linear(256, 1), torch.nn.Sigmoid())
+    head[0].weight.data, head[0].bias.data = p["linear.0.weight"], p["linear.0.bias"]
+    want = head(torch.cat([out[4], out[5]], -1)).squeeze(-1)
+    assert_close(result, want.detach(), 1e-6, "result")
+    assert_close(loss, torch.nn.BCELoss()(want, target).detach(), 1e-6, "loss")
