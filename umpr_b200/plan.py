@@ -101,6 +101,14 @@ def upload_int32(arr, device):
     return _RINGS[key].upload(arr, device)
 
 
+def _dense_ids(raw):
+    """Consecutive ids 0, 1, 2, ... for a non-decreasing integer array (``np.unique(raw, return_inverse=True)[1]`` without the sort)."""
+    import numpy as np
+    out = np.zeros(raw.size, dtype=np.int64)
+    np.cumsum(raw[1:] != raw[:-1], out=out[1:])
+    return out
+
+
 class PackPlan:
     """Permutation, lengths and slab layout of one ImprovedRnn call.
 
@@ -213,7 +221,7 @@ class PackPlan:
             row_len[h[rp:rp + n]] = h[2 * rp:2 * rp + n]                     # output row row_of[k] holds a sequence of len_of[k] steps
             cstart = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(row_len, out=cstart[1:])
-            tid = np.unique(cstart[:-1] // (129 - self.L), return_inverse=True)[1]      # dense ids: no empty tiles when L > 129-L
+            tid = _dense_ids(cstart[:-1] // (129 - self.L))                             # dense ids: no empty tiles when L > 129-L
             nt = int(tid[-1]) + 1
             tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
             self._snet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
@@ -239,7 +247,7 @@ class PackPlan:
             rows[h[rp:rp + n]] = h[2 * rp:2 * rp + n].astype(np.int64) + 2
             cstart = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(rows, out=cstart[1:])
-            tid = np.unique(cstart[:-1] // (129 - (self.L + 2)), return_inverse=True)[1]
+            tid = _dense_ids(cstart[:-1] // (129 - (self.L + 2)))
             nt = int(tid[-1]) + 1
             tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
             self._cnet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
