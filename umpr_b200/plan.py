@@ -101,12 +101,14 @@ def upload_int32(arr, device):
     return _RINGS[key].upload(arr, device)
 
 
-def _dense_ids(raw):
-    """Consecutive ids 0, 1, 2, ... for a non-decreasing integer array (``np.unique(raw, return_inverse=True)[1]`` without the sort)."""
+def _tile_starts(window, n):
+    """First sentence of every tile (+ n at the end) for a non-decreasing window index per sentence: a tile starts wherever the
+    index changes (what ``searchsorted`` over ``np.unique(...)`` ids gives, without the sort)."""
     import numpy as np
-    out = np.zeros(raw.size, dtype=np.int64)
-    np.cumsum(raw[1:] != raw[:-1], out=out[1:])
-    return out
+    change = np.empty(n, dtype=bool)
+    change[0] = True
+    np.not_equal(window[1:], window[:-1], out=change[1:])
+    return np.append(np.flatnonzero(change), n)
 
 
 class PackPlan:
@@ -221,9 +223,8 @@ class PackPlan:
             row_len[h[rp:rp + n]] = h[2 * rp:2 * rp + n]                     # output row row_of[k] holds a sequence of len_of[k] steps
             cstart = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(row_len, out=cstart[1:])
-            tid = _dense_ids(cstart[:-1] // (129 - self.L))                             # dense ids: no empty tiles when L > 129-L
-            nt = int(tid[-1]) + 1
-            tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
+            tso = _tile_starts(cstart[:-1] // (129 - self.L), n)       # a new tile wherever the window index changes: no empty tiles
+            nt = tso.size - 1
             self._snet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
         return self._snet_np
 
@@ -247,9 +248,8 @@ class PackPlan:
             rows[h[rp:rp + n]] = h[2 * rp:2 * rp + n].astype(np.int64) + 2
             cstart = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(rows, out=cstart[1:])
-            tid = _dense_ids(cstart[:-1] // (129 - (self.L + 2)))
-            nt = int(tid[-1]) + 1
-            tso = np.searchsorted(tid, np.arange(nt + 1), side="left")
+            tso = _tile_starts(cstart[:-1] // (129 - (self.L + 2)), n)
+            nt = tso.size - 1
             self._cnet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
         return self._cnet_np
 
