@@ -242,12 +242,9 @@ class PackPlan:
             import numpy as np
             if self.L + 2 > 128:
                 raise RuntimeError(f"umpr_b200: C-Net sentence length {self.L} exceeds 126")
-            n, rp = self.N, self.n_tiles * self.R
-            h = self._host_np
-            rows = np.empty(n, dtype=np.int64)
-            rows[h[rp:rp + n]] = h[2 * rp:2 * rp + n].astype(np.int64) + 2
-            cstart = np.zeros(n + 1, dtype=np.int64)
-            np.cumsum(rows, out=cstart[1:])
+            n = self.N
+            stab, s_nt = self._snet_host()                                   # prefix sums of the lengths are already there
+            cstart = stab[s_nt + 1:].astype(np.int64) + 2 * np.arange(n + 1, dtype=np.int64)
             tso = _tile_starts(cstart[:-1] // (129 - (self.L + 2)), n)
             nt = tso.size - 1
             self._cnet_np = (np.concatenate([tso, cstart]).astype(np.int32), nt)
