@@ -217,10 +217,10 @@ class PackPlan:
             import numpy as np
             if self.L > 128:
                 raise RuntimeError(f"umpr_b200: S-Net sentence length {self.L} exceeds 128")
-            n, rp = self.N, self.n_tiles * self.R
-            h = self._host_np
+            n = self.N
             row_len = np.empty(n, dtype=np.int64)
-            row_len[h[rp:rp + n]] = h[2 * rp:2 * rp + n]                     # output row row_of[k] holds a sequence of len_of[k] steps
+            # output row row_of[k] = si[si[k]] holds sequence si[k] (model.py:21), i.e. row si[j] holds sequence j
+            row_len[self.sorted_indices.numpy()] = self.lengths.numpy()
             cstart = np.zeros(n + 1, dtype=np.int64)
             np.cumsum(row_len, out=cstart[1:])
             tso = _tile_starts(cstart[:-1] // (129 - self.L), n)       # a new tile wherever the window index changes: no empty tiles
