@@ -146,3 +146,23 @@ def test_max_valid_positions_per_sample():
     p = PackPlan(lens, L, "cpu", tile_rows=128)
     eff = p.row_lengths().numpy().reshape(B, S)                              # lengths in OUTPUT-row order (the double un-sort)
     assert p.max_valid_per_sample(B) == int(eff.sum(1).max())
+
+
+def test_prefetched_plan_uploads_plan_and_tables_in_one_buffer():
+    """train.prepare_batch builds the pack plan and both valid-row tables off-thread; ``ensure_uploaded`` then ships them as ONE
+    buffer and hands out the three views (plan, S-Net table, convolution table) the kernels read."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.train import prepare_batch
+    b = prepare_batch(syn.make_batch("music_full", 110, vocab=500, seed=1), "cpu")      # 2200 sentences per side: 128-row tiles
+    lens = b[3]
+    pl = lens._umpr_plan
+    assert pl.R == 128 and pl.buf is None and pl._snet_np is not None and pl._cnet_np is not None
+    pl.ensure_uploaded()
+    assert torch.equal(pl.buf, pl.host)
+    (st, s_nt), (ct, c_nt) = pl.snet_table(), pl.cnet_table()
+    assert s_nt == pl._snet_np[1] and np.array_equal(st.numpy(), pl._snet_np[0])
+    assert c_nt == pl._cnet_np[1] and np.array_equal(ct.numpy(), pl._cnet_np[0])
+    assert st.is_contiguous() and ct.is_contiguous() and pl.buf.is_contiguous()
+    # the user->item side of the batch is small (550 sentences): no tables are prepared for it
+    small = b[5]._umpr_plan
+    assert small.R != 128 and getattr(small, "_snet_np", None) is None
