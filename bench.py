@@ -283,8 +283,11 @@ def main():
     h2d = tensor_bytes([host[0][j] for j in (0, 1, 2, 6, 7)])
     # plus the int32 pack plans built from the host lengths (3 or 5 GRU plans share 3 buffers)
     from umpr_b200.plan import PackPlan
-    h2d += sum(PackPlan(host[0][j], host[0][j - 3].shape[2], "cpu", tile_rows=128).host.numel() * 4
-               for j in ((3, 4) if syn.WORKLOADS[args.workload]["review_net_only"] else (3, 4, 5)))
+    for j in ((3, 4) if syn.WORKLOADS[args.workload]["review_net_only"] else (3, 4, 5)):
+        pl = PackPlan(host[0][j], host[0][j - 3].shape[2], "cpu")
+        h2d += pl.host.numel() * 4
+        if pl.R == 128:              # large sides also ship their valid-row tables (S-Net / co-attention / GEMM rows, convolution tiles)
+            h2d += pl._snet_host()[0].size * 4 + (pl._cnet_host()[0].size * 4 if pl.L + 2 <= 128 else 0)
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
