@@ -286,7 +286,7 @@ def main():
     for j in ((3, 4) if syn.WORKLOADS[args.workload]["review_net_only"] else (3, 4, 5)):
         pl = PackPlan(host[0][j], host[0][j - 3].shape[2], "cpu")
         h2d += pl.host.numel() * 4
-        if pl.R == 128:              # large sides also ship their valid-row tables (S-Net / co-attention / GEMM rows, convolution tiles)
+        if pl.R == 128 and pl.L <= 128:   # large sides also ship their valid-row tables (S-Net / co-attention / GEMM rows, convolution tiles)
             h2d += pl._snet_host()[0].size * 4 + (pl._cnet_host()[0].size * 4 if pl.L + 2 <= 128 else 0)
 
     line = {
