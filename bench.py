@@ -84,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -101,8 +101,75 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def host_threads():
+    """Host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the
+    CPU arm into a single-thread run: the count is taken from the affinity mask and set explicitly."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
+
+
+def load_reference():
+    """The reference's own ``src/model.py``, unmodified, from the git-ignored staging directory baseline/_ref/ (written by
+    ``__graft_entry__.build()`` in the build container; it travels to the GPU box with the snapshot).  Only harness patch
+    (SURVEY.md §8c): torchvision's VGG16 constructor - which would download weights - becomes ``nn.Flatten``, so ``photos`` carries
+    the backbone's 1000-d output features and model.py:216-218 passes them on unchanged.  → module, or None when not staged."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "src", "model.py")):
+        return None
+    import importlib
+    import torchvision
+    torchvision.models.vgg16 = lambda pretrained=True, num_classes=1000: torch.nn.Flatten()
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    return importlib.import_module("src.model")
+
+
+def cpu_reference_run(workload, batch, steps, warmup, seed=0):
+    """main.py:22-25,32-37 with the reference's own modules on the host cores: UMPR(config, word_emb) from baseline/_ref,
+    the weights of the GPU arm, torch.optim.Adam with the reference's parameter groups, forward + backward + step.
+    → (samples/s, ms/step, kind)."""
+    from umpr_b200 import synthetic as syn
+    ref = load_reference()
+    if ref is None:
+        v, ms = cpu_port_run(workload, batch, steps, warmup, seed)
+        return v, ms, "port"
+    table = syn.make_table(400003, seed=0)
+    ours = syn.build_model(workload, table, seed=0, device="cpu")           # parameter container only: same init as the GPU arm
+    model = ref.UMPR(syn.workload_config(workload), table.numpy())
+    r = model.load_state_dict(ours.state_dict(), strict=True)
+    assert not r.missing_keys and not r.unexpected_keys
+    del ours
+    opt = torch.optim.Adam([
+        {'params': (p for name, p in model.named_parameters() if 'bias' not in name)},
+        {'params': (p for name, p in model.named_parameters() if 'bias' in name), 'weight_decay': 0.}
+    ], 1e-6, weight_decay=1e-3)                                              # main.py:22-25 (config.py:13-14)
+    rno = syn.WORKLOADS[workload]["review_net_only"]
+    batches = []
+    for i in range(2):
+        b = list(syn.make_batch(workload, batch, seed=seed + i))
+        if not rno:
+            b[6] = b[6].reshape(*b[6].shape, 1, 1)                           # features where the reference expects images
+        batches.append(b)
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        model.train()                                                        # main.py:32-37
+        pred, loss = model(*batches[i % 2])
+        loss = loss.mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, "reference"
+
+
 def cpu_port_run(workload, batch, steps, warmup, seed=0):
-    """The reference's CPU path for this workload: oracle port with the library GRU calls of model.py:18-20,
+    """Fallback when baseline/_ref is not staged: the oracle port with the library GRU calls of model.py:18-20,
     forward + backward + torch.optim.Adam (main.py:22-25,32-37), all host threads."""
     from oracle import umpr_oracle as orc     # the one place bench.py executes oracle/: the CPU baseline
     from umpr_b200 import synthetic as syn
@@ -128,20 +195,31 @@ def cpu_port_run(workload, batch, steps, warmup, seed=0):
     return batch * steps / dt, dt / steps * 1e3
 
 
+def workload_name(workload):
+    return (f"{workload}: full UMPR, Amazon Digital Music shape (S=20, L=20, S_ui=5, V=1, Pc=1, GloVe-50d table 400003x50, VGG16 features)"
+            if workload == "music_full" else workload)
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the same step on the box's host cores, on the GPU arm's workload and
+    per-GPU batch.  Under torchrun only rank 0 works; every step is one per-GPU batch (a bounded sample of the N-GPU global batch:
+    CPU throughput in samples/s does not depend on how many such batches make up a global step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = args.ref_batch
-    val, ms = cpu_port_run(args.workload, B, args.steps, args.warmup)
-    cores = torch.get_num_threads()
+    cores = host_threads()
+    B = args.ref_batch or args.batch
+    val, ms, kind = cpu_reference_run(args.workload, B, args.steps, args.warmup)
+    what = "unmodified src/model.py from baseline/_ref (VGG16 -> Flatten: photos are features)" if kind == "reference" else "oracle port with torch's CPU GRU"
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "per_step_sample_batch": B, "device": "cpu", "host_threads": cores,
-                       "os_cpu_count": os.cpu_count()},
-            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} train steps of batch {B} ({args.workload}), oracle port with torch's CPU GRU"},
+            "config": {"workload": workload_name(args.workload), "per_gpu_batch": B, "global_batch": B * args.gpus,
+                       "parallelism": f"dp{args.gpus}", "step": "zero_grad+fwd+bwd+adam (main.py:32-37)", "device": "cpu",
+                       "host_threads": cores, "os_cpu_count": os.cpu_count(),
+                       "sample": f"each step = one batch of {B} samples on the host cores" + (f" (1/{args.gpus} of the global batch)" if args.gpus > 1 else "")},
+            "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} train steps of batch {B} ({args.workload}), {what}, fwd+bwd+Adam"},
             "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -159,7 +237,8 @@ def main():
     ap.add_argument("--impl", default="umpr_b200", choices=["umpr_b200", "reference"])
     ap.add_argument("--workload", default="music_full")
     ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch (weak scaling)")
-    ap.add_argument("--ref-batch", type=int, default=64, help="batch of one CPU reference step (config.py:12)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="batch of one CPU reference step (default: the GPU arm's per-GPU batch)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --batch per GPU; strong: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch64", action="store_true")
     ap.add_argument("--kernel-table", action="store_true", help="print the per-entry-point time table to stderr")
@@ -186,6 +265,10 @@ def main():
     umpr_b200.require_lib()
     peaks = load_peaks()
     B, K, W = args.batch, args.steps, args.warmup
+    if args.scaling == "strong":          # fixed GLOBAL batch: every rank takes the chunk DataParallel's scatter would give it
+        if B % world:
+            raise SystemExit(f"bench.py: --scaling strong needs a global batch divisible by the world size ({B} % {world})")
+        B = B // world
 
     table = syn.make_table(400003, seed=0)
     model = syn.build_model(args.workload, table, seed=0, device=dev)       # identical replicas: same seed on every rank
@@ -291,10 +374,9 @@ def main():
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: full UMPR, Amazon Digital Music shape (S=20, L=20, S_ui=5, V=1, Pc=1, GloVe-50d table "
-                               f"400003x50, VGG16 features)" if args.workload == "music_full" else args.workload,
+        "config": {"workload": workload_name(args.workload),
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "tokens_per_step_per_gpu": int(sum(tokens) / NB), "trainable_params": n_params,
                    "step": "zero_grad+fwd+bwd+allreduce+adam",
@@ -347,12 +429,16 @@ def main():
             line["batch64"] = {"value": round(64 * K / (ms64 / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms64 / K, 4),
                                "note": "reference default batch_size=64 (config.py:12), inputs resident"}
         if not args.no_cpu_baseline:
-            steps_cpu = 12
-            v, msc = cpu_port_run(args.workload, args.ref_batch, steps_cpu, 2)
-            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "ms_per_step": round(msc, 2),
-                                    "sample": f"{steps_cpu} train steps of batch {args.ref_batch} of the same workload "
-                                              f"(oracle port, torch CPU GRU, fwd+bwd+Adam), os.cpu_count={os.cpu_count()}"}
+            # the reference's CPU path on this box's host cores, same workload and SAME batch as the GPU arm (a bounded sample: 4 steps),
+            # and at the reference's default batch_size=64 (config.py:12) next to it
+            cores = host_threads()
+            v, msc, kind = cpu_reference_run(args.workload, B, 4, 1)
+            v64, ms64c, _ = cpu_reference_run(args.workload, 64, 10, 2)
+            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": round(msc, 2),
+                                    "sample": f"4 train steps of batch {B} of the same workload (fwd+bwd+Adam, "
+                                              + ("unmodified src/model.py from baseline/_ref" if kind == "reference" else "oracle port, torch CPU GRU")
+                                              + f"), os.cpu_count={os.cpu_count()}",
+                                    "batch64": {"value": round(v64, 3), "ms_per_step": round(ms64c, 2), "sample": "10 train steps of batch 64"}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

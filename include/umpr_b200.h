@@ -226,6 +226,10 @@ int umpr_cnet_conv_bwd_dx_tc(const float* dcfeat, const int32_t* cidx, const flo
                              int n_tiles, void* scratch, float* dx, int n_ctas, void* stream);
 
 /* ---- ControlNet tail: SSNet (model.py:142-143), Eq.18 (model.py:188, eps 1e-4 in code), gates (model.py:189-197) ---- */
+/* standalone SSNet (model.py:129-143): y[r] = sigmoid(x[r,:128] . w + b); backward adds into dw (128) / db (1), dx may be NULL */
+int umpr_ssnet_fwd(const float* x, const float* w, const float* b, long rows, float* y, void* stream);
+int umpr_ssnet_bwd(const float* x, const float* w, const float* y, const float* dy, long rows, float* dx, float* dw, float* db,
+                   void* stream);
 int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b, float eps,
                           int B, int Su, int V, float* senti, float* score, float* prefer_pos, float* prefer_neg, void* stream);
 int umpr_control_tail_bwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* senti,
@@ -257,7 +261,10 @@ int umpr_tanh_bwd(const float* y, const float* dy, long n, float* dx, void* stre
 
 /* ---- train step tail: main.py:22-26,37 Adam with L2 on non-bias tensors, fused over one flat parameter buffer ---- */
 int umpr_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* weight_decay /*per element*/,
-                   long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+                   long n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                   const float* shard_count /* device scalar or NULL: when given, the gradient scale is 1 / max(1, *shard_count) -
+                                               the number of replicas that received a chunk (DataParallel's loss.mean(), main.py:34) */,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -159,11 +159,25 @@ _ROUTING = None
 
 
 class routed:
-    """``with routed({"coattn": [(arg_u, arg_i)], "cnet": [cidx_ui, cidx_user, cidx_item]}) as r: ...`` ; r.margin afterwards."""
+    """``with routed({"coattn": [(arg_u, arg_i)], "cnet": [cidx_ui, cidx_user, cidx_item]}) as r: ...`` ; afterwards ``r.margin``
+    (how far below the oracle's own maximum the supplied winners are, relative to the value range) and ``r.stats`` (per kind:
+    ``total`` maxima, ``differ`` = supplied position is not the oracle's own arg-max, ``strict`` = ... and its value is strictly
+    below the oracle's maximum, i.e. a near-tie decided differently rather than an exact tie).
 
-    def __init__(self, picks):
+    ``mode``:
+      "routed"         values and gradient paths of the supplied positions                                   (default)
+      "routed_masked"  the same, but no gradient flows through the entries where the supplied position differs from the
+                       oracle's own arg-max
+      "own_masked"     the oracle's OWN maxima, no gradient through those same entries
+    The two masked modes differ only in forward values at the masked entries (by at most ``margin``): if they agree, the supplied
+    routing and the oracle's routing are identical everywhere else."""
+
+    def __init__(self, picks, mode: str = "routed"):
+        assert mode in ("routed", "routed_masked", "own_masked")
         self.picks = {k: list(v) for k, v in picks.items()}
+        self.mode = mode
         self.margin = {"coattn": 0.0, "cnet": 0.0}
+        self.stats = {k: {"total": 0, "differ": 0, "strict": 0} for k in ("coattn", "cnet")}
 
     def __enter__(self):
         global _ROUTING
@@ -177,14 +191,26 @@ class routed:
     def take(self, kind):
         return self.picks[kind].pop(0) if self.picks.get(kind) else None
 
+    def resolve(self, kind, top, got, differ):
+        """Book-keeping + the value to continue with.  top/got: the oracle's own maxima / the values at the supplied positions."""
+        st = self.stats[kind]
+        st["total"] += differ.numel()
+        st["differ"] += int(differ.sum())
+        st["strict"] += int((differ & (got.detach() < top.detach())).sum())
+        self.margin[kind] = max(self.margin[kind], float(((top - got).abs().max() / top.abs().max().clamp_min(1e-30)).detach()))
+        if self.mode == "routed":
+            return got
+        val = got if self.mode == "routed_masked" else top
+        return torch.where(differ, val.detach(), val)
+
 
 def _routed_max(t: Tensor, dim: int, idx, kind: str) -> Tensor:
-    top = t.max(dim=dim).values
+    top, own = t.max(dim=dim)
     if idx is None:
         return top
-    got = t.gather(dim, idx.to(torch.int64).clamp(min=0).unsqueeze(dim)).squeeze(dim)
-    _ROUTING.margin[kind] = max(_ROUTING.margin[kind], float(((top - got).max() / top.abs().max().clamp_min(1e-30)).detach()))
-    return got
+    idx = idx.to(torch.int64).clamp(min=0)
+    got = t.gather(dim, idx.unsqueeze(dim)).squeeze(dim)
+    return _ROUTING.resolve(kind, top, got, idx != own)
 
 
 def co_attention(gru_u: Tensor, gru_i: Tensor, M: Tensor):
@@ -257,9 +283,11 @@ def c_net(review_emb, lengths, params, threshold, prefix="control_net.c_net", im
         # routed: position AND the ReLU decision (index -1 = clipped) come from the implementation under test - relu(max) has a
         # kink at 0 just like max has one at a tie
         idx = pick.to(torch.int64)
-        top = torch.relu(pre).max(dim=-1)[0]
-        feat = torch.where(idx >= 0, pre.gather(-1, idx.clamp(min=0).unsqueeze(-1)).squeeze(-1), torch.zeros_like(top))
-        _ROUTING.margin["cnet"] = max(_ROUTING.margin["cnet"], float(((top - feat).abs().max() / top.abs().max().clamp_min(1e-30)).detach()))
+        top_pre, own = pre.max(dim=-1)
+        top = torch.relu(top_pre)
+        own = torch.where(top_pre > 0, own, torch.full_like(own, -1))                         # the oracle's own routing, same encoding
+        got = torch.where(idx >= 0, pre.gather(-1, idx.clamp(min=0).unsqueeze(-1)).squeeze(-1), torch.zeros_like(top))
+        feat = _ROUTING.resolve("cnet", top, got, idx != own)
     feat = feat.reshape(B, S, -1)
     view_p = torch.sigmoid(feat @ params[f"{prefix}.linear.0.weight"].t() + params[f"{prefix}.linear.0.bias"])
     view_p = torch.where(view_p < threshold, torch.zeros_like(view_p), view_p)                # model.py:124

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import cases
-from conftest import assert_close, load_golden
+from conftest import assert_close, rel_max, load_golden
 from oracle import umpr_oracle as orc
 
 TOL = 2e-6   # two fp32 CPU evaluation orders of the same arithmetic
@@ -135,6 +135,41 @@ def test_routed_oracle_with_its_own_argmax_is_the_plain_oracle(name):
     top2 = A.topk(2, dim=-2).values[..., :, 0]
     assert r2.margin["coattn"] > 0.0
     assert abs(r2.margin["coattn"] - float(((top2[:, 0] - top2[:, 1]).max()) / A.max(dim=-2).values.abs().max())) < 1e-6
+
+
+def test_routed_oracle_statistics_and_masked_modes():
+    """The book-keeping behind the large-batch GPU parity tests: ``stats`` counts the supplied positions that are not the oracle's
+    own arg-max (``differ``; ``strict`` when their value is lower), and the two masked modes - supplied routing vs. the oracle's own
+    routing, no gradient through the differing entries - give identical gradients, i.e. routing differs ONLY at the counted entries."""
+    c = cases.CASES["umpr_r_softM"]
+    params = cases.make_params(True, 1, c["vocab"], c["seed"], c["m_scale"])
+    batch = cases.make_batch(c)
+    user, item, ui, ul, il, uil, photos, labels = batch
+    t = params["embedding.weight"]
+    gru_u, gru_i, *_ = orc.r_net(t[user], t[item], ul, il, params)
+    A = torch.tanh(gru_i @ params["review_net.r_net.M"] @ gru_u.transpose(-1, -2))
+    own = (A.argmax(dim=-2), A.argmax(dim=-1))
+    second = A.topk(2, dim=-2).indices[..., 1, :]
+    cols = torch.arange(A.shape[-1])[None, :] < 3                      # the first three columns of every sample take the runner-up
+    picks = (torch.where(cols, second, own[0]), own[1])
+    with orc.routed({"coattn": [own]}) as r0:
+        orc.umpr_loss_and_grads(params, batch, review_net_only=True)
+    assert r0.stats["coattn"] == {"total": 2 * A.shape[0] * A.shape[-1], "differ": 0, "strict": 0}
+    res = {}
+    for mode in ("routed", "routed_masked", "own_masked"):
+        with orc.routed({"coattn": [picks]}, mode=mode) as r:
+            res[mode] = orc.umpr_loss_and_grads(params, batch, review_net_only=True)
+        assert r.stats["coattn"]["differ"] == 3 * A.shape[0]
+        assert 0 < r.stats["coattn"]["strict"] <= r.stats["coattn"]["differ"]
+    plain = orc.umpr_loss_and_grads(params, batch, review_net_only=True)
+    # masking never changes forward values: own_masked is the plain forward, routed_masked the routed one
+    assert torch.equal(res["own_masked"][1], plain[1]) and torch.equal(res["routed_masked"][1], res["routed"][1])
+    # ... but removes the gradient paths of exactly the re-routed entries: grad(M) changes in both masked modes
+    gM = "review_net.r_net.M"
+    assert rel_max(res["routed"][2][gM], plain[2][gM]) > 1e-3
+    assert rel_max(res["own_masked"][2][gM], plain[2][gM]) > 1e-4 and rel_max(res["routed_masked"][2][gM], res["routed"][2][gM]) > 1e-4
+    # (here the runner-up is far below the maximum, so the two masked modes see different forward values; in the GPU tests the
+    # margin is <= 2e-5 and they are asserted to agree)
 
 
 def test_pretrain_rnet_restatement_is_rnet_plus_torch_head():

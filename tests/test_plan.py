@@ -63,10 +63,10 @@ def test_sort_is_the_reference_call():
 
 
 def test_tile_rows_heuristic():
-    assert choose_tile_rows(1280, 148) == 32
+    assert choose_tile_rows(1280, 148) == 128      # reference default batch 64: >= TC_MIN_SEQS -> 128-row tiles for the tensor-core GRU
     assert choose_tile_rows(20480, 148) == 128
-    assert choose_tile_rows(5000, 148) == 128      # >= TC_MIN_SEQS: 128-row tiles for the tensor-core GRU
-    assert choose_tile_rows(2000, 148) == 32
+    assert choose_tile_rows(320, 148) == 128       # the user->item side of batch 64
+    assert choose_tile_rows(120, 148) == 32        # below two tiles: CUDA-core kernels
 
 
 @pytest.mark.parametrize("sizes,ctas", [([160], 74), ([160, 160], 74), ([40, 160, 160], 74), ([5], 74), ([1], 1), ([300, 7], 3)])
@@ -163,6 +163,6 @@ def test_prefetched_plan_uploads_plan_and_tables_in_one_buffer():
     assert s_nt == pl._snet_np[1] and np.array_equal(st.numpy(), pl._snet_np[0])
     assert c_nt == pl._cnet_np[1] and np.array_equal(ct.numpy(), pl._cnet_np[0])
     assert st.is_contiguous() and ct.is_contiguous() and pl.buf.is_contiguous()
-    # the user->item side of the batch is small (550 sentences): no tables are prepared for it
-    small = b[5]._umpr_plan
-    assert small.R != 128 and getattr(small, "_snet_np", None) is None
+    # a side below the tensor-core threshold (2 * 5 = 10 user->item sentences): CUDA-core tiles, no tables are prepared for it
+    tiny = prepare_batch(syn.make_batch("music_full", 2, vocab=500, seed=1), "cpu")[5]._umpr_plan
+    assert tiny.R != 128 and getattr(tiny, "_snet_np", None) is None

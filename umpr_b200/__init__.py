@@ -7,9 +7,10 @@ from . import _lib
 from .config import Config
 from .model import (CNet, ControlNet, ImprovedRnn, PackedReviews, ReviewNet, RNet, SNet, SSNet, UMPR, VisualNet)
 from .plan import PackPlan
+from .eval import evaluate_mse
 
 __all__ = ["Config", "ImprovedRnn", "RNet", "SNet", "CNet", "SSNet", "ReviewNet", "ControlNet", "VisualNet", "UMPR",
-           "PackedReviews", "PackPlan", "require_lib"]
+           "PackedReviews", "PackPlan", "evaluate_mse", "require_lib"]
 
 
 def require_lib():

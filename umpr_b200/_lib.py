@@ -69,7 +69,9 @@ SIGNATURES = {
     "umpr_loss_fwd": [P, P, P, P, P, P, I, I, F, P, P],
     "umpr_loss_bwd": [P, P, P, P, P, P, P, I, I, F, P, P, P, P, P, P],
     "umpr_tanh_bwd": [P, P, L, P, P],
-    "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P],
+    "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
+    "umpr_ssnet_fwd": [P, P, P, L, P, P],
+    "umpr_ssnet_bwd": [P, P, P, P, L, P, P, P, P],
 }
 
 

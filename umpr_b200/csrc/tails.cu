@@ -103,6 +103,35 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ y, const float* __rest
   if (i < n) { const float t = y[i]; dx[i] = dy[i] * (1.f - t * t); }
 }
 
+// ---------------------------------------------------------------- standalone SSNet (model.py:129-143): y = sigmoid(x · w + b), x (rows, 128)
+__global__ void __launch_bounds__(128) ssnet_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                        long rows, float* __restrict__ y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long r = (long)blockIdx.x * 4 + warp;
+  if (r >= rows) return;
+  const float4 xv = *reinterpret_cast<const float4*>(x + r * D + lane * 4);
+  const float4 wv = *reinterpret_cast<const float4*>(w + lane * 4);
+  const float a = warp_sum(xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w);
+  if (lane == 0) y[r] = sigmoidf_acc(a + b[0]);
+}
+// dpre = dy y (1-y);  dx = dpre w;  dw += sum_r dpre x_r;  db += sum_r dpre.  One CTA per strip of 32 rows, thread = feature column.
+__global__ void __launch_bounds__(128) ssnet_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y,
+                                                        const float* __restrict__ dy, long rows, float* __restrict__ dx,
+                                                        float* __restrict__ dw, float* __restrict__ db) {
+  const int tid = threadIdx.x;
+  const long r0 = (long)blockIdx.x * 32, r1 = r0 + 32 < rows ? r0 + 32 : rows;
+  const float wc = w[tid];
+  float dwc = 0.f, dbb = 0.f;
+  for (long r = r0; r < r1; ++r) {
+    const float yy = y[r], dp = dy[r] * yy * (1.f - yy);
+    if (dx) dx[r * D + tid] = dp * wc;
+    dwc += dp * x[r * D + tid];
+    dbb += dp;
+  }
+  atomicAdd(&dw[tid], dwc);
+  if (tid == 0) atomicAdd(db, dbb);
+}
+
 // ---------------------------------------------------------------- ControlNet tail (model.py:186-197)
 __global__ void __launch_bounds__(128) control_tail_fwd_kernel(const float* __restrict__ s, const float* __restrict__ view_p,
                                                                const float* __restrict__ c_out, const float* __restrict__ ss_w,
@@ -334,6 +363,19 @@ extern "C" int umpr_tanh_bwd(const float* y, const float* dy, long n, float* dx,
   tanh_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST>>>(y, dy, n, dx);
   return check_launch("tanh_bwd");
 }
+extern "C" int umpr_ssnet_fwd(const float* x, const float* w, const float* b, long rows, float* y, void* stream) {
+  if (rows <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) return fail_arg("ssnet_fwd: x and w must be 16-byte aligned");
+  ssnet_fwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, (cudaStream_t)stream>>>(x, w, b, rows, y);
+  return check_launch("ssnet_fwd");
+}
+extern "C" int umpr_ssnet_bwd(const float* x, const float* w, const float* y, const float* dy, long rows, float* dx /* may be NULL */,
+                              float* dw /* += */, float* db /* += */, void* stream) {
+  if (rows <= 0) return 0;
+  ssnet_bwd_kernel<<<(unsigned)((rows + 31) / 32), 128, 0, (cudaStream_t)stream>>>(x, w, y, dy, rows, dx, dw, db);
+  return check_launch("ssnet_bwd");
+}
+
 extern "C" int umpr_control_tail_fwd(const float* s, const float* view_p, const float* c_out, const float* ss_w, const float* ss_b,
                                      float eps, int B, int Su, int V, float* senti, float* score, float* prefer_pos, float* prefer_neg,
                                      void* stream) {

@@ -25,7 +25,10 @@ TENSOR_CORE_GEMM = True        # tcgen05 3xBF16 dense products (gemm_tc.cu); Fal
 TENSOR_CORE_COATTN = os.environ.get("UMPR_TC_COATTN", "1") == "1"     # tcgen05 affinity (coattn_tc.cu) is correct but epilogue-bound (profiles/r1b notes); fp32 kernel is faster for now
 
 
+GRU_SCHED_CTAS = None          # tests: CTAs per direction the fused GRU launches are scheduled onto (default: half the SMs)
 ROUTING_LOG = None             # tests: a list that receives ("coattn", arg (2,B,P)) / ("cnet", cidx (N,KC)) - the arg-max positions the kernels chose
+POISON_UNWRITTEN = False       # tests: fill the gradient rows the kernels leave unwritten (positions beyond a sentence's length, which the
+                               # packed GRU backward never reads, model.py:18) with NaN - parameter gradients must not change
 DIRECT_GRAD_ACCUM = False      # set by train.FlatTrainer for the duration of its backward pass (see _sinks)
 
 
@@ -58,6 +61,12 @@ def _sinks(params):
         out.append(flat[o:o + p.numel()].view(p.shape))
         o += p.numel()
     return out, out
+
+
+def _grad_like(x):
+    """Gradient buffer for a GRU output.  With a pack plan the kernels write the rows below each sentence's length only; the rest is
+    never read downstream (the packed GRU backward skips them) and stays unwritten - or NaN under POISON_UNWRITTEN."""
+    return torch.full_like(x, float("nan")) if POISON_UNWRITTEN else torch.empty_like(x)
 
 
 def _f32(t):
@@ -195,7 +204,7 @@ class _GruTcFn(Function):
             outs.append(out); hns.append(hn); svs.append(sv); hqs.append(hq)
             tokens += plan.tokens
         from .plan import build_schedule, upload_int32
-        sched, nq = build_schedule([p.tile_len for p in plans], max(1, _n_ctas(dev) // 2))
+        sched, nq = build_schedule([p.tile_len for p in plans], GRU_SCHED_CTAS or max(1, _n_ctas(dev) // 2))
         sched = upload_int32(sched, dev)
         call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
              work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
@@ -307,11 +316,26 @@ class GradSink:
     """Hand-over of one gradient between two autograd Functions that consume the same tensor.  ``gru_u`` feeds the co-attention
     and S-Net, and S-Net's other input is the co-attention's soft-max - so S-Net's backward always runs first.  Instead of returning
     its ``dx`` (autograd would then add it to the co-attention's ``dgu`` with one more full pass over both tensors), S-Net parks it
-    here and returns nothing; the co-attention backward folds it into the rows it writes anyway (``add_u`` / ``add_i``)."""
-    __slots__ = ("armed", "dx")
+    here and returns nothing; the co-attention backward folds it into the rows it writes anyway (``add_u`` / ``add_i``).
+
+    The hand-over is only taken when S-Net's ``word_soft`` IS the soft-max this sink's co-attention node produced (``key`` = its
+    storage address, checked in ``_SNetTcFn.forward``) - only then is the co-attention backward guaranteed to run after S-Net's and
+    to need this gradient.  A parked gradient that is still there when the backward pass ends raises (``_check_consumed``)."""
+    __slots__ = ("armed", "dx", "key")
 
     def __init__(self):
-        self.armed, self.dx = False, None
+        self.armed, self.dx, self.key = False, None, None
+
+    def park(self, dx):
+        self.dx = dx
+        from torch.autograd import Variable
+        Variable._execution_engine.queue_callback(self._check_consumed)      # runs when the current backward pass has finished
+
+    def _check_consumed(self):
+        if self.dx is not None:
+            self.dx = None
+            raise RuntimeError("umpr_b200: S-Net parked its input gradient for the co-attention backward, which never ran - the "
+                               "GRU would silently miss that gradient (call backward on a loss that reaches the co-attention node)")
 
 
 class _CoAttnFn(Function):
@@ -320,7 +344,7 @@ class _CoAttnFn(Function):
         ctx.sinks = sinks
         if sinks is not None:
             for sk, t in zip(sinks, (gu, gi)):
-                sk.armed = bool(t.requires_grad)
+                sk.armed, sk.dx = bool(t.requires_grad), None
         ctx.params = (M,)
         ctx.cst = (None, 0, 0, None, 0, 0)
         gu, gi, M = _f32(_chk(gu, "gru_u")), _f32(gi), _f32(M)
@@ -362,6 +386,8 @@ class _CoAttnFn(Function):
         if ROUTING_LOG is not None:
             ROUTING_LOG.append(("coattn", arg.clone()))
         ctx.save_for_backward(gu, gi, giM, M, soft, arg)
+        if sinks is not None:
+            sinks[0].key, sinks[1].key = soft[0].data_ptr(), soft[1].data_ptr()
         return soft[0], soft[1], atte[0], atte[1]
 
     @staticmethod
@@ -371,8 +397,8 @@ class _CoAttnFn(Function):
         B, P, _ = gu.shape
         dev = gu.device
         c = lambda t: None if t is None else _f32(t)
-        dgu = torch.empty_like(gu)
-        dgi = torch.empty_like(gi)
+        dgu = _grad_like(gu)
+        dgi = _grad_like(gi)
         dgiM = torch.empty_like(gi)
         adds = [None, None]
         if ctx.sinks is not None:
@@ -455,7 +481,8 @@ class _SNetTcFn(Function):
     @staticmethod
     def forward(ctx, plan, sink, gru_repr, word_soft, sent_length, Ms, Ws):
         ctx.params = (Ms, Ws)
-        ctx.sink = sink
+        # the hand-over is only valid when word_soft is the soft-max of the co-attention node that owns the sink (see GradSink)
+        ctx.sink = sink if (sink is not None and sink.key is not None and word_soft.data_ptr() == sink.key) else None
         x = _f32(_chk(gru_repr, "gru_repr"))
         Ms, Ws = _f32(Ms), _f32(Ws)
         word_soft = _f32(word_soft)
@@ -489,7 +516,7 @@ class _SNetTcFn(Function):
         d_wsum = torch.empty(N, dtype=torch.float32, device=dev) if want_ws else None
         call("umpr_snet_sentiment_bwd", ptr(self_atte), ptr(wsum), ptr(None if d_sentiment is None else _f32(d_sentiment)),
              ptr(None if d_self_atte is None else _f32(d_self_atte)), B, S, ptr(d_sa), ptr(d_wsum))
-        dx = torch.empty_like(x)        # positions beyond a sentence's length stay unwritten: the packed GRU never reads them (model.py:18)
+        dx = _grad_like(x)              # positions beyond a sentence's length stay unwritten: the packed GRU never reads them (model.py:18)
         (dMs, dWs), (rMs, rWs) = _sinks(ctx.params)
         table, n_tiles = ctx.plan.snet_table()
         T_v = float(ctx.plan.tokens)
@@ -497,7 +524,8 @@ class _SNetTcFn(Function):
              work=(6.0 * T_v * D * ATT, T_v * D * 8.0))
         d_word_soft = d_wsum.view(N, 1).expand(N, Wd).reshape(ws_shape) if want_ws else None
         if ctx.sink is not None and ctx.sink.armed and want_ws:
-            ctx.sink.dx, dx = dx, None            # the co-attention backward (which needs d_word_soft, so it runs after us) adds it in
+            ctx.sink.park(dx)                     # the co-attention backward (which needs d_word_soft, so it runs after us) adds it in
+            dx = None
         return None, None, dx, d_word_soft, None, rMs, rWs
 
 
@@ -606,7 +634,7 @@ class _CNetTailFn(Function):
         (d_conv_w, d_conv_b, d_lin_w, d_lin_b), rets = _sinks(ctx.params)
         call("umpr_cnet_head_bwd", ptr(cfeat), ptr(cidx), ptr(view_p), ptr(lin_w), ptr(None if d_view_p is None else _f32(d_view_p)),
              ptr(None if d_final is None else _f32(d_final)), B, S, V, KC, ptr(dcfeat), ptr(d_lin_w), ptr(d_lin_b), ptr(d_conv_b))
-        dx = torch.empty_like(x)        # with a plan: rows beyond a sentence's length stay unwritten (never read, model.py:18)
+        dx = _grad_like(x) if getattr(ctx, "keep", None) is not None else torch.empty_like(x)   # with a plan: rows beyond a sentence's length stay unwritten (never read, model.py:18)
         wt = torch.empty(_workspace_floats("cnet_conv_bwd_dx", KC), dtype=torch.float32, device=dev)
         cst = None
         plan = getattr(ctx, "keep", None)
@@ -672,6 +700,38 @@ class _ControlTailFn(Function):
         call("umpr_control_tail_bwd", ptr(s), ptr(view_p), ptr(c_out), ptr(ss_w), ptr(senti), ptr(out[0]), ptr(z(d_pp)), ptr(z(d_pn)),
              ctx.eps, B, Su, V, ptr(d_s), ptr(d_vp), ptr(d_co), ptr(dw_), ptr(db_))
         return d_s, d_vp, d_co, rw_, rb_, None
+
+
+class _SSNetFn(Function):
+    """Standalone SSNet (model.py:142-143): sigmoid(Linear(128 -> 1)).  Inside UMPR it is fused into the ControlNet tail."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.params = (w, b)
+        ctx.shape = tuple(x.shape)
+        x, w, b = _f32(_chk(x, "sentiment_emb")), _f32(w), _f32(b)
+        if x.shape[-1] != D or w.numel() != D:
+            raise RuntimeError("umpr_b200: SSNet is built for input_size=128 (2 * gru_size)")
+        rows = x.numel() // D
+        y = torch.empty(rows, dtype=torch.float32, device=x.device)
+        call("umpr_ssnet_fwd", ptr(x), ptr(w), ptr(b), rows, ptr(y))
+        ctx.save_for_backward(x, w, y)
+        return y.view(*ctx.shape[:-1], 1)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        rows = y.numel()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        (dw, db), (rw, rb) = _sinks(ctx.params)
+        call("umpr_ssnet_bwd", ptr(x), ptr(w), ptr(y), ptr(_f32(dy).reshape(-1)), rows, ptr(dx), ptr(dw), ptr(db))
+        return (dx.view(ctx.shape) if dx is not None else None), rw, rb
+
+
+def ss_net(x, w, b):
+    """→ sigmoid(x @ w^T + b), shape (..., 1)."""
+    return _SSNetFn.apply(x, w, b)
 
 
 def control_tail(s, view_p, c_out, ss_w, ss_b, eps):

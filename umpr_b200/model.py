@@ -1,8 +1,8 @@
 """Drop-in mirror of the reference ``src/model.py`` module tree on the B200 kernels.
 
 Same class names, constructor arguments, ``forward`` signatures, return tuples and ``state_dict`` keys
-(SURVEY.md §8b), so ``main.py:33`` / ``evaluate.py:11`` / ``pretrain_rnet.py:165`` style host code and reference
-checkpoints work unchanged.  The ``nn`` sub-modules (``nn.GRU``, ``nn.Conv1d``, ``nn.Linear``) are kept ONLY as
+(SURVEY.md §8b), so ``main.py:33`` / ``evaluate.py:11`` / ``pretrain_rnet.py:165`` style host code works unchanged and reference
+checkpoints load through ``load_reference_checkpoint`` (it drops the out-of-scope ``visual_net.vgg16.*`` backbone keys).  The ``nn`` sub-modules (``nn.GRU``, ``nn.Conv1d``, ``nn.Linear``) are kept ONLY as
 parameter containers with the reference's initialisation; their ``forward`` is never called — every operator runs
 through ``umpr_b200.functional`` → ``libumpr_b200.so``.  There is no CPU path: parameters must be on a CUDA device.
 """
@@ -15,6 +15,39 @@ from . import functional as F
 from .plan import PackPlan
 
 EQ18_EPS = 1e-4   # model.py:188 (the code, not the readme's 1e-6, is the oracle)
+
+
+def _on(device):
+    """Every kernel is launched on the CURRENT device's stream (``_lib.call``): make the device that holds the data current for the
+    duration of a forward (the reference lets the model live on any ``config.device``).  Backward needs no guard: the autograd engine
+    runs each node on the worker thread of the device its forward ran on."""
+    if device.type != "cuda":
+        raise RuntimeError("umpr_b200: move the module to a CUDA device first (there is no CPU path)")
+    return torch.cuda.device(device)
+
+
+def _load_pretrained(module, path, what):
+    """``pretrained=`` of model.py:31-34,66-69,101-104,135-138: the reference pickles whole modules (``torch.save(model)``) and swallows
+    any failure after printing.  Same behaviour, except that the load uses ``weights_only=False`` (PyTorch >= 2.6 would otherwise
+    reject every such pickle and the pre-trained weights would silently never load) and that a failure is also a RuntimeWarning."""
+    import warnings
+    try:
+        obj = torch.load(path, weights_only=False)
+        module.load_state_dict(obj.state_dict() if hasattr(obj, "state_dict") else obj)
+    except Exception as e:                                   # noqa: BLE001 - the reference's bare except
+        print(f'Failed to load {what} pre-trained weights from "{path}"')
+        warnings.warn(f'umpr_b200: {what} pre-trained weights NOT loaded from "{path}": {e!r}', RuntimeWarning, stacklevel=3)
+
+
+def load_reference_checkpoint(model, checkpoint, strict: bool = True):
+    """Load a checkpoint written by the reference (``torch.save(model)`` of a ``src.model.UMPR``, main.py:47-52 - or its state_dict)
+    into the drop-in ``model``.  The reference's ``visual_net.vgg16.*`` backbone parameters have no counterpart here (the backbone is
+    upstream of this path, ``photos`` are its features) and are dropped; every other key must match when ``strict``."""
+    obj = torch.load(checkpoint, weights_only=False) if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "read") else checkpoint
+    sd = obj.state_dict() if hasattr(obj, "state_dict") else dict(obj)
+    sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}          # a DataParallel wrapper (main.py:82)
+    sd = {k: v for k, v in sd.items() if not k.startswith("visual_net.vgg16.")}
+    return model.load_state_dict(sd, strict=strict)
 
 
 class PackedReviews:
@@ -49,6 +82,19 @@ class PackedReviews:
         return self._xp
 
 
+def _tag(gru_repr, plan, sink=None):
+    """Attach the pack plan that produced an ImprovedRnn output (rows beyond each sentence's length are exactly zero) - and the
+    version counter of the tensor at that moment: an in-place modification afterwards invalidates the tag (``_tagged_plan``)."""
+    gru_repr._umpr_plan, gru_repr._umpr_sink, gru_repr._umpr_version = plan, sink, gru_repr._version
+
+
+def _tagged_plan(gru_repr):
+    """→ (plan, sink) if ``gru_repr`` is an untouched ImprovedRnn output of this library, else (None, None)."""
+    if getattr(gru_repr, "_umpr_plan", None) is None or getattr(gru_repr, "_umpr_version", -1) != gru_repr._version:
+        return None, None
+    return gru_repr._umpr_plan, getattr(gru_repr, "_umpr_sink", None)
+
+
 def _gru_weights(gru: nn.GRU):
     return [gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0,
             gru.weight_ih_l0_reverse, gru.weight_hh_l0_reverse, gru.bias_ih_l0_reverse, gru.bias_hh_l0_reverse]
@@ -69,11 +115,12 @@ class ImprovedRnn(nn.Module):
                                       "bidirectional, 1 layer, hidden_size=64, input_size<64")
 
     def forward(self, data, lengths):
-        if isinstance(data, PackedReviews):
-            pk = data
-        else:
-            pk = PackedReviews(lengths, emb=data.unsqueeze(0))
-        return self.run(pk)
+        with _on(self.module.weight_ih_l0.device):
+            if isinstance(data, PackedReviews):
+                pk = data
+            else:
+                pk = PackedReviews(lengths, emb=data.unsqueeze(0))
+            return self.run(pk)
 
     def run(self, pk: PackedReviews, want_hidden=True):
         return F.gru_forward(pk.plan, pk.xp if pk.xq is None else None, pk.E, _gru_weights(self.module), want_hidden, xq=pk.xq)
@@ -92,24 +139,22 @@ class RNet(nn.Module):
         self.gru = ImprovedRnn(nn.GRU, input_size=gru_in, hidden_size=gru_out, batch_first=True, bidirectional=True)
         self.M = nn.Parameter(torch.randn(2 * gru_out, 2 * gru_out))
         if pretrained is not None:
-            try:
-                self.load_state_dict(torch.load(pretrained).state_dict())
-            except Exception:
-                print(f'Failed to load R-Net pre-trained weights from "{pretrained}"')
+            _load_pretrained(self, pretrained, "R-Net")
 
     def forward(self, user_emb, item_emb, u_lengths, i_lengths):
-        pu = user_emb if isinstance(user_emb, PackedReviews) else PackedReviews(u_lengths, emb=user_emb)
-        pi = item_emb if isinstance(item_emb, PackedReviews) else PackedReviews(i_lengths, emb=item_emb)
-        (gru_u, _), (gru_i, _) = self.gru.run_many([pu, pi])           # model.py:45-46: shared weights, one fused launch
-        gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
-        gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
-        sinks = (F.GradSink(), F.GradSink())
-        # valid-row tables pay for their host-side cost on large sides only (the small-batch regime is host-bound)
-        plans = (pu.plan, pi.plan) if (pu.plan.R == 128 and pi.plan.R == 128) else None
-        soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=plans, sinks=sinks)
-        gru_u._umpr_plan, gru_i._umpr_plan = pu.plan, pi.plan          # lets S-Net skip the positions beyond each sentence's length
-        gru_u._umpr_sink, gru_i._umpr_sink = sinks                      # and hand its dx to the co-attention backward (F.GradSink)
-        return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
+        with _on(self.M.device):
+            pu = user_emb if isinstance(user_emb, PackedReviews) else PackedReviews(u_lengths, emb=user_emb)
+            pi = item_emb if isinstance(item_emb, PackedReviews) else PackedReviews(i_lengths, emb=item_emb)
+            (gru_u, _), (gru_i, _) = self.gru.run_many([pu, pi])           # model.py:45-46: shared weights, one fused launch
+            gru_u = gru_u.view(pu.B, pu.S * pu.L, -1)
+            gru_i = gru_i.view(pi.B, pi.S * pi.L, -1)
+            sinks = (F.GradSink(), F.GradSink())
+            # valid-row tables pay for their host-side cost on large sides only (the small-batch regime is host-bound)
+            plans = (pu.plan, pi.plan) if (pu.plan.R == 128 and pi.plan.R == 128) else None
+            soft_u, soft_i, atte_u, atte_i = F.co_attention(gru_u, gru_i, self.M, plans=plans, sinks=sinks)
+            _tag(gru_u, pu.plan, sinks[0])          # lets S-Net skip the positions beyond each sentence's length
+            _tag(gru_i, pi.plan, sinks[1])          # and hand its dx to the co-attention backward (F.GradSink)
+            return gru_u, gru_i, soft_u, soft_i, atte_u, atte_i
 
 
 class SNet(nn.Module):
@@ -120,14 +165,12 @@ class SNet(nn.Module):
         self.Ms = nn.Parameter(torch.randn(self_atte_size, repr_size))
         self.Ws = nn.Parameter(torch.randn(1, self_atte_size))
         if pretrained is not None:
-            try:
-                self.load_state_dict(torch.load(pretrained).state_dict())
-            except Exception:
-                print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
+            _load_pretrained(self, pretrained, "S-Net")
 
     def forward(self, gru_repr, word_soft, sent_length):
-        return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws, plan=getattr(gru_repr, "_umpr_plan", None),
-                       sink=getattr(gru_repr, "_umpr_sink", None))
+        plan, sink = _tagged_plan(gru_repr)
+        with _on(self.Ms.device):
+            return F.s_net(gru_repr, word_soft, sent_length, self.Ms, self.Ws, plan=plan, sink=sink)
 
 
 class CNet(nn.Module):
@@ -143,14 +186,12 @@ class CNet(nn.Module):
         )
         self.linear = nn.Sequential(nn.Linear(k_count, view_size), nn.Sigmoid())
         if pretrained is not None:
-            try:
-                self.load_state_dict(torch.load(pretrained).state_dict())
-            except Exception:
-                print(f'Failed to load S-Net pre-trained weights from "{pretrained}"')
+            _load_pretrained(self, pretrained, "S-Net")
 
     def forward(self, review_emb, lengths):
-        pk = review_emb if isinstance(review_emb, PackedReviews) else PackedReviews(lengths, emb=review_emb)
-        return self.forward_many([pk])[0]
+        with _on(self.cnn[0].weight.device):
+            pk = review_emb if isinstance(review_emb, PackedReviews) else PackedReviews(lengths, emb=review_emb)
+            return self.forward_many([pk])[0]
 
     def forward_many(self, pks):
         """``forward`` for several review sides (model.py:182-184 calls C-Net on ui, user and item with shared weights):
@@ -158,7 +199,7 @@ class CNet(nn.Module):
         res = []
         for pk, (gru_repr, _) in zip(pks, self.gru.run_many(pks)):
             gru_repr = gru_repr.view(pk.B, pk.S * pk.L, -1)
-            gru_repr._umpr_plan = pk.plan
+            _tag(gru_repr, pk.plan)
             view_p, final_repr = F.c_net_tail(gru_repr, pk.S, pk.L, self.cnn[0].weight, self.cnn[0].bias,
                                               self.linear[0].weight, self.linear[0].bias, self.threshold, plan=pk.plan if pk.plan.R == 128 else None)
             res.append((gru_repr, view_p, final_repr))
@@ -166,26 +207,18 @@ class CNet(nn.Module):
 
 
 class SSNet(nn.Module):
-    """model.py:129-143.  Used through ``ControlNet`` (fused with Eq.18); standalone forward kept for API parity."""
+    """model.py:129-143.  Inside ``ControlNet`` it is fused with Eq.18; the standalone forward (trainable) is its own small kernel."""
 
     def __init__(self, input_size, pretrained: str = None):
         super().__init__()
         self.linear = nn.Sequential(nn.Linear(input_size, 1), nn.Sigmoid())
         if pretrained is not None:
-            try:
-                self.load_state_dict(torch.load(pretrained).state_dict())
-            except Exception:
-                print(f'Failed to load SS-Net pre-trained weights from "{pretrained}"')
+            _load_pretrained(self, pretrained, "SS-Net")
 
     def forward(self, sentiment_emb):
-        x = sentiment_emb
-        y = torch.empty(*x.shape[:-1], 1, dtype=torch.float32, device=x.device)
-        w, b = self.linear[0].weight, self.linear[0].bias
-        if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
-            raise NotImplementedError("umpr_b200: SSNet trains through ControlNet's fused tail; standalone SSNet is inference-only")
-        rows = x.numel() // x.shape[-1]
-        F.sgemm(x.contiguous(), (x.shape[-1], 1), w.detach(), (1, x.shape[-1]), y, 1, rows, 1, x.shape[-1], bias=b.detach(), act=3)
-        return y
+        lin = self.linear[0]
+        with _on(lin.weight.device):
+            return F.ss_net(sentiment_emb, lin.weight, lin.bias)
 
 
 class ReviewNet(nn.Module):
@@ -202,10 +235,11 @@ class ReviewNet(nn.Module):
     def forward(self, user_emb, item_emb, u_lengths, i_lengths):
         u_s_length = user_emb.L if isinstance(user_emb, PackedReviews) else user_emb.shape[-2]
         i_s_length = item_emb.L if isinstance(item_emb, PackedReviews) else item_emb.shape[-2]
-        gru_u, gru_i, soft_u, soft_i, atte_u, atte_i = self.r_net(user_emb, item_emb, u_lengths, i_lengths)
-        _, sentiment_u = self.s_net_u(gru_u, soft_u, u_s_length)
-        _, sentiment_i = self.s_net_i(gru_i, soft_i, i_s_length)
-        return F.text_match(atte_u, sentiment_u, atte_i, sentiment_i, self.linear_u.weight, self.linear_i.weight)
+        with _on(self.linear_u.weight.device):
+            gru_u, gru_i, soft_u, soft_i, atte_u, atte_i = self.r_net(user_emb, item_emb, u_lengths, i_lengths)
+            _, sentiment_u = self.s_net_u(gru_u, soft_u, u_s_length)
+            _, sentiment_i = self.s_net_i(gru_i, soft_i, i_s_length)
+            return F.text_match(atte_u, sentiment_u, atte_i, sentiment_i, self.linear_u.weight, self.linear_i.weight)
 
 
 class ControlNet(nn.Module):
@@ -219,13 +253,14 @@ class ControlNet(nn.Module):
 
     def forward(self, user_emb, item_emb, ui_emb, u_lengths, i_lengths, ui_lengths):
         ui_s_length = ui_emb.L if isinstance(ui_emb, PackedReviews) else ui_emb.shape[-2]
-        pks = [e if isinstance(e, PackedReviews) else PackedReviews(l, emb=e)
-               for e, l in ((ui_emb, ui_lengths), (user_emb, u_lengths), (item_emb, i_lengths))]
-        (gru_repr, view_p, c_net_out), (_, _, c_u), (_, _, c_i) = self.c_net.forward_many(pks)      # model.py:182-184
-        s, _ = self.s_net(gru_repr, view_p, ui_s_length)
         lin = self.ss_net.linear[0]
-        prefer_pos, prefer_neg = F.control_tail(s, view_p, c_net_out, lin.weight, lin.bias, EQ18_EPS)
-        return c_u, c_i, prefer_pos, prefer_neg
+        with _on(lin.weight.device):
+            pks = [e if isinstance(e, PackedReviews) else PackedReviews(l, emb=e)
+                   for e, l in ((ui_emb, ui_lengths), (user_emb, u_lengths), (item_emb, i_lengths))]
+            (gru_repr, view_p, c_net_out), (_, _, c_u), (_, _, c_i) = self.c_net.forward_many(pks)      # model.py:182-184
+            s, _ = self.s_net(gru_repr, view_p, ui_s_length)
+            prefer_pos, prefer_neg = F.control_tail(s, view_p, c_net_out, lin.weight, lin.bias, EQ18_EPS)
+            return c_u, c_i, prefer_pos, prefer_neg
 
 
 class VisualNet(nn.Module):
@@ -240,7 +275,8 @@ class VisualNet(nn.Module):
 
     def forward(self, images, c_u, c_i):
         feat = images.reshape(images.shape[0], images.shape[1], images.shape[2], -1)
-        return F.visual_tail(feat, c_u, c_i, self.pos_v_emb, self.neg_v_emb, self.linear.weight, self.linear.bias)
+        with _on(self.pos_v_emb.device):
+            return F.visual_tail(feat, c_u, c_i, self.pos_v_emb, self.neg_v_emb, self.linear.weight, self.linear.bias)
 
 
 class UMPR(nn.Module):
@@ -266,6 +302,10 @@ class UMPR(nn.Module):
         device = table.device
         if device.type != "cuda":
             raise RuntimeError("umpr_b200: move the model to a CUDA device first (there is no CPU path)")
+        with _on(device):
+            return self._forward(table, device, user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels)
+
+    def _forward(self, table, device, user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels):
         to = lambda v: v.to(device, non_blocking=True)
         user_reviews, item_reviews = to(user_reviews), to(item_reviews)
         labels = to(labels)

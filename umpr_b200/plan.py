@@ -14,7 +14,8 @@ from . import _lib
 TILE_ROWS = (32, 64, 128)
 
 
-TC_MIN_SEQS = 2048     # from this many sequences on, a call runs on the fused tensor-core GRU kernel (tiles of 128)
+TC_MIN_SEQS = 256      # from this many sequences on (two full tiles), a call runs on the fused tensor-core GRU kernel (tiles of 128):
+                       # the reference default batch_size=64 (1280 sentences per side, 320 user->item sentences) is on tcgen05
 
 
 def choose_tile_rows(n_seq: int, n_sm: int) -> int:

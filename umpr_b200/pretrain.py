@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from . import functional as F
-from .model import PackedReviews, RNet
+from .model import PackedReviews, RNet, _on
 
 
 class PretrainRNet(nn.Module):
@@ -23,12 +23,13 @@ class PretrainRNet(nn.Module):
         device = table.device
         if device.type != "cuda":
             raise RuntimeError("umpr_b200: this path runs on CUDA only (no CPU fallback); move the model to a GPU")
-        u, i, target = [d.to(device) for d in (u, i, target)]                       # pretrain_rnet.py:157
-        pu = PackedReviews(u_length.view(-1, 1), ids=u.view(u.shape[0], 1, u.shape[1]), table=table)    # :158-161, embedding gather fused
-        pi = PackedReviews(i_length.view(-1, 1), ids=i.view(i.shape[0], 1, i.shape[1]), table=table)
-        _, _, _, _, att_u, att_i = self.r_net(pu, pi, None, None)                    # :164
-        lin = self.linear[0]
-        return F.bce_head(att_u, att_i, lin.weight, lin.bias, target.to(torch.float32))   # :165-168
+        with _on(device):
+            u, i, target = [d.to(device) for d in (u, i, target)]                       # pretrain_rnet.py:157
+            pu = PackedReviews(u_length.view(-1, 1), ids=u.view(u.shape[0], 1, u.shape[1]), table=table)    # :158-161, embedding gather fused
+            pi = PackedReviews(i_length.view(-1, 1), ids=i.view(i.shape[0], 1, i.shape[1]), table=table)
+            _, _, _, _, att_u, att_i = self.r_net(pu, pi, None, None)                    # :164
+            lin = self.linear[0]
+            return F.bce_head(att_u, att_i, lin.weight, lin.bias, target.to(torch.float32))   # :165-168
 
     def save_r_net(self, save_path):
         torch.save(self.r_net, save_path)

@@ -67,7 +67,11 @@ class FlatTrainer:
         self.model, self.names = model, [n for n, _ in named]
         self.n_params = sum(p.numel() for _, p in named)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # the gradient bucket carries one extra element: 1.0 on every rank that received a chunk of the batch.  After the all-reduce
+        # it holds the number of non-empty shards, which is what DataParallel's loss.mean() divides by (main.py:34)
+        self.bucket = torch.zeros(total + ALIGN, dtype=torch.float32, device=dev)
+        self.grad = self.bucket[:total]
+        self.shard_count = self.bucket[total:total + 1]
         self.wd = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
@@ -80,6 +84,7 @@ class FlatTrainer:
                 p.grad = self.grad[o:o + k].view_as(p)          # autograd accumulates straight into the bucket
                 self.wd[o:o + k] = 0.0 if "bias" in n else weight_decay      # main.py:23-24
                 o += up(k)
+        self._grad_ptrs = [(n, p, p.grad.data_ptr()) for n, p in named]
         self.lr, self.betas, self.eps, self.lr_decay = lr, betas, eps, lr_decay
         self.step_no = 0
         self.pg = process_group
@@ -90,20 +95,30 @@ class FlatTrainer:
             self.comm = AbiComm(dist.get_rank(process_group), self.world, dev, process_group)
 
     def zero_grad(self):
-        self.grad.zero_()
+        self.bucket.zero_()
+
+    def check_bucket(self):
+        """The kernels (and autograd) accumulate into ``p.grad``, which must still be the view into the flat bucket: ``model.zero_grad()``
+        (set_to_none) or an outside optimizer detaches it, and Adam would then silently step on zeros."""
+        for n, p, addr in self._grad_ptrs:
+            if p.grad is None or p.grad.data_ptr() != addr:
+                raise RuntimeError(f"umpr_b200: the gradient of {n!r} no longer lives in FlatTrainer's bucket (was model.zero_grad() or "
+                                   "another optimizer used?) - use FlatTrainer.zero_grad()")
 
     def reduce_gradients(self):
         """One flat bucket (0.57–1.0 MB): latency-bound, so a single NCCL all-reduce is the whole exchange."""
         if self.comm is not None:
-            self.comm.all_reduce(self.grad)
+            self.comm.all_reduce(self.bucket)
         elif self.world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def optimizer_step(self):
+    def optimizer_step(self, use_shard_count: bool = False):
+        """``use_shard_count``: scale by 1 / (number of ranks that had a shard), read on the device from the all-reduced bucket."""
         self.step_no += 1
         if self.flat.is_cuda:
             call("umpr_adam_step", ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.wd), self.flat.numel(),
-                 float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_no, 1.0 / self.world)
+                 float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_no, 1.0 / self.world,
+                 ptr(self.shard_count) if use_shard_count else None)
         else:
             raise RuntimeError("umpr_b200: optimizer runs on the GPU only")
 
@@ -111,19 +126,25 @@ class FlatTrainer:
         self.lr *= self.lr_decay                                   # ExponentialLR, main.py:26,54
 
     def train_step(self, batch):
-        """main.py:32-37 on this rank's shard.  Returns (prediction, loss) of the shard."""
+        """main.py:32-37 on this rank's shard.  Returns (prediction, loss) of the shard.  ``batch=None``: this rank got no chunk of
+        a short last batch (``shard_batch``) - it still takes part in the all-reduce and applies the same update as everybody else."""
         from . import functional as F
         if not self.model.training:          # nn.Module.train() walks the whole module tree: ~0.2 ms of host time per step when repeated
             self.model.train()
         self.zero_grad()
-        pred, loss = self.model(*batch)
-        F.DIRECT_GRAD_ACCUM = True          # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
-        try:
-            (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
-        finally:
-            F.DIRECT_GRAD_ACCUM = False
+        pred = loss = None
+        if batch is not None:
+            self.check_bucket()
+            pred, loss = self.model(*batch)
+            F.DIRECT_GRAD_ACCUM = True      # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
+            try:
+                (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
+            finally:
+                F.DIRECT_GRAD_ACCUM = False
+            if self.world > 1:
+                self.shard_count.fill_(1.0)
         self.reduce_gradients()
-        self.optimizer_step()
+        self.optimizer_step(use_shard_count=self.world > 1)
         return pred, loss
 
 
