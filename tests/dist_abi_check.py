@@ -37,6 +37,24 @@ for kind in ("torch", "abi"):
 # float atomics make two runs of the same step differ in the last bits: compare to 1e-6 of the parameter scale
 err = float((out[0] - out[1]).abs().max() / out[0].abs().max())
 assert err < 1e-6, err
+# a short last batch: 1 sample over 2 ranks -> rank 1 gets no chunk (DataParallel would use one replica).  Both ranks must end with
+# the parameters a single-GPU step on that one sample gives.
+one = syn.make_batch("music_full", 1, vocab=3000, seed=4)
+sh = shard_batch(one, rank, world)
+assert (sh is None) == (rank == 1)
+model = syn.build_model("music_full", table, seed=1, device=dev)
+tr = FlatTrainer(model, lr=1e-3)
+tr.train_step(sh)
+solo = syn.build_model("music_full", table, seed=1, device=dev)
+ts = FlatTrainer(solo, lr=1e-3, process_group=None)
+ts.world = 1                                               # a private single-replica step on the same sample
+ts.zero_grad()
+pred, loss = solo(*one)
+loss.backward()
+ts.optimizer_step()
+torch.cuda.synchronize()
+err = float((tr.flat - ts.flat).abs().max() / ts.flat.abs().max())
+assert err < 1e-6, ("short batch", rank, err)
 comm.close()
 dist.barrier()
 if rank == 0:

@@ -345,3 +345,103 @@ def test_pretrain_rnet_vs_oracle(B, L):
                 assert float((got.cpu() - ref).abs().max()) <= TOL * scale, (k, float(got), float(ref), scale)
             else:
                 _check_grad(k, got, ref)
+
+
+def test_standalone_ssnet_trains():
+    """SSNet (model.py:129-143) called on its own: sigmoid(Linear(128 -> 1)), forward and all three gradients against torch."""
+    import umpr_b200
+    torch.manual_seed(8)
+    net = umpr_b200.SSNet(128).to(DEV)
+    x = (torch.randn(6, 5, 128, device=DEV) * 0.7).requires_grad_(True)
+    gy = torch.randn(6, 5, 1, device=DEV)
+    y = net(x)
+    assert y.shape == (6, 5, 1)
+    (y * gy).sum().backward()
+    w, b = net.linear[0].weight.detach().clone().requires_grad_(True), net.linear[0].bias.detach().clone().requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    yr = torch.sigmoid(xr @ w.t() + b)
+    (yr * gy).sum().backward()
+    assert_close(y, yr, 1e-6, "ssnet forward")
+    assert_close(x.grad, xr.grad, 1e-5, "ssnet dx")
+    assert_close(net.linear[0].weight.grad, w.grad, 1e-5, "ssnet dw")
+    assert_close(net.linear[0].bias.grad, b.grad, 1e-5, "ssnet db")
+
+
+def test_unwritten_gradient_rows_are_never_read():
+    """The kernels leave the gradient rows of positions beyond a sentence's length unwritten (the packed GRU backward never reads
+    them, model.py:18).  Filled with NaN instead, every parameter gradient must come out the same."""
+    from umpr_b200 import functional as F
+    from umpr_b200 import synthetic as syn
+    table = syn.make_table(3000, seed=2)
+    batch = syn.make_batch("music_full", 24, vocab=3000, seed=11)          # 480 sentences per side: tensor-core path with plans
+    res = []
+    for poison in (False, True):
+        model = syn.build_model("music_full", table, seed=1, device=DEV)
+        with torch.no_grad():
+            model.review_net.r_net.M.mul_(0.05)
+        F.POISON_UNWRITTEN = poison
+        try:
+            pred, loss = model(*batch)
+            loss.backward()
+        finally:
+            F.POISON_UNWRITTEN = False
+        res.append({k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad and p.grad is not None})
+    for k in res[0]:
+        assert torch.isfinite(res[1][k]).all(), k
+        if float(res[0][k].abs().max()) > 1e-7:
+            assert_close(res[1][k], res[0][k], 2e-6, "poisoned " + k)       # float atomics: last-bit differences only
+
+
+def test_snet_with_a_foreign_word_soft_keeps_its_input_gradient():
+    """functional.GradSink hands S-Net's input gradient to the co-attention backward ONLY when word_soft is that node's soft-max.
+    With any other word_soft (here: a fresh tensor) S-Net must return its dx itself - the GRU output's gradient is then the sum of
+    both consumers' contributions, exactly what plain autograd gives."""
+    import umpr_b200
+    torch.manual_seed(3)
+    B, S, L = 40, 8, 9                                                   # 320 sentences: tensor-core kernels with plans
+    emb_u, emb_i = torch.randn(B, S, L, 50) * 0.5, torch.randn(B, S, L, 50) * 0.5
+    lu, li = torch.randint(1, L + 1, (B, S)), torch.randint(1, L + 1, (B, S))
+    rnet = umpr_b200.RNet(50, 64).to(DEV)
+    snet = umpr_b200.SNet(64, 128).to(DEV)
+    with torch.no_grad():
+        rnet.M.mul_(0.05)
+    grads = []
+    for foreign in (False, True):
+        rnet.zero_grad(); snet.zero_grad()
+        out = rnet(emb_u.to(DEV), emb_i.to(DEV), lu, li)
+        ws = torch.softmax(torch.randn(B, S * L, device=DEV, generator=torch.Generator(DEV).manual_seed(1)), -1).requires_grad_(True) if foreign else out[2]
+        sa, se = snet(out[0], ws, L)
+        ((se ** 2).sum() + out[4].sum()).backward()
+        grads.append({k: p.grad.clone() for k, p in rnet.named_parameters()})
+    p = {"review_net.r_net." + k: v.detach().cpu() for k, v in rnet.state_dict().items()}
+    # oracle for the foreign case: the same graph in CPU autograd
+    pr = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ref = orc.r_net(emb_u, emb_i, lu, li, pr, impl="lib")
+    ws_c = torch.softmax(torch.randn(B, S * L, device=DEV, generator=torch.Generator(DEV).manual_seed(1)), -1).cpu()
+    _, se_ref = orc.s_net(ref[0], ws_c, L, snet.Ms.detach().cpu(), snet.Ws.detach().cpu())
+    ((se_ref ** 2).sum() + ref[4].sum()).backward()
+    for k, g in grads[1].items():
+        r = pr["review_net.r_net." + k].grad
+        if float(r.abs().max()) > 1e-7:
+            assert_close(g, r, TOL, "foreign word_soft: grad " + k)
+
+
+def test_model_on_a_non_current_device():
+    """The reference lets the model live on any ``config.device``; every forward makes that device current for its kernels."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from umpr_b200 import synthetic as syn
+    table = syn.make_table(3000, seed=2)
+    batch = syn.make_batch("music_full", 8, vocab=3000, seed=3)
+    torch.cuda.set_device(0)
+    out = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = syn.build_model("music_full", table, seed=1, device=dev)
+        pred, loss = m(*batch)
+        loss.backward()
+        out.append((pred.detach().cpu(), {k: p.grad.cpu() for k, p in m.named_parameters() if p.grad is not None}))
+    assert torch.cuda.current_device() == 0
+    assert_close(out[1][0], out[0][0], 1e-6, "prediction on cuda:1")
+    for k, g in out[0][1].items():
+        if float(g.abs().max()) > 1e-7:
+            assert_close(out[1][1][k], g, 1e-5, "grad on cuda:1 " + k)
