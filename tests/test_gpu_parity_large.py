@@ -177,7 +177,7 @@ def test_fused_gru_autograd_with_deep_tile_queues(ctas):
             assert_close(res[1][0][i][j], res[0][0][i][j], 2e-5, f"side {i} {nm} vs CUDA-core path")
     for k, (a, b, c) in enumerate(zip(res[1][1], res[0][1], wc)):
         assert_close(a, c.grad, TOL, f"weight gradient {k} vs oracle")
-        assert_close(a, b, 5e-5, f"weight gradient {k} vs CUDA-core path")
+        assert_close(a, b, 1e-4, f"weight gradient {k} vs CUDA-core path")      # two fp32-class implementations: each is within its own error of the oracle
 
 
 @pytest.mark.parametrize("workload,B,L", [("music_full", 24, 32), ("music_full", 16, 64), ("music_small_r", 12, 128), ("music_full", 8, 126)])
