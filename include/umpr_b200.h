@@ -95,8 +95,8 @@ typedef struct umpr_gru_seg {
   const int32_t* plan;    /* pack plan with R = 128 */
   float* out;             /* (N,L,128), fully written */
   float* hn;              /* (2,N,64) or NULL */
-  float* sv;              /* [n_slabs][2][256][128] saved gates (column-major inside a tile) or NULL (inference) */
-  void* hq;               /* [n_slabs][2][hi|lo][128][64 bf16] h_t operand images for the backward kernel, or NULL (inference) */
+  void* hq;               /* [n_slabs][2][hi|lo][128][64 bf16] h_t operand images: with xq ALL the backward kernel reads (it recomputes the
+                             gates); NULL = inference, nothing is kept */
   int32_t n_tiles, n_slabs, N, L;
 } umpr_gru_seg;
 /* xq[n_slabs][hi|lo][128][64 bf16]: gathered + packed tokens as SWIZZLE_128B bf16 hi/lo operand images (E values, 1.0, zeros) */
@@ -106,14 +106,14 @@ int umpr_gru_fwd_tc(const umpr_gru_seg* segs /*host array*/, int n_seg, const fl
                     int n_queues, void* stream);
 
 /* backward of umpr_gru_fwd_tc (same tiles, queues and segments, reverse time), recurrence AND weight gradients in one kernel:
- * the carry product [dr, dz, dn*r]·W_hh runs on tcgen05 with its A operand written into tensor memory, the weight-gradient
- * product [xq | hq]^T·[dr, dz, dn, dn*r] accumulates in tensor memory over each CTA's queue - the gate gradients never reach
- * HBM.  sv, xq, hq: what the forward launch read / wrote.  dw[8] (+=): gradients of the 8 GRU tensors (nn.GRU order).
+ * the gates are recomputed from xq[t] and hq[t-1] with the forward's own MMAs; the gate gradients go into a shared-memory tile
+ * that is the A operand of the carry product [dr, dz, dn*r]·W_hh and the B operand of the weight-gradient product
+ * [xq | hq]^T·[dr, dz, dn*r, dn], which accumulates in tensor memory over each CTA's queue - neither gates nor gate gradients
+ * ever reach HBM.  xq, hq: what the forward launch read / wrote.  dw[8] (+=): gradients of the 8 GRU tensors (nn.GRU order).
  * zero_img: 32 KB of zeros (h_{t-1} of a sequence's first step). */
 typedef struct umpr_gru_bwd_seg {
   const float* d_out;     /* (N,L,128) gradient of the ImprovedRnn result */
   const float* d_hn;      /* (2,N,64) or NULL */
-  const float* sv;        /* forward's saved gates */
   const void* xq;         /* packed token images (forward input) */
   const void* hq;         /* h_t operand images written by the forward */
   const int32_t* plan;

@@ -78,13 +78,13 @@ SIGNATURES = {
 
 class GruSeg(C.Structure):
     """``umpr_gru_seg`` of include/umpr_b200.h: one ImprovedRnn call inside a fused tensor-core GRU launch."""
-    _fields_ = [("xq", P), ("plan", P), ("out", P), ("hn", P), ("sv", P), ("hq", P), ("n_tiles", C.c_int32), ("n_slabs", C.c_int32),
+    _fields_ = [("xq", P), ("plan", P), ("out", P), ("hn", P), ("hq", P), ("n_tiles", C.c_int32), ("n_slabs", C.c_int32),
                 ("N", C.c_int32), ("L", C.c_int32)]
 
 
 class GruBwdSeg(C.Structure):
     """``umpr_gru_bwd_seg`` of include/umpr_b200.h."""
-    _fields_ = [("d_out", P), ("d_hn", P), ("sv", P), ("xq", P), ("hq", P), ("plan", P), ("n_tiles", C.c_int32),
+    _fields_ = [("d_out", P), ("d_hn", P), ("xq", P), ("hq", P), ("plan", P), ("n_tiles", C.c_int32),
                 ("n_slabs", C.c_int32), ("N", C.c_int32), ("L", C.c_int32)]
 
 

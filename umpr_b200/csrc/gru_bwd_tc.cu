@@ -1,21 +1,26 @@
 // ImprovedRnn backward on the tensor cores: reverse-time recurrence AND the GRU weight gradients in one persistent kernel
-// (backward of reference src/model.py:19-21; main.py:36).  The gate gradients never leave the SM.
+// (backward of reference src/model.py:19-21; main.py:36).  NOTHING but the operand images of the forward is read: the gates are
+// RECOMPUTED from x_t and h_{t-1} with the forward's own MMAs, and the gate gradients never leave the SM.
 //
 // Per CTA (one direction, one 128-sequence tile at a time, same tile queues as the forward), per time step in reverse order:
+//     [r, z, n_x, n_h] = [x_t | h_{t-1}] · [W_ih | W_hh]^T          (the forward's 36 MMAs, bit-identical accumulators)
 //     dh_t   = dy_t + dh_{t+1} (.) z_{t+1} + [dr, dz, dn*r]_{t+1} · W_hh                         (carry)
 //     dn_pre = dh (1-z)(1-n^2)   dz_pre = dh (h_{t-1} - n) z (1-z)   dr_pre = dn_pre (W_hn h + b_hn) r (1-r)
-//     dW^T[feature][gate] += [x_t | h_{t-1}]^T · [dr, dz, dn, dn*r]                                 (weight gradients)
-//   * carry product (K=192, N=64, 36 MMAs): A operand = the gate threads' own rows written into TENSOR MEMORY (tcgen05.st),
-//     B operand = the resident W_hh image read MN-major (the bytes the forward reads K-major);
-//   * weight-gradient product (M=128 features, N=256 gates in two passes of 128, K=128 sequences, 2 x 24 MMAs): A operand =
-//     the forward's token image xq and hidden image hq (bf16 hi|lo operand images, token-major = MN-major, loaded by ONE TMA
-//     bulk copy each), B operand = the gate gradients written by the gate threads as a token-major bf16 hi|lo tile;
-//     accumulated in TMEM over the CTA's whole queue and flushed once with atomics into the eight nn.GRU gradients;
-//   * TMEM (512 columns): [0,64) dh | [64,160) carry A hi | [160,256) carry A lo | [256,512) dW^T accumulator;
-//   * warps 0-7: gate threads (one sequence row x 32 hidden units each): saved gates, d_out and h_{t-1} (hq image, hi + lo) are
-//     read straight from global memory (prefetched into L2 one step ahead); warp 8: driver thread (TMA copies of the two
-//     operand images, MMAs);
-//   * `out` is not touched; saved gates svT are column-major inside a (slab, direction) tile (lanes = rows read 128 contiguous bytes).
+//     dW^T[feature][gate] += [x_t | h_{t-1}]^T · [dr, dz, dn*r, dn]                                 (weight gradients)
+//   * shared memory (225 KB): W_ih and W_hh images (bf16 hi|lo, pre-scaled by -log2e / 2 log2e exactly as in the forward), the
+//     step's token image xq[t] and hidden image hq[t-1] (ONE TMA bulk copy each - they serve K-major as the A operand of the
+//     recomputation and MN-major as the A operand of the weight-gradient product), and a 64 KB gate-gradient tile;
+//   * the gate-gradient tile (token-major bf16 hi|lo, two blocks of 64 gates, written by the gate threads in two passes:
+//     [dr | dz], then [dn*r | dn]) is BOTH the K-major A operand of the carry product (B = the resident W_hh image read MN-major)
+//     and the MN-major B operand of the weight-gradient product; its values carry the inverse of the weight pre-scaling, which the
+//     final flush undoes;
+//   * tensor memory (512 columns): [0,64) r | [64,128) z | [128,192) n_x | [192,256) n_h, re-used for dh (the carry product lands
+//     where the next step's W_hn h will: the gate threads fold dh into their registers first) | [256,512) dW^T accumulator, kept
+//     over the CTA's whole queue and flushed once with atomics into the eight nn.GRU gradients;
+//   * warps 0-15: gate threads (one sequence row x 16 hidden units each: 5 MUFU per unit for the recomputed cell, so 16 warps
+//     keep the XU pipe fed); warp 16: driver thread (TMA copies, L2 prefetch of the next step's images, all MMAs);
+//   * HBM traffic per token and direction: xq 256 B + hq 256 B + d_out 256 B (the saved-gate tensor of the first design, 1 KB
+//     written by the forward and read back here, is gone).
 #include "common.cuh"
 #include "tc.cuh"
 #include "gru_tc.cuh"
@@ -24,15 +29,20 @@
 namespace umpr {
 using namespace tc;
 
-constexpr int RB_GATE_WARPS = 8;
-constexpr int RB_THREADS = (RB_GATE_WARPS + 1) * 32;      // 288
-constexpr int RB_W_BYTES = 2 * G3 * 128;                  // W_hh hi | lo, [192][64 bf16]
+constexpr int RB_GATE_WARPS = 16;
+constexpr int RB_GATE_THREADS = RB_GATE_WARPS * 32;       // 512
+constexpr int RB_THREADS = (RB_GATE_WARPS + 1) * 32;      // 544
+constexpr int RB_W_BYTES = 2 * G3 * 128;                  // one weight image: hi | lo, [192][64 bf16] = 48 KB
 constexpr int RB_IMG = 2 * RT_R * 128;                    // one operand image: hi | lo, [128][64 bf16] = 32 KB
-constexpr int RB_GT = 4 * RT_R * 128;                     // gate-gradient tile: [hi|lo][2 blocks of 64 gates][128 sequences][128 B] = 64 KB
-constexpr int RB_SMEM = RB_W_BYTES + 2 * RB_IMG + RB_GT + 1024;
+constexpr int RB_BLK = RT_R * 128;                        // one block of the gate-gradient tile: [128 sequences][64 gates bf16] = 16 KB
+constexpr int RB_GT = 4 * RB_BLK;                         // gate-gradient tile: [hi|lo][2 blocks] = 64 KB
+constexpr int RB_SMEM = 2 * RB_W_BYTES + 2 * RB_IMG + RB_GT + 1024;
+
+constexpr float RB_K_RZ = -1.4426950408889634f;           // the forward's weight pre-scaling (gru_rec_tc.cu): r, z rows by -log2(e),
+constexpr float RB_K_N = 2.8853900817779268f;             // n rows and b_hn by 2 log2(e)
 
 struct BwdSeg {
-  const float* d_out; const float* d_hn; const float* sv; const unsigned char* xq; const unsigned char* hq; const int* plan;
+  const float* d_out; const float* d_hn; const unsigned char* xq; const unsigned char* hq; const int* plan;
   int n_tiles, n_slabs, N, L, tile_base;
 };
 struct BwdArgs {
@@ -42,16 +52,16 @@ struct BwdArgs {
   const float* w[8];
   float* dw[8];
   const unsigned char* zero_img;      // 32 KB of zeros: h_{t-1} of a sequence's first step
-  int E;
+  int E, kx;
 };
 
 struct BwdRow {
-  float part[32];      // dh_{t+1} (.) z_{t+1} (+ d_hn at the row's last step): the element-wise half of the carry
+  float part[16];      // dh_{t+1} (.) z_{t+1} + the carry product (+ d_hn at the row's last step): everything of dh_t but dy_t
   int len, rowo;
 };
 
 struct BwdBars {
-  uint64_t stage_full, stage_free, p1_ready, p2_ready, acc_full, w1_done, w2_done;
+  uint64_t img_full, p1_full, t1_ready, t1_done, t2_ready, dh_full, step_done, dh_read;
 };
 
 // bf16 hi + lo of 8 consecutive units (one 16-byte chunk of each image row) -> fp32
@@ -64,175 +74,200 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float* v
   }
 }
 
-// Everything a gate thread needs for 8 hidden units of its row that does NOT depend on the carry: saved gates (column-major
-// tile: lanes = rows are contiguous), d_out (the row's own 32 bytes) and h_{t-1} (one 16-byte chunk of the hq image, hi and lo).
-// Loaded straight from global memory (the driver pulls the step's tile into L2 one step ahead).
-struct ChunkIn {
-  float r[8], z[8], n[8], hh[8];
-  float4 y0, y1;
-  uint4 hhi, hlo;
-};
-__device__ __forceinline__ void load_chunk(ChunkIn& in, bool live, const float* svcol, const float* dyrow, const unsigned char* hrow, int cc,
-                                           uint32_t off) {
-  if (live) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
-      in.r[i] = s1[0]; in.z[i] = s1[(size_t)H * RT_R]; in.n[i] = s1[(size_t)2 * H * RT_R]; in.hh[i] = s1[(size_t)3 * H * RT_R];
-    }
-    in.y0 = *reinterpret_cast<const float4*>(dyrow + cc * 8);
-    in.y1 = *reinterpret_cast<const float4*>(dyrow + cc * 8 + 4);
-    in.hhi = make_uint4(0u, 0u, 0u, 0u); in.hlo = in.hhi;
-    if (hrow) {
-      in.hhi = *reinterpret_cast<const uint4*>(hrow + off);
-      in.hlo = *reinterpret_cast<const uint4*>(hrow + RT_R * 128 + off);
-    }
-  }
-}
-
-__device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, BwdRow& g, int n, int dir, int row, int hf,
-                                              unsigned char* base, BwdBars* bar, uint32_t tmem) {
+// One reverse time step of one tile for one gate thread (row = sequence of the tile, ug = which 16 of the 64 hidden units).
+__device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, BwdRow& g, int n, int dir, int row, int ug,
+                                              const unsigned char* himg, unsigned char* gt, const float* s_bhn, BwdBars* bar, uint32_t tmem) {
   const BwdSeg& sg = a.seg[c.si];
-  const int u0 = hf * 32;
+  const int u0 = ug * 16;
   const int Rp = sg.n_tiles * RT_R;
-  unsigned char* gt = base + RB_W_BYTES + 2 * RB_IMG;       // gate-gradient tile
   if (c.s == 0) {
     const int k = c.tile * RT_R + row;
     g.rowo = sg.plan[Rp + k];
     g.len = sg.plan[2 * Rp + k];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) g.part[i] = 0.f;
+    for (int i = 0; i < 16; ++i) g.part[i] = 0.f;
     if (sg.d_hn && g.rowo >= 0) {
       const float* hp = sg.d_hn + ((size_t)dir * sg.N + sg.plan[k]) * H + u0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(hp + i * 4);
         g.part[4 * i] = v.x; g.part[4 * i + 1] = v.y; g.part[4 * i + 2] = v.z; g.part[4 * i + 3] = v.w;
       }
     }
   }
   const int t = dir ? c.s : (c.Lj - 1 - c.s);          // reverse of the forward kernel's order
-  const int tp = dir ? t + 1 : t - 1;
   const bool live = t < g.len;
-  const size_t slab0 = (size_t)sg.plan[3 * Rp + c.tile];
-  const float* svcol = sg.sv + (((slab0 + t) * 2 + dir) * SV + u0) * RT_R + row;
-  const float* dyrow = sg.d_out + ((size_t)(g.rowo < 0 ? 0 : g.rowo) * sg.L + t) * D + dir * H + u0;
-  const unsigned char* hrow = (tp >= 0 && tp < c.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : nullptr;     // h_{t-1} image (zeros at the first step)
+  const bool any_live = __any_sync(0xffffffffu, live);
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16);
   const uint32_t off0 = (uint32_t)(row * 128);
 
-  ChunkIn ci;                                   // chunk 0 is requested before the barrier waits: its latency hides behind them
-  load_chunk(ci, live, svcol, dyrow, hrow, 0, off0 + (((hf * 4) ^ (row & 7)) << 4));
-  if (n > 0) {
-    mbar_wait(&bar->acc_full, (n - 1) & 1);     // previous carry product retired: dh readable, its TMEM A operand reusable
-    mbar_wait(&bar->w2_done, (n - 1) & 1);      // previous weight-gradient MMAs retired: the gate-gradient tile is reusable
-    tc_fence_after();
+  // d_out row of this step: requested before the barrier waits, so that its latency hides behind them
+  float4 dy4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dy4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const float* dyrow = sg.d_out + ((size_t)g.rowo * sg.L + t) * D + dir * H + u0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dy4[i] = *reinterpret_cast<const float4*>(dyrow + 4 * i);
   }
-  uint32_t dn_hi[16], dn_lo[16], dnr_hi[16], dnr_lo[16];          // pass-2 gate gradients, kept packed until pass 1 retires
+  if (n > 0) {
+    // the previous step's carry product [dr, dz, dn*r] · W_hh: fold it into the running part, then release its columns
+    mbar_wait(&bar->dh_full, (n - 1) & 1);
+    tc_fence_after();
+    if (c.s > 0) {                                      // (a tile's first step: what is there belongs to the previous tile)
+      uint32_t acc[16];
+      tmem_ld8_issue(trow + 192 + u0, acc);
+      tmem_ld8_issue(trow + 192 + u0 + 8, acc + 8);
+      tmem_ld_wait();
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int chunk = hf * 4 + cc;
-    const uint32_t off = off0 + ((chunk ^ (row & 7)) << 4);
-    if (cc > 0) load_chunk(ci, live, svcol, dyrow, hrow, cc, off);
-    uint32_t acc[8];
+      for (int i = 0; i < 16; ++i) g.part[i] += __uint_as_float(acc[i]);
+    }
+    tc_fence_before();
+    mbar_arrive(&bar->dh_read);
+  }
+  mbar_wait(&bar->img_full, n & 1);                     // h_{t-1} image readable (TMA write)
+  mbar_wait(&bar->p1_full, n & 1);                      // recomputed accumulators complete
+  tc_fence_after();
+
+  // pass-2 blocks (dn*r, dn) wait, packed, in TENSOR MEMORY until the pass-1 MMAs have read the tile: each thread parks them in
+  // the r / z accumulator columns IT has just read (nobody else reads those; the next recomputation overwrites them later)
+  const uint32_t park = trow + u0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0u;
-    if (c.s > 0) { tmem_ld8_issue(trow + u0 + cc * 8, acc); tmem_ld_wait(); }     // warp-uniform: outside the per-row branch
+  for (int cc = 0; cc < 2; ++cc) {
+    const int chunk = ug * 2 + cc;
+    const uint32_t off = off0 + ((uint32_t)(chunk ^ (row & 7)) << 4);
     float dr[8], dz[8], dn8[8], dnr[8];
-    if (live) {
-      const float dy[8] = {ci.y0.x, ci.y0.y, ci.y0.z, ci.y0.w, ci.y1.x, ci.y1.y, ci.y1.z, ci.y1.w};
+    if (any_live) {
+      const int ub = u0 + cc * 8;
+      uint32_t v[32];
+      tmem_ld8_issue(trow + ub, v);
+      tmem_ld8_issue(trow + 64 + ub, v + 8);
+      tmem_ld8_issue(trow + 128 + ub, v + 16);
+      tmem_ld8_issue(trow + 192 + ub, v + 24);
+      const uint4 hhi = *reinterpret_cast<const uint4*>(himg + off);
+      const uint4 hlo = *reinterpret_cast<const uint4*>(himg + RT_R * 128 + off);
+      const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + ub), b1 = *reinterpret_cast<const float4*>(s_bhn + ub + 4);
+      const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float dy[8] = {dy4[2 * cc].x, dy4[2 * cc].y, dy4[2 * cc].z, dy4[2 * cc].w, dy4[2 * cc + 1].x, dy4[2 * cc + 1].y, dy4[2 * cc + 1].z, dy4[2 * cc + 1].w};
       float hp[8];
-      unpack8(ci.hhi, ci.hlo, hp);
+      unpack8(hhi, hlo, hp);
+      tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float dh = g.part[cc * 8 + i] + __uint_as_float(acc[i]) + dy[i];
-        const float dnv = dh * (1.f - ci.z[i]);
-        const float dn_pre = dnv * (1.f - ci.n[i] * ci.n[i]);
-        dz[i] = dh * (hp[i] - ci.n[i]) * ci.z[i] * (1.f - ci.z[i]);
-        dr[i] = dn_pre * ci.hh[i] * ci.r[i] * (1.f - ci.r[i]);
-        dnr[i] = dn_pre * ci.r[i];
-        dn8[i] = dn_pre;
-        g.part[cc * 8 + i] = dh * ci.z[i];
+        // the forward's cell, same operations in the same order (gru_rec_tc.cu gate_step)
+        const float er = ex2f(__uint_as_float(v[i]));
+        const float r = rcpf(1.f + er);
+        const float hcand = __uint_as_float(v[24 + i]) + bh[i];           // 2 log2e (W_hn h + b_hn)
+        const float xn = fmaf(r, hcand, __uint_as_float(v[16 + i]));
+        const float ez = ex2f(fminf(__uint_as_float(v[8 + i]), 60.f));
+        const float en = ex2f(fminf(xn, 60.f));
+        const float dzd = 1.f + ez, dnd = 1.f + en;
+        const float inv = rcpf(dzd * dnd);
+        const float z = dnd * inv;
+        const float nv = fmaf(-2.f * dzd, inv, 1.f);
+        // backward of the cell
+        const float dh = g.part[cc * 8 + i] + dy[i];
+        const float dn_pre = dh * (1.f - z) * (1.f - nv * nv);
+        const float dz_pre = dh * (hp[i] - nv) * z * (1.f - z);
+        const float dr_pre = dn_pre * (hcand * (1.f / RB_K_N)) * r * (1.f - r);
+        // stored with the inverse of the resident weights' pre-scaling (the carry product then needs no rescaling; the flush
+        // of the weight gradients multiplies it back)
+        dr[i] = live ? dr_pre * (1.f / RB_K_RZ) : 0.f;
+        dz[i] = live ? dz_pre * (1.f / RB_K_RZ) : 0.f;
+        dnr[i] = live ? dn_pre * r * (1.f / RB_K_N) : 0.f;
+        dn8[i] = live ? dn_pre * (1.f / RB_K_N) : 0.f;
+        if (live) g.part[cc * 8 + i] = dh * z;          // beyond this row's length the carry just passes through
       }
     } else {
-      // beyond this row's length: no gradient (zero rows in both products), the carry just passes through
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        g.part[cc * 8 + i] += __uint_as_float(acc[i]);
-        dr[i] = 0.f; dz[i] = 0.f; dn8[i] = 0.f; dnr[i] = 0.f;
-      }
+      for (int i = 0; i < 8; ++i) { dr[i] = 0.f; dz[i] = 0.f; dnr[i] = 0.f; dn8[i] = 0.f; }
     }
-    // carry A operand in tensor memory: k = gate block * 64 + unit, two bf16 per 32-bit column, hi at +64, lo at +160;
-    // weight-gradient B operand in shared memory: token-major tile, block 0 = dr (pass 2: dn), block 1 = dz (pass 2: dn*r)
-    const uint32_t acol = trow + 64 + (u0 + cc * 8) / 2;
-    const uint32_t goff = off;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(dr[2 * i], dr[2 * i + 1], hi[i], lo[i]);
-    tmem_st4(acol, hi[0], hi[1], hi[2], hi[3]);
-    tmem_st4(acol + 96, lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(gt + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 2 * RT_R * 128 + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(gt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) split2(dz[2 * i], dz[2 * i + 1], hi[i], lo[i]);
-    tmem_st4(acol + 32, hi[0], hi[1], hi[2], hi[3]);
-    tmem_st4(acol + 96 + 32, lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4*>(gt + RT_R * 128 + goff) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 3 * RT_R * 128 + goff) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], dnr_hi[cc * 4 + i], dnr_lo[cc * 4 + i]);
-    tmem_st4(acol + 64, dnr_hi[cc * 4], dnr_hi[cc * 4 + 1], dnr_hi[cc * 4 + 2], dnr_hi[cc * 4 + 3]);
-    tmem_st4(acol + 96 + 64, dnr_lo[cc * 4], dnr_lo[cc * 4 + 1], dnr_lo[cc * 4 + 2], dnr_lo[cc * 4 + 3]);
+    for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], hi[i], lo[i]);
+    tmem_st4(park + cc * 8, hi[0], hi[1], hi[2], hi[3]);
+    tmem_st4(park + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dn8[2 * i], dn8[2 * i + 1], dn_hi[cc * 4 + i], dn_lo[cc * 4 + i]);
+    for (int i = 0; i < 4; ++i) split2(dn8[2 * i], dn8[2 * i + 1], hi[i], lo[i]);
+    tmem_st4(park + 64 + cc * 8, hi[0], hi[1], hi[2], hi[3]);
+    tmem_st4(park + 64 + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
   }
   tmem_st_wait();
   fence_async_smem();
   tc_fence_before();
-  mbar_arrive(&bar->p1_ready);         // carry A operand + pass-1 tile (dr | dz) complete
+  mbar_arrive(&bar->t1_ready);         // pass-1 tile (dr | dz) complete, accumulator columns drained
   // pass 2: the same tile buffer, once the pass-1 MMAs have read it
-  mbar_wait(&bar->w1_done, n & 1);
+  mbar_wait(&bar->t1_done, n & 1);
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int chunk = hf * 4 + cc;
-    const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-    *reinterpret_cast<uint4*>(gt + off) = make_uint4(dn_hi[cc * 4], dn_hi[cc * 4 + 1], dn_hi[cc * 4 + 2], dn_hi[cc * 4 + 3]);
-    *reinterpret_cast<uint4*>(gt + 2 * RT_R * 128 + off) = make_uint4(dn_lo[cc * 4], dn_lo[cc * 4 + 1], dn_lo[cc * 4 + 2], dn_lo[cc * 4 + 3]);
-    *reinterpret_cast<uint4*>(gt + RT_R * 128 + off) = make_uint4(dnr_hi[cc * 4], dnr_hi[cc * 4 + 1], dnr_hi[cc * 4 + 2], dnr_hi[cc * 4 + 3]);
-    *reinterpret_cast<uint4*>(gt + 3 * RT_R * 128 + off) = make_uint4(dnr_lo[cc * 4], dnr_lo[cc * 4 + 1], dnr_lo[cc * 4 + 2], dnr_lo[cc * 4 + 3]);
+  for (int cc = 0; cc < 2; ++cc) {
+    const int chunk = ug * 2 + cc;
+    const uint32_t off = off0 + ((uint32_t)(chunk ^ (row & 7)) << 4);
+    uint32_t q[16];                                     // [dn*r hi 4 | lo 4 | dn hi 4 | lo 4]
+    tmem_ld8_issue(park + cc * 8, q);
+    tmem_ld8_issue(park + 64 + cc * 8, q + 8);
+    tmem_ld_wait();
+    *reinterpret_cast<uint4*>(gt + off) = make_uint4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(q[4], q[5], q[6], q[7]);
+    *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(q[8], q[9], q[10], q[11]);
+    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(q[12], q[13], q[14], q[15]);
   }
   fence_async_smem();
-  mbar_arrive(&bar->p2_ready);
+  tc_fence_before();                   // the parked words have been read: the next step's recomputation may overwrite the columns
+  mbar_arrive(&bar->t2_ready);
 }
 
 __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_constant__ BwdArgs a) {
   extern __shared__ unsigned char raw[];
   __shared__ BwdBars bars;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bhn[H];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* whh = base;                                  // [hi|lo][192][128 B]
-  unsigned char* ximg = base + RB_W_BYTES;                    // xq image (hi|lo), then hq image (hi|lo): operands of the weight-gradient MMAs
+  unsigned char* wih = base;                                  // [hi|lo][192][128 B]
+  unsigned char* whh = base + RB_W_BYTES;
+  unsigned char* ximg = base + 2 * RB_W_BYTES;                // xq image (hi|lo), then hq image (hi|lo)
+  unsigned char* himg = ximg + RB_IMG;
   unsigned char* gt = ximg + 2 * RB_IMG;                      // gate-gradient tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
 
   if (tid == 0) {
-    mbar_init(&bars.stage_full, 1);
-    mbar_init(&bars.stage_free, 1);
-    mbar_init(&bars.p1_ready, RB_GATE_WARPS * 32);
-    mbar_init(&bars.p2_ready, RB_GATE_WARPS * 32);
-    mbar_init(&bars.acc_full, 1);
-    mbar_init(&bars.w1_done, 1);
-    mbar_init(&bars.w2_done, 1);
+    mbar_init(&bars.img_full, 1);
+    mbar_init(&bars.p1_full, 1);
+    mbar_init(&bars.t1_ready, RB_GATE_THREADS);
+    mbar_init(&bars.t1_done, 1);
+    mbar_init(&bars.t2_ready, RB_GATE_THREADS);
+    mbar_init(&bars.dh_full, 1);
+    mbar_init(&bars.step_done, 1);
+    mbar_init(&bars.dh_read, RB_GATE_THREADS);
     mbar_fence_init();
   }
   if (warp == RB_GATE_WARPS) tmem_alloc(&tmem_slot, 512);
   {
-    const float* w_hh = a.w[dir * 4 + 1];
+    // resident weights of this direction, scaled exactly as in the forward kernel (the recomputed accumulators are then
+    // bit-identical to the forward's): W_ih with column E = b_ih (+ b_hh for r, z), W_hh, b_hn
+    const float* w_ih = a.w[dir * 4 + 0], *w_hh = a.w[dir * 4 + 1], *b_ih = a.w[dir * 4 + 2], *b_hh = a.w[dir * 4 + 3];
     for (int idx = tid; idx < G3 * 16; idx += RB_THREADS) {
       const int n = idx >> 4, k = (idx & 15) * 4;
-      store_split4(whh, whh + G3 * 128, n, k, *reinterpret_cast<const float4*>(w_hh + n * H + k));
+      const float sc = n < 2 * H ? RB_K_RZ : RB_K_N;
+      float t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kk = k + q;
+        t[q] = sc * (kk < a.E ? w_ih[(size_t)n * a.E + kk] : (kk == a.E ? b_ih[n] + (n < 2 * H ? b_hh[n] : 0.f) : 0.f));
+      }
+      store_split4(wih, wih + G3 * 128, n, k, make_float4(t[0], t[1], t[2], t[3]));
+      const float4 wh = *reinterpret_cast<const float4*>(w_hh + n * H + k);
+      store_split4(whh, whh + G3 * 128, n, k, make_float4(sc * wh.x, sc * wh.y, sc * wh.z, sc * wh.w));
     }
+    if (tid < H) s_bhn[tid] = RB_K_N * b_hh[2 * H + tid];
   }
   fence_async_smem();
   tc_fence_before();
@@ -240,103 +275,141 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  // this CTA walks slot queue 2c, then 2c+1 (one tile at a time: the kernel is bound by the saved-gate traffic, not by overlap)
-  int n_total = 0;
+  // this CTA walks slot queue 2c, then 2c+1, one tile at a time
   if (warp < RB_GATE_WARPS) {
-    const int row = (warp & 3) * 32 + lane, hf = warp >> 2;
+    const int row = (warp & 3) * 32 + lane, ug = warp >> 2;
     BwdRow g;
     g.len = 0; g.rowo = -1;
+    int n_total = 0;
     for (int qi = 0; qi < 2; ++qi) {
       Cur c;
       cur_init(a, c, 2 * blockIdx.x + qi);
       for (; c.active; ++n_total) {
-        bwd_gate_step(a, c, g, n_total, dir, row, hf, base, &bars, tmem);
+        bwd_gate_step(a, c, g, n_total, dir, row, ug, himg, gt, s_bhn, &bars, tmem);
         cur_next(a, c);
       }
     }
-    if (n_total > 0) {
-      mbar_wait(&bars.acc_full, (n_total - 1) & 1);
-      mbar_wait(&bars.w2_done, (n_total - 1) & 1);
-      tc_fence_after();
-    }
-  } else {
-    // ------------------------------------------------------------------ driver warp
-    constexpr uint32_t id_carry = idesc_bf16(128, 64) | (1u << 16);                  // A in TMEM (K-major), B = W_hh image MN-major
-    constexpr uint32_t id_wg = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);       // A = [xq | hq] images, B = gate-gradient tile: both token-major
+  } else if (lane == 0) {
+    // ------------------------------------------------------------------ driver thread
+    constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
+    constexpr uint32_t id_carry = idesc_bf16(128, 64) | (1u << 16);                  // A = gate tile (K-major), B = W_hh image MN-major
+    constexpr uint32_t id_wg = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);       // A = [xq | hq] images, B = gate tile: both token-major
+    const uint64_t wih_h = smem_desc_sw128(smem_u32(wih)), wih_l = smem_desc_sw128(smem_u32(wih + G3 * 128));
+    const uint64_t whh_h = smem_desc_sw128(smem_u32(whh)), whh_l = smem_desc_sw128(smem_u32(whh + G3 * 128));
+    const uint64_t whn_h = smem_desc_sw128(smem_u32(whh + 128 * 128)), whn_l = smem_desc_sw128(smem_u32(whh + G3 * 128 + 128 * 128));
+    const uint64_t x_h = smem_desc_sw128(smem_u32(ximg)), x_l = smem_desc_sw128(smem_u32(ximg + RT_R * 128));
+    const uint64_t h_h = smem_desc_sw128(smem_u32(himg)), h_l = smem_desc_sw128(smem_u32(himg + RT_R * 128));
     const uint32_t b_hi = smem_u32(whh), b_lo = smem_u32(whh + G3 * 128);
-    const uint32_t d_dh = tmem, a_hi = tmem + 64, a_lo = tmem + 160, d_w = tmem + 256;
+    const uint32_t d_gates = tmem, d_dh = tmem + 192, d_w = tmem + 256;
     // weight-gradient A operand: M = 128 features = [64 of xq | 64 of hq]: the second 64-feature block lies one image (32 KB) further
     const uint32_t xa_hi = smem_u32(ximg), xa_lo = smem_u32(ximg + RT_R * 128);
-    const uint32_t g_hi = smem_u32(gt), g_lo = smem_u32(gt + 2 * RT_R * 128);
-    auto produce = [&](const Cur& cc) {      // the step's two operand images, one TMA bulk copy each (lane 0)
-      if (lane != 0) return;
+    const uint32_t g_hi = smem_u32(gt), g_lo = smem_u32(gt + 2 * RB_BLK);
+    auto slab_of = [&](const Cur& cc, int& t, int& tp) -> size_t {
       const BwdSeg& sg = a.seg[cc.si];
-      const int t = dir ? cc.s : (cc.Lj - 1 - cc.s);
-      const int tp = dir ? t + 1 : t - 1;
-      const size_t slab0 = (size_t)sg.plan[3 * sg.n_tiles * RT_R + cc.tile];
-      mbar_arrive_expect_tx(&bars.stage_full, 2 * RB_IMG);
-      bulk_copy_g2s(ximg, sg.xq + (slab0 + t) * RB_IMG, RB_IMG, &bars.stage_full);
+      t = dir ? cc.s : (cc.Lj - 1 - cc.s);
+      tp = dir ? t + 1 : t - 1;
+      return (size_t)sg.plan[3 * sg.n_tiles * RT_R + cc.tile];
+    };
+    auto produce = [&](const Cur& cc) {      // the step's two operand images, one TMA bulk copy each
+      const BwdSeg& sg = a.seg[cc.si];
+      int t, tp;
+      const size_t slab0 = slab_of(cc, t, tp);
+      mbar_arrive_expect_tx(&bars.img_full, 2 * RB_IMG);
+      bulk_copy_g2s(ximg, sg.xq + (slab0 + t) * RB_IMG, RB_IMG, &bars.img_full);
       const unsigned char* hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
-      bulk_copy_g2s(ximg + RB_IMG, hsrc, RB_IMG, &bars.stage_full);
+      bulk_copy_g2s(himg, hsrc, RB_IMG, &bars.img_full);
     };
     Cur c;
     int qi = 0;
     cur_init(a, c, 2 * blockIdx.x);
     if (!c.active) { qi = 1; cur_init(a, c, 2 * blockIdx.x + 1); }
     if (c.active) produce(c);
-    for (int n = 0; c.active; ++n) {
+    int n = 0;
+    for (; c.active; ++n) {
       Cur nx = c;
       cur_next(a, nx);
       if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
-      if (nx.active && lane == 0) {
-        // the next step's saved gates (128 KB) and operand images are pulled into L2 while this step computes
+      if (nx.active) {
+        // the next step's operand images are pulled into L2 while this step computes
         const BwdSeg& sg = a.seg[nx.si];
-        const int t = dir ? nx.s : (nx.Lj - 1 - nx.s);
-        const int tp = dir ? t + 1 : t - 1;
-        const size_t slab0 = (size_t)sg.plan[3 * sg.n_tiles * RT_R + nx.tile];
-        bulk_prefetch_l2(sg.sv + ((slab0 + t) * 2 + dir) * SV * RT_R, SV * RT_R * 4);
+        int t, tp;
+        const size_t slab0 = slab_of(nx, t, tp);
         bulk_prefetch_l2(sg.xq + (slab0 + t) * RB_IMG, RB_IMG);
         if (tp >= 0 && tp < nx.Lj) bulk_prefetch_l2(sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG, RB_IMG);
       }
-      if (lane == 0) {
-        mbar_wait(&bars.p1_ready, n & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 12; ++ks) {       // carry: dh[128 x 64] = A[128 x 192] (TMEM) · W_hh[192 x 64]
-          const uint64_t bh = smem_desc_mn_sw128(b_hi + ks * 2048), bl = smem_desc_mn_sw128(b_lo + ks * 2048);
-          umma_bf16_ts(d_dh, a_hi + ks * 8, bh, id_carry, ks != 0);
-          umma_bf16_ts(d_dh, a_hi + ks * 8, bl, id_carry, 1);
-          umma_bf16_ts(d_dh, a_lo + ks * 8, bh, id_carry, 1);
-        }
-        umma_commit(&bars.acc_full);
-        mbar_wait(&bars.stage_full, n & 1);      // the step's operand images have landed
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {  // dW^T[128 features][pass*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
-          if (pass == 1) { mbar_wait(&bars.p2_ready, n & 1); tc_fence_after(); }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t ah = desc_mn(xa_hi + ks * 2048, RB_IMG), al = desc_mn(xa_lo + ks * 2048, RB_IMG);
-            const uint64_t gh = desc_mn(g_hi + ks * 2048, RT_R * 128), gl = desc_mn(g_lo + ks * 2048, RT_R * 128);
-            const uint32_t accf = (n | ks) != 0;
-            umma_bf16(d_w + pass * 128, ah, gh, id_wg, accf);
-            umma_bf16(d_w + pass * 128, ah, gl, id_wg, 1);
-            umma_bf16(d_w + pass * 128, al, gh, id_wg, 1);
-          }
-          umma_commit(pass == 0 ? &bars.w1_done : &bars.w2_done);
-        }
-        umma_commit(&bars.stage_free);           // (same completion as w2_done: operand images and staging are free again)
+      mbar_wait(&bars.img_full, n & 1);         // the step's operand images have landed
+      if (n > 0) mbar_wait(&bars.dh_read, (n - 1) & 1);      // the previous carry product has been folded in: its columns are free
+      tc_fence_after();
+      // ---- recomputation: the forward's MMAs (gru_rec_tc.cu), same operands, same order
+      for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16(d_gates, x_h + o, wih_h + o, id192, kk != 0);
+        umma_bf16(d_gates, x_h + o, wih_l + o, id192, 1);
+        umma_bf16(d_gates, x_l + o, wih_h + o, id192, 1);
       }
-      __syncwarp();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {          // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16(d_gates, h_h + o, whh_h + o, id128, 1);
+        umma_bf16(d_gates, h_h + o, whh_l + o, id128, 1);
+        umma_bf16(d_gates, h_l + o, whh_h + o, id128, 1);
+        umma_bf16(d_gates + 192, h_h + o, whn_h + o, id64, kk != 0);
+        umma_bf16(d_gates + 192, h_h + o, whn_l + o, id64, 1);
+        umma_bf16(d_gates + 192, h_l + o, whn_h + o, id64, 1);
+      }
+      umma_commit(&bars.p1_full);
+      // ---- pass 1: tile = [dr | dz]
+      mbar_wait(&bars.t1_ready, n & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {          // carry, first 128 of K = 192: dh[128 x 64] = tile[128 x 128] · W_hh[r,z rows][128 x 64]
+        const uint32_t blk = (uint32_t)(ks >> 2) * RB_BLK, ko = (uint32_t)(ks & 3) * 32;
+        const uint64_t ah = smem_desc_sw128(g_hi + blk + ko), al = smem_desc_sw128(g_lo + blk + ko);
+        const uint64_t bh = smem_desc_mn_sw128(b_hi + ks * 2048), bl = smem_desc_mn_sw128(b_lo + ks * 2048);
+        umma_bf16(d_dh, ah, bh, id_carry, ks != 0);
+        umma_bf16(d_dh, ah, bl, id_carry, 1);
+        umma_bf16(d_dh, al, bh, id_carry, 1);
+      }
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+          // ---- pass 2: tile = [dn*r | dn]
+          mbar_wait(&bars.t2_ready, n & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 8; ks < 12; ++ks) {     // carry, last 64 of K: += tile block 0 (dn*r) · W_hh[n rows]
+            const uint32_t ko = (uint32_t)(ks & 3) * 32;
+            const uint64_t ah = smem_desc_sw128(g_hi + ko), al = smem_desc_sw128(g_lo + ko);
+            const uint64_t bh = smem_desc_mn_sw128(b_hi + ks * 2048), bl = smem_desc_mn_sw128(b_lo + ks * 2048);
+            umma_bf16(d_dh, ah, bh, id_carry, 1);
+            umma_bf16(d_dh, ah, bl, id_carry, 1);
+            umma_bf16(d_dh, al, bh, id_carry, 1);
+          }
+          umma_commit(&bars.dh_full);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {        // dW^T[128 features][pass*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
+          const uint64_t ah = desc_mn(xa_hi + ks * 2048, RB_IMG), al = desc_mn(xa_lo + ks * 2048, RB_IMG);
+          const uint64_t gh = desc_mn(g_hi + ks * 2048, RB_BLK), gl = desc_mn(g_lo + ks * 2048, RB_BLK);
+          const uint32_t accf = (n | ks) != 0;
+          umma_bf16(d_w + pass * 128, ah, gh, id_wg, accf);
+          umma_bf16(d_w + pass * 128, ah, gl, id_wg, 1);
+          umma_bf16(d_w + pass * 128, al, gh, id_wg, 1);
+        }
+        umma_commit(pass == 0 ? &bars.t1_done : &bars.step_done);
+      }
       if (nx.active) {
-        mbar_wait(&bars.stage_free, n & 1);     // all MMAs that read this step's images have retired (the gate threads read theirs before p1_ready)
+        mbar_wait(&bars.step_done, n & 1);      // every MMA that reads this step's images and tile has retired
         produce(nx);
       }
       c = nx;
     }
+    if (n > 0) mbar_wait(&bars.step_done, (n - 1) & 1);      // the accumulator is complete before the flush below
   }
   __syncthreads();
   tc_fence_after();
-  // ---- flush dW^T: TMEM lane = feature (x features 0..63, hidden features 64..127), column = gate (dr, dz, dn, dn*r blocks of 64)
+  // ---- flush dW^T: TMEM lane = feature (x features 0..63, hidden features 64..127), column = gate gradient
+  //      [0,64) dr | [64,128) dz | [128,192) dn*r | [192,256) dn, each scaled by 1 / (the resident weights' pre-scaling)
   const bool has_work = a.q_off[2 * blockIdx.x + 2] > a.q_off[2 * blockIdx.x];       // otherwise the accumulator was never written
   if (warp < 4 && has_work) {
     const int f = warp * 32 + lane;
@@ -349,20 +422,23 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     for (int c0 = 0; c0 < 256; c0 += 32) {
       float v[32];
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+      const float sc = c0 < 2 * H ? RB_K_RZ : RB_K_N;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int gc = c0 + i;                 // 0..255: dr, dz, dn, dn*r
+        const int gc = c0 + i;                 // 0..255: dr, dz, dn*r, dn
+        const float val = v[i] * sc;
         if (f < KP) {
-          if (gc < G3) {
-            if (f < E) atomicAdd(&dw_ih[gc * E + f], v[i]);
-            else if (f == E) { atomicAdd(&db_ih[gc], v[i]); if (gc < 2 * H) atomicAdd(&db_hh[gc], v[i]); }
+          // token features: W_ih columns, the 1.0 column feeds the biases
+          const int grow = gc < 2 * H ? gc : gc - H;                   // dr -> u, dz -> 64+u, dn -> 128+u
+          if (gc < 2 * H || gc >= G3) {
+            if (f < E) atomicAdd(&dw_ih[grow * E + f], val);
+            else if (f == E) { atomicAdd(&db_ih[grow], val); if (gc < 2 * H) atomicAdd(&db_hh[grow], val); }
           } else if (f == E) {
-            atomicAdd(&db_hh[gc - H], v[i]);   // dn*r column u -> b_hn at index 128 + u
+            atomicAdd(&db_hh[gc], val);        // dn*r column 128+u -> b_hn at index 128 + u
           }
         } else {
-          const int j = f - KP;
-          if (gc < 2 * H) atomicAdd(&dw_hh[gc * H + j], v[i]);
-          else if (gc >= G3) atomicAdd(&dw_hh[(gc - H) * H + j], v[i]);
+          const int j = f - KP;                // hidden features: W_hh columns
+          if (gc < G3) atomicAdd(&dw_hh[gc * H + j], val);             // dr, dz, dn*r -> rows u, 64+u, 128+u
         }
       }
     }
@@ -386,9 +462,9 @@ extern "C" int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs, int n_seg, const fl
   int base = 0;
   for (int i = 0; i < n_seg; ++i) {
     const umpr_gru_bwd_seg& s = segs[i];
-    if (s.n_tiles < 1 || s.L < 1 || !s.d_out || !s.sv || !s.xq || !s.hq || !s.plan) return fail_arg("gru_bwd_tc: segment %d is incomplete", i);
+    if (s.n_tiles < 1 || s.L < 1 || !s.d_out || !s.xq || !s.hq || !s.plan) return fail_arg("gru_bwd_tc: segment %d is incomplete", i);
     if (reinterpret_cast<uintptr_t>(s.d_out) & 15) return fail_arg("gru_bwd_tc: d_out must be 16-byte aligned");
-    a.seg[i] = BwdSeg{s.d_out, s.d_hn, s.sv, reinterpret_cast<const unsigned char*>(s.xq), reinterpret_cast<const unsigned char*>(s.hq), s.plan,
+    a.seg[i] = BwdSeg{s.d_out, s.d_hn, reinterpret_cast<const unsigned char*>(s.xq), reinterpret_cast<const unsigned char*>(s.hq), s.plan,
                       s.n_tiles, s.n_slabs, s.N, s.L, base};
     base += s.n_tiles;
   }
@@ -398,6 +474,7 @@ extern "C" int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs, int n_seg, const fl
   for (int i = 0; i < 8; ++i) { a.w[i] = w[i]; a.dw[i] = dw[i]; }
   a.zero_img = reinterpret_cast<const unsigned char*>(zero_img);
   a.E = E;
+  a.kx = (E + 1 + 15) / 16;
   cudaError_t e = cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM);
   if (e != cudaSuccess) { set_error("gru_bwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   gru_bwd_tc_kernel<<<dim3(n_queues / 2, 2), RB_THREADS, RB_SMEM, (cudaStream_t)stream>>>(a);

@@ -9,8 +9,9 @@
 //   * per time step and slot:  D  = x_t · W_ih^T          (N=192, K=64: 12 MMAs, independent of h)
 //                              D += h_{t-1} · W_hh^T      (N=128 into r,z and N=64 into its own n columns: 24 MMAs)
 //     then 8 gate warps read their TMEM lanes, apply the ATen GRU cell, mask each row by its own length, write the
-//     ImprovedRnn output row in the reference's doubly-permuted order (zeros beyond the length), the saved gates for
-//     backward, and h_t as the next step's bf16 hi/lo A-operand;
+//     ImprovedRnn output row in the reference's doubly-permuted order (zeros beyond the length) and h_t as the next step's bf16
+//     hi/lo A-operand; in training the driver also streams every h image out (hq, one TMA bulk store per step): together with
+//     the token images it is ALL the backward kernel needs - the gates are recomputed there, nothing else is saved;
 //   * warp roles: 0-7 gates of slot 0, 8-15 gates of slot 1 (TMEM lane quarter = warp%4, hidden half = (warp/4)%2); warps 16, 17:
 //     one driver thread per slot (TMA bulk copy of the pre-split bf16 hi/lo token image, then the step's tcgen05.mma);
 //     hand-offs are mbarriers, no __syncthreads in the steady state, the two slots never wait for each other;
@@ -39,7 +40,7 @@ constexpr int RT_SMEM = 2 * RT_W_BYTES + 4 * RT_A_BYTES + 1024;
 #endif
 
 struct RecSeg {
-  const unsigned char* xq; const int* plan; float* out; float* hn; float* sv; unsigned char* hq;
+  const unsigned char* xq; const int* plan; float* out; float* hn; unsigned char* hq;
   int n_tiles, n_slabs, N, L, tile_base;
 };
 struct RecArgs {
@@ -89,9 +90,6 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
   }
   const int t = dir ? (c.Lj - 1 - c.s) : c.s;
   const bool live = t < g.len;
-  // saved gates, column-major inside the (slab, direction) tile: svT[col = gate*64 + unit][row] -> lanes (= rows) are contiguous
-  float* svcol = nullptr;
-  if (TRAIN) svcol = sg.sv + (((size_t)(sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t) * 2 + dir) * SV + u0) * RT_R + row;
   const uint32_t trow = tmem + ((uint32_t)((row >> 5) * 32) << 16) + X * 256 + u0;
 
   if ((threadIdx.x & 255) == 0) TRACE(0, X, n, 0);
@@ -124,13 +122,6 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
       const float hold = g.h[cc * 8 + i];
       const float hnew = fmaf(hold - nv, z, nv);                        // ATen GRU cell: (h - n) * z + n
       hv[i] = live ? hnew : hold;
-      if (TRAIN) {
-        float* s1 = svcol + (size_t)(cc * 8 + i) * RT_R;
-        s1[0] = r;
-        s1[(size_t)H * RT_R] = z;
-        s1[(size_t)2 * H * RT_R] = nv;
-        s1[(size_t)3 * H * RT_R] = hcand * (1.f / K_N);
-      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) g.h[cc * 8 + i] = hv[i];
@@ -397,7 +388,7 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
   for (int i = 0; i < n_seg; ++i) {
     const umpr_gru_seg& s = segs[i];
     if (s.n_tiles < 1 || s.L < 1 || !s.xq || !s.plan || !s.out) return fail_arg("gru_fwd_tc: segment %d is incomplete", i);
-    a.seg[i] = RecSeg{reinterpret_cast<const unsigned char*>(s.xq), s.plan, s.out, s.hn, s.sv, reinterpret_cast<unsigned char*>(s.hq), s.n_tiles, s.n_slabs, s.N, s.L, base};
+    a.seg[i] = RecSeg{reinterpret_cast<const unsigned char*>(s.xq), s.plan, s.out, s.hn, reinterpret_cast<unsigned char*>(s.hq), s.n_tiles, s.n_slabs, s.N, s.L, base};
     base += s.n_tiles;
   }
   a.n_seg = n_seg;
@@ -414,10 +405,10 @@ extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float*
 #else
   a.trace = nullptr;
 #endif
-  bool train = segs[0].sv != nullptr;
+  bool train = segs[0].hq != nullptr;
   for (int i = 0; i < n_seg; ++i)
-    if ((segs[i].sv != nullptr) != train || (segs[i].hq != nullptr) != train)
-      return fail_arg("gru_fwd_tc: sv and hq must be given for all segments (training) or for none (inference)");
+    if ((segs[i].hq != nullptr) != train)
+      return fail_arg("gru_fwd_tc: hq must be given for all segments (training) or for none (inference)");
   auto kern = train ? gru_fwd_tc_kernel<true> : gru_fwd_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM);
   if (e != cudaSuccess) { set_error("gru_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }

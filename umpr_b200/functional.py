@@ -191,17 +191,17 @@ class _GruTcFn(Function):
         n = len(plans)
         need_grad = any(ctx.needs_input_grad[5:])
         segs = (_lib.GruSeg * n)()
-        outs, hns, svs, hqs = [], [], [], []
+        outs, hns, hqs = [], [], []
         tokens = 0
         for i, (plan, xq) in enumerate(zip(plans, xqs)):
             if plan.R != 128:
                 raise RuntimeError("umpr_b200: the tensor-core GRU needs pack plans with 128-row tiles")
             out = torch.empty(plan.N, plan.L, D, dtype=torch.float32, device=dev)
             hn = torch.empty(2, plan.N, H, dtype=torch.float32, device=dev) if want_hidden else None
-            sv = torch.empty(plan.n_slabs * 2 * 128 * SV, dtype=torch.float32, device=dev) if need_grad else None
+            # training keeps h_t as operand images (256 B per token and direction); the backward recomputes the gates from them
             hq = torch.empty(plan.n_slabs * 2 * 2 * 128 * 128, dtype=torch.uint8, device=dev) if need_grad else None
-            segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(sv), ptr(hq), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
-            outs.append(out); hns.append(hn); svs.append(sv); hqs.append(hq)
+            segs[i] = _lib.GruSeg(ptr(xq), ptr(plan.buf), ptr(out), ptr(hn), ptr(hq), plan.n_tiles, plan.n_slabs, plan.N, plan.L)
+            outs.append(out); hns.append(hn); hqs.append(hq)
             tokens += plan.tokens
         from .plan import build_schedule, upload_int32
         sched, nq = build_schedule([p.tile_len for p in plans], GRU_SCHED_CTAS or max(1, _n_ctas(dev) // 2))
@@ -209,7 +209,7 @@ class _GruTcFn(Function):
         call("umpr_gru_fwd_tc", C.addressof(segs), n, ptr_array(w), E, ptr(sched), nq,
              work=(2.0 * tokens * (E + H) * 6 * H, 0.0))
         ctx.plans, ctx.E, ctx.n, ctx.sched, ctx.nq = plans, E, n, sched, nq
-        ctx.save_for_backward(*xqs, *[t for t in hqs if t is not None], *[t for t in svs if t is not None], *w)
+        ctx.save_for_backward(*xqs, *[t for t in hqs if t is not None], *w)
         ctx.out_shapes = [tuple(o.shape) for o in outs]
         res = list(outs)
         for hn in hns:
@@ -225,7 +225,7 @@ class _GruTcFn(Function):
     def backward(ctx, *grads_in):
         plans, E, n = ctx.plans, ctx.E, ctx.n
         saved = ctx.saved_tensors
-        xqs, hqs, svs, w = saved[:n], saved[n:2 * n], saved[2 * n:3 * n], list(saved[3 * n:])
+        xqs, hqs, w = saved[:n], saved[n:2 * n], list(saved[2 * n:])
         dev = xqs[0].device
         grads, rets = _sinks(ctx.params)
         segs = (_lib.GruBwdSeg * n)()
@@ -234,11 +234,13 @@ class _GruTcFn(Function):
             d_out, d_hn = grads_in[i], grads_in[n + i]
             d_out = _f32(d_out) if d_out is not None else torch.zeros(ctx.out_shapes[i], dtype=torch.float32, device=dev)
             d_hn = _f32(d_hn) if (d_hn is not None and d_hn.numel()) else None
-            segs[i] = _lib.GruBwdSeg(ptr(d_out), ptr(d_hn), ptr(svs[i]), ptr(xqs[i]), ptr(hqs[i]), ptr(plan.buf), plan.n_tiles,
+            segs[i] = _lib.GruBwdSeg(ptr(d_out), ptr(d_hn), ptr(xqs[i]), ptr(hqs[i]), ptr(plan.buf), plan.n_tiles,
                                      plan.n_slabs, plan.N, plan.L)
             keep += [d_out, d_hn]
             tokens += plan.tokens
-        # one reverse-time launch over every side (same tile queues as the forward): recurrence + all eight weight gradients
+        # one reverse-time launch over every side (same tile queues as the forward): gate recomputation + recurrence + all eight
+        # weight gradients.  Algorithmic work: 98 304 FLOP/token for the recurrence backward (dh and dW_hh) +
+        # 38 400 for dW_ih; the recomputation of the gates (87 552 FLOP/token) is NOT counted
         call("umpr_gru_bwd_tc", C.addressof(segs), n, ptr_array(w), ptr_array(grads), E, ptr(_zero_image(dev)), ptr(ctx.sched), ctx.nq,
              work=(2.0 * tokens * 2 * H * 3 * H + 2.0 * tokens * 2 * 3 * H * (E + H), 0.0))
         return (None, None, None, None, None, *rets)
