@@ -21,6 +21,8 @@
 //     keep the XU pipe fed); warp 16: driver thread (TMA copies, L2 prefetch of the next step's images, all MMAs);
 //   * HBM traffic per token and direction: xq 256 B + hq 256 B + d_out 256 B (the saved-gate tensor of the first design, 1 KB
 //     written by the forward and read back here, is gone).
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc.cuh"
 #include "gru_tc.cuh"
@@ -28,6 +30,9 @@
 
 namespace umpr {
 using namespace tc;
+
+// clock64 trace of CTA (0,0) (UMPR_TRACE_BWD=<file> at run time): role 0 = gate thread 0, role 1 = driver; 8 events x 64 steps each
+#define BTRACE(role, n, ev) do { if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && (n) < 64) a.trace[((role) * 64 + (n)) * 8 + (ev)] = clock64(); } while (0)
 
 constexpr int RB_GATE_WARPS = 16;
 constexpr int RB_GATE_THREADS = RB_GATE_WARPS * 32;       // 512
@@ -53,6 +58,7 @@ struct BwdArgs {
   float* dw[8];
   const unsigned char* zero_img;      // 32 KB of zeros: h_{t-1} of a sequence's first step
   int E, kx;
+  long long* trace;
 };
 
 struct BwdRow {
@@ -61,7 +67,8 @@ struct BwdRow {
 };
 
 struct BwdBars {
-  uint64_t img_full, p1_full, t1_ready, t1_done, t2_ready, dh_full, step_done, dh_read;
+  uint64_t img_q[4];        // the step's operand images land in four 16 KB quarters: x hi, x lo, h hi, h lo
+  uint64_t p1_full, t1_ready, t1_done, t2_ready, dh_full, step_done, dh_read;
 };
 
 // bf16 hi + lo of 8 consecutive units (one 16-byte chunk of each image row) -> fp32
@@ -110,6 +117,8 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
 #pragma unroll
     for (int i = 0; i < 4; ++i) dy4[i] = *reinterpret_cast<const float4*>(dyrow + 4 * i);
   }
+  const bool tr = threadIdx.x == 0;
+  if (tr) BTRACE(0, n, 0);
   if (n > 0) {
     // the previous step's carry product [dr, dz, dn*r] · W_hh: fold it into the running part, then release its columns
     mbar_wait(&bar->dh_full, (n - 1) & 1);
@@ -125,9 +134,13 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
     tc_fence_before();
     mbar_arrive(&bar->dh_read);
   }
-  mbar_wait(&bar->img_full, n & 1);                     // h_{t-1} image readable (TMA write)
+  if (tr) BTRACE(0, n, 1);
+  mbar_wait(&bar->img_q[2], n & 1);                     // h_{t-1} image readable (TMA write), hi and lo halves
+  mbar_wait(&bar->img_q[3], n & 1);
+  if (tr) BTRACE(0, n, 2);
   mbar_wait(&bar->p1_full, n & 1);                      // recomputed accumulators complete
   tc_fence_after();
+  if (tr) BTRACE(0, n, 3);
 
   // pass-2 blocks (dn*r, dn) wait, packed, in TENSOR MEMORY until the pass-1 MMAs have read the tile: each thread parks them in
   // the r / z accumulator columns IT has just read (nobody else reads those; the next recomputation overwrites them later)
@@ -136,7 +149,6 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
   for (int cc = 0; cc < 2; ++cc) {
     const int chunk = ug * 2 + cc;
     const uint32_t off = off0 + ((uint32_t)(chunk ^ (row & 7)) << 4);
-    float dr[8], dz[8], dn8[8], dnr[8];
     if (any_live) {
       const int ub = u0 + cc * 8;
       uint32_t v[32];
@@ -152,60 +164,82 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
       float hp[8];
       unpack8(hhi, hlo, hp);
       tmem_ld_wait();
+      float dr[8], dz[8], dn8[8], dnr[8];
+      const f2 one = f2_set(1.f, 1.f), mone = f2_set(-1.f, -1.f), two = f2_set(2.f, 2.f);
+      const f2 c4n = f2_set(4.f / RB_K_N, 4.f / RB_K_N), crz = f2_set(1.f / RB_K_RZ, 1.f / RB_K_RZ);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // the forward's cell, same operations in the same order (gru_rec_tc.cu gate_step)
-        const float er = ex2f(__uint_as_float(v[i]));
-        const float r = rcpf(1.f + er);
-        const float hcand = __uint_as_float(v[24 + i]) + bh[i];           // 2 log2e (W_hn h + b_hn)
-        const float xn = fmaf(r, hcand, __uint_as_float(v[16 + i]));
-        const float ez = ex2f(fminf(__uint_as_float(v[8 + i]), 60.f));
-        const float en = ex2f(fminf(xn, 60.f));
-        const float dzd = 1.f + ez, dnd = 1.f + en;
-        const float inv = rcpf(dzd * dnd);
-        const float z = dnd * inv;
-        const float nv = fmaf(-2.f * dzd, inv, 1.f);
-        // backward of the cell
-        const float dh = g.part[cc * 8 + i] + dy[i];
-        const float dn_pre = dh * (1.f - z) * (1.f - nv * nv);
-        const float dz_pre = dh * (hp[i] - nv) * z * (1.f - z);
-        const float dr_pre = dn_pre * (hcand * (1.f / RB_K_N)) * r * (1.f - r);
-        // stored with the inverse of the resident weights' pre-scaling (the carry product then needs no rescaling; the flush
-        // of the weight gradients multiplies it back)
-        dr[i] = live ? dr_pre * (1.f / RB_K_RZ) : 0.f;
-        dz[i] = live ? dz_pre * (1.f / RB_K_RZ) : 0.f;
-        dnr[i] = live ? dn_pre * r * (1.f / RB_K_N) : 0.f;
-        dn8[i] = live ? dn_pre * (1.f / RB_K_N) : 0.f;
-        if (live) g.part[cc * 8 + i] = dh * z;          // beyond this row's length the carry just passes through
+      for (int j = 0; j < 4; ++j) {
+        // two hidden units per instruction (packed fp32).  The forward's cell (gru_rec_tc.cu gate_step): with p = 1 / (1 + e^{2 a_n}),
+        // n = 1 - 2p and 1 - n^2 = 4 p (1 - p)
+        const int i = 2 * j;
+        const f2 er = f2_ex2(f2_bits(v[i], v[i + 1]));
+        const f2 r = f2_rcp(f2_add(er, one));
+        const f2 hcand = f2_add(f2_bits(v[24 + i], v[25 + i]), f2_set(bh[i], bh[i + 1]));   // 2 log2e (W_hn h + b_hn)
+        const f2 xn = f2_fma(r, hcand, f2_bits(v[16 + i], v[17 + i]));
+        const f2 ez = f2_ex2(f2_min(f2_bits(v[8 + i], v[9 + i]), 60.f));
+        const f2 en = f2_ex2(f2_min(xn, 60.f));
+        const f2 dzd = f2_add(ez, one), dnd = f2_add(en, one);
+        const f2 inv = f2_rcp(f2_mul(dzd, dnd));
+        const f2 z = f2_mul(dnd, inv);
+        const f2 pp = f2_mul(dzd, inv);
+        // backward of the cell.  Rows beyond their length: dh = 0 makes every gate gradient an exact zero (the gates are finite),
+        // and the carry just passes through.  The tile values carry the inverse of the resident weights' pre-scaling (the carry
+        // product then needs no rescaling; the flush of the weight gradients multiplies it back):
+        //   dn' = dh (1-z) 4p(1-p) / (2 log2e)   dnr' = dn' r   dr' = dn' hcand r (1-r) / (-log2e)   dz' = dh (h_prev - n) z (1-z) / (-log2e)
+        const f2 part = f2_set(g.part[cc * 8 + i], g.part[cc * 8 + i + 1]);
+        f2 dh = f2_add(part, f2_set(dy[i], dy[i + 1]));
+        if (!live) dh = f2_set(0.f, 0.f);
+        const f2 omz = f2_fma(z, mone, one), omp = f2_fma(pp, mone, one), omr = f2_fma(r, mone, one);
+        const f2 dnp = f2_mul(f2_mul(dh, c4n), f2_mul(f2_mul(omz, pp), omp));
+        const f2 dnrp = f2_mul(dnp, r);
+        const f2 drp = f2_mul(f2_mul(dnp, f2_mul(r, omr)), f2_mul(hcand, crz));
+        const f2 hmn = f2_fma(pp, two, f2_add(f2_set(hp[i], hp[i + 1]), mone));            // h_prev - n
+        const f2 dzp = f2_mul(f2_mul(f2_mul(dh, crz), f2_mul(z, omz)), hmn);
+        const f2 pnew = f2_mul(dh, z);
+        dn8[i] = dnp.x; dn8[i + 1] = dnp.y;
+        dnr[i] = dnrp.x; dnr[i + 1] = dnrp.y;
+        dr[i] = drp.x; dr[i + 1] = drp.y;
+        dz[i] = dzp.x; dz[i + 1] = dzp.y;
+        if (live) { g.part[cc * 8 + i] = pnew.x; g.part[cc * 8 + i + 1] = pnew.y; }
       }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(dr[2 * i], dr[2 * i + 1], hi[i], lo[i]);
+      *reinterpret_cast<uint4*>(gt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(dz[2 * i], dz[2 * i + 1], hi[i], lo[i]);
+      *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], hi[i], lo[i]);
+      tmem_st4(park + cc * 8, hi[0], hi[1], hi[2], hi[3]);
+      tmem_st4(park + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(dn8[2 * i], dn8[2 * i + 1], hi[i], lo[i]);
+      tmem_st4(park + 64 + cc * 8, hi[0], hi[1], hi[2], hi[3]);
+      tmem_st4(park + 64 + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
     } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { dr[i] = 0.f; dz[i] = 0.f; dnr[i] = 0.f; dn8[i] = 0.f; }
+      // no live row in this warp at this step: zero rows in both products
+      const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(gt + off) = zz;
+      *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = zz;
+      *reinterpret_cast<uint4*>(gt + RB_BLK + off) = zz;
+      *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = zz;
+      tmem_st4(park + cc * 8, 0u, 0u, 0u, 0u);
+      tmem_st4(park + cc * 8 + 4, 0u, 0u, 0u, 0u);
+      tmem_st4(park + 64 + cc * 8, 0u, 0u, 0u, 0u);
+      tmem_st4(park + 64 + cc * 8 + 4, 0u, 0u, 0u, 0u);
     }
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dr[2 * i], dr[2 * i + 1], hi[i], lo[i]);
-    *reinterpret_cast<uint4*>(gt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dz[2 * i], dz[2 * i + 1], hi[i], lo[i]);
-    *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], hi[i], lo[i]);
-    tmem_st4(park + cc * 8, hi[0], hi[1], hi[2], hi[3]);
-    tmem_st4(park + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split2(dn8[2 * i], dn8[2 * i + 1], hi[i], lo[i]);
-    tmem_st4(park + 64 + cc * 8, hi[0], hi[1], hi[2], hi[3]);
-    tmem_st4(park + 64 + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
   }
   tmem_st_wait();
   fence_async_smem();
   tc_fence_before();
   mbar_arrive(&bar->t1_ready);         // pass-1 tile (dr | dz) complete, accumulator columns drained
+  if (tr) BTRACE(0, n, 4);
   // pass 2: the same tile buffer, once the pass-1 MMAs have read it
   mbar_wait(&bar->t1_done, n & 1);
+  if (tr) BTRACE(0, n, 5);
 #pragma unroll
   for (int cc = 0; cc < 2; ++cc) {
     const int chunk = ug * 2 + cc;
@@ -222,6 +256,7 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
   fence_async_smem();
   tc_fence_before();                   // the parked words have been read: the next step's recomputation may overwrite the columns
   mbar_arrive(&bar->t2_ready);
+  if (tr) BTRACE(0, n, 6);
 }
 
 __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_constant__ BwdArgs a) {
@@ -239,7 +274,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   const int dir = blockIdx.y;
 
   if (tid == 0) {
-    mbar_init(&bars.img_full, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&bars.img_q[q], 1);
     mbar_init(&bars.p1_full, 1);
     mbar_init(&bars.t1_ready, RB_GATE_THREADS);
     mbar_init(&bars.t1_done, 1);
@@ -274,6 +309,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) BTRACE(1, 63, 0);
 
   // this CTA walks slot queue 2c, then 2c+1, one tile at a time
   if (warp < RB_GATE_WARPS) {
@@ -289,8 +325,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
         cur_next(a, c);
       }
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------------ driver thread
+  } else {
+    // ------------------------------------------------------------------ driver warp: the whole warp runs this code converged, so
+    // that descriptors and addresses stay in uniform registers; the elected lane alone issues the TMA copies and the MMAs (tc.cuh)
+    const uint32_t el = elect_one_sync();
     constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
     constexpr uint32_t id_carry = idesc_bf16(128, 64) | (1u << 16);                  // A = gate tile (K-major), B = W_hh image MN-major
     constexpr uint32_t id_wg = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);       // A = [xq | hq] images, B = gate tile: both token-major
@@ -299,108 +337,134 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     const uint64_t whn_h = smem_desc_sw128(smem_u32(whh + 128 * 128)), whn_l = smem_desc_sw128(smem_u32(whh + G3 * 128 + 128 * 128));
     const uint64_t x_h = smem_desc_sw128(smem_u32(ximg)), x_l = smem_desc_sw128(smem_u32(ximg + RT_R * 128));
     const uint64_t h_h = smem_desc_sw128(smem_u32(himg)), h_l = smem_desc_sw128(smem_u32(himg + RT_R * 128));
-    const uint32_t b_hi = smem_u32(whh), b_lo = smem_u32(whh + G3 * 128);
+    // descriptor of byte offset `o` (a multiple of 16) from a base descriptor: the start-address field counts 16-byte units
+    const uint64_t cb_h = smem_desc_mn_sw128(smem_u32(whh)), cb_l = smem_desc_mn_sw128(smem_u32(whh + G3 * 128));       // carry B: W_hh MN-major
+    const uint64_t ca_h = smem_desc_sw128(smem_u32(gt)), ca_l = smem_desc_sw128(smem_u32(gt + 2 * RB_BLK));             // carry A: gate tile K-major
+    const uint64_t wa_h = desc_mn(smem_u32(ximg), RB_IMG), wa_l = desc_mn(smem_u32(ximg + RT_R * 128), RB_IMG);         // wgrad A: [xq | hq] MN-major
+    const uint64_t wb_h = desc_mn(smem_u32(gt), RB_BLK), wb_l = desc_mn(smem_u32(gt + 2 * RB_BLK), RB_BLK);             // wgrad B: gate tile MN-major
     const uint32_t d_gates = tmem, d_dh = tmem + 192, d_w = tmem + 256;
-    // weight-gradient A operand: M = 128 features = [64 of xq | 64 of hq]: the second 64-feature block lies one image (32 KB) further
-    const uint32_t xa_hi = smem_u32(ximg), xa_lo = smem_u32(ximg + RT_R * 128);
-    const uint32_t g_hi = smem_u32(gt), g_lo = smem_u32(gt + 2 * RB_BLK);
     auto slab_of = [&](const Cur& cc, int& t, int& tp) -> size_t {
       const BwdSeg& sg = a.seg[cc.si];
       t = dir ? cc.s : (cc.Lj - 1 - cc.s);
       tp = dir ? t + 1 : t - 1;
       return (size_t)sg.plan[3 * sg.n_tiles * RT_R + cc.tile];
     };
-    auto produce = [&](const Cur& cc) {      // the step's two operand images, one TMA bulk copy each
+    auto images_of = [&](const Cur& cc, const unsigned char*& xsrc, const unsigned char*& hsrc) {
       const BwdSeg& sg = a.seg[cc.si];
       int t, tp;
       const size_t slab0 = slab_of(cc, t, tp);
-      mbar_arrive_expect_tx(&bars.img_full, 2 * RB_IMG);
-      bulk_copy_g2s(ximg, sg.xq + (slab0 + t) * RB_IMG, RB_IMG, &bars.img_full);
-      const unsigned char* hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
-      bulk_copy_g2s(himg, hsrc, RB_IMG, &bars.img_full);
+      xsrc = sg.xq + (slab0 + t) * RB_IMG;
+      hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
+    };
+    // the step's two operand images as four TMA bulk copies (hi and lo halves land separately, in the order the recomputation
+    // consumes them)
+    auto produce = [&](const unsigned char* xsrc, const unsigned char* hsrc) {
+      constexpr uint32_t HALF = RB_IMG / 2;
+      mbar_arrive_expect_tx_e(el, &bars.img_q[0], HALF);
+      bulk_copy_g2s_e(el, ximg, xsrc, HALF, &bars.img_q[0]);
+      mbar_arrive_expect_tx_e(el, &bars.img_q[1], HALF);
+      bulk_copy_g2s_e(el, ximg + HALF, xsrc + HALF, HALF, &bars.img_q[1]);
+      mbar_arrive_expect_tx_e(el, &bars.img_q[2], HALF);
+      bulk_copy_g2s_e(el, himg, hsrc, HALF, &bars.img_q[2]);
+      mbar_arrive_expect_tx_e(el, &bars.img_q[3], HALF);
+      bulk_copy_g2s_e(el, himg + HALF, hsrc + HALF, HALF, &bars.img_q[3]);
     };
     Cur c;
     int qi = 0;
     cur_init(a, c, 2 * blockIdx.x);
     if (!c.active) { qi = 1; cur_init(a, c, 2 * blockIdx.x + 1); }
-    if (c.active) produce(c);
+    const unsigned char* nx_x = nullptr, *nx_h = nullptr;
+    if (c.active) { images_of(c, nx_x, nx_h); produce(nx_x, nx_h); }
     int n = 0;
     for (; c.active; ++n) {
       Cur nx = c;
       cur_next(a, nx);
       if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
       if (nx.active) {
-        // the next step's operand images are pulled into L2 while this step computes
-        const BwdSeg& sg = a.seg[nx.si];
-        int t, tp;
-        const size_t slab0 = slab_of(nx, t, tp);
-        bulk_prefetch_l2(sg.xq + (slab0 + t) * RB_IMG, RB_IMG);
-        if (tp >= 0 && tp < nx.Lj) bulk_prefetch_l2(sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG, RB_IMG);
+        // the next step's operand images: addresses resolved now (plan look-ups are global loads), pulled into L2 while this step
+        // computes, copied as soon as this step's MMAs have retired
+        images_of(nx, nx_x, nx_h);
+        bulk_prefetch_l2_e(el, nx_x, RB_IMG);
+        if (nx_h != a.zero_img) bulk_prefetch_l2_e(el, nx_h, RB_IMG);
       }
-      mbar_wait(&bars.img_full, n & 1);         // the step's operand images have landed
-      if (n > 0) mbar_wait(&bars.dh_read, (n - 1) & 1);      // the previous carry product has been folded in: its columns are free
+      if (el) BTRACE(1, n, 0);
+      // ---- recomputation: the forward's MMAs (gru_rec_tc.cu), issued quarter by quarter as the images land
+      mbar_wait(&bars.img_q[0], n & 1);         // x hi
       tc_fence_after();
-      // ---- recomputation: the forward's MMAs (gru_rec_tc.cu), same operands, same order
+      if (el) BTRACE(1, n, 1);
       for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
         const uint64_t o = (uint64_t)(kk * 2);
-        umma_bf16(d_gates, x_h + o, wih_h + o, id192, kk != 0);
-        umma_bf16(d_gates, x_h + o, wih_l + o, id192, 1);
-        umma_bf16(d_gates, x_l + o, wih_h + o, id192, 1);
+        umma_bf16_e(el, d_gates, x_h + o, wih_h + o, id192, kk != 0);
+        umma_bf16_e(el, d_gates, x_h + o, wih_l + o, id192, 1);
       }
+      mbar_wait(&bars.img_q[1], n & 1);         // x lo
+      for (int kk = 0; kk < a.kx; ++kk) {
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16_e(el, d_gates, x_l + o, wih_h + o, id192, 1);
+      }
+      mbar_wait(&bars.img_q[2], n & 1);         // h hi
+      if (n > 0) mbar_wait(&bars.dh_read, (n - 1) & 1);      // the previous carry product has been folded in: its columns (= n_h) are free
+      tc_fence_after();
+      if (el) BTRACE(1, n, 2);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {          // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
         const uint64_t o = (uint64_t)(kk * 2);
-        umma_bf16(d_gates, h_h + o, whh_h + o, id128, 1);
-        umma_bf16(d_gates, h_h + o, whh_l + o, id128, 1);
-        umma_bf16(d_gates, h_l + o, whh_h + o, id128, 1);
-        umma_bf16(d_gates + 192, h_h + o, whn_h + o, id64, kk != 0);
-        umma_bf16(d_gates + 192, h_h + o, whn_l + o, id64, 1);
-        umma_bf16(d_gates + 192, h_l + o, whn_h + o, id64, 1);
+        umma_bf16_e(el, d_gates, h_h + o, whh_h + o, id128, 1);
+        umma_bf16_e(el, d_gates, h_h + o, whh_l + o, id128, 1);
+        umma_bf16_e(el, d_gates + 192, h_h + o, whn_h + o, id64, kk != 0);
+        umma_bf16_e(el, d_gates + 192, h_h + o, whn_l + o, id64, 1);
       }
-      umma_commit(&bars.p1_full);
+      mbar_wait(&bars.img_q[3], n & 1);         // h lo
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t o = (uint64_t)(kk * 2);
+        umma_bf16_e(el, d_gates, h_l + o, whh_h + o, id128, 1);
+        umma_bf16_e(el, d_gates + 192, h_l + o, whn_h + o, id64, 1);
+      }
+      umma_commit_e(el, &bars.p1_full);
+      if (el) BTRACE(1, n, 3);
       // ---- pass 1: tile = [dr | dz]
       mbar_wait(&bars.t1_ready, n & 1);
       tc_fence_after();
+      if (el) BTRACE(1, n, 4);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {          // carry, first 128 of K = 192: dh[128 x 64] = tile[128 x 128] · W_hh[r,z rows][128 x 64]
-        const uint32_t blk = (uint32_t)(ks >> 2) * RB_BLK, ko = (uint32_t)(ks & 3) * 32;
-        const uint64_t ah = smem_desc_sw128(g_hi + blk + ko), al = smem_desc_sw128(g_lo + blk + ko);
-        const uint64_t bh = smem_desc_mn_sw128(b_hi + ks * 2048), bl = smem_desc_mn_sw128(b_lo + ks * 2048);
-        umma_bf16(d_dh, ah, bh, id_carry, ks != 0);
-        umma_bf16(d_dh, ah, bl, id_carry, 1);
-        umma_bf16(d_dh, al, bh, id_carry, 1);
+        const uint64_t ao = (uint64_t)(((ks >> 2) * RB_BLK + (ks & 3) * 32) >> 4), bo = (uint64_t)((ks * 2048) >> 4);
+        umma_bf16_e(el, d_dh, ca_h + ao, cb_h + bo, id_carry, ks != 0);
+        umma_bf16_e(el, d_dh, ca_h + ao, cb_l + bo, id_carry, 1);
+        umma_bf16_e(el, d_dh, ca_l + ao, cb_h + bo, id_carry, 1);
       }
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
           // ---- pass 2: tile = [dn*r | dn]
+          if (el) BTRACE(1, n, 5);
           mbar_wait(&bars.t2_ready, n & 1);
           tc_fence_after();
+          if (el) BTRACE(1, n, 6);
 #pragma unroll
           for (int ks = 8; ks < 12; ++ks) {     // carry, last 64 of K: += tile block 0 (dn*r) · W_hh[n rows]
-            const uint32_t ko = (uint32_t)(ks & 3) * 32;
-            const uint64_t ah = smem_desc_sw128(g_hi + ko), al = smem_desc_sw128(g_lo + ko);
-            const uint64_t bh = smem_desc_mn_sw128(b_hi + ks * 2048), bl = smem_desc_mn_sw128(b_lo + ks * 2048);
-            umma_bf16(d_dh, ah, bh, id_carry, 1);
-            umma_bf16(d_dh, ah, bl, id_carry, 1);
-            umma_bf16(d_dh, al, bh, id_carry, 1);
+            const uint64_t ao = (uint64_t)(((ks & 3) * 32) >> 4), bo = (uint64_t)((ks * 2048) >> 4);
+            umma_bf16_e(el, d_dh, ca_h + ao, cb_h + bo, id_carry, 1);
+            umma_bf16_e(el, d_dh, ca_h + ao, cb_l + bo, id_carry, 1);
+            umma_bf16_e(el, d_dh, ca_l + ao, cb_h + bo, id_carry, 1);
           }
-          umma_commit(&bars.dh_full);
+          umma_commit_e(el, &bars.dh_full);
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {        // dW^T[128 features][pass*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
-          const uint64_t ah = desc_mn(xa_hi + ks * 2048, RB_IMG), al = desc_mn(xa_lo + ks * 2048, RB_IMG);
-          const uint64_t gh = desc_mn(g_hi + ks * 2048, RB_BLK), gl = desc_mn(g_lo + ks * 2048, RB_BLK);
+          const uint64_t o = (uint64_t)((ks * 2048) >> 4);
           const uint32_t accf = (n | ks) != 0;
-          umma_bf16(d_w + pass * 128, ah, gh, id_wg, accf);
-          umma_bf16(d_w + pass * 128, ah, gl, id_wg, 1);
-          umma_bf16(d_w + pass * 128, al, gh, id_wg, 1);
+          umma_bf16_e(el, d_w + pass * 128, wa_h + o, wb_h + o, id_wg, accf);
+          umma_bf16_e(el, d_w + pass * 128, wa_h + o, wb_l + o, id_wg, 1);
+          umma_bf16_e(el, d_w + pass * 128, wa_l + o, wb_h + o, id_wg, 1);
         }
-        umma_commit(pass == 0 ? &bars.t1_done : &bars.step_done);
+        umma_commit_e(el, pass == 0 ? &bars.t1_done : &bars.step_done);
       }
       if (nx.active) {
         mbar_wait(&bars.step_done, n & 1);      // every MMA that reads this step's images and tile has retired
-        produce(nx);
+        if (el) BTRACE(1, n, 7);
+        produce(nx_x, nx_h);
       }
       c = nx;
     }
@@ -408,20 +472,22 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   }
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) BTRACE(1, 63, 1);
   // ---- flush dW^T: TMEM lane = feature (x features 0..63, hidden features 64..127), column = gate gradient
   //      [0,64) dr | [64,128) dz | [128,192) dn*r | [192,256) dn, each scaled by 1 / (the resident weights' pre-scaling)
   const bool has_work = a.q_off[2 * blockIdx.x + 2] > a.q_off[2 * blockIdx.x];       // otherwise the accumulator was never written
-  if (warp < 4 && has_work) {
-    const int f = warp * 32 + lane;
+  if (warp < RB_GATE_WARPS && has_work) {
+    // warp w reads the lanes of quarter w % 4 (all a warp may touch) and the 64 columns of column group w / 4
+    const int f = (warp & 3) * 32 + lane;
     float* dw_ih = a.dw[dir * 4 + 0];
     float* dw_hh = a.dw[dir * 4 + 1];
     float* db_ih = a.dw[dir * 4 + 2];
     float* db_hh = a.dw[dir * 4 + 3];
     const int E = a.E;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    for (int c0 = (warp >> 2) * 64; c0 < (warp >> 2) * 64 + 64; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + c0, v);
       const float sc = c0 < 2 * H ? RB_K_RZ : RB_K_N;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -445,6 +511,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) BTRACE(1, 63, 2);
   if (warp == RB_GATE_WARPS) tmem_dealloc(tmem, 512);
 }
 
@@ -475,8 +542,33 @@ extern "C" int umpr_gru_bwd_tc(const umpr_gru_bwd_seg* segs, int n_seg, const fl
   a.zero_img = reinterpret_cast<const unsigned char*>(zero_img);
   a.E = E;
   a.kx = (E + 1 + 15) / 16;
+  a.trace = nullptr;
+  const char* trace_path = getenv("UMPR_TRACE_BWD");
+  static long long* tr = nullptr;
+  if (trace_path) {
+    if (!tr) cudaMalloc(&tr, 2 * 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(tr, 0, 2 * 64 * 8 * sizeof(long long), (cudaStream_t)stream);
+    a.trace = tr;
+  }
   cudaError_t e = cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM);
   if (e != cudaSuccess) { set_error("gru_bwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   gru_bwd_tc_kernel<<<dim3(n_queues / 2, 2), RB_THREADS, RB_SMEM, (cudaStream_t)stream>>>(a);
+  if (trace_path) {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    static long long host[2 * 64 * 8];
+    cudaMemcpy(host, tr, sizeof(host), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      const long long t0 = host[(1 * 64 + 0) * 8 + 0];
+      for (int role = 0; role < 2; ++role)
+        for (int n = 0; n < 40; ++n) {
+          fprintf(f, "%s step %2d:", role ? "driver" : "gate  ", n);
+          for (int ev = 0; ev < 8; ++ev) fprintf(f, " %8lld", host[(role * 64 + n) * 8 + ev] ? host[(role * 64 + n) * 8 + ev] - t0 : -1);
+          fprintf(f, "\n");
+        }
+      fprintf(f, "phases (cycles since the driver's first event): main loop starts %lld, ends %lld, flush done %lld\n",
+              host[(1 * 64 + 63) * 8 + 0] - t0, host[(1 * 64 + 63) * 8 + 1] - t0, host[(1 * 64 + 63) * 8 + 2] - t0);
+      fclose(f);
+    }
+  }
   return check_launch("gru_bwd_tc");
 }

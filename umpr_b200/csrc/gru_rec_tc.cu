@@ -107,21 +107,27 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
     const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     tmem_ld_wait();
     float hv[8];
+    const f2 one = f2_set(1.f, 1.f), mone = f2_set(-1.f, -1.f), two = f2_set(2.f, 2.f), mtwo = f2_set(-2.f, -2.f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float er = ex2f(__uint_as_float(v[i]));                     // e^{-a_r}
-      const float r = rcpf(1.f + er);                                   // sigmoid
-      const float hcand = __uint_as_float(v[24 + i]) + bh[i];           // K_N (W_hn h + b_hn)
-      const float xn = fmaf(r, hcand, __uint_as_float(v[16 + i]));      // K_N (n pre-activation)
-      const float ez = ex2f(fminf(__uint_as_float(v[8 + i]), 60.f));    // e^{-a_z}
-      const float en = ex2f(fminf(xn, 60.f));                           // e^{2 a_n}
-      const float dz = 1.f + ez, dn = 1.f + en;
-      const float inv = rcpf(dz * dn);                                  // one reciprocal for z and n
-      const float z = dn * inv;
-      const float nv = fmaf(-2.f * dz, inv, 1.f);                       // tanh(a_n) = 1 - 2 / (1 + e^{2 a_n})
-      const float hold = g.h[cc * 8 + i];
-      const float hnew = fmaf(hold - nv, z, nv);                        // ATen GRU cell: (h - n) * z + n
-      hv[i] = live ? hnew : hold;
+    for (int j = 0; j < 4; ++j) {
+      // two hidden units per instruction (packed fp32); with p = 1 / (1 + e^{2 a_n}):  n = tanh(a_n) = 1 - 2p
+      const int i = 2 * j;
+      const f2 er = f2_ex2(f2_bits(v[i], v[i + 1]));                                   // e^{-a_r}
+      const f2 r = f2_rcp(f2_add(er, one));                                             // sigmoid
+      const f2 hcand = f2_add(f2_bits(v[24 + i], v[25 + i]), f2_set(bh[i], bh[i + 1])); // K_N (W_hn h + b_hn)
+      const f2 xn = f2_fma(r, hcand, f2_bits(v[16 + i], v[17 + i]));                    // K_N (n pre-activation)
+      const f2 ez = f2_ex2(f2_min(f2_bits(v[8 + i], v[9 + i]), 60.f));                  // e^{-a_z}
+      const f2 en = f2_ex2(f2_min(xn, 60.f));                                           // e^{2 a_n}
+      const f2 dz = f2_add(ez, one), dn = f2_add(en, one);
+      const f2 inv = f2_rcp(f2_mul(dz, dn));                                            // one reciprocal for z and n
+      const f2 z = f2_mul(dn, inv);
+      const f2 pp = f2_mul(dz, inv);
+      const f2 nv = f2_fma(pp, mtwo, one);
+      const f2 hold = f2_set(g.h[cc * 8 + i], g.h[cc * 8 + i + 1]);
+      const f2 hmn = f2_fma(pp, two, f2_add(hold, mone));                               // h - n
+      const f2 hnew = f2_fma(hmn, z, nv);                                               // ATen GRU cell: (h - n) * z + n
+      hv[i] = live ? hnew.x : hold.x;
+      hv[i + 1] = live ? hnew.y : hold.y;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) g.h[cc * 8 + i] = hv[i];
@@ -292,9 +298,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
       if (X == 0 && n == 0) mbar_arrive(&stagger);
       cur_next(a, c);
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------------ slot drivers (warp 16: slot 0, warp 17: slot 1), one thread each:
-    // TMA producer of the packed-token image AND tcgen05.mma issuer of its slot
+  } else {
+    // ------------------------------------------------------------------ slot drivers (warp 16: slot 0, warp 17: slot 1): TMA producer of the
+    // packed-token image AND tcgen05.mma issuer of its slot.  The whole warp runs this code converged so that descriptors and
+    // addresses stay in uniform registers; only the elected lane's predicate lets the TMA / MMA instructions through (tc.cuh)
+    const uint32_t el = elect_one_sync();
     const int X = warp - RT_GATE_WARPS;
     constexpr uint32_t id192 = idesc_bf16(128, 192), id128 = idesc_bf16(128, 128), id64 = idesc_bf16(128, 64);
     const uint64_t wih_h = smem_desc_sw128(smem_u32(wih)), wih_l = smem_desc_sw128(smem_u32(wih + G3 * 128));
@@ -310,47 +318,47 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
       const RecSeg& sg = a.seg[c.si];
       const int t = dir ? (c.Lj - 1 - c.s) : c.s;
       const int slab = sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t;
-      mbar_arrive_expect_tx(&x_full[X], RT_A_BYTES);
-      bulk_copy_g2s(xbuf, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
+      mbar_arrive_expect_tx_e(el, &x_full[X], RT_A_BYTES);
+      bulk_copy_g2s_e(el, xbuf, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
     };
     if (c.active) load_x();
     // start slot 1 half a period late: its MMAs then run under slot 0's gate math and vice versa (anti-phase is self-sustaining)
     if (X == 1 && c.active) mbar_wait(&stagger, 0);
     for (int n = 0; c.active; ++n) {
-      TRACE(1, X, n, 0);
+      if (el) TRACE(1, X, n, 0);
       mbar_wait(&x_full[X], n & 1);
-      TRACE(1, X, n, 1);
+      if (el) TRACE(1, X, n, 1);
       mbar_wait(&h_ready[X], n & 1);            // h_{t-1} image written AND the slot's accumulator columns drained
       tc_fence_after();
-      TRACE(1, X, n, 2);
+      if (el) TRACE(1, X, n, 2);
       if (TRAIN && c.s > 0) {
         // training: keep h_{t-1} as an operand image (bf16 hi|lo, 32 KB) for the backward kernel: it is the A operand of this
         // step's MMAs, the h_prev of the GRU cell's backward and the token-major operand of the weight-gradient MMA
         const RecSeg& sg = a.seg[c.si];
         const int tprev = dir ? (c.Lj - c.s) : (c.s - 1);
         const size_t slab = (size_t)sg.plan[3 * sg.n_tiles * RT_R + c.tile] + tprev;
-        bulk_copy_s2g(sg.hq + (slab * 2 + dir) * RT_A_BYTES, hs + X * RT_A_BYTES, RT_A_BYTES);
+        bulk_copy_s2g_e(el, sg.hq + (slab * 2 + dir) * RT_A_BYTES, hs + X * RT_A_BYTES, RT_A_BYTES);
       }
       for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
         const uint64_t o = (uint64_t)(kk * 2);
-        umma_bf16(d, x_h + o, wih_h + o, id192, kk != 0);
-        umma_bf16(d, x_h + o, wih_l + o, id192, 1);
-        umma_bf16(d, x_l + o, wih_h + o, id192, 1);
+        umma_bf16_e(el, d, x_h + o, wih_h + o, id192, kk != 0);
+        umma_bf16_e(el, d, x_h + o, wih_l + o, id192, 1);
+        umma_bf16_e(el, d, x_l + o, wih_h + o, id192, 1);
       }
-      umma_commit(&x_empty[X]);
+      umma_commit_e(el, &x_empty[X]);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {          // h_{t-1} · W_hh^T -> += r, z ; n_h (own columns)
         const uint64_t o = (uint64_t)(kk * 2);
-        umma_bf16(d, h_h + o, whh_h + o, id128, 1);
-        umma_bf16(d, h_h + o, whh_l + o, id128, 1);
-        umma_bf16(d, h_l + o, whh_h + o, id128, 1);
-        umma_bf16(d + 192, h_h + o, whn_h + o, id64, kk != 0);
-        umma_bf16(d + 192, h_h + o, whn_l + o, id64, 1);
-        umma_bf16(d + 192, h_l + o, whn_h + o, id64, 1);
+        umma_bf16_e(el, d, h_h + o, whh_h + o, id128, 1);
+        umma_bf16_e(el, d, h_h + o, whh_l + o, id128, 1);
+        umma_bf16_e(el, d, h_l + o, whh_h + o, id128, 1);
+        umma_bf16_e(el, d + 192, h_h + o, whn_h + o, id64, kk != 0);
+        umma_bf16_e(el, d + 192, h_h + o, whn_l + o, id64, 1);
+        umma_bf16_e(el, d + 192, h_l + o, whn_h + o, id64, 1);
       }
       if (TRAIN) bulk_wait_read();              // the h image has been read out before the gate threads may overwrite it
-      umma_commit(&acc_full[X]);
-      TRACE(1, X, n, 3);
+      umma_commit_e(el, &acc_full[X]);
+      if (el) TRACE(1, X, n, 3);
       cur_next(a, c);
       if (c.active) {
         mbar_wait(&x_empty[X], n & 1);          // the x-part MMAs of this step have consumed the buffer

@@ -50,6 +50,17 @@ __device__ __forceinline__ void tmem_wait8(uint32_t* r) {
 }
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): the gate math is bound by the FP32 pipe's issue rate, one instruction per two
+// hidden units halves it.  MUFU (ex2, rcp) and min stay scalar.
+typedef float2 f2;
+__device__ __forceinline__ f2 f2_set(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ f2 f2_bits(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 f2_ex2(f2 a) { return make_float2(ex2f(a.x), ex2f(a.y)); }
+__device__ __forceinline__ f2 f2_rcp(f2 a) { return make_float2(rcpf(a.x), rcpf(a.y)); }
+__device__ __forceinline__ f2 f2_min(f2 a, float m) { return make_float2(fminf(a.x, m), fminf(a.y, m)); }
 __device__ __forceinline__ void st_zero8(float* p) {
   *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
   *reinterpret_cast<float4*>(p + 4) = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -128,6 +128,74 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- warp-uniform issue -------------------------------------------------------------------------------------------------------
+// tcgen05.mma / TMA / commit take their operands from UNIFORM registers.  Inside an `if (lane == 0)` region the compiler has to
+// treat every operand as divergent and wraps each instruction in an ELECT + R2UR.BROADCAST loop (~100 cycles per MMA).  The
+// "_e" forms below are executed by the whole, converged warp with uniform operands; only the elected lane's predicate lets the
+// instruction itself through - descriptors then live in uniform registers and an MMA costs a handful of issue slots.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_e(uint32_t el, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(el) : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t el, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(el) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint32_t el, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      ".reg .b64 st;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(bytes), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_e(uint32_t el, void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %4, 0;\n\t"
+      "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+      "}" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2_e(uint32_t el, const void* gmem_src, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q cp.async.bulk.prefetch.L2.global [%0], %1;\n\t"
+      "}" ::"l"(gmem_src), "r"(bytes), "r"(el) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_s2g_e(uint32_t el, void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\t"
+      "}" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes), "r"(el) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");      // (an empty group on the other lanes)
+}
+
 // ---- TMEM -> registers: each lane of the warp reads its own TMEM lane (= accumulator row), 32 consecutive columns
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
