@@ -10,10 +10,11 @@
 //   * shared memory (225 KB): W_ih and W_hh images (bf16 hi|lo, pre-scaled by -log2e / 2 log2e exactly as in the forward), the
 //     step's token image xq[t] and hidden image hq[t-1] (ONE TMA bulk copy each - they serve K-major as the A operand of the
 //     recomputation and MN-major as the A operand of the weight-gradient product), and a 64 KB gate-gradient tile;
-//   * the gate-gradient tile (token-major bf16 hi|lo, two blocks of 64 gates, written by the gate threads in two passes:
-//     [dr | dz], then [dn*r | dn]) is BOTH the K-major A operand of the carry product (B = the resident W_hh image read MN-major)
-//     and the MN-major B operand of the weight-gradient product; its values carry the inverse of the weight pre-scaling, which the
-//     final flush undoes;
+//   * the gate-gradient tile (token-major bf16 hi|lo, two blocks of 64 gates: [dr | dz] and [dn*r | dn] of 32 hidden units) is
+//     BOTH the K-major A operand of the carry product (B = the resident W_hh image read MN-major) and the MN-major B operand of
+//     the weight-gradient product; its values carry the inverse of the weight pre-scaling, which the final flush undoes.  It is
+//     written twice per step - hidden units 0..31, then 32..63 - so that the MMAs of the first half run under the gate math of
+//     the second;
 //   * tensor memory (512 columns): [0,64) r | [64,128) z | [128,192) n_x | [192,256) n_h, re-used for dh (the carry product lands
 //     where the next step's W_hn h will: the gate threads fold dh into their registers first) | [256,512) dW^T accumulator, kept
 //     over the CTA's whole queue and flushed once with atomics into the eight nn.GRU gradients;
@@ -67,8 +68,8 @@ struct BwdRow {
 };
 
 struct BwdBars {
-  uint64_t img_q[4];        // the step's operand images land in four 16 KB quarters: x hi, x lo, h hi, h lo
-  uint64_t p1_full, t1_ready, t1_done, t2_ready, dh_full, step_done, dh_read;
+  uint64_t img_q[2];        // the step's operand images land separately: x (hi|lo), h (hi|lo)
+  uint64_t p1_full, ta_ready, ta_done, tb_ready, dh_full, step_done, dh_read;
 };
 
 // bf16 hi + lo of 8 consecutive units (one 16-byte chunk of each image row) -> fp32
@@ -81,11 +82,67 @@ __device__ __forceinline__ void unpack8(const uint4 hi, const uint4 lo, float* v
   }
 }
 
-// One reverse time step of one tile for one gate thread (row = sequence of the tile, ug = which 16 of the 64 hidden units).
+// Gate gradients of 8 hidden units (u .. u+7) of one row: recompute the cell from the accumulators, back-propagate dh.
+// -> packed bf16 hi / lo words of [dr | dz | dn*r | dn] (4 words each), carrying the inverse of the resident weights' pre-scaling.
+// v: the unit's four accumulator groups (bwd_cell_load), already waited for.
+__device__ __forceinline__ void bwd_cell_load(uint32_t trow, int u, uint32_t (&v)[32]) {
+  tmem_ld8_issue(trow + u, v);
+  tmem_ld8_issue(trow + 64 + u, v + 8);
+  tmem_ld8_issue(trow + 128 + u, v + 16);
+  tmem_ld8_issue(trow + 192 + u, v + 24);
+}
+__device__ __forceinline__ void bwd_cell8(const uint32_t (&v)[32], int u, const unsigned char* himg, uint32_t hoff, const float* s_bhn, const float4 dya,
+                                          const float4 dyb, bool live, float* part, uint32_t (&hi)[4][4], uint32_t (&lo)[4][4]) {
+  const uint4 hhi = *reinterpret_cast<const uint4*>(himg + hoff);
+  const uint4 hlo = *reinterpret_cast<const uint4*>(himg + RT_R * 128 + hoff);
+  const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + u), b1 = *reinterpret_cast<const float4*>(s_bhn + u + 4);
+  const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const float dy[8] = {dya.x, dya.y, dya.z, dya.w, dyb.x, dyb.y, dyb.z, dyb.w};
+  float hp[8];
+  unpack8(hhi, hlo, hp);
+  const f2 one = f2_set(1.f, 1.f), mone = f2_set(-1.f, -1.f), two = f2_set(2.f, 2.f);
+  const f2 c4n = f2_set(4.f / RB_K_N, 4.f / RB_K_N), crz = f2_set(1.f / RB_K_RZ, 1.f / RB_K_RZ);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    // two hidden units per instruction (packed fp32).  The forward's cell (gru_rec_tc.cu gate_step): with p = 1 / (1 + e^{2 a_n}),
+    // n = 1 - 2p and 1 - n^2 = 4 p (1 - p)
+    const int i = 2 * j;
+    const f2 er = f2_ex2(f2_bits(v[i], v[i + 1]));
+    const f2 r = f2_rcp(f2_add(er, one));
+    const f2 hcand = f2_add(f2_bits(v[24 + i], v[25 + i]), f2_set(bh[i], bh[i + 1]));   // 2 log2e (W_hn h + b_hn)
+    const f2 xn = f2_fma(r, hcand, f2_bits(v[16 + i], v[17 + i]));
+    const f2 ez = f2_ex2(f2_min(f2_bits(v[8 + i], v[9 + i]), 60.f));
+    const f2 en = f2_ex2(f2_min(xn, 60.f));
+    const f2 dzd = f2_add(ez, one), dnd = f2_add(en, one);
+    const f2 inv = f2_rcp(f2_mul(dzd, dnd));
+    const f2 z = f2_mul(dnd, inv);
+    const f2 pp = f2_mul(dzd, inv);
+    // backward of the cell.  Rows beyond their length: dh = 0 makes every gate gradient an exact zero (the gates are finite), and
+    // the carry just passes through.  With the inverse pre-scaling folded in:
+    //   dn' = dh (1-z) 4p(1-p) / (2 log2e)   dnr' = dn' r   dr' = dn' hcand r (1-r) / (-log2e)   dz' = dh (h_prev - n) z (1-z) / (-log2e)
+    f2 dh = f2_add(f2_set(part[i], part[i + 1]), f2_set(dy[i], dy[i + 1]));
+    if (!live) dh = f2_set(0.f, 0.f);
+    const f2 omz = f2_fma(z, mone, one), omp = f2_fma(pp, mone, one), omr = f2_fma(r, mone, one);
+    const f2 dnp = f2_mul(f2_mul(dh, c4n), f2_mul(f2_mul(omz, pp), omp));
+    const f2 dnrp = f2_mul(dnp, r);
+    const f2 drp = f2_mul(f2_mul(dnp, f2_mul(r, omr)), f2_mul(hcand, crz));
+    const f2 hmn = f2_fma(pp, two, f2_add(f2_set(hp[i], hp[i + 1]), mone));            // h_prev - n
+    const f2 dzp = f2_mul(f2_mul(f2_mul(dh, crz), f2_mul(z, omz)), hmn);
+    const f2 pnew = f2_mul(dh, z);
+    split2(drp.x, drp.y, hi[0][j], lo[0][j]);
+    split2(dzp.x, dzp.y, hi[1][j], lo[1][j]);
+    split2(dnrp.x, dnrp.y, hi[2][j], lo[2][j]);
+    split2(dnp.x, dnp.y, hi[3][j], lo[3][j]);
+    if (live) { part[i] = pnew.x; part[i + 1] = pnew.y; }
+  }
+}
+
+// One reverse time step of one tile for one gate thread: row = sequence of the tile, ug = which 8 hidden units of each half
+// (units ug*8 .. +7 of 0..31, then of 32..63).
 __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, BwdRow& g, int n, int dir, int row, int ug,
                                               const unsigned char* himg, unsigned char* gt, const float* s_bhn, BwdBars* bar, uint32_t tmem) {
   const BwdSeg& sg = a.seg[c.si];
-  const int u0 = ug * 16;
+  const int ua = ug * 8, ub = 32 + ug * 8;              // this thread's units in the two halves
   const int Rp = sg.n_tiles * RT_R;
   if (c.s == 0) {
     const int k = c.tile * RT_R + row;
@@ -94,10 +151,10 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
 #pragma unroll
     for (int i = 0; i < 16; ++i) g.part[i] = 0.f;
     if (sg.d_hn && g.rowo >= 0) {
-      const float* hp = sg.d_hn + ((size_t)dir * sg.N + sg.plan[k]) * H + u0;
+      const float* hp = sg.d_hn + ((size_t)dir * sg.N + sg.plan[k]) * H;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(hp + i * 4);
+        const float4 v = *reinterpret_cast<const float4*>(hp + (i < 2 ? ua : ub - 8) + i * 4);
         g.part[4 * i] = v.x; g.part[4 * i + 1] = v.y; g.part[4 * i + 2] = v.z; g.part[4 * i + 3] = v.w;
       }
     }
@@ -113,9 +170,11 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
 #pragma unroll
   for (int i = 0; i < 4; ++i) dy4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live) {
-    const float* dyrow = sg.d_out + ((size_t)g.rowo * sg.L + t) * D + dir * H + u0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dy4[i] = *reinterpret_cast<const float4*>(dyrow + 4 * i);
+    const float* dyrow = sg.d_out + ((size_t)g.rowo * sg.L + t) * D + dir * H;
+    dy4[0] = *reinterpret_cast<const float4*>(dyrow + ua);
+    dy4[1] = *reinterpret_cast<const float4*>(dyrow + ua + 4);
+    dy4[2] = *reinterpret_cast<const float4*>(dyrow + ub);
+    dy4[3] = *reinterpret_cast<const float4*>(dyrow + ub + 4);
   }
   const bool tr = threadIdx.x == 0;
   if (tr) BTRACE(0, n, 0);
@@ -125,8 +184,8 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
     tc_fence_after();
     if (c.s > 0) {                                      // (a tile's first step: what is there belongs to the previous tile)
       uint32_t acc[16];
-      tmem_ld8_issue(trow + 192 + u0, acc);
-      tmem_ld8_issue(trow + 192 + u0 + 8, acc + 8);
+      tmem_ld8_issue(trow + 192 + ua, acc);
+      tmem_ld8_issue(trow + 192 + ub, acc + 8);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) g.part[i] += __uint_as_float(acc[i]);
@@ -135,127 +194,64 @@ __device__ __forceinline__ void bwd_gate_step(const BwdArgs& a, const Cur& c, Bw
     mbar_arrive(&bar->dh_read);
   }
   if (tr) BTRACE(0, n, 1);
-  mbar_wait(&bar->img_q[2], n & 1);                     // h_{t-1} image readable (TMA write), hi and lo halves
-  mbar_wait(&bar->img_q[3], n & 1);
+  mbar_wait(&bar->img_q[1], n & 1);                     // h_{t-1} image readable (TMA write)
   if (tr) BTRACE(0, n, 2);
   mbar_wait(&bar->p1_full, n & 1);                      // recomputed accumulators complete
   tc_fence_after();
   if (tr) BTRACE(0, n, 3);
 
-  // pass-2 blocks (dn*r, dn) wait, packed, in TENSOR MEMORY until the pass-1 MMAs have read the tile: each thread parks them in
-  // the r / z accumulator columns IT has just read (nobody else reads those; the next recomputation overwrites them later)
-  const uint32_t park = trow + u0;
+  // tile rows: block 0 = [dr (32 units of the half) | dz (32)], block 1 = [dn*r | dn]; this thread's 8 units are 16-byte chunk ug
+  // of the first gate type and chunk 4 + ug of the second (chunks are XOR-swizzled with the row, SWIZZLE_128B)
+  const uint32_t o1 = off0 + ((uint32_t)(ug ^ (row & 7)) << 4), o2 = off0 + ((uint32_t)((4 + ug) ^ (row & 7)) << 4);
+  auto store_tile = [&](const uint32_t (&hi)[4][4], const uint32_t (&lo)[4][4]) {
+    *reinterpret_cast<uint4*>(gt + o1) = make_uint4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);                     // dr
+    *reinterpret_cast<uint4*>(gt + o2) = make_uint4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);                     // dz
+    *reinterpret_cast<uint4*>(gt + RB_BLK + o1) = make_uint4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);            // dn*r
+    *reinterpret_cast<uint4*>(gt + RB_BLK + o2) = make_uint4(hi[3][0], hi[3][1], hi[3][2], hi[3][3]);            // dn
+    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + o1) = make_uint4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + o2) = make_uint4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + o1) = make_uint4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + o2) = make_uint4(lo[3][0], lo[3][1], lo[3][2], lo[3][3]);
+  };
+  auto store_zero = [&]() {                             // no live row in this warp at this step: zero rows in both products
+    const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int chunk = ug * 2 + cc;
-    const uint32_t off = off0 + ((uint32_t)(chunk ^ (row & 7)) << 4);
-    if (any_live) {
-      const int ub = u0 + cc * 8;
-      uint32_t v[32];
-      tmem_ld8_issue(trow + ub, v);
-      tmem_ld8_issue(trow + 64 + ub, v + 8);
-      tmem_ld8_issue(trow + 128 + ub, v + 16);
-      tmem_ld8_issue(trow + 192 + ub, v + 24);
-      const uint4 hhi = *reinterpret_cast<const uint4*>(himg + off);
-      const uint4 hlo = *reinterpret_cast<const uint4*>(himg + RT_R * 128 + off);
-      const float4 b0 = *reinterpret_cast<const float4*>(s_bhn + ub), b1 = *reinterpret_cast<const float4*>(s_bhn + ub + 4);
-      const float bh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const float dy[8] = {dy4[2 * cc].x, dy4[2 * cc].y, dy4[2 * cc].z, dy4[2 * cc].w, dy4[2 * cc + 1].x, dy4[2 * cc + 1].y, dy4[2 * cc + 1].z, dy4[2 * cc + 1].w};
-      float hp[8];
-      unpack8(hhi, hlo, hp);
-      tmem_ld_wait();
-      float dr[8], dz[8], dn8[8], dnr[8];
-      const f2 one = f2_set(1.f, 1.f), mone = f2_set(-1.f, -1.f), two = f2_set(2.f, 2.f);
-      const f2 c4n = f2_set(4.f / RB_K_N, 4.f / RB_K_N), crz = f2_set(1.f / RB_K_RZ, 1.f / RB_K_RZ);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // two hidden units per instruction (packed fp32).  The forward's cell (gru_rec_tc.cu gate_step): with p = 1 / (1 + e^{2 a_n}),
-        // n = 1 - 2p and 1 - n^2 = 4 p (1 - p)
-        const int i = 2 * j;
-        const f2 er = f2_ex2(f2_bits(v[i], v[i + 1]));
-        const f2 r = f2_rcp(f2_add(er, one));
-        const f2 hcand = f2_add(f2_bits(v[24 + i], v[25 + i]), f2_set(bh[i], bh[i + 1]));   // 2 log2e (W_hn h + b_hn)
-        const f2 xn = f2_fma(r, hcand, f2_bits(v[16 + i], v[17 + i]));
-        const f2 ez = f2_ex2(f2_min(f2_bits(v[8 + i], v[9 + i]), 60.f));
-        const f2 en = f2_ex2(f2_min(xn, 60.f));
-        const f2 dzd = f2_add(ez, one), dnd = f2_add(en, one);
-        const f2 inv = f2_rcp(f2_mul(dzd, dnd));
-        const f2 z = f2_mul(dnd, inv);
-        const f2 pp = f2_mul(dzd, inv);
-        // backward of the cell.  Rows beyond their length: dh = 0 makes every gate gradient an exact zero (the gates are finite),
-        // and the carry just passes through.  The tile values carry the inverse of the resident weights' pre-scaling (the carry
-        // product then needs no rescaling; the flush of the weight gradients multiplies it back):
-        //   dn' = dh (1-z) 4p(1-p) / (2 log2e)   dnr' = dn' r   dr' = dn' hcand r (1-r) / (-log2e)   dz' = dh (h_prev - n) z (1-z) / (-log2e)
-        const f2 part = f2_set(g.part[cc * 8 + i], g.part[cc * 8 + i + 1]);
-        f2 dh = f2_add(part, f2_set(dy[i], dy[i + 1]));
-        if (!live) dh = f2_set(0.f, 0.f);
-        const f2 omz = f2_fma(z, mone, one), omp = f2_fma(pp, mone, one), omr = f2_fma(r, mone, one);
-        const f2 dnp = f2_mul(f2_mul(dh, c4n), f2_mul(f2_mul(omz, pp), omp));
-        const f2 dnrp = f2_mul(dnp, r);
-        const f2 drp = f2_mul(f2_mul(dnp, f2_mul(r, omr)), f2_mul(hcand, crz));
-        const f2 hmn = f2_fma(pp, two, f2_add(f2_set(hp[i], hp[i + 1]), mone));            // h_prev - n
-        const f2 dzp = f2_mul(f2_mul(f2_mul(dh, crz), f2_mul(z, omz)), hmn);
-        const f2 pnew = f2_mul(dh, z);
-        dn8[i] = dnp.x; dn8[i + 1] = dnp.y;
-        dnr[i] = dnrp.x; dnr[i + 1] = dnrp.y;
-        dr[i] = drp.x; dr[i + 1] = drp.y;
-        dz[i] = dzp.x; dz[i + 1] = dzp.y;
-        if (live) { g.part[cc * 8 + i] = pnew.x; g.part[cc * 8 + i + 1] = pnew.y; }
-      }
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split2(dr[2 * i], dr[2 * i + 1], hi[i], lo[i]);
-      *reinterpret_cast<uint4*>(gt + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split2(dz[2 * i], dz[2 * i + 1], hi[i], lo[i]);
-      *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split2(dnr[2 * i], dnr[2 * i + 1], hi[i], lo[i]);
-      tmem_st4(park + cc * 8, hi[0], hi[1], hi[2], hi[3]);
-      tmem_st4(park + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split2(dn8[2 * i], dn8[2 * i + 1], hi[i], lo[i]);
-      tmem_st4(park + 64 + cc * 8, hi[0], hi[1], hi[2], hi[3]);
-      tmem_st4(park + 64 + cc * 8 + 4, lo[0], lo[1], lo[2], lo[3]);
-    } else {
-      // no live row in this warp at this step: zero rows in both products
-      const uint4 zz = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(gt + off) = zz;
-      *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = zz;
-      *reinterpret_cast<uint4*>(gt + RB_BLK + off) = zz;
-      *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = zz;
-      tmem_st4(park + cc * 8, 0u, 0u, 0u, 0u);
-      tmem_st4(park + cc * 8 + 4, 0u, 0u, 0u, 0u);
-      tmem_st4(park + 64 + cc * 8, 0u, 0u, 0u, 0u);
-      tmem_st4(park + 64 + cc * 8 + 4, 0u, 0u, 0u, 0u);
+    for (int b = 0; b < 4; ++b) {
+      *reinterpret_cast<uint4*>(gt + b * RB_BLK + o1) = zz;
+      *reinterpret_cast<uint4*>(gt + b * RB_BLK + o2) = zz;
     }
-  }
-  tmem_st_wait();
-  fence_async_smem();
-  tc_fence_before();
-  mbar_arrive(&bar->t1_ready);         // pass-1 tile (dr | dz) complete, accumulator columns drained
-  if (tr) BTRACE(0, n, 4);
-  // pass 2: the same tile buffer, once the pass-1 MMAs have read it
-  mbar_wait(&bar->t1_done, n & 1);
-  if (tr) BTRACE(0, n, 5);
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    const int chunk = ug * 2 + cc;
-    const uint32_t off = off0 + ((uint32_t)(chunk ^ (row & 7)) << 4);
-    uint32_t q[16];                                     // [dn*r hi 4 | lo 4 | dn hi 4 | lo 4]
-    tmem_ld8_issue(park + cc * 8, q);
-    tmem_ld8_issue(park + 64 + cc * 8, q + 8);
+  };
+  // ---- half A: hidden units 0..31
+  uint32_t v[32];
+  if (any_live) {
+    uint32_t hi[4][4], lo[4][4];
+    bwd_cell_load(trow, ua, v);
     tmem_ld_wait();
-    *reinterpret_cast<uint4*>(gt + off) = make_uint4(q[0], q[1], q[2], q[3]);
-    *reinterpret_cast<uint4*>(gt + 2 * RB_BLK + off) = make_uint4(q[4], q[5], q[6], q[7]);
-    *reinterpret_cast<uint4*>(gt + RB_BLK + off) = make_uint4(q[8], q[9], q[10], q[11]);
-    *reinterpret_cast<uint4*>(gt + 3 * RB_BLK + off) = make_uint4(q[12], q[13], q[14], q[15]);
+    bwd_cell8(v, ua, himg, o1, s_bhn, dy4[0], dy4[1], live, g.part, hi, lo);
+    store_tile(hi, lo);
+    // half B's accumulators are read BEFORE half A is handed over: the carry product of half A lands in the n_h columns
+    bwd_cell_load(trow, ub, v);
+    tmem_ld_wait();
+  } else {
+    store_zero();
   }
   fence_async_smem();
-  tc_fence_before();                   // the parked words have been read: the next step's recomputation may overwrite the columns
-  mbar_arrive(&bar->t2_ready);
+  tc_fence_before();                   // every accumulator column this thread reads has been read
+  mbar_arrive(&bar->ta_ready);
+  if (tr) BTRACE(0, n, 4);
+  // ---- half B: hidden units 32..63, computed while the MMAs of half A run; written once they have read the tile
+  if (any_live) {
+    uint32_t hi[4][4], lo[4][4];
+    bwd_cell8(v, ub, himg, o2, s_bhn, dy4[2], dy4[3], live, g.part + 8, hi, lo);
+    mbar_wait(&bar->ta_done, n & 1);
+    if (tr) BTRACE(0, n, 5);
+    store_tile(hi, lo);
+  } else {
+    mbar_wait(&bar->ta_done, n & 1);
+    store_zero();
+  }
+  fence_async_smem();
+  mbar_arrive(&bar->tb_ready);
   if (tr) BTRACE(0, n, 6);
 }
 
@@ -274,11 +270,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   const int dir = blockIdx.y;
 
   if (tid == 0) {
-    for (int q = 0; q < 4; ++q) mbar_init(&bars.img_q[q], 1);
+    for (int q = 0; q < 2; ++q) mbar_init(&bars.img_q[q], 1);
     mbar_init(&bars.p1_full, 1);
-    mbar_init(&bars.t1_ready, RB_GATE_THREADS);
-    mbar_init(&bars.t1_done, 1);
-    mbar_init(&bars.t2_ready, RB_GATE_THREADS);
+    mbar_init(&bars.ta_ready, RB_GATE_THREADS);
+    mbar_init(&bars.ta_done, 1);
+    mbar_init(&bars.tb_ready, RB_GATE_THREADS);
     mbar_init(&bars.dh_full, 1);
     mbar_init(&bars.step_done, 1);
     mbar_init(&bars.dh_read, RB_GATE_THREADS);
@@ -347,7 +343,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
       const BwdSeg& sg = a.seg[cc.si];
       t = dir ? cc.s : (cc.Lj - 1 - cc.s);
       tp = dir ? t + 1 : t - 1;
-      return (size_t)sg.plan[3 * sg.n_tiles * RT_R + cc.tile];
+      return (size_t)cc.slab0;
     };
     auto images_of = [&](const Cur& cc, const unsigned char*& xsrc, const unsigned char*& hsrc) {
       const BwdSeg& sg = a.seg[cc.si];
@@ -356,18 +352,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
       xsrc = sg.xq + (slab0 + t) * RB_IMG;
       hsrc = (tp >= 0 && tp < cc.Lj) ? sg.hq + ((slab0 + tp) * 2 + dir) * RB_IMG : a.zero_img;
     };
-    // the step's two operand images as four TMA bulk copies (hi and lo halves land separately, in the order the recomputation
-    // consumes them)
+    // the step's two operand images, one TMA bulk copy each, landing on their own barriers (the x-part of the recomputation
+    // starts as soon as the token image is there)
     auto produce = [&](const unsigned char* xsrc, const unsigned char* hsrc) {
-      constexpr uint32_t HALF = RB_IMG / 2;
-      mbar_arrive_expect_tx_e(el, &bars.img_q[0], HALF);
-      bulk_copy_g2s_e(el, ximg, xsrc, HALF, &bars.img_q[0]);
-      mbar_arrive_expect_tx_e(el, &bars.img_q[1], HALF);
-      bulk_copy_g2s_e(el, ximg + HALF, xsrc + HALF, HALF, &bars.img_q[1]);
-      mbar_arrive_expect_tx_e(el, &bars.img_q[2], HALF);
-      bulk_copy_g2s_e(el, himg, hsrc, HALF, &bars.img_q[2]);
-      mbar_arrive_expect_tx_e(el, &bars.img_q[3], HALF);
-      bulk_copy_g2s_e(el, himg + HALF, hsrc + HALF, HALF, &bars.img_q[3]);
+      mbar_arrive_expect_tx_e(el, &bars.img_q[0], RB_IMG);
+      bulk_copy_g2s_e(el, ximg, xsrc, RB_IMG, &bars.img_q[0]);
+      mbar_arrive_expect_tx_e(el, &bars.img_q[1], RB_IMG);
+      bulk_copy_g2s_e(el, himg, hsrc, RB_IMG, &bars.img_q[1]);
     };
     Cur c;
     int qi = 0;
@@ -377,32 +368,18 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     if (c.active) { images_of(c, nx_x, nx_h); produce(nx_x, nx_h); }
     int n = 0;
     for (; c.active; ++n) {
-      Cur nx = c;
-      cur_next(a, nx);
-      if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
-      if (nx.active) {
-        // the next step's operand images: addresses resolved now (plan look-ups are global loads), pulled into L2 while this step
-        // computes, copied as soon as this step's MMAs have retired
-        images_of(nx, nx_x, nx_h);
-        bulk_prefetch_l2_e(el, nx_x, RB_IMG);
-        if (nx_h != a.zero_img) bulk_prefetch_l2_e(el, nx_h, RB_IMG);
-      }
       if (el) BTRACE(1, n, 0);
-      // ---- recomputation: the forward's MMAs (gru_rec_tc.cu), issued quarter by quarter as the images land
-      mbar_wait(&bars.img_q[0], n & 1);         // x hi
+      // ---- recomputation: the forward's MMAs (gru_rec_tc.cu)
+      mbar_wait(&bars.img_q[0], n & 1);         // token image
       tc_fence_after();
       if (el) BTRACE(1, n, 1);
       for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)
         const uint64_t o = (uint64_t)(kk * 2);
         umma_bf16_e(el, d_gates, x_h + o, wih_h + o, id192, kk != 0);
         umma_bf16_e(el, d_gates, x_h + o, wih_l + o, id192, 1);
-      }
-      mbar_wait(&bars.img_q[1], n & 1);         // x lo
-      for (int kk = 0; kk < a.kx; ++kk) {
-        const uint64_t o = (uint64_t)(kk * 2);
         umma_bf16_e(el, d_gates, x_l + o, wih_h + o, id192, 1);
       }
-      mbar_wait(&bars.img_q[2], n & 1);         // h hi
+      mbar_wait(&bars.img_q[1], n & 1);         // hidden image
       if (n > 0) mbar_wait(&bars.dh_read, (n - 1) & 1);      // the previous carry product has been folded in: its columns (= n_h) are free
       tc_fence_after();
       if (el) BTRACE(1, n, 2);
@@ -411,55 +388,50 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
         const uint64_t o = (uint64_t)(kk * 2);
         umma_bf16_e(el, d_gates, h_h + o, whh_h + o, id128, 1);
         umma_bf16_e(el, d_gates, h_h + o, whh_l + o, id128, 1);
+        umma_bf16_e(el, d_gates, h_l + o, whh_h + o, id128, 1);
         umma_bf16_e(el, d_gates + 192, h_h + o, whn_h + o, id64, kk != 0);
         umma_bf16_e(el, d_gates + 192, h_h + o, whn_l + o, id64, 1);
-      }
-      mbar_wait(&bars.img_q[3], n & 1);         // h lo
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint64_t o = (uint64_t)(kk * 2);
-        umma_bf16_e(el, d_gates, h_l + o, whh_h + o, id128, 1);
         umma_bf16_e(el, d_gates + 192, h_l + o, whn_h + o, id64, 1);
       }
       umma_commit_e(el, &bars.p1_full);
       if (el) BTRACE(1, n, 3);
-      // ---- pass 1: tile = [dr | dz]
-      mbar_wait(&bars.t1_ready, n & 1);
-      tc_fence_after();
-      if (el) BTRACE(1, n, 4);
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {          // carry, first 128 of K = 192: dh[128 x 64] = tile[128 x 128] · W_hh[r,z rows][128 x 64]
-        const uint64_t ao = (uint64_t)(((ks >> 2) * RB_BLK + (ks & 3) * 32) >> 4), bo = (uint64_t)((ks * 2048) >> 4);
-        umma_bf16_e(el, d_dh, ca_h + ao, cb_h + bo, id_carry, ks != 0);
-        umma_bf16_e(el, d_dh, ca_h + ao, cb_l + bo, id_carry, 1);
-        umma_bf16_e(el, d_dh, ca_l + ao, cb_h + bo, id_carry, 1);
+      // while the gate threads work: the next step's operand images - addresses resolved now (queue / plan look-ups are global
+      // loads), pulled into L2, copied as soon as this step's MMAs have retired
+      Cur nx = c;
+      cur_next(a, nx);
+      if (!nx.active && qi == 0) { qi = 1; cur_init(a, nx, 2 * blockIdx.x + 1); }
+      if (nx.active) {
+        images_of(nx, nx_x, nx_h);
+        bulk_prefetch_l2_e(el, nx_x, RB_IMG);
+        if (nx_h != a.zero_img) bulk_prefetch_l2_e(el, nx_h, RB_IMG);
       }
+      // ---- the two halves of the hidden units: tile = [dr | dz][dn*r | dn] of units 0..31, then of units 32..63
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 1) {
-          // ---- pass 2: tile = [dn*r | dn]
-          if (el) BTRACE(1, n, 5);
-          mbar_wait(&bars.t2_ready, n & 1);
-          tc_fence_after();
-          if (el) BTRACE(1, n, 6);
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1 && el) BTRACE(1, n, 5);
+        mbar_wait(half == 0 ? &bars.ta_ready : &bars.tb_ready, n & 1);
+        tc_fence_after();
+        if (el) BTRACE(1, n, half == 0 ? 4 : 6);
+        // carry: dh[128 x 64] (+)= tile[128 x 96: dr, dz, dn*r of this half] · W_hh[those 96 rows][64]; six k-steps of 16 gates
 #pragma unroll
-          for (int ks = 8; ks < 12; ++ks) {     // carry, last 64 of K: += tile block 0 (dn*r) · W_hh[n rows]
-            const uint64_t ao = (uint64_t)(((ks & 3) * 32) >> 4), bo = (uint64_t)((ks * 2048) >> 4);
-            umma_bf16_e(el, d_dh, ca_h + ao, cb_h + bo, id_carry, 1);
-            umma_bf16_e(el, d_dh, ca_h + ao, cb_l + bo, id_carry, 1);
-            umma_bf16_e(el, d_dh, ca_l + ao, cb_h + bo, id_carry, 1);
-          }
-          umma_commit_e(el, &bars.dh_full);
+        for (int ks = 0; ks < 6; ++ks) {
+          // k-step ks: gate type ks / 2 (dr, dz in block 0; dn*r in block 1), units 16 (ks % 2) .. +15 of the half
+          const uint64_t ao = (uint64_t)((((ks >> 2) * RB_BLK) + (ks & 3) * 32) >> 4);
+          const uint64_t bo = (uint64_t)((((ks >> 1) * 4 + half * 2 + (ks & 1)) * 2048) >> 4);      // W_hh rows 64 type + 32 half + 16 (ks % 2)
+          umma_bf16_e(el, d_dh, ca_h + ao, cb_h + bo, id_carry, (half | ks) != 0);
+          umma_bf16_e(el, d_dh, ca_h + ao, cb_l + bo, id_carry, 1);
+          umma_bf16_e(el, d_dh, ca_l + ao, cb_h + bo, id_carry, 1);
         }
+        if (half == 1) umma_commit_e(el, &bars.dh_full);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {        // dW^T[128 features][pass*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
+        for (int ks = 0; ks < 8; ++ks) {        // dW^T[128 features][half*128 + 128 gates] += [xq | hq]^T · tile, K = 128 sequences
           const uint64_t o = (uint64_t)((ks * 2048) >> 4);
           const uint32_t accf = (n | ks) != 0;
-          umma_bf16_e(el, d_w + pass * 128, wa_h + o, wb_h + o, id_wg, accf);
-          umma_bf16_e(el, d_w + pass * 128, wa_h + o, wb_l + o, id_wg, 1);
-          umma_bf16_e(el, d_w + pass * 128, wa_l + o, wb_h + o, id_wg, 1);
+          umma_bf16_e(el, d_w + half * 128, wa_h + o, wb_h + o, id_wg, accf);
+          umma_bf16_e(el, d_w + half * 128, wa_h + o, wb_l + o, id_wg, 1);
+          umma_bf16_e(el, d_w + half * 128, wa_l + o, wb_h + o, id_wg, 1);
         }
-        umma_commit_e(el, pass == 0 ? &bars.t1_done : &bars.step_done);
+        umma_commit_e(el, half == 0 ? &bars.ta_done : &bars.step_done);
       }
       if (nx.active) {
         mbar_wait(&bars.step_done, n & 1);      // every MMA that reads this step's images and tile has retired
@@ -473,8 +445,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   if (tid == 0) BTRACE(1, 63, 1);
-  // ---- flush dW^T: TMEM lane = feature (x features 0..63, hidden features 64..127), column = gate gradient
-  //      [0,64) dr | [64,128) dz | [128,192) dn*r | [192,256) dn, each scaled by 1 / (the resident weights' pre-scaling)
+  // ---- flush dW^T: TMEM lane = feature (x features 0..63, hidden features 64..127); column c: half = c / 128 (hidden units 0..31 |
+  //      32..63), gate type = (c % 128) / 32 (dr, dz, dn*r, dn), unit = 32 half + c % 32; scaled by 1 / (the weights' pre-scaling)
   const bool has_work = a.q_off[2 * blockIdx.x + 2] > a.q_off[2 * blockIdx.x];       // otherwise the accumulator was never written
   if (warp < RB_GATE_WARPS && has_work) {
     // warp w reads the lanes of quarter w % 4 (all a warp may touch) and the 64 columns of column group w / 4
@@ -488,23 +460,24 @@ __global__ void __launch_bounds__(RB_THREADS, 1) gru_bwd_tc_kernel(const __grid_
     for (int c0 = (warp >> 2) * 64; c0 < (warp >> 2) * 64 + 64; c0 += 32) {
       float v[32];
       tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 256 + c0, v);
-      const float sc = c0 < 2 * H ? RB_K_RZ : RB_K_N;
+      const int type = (c0 & 127) >> 5;          // one gate type per 32 columns
+      const float sc = type < 2 ? RB_K_RZ : RB_K_N;
+      const int ubase = (c0 >> 7) * 32;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int gc = c0 + i;                 // 0..255: dr, dz, dn*r, dn
+        const int u = ubase + i;
         const float val = v[i] * sc;
         if (f < KP) {
-          // token features: W_ih columns, the 1.0 column feeds the biases
-          const int grow = gc < 2 * H ? gc : gc - H;                   // dr -> u, dz -> 64+u, dn -> 128+u
-          if (gc < 2 * H || gc >= G3) {
+          // token features: W_ih columns, the 1.0 column feeds the biases.  dr -> row u, dz -> 64 + u, dn -> 128 + u
+          if (type != 2) {
+            const int grow = (type == 3 ? 2 : type) * H + u;
             if (f < E) atomicAdd(&dw_ih[grow * E + f], val);
-            else if (f == E) { atomicAdd(&db_ih[grow], val); if (gc < 2 * H) atomicAdd(&db_hh[grow], val); }
+            else if (f == E) { atomicAdd(&db_ih[grow], val); if (type < 2) atomicAdd(&db_hh[grow], val); }
           } else if (f == E) {
-            atomicAdd(&db_hh[gc], val);        // dn*r column 128+u -> b_hn at index 128 + u
+            atomicAdd(&db_hh[2 * H + u], val);   // dn*r -> b_hn
           }
-        } else {
-          const int j = f - KP;                // hidden features: W_hh columns
-          if (gc < G3) atomicAdd(&dw_hh[gc * H + j], val);             // dr, dz, dn*r -> rows u, 64+u, 128+u
+        } else if (type != 3) {
+          atomicAdd(&dw_hh[(type * H + u) * H + (f - KP)], val);       // hidden features: W_hh columns; dr, dz, dn*r -> rows u, 64+u, 128+u
         }
       }
     }

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
     auto load_x = [&]() {       // the token image is already bf16 hi|lo, SWIZZLE_128B (gather_pack_tc_kernel): 32 KB land as they are
       const RecSeg& sg = a.seg[c.si];
       const int t = dir ? (c.Lj - 1 - c.s) : c.s;
-      const int slab = sg.plan[3 * sg.n_tiles * RT_R + c.tile] + t;
+      const int slab = c.slab0 + t;
       mbar_arrive_expect_tx_e(el, &x_full[X], RT_A_BYTES);
       bulk_copy_g2s_e(el, xbuf, sg.xq + (size_t)slab * RT_A_BYTES, RT_A_BYTES, &x_full[X]);
     };
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) gru_fwd_tc_kernel(const __grid_
         // step's MMAs, the h_prev of the GRU cell's backward and the token-major operand of the weight-gradient MMA
         const RecSeg& sg = a.seg[c.si];
         const int tprev = dir ? (c.Lj - c.s) : (c.s - 1);
-        const size_t slab = (size_t)sg.plan[3 * sg.n_tiles * RT_R + c.tile] + tprev;
+        const size_t slab = (size_t)c.slab0 + tprev;
         bulk_copy_s2g_e(el, sg.hq + (slab * 2 + dir) * RT_A_BYTES, hs + X * RT_A_BYTES, RT_A_BYTES);
       }
       for (int kk = 0; kk < a.kx; ++kk) {       // x_t · W_ih^T  -> r, z, n_x  (overwrites)

@@ -13,7 +13,8 @@ constexpr int RT_MAX_SEG = 3;      // ImprovedRnn calls (review sides) per launc
 // one slot's position in its tile queue; every warp role walks the same deterministic sequence
 struct Cur {
   int q, qend, s, Lj, tile, si;
-  bool active;
+  int slab0;          // first slab of the tile (tile_off[tile]): looked up once per tile - a global load per step would sit on the
+  bool active;        // critical path of the drivers
 };
 template <class Args> __device__ __forceinline__ void cur_tile(const Args& a, Cur& c) {
   const int g = a.q_tile[c.q];
@@ -23,12 +24,13 @@ template <class Args> __device__ __forceinline__ void cur_tile(const Args& a, Cu
   c.si = si;
   c.tile = g - a.seg[si].tile_base;
   c.Lj = a.seg[si].plan[2 * a.seg[si].n_tiles * RT_R + c.tile * RT_R];    // len_of[tile*R]: the tile's longest job
+  c.slab0 = a.seg[si].plan[3 * a.seg[si].n_tiles * RT_R + c.tile];         // tile_off[tile]
   c.s = 0;
 }
 template <class Args> __device__ __forceinline__ void cur_init(const Args& a, Cur& c, int qi) {
   c.q = a.q_off[qi]; c.qend = a.q_off[qi + 1];
   c.active = c.q < c.qend;
-  c.s = 0; c.Lj = 0; c.tile = 0; c.si = 0;
+  c.s = 0; c.Lj = 0; c.tile = 0; c.si = 0; c.slab0 = 0;
   if (c.active) cur_tile(a, c);
 }
 template <class Args> __device__ __forceinline__ void cur_next(const Args& a, Cur& c) {
