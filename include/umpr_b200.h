@@ -266,6 +266,45 @@ int umpr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                                                the number of replicas that received a chunk (DataParallel's loss.mean(), main.py:34) */,
                    void* stream);
 
+/* ---- the whole step as ONE call (model.py:257-278 forward; with train != 0 also its backward, main.py:36): the same kernels as
+ * above, issued from native host code out of one caller-owned workspace - no per-kernel host round trips.  Tensor-core path only:
+ * every side needs a pack plan with R = 128 and its valid-row tables (plan.py: snet_table / cnet_table), L <= 126 for the full
+ * model (<= 128 review-net only), at most 512 valid positions per sample.  Parameter gradients are accumulated (+=) into g_*:
+ * the caller zeroes its bucket before the call and all-reduces / applies it afterwards (umpr_allreduce, umpr_adam_step). ---- */
+typedef struct umpr_step_side {        /* one review side: user, item, user->item (dataset.py:173-182) */
+  const int64_t* ids;                  /* (B, S, L) token ids */
+  const int32_t* plan;                 /* pack plan, R = 128 */
+  const int32_t* snet_table;           /* [tile_sent_off (snet_tiles+1) | cstart (B*S+1)] */
+  const int32_t* cnet_table;           /* [tile_sent_off (cnet_tiles+1) | cstart (B*S+1)], full model only */
+  int32_t snet_tiles, cnet_tiles, n_tiles, n_slabs, B, S, L, pv_max /* most valid positions of any sample */;
+} umpr_step_side;
+typedef struct umpr_step_model {
+  int32_t review_net_only, V, Pc, F /* photo feature width */, KC, ksize, E, reserved;
+  float threshold, loss_v_rate, eq18_eps, reserved_f;
+  const float* table;                  /* embedding.weight (rows, E), frozen */
+  /* parameters, reference state_dict order; GRU tensors in nn.GRU order (see umpr_gru_fwd_tc) */
+  const float* rnet_gru[8]; const float* M; const float* snet_u_Ms; const float* snet_u_Ws; const float* snet_i_Ms; const float* snet_i_Ws;
+  const float* lin_u; const float* lin_i; const float* fus_w; const float* fus_b;
+  const float* cnet_gru[8]; const float* conv_w; const float* conv_b; const float* clin_w; const float* clin_b;
+  const float* csnet_Ms; const float* csnet_Ws; const float* ss_w; const float* ss_b;
+  const float* pos_e; const float* neg_e; const float* vis_w; const float* vis_b;
+  /* their gradients (+=), same order; unused for train == 0 */
+  float* g_rnet_gru[8]; float* g_M; float* g_snet_u_Ms; float* g_snet_u_Ws; float* g_snet_i_Ms; float* g_snet_i_Ws;
+  float* g_lin_u; float* g_lin_i; float* g_fus_w; float* g_fus_b;
+  float* g_cnet_gru[8]; float* g_conv_w; float* g_conv_b; float* g_clin_w; float* g_clin_b;
+  float* g_csnet_Ms; float* g_csnet_Ws; float* g_ss_w; float* g_ss_b;
+  float* g_pos_e; float* g_neg_e; float* g_vis_w; float* g_vis_b;
+  /* optional taps (tests): the arg-max positions the kernels chose - co-attention (2, B, P), max-pool (B*S, KC) of ui / user / item */
+  int32_t* routing_coattn; int32_t* routing_cnet[3];
+} umpr_step_model;
+int umpr_step_workspace_bytes(const umpr_step_model* model, const umpr_step_side* sides /* 2 (review net only) or 3: user, item, ui */,
+                              int train, long long* bytes);
+int umpr_step(const umpr_step_model* model, const umpr_step_side* sides, const float* photos /* (B,V,Pc,F) features or NULL */,
+              const float* labels /* (B) */, const int32_t* sched_r, int nq_r /* tile schedule of the user+item GRU launch */,
+              const int32_t* sched_c, int nq_c /* ... of the ui+user+item launch (full model) */, const void* zero_img /* 32 KB of zeros */,
+              void* workspace /* 256-byte aligned */, long long workspace_bytes, float* pred /* (B) */, float* loss /* scalar */,
+              int train, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,33 +51,44 @@ def _record(name, payload):
         pass
 
 
-def _run_model(workload, batch, m_scale, seed, vocab=30000):
+def _run_model(workload, batch, m_scale, seed, vocab=30000, native=False):
+    """One forward + backward of the CUDA path: through the autograd Functions (``model(*batch)``; ``loss.backward()``), or - ``native`` -
+    through the one-call native step (csrc/step.cu) exactly as ``FlatTrainer.train_step`` and bench.py run it."""
     from umpr_b200 import functional as F
     from umpr_b200 import synthetic as syn
+    from umpr_b200.train import FlatTrainer
     table = syn.make_table(vocab, seed=2)
     batch_t = syn.make_batch(workload, batch, vocab=vocab, seed=seed)
     model = syn.build_model(workload, table, seed=1, device=DEV)
     with torch.no_grad():
         model.review_net.r_net.M.mul_(m_scale)
     model.train()
-    F.ROUTING_LOG = []
-    try:
-        pred, loss = model(*batch_t)
-        log = F.ROUTING_LOG
-    finally:
-        F.ROUTING_LOG = None
-    loss.backward()
+    log = []
+    if native:
+        tr = FlatTrainer(model)
+        tr.zero_grad()
+        plans = tr.native.plans_of(batch_t, torch.device(DEV))
+        assert tr.native.supported(batch_t, plans)
+        pred, loss = tr.native.run(batch_t, True, plans, routing_log=log)
+    else:
+        F.ROUTING_LOG = log
+        try:
+            pred, loss = model(*batch_t)
+        finally:
+            F.ROUTING_LOG = None
+        loss.backward()
     picks = {"coattn": [(a[0].cpu(), a[1].cpu()) for k, a in log if k == "coattn"], "cnet": [a.cpu() for k, a in log if k == "cnet"]}
     params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu() for k, p in model.named_parameters() if p.requires_grad}
     return model, batch_t, picks, params, pred.detach().cpu(), loss.detach().cpu(), grads
 
 
-@pytest.mark.parametrize("workload,batch,m_scale,masked", [("music_full", 1024, 1.0, False), ("yelp_full", 256, 0.05, True),
-                                                           ("csj_long", 256, 0.05, True), ("music_small_r", 512, 0.05, False)])
-def test_benchmarked_configurations_vs_oracle(workload, batch, m_scale, masked):
+@pytest.mark.parametrize("workload,batch,m_scale,masked,native", [("music_full", 1024, 1.0, False, True), ("yelp_full", 256, 0.05, True, True),
+                                                                  ("csj_long", 256, 0.05, True, True), ("music_small_r", 512, 0.05, False, True),
+                                                                  ("music_full", 512, 0.05, False, False)])
+def test_benchmarked_configurations_vs_oracle(workload, batch, m_scale, masked, native):
     from umpr_b200 import synthetic as syn
-    model, batch_t, picks, params, pred, loss, grads = _run_model(workload, batch, m_scale, seed=5)
+    model, batch_t, picks, params, pred, loss, grads = _run_model(workload, batch, m_scale, seed=5, native=native)
     rno = syn.WORKLOADS[workload]["review_net_only"]
     kw = dict(review_net_only=rno, impl="lib")
     with orc.routed(picks) as r:
@@ -119,7 +130,7 @@ def test_benchmarked_configurations_vs_oracle(workload, batch, m_scale, masked):
                 worst = max(worst, e)
                 assert e <= TOL, f"masked routing comparison, grad {k}: {e:.3e}"
         stats["masked_worst_rel_err"] = worst
-    _record(f"{workload}_b{batch}_m{m_scale}", stats)
+    _record(f"{workload}_b{batch}_m{m_scale}_{'native' if native else 'autograd'}", stats)
 
 
 def _weights(E, seed):
@@ -209,3 +220,66 @@ def test_eval_forward_on_skewed_lengths_vs_oracle(workload, B, L):
     mse = evaluate_mse(model, [tuple(batch), tuple(batch)])
     want = float(((p_ref - batch[7]) ** 2).sum()) / B
     assert abs(mse - want) <= TOL * max(1.0, want), (mse, want)
+
+
+@pytest.mark.parametrize("workload,B", [("music_full", 64), ("music_small_r", 40), ("yelp_full", 33)])
+def test_native_step_equals_the_autograd_path(workload, B):
+    """csrc/step.cu issues the same kernels as functional.py: prediction, loss and every parameter gradient agree to float-atomics noise
+    (reference default batch 64 included: 1280 sentences per side, 320 user->item sentences - all on the tensor-core path)."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.train import FlatTrainer
+    table = syn.make_table(3000, seed=2)
+    batch = syn.make_batch(workload, B, vocab=3000, seed=9)
+    res = []
+    for native in (False, True):
+        model = syn.build_model(workload, table, seed=1, device=DEV)
+        with torch.no_grad():
+            model.review_net.r_net.M.mul_(0.05)
+        tr = FlatTrainer(model, native=native)
+        tr.zero_grad()
+        if native:
+            plans = tr.native.plans_of(batch, torch.device(DEV))
+            assert tr.native.supported(batch, plans)
+            pred, loss = tr.native.run(batch, True, plans)
+        else:
+            assert tr.native is None
+            pred, loss = model(*batch)
+            loss.backward()
+        res.append((pred.detach().clone(), loss.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}))
+    assert_close(res[1][0], res[0][0], 1e-6, "prediction")
+    assert_close(res[1][1], res[0][1], 1e-6, "loss")
+    for k, g in res[0][2].items():
+        if float(g.abs().max()) > 1e-7:
+            assert_close(res[1][2][k], g, 5e-6, "grad " + k)
+    # and the evaluation forward (no_grad -> native) equals the autograd-path forward
+    model.eval()
+    with torch.no_grad():
+        pe, le = model(*batch)
+    from umpr_b200 import model as M
+    M.NATIVE_EVAL = False
+    try:
+        with torch.no_grad():
+            pa, la = model(*batch)
+    finally:
+        M.NATIVE_EVAL = True
+    assert_close(pe, pa, 1e-6, "eval prediction")
+    assert_close(le, la, 1e-6, "eval loss")
+
+
+def test_flat_trainer_steps_through_the_native_path():
+    """FlatTrainer.train_step on the standard model: the native one-call path is what runs, and a few steps of it move the parameters
+    exactly as the autograd path does."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.train import FlatTrainer, PlanPrefetcher
+    table = syn.make_table(3000, seed=2)
+    batches = [syn.make_batch("music_full", 64, vocab=3000, seed=20 + i) for i in range(3)]
+    flats = []
+    for native in (True, False):
+        model = syn.build_model("music_full", table, seed=1, device=DEV)
+        tr = FlatTrainer(model, lr=1e-3, native=native)
+        for b in PlanPrefetcher(iter(batches), torch.device(DEV)):
+            tr.train_step(b)
+        assert tr.native_steps == (3 if native else 0)
+        flats.append(tr.flat.clone())
+    err = float((flats[0] - flats[1]).abs().max() / flats[1].abs().max())
+    assert err < 2e-5, err

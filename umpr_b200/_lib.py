@@ -70,6 +70,8 @@ SIGNATURES = {
     "umpr_loss_bwd": [P, P, P, P, P, P, P, I, I, F, P, P, P, P, P, P],
     "umpr_tanh_bwd": [P, P, L, P, P],
     "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
+    "umpr_step_workspace_bytes": [P, P, I, P],
+    "umpr_step": [P, P, P, P, P, I, P, I, P, P, C.c_longlong, P, P, I, P],
     "umpr_ssnet_fwd": [P, P, P, L, P, P],
     "umpr_ssnet_bwd": [P, P, P, P, L, P, P, P, P],
 }
@@ -86,6 +88,25 @@ class GruBwdSeg(C.Structure):
     """``umpr_gru_bwd_seg`` of include/umpr_b200.h."""
     _fields_ = [("d_out", P), ("d_hn", P), ("xq", P), ("hq", P), ("plan", P), ("n_tiles", C.c_int32),
                 ("n_slabs", C.c_int32), ("N", C.c_int32), ("L", C.c_int32)]
+
+
+class StepSide(C.Structure):
+    """``umpr_step_side`` of include/umpr_b200.h."""
+    _fields_ = [("ids", P), ("plan", P), ("snet_table", P), ("cnet_table", P), ("snet_tiles", C.c_int32), ("cnet_tiles", C.c_int32),
+                ("n_tiles", C.c_int32), ("n_slabs", C.c_int32), ("B", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("pv_max", C.c_int32)]
+
+
+STEP_PARAMS = ["rnet_gru", "M", "snet_u_Ms", "snet_u_Ws", "snet_i_Ms", "snet_i_Ws", "lin_u", "lin_i", "fus_w", "fus_b",
+               "cnet_gru", "conv_w", "conv_b", "clin_w", "clin_b", "csnet_Ms", "csnet_Ws", "ss_w", "ss_b", "pos_e", "neg_e", "vis_w", "vis_b"]
+
+
+class StepModel(C.Structure):
+    """``umpr_step_model`` of include/umpr_b200.h (parameter pointers, then gradient pointers in the same order)."""
+    _fields_ = ([("review_net_only", C.c_int32), ("V", C.c_int32), ("Pc", C.c_int32), ("F", C.c_int32), ("KC", C.c_int32), ("ksize", C.c_int32),
+                 ("E", C.c_int32), ("reserved", C.c_int32), ("threshold", F), ("loss_v_rate", F), ("eq18_eps", F), ("reserved_f", F), ("table", P)]
+                + [(n, P * 8 if n.endswith("_gru") else P) for n in STEP_PARAMS]
+                + [("g_" + n, P * 8 if n.endswith("_gru") else P) for n in STEP_PARAMS]
+                + [("routing_coattn", P), ("routing_cnet", P * 3)])
 
 
 _lib = None

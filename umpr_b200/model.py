@@ -15,6 +15,7 @@ from . import functional as F
 from .plan import PackPlan
 
 EQ18_EPS = 1e-4   # model.py:188 (the code, not the readme's 1e-6, is the oracle)
+NATIVE_EVAL = True  # UMPR.forward under no_grad goes through the one-call native step (csrc/step.cu) when the batch fits its envelope
 
 
 def _on(device):
@@ -305,7 +306,28 @@ class UMPR(nn.Module):
         with _on(device):
             return self._forward(table, device, user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels)
 
+    def _native_eval(self):
+        """``umpr_step`` bound to this model for forward-only use (evaluate.py:8-11); rebuilt when the parameters have moved."""
+        from .step import NativeStep
+        st = getattr(self, "_eval_step", None)
+        if st is not None:
+            try:
+                st.check_addresses()
+            except RuntimeError:
+                st = None
+        if st is None:
+            st = NativeStep(self, with_grads=False)
+            object.__setattr__(self, "_eval_step", st)
+        return st
+
     def _forward(self, table, device, user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels):
+        if not torch.is_grad_enabled() and NATIVE_EVAL:
+            # no autograd tape wanted: the whole forward as one native call when the batch lies inside that path's envelope
+            st = self._native_eval()
+            batch = (user_reviews, item_reviews, ui_reviews, u_lengths, i_lengths, ui_lengths, photos, labels)
+            plans = st.plans_of(batch, device)
+            if st.supported(batch, plans):
+                return st.run(batch, False, plans, routing_log=F.ROUTING_LOG)
         to = lambda v: v.to(device, non_blocking=True)
         user_reviews, item_reviews = to(user_reviews), to(item_reviews)
         labels = to(labels)

@@ -53,7 +53,8 @@ class AbiComm:
 
 
 class FlatTrainer:
-    def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None, comm=None):
+    def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None, comm=None,
+                 native=True):
         """``comm``: "torch" = ``torch.distributed.all_reduce`` on ``process_group`` (default), "abi" = the library's own NCCL
         communicator (``umpr_comm_init`` / ``umpr_allreduce``, include/umpr_b200.h), bootstrapped by broadcasting the NCCL unique
         id through ``torch.distributed``; default from ``UMPR_COMM``."""
@@ -87,12 +88,21 @@ class FlatTrainer:
         self._grad_ptrs = [(n, p, p.grad.data_ptr()) for n, p in named]
         self.lr, self.betas, self.eps, self.lr_decay = lr, betas, eps, lr_decay
         self.step_no = 0
+        self.native_steps = 0          # steps taken through the native one-call path
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.comm = None
         import os
         if (comm or os.environ.get("UMPR_COMM", "torch")) == "abi" and self.world > 1 and self.flat.is_cuda:
             self.comm = AbiComm(dist.get_rank(process_group), self.world, dev, process_group)
+        # the whole forward + backward as one native call (csrc/step.cu) whenever the model is the standard UMPR on a CUDA device
+        # and the batch lies inside that path's envelope; the autograd path (functional.py) is the general fallback
+        self.native = None
+        if native and self.flat.is_cuda and os.environ.get("UMPR_NATIVE_STEP", "1") == "1":
+            from .model import UMPR
+            from .step import NativeStep
+            if isinstance(model, UMPR):
+                self.native = NativeStep(model, with_grads=True)
 
     def zero_grad(self):
         self.bucket.zero_()
@@ -135,12 +145,19 @@ class FlatTrainer:
         pred = loss = None
         if batch is not None:
             self.check_bucket()
-            pred, loss = self.model(*batch)
-            F.DIRECT_GRAD_ACCUM = True      # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
-            try:
-                (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
-            finally:
-                F.DIRECT_GRAD_ACCUM = False
+            plans = self.native.plans_of(batch, self.flat.device) if self.native is not None else None
+            if plans is not None and self.native.supported(batch, plans):
+                # one C-ABI call: forward, backward, gradients accumulated into the flat bucket
+                with torch.cuda.device(self.flat.device):
+                    pred, loss = self.native.run(batch, True, plans, routing_log=F.ROUTING_LOG)
+                self.native_steps += 1
+            else:
+                pred, loss = self.model(*batch)
+                F.DIRECT_GRAD_ACCUM = True      # the kernels accumulate parameter gradients straight into the flat bucket (functional._sinks)
+                try:
+                    (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
+                finally:
+                    F.DIRECT_GRAD_ACCUM = False
             if self.world > 1:
                 self.shard_count.fill_(1.0)
         self.reduce_gradients()
