@@ -14,7 +14,7 @@ from . import _lib
 TILE_ROWS = (32, 64, 128)
 
 
-TC_MIN_SEQS = 256      # from this many sequences on (two full tiles), a call runs on the fused tensor-core GRU kernel (tiles of 128):
+TC_MIN_SEQS = 128      # from this many sequences on (one full tile), a call runs on the fused tensor-core GRU kernel (tiles of 128):
                        # the reference default batch_size=64 (1280 sentences per side, 320 user->item sentences) is on tcgen05
 
 
