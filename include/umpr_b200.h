@@ -305,6 +305,11 @@ int umpr_step(const umpr_step_model* model, const umpr_step_side* sides, const f
               void* workspace /* 256-byte aligned */, long long workspace_bytes, float* pred /* (B) */, float* loss /* scalar */,
               int train, void* stream);
 
+/* optional timing of the entry points inside the following umpr_step calls (CUDA-event pairs on the launching stream): all of them
+ * (only == NULL) or just the named one.  _end synchronises and returns the totals aggregated by entry-point name. */
+int umpr_step_profile_begin(const char* only);
+int umpr_step_profile_end(int max_entries, char* names /* max_entries x 48 bytes */, float* ms, int* calls, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

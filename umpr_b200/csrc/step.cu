@@ -9,10 +9,40 @@
 // Parameter gradients are ACCUMULATED into the caller's gradient bucket (zeroed by the caller, all-reduced and consumed by
 // umpr_adam_step afterwards), exactly as functional._sinks does under FlatTrainer.
 #include <string.h>
+#include <string>
+#include <vector>
 #include "common.cuh"
 #include "../../include/umpr_b200.h"
 
 namespace umpr {
+
+// ---- optional per-entry-point timing (bench.py's kernel table and roofline): CUDA-event pairs on the launching stream around the
+// entry points of one umpr_step call - all of them, or only the one named in umpr_step_profile_begin.  Off by default: no events.
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+struct Profiler {
+  bool on = false;
+  std::string only;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t event() {
+    if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+    return pool[used++];
+  }
+};
+static Profiler g_prof;
+struct ProfScope {
+  cudaEvent_t e1 = nullptr;
+  cudaStream_t st;
+  ProfScope(const char* name, cudaStream_t s) : st(s) {
+    if (!g_prof.on || (!g_prof.only.empty() && g_prof.only != name)) return;
+    ProfRec r{name, g_prof.event(), g_prof.event()};
+    cudaEventRecord(r.e0, st);
+    e1 = r.e1;
+    g_prof.recs.push_back(r);
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
+};
 
 struct Arena {
   unsigned char* base;
@@ -26,6 +56,7 @@ struct Arena {
 };
 
 #define UMPR_TRY(call) do { if (int rc_ = (call)) return rc_; } while (0)
+#define STEP_CALL(name, call) do { ProfScope ps_(name, st); if (int rc_ = (call)) return rc_; } while (0)
 
 __global__ void expand_rows_kernel(const float* __restrict__ src, long n_rows, int L, float* __restrict__ dst) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,31 +178,31 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
 
   // ------------------------------------------------------------------------------------------------ forward
   for (int k = 0; k < n_sides; ++k)          // model.py:262-264 fused into the pack half of model.py:18
-    UMPR_TRY(umpr_gather_pack_tc(m.table, sd[k].ids, nullptr, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].L, E, sb[k].xq, stream));
+    STEP_CALL("umpr_gather_pack_tc", umpr_gather_pack_tc(m.table, sd[k].ids, nullptr, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].L, E, sb[k].xq, stream));
   {                                          // R-Net's GRU over user + item, one launch (model.py:45-46)
     umpr_gru_seg segs[2];
     for (int k = 0; k < 2; ++k)
       segs[k] = umpr_gru_seg{sb[k].xq, sd[k].plan, sb[k].out_r, nullptr, sb[k].hq_r, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
-    UMPR_TRY(umpr_gru_fwd_tc(segs, 2, m.rnet_gru, E, sched_r, nq_r, stream));
+    STEP_CALL("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 2, m.rnet_gru, E, sched_r, nq_r, stream));
   }
   const float* gu = sb[0].out_r, *gi = sb[1].out_r;
   // co-attention (model.py:50-55): giM = gi · M over the valid rows, flash-style affinity on tcgen05
   if (BP >= 1024)
-    UMPR_TRY(umpr_tc_gemm_ws(gi, Dm, m.M, Dm, giM, Dm, (int)BP, Dm, Dm, 0, nullptr, 0, 1, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
+    STEP_CALL("umpr_tc_gemm_ws", umpr_tc_gemm_ws(gi, Dm, m.M, Dm, giM, Dm, (int)BP, Dm, Dm, 0, nullptr, 0, 1, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
   else
-    UMPR_TRY(umpr_tc_gemm_nt(gi, Dm, m.M, Dm, giM, Dm, (int)BP, Dm, Dm, 0, nullptr, 0, 1, stream));
+    STEP_CALL("umpr_tc_gemm_nt", umpr_tc_gemm_nt(gi, Dm, m.M, Dm, giM, Dm, (int)BP, Dm, Dm, 0, nullptr, 0, 1, stream));
   const int32_t* cst_u = sd[0].snet_table + sd[0].snet_tiles + 1, *cst_i = sd[1].snet_table + sd[1].snet_tiles + 1;
   const int pv_max = sd[0].pv_max > sd[1].pv_max ? sd[0].pv_max : sd[1].pv_max;
-  UMPR_TRY(umpr_coattn_fwd_tc(gu, gi, giM, B, P, cst_u, sd[0].S, sd[0].L, cst_i, sd[1].S, sd[1].L, pv_max, co_scratch, soft, soft + BP,
+  STEP_CALL("umpr_coattn_fwd_tc", umpr_coattn_fwd_tc(gu, gi, giM, B, P, cst_u, sd[0].S, sd[0].L, cst_i, sd[1].S, sd[1].L, pv_max, co_scratch, soft, soft + BP,
                               soft + 2 * BP, soft + 3 * BP, arg, arg + BP, atte, atte + (size_t)B * Dm, stream));
   if (m.routing_coattn) cudaMemcpyAsync(m.routing_coattn, arg, 2 * BP * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
   for (int k = 0; k < 2; ++k) {              // S-Net of each side (model.py:162-163)
     const float* Ms = k ? m.snet_i_Ms : m.snet_u_Ms, *Ws = k ? m.snet_i_Ws : m.snet_u_Ws;
     const int N = sd[k].B * sd[k].S;
-    UMPR_TRY(umpr_snet_fwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, Ms, Ws, N, sd[k].L, sb[k].self_atte, n_ctas, stream));
-    UMPR_TRY(umpr_snet_sentiment_fwd(sb[k].self_atte, soft + k * BP, B, sd[k].S, sd[k].L, sb[k].wsum, sb[k].senti, stream));
+    STEP_CALL("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, Ms, Ws, N, sd[k].L, sb[k].self_atte, n_ctas, stream));
+    STEP_CALL("umpr_snet_sentiment_fwd", umpr_snet_sentiment_fwd(sb[k].self_atte, soft + k * BP, B, sd[k].S, sd[k].L, sb[k].wsum, sb[k].senti, stream));
   }
-  UMPR_TRY(umpr_text_match_fwd(atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, m.lin_u, m.lin_i, B, repr, stream));      // model.py:166-168
+  STEP_CALL("umpr_text_match_fwd", umpr_text_match_fwd(atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, m.lin_u, m.lin_i, B, repr, stream));      // model.py:166-168
   const float* pp = nullptr, *pn = nullptr, *pm = nullptr, *nm = nullptr, *fpos = nullptr, *fneg = nullptr;
   if (full) {
     {                                        // C-Net's GRU over ui + user + item, one launch (model.py:182-184)
@@ -181,53 +212,53 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
         const int k = order[j];
         segs[j] = umpr_gru_seg{sb[k].xq, sd[k].plan, sb[k].out_c, nullptr, sb[k].hq_c, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
       }
-      UMPR_TRY(umpr_gru_fwd_tc(segs, 3, m.cnet_gru, E, sched_c, nq_c, stream));
+      STEP_CALL("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 3, m.cnet_gru, E, sched_c, nq_c, stream));
     }
     for (int k = 0; k < 3; ++k) {            // conv + ReLU + max-pool + view head (model.py:118-125)
       const int N = sd[k].B * sd[k].S;
-      UMPR_TRY(umpr_cnet_conv_fwd_tc(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
+      STEP_CALL("umpr_cnet_conv_fwd_tc", umpr_cnet_conv_fwd_tc(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
                                      sb[k].cfeat, sb[k].cidx, n_ctas, stream));
-      UMPR_TRY(umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, stream));
+      STEP_CALL("umpr_cnet_head_fwd", umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, stream));
       if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     }
     // ControlNet tail (model.py:185-197): S-Net on the user->item review (its `sentiment` output is unused), SSNet + Eq.18 + gates
-    UMPR_TRY(umpr_snet_fwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, s_ui, n_ctas, stream));
-    UMPR_TRY(umpr_control_tail_fwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, m.ss_b, m.eq18_eps, B, sd[2].S, V, senti_ss, ct_out, ct_out + (size_t)B * V,
+    STEP_CALL("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, s_ui, n_ctas, stream));
+    STEP_CALL("umpr_control_tail_fwd", umpr_control_tail_fwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, m.ss_b, m.eq18_eps, B, sd[2].S, V, senti_ss, ct_out, ct_out + (size_t)B * V,
                                    ct_out + 2 * (size_t)B * V, stream));
     // VisualNet tail (model.py:219-228)
-    UMPR_TRY(umpr_visual_fwd(photos, m.pos_e, m.neg_e, m.vis_w, m.vis_b, sb[0].fin, sb[1].fin, B, V, m.Pc, m.F, vis_emb, vis_out, vis_out + (size_t)B * V,
+    STEP_CALL("umpr_visual_fwd", umpr_visual_fwd(photos, m.pos_e, m.neg_e, m.vis_w, m.vis_b, sb[0].fin, sb[1].fin, B, V, m.Pc, m.F, vis_emb, vis_out, vis_out + (size_t)B * V,
                              vis_out + 2 * (size_t)B * V, vis_out + 3 * (size_t)B * V, vis_out + 4 * (size_t)B * V, stream));
     pp = ct_out + (size_t)B * V; pn = ct_out + 2 * (size_t)B * V;
     pm = vis_out + (size_t)B * V; nm = vis_out + 2 * (size_t)B * V;
     fpos = vis_out + 3 * (size_t)B * V; fneg = vis_out + 4 * (size_t)B * V;
   }
-  UMPR_TRY(umpr_fusion_fwd(repr, fpos, fneg, m.fus_w, m.fus_b, B, full ? V : 0, pred, stream));          // model.py:268,274
+  STEP_CALL("umpr_fusion_fwd", umpr_fusion_fwd(repr, fpos, fneg, m.fus_w, m.fus_b, B, full ? V : 0, pred, stream));          // model.py:268,274
   cudaMemsetAsync(loss, 0, sizeof(float), st);
-  UMPR_TRY(umpr_loss_fwd(pred, labels, pp, pn, pm, nm, B, full ? V : 0, m.loss_v_rate, loss, stream));   // model.py:269,275-277
+  STEP_CALL("umpr_loss_fwd", umpr_loss_fwd(pred, labels, pp, pn, pm, nm, B, full ? V : 0, m.loss_v_rate, loss, stream));   // model.py:269,275-277
   if (!train) return 0;
 
   // ------------------------------------------------------------------------------------------------ backward (main.py:36)
   set_scalar_kernel<<<1, 1, 0, st>>>(one, 1.0f);                                 // d(loss) = 1
-  UMPR_TRY(umpr_loss_bwd(pred, labels, pp, pn, pm, nm, one, B, full ? V : 0, m.loss_v_rate, d_pred, full ? g4 : nullptr, full ? g4 + (size_t)B * V : nullptr,
+  STEP_CALL("umpr_loss_bwd", umpr_loss_bwd(pred, labels, pp, pn, pm, nm, one, B, full ? V : 0, m.loss_v_rate, d_pred, full ? g4 : nullptr, full ? g4 + (size_t)B * V : nullptr,
                          full ? g4 + 2 * (size_t)B * V : nullptr, full ? g4 + 3 * (size_t)B * V : nullptr, stream));
-  UMPR_TRY(umpr_fusion_bwd(repr, fpos, fneg, m.fus_w, pred, d_pred, B, full ? V : 0, d_repr, full ? d_f : nullptr, full ? d_f + (size_t)B * V : nullptr,
+  STEP_CALL("umpr_fusion_bwd", umpr_fusion_bwd(repr, fpos, fneg, m.fus_w, pred, d_pred, B, full ? V : 0, d_repr, full ? d_f : nullptr, full ? d_f + (size_t)B * V : nullptr,
                            m.g_fus_w, m.g_fus_b, stream));
   if (full) {
-    UMPR_TRY(umpr_visual_bwd(photos, m.pos_e, m.neg_e, m.vis_w, vis_emb, vis_out, pm, nm, sb[0].fin, sb[1].fin, g4 + 2 * (size_t)B * V, g4 + 3 * (size_t)B * V,
+    STEP_CALL("umpr_visual_bwd", umpr_visual_bwd(photos, m.pos_e, m.neg_e, m.vis_w, vis_emb, vis_out, pm, nm, sb[0].fin, sb[1].fin, g4 + 2 * (size_t)B * V, g4 + 3 * (size_t)B * V,
                              d_f, d_f + (size_t)B * V, B, V, m.Pc, m.F, vis_scr, d_c, d_c + (size_t)B * V, m.g_pos_e, m.g_neg_e, m.g_vis_w, m.g_vis_b, stream));
-    UMPR_TRY(umpr_control_tail_bwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, senti_ss, ct_out, g4, g4 + (size_t)B * V, m.eq18_eps, B, sd[2].S, V, d_s, d_vp, d_co,
+    STEP_CALL("umpr_control_tail_bwd", umpr_control_tail_bwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, senti_ss, ct_out, g4, g4 + (size_t)B * V, m.eq18_eps, B, sd[2].S, V, d_s, d_vp, d_co,
                                    m.g_ss_w, m.g_ss_b, stream));
     // S-Net on the user->item review: only self_atte was used, so d(self_atte) = d_s as it is
-    UMPR_TRY(umpr_snet_bwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, d_s, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, dx_s_ui,
+    STEP_CALL("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, d_s, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, dx_s_ui,
                               m.g_csnet_Ms, m.g_csnet_Ws, n_ctas, stream));
     for (int k = 0; k < 3; ++k) {
       const int N = sd[k].B * sd[k].S;
       const float* d_view = k == 2 ? d_vp : nullptr;
       const float* d_fin = k == 2 ? d_co : d_c + (size_t)k * B * V;              // c_u, c_i feed the visual tail; c_net_out the control tail
-      UMPR_TRY(umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
+      STEP_CALL("umpr_cnet_head_bwd", umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
                                   m.g_conv_b, stream));
-      UMPR_TRY(umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch, sb[k].dx_c, n_ctas, stream));
-      UMPR_TRY(umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, stream));
+      STEP_CALL("umpr_cnet_conv_bwd_dx_tc", umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch, sb[k].dx_c, n_ctas, stream));
+      STEP_CALL("umpr_cnet_conv_bwd_dw_tc", umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, stream));
     }
     {                                        // the user->item GRU output feeds the convolution AND S-Net: sum of both gradients
       const long n4 = (long)(side_tokens_rows(sd[2]) * Dm / 4);
@@ -240,41 +271,41 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
       const int k = order[j];
       segs[j] = umpr_gru_bwd_seg{sb[k].dx_c, nullptr, sb[k].xq, sb[k].hq_c, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
     }
-    UMPR_TRY(umpr_gru_bwd_tc(segs, 3, m.cnet_gru, m.g_cnet_gru, E, zero_img, sched_c, nq_c, stream));
+    STEP_CALL("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 3, m.cnet_gru, m.g_cnet_gru, E, zero_img, sched_c, nq_c, stream));
   }
   // text matching (model.py:166-168)
-  UMPR_TRY(umpr_tanh_bwd(repr, d_repr, (long)B * Dm, dpre, stream));
-  UMPR_TRY(umpr_text_match_bwd(dpre, m.lin_u, m.lin_i, B, dins, dins + (size_t)B * Dm, dins + 2 * (size_t)B * Dm, dins + 3 * (size_t)B * Dm, stream));
-  UMPR_TRY(umpr_text_match_wgrad(dpre, atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, B, m.g_lin_u, m.g_lin_i, stream));
+  STEP_CALL("umpr_tanh_bwd", umpr_tanh_bwd(repr, d_repr, (long)B * Dm, dpre, stream));
+  STEP_CALL("umpr_text_match_bwd", umpr_text_match_bwd(dpre, m.lin_u, m.lin_i, B, dins, dins + (size_t)B * Dm, dins + 2 * (size_t)B * Dm, dins + 3 * (size_t)B * Dm, stream));
+  STEP_CALL("umpr_text_match_wgrad", umpr_text_match_wgrad(dpre, atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, B, m.g_lin_u, m.g_lin_i, stream));
   for (int k = 0; k < 2; ++k) {              // S-Net of each side; its input gradient is handed to the co-attention backward (add_u / add_i)
     const float* Ms = k ? m.snet_i_Ms : m.snet_u_Ms, *Ws = k ? m.snet_i_Ws : m.snet_u_Ws;
     float* gMs = k ? m.g_snet_i_Ms : m.g_snet_u_Ms, *gWs = k ? m.g_snet_i_Ws : m.g_snet_u_Ws;
     const int N = sd[k].B * sd[k].S;
-    UMPR_TRY(umpr_snet_sentiment_bwd(sb[k].self_atte, sb[k].wsum, dins + (size_t)(2 * k + 1) * B * Dm, nullptr, B, sd[k].S, sb[k].d_sa, sb[k].d_wsum, stream));
-    UMPR_TRY(umpr_snet_bwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, sb[k].d_sa, Ms, Ws, N, sd[k].L, sb[k].dx_s, gMs, gWs, n_ctas, stream));
+    STEP_CALL("umpr_snet_sentiment_bwd", umpr_snet_sentiment_bwd(sb[k].self_atte, sb[k].wsum, dins + (size_t)(2 * k + 1) * B * Dm, nullptr, B, sd[k].S, sb[k].d_sa, sb[k].d_wsum, stream));
+    STEP_CALL("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, sb[k].d_sa, Ms, Ws, N, sd[k].L, sb[k].dx_s, gMs, gWs, n_ctas, stream));
     const long n = (long)N * sd[k].L;        // d(word_soft)[n][l] = d(sum_l word_soft)[n]  (model.py:79)
     expand_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sb[k].d_wsum, N, sd[k].L, sb[k].d_soft);
     UMPR_TRY(check_launch("step expand"));
   }
-  UMPR_TRY(umpr_coattn_bwd(gu, gi, giM, soft, soft + BP, soft + 2 * BP, soft + 3 * BP, arg, arg + BP, sb[0].d_soft, sb[1].d_soft, dins, dins + 2 * (size_t)B * Dm,
+  STEP_CALL("umpr_coattn_bwd", umpr_coattn_bwd(gu, gi, giM, soft, soft + BP, soft + 2 * BP, soft + 3 * BP, arg, arg + BP, sb[0].d_soft, sb[1].d_soft, dins, dins + 2 * (size_t)B * Dm,
                            B, P, cst_u, sd[0].S, sd[0].L, cst_i, sd[1].S, sd[1].L, sb[0].dx_s, sb[1].dx_s, sb[0].dx_r, sb[1].dx_r, dgiM, stream));
   // dgi += dgiM · M^T ;  dM = gi^T · dgiM
   if (BP >= 1024)
-    UMPR_TRY(umpr_tc_gemm_ws(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
+    STEP_CALL("umpr_tc_gemm_ws", umpr_tc_gemm_ws(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
   else
-    UMPR_TRY(umpr_tc_gemm_nt(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, stream));
+    STEP_CALL("umpr_tc_gemm_nt", umpr_tc_gemm_nt(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, stream));
   if (BP >= 4096) {
-    UMPR_TRY(umpr_tc_gemm_tn(gi, Dm, dgiM, Dm, m.g_M, Dm, Dm, Dm, (long)BP, n_ctas, stream));
+    STEP_CALL("umpr_tc_gemm_tn", umpr_tc_gemm_tn(gi, Dm, dgiM, Dm, m.g_M, Dm, Dm, Dm, (long)BP, n_ctas, stream));
   } else {
     int splits = (int)(BP / 256);
     splits = splits < 1 ? 1 : (splits > n_ctas ? n_ctas : splits);
-    UMPR_TRY(umpr_sgemm(gi, 1, Dm, dgiM, Dm, 1, m.g_M, Dm, Dm, Dm, (int)BP, splits, 1, nullptr, 0, stream));
+    STEP_CALL("umpr_sgemm", umpr_sgemm(gi, 1, Dm, dgiM, Dm, 1, m.g_M, Dm, Dm, Dm, (int)BP, splits, 1, nullptr, 0, stream));
   }
   {
     umpr_gru_bwd_seg segs[2];
     for (int k = 0; k < 2; ++k)
       segs[k] = umpr_gru_bwd_seg{sb[k].dx_r, nullptr, sb[k].xq, sb[k].hq_r, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
-    UMPR_TRY(umpr_gru_bwd_tc(segs, 2, m.rnet_gru, m.g_rnet_gru, E, zero_img, sched_r, nq_r, stream));
+    STEP_CALL("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 2, m.rnet_gru, m.g_rnet_gru, E, zero_img, sched_r, nq_r, stream));
   }
   return 0;
 }
@@ -321,4 +352,40 @@ extern "C" int umpr_step(const umpr_step_model* model, const umpr_step_side* sid
   }
   Arena a{reinterpret_cast<unsigned char*>(workspace), 0, (size_t)workspace_bytes};
   return run_step(*model, sides, photos, labels, sched_r, nq_r, sched_c, nq_c, zero_img, a, pred, loss, train, n_ctas, stream);
+}
+
+// per-entry-point timing of the following umpr_step calls: every entry point (only == NULL) or just the named one
+extern "C" int umpr_step_profile_begin(const char* only) {
+  g_prof.on = true;
+  g_prof.only = only ? only : "";
+  g_prof.recs.clear();
+  g_prof.used = 0;
+  return 0;
+}
+// stops the timing, synchronises, and returns per entry point (aggregated by name, first-launch order): names[i] (48 bytes each,
+// NUL-terminated), total milliseconds, number of calls; *n_out entries (at most max_entries)
+extern "C" int umpr_step_profile_end(int max_entries, char* names, float* ms, int* calls, int* n_out) {
+  g_prof.on = false;
+  if (!names || !ms || !calls || !n_out) return fail_arg("step_profile_end: NULL output");
+  int n = 0;
+  for (const ProfRec& r : g_prof.recs) {
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e != cudaSuccess) { set_error("step_profile_end: %s", cudaGetErrorString(e)); return (int)e; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    int k = 0;
+    for (; k < n; ++k) if (!strcmp(names + 48 * k, r.name)) break;
+    if (k == n) {
+      if (n == max_entries) continue;
+      strncpy(names + 48 * k, r.name, 47);
+      names[48 * k + 47] = 0;
+      ms[k] = 0.f; calls[k] = 0;
+      ++n;
+    }
+    ms[k] += t; calls[k] += 1;
+  }
+  *n_out = n;
+  g_prof.recs.clear();
+  g_prof.used = 0;
+  return 0;
 }

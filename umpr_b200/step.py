@@ -114,6 +114,49 @@ class NativeStep:
                 return False
         return True
 
+    def work_table(self, batch, plans):
+        """Algorithmic work of one training step per entry point, {name: [flops, bytes]} (SURVEY.md §8d / DESIGN.md §4 formulas over the
+        VALID tokens of each side) - what bench.py divides by the measured kernel time."""
+        H, D, ATT, KP = 64, 128, 64, 64
+        E, KC = self.m.E, self.m.KC
+        B = batch[0].shape[0]
+        tok = [float(p.tokens) if p is not None else 0.0 for p in plans]
+        nsent = [float(p.N) if p is not None else 0.0 for p in plans]
+        n = 3 if self.full else 2
+        launches = [tok[0] + tok[1]] + ([tok[0] + tok[1] + tok[2]] if self.full else [])
+        P = batch[0].shape[1] * batch[0].shape[2]
+        w = {"umpr_gather_pack_tc": [0.0, sum(tok[:n]) * (8 + 4 * E + 4 * KP)],
+             "umpr_gru_fwd_tc": [sum(2.0 * t * (E + H) * 6 * H for t in launches), 0.0],
+             # recurrence backward (dh and dW_hh) 98 304 + dW_ih 38 400 FLOP per token; the recomputed gates are not counted
+             "umpr_gru_bwd_tc": [sum(2.0 * t * 2 * H * 3 * H + 2.0 * t * 2 * 3 * H * (E + H) for t in launches), 0.0],
+             "umpr_tc_gemm_ws": [2 * 2.0 * tok[1] * D * D, 0.0],
+             "umpr_tc_gemm_tn": [2.0 * D * D * B * P, 0.0],
+             "umpr_coattn_fwd_tc": [2.0 * tok[0] * tok[1] / B * D, 2.0 * (tok[0] + tok[1]) * D * 4],
+             "umpr_coattn_bwd": [0.0, 3.0 * (tok[0] + tok[1]) * D * 4],
+             "umpr_snet_fwd_tc": [sum(2.0 * t * D * ATT for t in tok[:n]), sum(t * D * 8.0 for t in tok[:n])],
+             "umpr_snet_bwd_tc": [sum(6.0 * t * D * ATT for t in tok[:n]), sum(t * D * 8.0 for t in tok[:n])]}
+        if self.full:
+            w["umpr_cnet_conv_fwd_tc"] = [sum(2.0 * (t + s) * 3 * D * KC for t, s in zip(tok, nsent)), sum(t * D * 4.0 for t in tok)]
+            for k in ("umpr_cnet_conv_bwd_dx_tc", "umpr_cnet_conv_bwd_dw_tc"):
+                w[k] = [sum(2.0 * (t + 2 * s) * 3 * D * KC for t, s in zip(tok, nsent)), sum(t * D * 4.0 + s * KC * 8.0 for t, s in zip(tok, nsent))]
+        return w
+
+    @staticmethod
+    def profile_begin(only=None):
+        """Time the entry points inside the following ``run`` calls (all, or only the named one) with CUDA events on the stream."""
+        if _lib.load().umpr_step_profile_begin(only.encode() if only else None) != 0:
+            raise RuntimeError(f"umpr_step_profile_begin: {_lib.last_error()}")
+
+    @staticmethod
+    def profile_end():
+        """→ {entry point: dict(calls, ms)}; synchronises."""
+        n_max = 64
+        names = C.create_string_buffer(48 * n_max)
+        ms, calls, n = (C.c_float * n_max)(), (C.c_int * n_max)(), C.c_int(0)
+        if _lib.load().umpr_step_profile_end(n_max, names, ms, calls, C.byref(n)) != 0:
+            raise RuntimeError(f"umpr_step_profile_end: {_lib.last_error()}")
+        return {names.raw[48 * i:48 * (i + 1)].split(b"\0", 1)[0].decode(): dict(calls=calls[i], ms=ms[i]) for i in range(n.value)}
+
     def run(self, batch, train: bool, plans=None, routing_log=None):
         """→ (prediction (B,), loss scalar).  ``train``: also the backward, parameter gradients accumulated into ``p.grad``."""
         if train and not self.with_grads:
