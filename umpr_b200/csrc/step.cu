@@ -8,6 +8,7 @@
 // integer pack plans / valid-row tables / tile schedules derived from it (umpr_b200/plan.py), uploaded in one buffer.
 // Parameter gradients are ACCUMULATED into the caller's gradient bucket (zeroed by the caller, all-reduced and consumed by
 // umpr_adam_step afterwards), exactly as functional._sinks does under FlatTrainer.
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -31,6 +32,7 @@ struct Profiler {
   }
 };
 static Profiler g_prof;
+static bool g_single_stream = false;      // UMPR_STEP_SINGLE_STREAM=1: never fork the C-Net branch (debugging / timing)
 struct ProfScope {
   cudaEvent_t e1 = nullptr;
   cudaStream_t st;
@@ -57,6 +59,7 @@ struct Arena {
 
 #define UMPR_TRY(call) do { if (int rc_ = (call)) return rc_; } while (0)
 #define STEP_CALL(name, call) do { ProfScope ps_(name, st); if (int rc_ = (call)) return rc_; } while (0)
+#define STEP_CALL_C(name, call) do { ProfScope ps_(name, stc); if (int rc_ = (call)) return rc_; } while (0)      // on the C-Net branch's stream
 
 __global__ void expand_rows_kernel(const float* __restrict__ src, long n_rows, int L, float* __restrict__ dst) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -179,6 +182,25 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   // ------------------------------------------------------------------------------------------------ forward
   for (int k = 0; k < n_sides; ++k)          // model.py:262-264 fused into the pack half of model.py:18
     STEP_CALL("umpr_gather_pack_tc", umpr_gather_pack_tc(m.table, sd[k].ids, nullptr, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].L, E, sb[k].xq, stream));
+  // Small batches leave most SMs idle inside one GRU launch (a tile is a serial chain of time steps): the C-Net branch (its GRU,
+  // convolution tails, ControlNet tail) then runs on a second stream beside the R-Net branch, forward and backward.
+  int tiles_all = 0;
+  for (int k = 0; k < n_sides; ++k) tiles_all += sd[k].n_tiles * (k < 2 && full ? 2 : 1);      // user, item tiles are in both launches
+  const bool two = full && 2 * tiles_all <= n_ctas + n_ctas / 4 && !g_single_stream;
+  cudaStream_t stc = st;
+  void* cstream = stream;
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev[4];
+  if (two) {
+    if (!side) {
+      if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return fail_arg("step: cannot create the side stream"); }
+      for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
+    stc = side;
+    cstream = side;
+    cudaEventRecord(ev[0], st);              // fork: the token images are packed
+    cudaStreamWaitEvent(stc, ev[0], 0);
+  }
   {                                          // R-Net's GRU over user + item, one launch (model.py:45-46)
     umpr_gru_seg segs[2];
     for (int k = 0; k < 2; ++k)
@@ -212,19 +234,20 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
         const int k = order[j];
         segs[j] = umpr_gru_seg{sb[k].xq, sd[k].plan, sb[k].out_c, nullptr, sb[k].hq_c, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
       }
-      STEP_CALL("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 3, m.cnet_gru, E, sched_c, nq_c, stream));
+      STEP_CALL_C("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 3, m.cnet_gru, E, sched_c, nq_c, cstream));
     }
     for (int k = 0; k < 3; ++k) {            // conv + ReLU + max-pool + view head (model.py:118-125)
       const int N = sd[k].B * sd[k].S;
-      STEP_CALL("umpr_cnet_conv_fwd_tc", umpr_cnet_conv_fwd_tc(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
-                                     sb[k].cfeat, sb[k].cidx, n_ctas, stream));
-      STEP_CALL("umpr_cnet_head_fwd", umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, stream));
-      if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+      STEP_CALL_C("umpr_cnet_conv_fwd_tc", umpr_cnet_conv_fwd_tc(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
+                                     sb[k].cfeat, sb[k].cidx, n_ctas, cstream));
+      STEP_CALL_C("umpr_cnet_head_fwd", umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, cstream));
+      if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, stc);
     }
     // ControlNet tail (model.py:185-197): S-Net on the user->item review (its `sentiment` output is unused), SSNet + Eq.18 + gates
-    STEP_CALL("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, s_ui, n_ctas, stream));
-    STEP_CALL("umpr_control_tail_fwd", umpr_control_tail_fwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, m.ss_b, m.eq18_eps, B, sd[2].S, V, senti_ss, ct_out, ct_out + (size_t)B * V,
-                                   ct_out + 2 * (size_t)B * V, stream));
+    STEP_CALL_C("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, s_ui, n_ctas, cstream));
+    STEP_CALL_C("umpr_control_tail_fwd", umpr_control_tail_fwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, m.ss_b, m.eq18_eps, B, sd[2].S, V, senti_ss, ct_out, ct_out + (size_t)B * V,
+                                   ct_out + 2 * (size_t)B * V, cstream));
+    if (two) { cudaEventRecord(ev[1], stc); cudaStreamWaitEvent(st, ev[1], 0); }      // join: the visual tail needs c_u, c_i
     // VisualNet tail (model.py:219-228)
     STEP_CALL("umpr_visual_fwd", umpr_visual_fwd(photos, m.pos_e, m.neg_e, m.vis_w, m.vis_b, sb[0].fin, sb[1].fin, B, V, m.Pc, m.F, vis_emb, vis_out, vis_out + (size_t)B * V,
                              vis_out + 2 * (size_t)B * V, vis_out + 3 * (size_t)B * V, vis_out + 4 * (size_t)B * V, stream));
@@ -246,23 +269,24 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   if (full) {
     STEP_CALL("umpr_visual_bwd", umpr_visual_bwd(photos, m.pos_e, m.neg_e, m.vis_w, vis_emb, vis_out, pm, nm, sb[0].fin, sb[1].fin, g4 + 2 * (size_t)B * V, g4 + 3 * (size_t)B * V,
                              d_f, d_f + (size_t)B * V, B, V, m.Pc, m.F, vis_scr, d_c, d_c + (size_t)B * V, m.g_pos_e, m.g_neg_e, m.g_vis_w, m.g_vis_b, stream));
-    STEP_CALL("umpr_control_tail_bwd", umpr_control_tail_bwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, senti_ss, ct_out, g4, g4 + (size_t)B * V, m.eq18_eps, B, sd[2].S, V, d_s, d_vp, d_co,
-                                   m.g_ss_w, m.g_ss_b, stream));
+    if (two) { cudaEventRecord(ev[2], st); cudaStreamWaitEvent(stc, ev[2], 0); }      // fork: d(c_u), d(c_i), d(prefer_*) are there
+    STEP_CALL_C("umpr_control_tail_bwd", umpr_control_tail_bwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, senti_ss, ct_out, g4, g4 + (size_t)B * V, m.eq18_eps, B, sd[2].S, V, d_s, d_vp, d_co,
+                                   m.g_ss_w, m.g_ss_b, cstream));
     // S-Net on the user->item review: only self_atte was used, so d(self_atte) = d_s as it is
-    STEP_CALL("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, d_s, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, dx_s_ui,
-                              m.g_csnet_Ms, m.g_csnet_Ws, n_ctas, stream));
+    STEP_CALL_C("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, d_s, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, dx_s_ui,
+                              m.g_csnet_Ms, m.g_csnet_Ws, n_ctas, cstream));
     for (int k = 0; k < 3; ++k) {
       const int N = sd[k].B * sd[k].S;
       const float* d_view = k == 2 ? d_vp : nullptr;
       const float* d_fin = k == 2 ? d_co : d_c + (size_t)k * B * V;              // c_u, c_i feed the visual tail; c_net_out the control tail
-      STEP_CALL("umpr_cnet_head_bwd", umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
-                                  m.g_conv_b, stream));
-      STEP_CALL("umpr_cnet_conv_bwd_dx_tc", umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch, sb[k].dx_c, n_ctas, stream));
-      STEP_CALL("umpr_cnet_conv_bwd_dw_tc", umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, stream));
+      STEP_CALL_C("umpr_cnet_head_bwd", umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
+                                  m.g_conv_b, cstream));
+      STEP_CALL_C("umpr_cnet_conv_bwd_dx_tc", umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch, sb[k].dx_c, n_ctas, cstream));
+      STEP_CALL_C("umpr_cnet_conv_bwd_dw_tc", umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, cstream));
     }
     {                                        // the user->item GRU output feeds the convolution AND S-Net: sum of both gradients
       const long n4 = (long)(side_tokens_rows(sd[2]) * Dm / 4);
-      add_inplace_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<float4*>(sb[2].dx_c), reinterpret_cast<const float4*>(dx_s_ui), n4);
+      add_inplace_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stc>>>(reinterpret_cast<float4*>(sb[2].dx_c), reinterpret_cast<const float4*>(dx_s_ui), n4);
       UMPR_TRY(check_launch("step add"));
     }
     umpr_gru_bwd_seg segs[3];
@@ -271,7 +295,7 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
       const int k = order[j];
       segs[j] = umpr_gru_bwd_seg{sb[k].dx_c, nullptr, sb[k].xq, sb[k].hq_c, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
     }
-    STEP_CALL("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 3, m.cnet_gru, m.g_cnet_gru, E, zero_img, sched_c, nq_c, stream));
+    STEP_CALL_C("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 3, m.cnet_gru, m.g_cnet_gru, E, zero_img, sched_c, nq_c, cstream));
   }
   // text matching (model.py:166-168)
   STEP_CALL("umpr_tanh_bwd", umpr_tanh_bwd(repr, d_repr, (long)B * Dm, dpre, stream));
@@ -307,6 +331,7 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
       segs[k] = umpr_gru_bwd_seg{sb[k].dx_r, nullptr, sb[k].xq, sb[k].hq_r, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
     STEP_CALL("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 2, m.rnet_gru, m.g_rnet_gru, E, zero_img, sched_r, nq_r, stream));
   }
+  if (two) { cudaEventRecord(ev[3], stc); cudaStreamWaitEvent(st, ev[3], 0); }        // join: every gradient is in the bucket
   return 0;
 }
 
@@ -346,6 +371,8 @@ extern "C" int umpr_step(const umpr_step_model* model, const umpr_step_side* sid
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail_arg("step: workspace must be 256-byte aligned");
   static int n_ctas = 0;
   if (!n_ctas) {
+    const char* e = getenv("UMPR_STEP_SINGLE_STREAM");
+    g_single_stream = e && e[0] == '1';
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n_ctas, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_ctas < 1) n_ctas = 148;

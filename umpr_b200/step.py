@@ -178,12 +178,13 @@ class NativeStep:
             sides[k] = _lib.StepSide(ids.data_ptr(), p.buf.data_ptr(), st.data_ptr(), ct.data_ptr() if ct is not None else None, s_nt, c_nt,
                                      p.n_tiles, p.n_slabs, B, ids.shape[1], ids.shape[2], p.max_valid_per_sample(B))
         n_ctas = max(1, _lib.sm_count(dev) // 2)
-        sr, nq_r = build_schedule([plans[0].tile_len, plans[1].tile_len], n_ctas)
+        pre = getattr(batch[3], "_umpr_sched", None) if plans[0] is getattr(batch[3], "_umpr_plan", None) else None     # built by the prefetch worker
+        sr, nq_r = pre[0] if pre else build_schedule([plans[0].tile_len, plans[1].tile_len], n_ctas)
         sr = upload_int32(sr, dev)
         sc, nq_c = None, 0
         photos = None
         if self.full:
-            sc, nq_c = build_schedule([plans[2].tile_len, plans[0].tile_len, plans[1].tile_len], n_ctas)
+            sc, nq_c = pre[1] if pre and len(pre) > 1 else build_schedule([plans[2].tile_len, plans[0].tile_len, plans[1].tile_len], n_ctas)
             sc = upload_int32(sc, dev)
             photos = batch[6].to(dev, non_blocking=True)
             photos = photos.reshape(B, photos.shape[1], photos.shape[2], -1).to(torch.float32).contiguous()

@@ -178,6 +178,15 @@ def prepare_batch(batch, device):
                 lens._umpr_plan._snet_host()                      # S-Net / C-Net tile tables (numpy; uploaded by the consumer)
                 if ids.shape[2] <= 126:
                     lens._umpr_plan._cnet_host()
+    # tile schedules of the two fused GRU launches (user+item; ui+user+item), for the native one-call step
+    pl = [getattr(t, "_umpr_plan", None) for t in (ul, il, uil)]
+    if pl[0] is not None and pl[1] is not None and pl[0].R == 128 and pl[1].R == 128:
+        from .plan import build_schedule
+        n_ctas = max(1, (_lib.sm_count(device) if torch.device(device).type == "cuda" else 148) // 2)
+        sched = [build_schedule([pl[0].tile_len, pl[1].tile_len], n_ctas)]
+        if pl[2] is not None and pl[2].R == 128:
+            sched.append(build_schedule([pl[2].tile_len, pl[0].tile_len, pl[1].tile_len], n_ctas))
+        ul._umpr_sched = sched
     return batch
 
 
