@@ -259,6 +259,10 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cores = None
+    if world > 1:
+        from umpr_b200.train import pin_rank_to_cores
+        cores = pin_rank_to_cores(local, world)         # one process per GPU, each on its own host cores
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -408,6 +412,10 @@ def main():
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "tokens_per_step_per_gpu": int(sum(tokens) / NB), "trainable_params": n_params,
                    "step": "zero_grad+fwd+bwd+allreduce+adam",
+                   "gradient_exchange": ("none (1 GPU)" if world == 1 else
+                                         ("C-ABI NCCL communicator (umpr_comm_*), 2 buckets [head/attention/conv/C-Net | R-Net GRU], the first all-reduced under the last backward kernel"
+                                          if trainer.overlap else ("C-ABI NCCL communicator, after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
+                   "host_cores_per_rank": len(cores) if cores else None,
                    "issue": "one native C-ABI call per step (umpr_step) + all-reduce + umpr_adam_step" if native else "autograd Functions over per-kernel C-ABI calls",
                    "host_pipeline": "the next batch's pack plans (torch.sort + int32 plan) are built on a worker thread, like a collate worker; rebuilt every step",
                    "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; 4 rotating input batches"},

@@ -305,6 +305,10 @@ int umpr_step(const umpr_step_model* model, const umpr_step_side* sides, const f
               void* workspace /* 256-byte aligned */, long long workspace_bytes, float* pred /* (B) */, float* loss /* scalar */,
               int train, void* stream);
 
+/* gradient exchange overlapped with the backward of the following umpr_step(train) calls (replaces DataParallel's reduce, main.py:81-82):
+ * the bucket is [early | late] with only R-Net's GRU gradients (+ trailing extras) late; `early` is all-reduced on a library stream while
+ * the last backward kernel runs, `late` after it; the caller's stream waits for both before umpr_step returns control to it. */
+int umpr_step_comm(void* comm /* umpr_comm_init handle, NULL = off */, float* bucket, long n_early, long n_total);
 /* optional timing of the entry points inside the following umpr_step calls (CUDA-event pairs on the launching stream): all of them
  * (only == NULL) or just the named one.  _end synchronises and returns the totals aggregated by entry-point name. */
 int umpr_step_profile_begin(const char* only);

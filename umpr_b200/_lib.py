@@ -71,6 +71,7 @@ SIGNATURES = {
     "umpr_tanh_bwd": [P, P, L, P, P],
     "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
     "umpr_step_workspace_bytes": [P, P, I, P],
+    "umpr_step_comm": [P, P, L, L],
     "umpr_step_profile_begin": [C.c_char_p],
     "umpr_step_profile_end": [I, P, P, P, P],
     "umpr_step": [P, P, P, P, P, I, P, I, P, P, C.c_longlong, P, P, I, P],

@@ -32,6 +32,11 @@ struct Profiler {
   }
 };
 static Profiler g_prof;
+// gradient exchange overlapped with the backward (umpr_step_comm): the flat bucket is [early | late]; `early` (everything but R-Net's
+// GRU gradients) is final before the last kernel of the backward - the fused R-Net GRU backward - starts, and is all-reduced on a
+// communication stream WHILE that kernel runs; `late` follows when it has finished (two hand-placed buckets)
+struct Overlap { void* comm = nullptr; float* bucket = nullptr; long n_early = 0, n_total = 0; };
+static Overlap g_ov;
 static bool g_single_stream = false;      // UMPR_STEP_SINGLE_STREAM=1: never fork the C-Net branch (debugging / timing)
 struct ProfScope {
   cudaEvent_t e1 = nullptr;
@@ -325,13 +330,36 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     splits = splits < 1 ? 1 : (splits > n_ctas ? n_ctas : splits);
     STEP_CALL("umpr_sgemm", umpr_sgemm(gi, 1, Dm, dgiM, Dm, 1, m.g_M, Dm, Dm, Dm, (int)BP, splits, 1, nullptr, 0, stream));
   }
+  static cudaStream_t comm_st = nullptr;
+  static cudaEvent_t cev[3];
+  const bool overlap = g_ov.comm != nullptr;
+  if (overlap) {
+    if (!comm_st) {
+      if (cudaStreamCreateWithFlags(&comm_st, cudaStreamNonBlocking) != cudaSuccess) { comm_st = nullptr; return fail_arg("step: cannot create the communication stream"); }
+      for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&cev[i], cudaEventDisableTiming);
+    }
+    // early bucket: every gradient but R-Net's GRU tensors has been accumulated (on this stream, and on the C-Net branch's)
+    cudaEventRecord(cev[0], st);
+    cudaStreamWaitEvent(comm_st, cev[0], 0);
+    if (two) { cudaEventRecord(ev[3], stc); cudaStreamWaitEvent(comm_st, ev[3], 0); }
+    UMPR_TRY(umpr_allreduce(g_ov.comm, g_ov.bucket, g_ov.n_early, comm_st));
+  }
   {
     umpr_gru_bwd_seg segs[2];
     for (int k = 0; k < 2; ++k)
       segs[k] = umpr_gru_bwd_seg{sb[k].dx_r, nullptr, sb[k].xq, sb[k].hq_r, sd[k].plan, sd[k].n_tiles, sd[k].n_slabs, sd[k].B * sd[k].S, sd[k].L};
     STEP_CALL("umpr_gru_bwd_tc", umpr_gru_bwd_tc(segs, 2, m.rnet_gru, m.g_rnet_gru, E, zero_img, sched_r, nq_r, stream));
   }
-  if (two) { cudaEventRecord(ev[3], stc); cudaStreamWaitEvent(st, ev[3], 0); }        // join: every gradient is in the bucket
+  if (overlap) {
+    cudaEventRecord(cev[1], st);             // late bucket: R-Net's GRU gradients (and the shard count behind them)
+    cudaStreamWaitEvent(comm_st, cev[1], 0);
+    UMPR_TRY(umpr_allreduce(g_ov.comm, g_ov.bucket + g_ov.n_early, g_ov.n_total - g_ov.n_early, comm_st));
+    cudaEventRecord(cev[2], comm_st);
+    cudaStreamWaitEvent(st, cev[2], 0);      // whatever follows on the caller's stream (umpr_adam_step) sees the reduced bucket
+  } else if (two) {
+    cudaEventRecord(ev[3], stc);
+    cudaStreamWaitEvent(st, ev[3], 0);       // join: every gradient is in the bucket
+  }
   return 0;
 }
 
@@ -414,5 +442,15 @@ extern "C" int umpr_step_profile_end(int max_entries, char* names, float* ms, in
   *n_out = n;
   g_prof.recs.clear();
   g_prof.used = 0;
+  return 0;
+}
+
+// Overlap the gradient exchange with the backward of the following umpr_step(train) calls: comm = umpr_comm_init handle (NULL switches
+// the overlap off), bucket = the flat gradient buffer the g_* pointers of the model point into, laid out [early (n_early floats) | late]
+// with ONLY R-Net's GRU gradients (and trailing extras such as a shard counter) in the late part.  Both all-reduces run on a stream
+// of the library; the caller's stream waits for them at the end of umpr_step.
+extern "C" int umpr_step_comm(void* comm, float* bucket, long n_early, long n_total) {
+  if (comm && (!bucket || n_early < 0 || n_total < n_early)) return fail_arg("step_comm: bucket=%p n_early=%ld n_total=%ld", (void*)bucket, n_early, n_total);
+  g_ov.comm = comm; g_ov.bucket = bucket; g_ov.n_early = n_early; g_ov.n_total = n_total;
   return 0;
 }

@@ -52,6 +52,23 @@ class AbiComm:
             self._h = None
 
 
+def pin_rank_to_cores(local_rank: int, local_world: int):
+    """Give every rank of a node its own slice of the host cores (one process per GPU): the step is issued by one Python thread plus a
+    plan-prefetch worker, and a rank whose threads get migrated or share a core with another rank's stalls all ranks at the all-reduce."""
+    import os
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    per = len(cores) // max(1, local_world)
+    if per < 1:
+        return None
+    mine = cores[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    torch.set_num_threads(max(1, min(per, 4)))
+    return mine
+
+
 class FlatTrainer:
     def __init__(self, model, lr=1e-6, weight_decay=1e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay=0.99, process_group=None, comm=None,
                  native=True):
@@ -61,6 +78,10 @@ class FlatTrainer:
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         if not named:
             raise RuntimeError("nothing to train")
+        # bucket layout [early | late]: R-Net's GRU tensors go last - their gradients are the last to become final (the fused R-Net GRU
+        # backward is the last kernel of a step), everything else can be all-reduced while that kernel runs
+        late = lambda n: n.startswith("review_net.r_net.gru.")
+        named = [x for x in named if not late(x[0])] + [x for x in named if late(x[0])]
         dev = named[0][1].device
         ALIGN = 64                                                  # floats: every tensor starts on a 256-byte boundary
         up = lambda k: (k + ALIGN - 1) // ALIGN * ALIGN             # (the kernels use 128-bit loads on some weights)
@@ -77,9 +98,12 @@ class FlatTrainer:
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         o = 0
+        self.n_early = total
         with torch.no_grad():
             for n, p in named:
                 k = p.numel()
+                if late(n) and self.n_early == total:
+                    self.n_early = o
                 self.flat[o:o + k].copy_(p.reshape(-1))
                 p.data = self.flat[o:o + k].view_as(p)          # parameters become views of the flat buffer
                 p.grad = self.grad[o:o + k].view_as(p)          # autograd accumulates straight into the bucket
@@ -93,7 +117,8 @@ class FlatTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.comm = None
         import os
-        if (comm or os.environ.get("UMPR_COMM", "torch")) == "abi" and self.world > 1 and self.flat.is_cuda:
+        # the gradient exchange goes through the library's own NCCL communicator (C-ABI) by default; "torch" = torch.distributed.all_reduce
+        if (comm or os.environ.get("UMPR_COMM", "abi")) == "abi" and self.world > 1 and self.flat.is_cuda:
             self.comm = AbiComm(dist.get_rank(process_group), self.world, dev, process_group)
         # the whole forward + backward as one native call (csrc/step.cu) whenever the model is the standard UMPR on a CUDA device
         # and the batch lies inside that path's envelope; the autograd path (functional.py) is the general fallback
@@ -103,6 +128,8 @@ class FlatTrainer:
             from .step import NativeStep
             if isinstance(model, UMPR):
                 self.native = NativeStep(model, with_grads=True)
+        # with both, the exchange overlaps the backward: two buckets all-reduced from inside umpr_step (csrc/step.cu, umpr_step_comm)
+        self.overlap = self.native is not None and self.comm is not None and os.environ.get("UMPR_OVERLAP", "1") == "1"
 
     def zero_grad(self):
         self.bucket.zero_()
@@ -116,9 +143,11 @@ class FlatTrainer:
                                    "another optimizer used?) - use FlatTrainer.zero_grad()")
 
     def reduce_gradients(self):
-        """One flat bucket (0.57–1.0 MB): latency-bound, so a single NCCL all-reduce is the whole exchange."""
+        """The flat bucket (0.57–1.0 MB, latency-bound) as two all-reduces, [early | late] - the same two collectives, in the same
+        order, that the native step issues from inside its backward (a rank without a shard joins them from here)."""
         if self.comm is not None:
-            self.comm.all_reduce(self.bucket)
+            self.comm.all_reduce(self.bucket[:self.n_early])
+            self.comm.all_reduce(self.bucket[self.n_early:])
         elif self.world > 1:
             dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
@@ -143,13 +172,24 @@ class FlatTrainer:
             self.model.train()
         self.zero_grad()
         pred = loss = None
+        reduced = False
         if batch is not None:
             self.check_bucket()
+            if self.world > 1:
+                self.shard_count.fill_(1.0)         # this rank contributes a shard (counted by the all-reduce, read by the Adam kernel)
             plans = self.native.plans_of(batch, self.flat.device) if self.native is not None else None
             if plans is not None and self.native.supported(batch, plans):
-                # one C-ABI call: forward, backward, gradients accumulated into the flat bucket
+                # one C-ABI call: forward, backward, gradients accumulated into the flat bucket - and, with the library's communicator,
+                # both all-reduces issued from inside it so that the first overlaps the last backward kernel
                 with torch.cuda.device(self.flat.device):
-                    pred, loss = self.native.run(batch, True, plans, routing_log=F.ROUTING_LOG)
+                    if self.overlap:
+                        self._set_overlap(True)
+                    try:
+                        pred, loss = self.native.run(batch, True, plans, routing_log=F.ROUTING_LOG)
+                    finally:
+                        if self.overlap:
+                            self._set_overlap(False)
+                reduced = self.overlap
                 self.native_steps += 1
             else:
                 pred, loss = self.model(*batch)
@@ -158,11 +198,15 @@ class FlatTrainer:
                     (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
                 finally:
                     F.DIRECT_GRAD_ACCUM = False
-            if self.world > 1:
-                self.shard_count.fill_(1.0)
-        self.reduce_gradients()
+        if not reduced:
+            self.reduce_gradients()
         self.optimizer_step(use_shard_count=self.world > 1)
         return pred, loss
+
+    def _set_overlap(self, on: bool):
+        lib = _lib.load()
+        if lib.umpr_step_comm(self.comm._h if on else None, ptr(self.bucket), self.n_early, self.bucket.numel()) != 0:
+            raise RuntimeError(f"umpr_step_comm: {_lib.last_error()}")
 
 
 def prepare_batch(batch, device):
