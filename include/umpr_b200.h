@@ -266,6 +266,15 @@ int umpr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                                                the number of replicas that received a chunk (DataParallel's loss.mean(), main.py:34) */,
                    void* stream);
 
+/* ---- the data formats either side of the path ----
+ * collate on device (dataset.py:122-131,163-171): expands ragged token lists - flat int32 tokens + the (n_sent + 1) exclusive prefix sum
+ * of the per-slot token counts - into the padded (n_sent, L) int64 id tensor the reference's collate emits (pad_id beyond each
+ * sentence, empty slots all pad). */
+int umpr_collate_ids(const int32_t* flat_tokens, const int32_t* sent_off, long n_sent, int L, long pad_id, int64_t* ids, void* stream);
+/* VGG16 feature cache (model.py:204-219, dataset.py:134-151): out[n] = table[idx[n]] (F floats per photo); idx < 0 or >= rows selects
+ * missing_row (the features of the reference's zero image; < 0: zeros). */
+int umpr_feature_gather(const float* table, const int32_t* idx, long n_photos, long rows, int F, long missing_row, float* out, void* stream);
+
 /* ---- the whole step as ONE call (model.py:257-278 forward; with train != 0 also its backward, main.py:36): the same kernels as
  * above, issued from native host code out of one caller-owned workspace - no per-kernel host round trips.  Tensor-core path only:
  * every side needs a pack plan with R = 128 and its valid-row tables (plan.py: snet_table / cnet_table), L <= 126 for the full

@@ -373,6 +373,45 @@ def pretrain_rnet_forward(params: Dict[str, Tensor], u: Tensor, u_len: Tensor, i
     return result, torch.nn.functional.binary_cross_entropy(result, target)                   # :167
 
 
+# ----------------------------------------------------------------------------
+# Collate  (src/dataset.py:122-131,153-182) and the photo features  (dataset.py:134-151, model.py:216-218) – next-rows (f2), (f4)
+# ----------------------------------------------------------------------------
+def pad_reviews(reviews, max_count=None, max_len=None, pad=0):
+    """dataset.py:122-131: pad every sample to ``max_count`` sentences (missing ones are EMPTY lists) and every sentence to ``max_len``
+    tokens with ``pad``; ``lengths = max(1, len)`` - an empty slot is a 1-token all-PAD sentence."""
+    if max_count is None:
+        max_count = max(len(r) for r in reviews)
+    lengths = [[max(1, len(r[j])) if j < len(r) else 1 for j in range(max_count)] for r in reviews]
+    if max_len is None:
+        max_len = max(max(row) for row in lengths)
+    ids = torch.full((len(reviews), max_count, max_len), pad, dtype=torch.int64)
+    for b, r in enumerate(reviews):
+        for j, sent in enumerate(r):
+            ids[b, j, :len(sent)] = torch.tensor(sent, dtype=torch.int64)
+    return ids, torch.tensor(lengths, dtype=torch.int64)
+
+
+def batch_loader(batch_list, pad=0):
+    """dataset.py:153-182 without the JPEG loading: user and item padded to SHARED (max_count, max_len) taken over the raw sentence
+    lengths of both (:163-170), the user->item review to its own maxima (:171).  → (user, item, ui, u_len, i_len, ui_len, labels)."""
+    ru, ri, rui = ([s[k] for s in batch_list] for k in range(3))
+    max_count = max(max(len(a), len(b)) for a, b in zip(ru, ri))
+    max_len = max(max(max(len(s) for s in a), max(len(s) for s in b)) for a, b in zip(ru, ri))
+    u, ul = pad_reviews(ru, max_count, max_len, pad)
+    i, il = pad_reviews(ri, max_count, max_len, pad)
+    ui, uil = pad_reviews(rui, pad=pad)
+    return u, i, ui, ul, il, uil, torch.tensor([s[4] for s in batch_list], dtype=torch.float32)
+
+
+def photo_features(table: Tensor, rows: Tensor, missing_row: int = -1) -> Tensor:
+    """What ``VisualNet`` sees at model.py:218 when the backbone's outputs are cached per photo: ``table[rows]``; a row < 0 (photo
+    missing / unreadable: the reference feeds a zero image, dataset.py:147-148) takes ``table[missing_row]``, or zeros."""
+    rows = rows.to(torch.int64)
+    out = table[rows.clamp(min=0)]
+    miss = table[missing_row] if missing_row >= 0 else torch.zeros(table.shape[1], dtype=table.dtype)
+    return torch.where((rows < 0).unsqueeze(-1), miss.expand_as(out), out)
+
+
 def trainable_keys(params: Dict[str, Tensor]):
     """Everything but the frozen embedding (model.py:237 ``from_pretrained`` ⇒ requires_grad=False)."""
     return [k for k in params if k != "embedding.weight"]

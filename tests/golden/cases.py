@@ -156,6 +156,28 @@ def make_rnn_case(c):
     return torch.tensor(data, dtype=torch.float32), torch.tensor(lens), w, cot_out, cot_hid
 
 
+COLLATE_CASES = {"collate_a": dict(B=7, seed=31, max_count=6, max_ui=3, max_len=9), "collate_b": dict(B=33, seed=32, max_count=20, max_ui=5, max_len=20)}
+
+
+def make_collate_case(c):
+    """Ragged samples in the shape ``Dataset.__getitem__`` hands to ``batch_loader`` (dataset.py:38-41,153): (user sentences, item
+    sentences, user->item sentences, photo ids (V, Pc), rating); sentences are token-id lists, some of them EMPTY (they become the
+    1-token all-PAD sentences of dataset.py:125-127), pools are shorter than ``max_count`` for most samples."""
+    rs = np.random.RandomState(c["seed"])
+
+    def pool(max_count):
+        n = rs.randint(1, max_count + 1)
+        return [[int(t) for t in rs.randint(3, 500, size=rs.randint(0, c["max_len"] + 1))] for _ in range(n)]
+
+    out = []
+    for b in range(c["B"]):
+        photos = [["p%d" % rs.randint(0, 40)] for _ in range(1)]
+        out.append((pool(c["max_count"]), pool(c["max_count"]), pool(c["max_ui"]), photos, float(rs.randint(1, 6))))
+    # the reference takes max_len over the raw sentence lengths: make sure at least one sentence per batch is non-empty
+    out[0][0][0] = [int(t) for t in rs.randint(3, 500, size=c["max_len"])]
+    return out
+
+
 class CaseConfig:
     """The reference reads these attributes off ``config`` (model.py:235-253)."""
     def __init__(self, c):

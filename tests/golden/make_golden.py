@@ -100,8 +100,19 @@ def run_sort():
     np.savez_compressed(os.path.join(HERE, "sort_order.npz"), **out)
 
 
+def run_collate():
+    """The reference's own collate (dataset.py:153-182, ignore_photos: no JPEGs here) on seeded ragged samples."""
+    from src import dataset as ref_ds
+    for name, c in cases.COLLATE_CASES.items():
+        out = ref_ds.batch_loader(cases.make_collate_case(c), ignore_photos=True)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: out[i].numpy() for i, k in
+                                                                    enumerate(["user", "item", "ui", "u_len", "i_len", "ui_len", "photos", "labels"])})
+        print(name, [tuple(t.shape) for t in out])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    run_collate()
     for name, c in cases.RNN_CASES.items():
         run_rnn(name, c)
     for name, c in cases.CASES.items():

@@ -445,3 +445,56 @@ def test_model_on_a_non_current_device():
     for k, g in out[0][1].items():
         if float(g.abs().max()) > 1e-7:
             assert_close(out[1][1][k], g, 1e-5, "grad on cuda:1 " + k)
+
+
+@pytest.mark.parametrize("name", list(cases.COLLATE_CASES))
+def test_device_collate_matches_reference_batch_loader(name):
+    """umpr_b200.data.collate (ragged lists shipped flat, padded on the device by umpr_collate_ids) against the reference's
+    batch_loader fixtures: bit-exact ids (int64, on the device) and lengths (on the host, >= 1)."""
+    from umpr_b200.data import collate
+    g = load_golden(name)
+    out = collate(cases.make_collate_case(cases.COLLATE_CASES[name]), DEV, ignore_photos=True)
+    for i, k in enumerate(["user", "item", "ui"]):
+        assert out[i].is_cuda and out[i].dtype == torch.int64
+        assert np.array_equal(out[i].cpu().numpy(), g[k]), k
+    for i, k in zip((3, 4, 5), ["u_len", "i_len", "ui_len"]):
+        assert not out[i].is_cuda and np.array_equal(out[i].numpy(), g[k]), k
+    assert out[6].numel() == 0 and np.array_equal(out[7].numpy(), g["labels"])
+
+
+def test_feature_cache_feeds_the_visual_tail(tmp_path):
+    """photo ids -> rows of the on-disk VGG16 feature table -> umpr_feature_gather -> VisualNet tail.  The gathered
+    tensor equals oracle.photo_features (missing photos take the zero image's features), and the model's forward + backward on a
+    collated batch equals the one on explicitly supplied features."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.data import FeatureStore, collate
+    rs = np.random.RandomState(7)
+    n_photo, V, Pc, B = 300, 4, 2, 9
+    ids = ["ph%d" % i for i in range(n_photo)]
+    feats = (rs.normal(0, 0.05, size=(n_photo, 1000))).astype(np.float32)
+    zero_img = (rs.normal(0, 0.05, size=1000)).astype(np.float32)
+    store = FeatureStore.build(str(tmp_path / "vgg16.umprfeat"), ids, feats, missing_features=zero_img).to_device(DEV)
+    pick = rs.randint(0, n_photo, size=(B, V, Pc))
+    names = [[["unknown" if rs.rand() < 0.2 else "ph%d" % pick[b, v, p] for p in range(Pc)] for v in range(V)] for b in range(B)]
+    rows = store.rows_of(names)
+    got = store.gather(rows)
+    want = orc.photo_features(torch.from_numpy(np.concatenate([feats, zero_img[None]])), torch.from_numpy(rows), store.missing_row)
+    assert torch.equal(got.cpu(), want)
+    # through the model: collate with the store vs. the same features passed explicitly
+    c = cases.COLLATE_CASES["collate_a"]
+    samples = [(s[0], s[1], s[2], names[b], s[4]) for b, s in enumerate(cases.make_collate_case(c) + cases.make_collate_case(dict(c, seed=77)))][:B]
+    batch = collate(samples, DEV, feature_store=store)
+    table = syn.make_table(600, seed=2)
+    m = syn.build_model("yelp_full", table, seed=1, device=DEV)
+    pred, loss = m(*batch)
+    loss.backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad()
+    explicit = list(batch)
+    explicit[6] = want.reshape(B, V, Pc, 1000)
+    pred2, loss2 = m(*explicit)
+    loss2.backward()
+    assert torch.equal(pred, pred2) or rel_max(pred, pred2) < 1e-6
+    for k, p in m.named_parameters():
+        if p.grad is not None and float(p.grad.abs().max()) > 1e-7:
+            assert_close(g1[k], p.grad, 1e-5, "grad " + k)

@@ -1,4 +1,6 @@
 """The oracle against the reference's own outputs (tests/golden/*.npz).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -192,3 +194,34 @@ def test_pretrain_rnet_restatement_is_rnet_plus_torch_head():
     want = head(torch.cat([out[4], out[5]], -1)).squeeze(-1)
     assert_close(result, want.detach(), 1e-6, "result")
     assert_close(loss, torch.nn.BCELoss()(want, target).detach(), 1e-6, "loss")
+
+
+@pytest.mark.parametrize("name", list(cases.COLLATE_CASES))
+def test_collate_restatement_matches_reference_batch_loader(name):
+    """``oracle.batch_loader`` / ``pad_reviews`` against the reference's own collate (dataset.py:153-182, fixtures from make_golden.py):
+    bit-exact ids and lengths, shared (S, L) for user and item, own maxima for the user->item review, lengths >= 1."""
+    g = load_golden(name)
+    out = orc.batch_loader(cases.make_collate_case(cases.COLLATE_CASES[name]))
+    for t, k in zip(out, ["user", "item", "ui", "u_len", "i_len", "ui_len", "labels"]):
+        assert np.array_equal(t.numpy(), g[k]), k
+    assert int(out[3].min()) >= 1 and out[0].shape == out[1].shape
+
+
+def test_feature_store_round_trip(tmp_path):
+    """The VGG16 feature cache file (umpr_b200/data.py): build, reopen memory-mapped, ids -> rows (unknown ids -> -1)."""
+    from umpr_b200.data import FeatureStore
+    rs = np.random.RandomState(3)
+    ids = ["photo_%d" % i for i in range(57)]
+    feats = rs.normal(size=(57, 1000)).astype(np.float32)
+    zero_img = rs.normal(size=1000).astype(np.float32)
+    st = FeatureStore.build(str(tmp_path / "f.umprfeat"), ids, feats, missing_features=zero_img)
+    st2 = FeatureStore(str(tmp_path / "f.umprfeat"))
+    assert (st2.rows, st2.dim, st2.missing_row) == (58, 1000, 57)
+    assert np.array_equal(np.asarray(st2.features[:57]), feats) and np.array_equal(np.asarray(st2.features[57]), zero_img)
+    rows = st2.rows_of([[["photo_3", "unknown"]], [["photo_56", "photo_0"]]])
+    assert rows.tolist() == [[[3, -1]], [[56, 0]]]
+    ref = orc.photo_features(torch.from_numpy(np.asarray(st2.features)), torch.from_numpy(rows), st2.missing_row)
+    assert torch.equal(ref[0, 0, 1], torch.from_numpy(zero_img)) and torch.equal(ref[1, 0, 0], torch.from_numpy(feats[56]))
+    # a store with many photos keeps its key table in a side file
+    big = FeatureStore.build(str(tmp_path / "g.umprfeat"), ["id%06d" % i for i in range(2000)], np.zeros((2000, 8), np.float32))
+    assert os.path.exists(str(tmp_path / "g.umprfeat") + ".keys.json") and big.rows_of(["id001999"]).tolist() == [1999]

@@ -70,6 +70,8 @@ SIGNATURES = {
     "umpr_loss_bwd": [P, P, P, P, P, P, P, I, I, F, P, P, P, P, P, P],
     "umpr_tanh_bwd": [P, P, L, P, P],
     "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
+    "umpr_collate_ids": [P, P, L, I, L, P, P],
+    "umpr_feature_gather": [P, P, L, L, I, L, P, P],
     "umpr_step_workspace_bytes": [P, P, I, P],
     "umpr_step_comm": [P, P, L, L],
     "umpr_step_profile_begin": [C.c_char_p],
