@@ -150,7 +150,7 @@ int umpr_tc_gemm_tn(const float* A, long lda, const float* B, long ldb, float* C
 int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, int P, unsigned long long* rowkey,
                     unsigned long long* colkey, float* soft_u, float* soft_i, float* t_u, float* t_i, int32_t* arg_u,
                     int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
-/* tensor-core form of umpr_coattn_fwd (P <= 512): operands pre-split into bf16 hi|lo images; one CTA per sample issues two tcgen05
+/* tensor-core form of umpr_coattn_fwd (at most 2560 valid positions per sample and side): operands pre-split into bf16 hi|lo images; one CTA per sample issues two tcgen05
  * products per tile pair (S and S^T, so row and column maxima are per-thread scans) in two passes - maxima, then every value
  * within the 3xBF16 error bound of its final maximum - and the surviving near-ties are re-scored with exact fp32 dot products
  * (the arg-max routes the gradient).  scratch: umpr_workspace_bytes("coattn_fwd_tc", B, P), 16-byte aligned.
@@ -159,7 +159,7 @@ int umpr_coattn_fwd(const float* gu, const float* gi, const float* giM, int B, i
  * sentence's length are exactly zero, model.py:20): only the valid rows are multiplied, their exact 0 enters each maximum
  * analytically.  NULL: all rows are treated as valid. */
 int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float* giM, int B, int P, const int32_t* cst_u, int S_u, int L_u,
-                       const int32_t* cst_i, int S_i, int L_i, int pv_max /* most valid rows of any sample and side; the limit of 512
+                       const int32_t* cst_i, int S_i, int L_i, int pv_max /* most valid rows of any sample and side; the limit of 2560
                        applies to it (to P without tables) */, void* scratch, float* soft_u, float* soft_i, float* t_u, float* t_i,
                        int32_t* arg_u, int32_t* arg_i, float* atte_u, float* atte_i, void* stream);
 /* dgu, dgi (without the dgiM·M^T term), dgiM: (B,P,128).  d_* inputs may be NULL.  cst_* as in umpr_coattn_fwd_tc: with them, rows

@@ -288,3 +288,43 @@ def test_flat_trainer_steps_through_the_native_path():
     # the last step's gradient bucket - which depends on the two earlier updates - to float-atomics noise)
     assert float((flats[0] - flats[1]).abs().max()) <= 3 * 1e-6 * 2.01
     assert float((grads[0] - grads[1]).abs().max() / grads[1].abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("workload,B,L", [("music_small_r", 8, 64), ("music_full", 8, 48)])
+def test_training_with_more_than_512_valid_positions_vs_oracle(workload, B, L):
+    """Samples whose valid positions exceed one 512-position co-attention pass (here 20 full sentences of L tokens: 1280 / 960 valid
+    positions, 10 / 8 column tiles): the tensor-core affinity kernel walks all tile pairs, candidates of a column are carried across
+    the row tiles in global memory.  Forward, loss and every gradient against the oracle, routing handed over and checked."""
+    import numpy as np
+    from umpr_b200 import functional as F
+    from umpr_b200 import synthetic as syn
+    vocab = 3000
+    table = syn.make_table(vocab, seed=2)
+    batch = list(syn.make_batch(workload, B, vocab=vocab, seed=L, L=L))
+    rs = np.random.RandomState(L)
+    for j in (0, 1):                                                     # half of the samples: every sentence at full length
+        batch[3 + j][: B // 2] = L
+        batch[j][: B // 2] = torch.from_numpy(rs.randint(3, vocab, size=tuple(batch[j][: B // 2].shape)))
+    batch = tuple(batch)
+    model = syn.build_model(workload, table, seed=1, device=DEV)
+    with torch.no_grad():
+        model.review_net.r_net.M.mul_(0.05)
+    model.train()
+    F.ROUTING_LOG = []
+    try:
+        pred, loss = model(*batch)
+        log = F.ROUTING_LOG
+    finally:
+        F.ROUTING_LOG = None
+    loss.backward()
+    picks = {"coattn": [(a[0].cpu(), a[1].cpu()) for k, a in log if k == "coattn"], "cnet": [a.cpu() for k, a in log if k == "cnet"]}
+    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    rno = syn.WORKLOADS[workload]["review_net_only"]
+    with orc.routed(picks) as r:
+        p_ref, l_ref, g_ref = orc.umpr_loss_and_grads(params, batch, review_net_only=rno, impl="lib")
+    assert r.margin["coattn"] <= 2e-5 and r.margin["cnet"] <= 2e-5, r.margin
+    assert_close(pred, p_ref, TOL, "prediction")
+    assert_close(loss, l_ref, TOL, "loss")
+    for k, p in model.named_parameters():
+        if p.requires_grad:
+            _check_grad(k, p.grad if p.grad is not None else torch.zeros_like(p), g_ref[k])

@@ -61,7 +61,8 @@ struct Cand4 {
 constexpr int CI_TILE = 128 * 128;          // bytes of one [128][64 bf16] tile
 constexpr int CI_IMG = 4 * CI_TILE;         // [kb 2][hi|lo][128][128 B]: a 128-row, K=128 operand image
 constexpr int C2_THREADS = 320;
-constexpr int C2_MAXP = 512;
+constexpr int C2_MAXP = 2560;               // valid positions per sample and side: 20 tiles of 128 (S = 20 sentences of L = 128, BASELINE configs[4])
+constexpr int C2_MAXS = 512;                // sentences per sample
 
 // Valid-position bookkeeping of one side of one sample.  Inputs that come out of ImprovedRnn have exactly-zero rows at and beyond each
 // sentence's length (model.py:20); their affinity entries are exactly 0, so only the VALID rows are compacted into the operand
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256) coattn_images_kernel(const float* __restr
                                                             int S_b, int L_b, unsigned char* __restrict__ imgA,
                                                             unsigned char* __restrict__ imgB, float* __restrict__ n2a, float* __restrict__ n2b,
                                                             int* __restrict__ posA, int* __restrict__ posB, int* __restrict__ meta) {
-  __shared__ int sb[C2_MAXP + 1];
+  __shared__ int sb[C2_MAXS + 1];
   const int t = blockIdx.x, b = blockIdx.y, which = blockIdx.z, tid = threadIdx.x;
   const int* cst = which ? cst_b : cst_a;
   const int S_ = which ? S_b : S_a, L_ = which ? L_b : L_a;
@@ -127,9 +128,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   extern __shared__ unsigned char raw[];
   __shared__ C2Bars bars;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_an[C2_MAXP], s_bn[C2_MAXP], s_rowmax[C2_MAXP], s_colmax[C2_MAXP];
-  __shared__ float4 s_cv[C2_MAXP];
-  __shared__ int4 s_ci[C2_MAXP];
+  // per-position state: the running maxima stay in shared memory (20 KB at the limit of 2560 positions); row norms are read from
+  // global memory once per tile pair, and the column candidates of pass 1 are parked in the output arrays cc_v / cc_i themselves
+  // (each column is owned by ONE thread for the whole kernel, so there is no sharing to order)
+  __shared__ float s_rowmax[C2_MAXP], s_colmax[C2_MAXP];
   __shared__ float red[32];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   unsigned char* a_img = base;                  // giM tile of the current i-tile
@@ -146,15 +148,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   }
   if (warp == 9) tmem_alloc(&tmem_slot, 512);
   float amax = 0.f;
-  for (int p = tid; p < C2_MAXP; p += C2_THREADS) {
-    const float an = p < Pa ? sqrtf(n2a[(size_t)b * P + p]) : 0.f;
-    s_an[p] = an;
-    s_bn[p] = p < Pb ? sqrtf(n2b[(size_t)b * P + p]) : 0.f;
+  for (int p = tid; p < Pa; p += C2_THREADS) amax = fmaxf(amax, n2a[(size_t)b * P + p]);
+  for (int p = tid; p < Tb * 128; p += C2_THREADS) {
     s_colmax[p] = -INFINITY;
-    s_cv[p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    s_ci[p] = make_int4(-1, -1, -1, -1);
-    amax = fmaxf(amax, an);
+    if (p < Pb) {
+      cc_v[(size_t)b * P + p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      cc_i[(size_t)b * P + p] = make_int4(-1, -1, -1, -1);
+    }
   }
+  amax = sqrtf(amax);
   amax = block_max(amax, red);              // max_i |giM_i| of the sample: bound for the column-side tolerance
   tc_fence_before();
   __syncthreads();
@@ -176,13 +178,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
 #pragma unroll 1
         for (int jt = 0; jt < Tb; ++jt, ++n) {
           const int s = n & 1;
-          const int own = (is_t ? jt : it) * 128 + r;                // the (compact) row i / column j this thread scans (< 512)
+          const int own = (is_t ? jt : it) * 128 + r;                // the (compact) row i / column j this thread scans
           const int o0 = (is_t ? it : jt) * 128;                     // first index of the scanned direction
           const int nv = min(128, (is_t ? Pa : Pb) - o0);
-          const float tau = is_t ? CA_EPS * s_bn[own] * amax : CA_EPS * s_an[own] * CA_GNORM;
+          const float own_norm = own < Pown ? sqrtf((is_t ? n2b : n2a)[(size_t)b * P + own]) : 0.f;
+          const float tau = is_t ? CA_EPS * own_norm * amax : CA_EPS * own_norm * CA_GNORM;
           if (pass == 1) {
             if (is_t) {
-              const float4 v = s_cv[own]; const int4 id = s_ci[own];
+              float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); int4 id = make_int4(-1, -1, -1, -1);
+              if (own < Pown) { v = cc_v[(size_t)b * P + own]; id = cc_i[(size_t)b * P + own]; }
               cd.v[0] = v.x; cd.v[1] = v.y; cd.v[2] = v.z; cd.v[3] = v.w;
               cd.id[0] = id.x; cd.id[1] = id.y; cd.id[2] = id.z; cd.id[3] = id.w;
               thr = s_colmax[own] - tau;
@@ -231,8 +235,8 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
               (is_t ? cc_v : rc_v)[o] = make_float4(cd.v[0], cd.v[1], cd.v[2], cd.v[3]);
               (is_t ? cc_i : rc_i)[o] = make_int4(cd.id[0], cd.id[1], cd.id[2], cd.id[3]);
             } else if (is_t) {
-              s_cv[own] = make_float4(cd.v[0], cd.v[1], cd.v[2], cd.v[3]);
-              s_ci[own] = make_int4(cd.id[0], cd.id[1], cd.id[2], cd.id[3]);
+              cc_v[(size_t)b * P + own] = make_float4(cd.v[0], cd.v[1], cd.v[2], cd.v[3]);
+              cc_i[(size_t)b * P + own] = make_int4(cd.id[0], cd.id[1], cd.id[2], cd.id[3]);
             }
           }
         }
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(256) coattn_resolve_kernel(const float* __rest
 
 using namespace umpr;
 
-// scratch (16-byte aligned): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][posA B*P i32][posB B*P i32][meta 4*B i32]
+// scratch (16-byte aligned, umpr_workspace_bytes("coattn_fwd_tc", B, P): sized for T = ceil(min(P, 2560) / 128)): [imgA B*T*64 KB][imgB B*T*64 KB][n2a B*P f32][n2b B*P f32][posA B*P i32][posB B*P i32][meta 4*B i32]
 // [rc_v][rc_i][cc_v][cc_i] (float4/int4 per (b,p)),  T = ceil(pv_max/128): 2*B*T*65536 + 4*B*P*4 + 16*B + 4*B*P*16 + 256 bytes.
 // cst_u / cst_i (optional, both or neither): exclusive prefix sums of the sentence lengths of the user / item side (S_x sentences of
 // L_x positions per sample, S_x*L_x == P) for inputs whose rows beyond each sentence's length are exactly zero - only the valid rows
@@ -445,7 +449,7 @@ extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float*
   if (B > 65535) return fail_arg("coattn_fwd_tc: batch %d > 65535", B);
   if (!cst_u || pv_max <= 0 || pv_max > P) pv_max = P;
   if (pv_max > C2_MAXP) return fail_arg("coattn_fwd_tc: %d valid positions per sample > %d (use umpr_coattn_fwd)", pv_max, C2_MAXP);
-  if (P > 16384 || S_u > C2_MAXP || S_i > C2_MAXP) return fail_arg("coattn_fwd_tc: P=%d / S=%d,%d too large", P, S_u, S_i);
+  if (P > 16384 || S_u > C2_MAXS || S_i > C2_MAXS) return fail_arg("coattn_fwd_tc: P=%d / S=%d,%d too large", P, S_u, S_i);
   if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_fwd_tc: length tables must be given for both sides or neither");
   if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
     return fail_arg("coattn_fwd_tc: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);

@@ -93,7 +93,8 @@ extern "C" int umpr_comm_destroy(void* comm) {
 extern "C" int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes) {
   if (!entry || !bytes) return fail_arg("workspace_bytes: NULL argument");
   if (!strcmp(entry, "coattn_fwd_tc")) {
-    const long T = 4;                           // images are sized for the limit of 512 (valid) positions per sample
+    const long pv = b < 2560 ? b : 2560;        // images are sized for min(P, 2560) (valid) positions per sample: 20 tiles at most
+    const long T = (pv + 127) / 128;
     *bytes = 2ll * a * T * 65536 + 4ll * a * b * 4 + 16ll * a + 4ll * a * b * 16 + 256;
   } else if (!strcmp(entry, "cnet_conv_fwd_tc")) {
     *bytes = 197632ll + 16ll * a;

@@ -354,9 +354,9 @@ class _CoAttnFn(Function):
         dev = gu.device
         giM = torch.empty_like(gi)
         ok_plans = plans is not None and all(pl is not None and pl.L <= 128 and pl.N % B == 0 and (pl.N // B) * pl.L == P for pl in plans)
-        # the tensor-core kernels handle 512 positions per sample; with the plans the limit applies to the VALID positions
+        # the tensor-core kernels handle 2560 positions per sample; with the plans the limit applies to the VALID positions
         pv_max = max(pl.max_valid_per_sample(B) for pl in plans) if ok_plans else P
-        use_tc = TENSOR_CORE_COATTN and pv_max <= 512 and P <= 16384
+        use_tc = TENSOR_CORE_COATTN and pv_max <= 2560 and P <= 16384
         use_rows = use_tc and ok_plans
         ctx.rows_i = plans[1] if use_rows else None       # giM / dgi rows beyond each sentence's length are never read: skip them
         sgemm(gi, (D, 1), M, (D, 1), giM, D, B * P, D, D, rows=ctx.rows_i)

@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .plan import PackPlan, build_schedule, upload_int32
 
-MAX_VALID = 512          # valid positions per sample the tensor-core co-attention handles (csrc/coattn_tc.cu)
+MAX_VALID = 2560         # valid positions per sample the tensor-core co-attention handles (csrc/coattn_tc.cu): S=20 sentences of L=128
 
 
 def _gru(gru):
