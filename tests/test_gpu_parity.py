@@ -482,7 +482,8 @@ def test_feature_cache_feeds_the_visual_tail(tmp_path):
     assert torch.equal(got.cpu(), want)
     # through the model: collate with the store vs. the same features passed explicitly
     c = cases.COLLATE_CASES["collate_a"]
-    samples = [(s[0], s[1], s[2], names[b], s[4]) for b, s in enumerate(cases.make_collate_case(c) + cases.make_collate_case(dict(c, seed=77)))][:B]
+    ragged = (cases.make_collate_case(c) + cases.make_collate_case(dict(c, seed=77)))[:B]
+    samples = [(s[0], s[1], s[2], names[b], s[4]) for b, s in enumerate(ragged)]
     batch = collate(samples, DEV, feature_store=store)
     table = syn.make_table(600, seed=2)
     m = syn.build_model("yelp_full", table, seed=1, device=DEV)

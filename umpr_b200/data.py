@@ -88,7 +88,7 @@ class FeatureStore:
         return flat.reshape(a.shape)
 
     def to_device(self, device):
-        self.table = torch.from_numpy(np.ascontiguousarray(self.features)).to(device)
+        self.table = torch.from_numpy(np.array(self.features, dtype=np.float32, copy=True)).to(device)
         return self
 
     def gather(self, rows, device=None):
