@@ -65,19 +65,29 @@ class _PinnedRing:
 
     def __init__(self, slots=32, slot_ints=1 << 17):
         # one pinned allocation up front: cudaHostAlloc inside the training loop costs milliseconds and synchronises
-        self.pool = torch.empty(slots * slot_ints, dtype=torch.int32).pin_memory()
-        self.bufs = [self.pool[i * slot_ints:(i + 1) * slot_ints] for i in range(slots)]
-        self.events, self.i, self.slots = [None] * slots, 0, slots
+        self.slots = slots
+        self._alloc(slot_ints)
+
+    def _alloc(self, slot_ints):
+        self.slot_ints = slot_ints
+        self.pool = torch.empty(self.slots * slot_ints, dtype=torch.int32).pin_memory()
+        self.bufs = [self.pool[i * slot_ints:(i + 1) * slot_ints] for i in range(self.slots)]
+        self.events, self.i = [None] * self.slots, 0
 
     def upload(self, arr, device):
         import numpy as np
+        n = int(arr.size)
+        if n > self.slot_ints:
+            # a plan larger than a slot (batches of several thousand samples): ONE re-allocation of the whole ring with slots of
+            # twice the size needed - not one cudaHostAlloc per slot as the ring rotates.  In-flight copies finish first.
+            for e in self.events:
+                if e is not None:
+                    e.synchronize()
+            self._alloc(1 << (2 * n - 1).bit_length())
         i = self.i
         self.i = (i + 1) % self.slots
-        n = int(arr.size)
         if self.events[i] is not None:
             self.events[i].synchronize()
-        if self.bufs[i].numel() < n:                     # oversized plan: give this slot its own buffer
-            self.bufs[i] = torch.empty(n, dtype=torch.int32).pin_memory()
         host = self.bufs[i][:n]
         host.numpy()[:] = np.asarray(arr, dtype=np.int32).reshape(-1)
         dev = host.to(device, non_blocking=True)
