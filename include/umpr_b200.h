@@ -266,6 +266,14 @@ int umpr_adam_step(float* params, const float* grads, float* exp_avg, float* exp
                                                the number of replicas that received a chunk (DataParallel's loss.mean(), main.py:34) */,
                    void* stream);
 
+/* ---- host-side integer bookkeeping of the packing (model.py:18-21), no CUDA: pack plan, valid-row tile tables and tile schedules from
+ * the reference's own sort result (sorted_idx / sorted_len = torch.sort(lengths.cpu(), descending=True)); see umpr_b200/plan.py ---- */
+int umpr_plan_build(const int64_t* sorted_idx, const int64_t* sorted_len, long n, int R, int32_t* plan, long plan_ints, int64_t* tokens_out);
+int umpr_plan_table(const int64_t* sorted_idx, const int64_t* lengths, long n, int L, int extra /* 0: S-Net rows, 2: convolution guard rows */,
+                    int32_t* table /* capacity 2*(n+1) */, int32_t* n_tiles_out);
+int umpr_plan_schedule(const int64_t* const* tile_lens, const int32_t* n_tiles, int n_seg, int n_ctas, int32_t* sched, long sched_ints,
+                       int32_t* n_queues_out);
+
 /* ---- the data formats either side of the path ----
  * collate on device (dataset.py:122-131,163-171): expands ragged token lists - flat int32 tokens + the (n_sent + 1) exclusive prefix sum
  * of the per-slot token counts - into the padded (n_sent, L) int64 id tensor the reference's collate emits (pad_id beyond each

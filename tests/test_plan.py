@@ -166,3 +166,29 @@ def test_prefetched_plan_uploads_plan_and_tables_in_one_buffer():
     # a side below the tensor-core threshold (2 * 5 = 10 user->item sentences): CUDA-core tiles, no tables are prepared for it
     tiny = prepare_batch(syn.make_batch("music_full", 2, vocab=500, seed=1), "cpu")[5]._umpr_plan
     assert tiny.R != 128 and getattr(tiny, "_snet_np", None) is None
+
+
+@pytest.mark.parametrize("n,L", [(20480, 20), (5120, 20), (300, 33), (129, 128), (7, 5)])
+def test_native_plan_builders_equal_the_numpy_specification(n, L):
+    """csrc/plan_host.cu (umpr_plan_build / umpr_plan_table / umpr_plan_schedule) against the numpy forms in plan.py: identical pack
+    plan, S-Net and convolution tile tables, and GRU tile schedules."""
+    from umpr_b200 import plan as P
+    rs = np.random.RandomState(n + L)
+    lens = torch.from_numpy(rs.randint(1, L + 1, size=n).astype(np.int64))
+    lens[torch.from_numpy(rs.rand(n) < 0.3)] = 1
+    res = []
+    for native in (True, False):
+        P.NATIVE_PLAN = native
+        try:
+            p = P.PackPlan(lens, L, "cpu", tile_rows=128)
+            res.append((p, p._snet_host(), p._cnet_host() if L <= 126 else None,
+                        [P.build_schedule([p.tile_len, p.tile_len[::2]], c) for c in (1, 3, 74)]))
+        finally:
+            P.NATIVE_PLAN = True
+    (a, ta, ca, sa), (b, tb, cb, sb) = res
+    assert torch.equal(a.host, b.host) and (a.tokens, a.n_slabs, a.n_tiles) == (b.tokens, b.n_slabs, b.n_tiles)
+    assert ta[1] == tb[1] and np.array_equal(ta[0], tb[0])
+    if ca is not None:
+        assert ca[1] == cb[1] and np.array_equal(ca[0], cb[0])
+    for x, y in zip(sa, sb):
+        assert x[1] == y[1] and np.array_equal(x[0], y[0])

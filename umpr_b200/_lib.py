@@ -70,6 +70,9 @@ SIGNATURES = {
     "umpr_loss_bwd": [P, P, P, P, P, P, P, I, I, F, P, P, P, P, P, P],
     "umpr_tanh_bwd": [P, P, L, P, P],
     "umpr_adam_step": [P, P, P, P, P, L, F, F, F, F, I, F, P, P],
+    "umpr_plan_build": [P, P, L, I, P, L, P],
+    "umpr_plan_table": [P, P, L, I, I, P, P],
+    "umpr_plan_schedule": [P, P, I, I, P, L, P],
     "umpr_collate_ids": [P, P, L, I, L, P, P],
     "umpr_feature_gather": [P, P, L, L, I, L, P, P],
     "umpr_step_workspace_bytes": [P, P, I, P],

@@ -160,7 +160,33 @@ __global__ void __launch_bounds__(256) coattn_pool_kernel(const unsigned long lo
   }
 }
 
-// backward of model.py:50-55 with respect to gu, gi (through giM = gi·M; the M products are GEMMs outside)
+// in-place exclusive prefix sum of a[0..n) by one 256-thread block (a[n] receives the total); `tmp` = 257 ints of shared memory
+__device__ __forceinline__ void block_excl_scan(int* a, int n, int* tmp) {
+  const int tid = threadIdx.x;
+  const int per = (n + 255) / 256, lo = tid * per, hi = min(n, lo + per);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  tmp[tid + 1] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    tmp[0] = 0;
+    for (int i = 1; i <= 256; ++i) tmp[i] += tmp[i - 1];
+  }
+  __syncthreads();
+  int run = tmp[tid];
+  for (int i = lo; i < hi; ++i) { const int c = a[i]; a[i] = run; run += c; }
+  if (tid == 255) a[n] = tmp[256];
+  __syncthreads();
+}
+
+// backward of model.py:50-55 with respect to gu, gi (through giM = gi·M; the M products are GEMMs outside).
+// One CTA per sample.  dA is sparse - one entry per row maximum and one per column maximum - so
+//     dgu[j]  = add_u[j] + soft_u[j] d_atte_u + w_j giM[arg_u[j]] + sum over {i : arg_i[i] = j} of v_i giM[i]
+//     dgiM[i] = v_i gu[arg_i[i]]                                  + sum over {j : arg_u[j] = i} of w_j gu[j]
+//     dgi[i]  = add_i[i] + soft_i[i] d_atte_i
+// The sums over the inverse arg-max relations are GATHERS here: the relations are inverted per sample in shared memory (counting
+// sort), every output row is written exactly once and no global atomics are issued (the first version scattered them with 128
+// atomic adds per entry).  Independent row loads are issued in batches so that several are in flight per warp.
 __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict__ gu, const float* __restrict__ gi,
                                                          const float* __restrict__ giM, const float* __restrict__ soft_u,
                                                          const float* __restrict__ soft_i, const float* __restrict__ t_u,
@@ -178,10 +204,17 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   float* dau = smem + 2 * P4;  // [128]
   float* dai = dau + D;        // [128]
   float* red = dai + D;        // [32]
+  int* tmp = reinterpret_cast<int*>(red + 32);          // [260] scan scratch
+  int* off_i = tmp + 260;      // [P4 + 4] list of item row i = user positions j with arg_u[j] == i: ent_i[off_i[i] .. off_i[i+1])
+  int* off_u = off_i + P4 + 4; // [P4 + 4] list of user row j = item positions i with arg_i[i] == j
+  int* cur_i = off_u + P4 + 4; // [P4] fill cursors
+  int* cur_u = cur_i + P4;
+  int* ent_i = cur_u + P4;     // [P4]
+  int* ent_u = ent_i + P4;     // [P4]
   // with length tables: rows at or beyond a sentence's length are exactly zero (model.py:20) and are neither read nor written
   // (their gradients are never used); dgiM alone gets explicit zeros there because the dM reduction runs over every row
-  unsigned char* mu = reinterpret_cast<unsigned char*>(red + 32);   // [P4] user-side row is valid
-  unsigned char* mi = mu + P4;                                       // [P4] item-side row is valid
+  unsigned char* mu = reinterpret_cast<unsigned char*>(ent_u + P4);   // [P4] user-side row is valid
+  unsigned char* mi = mu + P4;                                         // [P4] item-side row is valid
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t bp = (size_t)b * P;
   if (tid < D) {
@@ -196,9 +229,10 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
       c = (p - si * L_i) < cst_i[(size_t)b * S_i + si + 1] - cst_i[(size_t)b * S_i + si];
     }
     mu[p] = a; mi[p] = c;
+    off_i[p] = 0; off_u[p] = 0;
   }
   __syncthreads();
-  // ds[p] = d_soft[p] + <g[p], d_atte>
+  // ds[p] = d_soft[p] + <g[p], d_atte>: four rows per warp and iteration, their loads issued together
   for (int side = 0; side < 2; ++side) {
     const float* g = (side ? gi : gu) + bp * D;
     const float* da = side ? dai : dau;
@@ -206,13 +240,23 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
     float* dst = side ? vi : wu;
     const float4 d4 = *reinterpret_cast<const float4*>(da + lane * 4);
     const unsigned char* ok = side ? mi : mu;
-#pragma unroll 4
-    for (int p = warp; p < P; p += 8) {
-      if (!ok[p]) { if (lane == 0) dst[p] = dso ? dso[bp + p] : 0.f; continue; }
-      const float4 v = *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4);
-      float s = v.x * d4.x + v.y * d4.y + v.z * d4.z + v.w * d4.w;
-      s = warp_sum(s);
-      if (lane == 0) dst[p] = s + (dso ? dso[bp + p] : 0.f);
+    for (int p0 = warp; p0 < P; p0 += 32) {
+      float4 v[4];
+      bool live[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = p0 + 8 * q;
+        live[q] = p < P && ok[p];
+        v[q] = live[q] ? *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = p0 + 8 * q;
+        if (p >= P) continue;
+        float s = v[q].x * d4.x + v[q].y * d4.y + v[q].z * d4.z + v[q].w * d4.w;
+        s = warp_sum(s);
+        if (lane == 0) dst[p] = (live[q] ? s : 0.f) + (dso ? dso[bp + p] : 0.f);
+      }
     }
   }
   __syncthreads();
@@ -230,47 +274,83 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
     }
     __syncthreads();
   }
-  // dense part (every row written exactly once)
+  // invert the two arg-max relations (entries with a zero weight or an invalid end carry nothing and are left out)
+  for (int p = tid; p < P; p += 256) {
+    if (wu[p] != 0.f && mu[p]) { const int a = arg_u[bp + p]; if (mi[a]) atomicAdd(&off_i[a], 1); }
+    if (vi[p] != 0.f && mi[p]) { const int a = arg_i[bp + p]; if (mu[a]) atomicAdd(&off_u[a], 1); }
+  }
+  __syncthreads();
+  block_excl_scan(off_i, P, tmp);
+  block_excl_scan(off_u, P, tmp);
+  for (int p = tid; p < P; p += 256) { cur_i[p] = off_i[p]; cur_u[p] = off_u[p]; }
+  __syncthreads();
+  for (int p = tid; p < P; p += 256) {
+    if (wu[p] != 0.f && mu[p]) { const int a = arg_u[bp + p]; if (mi[a]) ent_i[atomicAdd(&cur_i[a], 1)] = p; }
+    if (vi[p] != 0.f && mi[p]) { const int a = arg_i[bp + p]; if (mu[a]) ent_u[atomicAdd(&cur_u[a], 1)] = p; }
+  }
+  __syncthreads();
+  // every valid row once: two rows per warp and iteration
   const float4 dau4 = *reinterpret_cast<const float4*>(dau + lane * 4);
   const float4 dai4 = *reinterpret_cast<const float4*>(dai + lane * 4);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int p = warp; p < P; p += 8) {
-    if (mu[p]) {
-      const float su = soft_u[bp + p], w = wu[p];
-      const int a = arg_u[bp + p];
-      const float4 m = mi[a] ? *reinterpret_cast<const float4*>(giM + (bp + a) * D + lane * 4) : zero4;
-      // add_u / add_i: gradient of the same rows from another consumer of gu / gi (S-Net), folded in here instead of a separate add pass
-      const float4 e = add_u ? *reinterpret_cast<const float4*>(add_u + (bp + p) * D + lane * 4) : zero4;
-      *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) =
-          make_float4(e.x + su * dau4.x + w * m.x, e.y + su * dau4.y + w * m.y, e.z + su * dau4.z + w * m.z, e.w + su * dau4.w + w * m.w);
+  auto row = [&](const float* base, int p) { return *reinterpret_cast<const float4*>(base + (bp + p) * D + lane * 4); };
+  auto fma4 = [](float4& acc, float s, const float4 v) { acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w; };
+  for (int p0 = warp; p0 < P; p0 += 16) {
+    float4 m[2], eu[2], u[2], ei[2];
+    bool vu[2], vv[2];
+    int pa[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int p = p0 + 8 * q;
+      pa[q] = p;
+      vu[q] = p < P && mu[p];
+      vv[q] = p < P && mi[p];
+      m[q] = eu[q] = u[q] = ei[q] = zero4;
+      if (vu[q]) {
+        const int a = arg_u[bp + p];
+        if (wu[p] != 0.f && mi[a]) m[q] = row(giM, a);
+        if (add_u) eu[q] = row(add_u, p);
+      }
+      if (vv[q]) {
+        const int a = arg_i[bp + p];
+        if (vi[p] != 0.f && mu[a]) u[q] = row(gu, a);
+        if (add_i) ei[q] = row(add_i, p);
+      }
     }
-    if (mi[p]) {
-      const float si = soft_i[bp + p], v = vi[p];
-      const int a = arg_i[bp + p];
-      const float4 u = mu[a] ? *reinterpret_cast<const float4*>(gu + (bp + a) * D + lane * 4) : zero4;
-      *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = make_float4(v * u.x, v * u.y, v * u.z, v * u.w);
-      const float4 e = add_i ? *reinterpret_cast<const float4*>(add_i + (bp + p) * D + lane * 4) : zero4;
-      *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = make_float4(e.x + si * dai4.x, e.y + si * dai4.y, e.z + si * dai4.z, e.w + si * dai4.w);
-    } else {
-      *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  // scatter part
-  for (int p = warp; p < P; p += 8) {
-    const float w = wu[p];
-    if (w != 0.f && mu[p] && mi[arg_u[bp + p]]) {
-      const float4 u = *reinterpret_cast<const float4*>(gu + (bp + p) * D + lane * 4);
-      float* d = dgiM + (bp + arg_u[bp + p]) * D + lane * 4;
-      atomicAdd(d, w * u.x); atomicAdd(d + 1, w * u.y); atomicAdd(d + 2, w * u.z); atomicAdd(d + 3, w * u.w);
-    }
-    const float v = vi[p];
-    if (v != 0.f && mi[p] && mu[arg_i[bp + p]]) {
-      const float4 m = *reinterpret_cast<const float4*>(giM + (bp + p) * D + lane * 4);
-      float* d = dgu + (bp + arg_i[bp + p]) * D + lane * 4;
-      atomicAdd(d, v * m.x); atomicAdd(d + 1, v * m.y); atomicAdd(d + 2, v * m.z); atomicAdd(d + 3, v * m.w);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int p = pa[q];
+      if (p >= P) continue;
+      if (vu[q]) {
+        float4 acc = eu[q];
+        fma4(acc, soft_u[bp + p], dau4);
+        fma4(acc, wu[p], m[q]);
+        const int e1 = off_u[p + 1];
+        for (int e = off_u[p]; e < e1; e += 2) {          // item rows whose maximum sits in this user position
+          const int i0 = ent_u[e], i1 = e + 1 < e1 ? ent_u[e + 1] : -1;
+          const float4 r0 = row(giM, i0), r1 = i1 >= 0 ? row(giM, i1) : zero4;
+          fma4(acc, vi[i0], r0);
+          if (i1 >= 0) fma4(acc, vi[i1], r1);
+        }
+        *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) = acc;
+      }
+      if (vv[q]) {
+        float4 acc = zero4;
+        fma4(acc, vi[p], u[q]);
+        const int e1 = off_i[p + 1];
+        for (int e = off_i[p]; e < e1; e += 2) {          // user positions whose maximum sits in this item row
+          const int j0 = ent_i[e], j1 = e + 1 < e1 ? ent_i[e + 1] : -1;
+          const float4 r0 = row(gu, j0), r1 = j1 >= 0 ? row(gu, j1) : zero4;
+          fma4(acc, wu[j0], r0);
+          if (j1 >= 0) fma4(acc, wu[j1], r1);
+        }
+        *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = acc;
+        float4 g2 = ei[q];
+        fma4(g2, soft_i[bp + p], dai4);
+        *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = g2;
+      } else {
+        *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
+      }
     }
   }
 }
@@ -308,7 +388,8 @@ extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* gi
   if ((cst_u == nullptr) != (cst_i == nullptr)) return fail_arg("coattn_bwd: length tables must be given for both sides or neither");
   if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
     return fail_arg("coattn_bwd: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);
-  const size_t sm = sizeof(float) * (2 * ((P + 3) & ~3) + 2 * D + 32) + 2 * ((P + 3) & ~3);
+  const size_t P4 = (size_t)((P + 3) & ~3);
+  const size_t sm = sizeof(float) * (2 * P4 + 2 * D + 32) + sizeof(int) * (260 + 2 * (P4 + 4) + 4 * P4) + 2 * P4;
   if (sm > 200 * 1024) return fail_arg("coattn_bwd: P=%d too large", P);
   if (sm > 48 * 1024) cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   coattn_bwd_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(gu, gi, giM, soft_u, soft_i, t_u, t_i, arg_u, arg_i, d_soft_u, d_soft_i,

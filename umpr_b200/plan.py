@@ -29,7 +29,40 @@ def choose_tile_rows(n_seq: int, n_sm: int) -> int:
     return 32
 
 
+NATIVE_PLAN = True     # integer bookkeeping in C (csrc/plan_host.cu) when the library is there; False = the numpy forms below (the specification)
+
+
+def _native_lib():
+    if not NATIVE_PLAN:
+        return None
+    try:
+        return _lib.load()
+    except RuntimeError:
+        return None
+
+
 def build_schedule(tile_lens, n_ctas: int):
+    """Tile queues of one fused GRU launch - ``umpr_plan_schedule`` (C) or ``build_schedule_np``; see the latter for the layout."""
+    lib = _native_lib()
+    if lib is None:
+        return build_schedule_np(tile_lens, n_ctas)
+    import ctypes as C
+    import numpy as np
+    arrs = [np.ascontiguousarray(t, dtype=np.int64).reshape(-1) for t in tile_lens]
+    T = sum(a.size for a in arrs)
+    if T == 0:
+        raise RuntimeError("umpr_b200: empty GRU launch")
+    G = max(1, min(int(n_ctas), T))
+    out = np.empty(2 * G + 1 + T, dtype=np.int32)
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    nts = (C.c_int32 * len(arrs))(*[a.size for a in arrs])
+    nq = C.c_int32(0)
+    if lib.umpr_plan_schedule(ptrs, nts, len(arrs), int(n_ctas), out.ctypes.data, out.size, C.byref(nq)) != 0:
+        raise RuntimeError(f"umpr_plan_schedule: {_lib.last_error()}")
+    return out, nq.value
+
+
+def build_schedule_np(tile_lens, n_ctas: int):
     """Tile queues of one fused GRU launch (umpr_gru_fwd_tc / umpr_gru_bwd_tc).
 
     ``tile_lens``: one int sequence per segment (steps of every 128-row tile, already descending inside a segment).
@@ -159,6 +192,14 @@ class PackPlan:
         self.tile_len = tile_len
         self.n_slabs = int(tile_len.sum())
         host = np.empty(3 * rp + self.n_tiles + 1 + self.n_slabs, dtype=np.int32)
+        lib = _native_lib()
+        if lib is not None:
+            import ctypes as C
+            tokens = C.c_int64(0)
+            if lib.umpr_plan_build(si.ctypes.data, sl.ctypes.data, n, R, host.ctypes.data, host.size, C.byref(tokens)) != 0:
+                raise RuntimeError(f"umpr_plan_build: {_lib.last_error()}")
+            self._finish(host, int(tokens.value), upload)
+            return
         host[:n] = si                                                        # seq_of
         host[n:rp] = 0
         host[rp:rp + n] = si[si]                                             # row_of: output row fed by job k (model.py:21)
@@ -168,9 +209,12 @@ class PackPlan:
         host[3 * rp] = 0
         np.cumsum(tile_len, out=host[3 * rp + 1:3 * rp + 1 + self.n_tiles])  # tile_off
         host[3 * rp + 1 + self.n_tiles:] = np.repeat(np.arange(self.n_tiles, dtype=np.int32), tile_len)   # slab_tile
+        self._finish(host, int(sl.sum()), upload)
+
+    def _finish(self, host, tokens, upload):
         self.host = torch.from_numpy(host)
-        self.tokens = int(sl.sum())                                          # T_v: valid tokens
-        self.slots = self.n_slabs * R                                        # token slots actually computed
+        self.tokens = tokens                                                 # T_v: valid tokens
+        self.slots = self.n_slabs * self.R                                   # token slots actually computed
         self._host_np = host
         self.buf = upload_int32(host, self.device) if upload else None      # upload=False: built off-thread, see ensure_uploaded()
 
@@ -223,11 +267,29 @@ class PackPlan:
             setattr(self, key, int((cs[S::S] - cs[:-1:S]).max()))
         return getattr(self, key)
 
+    def _table_native(self, extra):
+        """[tile_sent_off | cstart] by ``umpr_plan_table`` → (int32 array, n_tiles), or None without the library."""
+        lib = _native_lib()
+        if lib is None:
+            return None
+        import ctypes as C
+        import numpy as np
+        buf = np.empty(2 * (self.N + 1), dtype=np.int32)
+        nt = C.c_int32(0)
+        si, ln = self.sorted_indices.numpy(), self.lengths.numpy()
+        if lib.umpr_plan_table(si.ctypes.data, ln.ctypes.data, self.N, self.L, extra, buf.ctypes.data, C.byref(nt)) != 0:
+            raise RuntimeError(f"umpr_plan_table: {_lib.last_error()}")
+        return buf[:nt.value + 1 + self.N + 1], nt.value
+
     def _snet_host(self):
         if getattr(self, "_snet_np", None) is None:
             import numpy as np
             if self.L > 128:
                 raise RuntimeError(f"umpr_b200: S-Net sentence length {self.L} exceeds 128")
+            nat = self._table_native(0)
+            if nat is not None:
+                self._snet_np = nat
+                return self._snet_np
             n = self.N
             row_len = np.empty(n, dtype=np.int64)
             # output row row_of[k] = si[si[k]] holds sequence si[k] (model.py:21), i.e. row si[j] holds sequence j
@@ -253,6 +315,10 @@ class PackPlan:
             import numpy as np
             if self.L + 2 > 128:
                 raise RuntimeError(f"umpr_b200: C-Net sentence length {self.L} exceeds 126")
+            nat = self._table_native(2)
+            if nat is not None:
+                self._cnet_np = nat
+                return self._cnet_np
             n = self.N
             stab, s_nt = self._snet_host()                                   # prefix sums of the lengths are already there
             cstart = stab[s_nt + 1:].astype(np.int64) + 2 * np.arange(n + 1, dtype=np.int64)

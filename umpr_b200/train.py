@@ -53,17 +53,34 @@ class AbiComm:
 
 
 def pin_rank_to_cores(local_rank: int, local_world: int):
-    """Give every rank of a node its own slice of the host cores (one process per GPU): the step is issued by one Python thread plus a
-    plan-prefetch worker, and a rank whose threads get migrated or share a core with another rank's stalls all ranks at the all-reduce."""
+    """Give every rank of a node its own slice of the host cores (one process per GPU): the step is issued by one Python thread next to
+    the plan-prefetch workers, and a rank whose threads get migrated - or share a physical core with another rank's - stalls all ranks
+    at the all-reduce.  Logical CPUs are grouped by physical core (hyper-thread siblings stay together) before they are dealt out."""
     import os
     try:
-        cores = sorted(os.sched_getaffinity(0))
+        cpus = sorted(os.sched_getaffinity(0))
     except AttributeError:
         return None
-    per = len(cores) // max(1, local_world)
+    groups, seen = [], set()
+    for c in cpus:
+        if c in seen:
+            continue
+        sib = {c}
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    sib |= set(range(int(lo), int(hi or lo) + 1))
+        except (OSError, ValueError):
+            pass
+        g = sorted(sib & set(cpus))
+        seen |= set(g)
+        groups.append(g)
+    ordered = [c for g in groups for c in g]             # siblings adjacent: a slice takes whole physical cores first
+    per = len(ordered) // max(1, local_world)
     if per < 1:
         return None
-    mine = cores[local_rank * per:(local_rank + 1) * per]
+    mine = ordered[local_rank * per:(local_rank + 1) * per]
     os.sched_setaffinity(0, mine)
     torch.set_num_threads(max(1, min(per, 4)))
     return mine
@@ -235,37 +252,41 @@ def prepare_batch(batch, device):
 
 
 class PlanPrefetcher:
-    """Iterator over batches that prepares the NEXT batch's pack plans on a worker thread while the current step runs
-    (the data-loader pattern; ``torch.sort`` and numpy release the GIL).  ``for batch in PlanPrefetcher(loader, device): ...``"""
+    """Iterator over batches that prepares the NEXT batches' pack plans on worker threads while the current step runs (the
+    data-loader pattern; ``torch.sort`` and the C plan builders release the GIL).  ``for batch in PlanPrefetcher(loader, device): ...``
+    Batches come out in the loader's order.  The reference's own ``torch.sort`` call is most of a plan's cost (~0.7 ms per review
+    side at batch 1024), so two workers keep up with a 5 ms step even when eight ranks share one host."""
 
-    def __init__(self, batches, device, depth: int = 2):
+    def __init__(self, batches, device, depth: int = 3, workers: int = 2):
         import queue
         import threading
+        from concurrent.futures import ThreadPoolExecutor
         self._q = queue.Queue(maxsize=depth)
         self._done = object()
-        self._err = None
+        self._pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="umpr-plan")
 
-        def work():
+        def feed():                             # pulls from the loader and hands the batches to the pool, in order
             try:
                 for b in batches:
-                    self._q.put(prepare_batch(b, device))
+                    self._q.put(self._pool.submit(prepare_batch, b, device))
             except BaseException as e:          # surfaced on the consumer's thread
-                self._err = e
+                self._q.put(e)
             self._q.put(self._done)
 
-        self._thr = threading.Thread(target=work, daemon=True)
+        self._thr = threading.Thread(target=feed, daemon=True)
         self._thr.start()
 
     def __iter__(self):
         return self
 
     def __next__(self):
-        b = self._q.get()
-        if b is self._done:
-            if self._err is not None:
-                raise self._err
+        f = self._q.get()
+        if f is self._done:
+            self._pool.shutdown(wait=False)
             raise StopIteration
-        return b
+        if isinstance(f, BaseException):
+            raise f
+        return f.result()
 
 
 class AsyncScalarReader:
