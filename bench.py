@@ -84,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.01)
+            self._stop.wait(0.02)
 
     def start(self):
         if self.nv is not None:

@@ -261,9 +261,14 @@ class PlanPrefetcher:
         import queue
         import threading
         from concurrent.futures import ThreadPoolExecutor
+        import sys
         self._q = queue.Queue(maxsize=depth)
         self._done = object()
         self._pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="umpr-plan")
+        # the step is issued by ONE Python thread: with CPython's default 5 ms switch interval a worker in a pure-Python stretch can
+        # keep the GIL for as long as a whole step takes.  0.2 ms bounds what the issuing thread can lose to the workers.
+        if sys.getswitchinterval() > 2e-4:
+            sys.setswitchinterval(2e-4)
 
         def feed():                             # pulls from the loader and hands the batches to the pool, in order
             try:
