@@ -29,6 +29,10 @@ def choose_tile_rows(n_seq: int, n_sm: int) -> int:
     return 32
 
 
+SMS_RESERVED_FOR_COMM = 0   # SMs the R-Net GRU launches leave free (train.FlatTrainer sets it when the gradient all-reduce overlaps the
+                            # backward): the fused GRU kernels are persistent with one CTA per SM and nearly all of its shared memory, so
+                            # an NCCL kernel that starts beside them would otherwise take SMs away from their grid for as long as it waits
+                            # for the slowest rank
 NATIVE_PLAN = True     # integer bookkeeping in C (csrc/plan_host.cu) when the library is there; False = the numpy forms below (the specification)
 
 

@@ -177,9 +177,11 @@ class NativeStep:
             keep += [ids, st, ct, p]
             sides[k] = _lib.StepSide(ids.data_ptr(), p.buf.data_ptr(), st.data_ptr(), ct.data_ptr() if ct is not None else None, s_nt, c_nt,
                                      p.n_tiles, p.n_slabs, B, ids.shape[1], ids.shape[2], p.max_valid_per_sample(B))
+        from . import plan as plan_mod
         n_ctas = max(1, _lib.sm_count(dev) // 2)
+        n_ctas_r = max(1, (_lib.sm_count(dev) - plan_mod.SMS_RESERVED_FOR_COMM) // 2)
         pre = getattr(batch[3], "_umpr_sched", None) if plans[0] is getattr(batch[3], "_umpr_plan", None) else None     # built by the prefetch worker
-        sr, nq_r = pre[0] if pre else build_schedule([plans[0].tile_len, plans[1].tile_len], n_ctas)
+        sr, nq_r = pre[0] if pre else build_schedule([plans[0].tile_len, plans[1].tile_len], n_ctas_r)
         sr = upload_int32(sr, dev)
         sc, nq_c = None, 0
         photos = None

@@ -19,13 +19,18 @@ from . import _lib
 from ._lib import call, ptr
 
 
+COMM_CTAS = 4        # CTAs NCCL may use for the ~1 MB gradient all-reduce (NCCL_MAX_CTAS, set before the communicator is created)
+
+
 class AbiComm:
     """The library's NCCL communicator (C-ABI ``umpr_comm_*``): rank 0 creates the unique id, ``torch.distributed`` carries its 128
     bytes to the other ranks (any backend), every rank joins; ``all_reduce`` sums a flat fp32 CUDA tensor in place on the current stream."""
 
     def __init__(self, rank, world, device, process_group=None):
         import ctypes
-        lib = _lib.load()
+        import os
+        os.environ.setdefault("NCCL_MAX_CTAS", str(COMM_CTAS))      # latency-bound message: a few CTAs are enough, and they must fit
+        lib = _lib.load()                                            # beside the persistent GRU backward (plan.SMS_RESERVED_FOR_COMM)
         buf = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             raw = (ctypes.c_ubyte * 128)()
@@ -147,6 +152,9 @@ class FlatTrainer:
                 self.native = NativeStep(model, with_grads=True)
         # with both, the exchange overlaps the backward: two buckets all-reduced from inside umpr_step (csrc/step.cu, umpr_step_comm)
         self.overlap = self.native is not None and self.comm is not None and os.environ.get("UMPR_OVERLAP", "1") == "1"
+        if self.overlap:
+            from . import plan as plan_mod
+            plan_mod.SMS_RESERVED_FOR_COMM = COMM_CTAS          # the R-Net GRU launches leave these SMs to the all-reduce kernel
 
     def zero_grad(self):
         self.bucket.zero_()
@@ -243,8 +251,10 @@ def prepare_batch(batch, device):
     pl = [getattr(t, "_umpr_plan", None) for t in (ul, il, uil)]
     if pl[0] is not None and pl[1] is not None and pl[0].R == 128 and pl[1].R == 128:
         from .plan import build_schedule
-        n_ctas = max(1, (_lib.sm_count(device) if torch.device(device).type == "cuda" else 148) // 2)
-        sched = [build_schedule([pl[0].tile_len, pl[1].tile_len], n_ctas)]
+        from . import plan as plan_mod
+        n_sm = _lib.sm_count(device) if torch.device(device).type == "cuda" else 148
+        n_ctas = max(1, n_sm // 2)
+        sched = [build_schedule([pl[0].tile_len, pl[1].tile_len], max(1, (n_sm - plan_mod.SMS_RESERVED_FOR_COMM) // 2))]
         if pl[2] is not None and pl[2].R == 128:
             sched.append(build_schedule([pl[2].tile_len, pl[0].tile_len, pl[1].tile_len], n_ctas))
         ul._umpr_sched = sched
