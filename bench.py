@@ -323,8 +323,16 @@ def main():
 
     feed = {"it": None}
 
+    host_t = {"wait_batch": 0.0, "issue": 0.0, "n": 0}
+
     def step_resident(i):
-        trainer.train_step(next(feed["it"]))
+        t0 = time.perf_counter()
+        b = next(feed["it"])
+        t1 = time.perf_counter()
+        trainer.train_step(b)
+        host_t["wait_batch"] += t1 - t0                  # host time waiting for the prefetched batch (plans)
+        host_t["issue"] += time.perf_counter() - t1      # host time inside train_step (asynchronous launches)
+        host_t["n"] += 1
 
     sink = []
     from umpr_b200.train import AsyncScalarReader
@@ -374,7 +382,14 @@ def main():
         _lib.start_timing(only=[top])
     feed["it"] = stream_of(devb, K)
     n0 = trainer.native_steps
+    host_t.update(wait_batch=0.0, issue=0.0, n=0)
     ms, clocks = timed(step_resident, K, ClockSampler(local))
+    host_ms = {"wait_for_batch_ms_per_step": round(1e3 * host_t["wait_batch"] / max(1, host_t["n"]), 3),
+               "issue_ms_per_step": round(1e3 * host_t["issue"] / max(1, host_t["n"]), 3)}
+    if world > 1:
+        hm = torch.tensor([host_ms["wait_for_batch_ms_per_step"], host_ms["issue_ms_per_step"]], device=dev)
+        dist.all_reduce(hm, op=dist.ReduceOp.MAX)
+        host_ms["max_over_ranks"] = [round(float(hm[0]), 3), round(float(hm[1]), 3)]
     launches = _lib.launch_count - launches0
     if native:
         kt = NS.profile_end()[top]
@@ -416,6 +431,7 @@ def main():
                                          ("C-ABI NCCL communicator (umpr_comm_*), 2 buckets [head/attention/conv/C-Net | R-Net GRU], the first all-reduced under the last backward kernel"
                                           if trainer.overlap else ("C-ABI NCCL communicator, after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
                    "host_cores_per_rank": len(cores) if cores else None,
+                   "host_thread": host_ms,
                    "issue": "one native C-ABI call per step (umpr_step) + all-reduce + umpr_adam_step" if native else "autograd Functions over per-kernel C-ABI calls",
                    "host_pipeline": "the next batch's pack plans (torch.sort + int32 plan) are built on a worker thread, like a collate worker; rebuilt every step",
                    "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; 4 rotating input batches"},

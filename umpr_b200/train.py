@@ -152,6 +152,9 @@ class FlatTrainer:
                 self.native = NativeStep(model, with_grads=True)
         # with both, the exchange overlaps the backward: two buckets all-reduced from inside umpr_step (csrc/step.cu, umpr_step_comm)
         self.overlap = self.native is not None and self.comm is not None and os.environ.get("UMPR_OVERLAP", "1") == "1"
+        self._skip_reduce = os.environ.get("UMPR_DIAG_NO_REDUCE", "0") == "1"     # diagnostics only: ranks run unsynchronised (wrong training)
+        if self._skip_reduce:
+            self.overlap = False
         if self.overlap:
             from . import plan as plan_mod
             plan_mod.SMS_RESERVED_FOR_COMM = COMM_CTAS          # the R-Net GRU launches leave these SMs to the all-reduce kernel
@@ -223,7 +226,7 @@ class FlatTrainer:
                     (loss if loss.dim() == 0 else loss.mean()).backward()      # main.py:34 (the mean over replica losses is the identity for one shard)
                 finally:
                     F.DIRECT_GRAD_ACCUM = False
-        if not reduced:
+        if not reduced and not self._skip_reduce:
             self.reduce_gradients()
         self.optimizer_step(use_shard_count=self.world > 1)
         return pred, loss
