@@ -87,7 +87,9 @@ def pin_rank_to_cores(local_rank: int, local_world: int):
         return None
     mine = ordered[local_rank * per:(local_rank + 1) * per]
     os.sched_setaffinity(0, mine)
-    torch.set_num_threads(max(1, min(per, 4)))
+    # one intra-op thread: the host work of a rank is many small calls (a 20 k-element sort, a few numpy passes) on the issuing
+    # thread and the plan workers - extra OpenMP threads per call would only fight them for this rank's few cores
+    torch.set_num_threads(1)
     return mine
 
 
