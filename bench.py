@@ -295,6 +295,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    per_rank = {}
+
     def timed(fn, steps, sampler=None):
         barrier()
         if sampler:
@@ -308,6 +310,12 @@ def main():
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            # every rank's own device time and SM clock (a slow or throttled GPU shows up here); the reported time is the MAX over ranks
+            mine = torch.tensor([float(ms), float((clocks or {}).get("sm_mhz") or 0)], device=dev)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank["ms_per_step"] = [round(float(t[0]) / steps, 4) for t in every]
+            per_rank["sm_mhz"] = [int(t[1]) for t in every]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms), clocks
@@ -384,6 +392,7 @@ def main():
     n0 = trainer.native_steps
     host_t.update(wait_batch=0.0, issue=0.0, n=0)
     ms, clocks = timed(step_resident, K, ClockSampler(local))
+    by_rank = dict(per_rank)
     host_ms = {"wait_for_batch_ms_per_step": round(1e3 * host_t["wait_batch"] / max(1, host_t["n"]), 3),
                "issue_ms_per_step": round(1e3 * host_t["issue"] / max(1, host_t["n"]), 3)}
     if world > 1:
@@ -431,7 +440,7 @@ def main():
                                          ("C-ABI NCCL communicator (umpr_comm_*), 2 buckets [head/attention/conv/C-Net | R-Net GRU], the first all-reduced under the last backward kernel"
                                           if trainer.overlap else ("C-ABI NCCL communicator, after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
                    "host_cores_per_rank": len(cores) if cores else None,
-                   "host_thread": host_ms,
+                   "host_thread": host_ms, "by_rank": by_rank or None,
                    "issue": "one native C-ABI call per step (umpr_step) + all-reduce + umpr_adam_step" if native else "autograd Functions over per-kernel C-ABI calls",
                    "host_pipeline": "the next batch's pack plans (torch.sort + int32 plan) are built on a worker thread, like a collate worker; rebuilt every step",
                    "l2_policy": "per-step working set (GBs of activations) exceeds the 126 MB L2; 4 rotating input batches"},
