@@ -408,6 +408,16 @@ def main():
         kt["flops"], kt["bytes"] = K * sum(x[0] for x in wk) / NB, K * sum(x[1] for x in wk) / NB
     else:
         kt = _lib.stop_timing()[top]
+    # host time to ISSUE one step with an empty launch queue (the figure above includes the back-pressure of a full queue: the host
+    # runs ahead of the GPU until the driver's queue is full and is then paced by the GPU)
+    feed["it"] = stream_of(devb, 3)
+    time.sleep(0.05)                                       # let the prefetch workers finish the three plans
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(3):
+        trainer.train_step(next(feed["it"]))
+    host_ms["issue_ms_per_step_empty_queue"] = round(1e3 * (time.perf_counter() - t0) / 3, 3)
+    torch.cuda.synchronize()
     value = world * B * K / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers

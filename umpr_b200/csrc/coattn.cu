@@ -160,22 +160,30 @@ __global__ void __launch_bounds__(256) coattn_pool_kernel(const unsigned long lo
   }
 }
 
-// in-place exclusive prefix sum of a[0..n) by one 256-thread block (a[n] receives the total); `tmp` = 257 ints of shared memory
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+  return v;
+}
+// in-place exclusive prefix sum of a[0..n) by one 256-thread block (a[n] receives the total); `tmp` = 32 ints of shared memory
 __device__ __forceinline__ void block_excl_scan(int* a, int n, int* tmp) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int per = (n + 255) / 256, lo = tid * per, hi = min(n, lo + per);
   int sum = 0;
   for (int i = lo; i < hi; ++i) sum += a[i];
-  tmp[tid + 1] = sum;
+  const int inc = warp_incl_scan(sum, lane);
+  if (lane == 31) tmp[w] = inc;
   __syncthreads();
-  if (tid == 0) {
-    tmp[0] = 0;
-    for (int i = 1; i <= 256; ++i) tmp[i] += tmp[i - 1];
+  if (w == 0) {
+    const int t = lane < 8 ? tmp[lane] : 0;
+    const int ti = warp_incl_scan(t, lane);
+    if (lane < 8) tmp[8 + lane] = ti - t;
+    if (lane == 7) tmp[16] = ti;
   }
   __syncthreads();
-  int run = tmp[tid];
+  int run = tmp[8 + w] + inc - sum;
   for (int i = lo; i < hi; ++i) { const int c = a[i]; a[i] = run; run += c; }
-  if (tid == 255) a[n] = tmp[256];
+  if (tid == 255) a[n] = tmp[16];
   __syncthreads();
 }
 
@@ -186,7 +194,10 @@ __device__ __forceinline__ void block_excl_scan(int* a, int n, int* tmp) {
 //     dgi[i]  = add_i[i] + soft_i[i] d_atte_i
 // The sums over the inverse arg-max relations are GATHERS here: the relations are inverted per sample in shared memory (counting
 // sort), every output row is written exactly once and no global atomics are issued (the first version scattered them with 128
-// atomic adds per entry).  Independent row loads are issued in batches so that several are in flight per warp.
+// atomic adds per entry).  The whole batch is ONE wave of CTAs, so the kernel lasts as long as one CTA's chain of dependent loads:
+// the valid rows of each side are compacted into a list first, the arg-max indices are staged in shared memory, and every pass
+// over the rows keeps 8 (dot products) or 16 (gathers: 4 rows x [arg-max row, hand-over row, first two inverse entries]) 512-byte
+// row loads in flight per warp.
 __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict__ gu, const float* __restrict__ gi,
                                                          const float* __restrict__ giM, const float* __restrict__ soft_u,
                                                          const float* __restrict__ soft_i, const float* __restrict__ t_u,
@@ -204,16 +215,20 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   float* dau = smem + 2 * P4;  // [128]
   float* dai = dau + D;        // [128]
   float* red = dai + D;        // [32]
-  int* tmp = reinterpret_cast<int*>(red + 32);          // [260] scan scratch
-  int* off_i = tmp + 260;      // [P4 + 4] list of item row i = user positions j with arg_u[j] == i: ent_i[off_i[i] .. off_i[i+1])
+  int* tmp = reinterpret_cast<int*>(red + 32);          // [36] scan scratch, [32..33] = number of valid rows per side
+  int* off_i = tmp + 36;       // [P4 + 4] list of item row i = user positions j with arg_u[j] == i: ent_i[off_i[i] .. off_i[i+1])
   int* off_u = off_i + P4 + 4; // [P4 + 4] list of user row j = item positions i with arg_i[i] == j
   int* cur_i = off_u + P4 + 4; // [P4] fill cursors
   int* cur_u = cur_i + P4;
   int* ent_i = cur_u + P4;     // [P4]
   int* ent_u = ent_i + P4;     // [P4]
+  int* au = ent_u + P4;        // [P4] arg_u / arg_i of this sample
+  int* ai = au + P4;
+  int* lst_u = ai + P4;        // [P4] the valid positions of each side, ascending
+  int* lst_i = lst_u + P4;
   // with length tables: rows at or beyond a sentence's length are exactly zero (model.py:20) and are neither read nor written
   // (their gradients are never used); dgiM alone gets explicit zeros there because the dM reduction runs over every row
-  unsigned char* mu = reinterpret_cast<unsigned char*>(ent_u + P4);   // [P4] user-side row is valid
+  unsigned char* mu = reinterpret_cast<unsigned char*>(lst_i + P4);   // [P4] user-side row is valid
   unsigned char* mi = mu + P4;                                         // [P4] item-side row is valid
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t bp = (size_t)b * P;
@@ -230,32 +245,47 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
     }
     mu[p] = a; mi[p] = c;
     off_i[p] = 0; off_u[p] = 0;
+    au[p] = arg_u[bp + p]; ai[p] = arg_i[bp + p];
+    wu[p] = d_soft_u ? d_soft_u[bp + p] : 0.f;        // ds[p] = d_soft[p] (+ <g[p], d_atte> for the valid rows, below)
+    vi[p] = d_soft_i ? d_soft_i[bp + p] : 0.f;
   }
   __syncthreads();
-  // ds[p] = d_soft[p] + <g[p], d_atte>: four rows per warp and iteration, their loads issued together
+  if (warp < 2) {              // compaction of the valid positions: warp 0 the user side, warp 1 the item side
+    const unsigned char* ok = warp ? mi : mu;
+    int* lst = warp ? lst_i : lst_u;
+    int n = 0;
+    for (int p0 = 0; p0 < P; p0 += 32) {
+      const int p = p0 + lane;
+      const bool v = p < P && ok[p];
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) lst[n + __popc(m & ((1u << lane) - 1u))] = p;
+      n += __popc(m);
+    }
+    if (lane == 0) tmp[32 + warp] = n;
+  }
+  __syncthreads();
+  const int nu = tmp[32], ni = tmp[33];
+  // ds[p] += <g[p], d_atte> over the valid rows: eight rows per warp and iteration, their loads issued together
   for (int side = 0; side < 2; ++side) {
-    const float* g = (side ? gi : gu) + bp * D;
-    const float* da = side ? dai : dau;
-    const float* dso = side ? d_soft_i : d_soft_u;
+    const float* g = (side ? gi : gu) + bp * D + lane * 4;
+    const float4 d4 = *reinterpret_cast<const float4*>((side ? dai : dau) + lane * 4);
     float* dst = side ? vi : wu;
-    const float4 d4 = *reinterpret_cast<const float4*>(da + lane * 4);
-    const unsigned char* ok = side ? mi : mu;
-    for (int p0 = warp; p0 < P; p0 += 32) {
-      float4 v[4];
-      bool live[4];
+    const int* lst = side ? lst_i : lst_u;
+    const int n = side ? ni : nu;
+    for (int i0 = warp; i0 < n; i0 += 64) {
+      float4 v[8];
+      int pp[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int p = p0 + 8 * q;
-        live[q] = p < P && ok[p];
-        v[q] = live[q] ? *reinterpret_cast<const float4*>(g + (size_t)p * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < 8; ++q) {
+        const int idx = i0 + 8 * q;
+        pp[q] = idx < n ? lst[idx] : -1;
+        v[q] = pp[q] >= 0 ? *reinterpret_cast<const float4*>(g + (size_t)pp[q] * D) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int p = p0 + 8 * q;
-        if (p >= P) continue;
+      for (int q = 0; q < 8; ++q) {
         float s = v[q].x * d4.x + v[q].y * d4.y + v[q].z * d4.z + v[q].w * d4.w;
         s = warp_sum(s);
-        if (lane == 0) dst[p] = (live[q] ? s : 0.f) + (dso ? dso[bp + p] : 0.f);
+        if (lane == 0 && pp[q] >= 0) dst[pp[q]] += s;
       }
     }
   }
@@ -276,8 +306,8 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   }
   // invert the two arg-max relations (entries with a zero weight or an invalid end carry nothing and are left out)
   for (int p = tid; p < P; p += 256) {
-    if (wu[p] != 0.f && mu[p]) { const int a = arg_u[bp + p]; if (mi[a]) atomicAdd(&off_i[a], 1); }
-    if (vi[p] != 0.f && mi[p]) { const int a = arg_i[bp + p]; if (mu[a]) atomicAdd(&off_u[a], 1); }
+    if (wu[p] != 0.f && mu[p]) { const int a = au[p]; if (mi[a]) atomicAdd(&off_i[a], 1); }
+    if (vi[p] != 0.f && mi[p]) { const int a = ai[p]; if (mu[a]) atomicAdd(&off_u[a], 1); }
   }
   __syncthreads();
   block_excl_scan(off_i, P, tmp);
@@ -285,74 +315,100 @@ __global__ void __launch_bounds__(256) coattn_bwd_kernel(const float* __restrict
   for (int p = tid; p < P; p += 256) { cur_i[p] = off_i[p]; cur_u[p] = off_u[p]; }
   __syncthreads();
   for (int p = tid; p < P; p += 256) {
-    if (wu[p] != 0.f && mu[p]) { const int a = arg_u[bp + p]; if (mi[a]) ent_i[atomicAdd(&cur_i[a], 1)] = p; }
-    if (vi[p] != 0.f && mi[p]) { const int a = arg_i[bp + p]; if (mu[a]) ent_u[atomicAdd(&cur_u[a], 1)] = p; }
+    if (wu[p] != 0.f && mu[p]) { const int a = au[p]; if (mi[a]) ent_i[atomicAdd(&cur_i[a], 1)] = p; }
+    if (vi[p] != 0.f && mi[p]) { const int a = ai[p]; if (mu[a]) ent_u[atomicAdd(&cur_u[a], 1)] = p; }
   }
   __syncthreads();
-  // every valid row once: two rows per warp and iteration
   const float4 dau4 = *reinterpret_cast<const float4*>(dau + lane * 4);
   const float4 dai4 = *reinterpret_cast<const float4*>(dai + lane * 4);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   auto row = [&](const float* base, int p) { return *reinterpret_cast<const float4*>(base + (bp + p) * D + lane * 4); };
   auto fma4 = [](float4& acc, float s, const float4 v) { acc.x += s * v.x; acc.y += s * v.y; acc.z += s * v.z; acc.w += s * v.w; };
-  for (int p0 = warp; p0 < P; p0 += 16) {
-    float4 m[2], eu[2], u[2], ei[2];
-    bool vu[2], vv[2];
-    int pa[2];
+  // user rows: four per warp and iteration
+  for (int i0 = warp; i0 < nu; i0 += 32) {
+    float4 m[4], eu[4], r0[4], r1[4];
+    float sf[4];
+    int pp[4], e0[4], e1[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int p = p0 + 8 * q;
-      pa[q] = p;
-      vu[q] = p < P && mu[p];
-      vv[q] = p < P && mi[p];
-      m[q] = eu[q] = u[q] = ei[q] = zero4;
-      if (vu[q]) {
-        const int a = arg_u[bp + p];
+    for (int q = 0; q < 4; ++q) {
+      const int idx = i0 + 8 * q;
+      const int p = idx < nu ? lst_u[idx] : -1;
+      pp[q] = p;
+      m[q] = eu[q] = r0[q] = r1[q] = zero4;
+      sf[q] = 0.f; e0[q] = e1[q] = 0;
+      if (p >= 0) {
+        const int a = au[p];
         if (wu[p] != 0.f && mi[a]) m[q] = row(giM, a);
         if (add_u) eu[q] = row(add_u, p);
-      }
-      if (vv[q]) {
-        const int a = arg_i[bp + p];
-        if (vi[p] != 0.f && mu[a]) u[q] = row(gu, a);
-        if (add_i) ei[q] = row(add_i, p);
+        sf[q] = soft_u[bp + p];
+        e0[q] = off_u[p]; e1[q] = off_u[p + 1];
+        if (e0[q] < e1[q]) r0[q] = row(giM, ent_u[e0[q]]);
+        if (e0[q] + 1 < e1[q]) r1[q] = row(giM, ent_u[e0[q] + 1]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int p = pa[q];
-      if (p >= P) continue;
-      if (vu[q]) {
-        float4 acc = eu[q];
-        fma4(acc, soft_u[bp + p], dau4);
-        fma4(acc, wu[p], m[q]);
-        const int e1 = off_u[p + 1];
-        for (int e = off_u[p]; e < e1; e += 2) {          // item rows whose maximum sits in this user position
-          const int i0 = ent_u[e], i1 = e + 1 < e1 ? ent_u[e + 1] : -1;
-          const float4 r0 = row(giM, i0), r1 = i1 >= 0 ? row(giM, i1) : zero4;
-          fma4(acc, vi[i0], r0);
-          if (i1 >= 0) fma4(acc, vi[i1], r1);
-        }
-        *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) = acc;
+    for (int q = 0; q < 4; ++q) {
+      const int p = pp[q];
+      if (p < 0) continue;
+      float4 acc = eu[q];
+      fma4(acc, sf[q], dau4);
+      fma4(acc, wu[p], m[q]);
+      if (e0[q] < e1[q]) fma4(acc, vi[ent_u[e0[q]]], r0[q]);          // item rows whose maximum sits in this user position
+      if (e0[q] + 1 < e1[q]) fma4(acc, vi[ent_u[e0[q] + 1]], r1[q]);
+      for (int e = e0[q] + 2; e < e1[q]; e += 2) {
+        const int x0 = ent_u[e], x1 = e + 1 < e1[q] ? ent_u[e + 1] : -1;
+        const float4 a0 = row(giM, x0), a1 = x1 >= 0 ? row(giM, x1) : zero4;
+        fma4(acc, vi[x0], a0);
+        if (x1 >= 0) fma4(acc, vi[x1], a1);
       }
-      if (vv[q]) {
-        float4 acc = zero4;
-        fma4(acc, vi[p], u[q]);
-        const int e1 = off_i[p + 1];
-        for (int e = off_i[p]; e < e1; e += 2) {          // user positions whose maximum sits in this item row
-          const int j0 = ent_i[e], j1 = e + 1 < e1 ? ent_i[e + 1] : -1;
-          const float4 r0 = row(gu, j0), r1 = j1 >= 0 ? row(gu, j1) : zero4;
-          fma4(acc, wu[j0], r0);
-          if (j1 >= 0) fma4(acc, wu[j1], r1);
-        }
-        *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = acc;
-        float4 g2 = ei[q];
-        fma4(g2, soft_i[bp + p], dai4);
-        *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = g2;
-      } else {
-        *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
-      }
+      *reinterpret_cast<float4*>(dgu + (bp + p) * D + lane * 4) = acc;
     }
   }
+  // item rows
+  for (int i0 = warp; i0 < ni; i0 += 32) {
+    float4 u[4], ei[4], r0[4], r1[4];
+    float sf[4];
+    int pp[4], e0[4], e1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int idx = i0 + 8 * q;
+      const int p = idx < ni ? lst_i[idx] : -1;
+      pp[q] = p;
+      u[q] = ei[q] = r0[q] = r1[q] = zero4;
+      sf[q] = 0.f; e0[q] = e1[q] = 0;
+      if (p >= 0) {
+        const int a = ai[p];
+        if (vi[p] != 0.f && mu[a]) u[q] = row(gu, a);
+        if (add_i) ei[q] = row(add_i, p);
+        sf[q] = soft_i[bp + p];
+        e0[q] = off_i[p]; e1[q] = off_i[p + 1];
+        if (e0[q] < e1[q]) r0[q] = row(gu, ent_i[e0[q]]);
+        if (e0[q] + 1 < e1[q]) r1[q] = row(gu, ent_i[e0[q] + 1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = pp[q];
+      if (p < 0) continue;
+      float4 acc = zero4;
+      fma4(acc, vi[p], u[q]);
+      if (e0[q] < e1[q]) fma4(acc, wu[ent_i[e0[q]]], r0[q]);          // user positions whose maximum sits in this item row
+      if (e0[q] + 1 < e1[q]) fma4(acc, wu[ent_i[e0[q] + 1]], r1[q]);
+      for (int e = e0[q] + 2; e < e1[q]; e += 2) {
+        const int x0 = ent_i[e], x1 = e + 1 < e1[q] ? ent_i[e + 1] : -1;
+        const float4 a0 = row(gu, x0), a1 = x1 >= 0 ? row(gu, x1) : zero4;
+        fma4(acc, wu[x0], a0);
+        if (x1 >= 0) fma4(acc, wu[x1], a1);
+      }
+      *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = acc;
+      float4 g2 = ei[q];
+      fma4(g2, sf[q], dai4);
+      *reinterpret_cast<float4*>(dgi + (bp + p) * D + lane * 4) = g2;
+    }
+  }
+  if (ni < P)                  // rows beyond the sentences' lengths: dgiM = 0 (the dM reduction reads every row)
+    for (int p = warp; p < P; p += 8)
+      if (!mi[p]) *reinterpret_cast<float4*>(dgiM + (bp + p) * D + lane * 4) = zero4;
 }
 
 }  // namespace umpr
@@ -389,7 +445,7 @@ extern "C" int umpr_coattn_bwd(const float* gu, const float* gi, const float* gi
   if (cst_u && (S_u * L_u != P || S_i * L_i != P || S_u < 1 || S_i < 1))
     return fail_arg("coattn_bwd: S*L must equal P=%d on both sides (got %d*%d, %d*%d)", P, S_u, L_u, S_i, L_i);
   const size_t P4 = (size_t)((P + 3) & ~3);
-  const size_t sm = sizeof(float) * (2 * P4 + 2 * D + 32) + sizeof(int) * (260 + 2 * (P4 + 4) + 4 * P4) + 2 * P4;
+  const size_t sm = sizeof(float) * (2 * P4 + 2 * D + 32) + sizeof(int) * (36 + 2 * (P4 + 4) + 8 * P4) + 2 * P4;
   if (sm > 200 * 1024) return fail_arg("coattn_bwd: P=%d too large", P);
   if (sm > 48 * 1024) cudaFuncSetAttribute(coattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   coattn_bwd_kernel<<<B, 256, sm, (cudaStream_t)stream>>>(gu, gi, giM, soft_u, soft_i, t_u, t_i, arg_u, arg_i, d_soft_u, d_soft_i,

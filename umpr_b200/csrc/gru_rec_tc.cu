@@ -196,42 +196,42 @@ __global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec2 = (E & 1) == 0;
   unsigned char* img = xq + (size_t)sl * RT_A_BYTES;
-  // 4 rows per warp in flight: the dependent chain plan -> token id -> table row is pure latency, so keep 4 of them outstanding
-#pragma unroll 1
-  for (int r0 = warp; r0 < RT_R; r0 += 32) {
-    const float* src[4];
+  // The dependent chain plan -> token id -> table row is pure latency: a warp owns 16 rows (warp + 8q) and walks the chain for all
+  // of them at once - lane q resolves row q's table offset (one plan / id load per lane instead of a broadcast load per row), the
+  // offsets are handed round by shuffles, and the 16 row loads are outstanding together.
+  long long mine = -1;
+  {
+    const int k = j * RT_R + warp + 8 * (lane & 15);
+    if (t < p.len_of[k]) {
+      const size_t tok = (size_t)p.seq_of[k] * L + t;
+      mine = (long long)(dense ? tok : (size_t)ids[tok]) * E;
+    }
+  }
+  const float* base = dense ? dense : table;
+  const int e0 = 2 * lane;
+  float2 v[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = j * RT_R + r0 + 8 * q;
-      src[q] = nullptr;
-      if (t < p.len_of[k]) {
-        const size_t tok = (size_t)p.seq_of[k] * L + t;
-        src[q] = dense ? dense + tok * E : table + (size_t)ids[tok] * E;
+  for (int q = 0; q < 16; ++q) {
+    const long long o = __shfl_sync(0xffffffffu, mine, q);
+    v[q] = make_float2(0.f, 0.f);
+    if (o >= 0) {
+      const float* src = base + o;
+      if (vec2 && e0 + 1 < E) {
+        v[q] = *reinterpret_cast<const float2*>(src + e0);
+      } else {
+        if (e0 < E) v[q].x = src[e0]; else if (e0 == E) v[q].x = 1.f;
+        if (e0 + 1 < E) v[q].y = src[e0 + 1]; else if (e0 + 1 == E) v[q].y = 1.f;
       }
     }
-    float2 v[4];
+  }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      v[q] = make_float2(0.f, 0.f);
-      if (src[q]) {
-        const int e0 = 2 * lane;
-        if (vec2 && e0 + 1 < E) {
-          v[q] = *reinterpret_cast<const float2*>(src[q] + e0);
-        } else {
-          if (e0 < E) v[q].x = src[q][e0]; else if (e0 == E) v[q].x = 1.f;
-          if (e0 + 1 < E) v[q].y = src[q][e0 + 1]; else if (e0 + 1 == E) v[q].y = 1.f;
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = r0 + 8 * q;
-      uint32_t hi, lo;
-      split2(v[q].x, v[q].y, hi, lo);
-      const uint32_t off = sw128_off(r, 2 * lane);
-      *reinterpret_cast<uint32_t*>(img + off) = hi;
-      *reinterpret_cast<uint32_t*>(img + RT_R * 128 + off) = lo;
-    }
+  for (int q = 0; q < 16; ++q) {
+    const int r = warp + 8 * q;
+    uint32_t hi, lo;
+    split2(v[q].x, v[q].y, hi, lo);
+    const uint32_t off = sw128_off(r, 2 * lane);
+    *reinterpret_cast<uint32_t*>(img + off) = hi;
+    *reinterpret_cast<uint32_t*>(img + RT_R * 128 + off) = lo;
   }
 }
 

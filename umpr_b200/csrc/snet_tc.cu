@@ -98,7 +98,12 @@ __device__ __forceinline__ void sentence_softmax(const StMeta& m, int j, int L, 
 }
 
 // ======================================================================================================= forward
-__global__ void __launch_bounds__(ST_THREADS, 1) snet_fwd_tc_kernel(const float* __restrict__ x, const int* __restrict__ tso,
+// 416 threads: warps 0-7 loaders (a warp per row and pass: the 16 row loads of a thread - the whole tile - are in flight together),
+// warp 8 MMA issuer, warps 9-12 row threads.  The pooling reads the tile's operand image in shared memory (x = hi + lo to 2^-18
+// relative) instead of fetching every row from L2 a second time, so the image stage is released by the row threads.
+constexpr int SF_THREADS = 416;
+
+__global__ void __launch_bounds__(SF_THREADS, 1) snet_fwd_tc_kernel(const float* __restrict__ x, const int* __restrict__ tso,
                                                                     const int* __restrict__ cst, const float* __restrict__ Ms,
                                                                     const float* __restrict__ Ws, int n_tiles, int L,
                                                                     float* __restrict__ self_atte) {
@@ -113,13 +118,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_fwd_tc_kernel(const float*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int s = 0; s < ST_NSTAGE; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < ST_NSTAGE; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 128); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
-    for (int s = 0; s < ST_NMETA; ++s) mbar_init(&m_full[s], 128);
+    for (int s = 0; s < ST_NMETA; ++s) mbar_init(&m_full[s], 256);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, 128);
-  load_ms_images(msi, Ms, tid);
+  if (warp == 8) tmem_alloc(&tmem_slot, 128);
+  for (int idx = tid; idx < ATT * 32; idx += SF_THREADS) {      // Ms [64][128] fp32 -> resident images
+    const int a = idx >> 5, c = (idx & 31) * 4, kb = c >> 6;
+    const float4 v = *reinterpret_cast<const float4*>(Ms + a * D + c);
+    unsigned char* t = msi + kb * 16384;
+    store_split4(t, t + 8192, a, c & 63, v);
+  }
   if (tid < ATT) ws_s[tid] = Ws[tid];
   fence_async_smem();
   tc_fence_before();
@@ -127,53 +137,57 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_fwd_tc_kernel(const float*
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int s = it % ST_NSTAGE;
       if (it >= ST_NSTAGE) mbar_wait(&a_empty[s], ((it / ST_NSTAGE) - 1) & 1);
       StMeta& m = meta[it % ST_NMETA];
       const int rows = build_meta(m, tso, cst, tile, L, tid);
-      bar_sync(1, 128);
-      unsigned char* st = xim + s * ST_XIMG;
-#pragma unroll 1
-      for (int kb = 0; kb < 2; ++kb) {
-        unsigned char* a_hi = st + kb * 32768, *a_lo = a_hi + 16384;
-        float4 va[16];
+      bar_sync(1, 256);
+      unsigned char* st = xim + s * ST_XIMG + (lane >> 4) * 32768;      // channel half of this lane
+      float4 va[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
-          va[i] = r < rows ? *reinterpret_cast<const float4*>(x + (size_t)m.rowmap[r] * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid;
-          store_split4(a_hi, a_lo, idx >> 4, (idx & 15) * 4, va[i]);
-        }
+      for (int i = 0; i < 16; ++i) {
+        const int r = i * 8 + warp;
+        va[i] = r < rows ? *reinterpret_cast<const float4*>(x + (size_t)m.rowmap[r] * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) store_split4(st, st + 16384, i * 8 + warp, (lane & 15) * 4, va[i]);
       fence_async_smem();
       mbar_arrive(&a_full[s]);
       mbar_arrive(&m_full[it % ST_NMETA]);
     }
-  } else if (warp == 4) {
-    if (lane == 0) {
-      const uint32_t b0 = smem_u32(msi);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % ST_NSTAGE, acc = it & 1;
-        if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);
-        mbar_wait(&a_full[s], (it / ST_NSTAGE) & 1);
-        tc_fence_after();
-        issue_scores(tmem + acc * ATT, smem_u32(xim + s * ST_XIMG), b0);
-        umma_commit(&a_empty[s]);
-        umma_commit(&acc_full[acc]);
-      }
-    }
-  } else {
-    const int q = warp & 3, r = q * 32 + lane, et = tid - 160;
+  } else if (warp == 8) {
+    const uint32_t el = elect_one_sync();
+    const uint32_t b0 = smem_u32(msi);
+    constexpr uint32_t idesc = idesc_bf16(128, ATT);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
+      const int s = it % ST_NSTAGE, acc = it & 1;
+      if (it >= 2) mbar_wait(&acc_empty[acc], ((it >> 1) - 1) & 1);
+      mbar_wait(&a_full[s], (it / ST_NSTAGE) & 1);
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(xim + s * ST_XIMG), d = tmem + acc * ATT;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint64_t ah = smem_desc_sw128(a0 + kb * 32768), al = smem_desc_sw128(a0 + kb * 32768 + 16384);
+        const uint64_t bh = smem_desc_sw128(b0 + kb * 16384), bl = smem_desc_sw128(b0 + kb * 16384 + 8192);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);
+          umma_bf16_e(el, d, ah + o, bh + o, idesc, (kb | kk) != 0);
+          umma_bf16_e(el, d, ah + o, bl + o, idesc, 1);
+          umma_bf16_e(el, d, al + o, bh + o, idesc, 1);
+        }
+      }
+      umma_commit_e(el, &acc_full[acc]);
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane, et = tid - 288;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int s = it % ST_NSTAGE, acc = it & 1;
       // the loaders' bookkeeping of this tile is visible (its own barrier: a_full may already be a phase ahead by now)
       mbar_wait(&m_full[it % ST_NMETA], (it / ST_NMETA) & 1);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
@@ -189,35 +203,34 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_fwd_tc_kernel(const float*
       }
       score[r] = sc;
       tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
       bar_sync(2, 128);
       if (et < m.ns) { float ps; sentence_softmax(m, et, L, score, soft, ps); }
       bar_sync(2, 128);
-      // pooling: self_atte[n] = sum_l soft[l] x[n,l]  (a warp per sentence, lanes = channel quads; x rows come from L2)
-      for (int j = q; j < m.ns; j += 4) {
+      // pooling: self_atte[n] = sum_l soft[l] x[n,l]  (a warp per sentence, lanes = channel quads, rows from the operand image)
+      const unsigned char* img = xim + s * ST_XIMG + (lane >> 4) * 32768;
+      const int k = (lane & 15) * 4;
+      for (int j = (warp - 9); j < m.ns; j += 4) {
         const int b = m.sbase[j], e = m.sbase[j + 1];
-        const float* xs = x + ((size_t)(m.s0 + j) * L) * D + lane * 4;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r0 = b; r0 < e; r0 += 4) {
-          float4 v[4];
-          float w[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool ok = r0 + u < e;
-            v[u] = ok ? *reinterpret_cast<const float4*>(xs + (size_t)(r0 + u - b) * D) : make_float4(0.f, 0.f, 0.f, 0.f);
-            w[u] = ok ? soft[r0 + u] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { a.x += w[u] * v[u].x; a.y += w[u] * v[u].y; a.z += w[u] * v[u].z; a.w += w[u] * v[u].w; }
+        for (int rr = b; rr < e; ++rr) {
+          const uint32_t off = sw128_off(rr, k);
+          const uint2 hi = *reinterpret_cast<const uint2*>(img + off), lo = *reinterpret_cast<const uint2*>(img + 16384 + off);
+          const float w = soft[rr];
+          a.x += w * (__uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16));
+          a.y += w * (__uint_as_float(hi.x & 0xffff0000u) + __uint_as_float(lo.x & 0xffff0000u));
+          a.z += w * (__uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16));
+          a.w += w * (__uint_as_float(hi.y & 0xffff0000u) + __uint_as_float(lo.y & 0xffff0000u));
         }
         *reinterpret_cast<float4*>(self_atte + (size_t)(m.s0 + j) * D + lane * 4) = a;
       }
+      mbar_arrive(&a_empty[s]);            // (the generic-proxy reads of the image are ordered before the loaders' next writes by the barrier)
       bar_sync(2, 128);
-      mbar_arrive(&acc_empty[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 8) tmem_dealloc(tmem, 128);
 }
 
 // ======================================================================================================= backward
@@ -492,7 +505,7 @@ extern "C" int umpr_snet_fwd_tc(const float* x, const int* table, int n_tiles, c
   if (e != cudaSuccess) { set_error("snet_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  snet_fwd_tc_kernel<<<grid, ST_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, Ms, Ws, n_tiles, L, self_atte);
+  snet_fwd_tc_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, Ms, Ws, n_tiles, L, self_atte);
   return check_launch("snet_fwd_tc");
 }
 
