@@ -30,7 +30,7 @@ extern "C" {
 
 int umpr_version(void);
 /* Scratch bytes of the entry points that take a caller-owned workspace (PyTorch owns every buffer):
- *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = worklist capacity     "cnet_conv_bwd_dx": a = kernel_count
+ *   "coattn_fwd_tc": a = B, b = P     "cnet_conv_fwd_tc": a = cap (>= N*KC/8)      "cnet_conv_bwd_dx": a = kernel_count
  *   "cnet_conv_bwd_dx_tc": no size argument */
 int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes);
 
@@ -196,7 +196,7 @@ int umpr_cnet_conv_fwd(const float* x, const float* wt, const float* conv_b, int
                        int32_t* cidx /*(N,KC) arg-max position, -1 if clipped by ReLU*/, int n_ctas, void* stream);
 /* tensor-core form of umpr_cnet_prep + umpr_cnet_conv_fwd (implicit GEMM on tcgen05, weights streamed by bulk copies); maxima
  * that are near-tied (or next to the ReLU threshold) are re-scored in exact fp32 because the arg-max routes the gradient.
- * scratch: 197632 + 16*cap bytes, 16-byte aligned; cap = capacity of the re-scoring worklist.
+ * scratch: 197632 + 16*cap bytes, 16-byte aligned; it holds one 2-byte re-scoring record per (sentence, filter): cap >= ceil(N*KC/8).
  * table (optional, int32 device) = [tile_sent_off (n_tiles+1) | cstart (N+1)], cstart = exclusive prefix sum of (len+2) per sentence,
  * for inputs produced by ImprovedRnn (rows at or beyond a sentence's length exactly zero): only the valid rows are laid out and
  * multiplied, the all-zero windows enter the max as the bias.  NULL: every sentence is processed at its full length L. */

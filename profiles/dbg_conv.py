@@ -29,7 +29,7 @@ def run(N, L, KC, n_ctas, use_plan, seed=0, short=False):
     x = x * mask.to(dev)[:, :, None]
     w = torch.randn(KC, 128, 3, device=dev) * 0.05
     b = torch.randn(KC, device=dev) * 0.3
-    cap = max(4096, N * KC // 8)
+    cap = max(4096, (N * KC + 7) // 8)
     scratch = torch.empty(_workspace_floats("cnet_conv_fwd_tc", cap), dtype=torch.float32, device=dev)
     cfeat = torch.full((N, KC), -7.0, dtype=torch.float32, device=dev)
     cidx = torch.full((N, KC), -9, dtype=torch.int32, device=dev)
@@ -70,7 +70,37 @@ def run(N, L, KC, n_ctas, use_plan, seed=0, short=False):
         print("   first bad row: len", int(lens[r0]), "got", cfeat[r0, :6].tolist(), "want", want[r0, :6].tolist())
 
 
-for args in [(40, 20, 120, 148, True), (600, 20, 120, 4, True), (3000, 20, 120, 7, True),
+for args in [] if "--time" in sys.argv else [(40, 20, 120, 148, True), (600, 20, 120, 4, True), (3000, 20, 120, 7, True),
              (20480, 20, 120, 148, True), (20480, 20, 120, 148, True, 1), (20480, 20, 120, 148, True, 2), (300, 100, 120, 3, True), (2000, 5, 100, 2, True)]:
     run(*args)
     run(*args, short=True)
+
+
+def timeit(N=20480, L=20, KC=120):
+    """kernel time of the convolution forward on a music_full-shaped side (lengths 6..20, sorted pools do not matter here)"""
+    torch.manual_seed(0)
+    lens = torch.randint(6, L + 1, (N,))
+    plan = PackPlan(lens, L, dev, tile_rows=128)
+    table, n_tiles = plan.cnet_table()
+    x = torch.tanh(torch.randn(N, L, 128, device=dev))
+    w = torch.randn(KC, 128, 3, device=dev) * 0.05
+    b = torch.randn(KC, device=dev) * 0.05
+    cap = max(4096, (N * KC + 7) // 8)
+    scratch = torch.empty(_workspace_floats("cnet_conv_fwd_tc", cap), dtype=torch.float32, device=dev)
+    cfeat = torch.empty(N, KC, device=dev)
+    cidx = torch.empty(N, KC, dtype=torch.int32, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("umpr_cnet_conv_fwd_tc", ptr(x), ptr(w), ptr(b), N, L, KC, 3, ptr(table), n_tiles, ptr(scratch), cap, ptr(cfeat), ptr(cidx), 148)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    print(f"UMPR_CONV_DBG={os.environ.get('UMPR_CONV_DBG', '0')}: N={N} tiles={n_tiles}: {sorted(ts)[len(ts) // 2] * 1e3:.1f} us (prep + conv + fix)")
+
+
+if "--time" in sys.argv:
+    timeit()

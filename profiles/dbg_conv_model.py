@@ -34,14 +34,14 @@ print("calls", len(calls), "bias range", float(cb.min()), float(cb.max()))
 for x, S, L, plan in calls:
     N = x.shape[0] * S
     xs = x.reshape(N, L, 128).contiguous()
-    cap = max(4096, N * KC // 8)
+    cap = max(4096, (N * KC + 7) // 8)
     scratch = torch.empty(_workspace_floats("cnet_conv_fwd_tc", cap), dtype=torch.float32, device=dev)
     cfeat = torch.full((N, KC), -7.0, dtype=torch.float32, device=dev)
     cidx = torch.full((N, KC), -9, dtype=torch.int32, device=dev)
     tbl, nt = plan.cnet_table() if plan is not None else (None, 0)
     call("umpr_cnet_conv_fwd_tc", ptr(xs), ptr(cw), ptr(cb), N, L, KC, 3, ptr(tbl), nt, ptr(scratch), cap, ptr(cfeat), ptr(cidx), 148)
     torch.cuda.synchronize()
-    counter = scratch.view(torch.int32)[(196608 + 512) // 4]
+    counter = (scratch.view(torch.int16)[(196608 + 1024) // 2:(196608 + 1024) // 2 + N * KC] >= 0).sum()
     y = torch.nn.functional.conv1d(xs.transpose(1, 2).double(), cw.double(), cb.double(), padding=1).float()
     top = y.max(dim=2).values
     want = torch.relu(top)

@@ -88,7 +88,7 @@ extern "C" int umpr_comm_destroy(void* comm) {
 }
 
 // Scratch bytes of the entry points that take a caller-owned workspace (PyTorch owns every buffer).
-//   "coattn_fwd_tc": a = B, b = P            "cnet_conv_fwd_tc": a = worklist capacity          "cnet_conv_bwd_dx": a = kernel_count
+//   "coattn_fwd_tc": a = B, b = P            "cnet_conv_fwd_tc": a = cap (>= N*KC/8)          "cnet_conv_bwd_dx": a = kernel_count
 //   "cnet_conv_bwd_dx_tc": (none)
 extern "C" int umpr_workspace_bytes(const char* entry, long a, long b, long long* bytes) {
   if (!entry || !bytes) return fail_arg("workspace_bytes: NULL argument");

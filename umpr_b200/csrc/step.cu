@@ -146,7 +146,7 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   // full model
   int Nmax = 0;
   for (int k = 0; k < n_sides; ++k) Nmax = sd[k].B * sd[k].S > Nmax ? sd[k].B * sd[k].S : Nmax;
-  const int cap = (Nmax * KC / 8) > 4096 ? (Nmax * KC / 8) : 4096;
+  const int cap = ((Nmax * KC + 7) / 8) > 4096 ? ((Nmax * KC + 7) / 8) : 4096;      // one 2-byte re-scoring record per (sentence, filter)
   void* conv_scratch = nullptr; float* s_ui = nullptr; float* senti_ss = nullptr; float* ct_out = nullptr; float* vis_emb = nullptr; float* vis_out = nullptr;
   void* dx_scratch = nullptr;
   if (full) {
@@ -243,8 +243,8 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     }
     for (int k = 0; k < 3; ++k) {            // conv + ReLU + max-pool + view head (model.py:118-125)
       const int N = sd[k].B * sd[k].S;
-      STEP_CALL_C("umpr_cnet_conv_fwd_tc", umpr_cnet_conv_fwd_tc(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
-                                     sb[k].cfeat, sb[k].cidx, n_ctas, cstream));
+      STEP_CALL_C("umpr_cnet_conv_fwd_tc", cnet_conv_fwd_tc_impl(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
+                                     sb[k].cfeat, sb[k].cidx, n_ctas, k == 0, cstream));      // the weight image of the first call serves all three
       STEP_CALL_C("umpr_cnet_head_fwd", umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, cstream));
       if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, stc);
     }

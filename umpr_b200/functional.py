@@ -601,7 +601,7 @@ class _CNetTailFn(Function):
         cidx = torch.empty(N, KC, dtype=torch.int32, device=dev)
         work = (2.0 * N * L * 3 * D * KC, N * L * D * 4.0)
         if TENSOR_CORE_CONV:
-            cap = max(4096, N * KC // 8)
+            cap = max(4096, (N * KC + 7) // 8)           # one 2-byte re-scoring record per (sentence, filter)
             scratch = torch.empty(_workspace_floats("cnet_conv_fwd_tc", cap), dtype=torch.float32, device=dev)
             table, n_tiles = None, 0
             ctx.keep = None
