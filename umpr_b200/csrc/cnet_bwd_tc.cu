@@ -155,8 +155,9 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
       mbar_arrive(&bar.m_full[it % CB_NMETA]);
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_mine > 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
+    if (n_mine > 0) {
+      const uint32_t el = elect_one_sync();
       constexpr uint32_t idesc = idesc_bf16(128, 64) | (1u << 15) | (1u << 16);       // A (x) and B (G half tile) MN-major
       const uint32_t g0 = smem_u32(gim);
       int q = 0;
@@ -175,15 +176,15 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
               const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
               const uint64_t gh = desc_mn(gq0 + ks * 2048, 8192), gl = desc_mn(gq0 + 16384 + ks * 2048, 8192);
               const uint32_t d = tmem + j * 128 + h * 64;
-              umma_bf16(d, xh, gh, idesc, (it | ks) != 0);
-              umma_bf16(d, xh, gl, idesc, 1);
-              umma_bf16(d, xl, gh, idesc, 1);
+              umma_bf16_e(el, d, xh, gh, idesc, (it | ks) != 0);
+              umma_bf16_e(el, d, xh, gl, idesc, 1);
+              umma_bf16_e(el, d, xl, gh, idesc, 1);
             }
-            umma_commit(&bar.g_free[gb]);
-            if (j == 2 && h == 1) umma_commit(&bar.a_empty[s]);
+            umma_commit_e(el, &bar.g_free[gb]);
+            if (j == 2 && h == 1) umma_commit_e(el, &bar.a_empty[s]);
           }
       }
-      umma_commit(&bar.w_full);
+      umma_commit_e(el, &bar.w_full);
     }
   } else {
     // ------------------------------------------------------------------ gradient scatter (one-hot tile per tap), final flush
@@ -308,15 +309,16 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ TMA producer (tap weights) + MMA issuer
-    if (lane == 0 && n_mine > 0) {
+    if (n_mine > 0) {       // whole warp converged, the elected lane issues
+      const uint32_t el = elect_one_sync();
       constexpr uint32_t idesc = idesc_bf16(128, 128);              // A (G) and B (W_j^T) K-major
       const uint32_t g0 = smem_u32(gim);
       const int n_taps = 3 * n_mine;
       auto fetch = [&](int p) {                                     // weights of tap p % 3 into stage p & 1
         const int ws = p & 1;
         if (p >= 2) mbar_wait(&bar.w_empty[ws], ((p >> 1) - 1) & 1);
-        mbar_arrive_expect_tx(&bar.w_full[ws], CX_WIMG);
-        bulk_copy_g2s(wsm + ws * CX_WIMG, wimg + (size_t)(p % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
+        mbar_arrive_expect_tx_e(el, &bar.w_full[ws], CX_WIMG);
+        bulk_copy_g2s_e(el, wsm + ws * CX_WIMG, wimg + (size_t)(p % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
       };
       fetch(0);
       int q = 0, p = 0;
@@ -338,14 +340,14 @@ __global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t o = (uint64_t)(kk * 2);
-              umma_bf16(tmem + acc * 128, gh + o, wh + o, idesc, (j | h | kk) != 0);
-              umma_bf16(tmem + acc * 128, gh + o, wl + o, idesc, 1);
-              umma_bf16(tmem + acc * 128, gl + o, wh + o, idesc, 1);
+              umma_bf16_e(el, tmem + acc * 128, gh + o, wh + o, idesc, (j | h | kk) != 0);
+              umma_bf16_e(el, tmem + acc * 128, gh + o, wl + o, idesc, 1);
+              umma_bf16_e(el, tmem + acc * 128, gl + o, wh + o, idesc, 1);
             }
-            umma_commit(&bar.g_free[gb]);
+            umma_commit_e(el, &bar.g_free[gb]);
           }
-          umma_commit(&bar.w_empty[ws]);
-          if (j == 2) umma_commit(&bar.acc_full[acc]);
+          umma_commit_e(el, &bar.w_empty[ws]);
+          if (j == 2) umma_commit_e(el, &bar.acc_full[acc]);
         }
       }
     }

@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           }
         }
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
+    const uint32_t el = elect_one_sync();
     constexpr uint32_t idesc = idesc_bf16(128, 128);
     const uint32_t a0 = smem_u32(a_img);
     int n = 0, na = 0;
@@ -280,17 +281,17 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t o = (uint64_t)(kk * 2);
               const uint32_t accf = (kb | kk) != 0;
-              umma_bf16(d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
-              umma_bf16(d1, ah + o, bl + o, idesc, 1);
-              umma_bf16(d1, al + o, bh + o, idesc, 1);
-              umma_bf16(d2, bh + o, ah + o, idesc, accf);      // S^T (rows j, cols i)
-              umma_bf16(d2, bh + o, al + o, idesc, 1);
-              umma_bf16(d2, bl + o, ah + o, idesc, 1);
+              umma_bf16_e(el, d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
+              umma_bf16_e(el, d1, ah + o, bl + o, idesc, 1);
+              umma_bf16_e(el, d1, al + o, bh + o, idesc, 1);
+              umma_bf16_e(el, d2, bh + o, ah + o, idesc, accf);      // S^T (rows j, cols i)
+              umma_bf16_e(el, d2, bh + o, al + o, idesc, 1);
+              umma_bf16_e(el, d2, bl + o, ah + o, idesc, 1);
             }
           }
-          umma_commit(&bars.b_empty[s]);
-          umma_commit(&bars.acc_full[s]);
-          if (jt == Tb - 1) umma_commit(&bars.a_empty);
+          umma_commit_e(el, &bars.b_empty[s]);
+          umma_commit_e(el, &bars.acc_full[s]);
+          if (jt == Tb - 1) umma_commit_e(el, &bars.a_empty);
         }
       }
   }

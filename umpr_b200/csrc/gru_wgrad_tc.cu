@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float
       fence_async_smem();
       mbar_arrive(&full_bar[s]);
     }
-  } else if (lane == 0) {
+  } else {
+    const uint32_t el = elect_one_sync();      // whole warp converged, the elected lane issues
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);     // A and B are MN-major
     for (int st = 0; st < n_steps; ++st) {
@@ -135,14 +136,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) gru_wgrad_tc_kernel(const float
         for (int half = 0; half < 2; ++half) {
           const uint64_t ah = smem_desc_mn_sw128(sb + (half * 2) * WT_TILE + ko), al = smem_desc_mn_sw128(sb + (half * 2 + 1) * WT_TILE + ko);
           const uint32_t d = tmem + half * 128;
-          umma_bf16(d, ah, bh, idesc, (st | kk) != 0);
-          umma_bf16(d, ah, bl, idesc, 1);
-          umma_bf16(d, al, bh, idesc, 1);
+          umma_bf16_e(el, d, ah, bh, idesc, (st | kk) != 0);
+          umma_bf16_e(el, d, ah, bl, idesc, 1);
+          umma_bf16_e(el, d, al, bh, idesc, 1);
         }
       }
-      umma_commit(&empty_bar[s]);
+      umma_commit_e(el, &empty_bar[s]);
     }
-    umma_commit(&acc_bar);
+    umma_commit_e(el, &acc_bar);
   }
   __syncwarp();
   if (warp < 4 && n_steps > 0) {
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
       fence_async_smem();
       mbar_arrive(&full_bar[s]);
     }
-  } else if (lane == 0) {
+  } else {
+    const uint32_t el = elect_one_sync();      // whole warp converged, the elected lane issues
     constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);     // A and B are MN-major
     for (int st = 0; st < n_steps; ++st) {
       const int s = st % TN_NSTAGE;
@@ -259,13 +261,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
         const uint32_t ko = kk * 2048;           // 16 k = two 1024-byte atoms
         const uint64_t ah = smem_desc_mn_sw128(sb + ko), al = smem_desc_mn_sw128(sb + WT_TILE + ko);
         const uint64_t bh = smem_desc_mn_sw128(sb + 2 * WT_TILE + ko), bl = smem_desc_mn_sw128(sb + 3 * WT_TILE + ko);
-        umma_bf16(tmem, ah, bh, idesc, (st | kk) != 0);
-        umma_bf16(tmem, ah, bl, idesc, 1);
-        umma_bf16(tmem, al, bh, idesc, 1);
+        umma_bf16_e(el, tmem, ah, bh, idesc, (st | kk) != 0);
+        umma_bf16_e(el, tmem, ah, bl, idesc, 1);
+        umma_bf16_e(el, tmem, al, bh, idesc, 1);
       }
-      umma_commit(&empty_bar[s]);
+      umma_commit_e(el, &empty_bar[s]);
     }
-    umma_commit(&acc_bar);
+    umma_commit_e(el, &acc_bar);
   }
   __syncwarp();
   if (warp < 4 && n_steps > 0) {

@@ -68,7 +68,7 @@ __device__ __forceinline__ int build_meta(StMeta& m, const int* __restrict__ tso
 }
 
 // the e = x·Ms^T product of one tile (24 MMAs)
-__device__ __forceinline__ void issue_scores(uint32_t d, uint32_t a0, uint32_t b0) {
+__device__ __forceinline__ void issue_scores(uint32_t el, uint32_t d, uint32_t a0, uint32_t b0) {
   constexpr uint32_t idesc = idesc_bf16(128, ATT);
 #pragma unroll
   for (int kb = 0; kb < 2; ++kb) {
@@ -77,9 +77,9 @@ __device__ __forceinline__ void issue_scores(uint32_t d, uint32_t a0, uint32_t b
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const uint64_t o = (uint64_t)(kk * 2);
-      umma_bf16(d, ah + o, bh + o, idesc, (kb | kk) != 0);
-      umma_bf16(d, ah + o, bl + o, idesc, 1);
-      umma_bf16(d, al + o, bh + o, idesc, 1);
+      umma_bf16_e(el, d, ah + o, bh + o, idesc, (kb | kk) != 0);
+      umma_bf16_e(el, d, ah + o, bl + o, idesc, 1);
+      umma_bf16_e(el, d, al + o, bh + o, idesc, 1);
     }
   }
 }
@@ -321,14 +321,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && n_mine > 0) {
+    if (n_mine > 0) {       // whole warp converged, the elected lane issues
+      const uint32_t el = elect_one_sync();
       const uint32_t b0 = smem_u32(msi), p0 = smem_u32(pim);
       constexpr uint32_t idesc_dx = idesc_bf16(128, 128) | (1u << 16);                 // A K-major (dpre), B MN-major (Ms)
       constexpr uint32_t idesc_w = idesc_bf16(128, ATT) | (1u << 15) | (1u << 16);    // A MN-major (x), B MN-major (dpre)
       mbar_wait(&bar.a_full[0], 0);
       tc_fence_after();
-      issue_scores(tmem + T_E, smem_u32(xim), b0);
-      umma_commit(&bar.e_full[0]);
+      issue_scores(el, tmem + T_E, smem_u32(xim), b0);
+      umma_commit_e(el, &bar.e_full[0]);
       for (int it = 0; it < n_mine; ++it) {
         const int s = it % ST_NSTAGE;
         if (it + 1 < n_mine) {
@@ -336,8 +337,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
           if (it + 1 >= 2) mbar_wait(&bar.e_empty[a1], (((it + 1) >> 1) - 1) & 1);
           mbar_wait(&bar.a_full[s1], ((it + 1) / ST_NSTAGE) & 1);
           tc_fence_after();
-          issue_scores(tmem + T_E + a1 * ATT, smem_u32(xim + s1 * ST_XIMG), b0);
-          umma_commit(&bar.e_full[a1]);
+          issue_scores(el, tmem + T_E + a1 * ATT, smem_u32(xim + s1 * ST_XIMG), b0);
+          umma_commit_e(el, &bar.e_full[a1]);
         }
         mbar_wait(&bar.p_ready, it & 1);
         tc_fence_after();
@@ -347,23 +348,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t ph = smem_desc_sw128(p0) + (uint64_t)(kk * 2), pl = smem_desc_sw128(p0 + 16384) + (uint64_t)(kk * 2);
           const uint64_t mh = desc_mn(b0 + kk * 2048, 16384), ml = desc_mn(b0 + 8192 + kk * 2048, 16384);
-          umma_bf16(tmem + T_DX, ph, mh, idesc_dx, kk != 0);
-          umma_bf16(tmem + T_DX, ph, ml, idesc_dx, 1);
-          umma_bf16(tmem + T_DX, pl, mh, idesc_dx, 1);
+          umma_bf16_e(el, tmem + T_DX, ph, mh, idesc_dx, kk != 0);
+          umma_bf16_e(el, tmem + T_DX, ph, ml, idesc_dx, 1);
+          umma_bf16_e(el, tmem + T_DX, pl, mh, idesc_dx, 1);
         }
         // dMs^T [128 c x 64 a] += x^T [128 c x 128 rows] · dpre [128 rows x 64 a]
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
           const uint64_t ph = desc_mn(p0 + ks * 2048, 8192), pl = desc_mn(p0 + 16384 + ks * 2048, 8192);
-          umma_bf16(tmem + T_W, xh, ph, idesc_w, (it | ks) != 0);
-          umma_bf16(tmem + T_W, xh, pl, idesc_w, 1);
-          umma_bf16(tmem + T_W, xl, ph, idesc_w, 1);
+          umma_bf16_e(el, tmem + T_W, xh, ph, idesc_w, (it | ks) != 0);
+          umma_bf16_e(el, tmem + T_W, xh, pl, idesc_w, 1);
+          umma_bf16_e(el, tmem + T_W, xl, ph, idesc_w, 1);
         }
-        umma_commit(&bar.a_empty[s]);
-        umma_commit(&bar.d_full);
+        umma_commit_e(el, &bar.a_empty[s]);
+        umma_commit_e(el, &bar.d_full);
       }
-      umma_commit(&bar.w_full);
+      umma_commit_e(el, &bar.w_full);
     }
   } else {
     // ------------------------------------------------------------------ row threads

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_nt_kernel(const TcGemmA
         }
       }
     }
-  } else if (lane == 0) {
+  } else {
+    const uint32_t el = elect_one_sync();      // whole warp converged, the elected lane issues
     // ------------------------------------------------------------------ MMA issuer (one thread)
     constexpr uint32_t idesc = idesc_bf16(TG_BM, BN);
     for (int kb = 0; kb < nkb; ++kb) {
@@ -196,13 +197,13 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tc_gemm_nt_kernel(const TcGemmA
 #pragma unroll
       for (int kk = 0; kk < TG_BK / 16; ++kk) {
         const uint64_t o = (uint64_t)(kk * 2);      // +32 bytes (>>4) inside the 128-byte swizzled row
-        umma_bf16(tmem, ah + o, bh + o, idesc, (kb | kk) != 0);
-        umma_bf16(tmem, ah + o, bl + o, idesc, 1);
-        umma_bf16(tmem, al + o, bh + o, idesc, 1);
+        umma_bf16_e(el, tmem, ah + o, bh + o, idesc, (kb | kk) != 0);
+        umma_bf16_e(el, tmem, ah + o, bl + o, idesc, 1);
+        umma_bf16_e(el, tmem, al + o, bh + o, idesc, 1);
       }
-      umma_commit(&empty_bar[s]);     // frees the stage when these MMAs have read it
+      umma_commit_e(el, &empty_bar[s]);     // frees the stage when these MMAs have read it
     }
-    umma_commit(&accum_bar);
+    umma_commit_e(el, &accum_bar);
   }
   tc_fence_before();
   __syncthreads();

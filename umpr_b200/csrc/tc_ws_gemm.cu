@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       if (by_rows) mbar_arrive(&m_full[it % WS_NMETA]);
     }
   } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
+    {
+      const uint32_t el = elect_one_sync();
       constexpr uint32_t idesc = idesc_bf16(128, BN);
       const uint32_t b0 = smem_u32(bsm);
       int it = 0;
@@ -163,13 +164,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t o = (uint64_t)(kk * 2);
-            umma_bf16(d, ah + o, bh + o, idesc, (kb | kk) != 0);
-            umma_bf16(d, ah + o, bl + o, idesc, 1);
-            umma_bf16(d, al + o, bh + o, idesc, 1);
+            umma_bf16_e(el, d, ah + o, bh + o, idesc, (kb | kk) != 0);
+            umma_bf16_e(el, d, ah + o, bl + o, idesc, 1);
+            umma_bf16_e(el, d, al + o, bh + o, idesc, 1);
           }
         }
-        umma_commit(&a_empty[s]);
-        umma_commit(&acc_full[acc]);
+        umma_commit_e(el, &a_empty[s]);
+        umma_commit_e(el, &acc_full[acc]);
       }
     }
   } else {
