@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Error reporting and version for the C-ABI (include/umpr_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
@@ -5,6 +6,12 @@
 #include "../../include/umpr_b200.h"
 
 namespace umpr {
+int dbg_flags() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UMPR_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {

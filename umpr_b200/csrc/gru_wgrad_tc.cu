@@ -220,17 +220,22 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
     const int m = lane * 4;
     const uint32_t off0 = mn_off(m, warp);
     const bool a_ok = m < M, b_ok = m < N;          // M, N are multiples of 4
-    for (int st = 0; st < n_steps; ++st) {
-      const int s = st % TN_NSTAGE;
+    // register double buffer: the 16 row loads of step st+1 are in flight while step st is split and stored
+    float4 va[8], vb[8], na[8], nb[8];
+    auto fetch = [&](int st, float4* xa, float4* xb) {
       const long k0 = k_beg + (long)st * 64 + warp;
-      float4 va[8], vb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long k = k0 + i * 8;
-        const bool in = k < k_end;
-        va[i] = (in && a_ok) ? *reinterpret_cast<const float4*>(A + k * lda + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[i] = (in && b_ok) ? *reinterpret_cast<const float4*>(B + k * ldb + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool in = st < n_steps && k < k_end;
+        xa[i] = (in && a_ok) ? *reinterpret_cast<const float4*>(A + k * lda + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[i] = (in && b_ok) ? *reinterpret_cast<const float4*>(B + k * ldb + m) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    fetch(0, va, vb);
+    for (int st = 0; st < n_steps; ++st) {
+      const int s = st % TN_NSTAGE;
+      fetch(st + 1, na, nb);
       if (st >= TN_NSTAGE) mbar_wait(&empty_bar[s], ((st / TN_NSTAGE) - 1) & 1);
       unsigned char* sb = base + s * TN_STAGE + off0;
 #pragma unroll
@@ -247,6 +252,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) tc_gemm_tn_kernel(const float* 
       }
       fence_async_smem();
       mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { va[i] = na[i]; vb[i] = nb[i]; }
     }
   } else {
     const uint32_t el = elect_one_sync();      // whole warp converged, the elected lane issues

@@ -53,18 +53,46 @@ __device__ __forceinline__ void load_ms_images(unsigned char* msi, const float* 
   }
 }
 
-// tile bookkeeping by the 128 loader threads: sentence bases, row maps
-__device__ __forceinline__ int build_meta(StMeta& m, const int* __restrict__ tso, const int* __restrict__ cst, int tile, int L, int tid) {
-  const int s0 = tso[tile], s1 = tso[tile + 1], ns = s1 - s0, c0 = cst[s0];
+// valid-row tables, software-pipelined by the loader threads: tile boundaries (tso) two tiles ahead, sentence offsets (cst) one tile
+// ahead, so that no table load sits in front of a tile's row loads
+struct TabPipe {
+  int s0c, s1c, s0n, s1n, cbc, cec, c0c, cendc;         // current tile, next tile's boundaries
+  int s0nn, s1nn, cbn, cen, c0n, cendn;                 // in flight
+  __device__ __forceinline__ void ld_tso(const int* __restrict__ tso, int tile, int n_tiles, int& s0, int& s1) {
+    if (tile < n_tiles) { s0 = tso[tile]; s1 = tso[tile + 1]; } else { s0 = s1 = 0; }
+  }
+  __device__ __forceinline__ void ld_cst(const int* __restrict__ cst, int s0, int s1, int tid, int& cb, int& ce, int& c0, int& cend) {
+    c0 = cst[s0]; cend = cst[s1];
+    cb = ce = 0;
+    if (tid < s1 - s0) { cb = cst[s0 + tid]; ce = cst[s0 + tid + 1]; }
+  }
+  __device__ __forceinline__ void init(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
+    ld_tso(tso, tile, n_tiles, s0c, s1c);
+    ld_tso(tso, tile + stride, n_tiles, s0n, s1n);
+    ld_cst(cst, s0c, s1c, tid, cbc, cec, c0c, cendc);
+  }
+  __device__ __forceinline__ void prefetch(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
+    ld_cst(cst, s0n, s1n, tid, cbn, cen, c0n, cendn);       // (past the end s0n == s1n == 0: a harmless read of cst[0])
+    ld_tso(tso, tile + 2 * stride, n_tiles, s0nn, s1nn);
+  }
+  __device__ __forceinline__ void rotate() {
+    s0c = s0n; s1c = s1n; s0n = s0nn; s1n = s1nn;
+    cbc = cbn; cec = cen; c0c = c0n; cendc = cendn;
+  }
+};
+
+// tile bookkeeping by the loader threads: sentence bases, row maps (table values from the pipeline above)
+__device__ __forceinline__ int build_meta(StMeta& m, const TabPipe& tp, int L, int tid) {
+  const int s0 = tp.s0c, ns = tp.s1c - s0, c0 = tp.c0c;
   if (tid < ns) {
-    const int b = cst[s0 + tid] - c0, e = cst[s0 + tid + 1] - c0;
+    const int b = tp.cbc - c0, e = tp.cec - c0;
     m.sbase[tid] = b;
     if (tid == ns - 1) m.sbase[ns] = e;
     const int g0 = (s0 + tid) * L - b;
     for (int r = b; r < e; ++r) { m.rowmap[r] = g0 + r; m.rsent[r] = (short)tid; }
   }
   if (tid == 0) { m.s0 = s0; m.ns = ns; }
-  return cst[s1] - c0;
+  return tp.cendc - c0;
 }
 
 // the e = x·Ms^T product of one tile (24 MMAs)
@@ -106,7 +134,7 @@ constexpr int SF_THREADS = 416;
 __global__ void __launch_bounds__(SF_THREADS, 1) snet_fwd_tc_kernel(const float* __restrict__ x, const int* __restrict__ tso,
                                                                     const int* __restrict__ cst, const float* __restrict__ Ms,
                                                                     const float* __restrict__ Ws, int n_tiles, int L,
-                                                                    float* __restrict__ self_atte) {
+                                                                    float* __restrict__ self_atte, int dbg) {
   extern __shared__ unsigned char raw[];
   __shared__ uint64_t a_full[ST_NSTAGE], a_empty[ST_NSTAGE], acc_full[2], acc_empty[2], m_full[ST_NMETA];
   __shared__ uint32_t tmem_slot;
@@ -138,25 +166,31 @@ __global__ void __launch_bounds__(SF_THREADS, 1) snet_fwd_tc_kernel(const float*
   const uint32_t tmem = tmem_slot;
 
   if (warp < 8) {
+    TabPipe tp;
+    tp.init(tso, cst, blockIdx.x, gridDim.x, n_tiles, tid);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int s = it % ST_NSTAGE;
+      tp.prefetch(tso, cst, tile, gridDim.x, n_tiles, tid);
       if (it >= ST_NSTAGE) mbar_wait(&a_empty[s], ((it / ST_NSTAGE) - 1) & 1);
       StMeta& m = meta[it % ST_NMETA];
-      const int rows = build_meta(m, tso, cst, tile, L, tid);
+      const int rows = build_meta(m, tp, L, tid);
       bar_sync(1, 256);
       unsigned char* st = xim + s * ST_XIMG + (lane >> 4) * 32768;      // channel half of this lane
       float4 va[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int r = i * 8 + warp;
-        va[i] = r < rows ? *reinterpret_cast<const float4*>(x + (size_t)m.rowmap[r] * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        va[i] = (r < rows && !(dbg & 2)) ? *reinterpret_cast<const float4*>(x + (size_t)m.rowmap[r] * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (!(dbg & 4)) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) store_split4(st, st + 16384, i * 8 + warp, (lane & 15) * 4, va[i]);
+        for (int i = 0; i < 16; ++i) store_split4(st, st + 16384, i * 8 + warp, (lane & 15) * 4, va[i]);
+      }
       fence_async_smem();
       mbar_arrive(&a_full[s]);
       mbar_arrive(&m_full[it % ST_NMETA]);
+      tp.rotate();
     }
   } else if (warp == 8) {
     const uint32_t el = elect_one_sync();
@@ -176,6 +210,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) snet_fwd_tc_kernel(const float*
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t o = (uint64_t)(kk * 2);
+          if (dbg & 8) break;
           umma_bf16_e(el, d, ah + o, bh + o, idesc, (kb | kk) != 0);
           umma_bf16_e(el, d, ah + o, bl + o, idesc, 1);
           umma_bf16_e(el, d, al + o, bh + o, idesc, 1);
@@ -194,23 +229,47 @@ __global__ void __launch_bounds__(SF_THREADS, 1) snet_fwd_tc_kernel(const float*
       tc_fence_after();
       const StMeta& m = meta[it % ST_NMETA];
       float sc = 0.f;
+      if (!(dbg & 1)) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * ATT + h * 32, v);
+        for (int h = 0; h < 2; ++h) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * ATT + h * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) sc += ws_s[h * 32 + i] * tanh_fast(v[i]);
+          for (int i = 0; i < 32; ++i) sc += ws_s[h * 32 + i] * tanh_fast(v[i]);
+        }
       }
       score[r] = sc;
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       bar_sync(2, 128);
-      if (et < m.ns) { float ps; sentence_softmax(m, et, L, score, soft, ps); }
+      // softmax over the L positions of each sentence, a thread per ROW (the rows of a sentence recompute its max and sum in the same
+      // order - a thread per sentence would leave all but ~15 of the 128 threads idle behind the longest sentence)
+      {
+        const int rows = m.sbase[m.ns];
+        float ex = 0.f, mx = 0.f;
+        int b = 0, e = 0, npad = 0;
+        if (r < rows && !(dbg & 16)) {
+          const int j = m.rsent[r];
+          b = m.sbase[j]; e = m.sbase[j + 1]; npad = L - (e - b);
+          mx = npad > 0 ? 0.f : -INFINITY;
+          for (int rr = b; rr < e; ++rr) mx = fmaxf(mx, score[rr]);
+          ex = expf(score[r] - mx);
+          soft[r] = ex;
+        }
+        bar_sync(2, 128);
+        if (r < rows && !(dbg & 16)) {
+          float sum = npad > 0 ? (float)npad * expf(-mx) : 0.f;
+          for (int rr = b; rr < e; ++rr) sum += soft[rr];
+          ex *= 1.f / sum;
+        }
+        bar_sync(2, 128);
+        if (r < rows) soft[r] = ex;
+      }
       bar_sync(2, 128);
       // pooling: self_atte[n] = sum_l soft[l] x[n,l]  (a warp per sentence, lanes = channel quads, rows from the operand image)
       const unsigned char* img = xim + s * ST_XIMG + (lane >> 4) * 32768;
       const int k = (lane & 15) * 4;
-      for (int j = (warp - 9); j < m.ns; j += 4) {
+      for (int j = (warp - 9); j < m.ns && !(dbg & 32); j += 4) {
         const int b = m.sbase[j], e = m.sbase[j + 1];
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int rr = b; rr < e; ++rr) {
@@ -278,14 +337,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
 
   if (warp < 4) {
     // ------------------------------------------------------------------ loaders (+ d_soft = <x row, d_self_atte of its sentence>)
+    TabPipe tp;
+    tp.init(tso, cst, blockIdx.x, gridDim.x, n_tiles, tid);
     for (int it = 0; it < n_mine; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = it % ST_NSTAGE;
+      tp.prefetch(tso, cst, tile, gridDim.x, n_tiles, tid);
       if (it >= ST_NSTAGE) mbar_wait(&bar.a_empty[s], ((it / ST_NSTAGE) - 1) & 1);
       StMeta& m = meta[it % ST_NMETA];
-      const int rows = build_meta(m, tso, cst, tile, L, tid);
+      const int rows = build_meta(m, tp, L, tid);
       bar_sync(1, 128);
-      const int s0 = tso[tile];
+      const int s0 = tp.s0c;
       unsigned char* st = xim + s * ST_XIMG;
       float dot[16];
 #pragma unroll
@@ -318,6 +380,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       fence_async_smem();
       mbar_arrive(&bar.a_full[s]);
       mbar_arrive(&bar.m_full[it % ST_NMETA]);
+      tp.rotate();
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
@@ -506,7 +569,7 @@ extern "C" int umpr_snet_fwd_tc(const float* x, const int* table, int n_tiles, c
   if (e != cudaSuccess) { set_error("snet_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  snet_fwd_tc_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, Ms, Ws, n_tiles, L, self_atte);
+  snet_fwd_tc_kernel<<<grid, SF_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, Ms, Ws, n_tiles, L, self_atte, dbg_flags());
   return check_launch("snet_fwd_tc");
 }
 

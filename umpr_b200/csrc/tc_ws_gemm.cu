@@ -1,8 +1,9 @@
 // Weight-stationary persistent tcgen05 GEMM: C[M][BN] = A[M][K] · B[BN][K]^T, K = KB*64, B resident in shared memory.
 // One CTA per SM loops over 128-row tiles of A:
-//   warps 0-3  loaders   : global fp32 rows -> bf16 hi/lo -> SWIZZLE_128B shared memory (NSTAGE-deep ring)
-//   warp  4    MMA issuer: one elected thread, 3xBF16 (hi*hi + hi*lo + lo*hi) into one of two TMEM accumulators
-//   warps 5-8  epilogue  : tcgen05.ld -> bias/accumulate/activation -> shared-memory transpose -> coalesced 128-B row stores
+//   warps 0-7  loaders   : global fp32 rows -> bf16 hi/lo -> SWIZZLE_128B shared memory (NSTAGE-deep ring); the whole tile's loads
+//                          are in flight together, the valid-row tables of the next tiles are fetched one / two tiles ahead
+//   warp  8    MMA issuer: one elected thread, 3xBF16 (hi*hi + hi*lo + lo*hi) into one of two TMEM accumulators
+//   warps 9-12 epilogue  : tcgen05.ld -> bias/accumulate/activation -> shared-memory transpose -> coalesced 128-B row stores
 // so the loads of tile i+1, the MMAs of tile i and the stores of tile i-1 overlap.  The same skeleton (resident weights,
 // TMEM double buffer, mbarrier hand-offs) is what the GRU recurrence kernel uses.
 //   MODE 0: plain (gi·M, dgiM·M^T of model.py:50 and its backward)      MODE 1: GRU input projection (model.py:19)
@@ -13,7 +14,7 @@
 namespace umpr {
 using namespace tc;
 
-constexpr int WS_THREADS = 288;   // 9 warps
+constexpr int WS_THREADS = 416;   // 13 warps: 0-7 loaders, 8 MMA issuer, 9-12 epilogue
 constexpr int WS_STG_LD = 36;     // floats per staged row (32 + 4: conflict-free 128-bit accesses)
 
 struct WsArgs {
@@ -28,6 +29,7 @@ struct WsArgs {
   // valid-row mode (MODE 0): tiles of whole consecutive sentences, <= 128 valid rows each (plan.py:snet_table); row r of sentence n is
   // global row n*L + r.  tso == NULL: plain 128-row tiles of all M rows
   const int* tso; const int* cst; int L, n_row_tiles;
+  int dbg;
 };
 
 constexpr int WS_NMETA = 8;      // deeper than stages + accumulators: the slot of tile it-8 is free for every NSTAGE
@@ -58,12 +60,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
   const int n_tiles = by_rows ? a.n_row_tiles : (a.M + 127) / 128;
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
-    for (int s = 0; s < WS_NMETA; ++s) mbar_init(&m_full[s], 128);
+    for (int s = 0; s < WS_NMETA; ++s) mbar_init(&m_full[s], 256);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, TCOLS);
+  if (warp == 8) tmem_alloc(&tmem_slot, TCOLS);
   // ---- resident B (weights), loaded once by all threads
   for (int idx = tid; idx < KB * BN * 16; idx += WS_THREADS) {
     const int kb = idx / (BN * 16), rem = idx - kb * BN * 16;
@@ -91,11 +93,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------------------------------------------ loaders
+    // valid-row tables, software-pipelined: tile boundaries (tso) two tiles ahead, sentence offsets (cst) one tile ahead, so that no
+    // table load sits in front of a tile's row loads
+    int s0c = 0, s1c = 0, s0n = 0, s1n = 0, cbc = 0, cec = 0, c0c = 0, cendc = 0;
+    auto ld_tso = [&](int tile, int& s0, int& s1) { if (tile < n_tiles) { s0 = a.tso[tile]; s1 = a.tso[tile + 1]; } else { s0 = s1 = 0; } };
+    auto ld_cst = [&](int s0, int s1, int& cb, int& ce, int& c0, int& cend) {
+      c0 = a.cst[s0]; cend = a.cst[s1];
+      if (tid < s1 - s0) { cb = a.cst[s0 + tid]; ce = a.cst[s0 + tid + 1]; }
+    };
+    if (by_rows) {
+      ld_tso(blockIdx.x, s0c, s1c);
+      ld_tso(blockIdx.x + gridDim.x, s0n, s1n);
+      ld_cst(s0c, s1c, cbc, cec, c0c, cendc);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int s = it % NSTAGE;
+      int s0nn = 0, s1nn = 0, cbn = 0, cen = 0, c0n = 0, cendn = 0;
+      if (by_rows) {
+        ld_cst(s0n, s1n, cbn, cen, c0n, cendn);                    // next tile (s0n == s1n == 0 past the end: harmless reads of cst[0])
+        ld_tso(tile + 2 * gridDim.x, s0nn, s1nn);
+      }
       if (it >= NSTAGE) mbar_wait(&a_empty[s], ((it / NSTAGE) - 1) & 1);
       unsigned char* st = asm_ + s * SM::A_STAGE;
       const int m0 = tile * 128;
@@ -104,25 +124,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       if (by_rows) {
         // slot it % 8 is free: the ring wait above implies the epilogue of tile it-5 has finished (it arrives acc_empty last)
         WsMeta& mw = meta[MODE == 0 ? it % WS_NMETA : 0];
-        const int s0 = a.tso[tile], ns = a.tso[tile + 1] - s0, c0 = a.cst[s0];
-        if (tid < ns) {
-          const int b = a.cst[s0 + tid] - c0, e = a.cst[s0 + tid + 1] - c0, g0 = (s0 + tid) * a.L - b;
+        if (tid < s1c - s0c) {
+          const int b = cbc - c0c, e = cec - c0c, g0 = (s0c + tid) * a.L - b;
           for (int r = b; r < e; ++r) mw.rowmap[r] = g0 + r;
         }
-        rows = a.cst[s0 + ns] - c0;
+        rows = cendc - c0c;
         if (tid == 0) mw.rows = rows;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-#pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) {
-        unsigned char* a_hi = st + kb * 2 * 128 * 128, *a_lo = a_hi + 128 * 128;
-        float4 va[16];
+      float4 va[KB][8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
+      for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
           const int m = by_rows ? (r < rows ? mt.rowmap[r] : a.M) : m0 + r;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < a.M) {
+          if (m < a.M && !(a.dbg & 2)) {
             const float* p = a.A + (long)m * a.lda + k;
             if (k + 3 < a.K) v = *reinterpret_cast<const float4*>(p);
             else {
@@ -131,19 +149,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
               if (k + 2 < a.K) v.z = p[2];
             }
           }
-          va[i] = v;
+          va[kb][i] = v;
         }
+      }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid;
-          store_split4(a_hi, a_lo, idx >> 4, (idx & 15) * 4, va[i]);
+      for (int kb = 0; kb < KB; ++kb) {
+        if (a.dbg & 4) break;
+        unsigned char* a_hi = st + kb * 2 * 128 * 128, *a_lo = a_hi + 128 * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 256 + tid;
+          store_split4(a_hi, a_lo, idx >> 4, (idx & 15) * 4, va[kb][i]);
         }
       }
       fence_async_smem();
       mbar_arrive(&a_full[s]);
       if (by_rows) mbar_arrive(&m_full[it % WS_NMETA]);
+      s0c = s0n; s1c = s1n; s0n = s0nn; s1n = s1nn;
+      cbc = cbn; cec = cen; c0c = c0n; cendc = cendn;
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
     {
       const uint32_t el = elect_one_sync();
@@ -163,6 +188,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
           const uint64_t bh = smem_desc_sw128(b0 + kb * 2 * BN * 128), bl = smem_desc_sw128(b0 + kb * 2 * BN * 128 + BN * 128);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (a.dbg & 8) break;
             const uint64_t o = (uint64_t)(kk * 2);
             umma_bf16_e(el, d, ah + o, bh + o, idesc, (kb | kk) != 0);
             umma_bf16_e(el, d, ah + o, bl + o, idesc, 1);
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 5..8 -> TMEM lane quarter warp%4)
+    // ------------------------------------------------------------------ epilogue (warps 9..12 -> TMEM lane quarter warp%4)
     const int q = warp & 3;
     float* sw = stg + q * 32 * WS_STG_LD;
     int it = 0;
@@ -185,51 +211,67 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       const WsMeta& mt = meta[MODE == 0 ? it % WS_NMETA : 0];
       if (by_rows) mbar_wait(&m_full[it % WS_NMETA], (it / WS_NMETA) & 1);
       // global row of tile row rr (a.M = none)
-      auto grow = [&](int rr) { return by_rows ? (q * 32 + rr < mt.rows ? mt.rowmap[q * 32 + rr] : a.M) : m0 + rr; };
+      auto grow = [&](int rr) { return (by_rows && !(a.dbg & 64)) ? (q * 32 + rr < mt.rows ? mt.rowmap[q * 32 + rr] : a.M) : m0 + rr; };
+      // the 8 output rows this thread stores (row j*4 + lane/8 of the warp's 32, 4 columns at c4): resolved once per tile
+      float* crow[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int m = grow(j * 4 + (lane >> 3));
+        crow[j] = nullptr;
+        if (m < a.M) {
+          if (MODE == 1) {
+            const int slab = m / a.R, rr = m - slab * a.R;
+            crow[j] = a.C + (((long)slab * 2 + dir) * a.R + rr) * G3 + c4;
+          } else {
+            crow[j] = a.C + (long)m * a.ldc + c4;
+          }
+        }
+      }
+      const bool acc_c = MODE == 0 && a.accumulate;
+      const bool plain = MODE == 1 || (!a.accumulate && !a.bias && a.act == 0);
       // accumulate mode: the C rows of a 32-column chunk are requested one chunk ahead (the first one before the accumulator
       // is even ready), so their latency hides behind the TMEM load / staging of the previous chunk
       float4 cnext[8];
-      const bool acc_c = MODE == 0 && a.accumulate;
       auto fetch_c = [&](int c0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int m = grow(j * 4 + (lane >> 3)), n = c0 + c4;
-          cnext[j] = (m < a.M && n < a.N) ? *reinterpret_cast<const float4*>(a.C + (long)m * a.ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int j = 0; j < 8; ++j)
+          cnext[j] = (crow[j] && c0 + c4 < a.N) ? *reinterpret_cast<const float4*>(crow[j] + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       if (acc_c) fetch_c(0);
       mbar_wait(&acc_full[acc], (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (a.dbg & 1) break;
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + acc * BN + c0, v);
-        float4 ccur[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ccur[j] = cnext[j];
-        if (acc_c && c0 + 32 < BN) fetch_c(c0 + 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(&sw[lane * WS_STG_LD + j * 4]) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         __syncwarp();
-        const int n = c0 + c4;
+        const bool col_ok = c0 + c4 < a.N;
+        if (plain) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = j * 4 + (lane >> 3), m = grow(r);
-          if (m < a.M && n < a.N) {
-            float4 o = *reinterpret_cast<const float4*>(&sw[r * WS_STG_LD + c4]);
-            float* crow;
-            if (MODE == 1) {
-              const int slab = m / a.R, rr = m - slab * a.R;
-              crow = a.C + (((long)slab * 2 + dir) * a.R + rr) * G3 + n;
-            } else {
-              crow = a.C + (long)m * a.ldc + n;
+          for (int j = 0; j < 8; ++j) {
+            const float4 o = *reinterpret_cast<const float4*>(&sw[(j * 4 + (lane >> 3)) * WS_STG_LD + c4]);
+            if (crow[j] && col_ok) *reinterpret_cast<float4*>(crow[j] + c0) = o;
+          }
+        } else {
+          float4 ccur[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ccur[j] = cnext[j];
+          if (acc_c && c0 + 32 < BN) fetch_c(c0 + 32);
+          const int n = c0 + c4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (crow[j] && col_ok) {
+              float4 o = *reinterpret_cast<const float4*>(&sw[(j * 4 + (lane >> 3)) * WS_STG_LD + c4]);
               if (a.accumulate) { o.x += ccur[j].x; o.y += ccur[j].y; o.z += ccur[j].z; o.w += ccur[j].w; }
               if (a.bias) { o.x += a.bias[n]; o.y += a.bias[n + 1]; o.z += a.bias[n + 2]; o.w += a.bias[n + 3]; }
               if (a.act == 1) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
               else if (a.act == 2) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(crow[j] + c0) = o;
             }
-            *reinterpret_cast<float4*>(crow) = o;
           }
         }
         __syncwarp();
@@ -240,7 +282,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, TCOLS);
+  if (warp == 8) tmem_dealloc(tmem, TCOLS);
 }
 
 template <int BN, int KB, int NSTAGE, int MODE> static int launch_ws(const WsArgs& a, int n_ctas, int gy, cudaStream_t st) {
@@ -272,7 +314,7 @@ extern "C" int umpr_tc_gemm_ws(const float* A, long lda, const float* B, long ld
   if (act < 0 || act > 2) return fail_arg("tc_gemm_ws: act=%d", act);
   WsArgs a{};
   a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.b_kn = b_kn; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-  a.accumulate = accumulate; a.act = act; a.bias = bias;
+  a.accumulate = accumulate; a.act = act; a.bias = bias; a.dbg = dbg_flags();
   if (table) {
     if (n_row_tiles < 1 || L < 1 || L > 128 || M % L) return fail_arg("tc_gemm_ws: row table inconsistent (n_row_tiles=%d, L=%d, M=%d)", n_row_tiles, L, M);
     a.tso = table; a.cst = table + n_row_tiles + 1; a.L = L; a.n_row_tiles = n_row_tiles;
