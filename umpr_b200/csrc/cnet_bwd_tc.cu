@@ -245,145 +245,224 @@ __global__ void cnet_bwd_wimg_kernel(const float* __restrict__ w, int KC, unsign
   store_split4(img, img + 16384, c, kk, make_float4(t[0], t[1], t[2], t[3]));
 }
 
-struct CxBars { uint64_t m_full[CB_NMETA], g_ready[2], g_free[2], w_full[2], w_empty[2], acc_full[2], acc_empty[2]; };
+// ---- v2 ----------------------------------------------------------------------------------------------------------------
+// ONE gradient image per tile instead of one one-hot tile per (tap, filter half):  dY[r][k] = g[n][k] at the tile row r of the
+// winning position (zero elsewhere; positions beyond the sentence's trailing guard row touch no valid x row and are dropped), laid
+// out like the forward's x image - [filter half][hi|lo][130 rows][64 bf16], image row = tile row + 1 - and
+//     dX[r][c] = sum_j sum_k dY[r + 1 - j][k] W[k][c][j]
+// reads it through descriptors shifted by (2 - j) rows: zero-fill + scatter ONCE per tile, 72 MMAs back to back.  Two tiles share
+// every weight stage (tap, filter half: 32 KB by TMA bulk copy); K runs over the first filter half (3 taps), then the second, so the
+// scatter of the NEXT pair's first half runs under the MMAs of this pair's second half.
+//   warps 0-3 / 4-7: bookkeeping + scatter of the first / second tile of a pair, warp 8: weight producer, warp 9: MMA issuer,
+//   warps 10-13: epilogue (valid rows only, row pointers resolved once per tile, 64-byte row pieces)
+constexpr int DX_THREADS = 448;
+constexpr int DX_GSUB = 17 * 1024;       // [136 rows][128 B]
+constexpr int DX_GIMG = 4 * DX_GSUB;     // [filter half 2][hi|lo]
+constexpr int DX_WST = 32768;            // one weight stage: [hi|lo][128 c rows][128 B] of (tap, filter half)
+constexpr int DX_NMETA = 8;
+constexpr int DX_STG_LD = 20;            // 16 staged columns + 4 floats of padding
+constexpr int DX_RC = 8;                 // (gradient, position) pairs per filter half a scatter thread prefetches into registers
 
-__global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
+struct DxBars { uint64_t m_full[DX_NMETA], g_full[2], g_empty[2], w_full[2], w_empty[2], acc_full[2], acc_empty[2]; };
+struct DxCache { float g[2][DX_RC]; int t[2][DX_RC]; };
+
+__global__ void __launch_bounds__(DX_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(const float* __restrict__ dcfeat, const int* __restrict__ cidx,
                                                                             const unsigned char* __restrict__ wimg, const int* __restrict__ tso,
                                                                             const int* __restrict__ cstc, int n_tiles, int L, int KC,
-                                                                            float* __restrict__ dx) {
+                                                                            float* __restrict__ dx, int dbg) {
   extern __shared__ unsigned char raw[];
-  __shared__ CxBars bar;
+  __shared__ DxBars bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ CbMeta meta[CB_NMETA];
+  __shared__ CbMeta meta[DX_NMETA];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* gim = base;
-  unsigned char* wsm = base + CB_GIMG;             // 2 stages of one tap's weights
-  float* stg = reinterpret_cast<float*>(base + CB_GIMG + 2 * CX_WIMG);
+  unsigned char* gim = base;                               // [tile of the pair 2][DX_GIMG]
+  unsigned char* wsm = base + 2 * DX_GIMG;                 // [2][DX_WST]
+  float* stg = reinterpret_cast<float*>(base + 2 * DX_GIMG + 2 * DX_WST);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int n_mine = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
+  const int n_pairs = (n_mine + 1) >> 1;
 
   if (tid == 0) {
-    for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar.g_ready[s], 128); mbar_init(&bar.g_free[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar.w_full[s], 1); mbar_init(&bar.w_empty[s], 1); mbar_init(&bar.acc_full[s], 1); mbar_init(&bar.acc_empty[s], 128); }
+    for (int s = 0; s < DX_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar.g_full[s], 256); mbar_init(&bar.g_empty[s], 1);
+      mbar_init(&bar.w_full[s], 1); mbar_init(&bar.w_empty[s], 1);
+      mbar_init(&bar.acc_full[s], 1); mbar_init(&bar.acc_empty[s], 128);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&tmem_slot, 256);
+  if (warp == 9) tmem_alloc(&tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ tile bookkeeping + gradient scatter
-    const int et = tid;
-    int q = 0;
-    for (int it = 0; it < n_mine; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      // meta slot it % 4: the epilogue of tile it-4 finished before the accumulator ring let tile it-2's MMAs start, and the last of
-      // those has retired (g_free of step q-2) before the bookkeeping below is written - so the slot is free
-      CbMeta& m = meta[it % CB_NMETA];
-      if (q >= 2) mbar_wait(&bar.g_free[q & 1], ((q >> 1) - 1) & 1);
-      m.rowsrc[tid] = -1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (warp < 8) {
+    // ------------------------------------------------------------------ tile bookkeeping + gradient scatter: group jt owns tile jt of a pair
+    const int jt = warp >> 2, et = tid & 127, kk = et & 63, sg = et >> 6;
+    unsigned char* img = gim + jt * DX_GIMG;
+    auto build = [&](int t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      CbMeta& m = meta[t % DX_NMETA];
+      m.rowsrc[et] = -1;
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + jt) : "memory");
       const int s0 = tso[tile], ns = tso[tile + 1] - s0;
-      if (tid < ns) {
-        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
-        m.sb[tid] = b; m.len[tid] = len;
-        const int g0 = (s0 + tid) * L;
+      if (et < ns) {
+        const int c0 = cstc[s0], b = cstc[s0 + et] - c0, len = cstc[s0 + et + 1] - cstc[s0 + et] - 2;
+        m.sb[et] = b; m.len[et] = len;
+        const int g0 = (s0 + et) * L;
         for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
       }
-      if (tid == 0) { m.s0 = s0; m.ns = ns; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_arrive(&bar.m_full[it % CB_NMETA]);
-      GradCache gc;
-      grad_cache_load(gc, dcfeat, cidx, s0, ns, KC, et);
-      for (int j = 0; j < 3; ++j)
-        for (int h = 0; h < 2; ++h, ++q) {
-          const int gb = q & 1;
-          if (q >= 2) mbar_wait(&bar.g_free[gb], ((q >> 1) - 1) & 1);
-          grad_scatter_step(gim + gb * CB_GHALF, m, gc, dcfeat, cidx, KC, j, h, et, 1);
-          mbar_arrive(&bar.g_ready[gb]);
-        }
-    }
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer (tap weights) + MMA issuer
-    if (n_mine > 0) {       // whole warp converged, the elected lane issues
-      const uint32_t el = elect_one_sync();
-      constexpr uint32_t idesc = idesc_bf16(128, 128);              // A (G) and B (W_j^T) K-major
-      const uint32_t g0 = smem_u32(gim);
-      const int n_taps = 3 * n_mine;
-      auto fetch = [&](int p) {                                     // weights of tap p % 3 into stage p & 1
-        const int ws = p & 1;
-        if (p >= 2) mbar_wait(&bar.w_empty[ws], ((p >> 1) - 1) & 1);
-        mbar_arrive_expect_tx_e(el, &bar.w_full[ws], CX_WIMG);
-        bulk_copy_g2s_e(el, wsm + ws * CX_WIMG, wimg + (size_t)(p % 3) * CX_WIMG, CX_WIMG, &bar.w_full[ws]);
-      };
-      fetch(0);
-      int q = 0, p = 0;
-      for (int it = 0; it < n_mine; ++it) {
-        const int acc = it & 1;
-        if (it >= 2) mbar_wait(&bar.acc_empty[acc], ((it >> 1) - 1) & 1);
-        for (int j = 0; j < 3; ++j, ++p) {
-          if (p + 1 < n_taps) fetch(p + 1);
-          const int ws = p & 1;
-          mbar_wait(&bar.w_full[ws], (p >> 1) & 1);
-          const uint32_t w0 = smem_u32(wsm + ws * CX_WIMG);
-          for (int h = 0; h < 2; ++h, ++q) {
-            const int gb = q & 1;
-            mbar_wait(&bar.g_ready[gb], (q >> 1) & 1);
-            tc_fence_after();
-            const uint32_t gq0 = g0 + gb * CB_GHALF;
-            const uint64_t gh = smem_desc_sw128(gq0), gl = smem_desc_sw128(gq0 + 16384);
-            const uint64_t wh = smem_desc_sw128(w0 + h * 32768), wl = smem_desc_sw128(w0 + h * 32768 + 16384);
+      if (et == 0) { m.s0 = s0; m.ns = ns; }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + jt) : "memory");
+      mbar_arrive(&bar.m_full[t % DX_NMETA]);
+    };
+    // thread et owns filter kk of each half and every second sentence (sg, sg+2, ...): the first DX_RC of them are fetched ahead
+    auto prefetch = [&](const CbMeta& m, DxCache& c) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t o = (uint64_t)(kk * 2);
-              umma_bf16_e(el, tmem + acc * 128, gh + o, wh + o, idesc, (j | h | kk) != 0);
-              umma_bf16_e(el, tmem + acc * 128, gh + o, wl + o, idesc, 1);
-              umma_bf16_e(el, tmem + acc * 128, gl + o, wh + o, idesc, 1);
-            }
-            umma_commit_e(el, &bar.g_free[gb]);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < DX_RC; ++i) {
+          const int sn = 2 * i + sg, k = h * 64 + kk;
+          c.g[h][i] = 0.f; c.t[h][i] = -1;
+          if (sn < m.ns && k < KC) {
+            const size_t o = (size_t)(m.s0 + sn) * KC + k;
+            c.g[h][i] = dcfeat[o];
+            c.t[h][i] = cidx[o];
           }
-          umma_commit_e(el, &bar.w_empty[ws]);
-          if (j == 2) umma_commit_e(el, &bar.acc_full[acc]);
         }
+    };
+    auto put = [&](unsigned char* half, const CbMeta& m, int sn, float g, int t) {
+      if (g == 0.f || t < 0 || t > m.len[sn]) return;            // positions past the trailing guard row touch no valid x row
+      const int r = m.sb[sn] + t + 2;                             // image row = tile row (sb + 1 + t) + 1
+      const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
+      const uint32_t off = (uint32_t)(r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2);
+      *reinterpret_cast<__nv_bfloat16*>(half + off) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(half + DX_GSUB + off) = lo;
+    };
+    DxCache cur, nxt;
+    if (jt < n_mine) { build(jt); prefetch(meta[jt % DX_NMETA], cur); }
+    for (int p = 0; p < n_pairs; ++p) {
+      const int t = 2 * p + jt;
+      const bool has = t < n_mine && !(dbg & 2);
+      const CbMeta& m = meta[t % DX_NMETA];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (p >= 1) mbar_wait(&bar.g_empty[h], (p - 1) & 1);      // the MMAs of the previous pair are through with this filter half
+        if (has) {
+          unsigned char* half = img + h * 2 * DX_GSUB;
+          for (int i = et; i < 2 * DX_GSUB / 16; i += 128) reinterpret_cast<uint4*>(half)[i] = make_uint4(0u, 0u, 0u, 0u);
+          asm volatile("bar.sync %0, 128;" ::"r"(2 + jt) : "memory");
+#pragma unroll
+          for (int i = 0; i < DX_RC; ++i) put(half, m, 2 * i + sg, cur.g[h][i], cur.t[h][i]);
+          const int k = h * 64 + kk;
+          if (k < KC)
+            for (int sn = 2 * DX_RC + sg; sn < m.ns; sn += 2) {
+              const size_t o = (size_t)(m.s0 + sn) * KC + k;
+              put(half, m, sn, dcfeat[o], cidx[o]);
+            }
+          fence_async_smem();
+        }
+        mbar_arrive(&bar.g_full[h]);
+        if (h == 0 && t + 2 < n_mine) { build(t + 2); prefetch(meta[(t + 2) % DX_NMETA], nxt); }      // next pair, early
       }
+      cur = nxt;
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ weight producer: stage (filter half kb, tap j), 6 per pair
+    const uint32_t el = elect_one_sync();
+    const int n_it = n_pairs * 6;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1, st = it % 6, kb = st / 3, j = st - 3 * kb;
+      if (it >= 2) mbar_wait(&bar.w_empty[s], ((it >> 1) - 1) & 1);
+      mbar_arrive_expect_tx_e(el, &bar.w_full[s], DX_WST);
+      bulk_copy_g2s_e(el, wsm + s * DX_WST, wimg + (size_t)j * CX_WIMG + kb * DX_WST, DX_WST, &bar.w_full[s]);
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
+    const uint32_t el = elect_one_sync();
+    constexpr uint32_t idesc = idesc_bf16(128, 128);              // A (dY) and B (W_j^T) K-major
+    int wit = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+      const int buf = p & 1;
+      const bool two = 2 * p + 1 < n_mine;
+      if (p >= 2) mbar_wait(&bar.acc_empty[buf], ((p >> 1) - 1) & 1);
+#pragma unroll 1
+      for (int st = 0; st < 6; ++st, ++wit) {
+        const int s = wit & 1, kb = st / 3, j = st - 3 * kb;
+        mbar_wait(&bar.w_full[s], (wit >> 1) & 1);
+        if (j == 0) mbar_wait(&bar.g_full[kb], p & 1);
+        tc_fence_after();
+        const uint32_t w0 = smem_u32(wsm + s * DX_WST);
+        const uint64_t wh = smem_desc_sw128(w0), wl = smem_desc_sw128(w0 + 16384);
+#pragma unroll
+        for (int t2 = 0; t2 < 2; ++t2) {
+          if (t2 == 1 && !two) break;
+          const uint32_t g0 = smem_u32(gim + t2 * DX_GIMG + kb * 2 * DX_GSUB) + (2 - j) * 128;      // dY rows r + 1 - j
+          const uint64_t gh = smem_desc_sw128(g0), gl = smem_desc_sw128(g0 + DX_GSUB);
+          const uint32_t d = tmem + buf * 256 + t2 * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (dbg & 4) break;
+            const uint64_t o = (uint64_t)(q * 2);
+            umma_bf16_e(el, d, gh + o, wh + o, idesc, (st | q) != 0);
+            umma_bf16_e(el, d, gh + o, wl + o, idesc, 1);
+            umma_bf16_e(el, d, gl + o, wh + o, idesc, 1);
+          }
+        }
+        umma_commit_e(el, &bar.w_empty[s]);
+        if (j == 2) umma_commit_e(el, &bar.g_empty[kb]);
+      }
+      umma_commit_e(el, &bar.acc_full[buf]);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: valid rows of dx, coalesced 128-byte row stores
+    // ------------------------------------------------------------------ epilogue: valid rows of dx
     const int q4 = warp & 3;
-    float* sw = stg + q4 * 32 * CX_STG_LD;
-    for (int it = 0; it < n_mine; ++it) {
-      const int acc = it & 1;
-      mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
-      const CbMeta& m = meta[it % CB_NMETA];
-      mbar_wait(&bar.acc_full[acc], (it >> 1) & 1);
+    float* sw = stg + q4 * 32 * DX_STG_LD;
+    const int c4 = (lane & 3) * 4;
+    for (int p = 0; p < n_pairs; ++p) {
+      const int buf = p & 1;
+      mbar_wait(&bar.acc_full[buf], (p >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + acc * 128 + c0, v);
+      for (int t2 = 0; t2 < 2; ++t2) {
+        const int t = 2 * p + t2;
+        if (t >= n_mine) break;
+        mbar_wait(&bar.m_full[t % DX_NMETA], (t / DX_NMETA) & 1);
+        if (dbg & 1) continue;
+        const CbMeta& m = meta[t % DX_NMETA];
+        float* orow[4];                                             // the 4 output rows this thread stores (row i*8 + lane/4 of the warp's 32)
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj)
-          *reinterpret_cast<float4*>(&sw[lane * CX_STG_LD + jj * 4]) = make_float4(v[jj * 4], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
-        __syncwarp();
-        const int c = c0 + (lane & 7) * 4;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const int rr = jj * 4 + (lane >> 3), src = m.rowsrc[q4 * 32 + rr];
-          if (src >= 0) *reinterpret_cast<float4*>(dx + (size_t)src * D + c) = *reinterpret_cast<const float4*>(&sw[rr * CX_STG_LD + (lane & 7) * 4]);
+        for (int i = 0; i < 4; ++i) {
+          const int src = m.rowsrc[q4 * 32 + i * 8 + (lane >> 2)];
+          orow[i] = src >= 0 ? dx + (size_t)src * D + c4 : nullptr;
         }
-        __syncwarp();
+        const uint32_t trow = tmem + ((uint32_t)(q4 * 32) << 16) + buf * 256 + t2 * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < D; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + c0, v);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<float4*>(&sw[lane * DX_STG_LD + jj * 4]) = make_float4(v[jj * 4], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 o = *reinterpret_cast<const float4*>(&sw[(i * 8 + (lane >> 2)) * DX_STG_LD + c4]);
+            if (orow[i]) *reinterpret_cast<float4*>(orow[i] + c0) = o;
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
-      mbar_arrive(&bar.acc_empty[acc]);
+      mbar_arrive(&bar.acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
+  if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace umpr
@@ -417,13 +496,13 @@ extern "C" int umpr_cnet_conv_bwd_dx_tc(const float* dcfeat, const int32_t* cidx
   if (!wimg_scratch || (reinterpret_cast<uintptr_t>(wimg_scratch) & 15)) return fail_arg("cnet_conv_bwd_dx_tc: scratch must be 16-byte aligned");
   cnet_bwd_wimg_kernel<<<(3 * 2 * 128 * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, reinterpret_cast<unsigned char*>(wimg_scratch));
   if (int e = check_launch("cnet_bwd_wimg")) return e;
-  constexpr int smem = CB_GIMG + 2 * CX_WIMG + 4 * 32 * CX_STG_LD * 4 + 1024;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+  constexpr int smem = 2 * DX_GIMG + 2 * DX_WST + 4 * 32 * DX_STG_LD * 4 + 1024;
+  static_assert(smem <= 220 * 1024, "shared memory budget (the bookkeeping ring is static shared memory on top)");
   cudaError_t e = cudaFuncSetAttribute(cnet_conv_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("cnet_conv_bwd_dx_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  cnet_conv_bwd_dx_tc_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(dcfeat, cidx, reinterpret_cast<const unsigned char*>(wimg_scratch),
-                                                                              table, table + n_tiles + 1, n_tiles, L, KC, dx);
+  cnet_conv_bwd_dx_tc_kernel<<<grid, DX_THREADS, smem, (cudaStream_t)stream>>>(dcfeat, cidx, reinterpret_cast<const unsigned char*>(wimg_scratch),
+                                                                              table, table + n_tiles + 1, n_tiles, L, KC, dx, dbg_flags());
   return check_launch("cnet_conv_bwd_dx_tc");
 }
