@@ -27,204 +27,6 @@ struct CbMeta {
   int rowsrc[128];                      // tile row -> global x row, -1 = zero row
 };
 
-constexpr int CB_GHALF = 32768;         // one half (64 filters) of a one-hot gradient tile: [hi|lo][128 rows][128 B]
-
-// The scatter side of both kernels.  A step = (tap j, filter half h); its one-hot tile G[r][k] (k in that half) holds g[n][k] at the
-// row r that tap j of sentence n's winning window touches.  Two half-tile buffers ping-pong with the MMA issuer, so the scatter of
-// step q+1 runs under the MMAs of step q.  Thread et owns filter column kk = et & 63 of the half and every second sentence.
-struct GradCache {
-  float g[2][CB_RC / 2];
-  int t[2][CB_RC / 2];
-};
-__device__ __forceinline__ void grad_cache_load(GradCache& c, const float* __restrict__ dcfeat, const int* __restrict__ cidx, int s0, int ns,
-                                                int KC, int et) {
-  const int kk = et & 63, sg = et >> 6;
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int i = 0; i < CB_RC / 2; ++i) {
-      const int sn = 2 * i + sg, k = h * 64 + kk;
-      c.g[h][i] = 0.f; c.t[h][i] = -1;
-      if (sn < ns && k < KC) {
-        const size_t o = (size_t)(s0 + sn) * KC + k;
-        c.g[h][i] = dcfeat[o];
-        c.t[h][i] = cidx[o];
-      }
-    }
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int i = 0; i < CB_RC / 2; ++i)
-      if (c.g[h][i] == 0.f) c.t[h][i] = -1;
-}
-__device__ __forceinline__ void grad_put(unsigned char* gbuf, const CbMeta& m, int sn, int kk, float g, int row) {
-  if (row < 0 || row >= m.len[sn]) return;
-  const int r = m.sb[sn] + 1 + row;
-  const __nv_bfloat16 hi = __float2bfloat16_rn(g);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
-  const uint32_t off = (uint32_t)(r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2);
-  *reinterpret_cast<__nv_bfloat16*>(gbuf + off) = hi;
-  *reinterpret_cast<__nv_bfloat16*>(gbuf + 16384 + off) = lo;
-}
-// one step: zero the half tile, scatter (register-cached pairs first, the rest re-read), publish
-__device__ __forceinline__ void grad_scatter_step(unsigned char* gbuf, const CbMeta& m, const GradCache& c, const float* __restrict__ dcfeat,
-                                                  const int* __restrict__ cidx, int KC, int j, int h, int et, int bar_id) {
-  for (int i = et; i < CB_GHALF / 16; i += 128) reinterpret_cast<uint4*>(gbuf)[i] = make_uint4(0u, 0u, 0u, 0u);
-  asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-  const int kk = et & 63, sg = et >> 6, ns = m.ns;
-#pragma unroll
-  for (int i = 0; i < CB_RC / 2; ++i)
-    if (c.t[h][i] >= 0) grad_put(gbuf, m, 2 * i + sg, kk, c.g[h][i], c.t[h][i] + j - 1);
-  const int k = h * 64 + kk;
-  if (k < KC)
-    for (int sn = CB_RC + sg; sn < ns; sn += 2) {
-      const size_t o = (size_t)(m.s0 + sn) * KC + k;
-      const float g = dcfeat[o];
-      const int t = cidx[o];
-      if (g != 0.f && t >= 0) grad_put(gbuf, m, sn, kk, g, t + j - 1);
-    }
-  fence_async_smem();
-}
-
-struct CbBars { uint64_t a_full[2], a_empty[2], m_full[CB_NMETA], g_ready[2], g_free[2], w_full; };
-
-__global__ void __launch_bounds__(CB_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
-                                                                            const int* __restrict__ cidx, const int* __restrict__ tso,
-                                                                            const int* __restrict__ cstc, int n_tiles, int L, int KC,
-                                                                            float* __restrict__ dw) {
-  extern __shared__ unsigned char raw[];
-  __shared__ CbBars bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ CbMeta meta[CB_NMETA];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* xim = base;                     // 2 stages
-  unsigned char* gim = base + 2 * CB_XIMG;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int n_mine = 0;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
-
-  if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar.a_full[s], 128); mbar_init(&bar.a_empty[s], 1); }
-    for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 128);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar.g_ready[s], 128); mbar_init(&bar.g_free[s], 1); }
-    mbar_init(&bar.w_full, 1);
-    mbar_fence_init();
-  }
-  if (warp == 4) tmem_alloc(&tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot;
-
-  if (warp < 4) {
-    // ------------------------------------------------------------------ loaders: tile bookkeeping + x rows -> bf16 hi/lo image
-    for (int it = 0; it < n_mine; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x, s = it & 1;
-      if (it >= 2) mbar_wait(&bar.a_empty[s], ((it >> 1) - 1) & 1);     // also frees meta slot it % 4 (tile it-4 is long finished)
-      CbMeta& m = meta[it % CB_NMETA];
-      m.rowsrc[tid] = -1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
-      if (tid < ns) {
-        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
-        m.sb[tid] = b; m.len[tid] = len;
-        const int g0 = (s0 + tid) * L;
-        for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
-      }
-      if (tid == 0) { m.s0 = s0; m.ns = ns; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      unsigned char* st = xim + s * CB_XIMG;
-#pragma unroll 1
-      for (int kb = 0; kb < 2; ++kb) {
-        unsigned char* a_hi = st + kb * 32768, *a_lo = a_hi + 16384;
-        float4 va[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
-          const int src = m.rowsrc[r];
-          va[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + (size_t)src * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int idx = i * 128 + tid;
-          store_split4(a_hi, a_lo, idx >> 4, (idx & 15) * 4, va[i]);
-        }
-      }
-      fence_async_smem();
-      mbar_arrive(&bar.a_full[s]);
-      mbar_arrive(&bar.m_full[it % CB_NMETA]);
-    }
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
-    if (n_mine > 0) {
-      const uint32_t el = elect_one_sync();
-      constexpr uint32_t idesc = idesc_bf16(128, 64) | (1u << 15) | (1u << 16);       // A (x) and B (G half tile) MN-major
-      const uint32_t g0 = smem_u32(gim);
-      int q = 0;
-      for (int it = 0; it < n_mine; ++it) {
-        const int s = it & 1;
-        mbar_wait(&bar.a_full[s], (it >> 1) & 1);
-        const uint32_t a0 = smem_u32(xim + s * CB_XIMG);
-        for (int j = 0; j < 3; ++j)
-          for (int h = 0; h < 2; ++h, ++q) {
-            const int gb = q & 1;
-            mbar_wait(&bar.g_ready[gb], (q >> 1) & 1);
-            tc_fence_after();
-            const uint32_t gq0 = g0 + gb * CB_GHALF;
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
-              const uint64_t gh = desc_mn(gq0 + ks * 2048, 8192), gl = desc_mn(gq0 + 16384 + ks * 2048, 8192);
-              const uint32_t d = tmem + j * 128 + h * 64;
-              umma_bf16_e(el, d, xh, gh, idesc, (it | ks) != 0);
-              umma_bf16_e(el, d, xh, gl, idesc, 1);
-              umma_bf16_e(el, d, xl, gh, idesc, 1);
-            }
-            umma_commit_e(el, &bar.g_free[gb]);
-            if (j == 2 && h == 1) umma_commit_e(el, &bar.a_empty[s]);
-          }
-      }
-      umma_commit_e(el, &bar.w_full);
-    }
-  } else {
-    // ------------------------------------------------------------------ gradient scatter (one-hot tile per tap), final flush
-    const int et = tid - 160;
-    int q = 0;
-    for (int it = 0; it < n_mine; ++it) {
-      mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
-      const CbMeta& m = meta[it % CB_NMETA];
-      // the tile's (gradient, position) pairs are fetched ONCE, all loads in flight together, and reused by the six steps
-      GradCache gc;
-      grad_cache_load(gc, dcfeat, cidx, m.s0, m.ns, KC, et);
-      for (int j = 0; j < 3; ++j)
-        for (int h = 0; h < 2; ++h, ++q) {
-          const int gb = q & 1;
-          if (q >= 2) mbar_wait(&bar.g_free[gb], ((q >> 1) - 1) & 1);      // the MMAs of step q-2 have read this buffer
-          grad_scatter_step(gim + gb * CB_GHALF, m, gc, dcfeat, cidx, KC, j, h, et, 2);
-          mbar_arrive(&bar.g_ready[gb]);
-        }
-    }
-    if (n_mine > 0) {
-      mbar_wait(&bar.w_full, 0);
-      tc_fence_after();
-      const int q4 = warp & 3, c = q4 * 32 + lane;                 // TMEM lane = channel
-#pragma unroll 1
-      for (int j = 0; j < 3; ++j)
-#pragma unroll 1
-        for (int k0 = 0; k0 < 128; k0 += 32) {
-          float v[32];
-          tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + j * 128 + k0, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + i < KC) atomicAdd(&dw[((size_t)(k0 + i) * D + c) * 3 + j], v[i]);
-        }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
-}
-
 // ------------------------------------------------------------------------------------------------------------------------
 // Input gradient on tcgen05:  dX [rows x c] = sum_j G_j [rows x k] . W_j [k x c]  with the same one-hot gradient tiles (K-major A
 // operand this time) and the tap's weights W_j^T as a K-major image streamed from L2 by one TMA bulk copy per tap.
@@ -465,6 +267,180 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
   if (warp == 9) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Weight gradient, same gradient image:  dW_j^T [c x k] = sum_r x[r][c] dY[r + 1 - j][k]  - the x image of the tile MN-major as the
+// A operand (unshifted), the dY image MN-major as the B operand read (2 - j) rows further down; 72 MMAs (N = 128) per tile into three
+// accumulators (one per tap) that live in tensor memory for the CTA's whole queue and are flushed once.
+//   warps 0-7: bookkeeping + x loaders (the next tile's row loads are in flight in registers while the MMAs of this one run; the
+//   image is single-buffered), warps 8-11: gradient scatter (dY double-buffered) and the final flush, warp 12: MMA issuer
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int DW_THREADS = 416;
+struct DwBars { uint64_t a_full, a_empty, m_full[CB_NMETA], g_full[2], g_empty[2], w_full; };
+
+__global__ void __launch_bounds__(DW_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(const float* __restrict__ x, const float* __restrict__ dcfeat,
+                                                                            const int* __restrict__ cidx, const int* __restrict__ tso,
+                                                                            const int* __restrict__ cstc, int n_tiles, int L, int KC,
+                                                                            float* __restrict__ dw, int dbg) {
+  extern __shared__ unsigned char raw[];
+  __shared__ DwBars bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ CbMeta meta[CB_NMETA];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* xim = base;                     // [c block 2][hi|lo][128 rows][128 B]
+  unsigned char* gim = base + CB_XIMG;           // [2][DX_GIMG]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int n_mine = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
+
+  if (tid == 0) {
+    mbar_init(&bar.a_full, 256); mbar_init(&bar.a_empty, 1);
+    for (int s = 0; s < CB_NMETA; ++s) mbar_init(&bar.m_full[s], 256);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar.g_full[s], 128); mbar_init(&bar.g_empty[s], 1); }
+    mbar_init(&bar.w_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 12) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ loaders: tile bookkeeping + x rows -> bf16 hi/lo image
+    auto build = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      CbMeta& m = meta[it % CB_NMETA];
+      if (tid < 128) m.rowsrc[tid] = -1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
+      if (tid < ns) {
+        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
+        m.sb[tid] = b; m.len[tid] = len;
+        const int g0 = (s0 + tid) * L;
+        for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
+      }
+      if (tid == 0) { m.s0 = s0; m.ns = ns; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_arrive(&bar.m_full[it % CB_NMETA]);
+    };
+    float4 va[16];                                                  // a warp per row and pass: rows i*8 + warp, 32 lanes x 4 channels
+    auto load = [&](const CbMeta& m) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int src = (dbg & 2) ? -1 : m.rowsrc[i * 8 + warp];
+        va[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + (size_t)src * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    build(0);
+    load(meta[0]);
+    unsigned char* sub = xim + (lane >> 4) * 32768;
+    for (int it = 0; it < n_mine; ++it) {
+      if (it >= 1) mbar_wait(&bar.a_empty, (it - 1) & 1);          // the MMAs of the previous tile have read the image
+#pragma unroll
+      for (int i = 0; i < 16; ++i) store_split4(sub, sub + 16384, i * 8 + warp, (lane & 15) * 4, va[i]);
+      fence_async_smem();
+      mbar_arrive(&bar.a_full);
+      if (it + 1 < n_mine) { build(it + 1); load(meta[(it + 1) % CB_NMETA]); }
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
+    const uint32_t el = elect_one_sync();
+    constexpr uint32_t idesc = idesc_bf16(128, 128) | (1u << 15) | (1u << 16);       // A (x) and B (dY) MN-major
+    const uint32_t a0 = smem_u32(xim);
+    for (int it = 0; it < n_mine; ++it) {
+      const int gb = it & 1;
+      mbar_wait(&bar.a_full, it & 1);
+      mbar_wait(&bar.g_full[gb], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t g0 = smem_u32(gim + gb * DX_GIMG);
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const uint32_t gj = g0 + (2 - j) * 128;                    // dY rows r + 1 - j (image row = tile row + 1)
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          if (dbg & 4) break;
+          const uint64_t xh = desc_mn(a0 + ks * 2048, 32768), xl = desc_mn(a0 + 16384 + ks * 2048, 32768);
+          const uint64_t gh = desc_mn(gj + ks * 2048, 2 * DX_GSUB), gl = desc_mn(gj + DX_GSUB + ks * 2048, 2 * DX_GSUB);
+          const uint32_t d = tmem + j * 128;
+          umma_bf16_e(el, d, xh, gh, idesc, (it | ks) != 0);
+          umma_bf16_e(el, d, xh, gl, idesc, 1);
+          umma_bf16_e(el, d, xl, gh, idesc, 1);
+        }
+      }
+      umma_commit_e(el, &bar.a_empty);
+      umma_commit_e(el, &bar.g_empty[gb]);
+    }
+    umma_commit_e(el, &bar.w_full);
+  } else {
+    // ------------------------------------------------------------------ gradient scatter (one image per tile), final flush
+    const int et = tid - 256, kk = et & 63, sg = et >> 6;
+    auto put = [&](unsigned char* half, const CbMeta& m, int sn, float g, int t) {
+      if (g == 0.f || t < 0 || t > m.len[sn]) return;            // positions past the trailing guard row touch no valid x row
+      const int r = m.sb[sn] + t + 2;                             // image row = tile row (sb + 1 + t) + 1
+      const __nv_bfloat16 hi = __float2bfloat16_rn(g);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(g - __bfloat162float(hi));
+      const uint32_t off = (uint32_t)(r * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2);
+      *reinterpret_cast<__nv_bfloat16*>(half + off) = hi;
+      *reinterpret_cast<__nv_bfloat16*>(half + DX_GSUB + off) = lo;
+    };
+    for (int it = 0; it < n_mine; ++it) {
+      const int gb = it & 1;
+      mbar_wait(&bar.m_full[it % CB_NMETA], (it / CB_NMETA) & 1);
+      const CbMeta& m = meta[it % CB_NMETA];
+      // the tile's (gradient, position) pairs: all loads in flight together, before the wait for the image buffer
+      DxCache c;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < DX_RC; ++i) {
+          const int sn = 2 * i + sg, k = h * 64 + kk;
+          c.g[h][i] = 0.f; c.t[h][i] = -1;
+          if (sn < m.ns && k < KC && !(dbg & 8)) {
+            const size_t o = (size_t)(m.s0 + sn) * KC + k;
+            c.g[h][i] = dcfeat[o];
+            c.t[h][i] = cidx[o];
+          }
+        }
+      if (it >= 2) mbar_wait(&bar.g_empty[gb], ((it >> 1) - 1) & 1);      // the MMAs of tile it-2 have read this buffer
+      unsigned char* img = gim + gb * DX_GIMG;
+      if (!(dbg & 8)) {
+        for (int i = et; i < DX_GIMG / 16; i += 128) reinterpret_cast<uint4*>(img)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned char* half = img + h * 2 * DX_GSUB;
+#pragma unroll
+          for (int i = 0; i < DX_RC; ++i) put(half, m, 2 * i + sg, c.g[h][i], c.t[h][i]);
+          const int k = h * 64 + kk;
+          if (k < KC)
+            for (int sn = 2 * DX_RC + sg; sn < m.ns; sn += 2) {
+              const size_t o = (size_t)(m.s0 + sn) * KC + k;
+              put(half, m, sn, dcfeat[o], cidx[o]);
+            }
+        }
+        fence_async_smem();
+      }
+      mbar_arrive(&bar.g_full[gb]);
+    }
+    mbar_wait(&bar.w_full, 0);
+    tc_fence_after();
+    const int q4 = warp & 3, cch = q4 * 32 + lane;                // TMEM lane = channel
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j)
+#pragma unroll 1
+      for (int k0 = 0; k0 < 128; k0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + j * 128 + k0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k0 + i < KC) atomicAdd(&dw[((size_t)(k0 + i) * D + cch) * 3 + j], v[i]);
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem, 512);
+}
+
 }  // namespace umpr
 
 using namespace umpr;
@@ -477,12 +453,12 @@ extern "C" int umpr_cnet_conv_bwd_dw_tc(const float* x, const float* dcfeat, con
   if (L < 1 || L + 2 > 128) return fail_arg("cnet_conv_bwd_dw_tc: sentence length L=%d must be in [1, 126]", L);
   if (!table || n_tiles < 1 || n_tiles > N) return fail_arg("cnet_conv_bwd_dw_tc: tile table missing or inconsistent (n_tiles=%d, N=%d)", n_tiles, N);
   if (reinterpret_cast<uintptr_t>(x) & 15) return fail_arg("cnet_conv_bwd_dw_tc: x must be 16-byte aligned");
-  constexpr int smem = 2 * CB_XIMG + CB_GIMG + 1024;
+  constexpr int smem = CB_XIMG + 2 * DX_GIMG + 1024;
   cudaError_t e = cudaFuncSetAttribute(cnet_conv_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("cnet_conv_bwd_dw_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  cnet_conv_bwd_dw_tc_kernel<<<grid, CB_THREADS, smem, (cudaStream_t)stream>>>(x, dcfeat, cidx, table, table + n_tiles + 1, n_tiles, L, KC, d_conv_w);
+  cnet_conv_bwd_dw_tc_kernel<<<grid, DW_THREADS, smem, (cudaStream_t)stream>>>(x, dcfeat, cidx, table, table + n_tiles + 1, n_tiles, L, KC, d_conv_w, dbg_flags());
   return check_launch("cnet_conv_bwd_dw_tc");
 }
 
