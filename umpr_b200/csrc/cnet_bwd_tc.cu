@@ -104,14 +104,17 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
     // ------------------------------------------------------------------ tile bookkeeping + gradient scatter: group jt owns tile jt of a pair
     const int jt = warp >> 2, et = tid & 127, kk = et & 63, sg = et >> 6;
     unsigned char* img = gim + jt * DX_GIMG;
-    auto build = [&](int t) {
-      const int tile = blockIdx.x + t * gridDim.x;
+    // the group's tiles are blockIdx.x + (jt + 2i) * gridDim.x; their tables are read one / two tiles ahead (TabPipe)
+    TabPipe tp;
+    tp.init(tso, cstc, blockIdx.x + jt * gridDim.x, 2 * gridDim.x, n_tiles, et);
+    tp.prefetch(tso, cstc, blockIdx.x + jt * gridDim.x, 2 * gridDim.x, n_tiles, et);
+    auto build = [&](int t) {                                       // bookkeeping of tile t from the pipeline's current values
       CbMeta& m = meta[t % DX_NMETA];
       m.rowsrc[et] = -1;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + jt) : "memory");
-      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
+      const int s0 = tp.s0c, ns = tp.s1c - s0;
       if (et < ns) {
-        const int c0 = cstc[s0], b = cstc[s0 + et] - c0, len = cstc[s0 + et + 1] - cstc[s0 + et] - 2;
+        const int b = tp.cbc - tp.c0c, len = tp.cec - tp.cbc - 2;
         m.sb[et] = b; m.len[et] = len;
         const int g0 = (s0 + et) * L;
         for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
@@ -168,7 +171,12 @@ __global__ void __launch_bounds__(DX_THREADS, 1) cnet_conv_bwd_dx_tc_kernel(cons
           fence_async_smem();
         }
         mbar_arrive(&bar.g_full[h]);
-        if (h == 0 && t + 2 < n_mine) { build(t + 2); prefetch(meta[(t + 2) % DX_NMETA], nxt); }      // next pair, early
+        if (h == 0 && t + 2 < n_mine) {                            // next pair, early
+          tp.rotate();
+          tp.prefetch(tso, cstc, blockIdx.x + (t + 2) * gridDim.x, 2 * gridDim.x, n_tiles, et);
+          build(t + 2);
+          prefetch(meta[(t + 2) % DX_NMETA], nxt);
+        }
       }
       cur = nxt;
     }
@@ -307,14 +315,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
 
   if (warp < 8) {
     // ------------------------------------------------------------------ loaders: tile bookkeeping + x rows -> bf16 hi/lo image
-    auto build = [&](int it) {
-      const int tile = blockIdx.x + it * gridDim.x;
+    // (the tile tables are read one / two tiles ahead: no table load sits in front of a tile's row loads)
+    TabPipe tp;
+    tp.init(tso, cstc, blockIdx.x, gridDim.x, n_tiles, tid);
+    auto build = [&](int it) {                                      // bookkeeping of tile `it` from the pipeline's current values
       CbMeta& m = meta[it % CB_NMETA];
       if (tid < 128) m.rowsrc[tid] = -1;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int s0 = tso[tile], ns = tso[tile + 1] - s0;
+      const int s0 = tp.s0c, ns = tp.s1c - s0;
       if (tid < ns) {
-        const int c0 = cstc[s0], b = cstc[s0 + tid] - c0, len = cstc[s0 + tid + 1] - cstc[s0 + tid] - 2;
+        const int b = tp.cbc - tp.c0c, len = tp.cec - tp.cbc - 2;
         m.sb[tid] = b; m.len[tid] = len;
         const int g0 = (s0 + tid) * L;
         for (int l = 0; l < len; ++l) m.rowsrc[b + 1 + l] = g0 + l;
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
         va[i] = src >= 0 ? *reinterpret_cast<const float4*>(x + (size_t)src * D + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    tp.prefetch(tso, cstc, blockIdx.x, gridDim.x, n_tiles, tid);
     build(0);
     load(meta[0]);
     unsigned char* sub = xim + (lane >> 4) * 32768;
@@ -340,7 +351,12 @@ __global__ void __launch_bounds__(DW_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
       for (int i = 0; i < 16; ++i) store_split4(sub, sub + 16384, i * 8 + warp, (lane & 15) * 4, va[i]);
       fence_async_smem();
       mbar_arrive(&bar.a_full);
-      if (it + 1 < n_mine) { build(it + 1); load(meta[(it + 1) % CB_NMETA]); }
+      if (it + 1 < n_mine) {
+        tp.rotate();                                               // tile it+1 becomes current; its tables were fetched an iteration ago
+        tp.prefetch(tso, cstc, blockIdx.x + (it + 1) * gridDim.x, gridDim.x, n_tiles, tid);
+        build(it + 1);
+        load(meta[(it + 1) % CB_NMETA]);
+      }
     }
   } else if (warp == 12) {
     // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
@@ -426,7 +442,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) cnet_conv_bwd_dw_tc_kernel(cons
     tc_fence_after();
     const int q4 = warp & 3, cch = q4 * 32 + lane;                // TMEM lane = channel
 #pragma unroll 1
-    for (int j = 0; j < 3; ++j)
+    for (int j = 0; j < 3 && !(dbg & 16); ++j)
 #pragma unroll 1
       for (int k0 = 0; k0 < 128; k0 += 32) {
         float v[32];

@@ -118,16 +118,22 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) cnet_conv_fwd_tc_kernel(const 
     const int j = warp >> 2, w4 = warp & 3, gt = tid & 127;
     const int kq = (lane & 15) * 4, rsub = lane >> 4;               // a half-warp per row: 16 lanes x 4 channels = one channel half
     float4 va[CT_LROWS];
+    // the group's tiles are blockIdx.x + (j + 2i) * gridDim.x; their tables are read one / two tiles ahead (TabPipe)
+    TabPipe tp;
+    if (tso) {
+      tp.init(tso, cstc, blockIdx.x + j * gridDim.x, 2 * gridDim.x, n_tiles, gt);
+      tp.prefetch(tso, cstc, blockIdx.x + j * gridDim.x, 2 * gridDim.x, n_tiles, gt);
+    }
     auto build = [&](int t) {                                       // tile bookkeeping by the group's 128 threads
       const int tile = blockIdx.x + t * gridDim.x;
       CtMeta& m = meta[t % CT_NMETA];
       m.rowsrc[gt] = -1;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + j) : "memory");
       int s0, ns;
-      if (tso) { s0 = tso[tile]; ns = tso[tile + 1] - s0; } else { s0 = tile * gs; ns = min(gs, N - s0); }
+      if (tso) { s0 = tp.s0c; ns = tp.s1c - s0; } else { s0 = tile * gs; ns = min(gs, N - s0); }
       if (gt < ns) {
         int rb, len;
-        if (tso) { const int c0 = cstc[s0]; rb = cstc[s0 + gt] - c0; len = cstc[s0 + gt + 1] - cstc[s0 + gt] - 2; }
+        if (tso) { rb = tp.cbc - tp.c0c; len = tp.cec - tp.cbc - 2; }
         else { rb = gt * Lg; len = L; }
         m.sb[gt] = rb; m.len[gt] = len;
         const int g0 = (s0 + gt) * L;
@@ -168,7 +174,11 @@ __global__ void __launch_bounds__(CT2_THREADS, 1) cnet_conv_fwd_tc_kernel(const 
       if (p >= 1) mbar_wait(&a_empty[1], (p - 1) & 1);
       if (has) { store(1); fence_async_smem(); }
       mbar_arrive(&a_full[1]);
-      if (t + 2 < n_mine) { build(t + 2); if (!off) load(meta[(t + 2) % CT_NMETA], 0); }      // next pair: bookkeeping, first half in flight
+      if (t + 2 < n_mine) {                                        // next pair: bookkeeping, first half in flight
+        if (tso) { tp.rotate(); tp.prefetch(tso, cstc, blockIdx.x + (t + 2) * gridDim.x, 2 * gridDim.x, n_tiles, gt); }
+        build(t + 2);
+        if (!off) load(meta[(t + 2) % CT_NMETA], 0);
+      }
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ weight producer: one 32 KB bulk copy per k-block and pair

@@ -94,4 +94,33 @@ inline Plan make_plan(const int32_t* buf, int n_tiles, int n_slabs, int R) {
   return p;
 }
 
+// valid-row tables, software-pipelined by the loader threads: tile boundaries (tso) two tiles ahead, sentence offsets (cst) one tile
+// ahead, so that no table load sits in front of a tile's row loads
+struct TabPipe {
+  int s0c, s1c, s0n, s1n, cbc, cec, c0c, cendc;         // current tile, next tile's boundaries
+  int s0nn, s1nn, cbn, cen, c0n, cendn;                 // in flight
+  __device__ __forceinline__ void ld_tso(const int* __restrict__ tso, int tile, int n_tiles, int& s0, int& s1) {
+    if (tile < n_tiles) { s0 = tso[tile]; s1 = tso[tile + 1]; } else { s0 = s1 = 0; }
+  }
+  __device__ __forceinline__ void ld_cst(const int* __restrict__ cst, int s0, int s1, int tid, int& cb, int& ce, int& c0, int& cend) {
+    c0 = cst[s0]; cend = cst[s1];
+    cb = ce = 0;
+    if (tid < s1 - s0) { cb = cst[s0 + tid]; ce = cst[s0 + tid + 1]; }
+  }
+  __device__ __forceinline__ void init(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
+    ld_tso(tso, tile, n_tiles, s0c, s1c);
+    ld_tso(tso, tile + stride, n_tiles, s0n, s1n);
+    ld_cst(cst, s0c, s1c, tid, cbc, cec, c0c, cendc);
+  }
+  __device__ __forceinline__ void prefetch(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
+    ld_cst(cst, s0n, s1n, tid, cbn, cen, c0n, cendn);       // (past the end s0n == s1n == 0: a harmless read of cst[0])
+    ld_tso(tso, tile + 2 * stride, n_tiles, s0nn, s1nn);
+  }
+  __device__ __forceinline__ void rotate() {
+    s0c = s0n; s1c = s1n; s0n = s0nn; s1n = s1nn;
+    cbc = cbn; cec = cen; c0c = c0n; cendc = cendn;
+  }
+};
+
+
 }  // namespace umpr

@@ -53,34 +53,6 @@ __device__ __forceinline__ void load_ms_images(unsigned char* msi, const float* 
   }
 }
 
-// valid-row tables, software-pipelined by the loader threads: tile boundaries (tso) two tiles ahead, sentence offsets (cst) one tile
-// ahead, so that no table load sits in front of a tile's row loads
-struct TabPipe {
-  int s0c, s1c, s0n, s1n, cbc, cec, c0c, cendc;         // current tile, next tile's boundaries
-  int s0nn, s1nn, cbn, cen, c0n, cendn;                 // in flight
-  __device__ __forceinline__ void ld_tso(const int* __restrict__ tso, int tile, int n_tiles, int& s0, int& s1) {
-    if (tile < n_tiles) { s0 = tso[tile]; s1 = tso[tile + 1]; } else { s0 = s1 = 0; }
-  }
-  __device__ __forceinline__ void ld_cst(const int* __restrict__ cst, int s0, int s1, int tid, int& cb, int& ce, int& c0, int& cend) {
-    c0 = cst[s0]; cend = cst[s1];
-    cb = ce = 0;
-    if (tid < s1 - s0) { cb = cst[s0 + tid]; ce = cst[s0 + tid + 1]; }
-  }
-  __device__ __forceinline__ void init(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
-    ld_tso(tso, tile, n_tiles, s0c, s1c);
-    ld_tso(tso, tile + stride, n_tiles, s0n, s1n);
-    ld_cst(cst, s0c, s1c, tid, cbc, cec, c0c, cendc);
-  }
-  __device__ __forceinline__ void prefetch(const int* tso, const int* cst, int tile, int stride, int n_tiles, int tid) {
-    ld_cst(cst, s0n, s1n, tid, cbn, cen, c0n, cendn);       // (past the end s0n == s1n == 0: a harmless read of cst[0])
-    ld_tso(tso, tile + 2 * stride, n_tiles, s0nn, s1nn);
-  }
-  __device__ __forceinline__ void rotate() {
-    s0c = s0n; s1c = s1n; s0n = s0nn; s1n = s1nn;
-    cbc = cbn; cec = cen; c0c = c0n; cendc = cendn;
-  }
-};
-
 // tile bookkeeping by the loader threads: sentence bases, row maps (table values from the pipeline above)
 __device__ __forceinline__ int build_meta(StMeta& m, const TabPipe& tp, int L, int tid) {
   const int s0 = tp.s0c, ns = tp.s1c - s0, c0 = tp.c0c;
@@ -455,13 +427,33 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       tc_fence_before();
       mbar_arrive(&bar.e_empty[acc]);
       bar_sync(2, 128);
-      if (et < m.ns) {
-        float ps;
-        sentence_softmax(m, et, L, score[pb], soft[pb], ps);
-        const int b = m.sbase[et], e = m.sbase[et + 1];
-        float dot = 0.f;                               // padded positions: d_soft = <0, .> = 0
-        for (int rr = b; rr < e; ++rr) dot += soft[pb][rr] * m.dsoft[rr];
-        for (int rr = b; rr < e; ++rr) dsc[pb][rr] = soft[pb][rr] * (m.dsoft[rr] - dot);
+      // softmax over each sentence's positions and its backward, a thread per ROW: the rows of a sentence recompute its max, sum and
+      // <soft, d_soft> in the same order (a thread per sentence leaves most of the 128 threads idle behind the longest sentence)
+      {
+        float ex = 0.f, mx = 0.f;
+        int b = 0, e = 0, npad = 0;
+        if (r < rows) {
+          const int j = m.rsent[r];
+          b = m.sbase[j]; e = m.sbase[j + 1]; npad = L - (e - b);
+          mx = npad > 0 ? 0.f : -INFINITY;
+          for (int rr = b; rr < e; ++rr) mx = fmaxf(mx, score[pb][rr]);
+          ex = expf(score[pb][r] - mx);
+          soft[pb][r] = ex;
+        }
+        bar_sync(2, 128);
+        if (r < rows) {
+          float sum = npad > 0 ? (float)npad * expf(-mx) : 0.f;
+          for (int rr = b; rr < e; ++rr) sum += soft[pb][rr];
+          ex *= 1.f / sum;
+        }
+        bar_sync(2, 128);
+        if (r < rows) soft[pb][r] = ex;
+        bar_sync(2, 128);
+        if (r < rows) {
+          float dot = 0.f;                               // padded positions: d_soft = <0, .> = 0
+          for (int rr = b; rr < e; ++rr) dot += soft[pb][rr] * m.dsoft[rr];
+          dsc[pb][r] = ex * (m.dsoft[r] - dot);
+        }
       }
       bar_sync(2, 128);
       // d(pre-tanh) row -> bf16 hi/lo image; dWs partial sums
@@ -498,28 +490,50 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       }
       dws0 += th[0];
       dws1 += th[1];
-      // dx rows: soft · d_self_atte + dpre · Ms
+      // dx rows: soft · d_self_atte + dpre · Ms.  The 8 rows a thread stores (row j*4 + lane/8 of the warp's 32, 4 channels at
+      // (lane%8)*4) are resolved once per tile - output pointer, d_self_atte row of the sentence, soft - and the d_self_atte values of a
+      // 32-channel chunk are requested one chunk ahead (the first before the accumulator is ready)
+      const int s0 = m.s0;
+      const int c4 = (lane & 7) * 4;
+      float* orow[8];
+      const float* drow[8];
+      float so[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = q * 32 + j * 4 + (lane >> 3);
+        orow[j] = nullptr; drow[j] = d_sa; so[j] = 0.f;
+        if (row < rows) {
+          orow[j] = dx + (size_t)m.rowmap[row] * D + c4;
+          drow[j] = d_sa + (size_t)(s0 + m.rsent[row]) * D + c4;
+          so[j] = soft[pb][row];
+        }
+      }
+      float4 dn[8];
+      auto fetch_d = [&](int c0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dn[j] = orow[j] ? *reinterpret_cast<const float4*>(drow[j] + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      fetch_d(0);
       mbar_wait(&bar.d_full, it & 1);
       tc_fence_after();
-      const int s0 = m.s0;
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         float v[32];
         tmem_ld32(trow + T_DX + c0, v);
+        float4 dc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dc[j] = dn[j];
+        if (c0 + 32 < D) fetch_d(c0 + 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<float4*>(&sw[lane * ST_STG_LD + j * 4]) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         __syncwarp();
-        const int c = c0 + (lane & 7) * 4;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int rr = j * 4 + (lane >> 3), row = q * 32 + rr;
-          if (row < rows) {
-            float4 o = *reinterpret_cast<const float4*>(&sw[rr * ST_STG_LD + (lane & 7) * 4]);
-            const float so = soft[pb][row];
-            const float4 d = *reinterpret_cast<const float4*>(d_sa + (size_t)(s0 + m.rsent[row]) * D + c);
-            o.x += so * d.x; o.y += so * d.y; o.z += so * d.z; o.w += so * d.w;
-            *reinterpret_cast<float4*>(dx + (size_t)m.rowmap[row] * D + c) = o;
+          if (orow[j]) {
+            float4 o = *reinterpret_cast<const float4*>(&sw[(j * 4 + (lane >> 3)) * ST_STG_LD + c4]);
+            o.x += so[j] * dc[j].x; o.y += so[j] * dc[j].y; o.z += so[j] * dc[j].z; o.w += so[j] * dc[j].w;
+            *reinterpret_cast<float4*>(orow[j] + c0) = o;
           }
         }
         __syncwarp();
