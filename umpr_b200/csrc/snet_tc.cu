@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
                                                                     const int* __restrict__ cst, const float* __restrict__ d_sa,
                                                                     const float* __restrict__ Ms, const float* __restrict__ Ws,
                                                                     int n_tiles, int L, float* __restrict__ dx,
-                                                                    float* __restrict__ dMs, float* __restrict__ dWs) {
+                                                                    float* __restrict__ dMs, float* __restrict__ dWs, int dbg) {
   extern __shared__ unsigned char raw[];
   __shared__ StBwdBars bar;
   __shared__ uint32_t tmem_slot;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
   float* stg = reinterpret_cast<float*>(base + ST_MSIMG + ST_PIMG + ST_NSTAGE * ST_XIMG);
   StMeta* meta = reinterpret_cast<StMeta*>(reinterpret_cast<unsigned char*>(stg) + 4 * 32 * ST_STG_LD * 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t T_E = 0, T_DX = 128, T_W = 256;
+  constexpr uint32_t T_E = 0, T_DX = 128, T_W = 384;      // e: 2 x 64 columns, dx: 2 x 128, dMs^T: 64
   int n_mine = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_mine;
 
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int idx = i * 128 + tid, r = idx >> 4, k = kb * 64 + (idx & 15) * 4;
-          const bool ok = r < rows;
+          const bool ok = r < rows && !(dbg & 2);
           va[i] = ok ? *reinterpret_cast<const float4*>(x + (size_t)m.rowmap[r] * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
           vd[i] = ok ? *reinterpret_cast<const float4*>(d_sa + (size_t)(s0 + m.rsent[r]) * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -383,9 +383,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t ph = smem_desc_sw128(p0) + (uint64_t)(kk * 2), pl = smem_desc_sw128(p0 + 16384) + (uint64_t)(kk * 2);
           const uint64_t mh = desc_mn(b0 + kk * 2048, 16384), ml = desc_mn(b0 + 8192 + kk * 2048, 16384);
-          umma_bf16_e(el, tmem + T_DX, ph, mh, idesc_dx, kk != 0);
-          umma_bf16_e(el, tmem + T_DX, ph, ml, idesc_dx, 1);
-          umma_bf16_e(el, tmem + T_DX, pl, mh, idesc_dx, 1);
+          umma_bf16_e(el, tmem + T_DX + (it & 1) * 128, ph, mh, idesc_dx, kk != 0);
+          umma_bf16_e(el, tmem + T_DX + (it & 1) * 128, ph, ml, idesc_dx, 1);
+          umma_bf16_e(el, tmem + T_DX + (it & 1) * 128, pl, mh, idesc_dx, 1);
         }
         // dMs^T [128 c x 64 a] += x^T [128 c x 128 rows] · dpre [128 rows x 64 a]
 #pragma unroll
@@ -407,7 +407,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     float* sw = stg + q * 32 * ST_STG_LD;
     float dws0 = 0.f, dws1 = 0.f;
-    for (int it = 0; it < n_mine; ++it) {
+    // Software pipeline over the tiles: A(t) = scores -> softmax backward -> d(pre-tanh) image of tile t, B(t) = dx rows of tile t.  The
+    // order is A(0), A(1), B(0), A(2), B(1), ...: the MMAs of tile t (dx, dMs^T) run while these threads are busy with A(t+1), so
+    // they never wait for the tensor pipe; the dx accumulator is double-buffered for that.
+    for (int it = 0; it <= n_mine; ++it) {
+     if (it < n_mine) {
       const int acc = it & 1, pb = it & 1;
       mbar_wait(&bar.m_full[it % ST_NMETA], (it / ST_NMETA) & 1);      // own barrier: a_full may already be a phase ahead by now
       mbar_wait(&bar.e_full[acc], (it >> 1) & 1);
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       bar_sync(2, 128);
       // softmax over each sentence's positions and its backward, a thread per ROW: the rows of a sentence recompute its max, sum and
       // <soft, d_soft> in the same order (a thread per sentence leaves most of the 128 threads idle behind the longest sentence)
-      {
+      if (!(dbg & 8)) {
         float ex = 0.f, mx = 0.f;
         int b = 0, e = 0, npad = 0;
         if (r < rows) {
@@ -458,6 +462,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       bar_sync(2, 128);
       // d(pre-tanh) row -> bf16 hi/lo image; dWs partial sums
       const float ds = r < rows ? dsc[pb][r] : 0.f;
+      if (it >= 1) { mbar_wait(&bar.d_full, (it - 1) & 1); tc_fence_after(); }      // the MMAs of tile it-1 have read the image
       {
         unsigned char* prow = pim + r * 128;
 #pragma unroll
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
 #pragma unroll
       for (int i = 0; i < ATT; ++i) th[i] *= ds;
 #pragma unroll
-      for (int w = 32, o = 16; o > 0; w >>= 1, o >>= 1) {
+      for (int w = 32, o = 16; o > 0 && !(dbg & 16); w >>= 1, o >>= 1) {
         const bool up = (lane & o) != 0;
 #pragma unroll
         for (int i = 0; i < w; ++i) {
@@ -490,6 +495,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
       }
       dws0 += th[0];
       dws1 += th[1];
+     }
+     if (it >= 1) {
+      const int jt = it - 1, pb = jt & 1;
+      const StMeta& m = meta[jt % ST_NMETA];
+      const int rows = m.sbase[m.ns];
+      if (it == n_mine) { mbar_wait(&bar.d_full, jt & 1); tc_fence_after(); }      // (otherwise waited for in A(it) above)
       // dx rows: soft · d_self_atte + dpre · Ms.  The 8 rows a thread stores (row j*4 + lane/8 of the warp's 32, 4 channels at
       // (lane%8)*4) are resolved once per tile - output pointer, d_self_atte row of the sentence, soft - and the d_self_atte values of a
       // 32-channel chunk are requested one chunk ahead (the first before the accumulator is ready)
@@ -514,12 +525,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
         for (int j = 0; j < 8; ++j) dn[j] = orow[j] ? *reinterpret_cast<const float4*>(drow[j] + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       fetch_d(0);
-      mbar_wait(&bar.d_full, it & 1);
-      tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < D; c0 += 32) {
+      for (int c0 = 0; c0 < D && !(dbg & 1); c0 += 32) {
         float v[32];
-        tmem_ld32(trow + T_DX + c0, v);
+        tmem_ld32(trow + T_DX + pb * 128 + c0, v);
         float4 dc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dc[j] = dn[j];
@@ -539,6 +548,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) snet_bwd_tc_kernel(const float*
         __syncwarp();
       }
       tc_fence_before();
+     }
     }
     if (n_mine > 0) {
       // flush: dMs[a][c] += W^T[c][a] (TMEM lane = c), dWs
@@ -598,6 +608,6 @@ extern "C" int umpr_snet_bwd_tc(const float* x, const int* table, int n_tiles, c
   if (e != cudaSuccess) { set_error("snet_bwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  snet_bwd_tc_kernel<<<grid, ST_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, d_sa, Ms, Ws, n_tiles, L, dx, dMs, dWs);
+  snet_bwd_tc_kernel<<<grid, ST_THREADS, smem, (cudaStream_t)stream>>>(x, table, table + n_tiles + 1, d_sa, Ms, Ws, n_tiles, L, dx, dMs, dWs, dbg_flags());
   return check_launch("snet_bwd_tc");
 }
