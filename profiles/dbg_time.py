@@ -72,3 +72,12 @@ if "tn" in what:
     dM = torch.zeros(D, D, device=dev)
     y = torch.randn(N * L, D, device=dev)
     timed("gemm_tn", lambda: call("umpr_tc_gemm_tn", ptr(x), D, ptr(y), D, ptr(dM), D, D, D, N * L, n_ctas))
+if "coattn" in what:
+    from umpr_b200 import functional as F
+    _, lens_i = syn._side(rs, B, S, L, 1000, 5, False, False)
+    plan_i = PackPlan(lens_i.reshape(-1), L, dev, tile_rows=128)
+    mask_i = (torch.arange(L, device=dev)[None, :] < plan_i.row_lengths().to(dev)[:, None])
+    gi = (torch.tanh(torch.randn(N, L, D, device=dev)) * mask_i[:, :, None]).view(B, S * L, D).contiguous()
+    gu = x.view(B, S * L, D)
+    with torch.no_grad():
+        timed("coattn_fwd", lambda: F.co_attention(gu, gi, M, plans=(plan, plan_i)))

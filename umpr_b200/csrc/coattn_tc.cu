@@ -124,7 +124,7 @@ struct C2Bars { uint64_t a_full, a_empty, b_full[2], b_empty[2], acc_full[2], ac
 __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(const unsigned char* __restrict__ imgA, const unsigned char* __restrict__ imgB,
                                                                             const float* __restrict__ n2a, const float* __restrict__ n2b, int P, int T,
                                                                             const int* __restrict__ meta, float4* __restrict__ rc_v, int4* __restrict__ rc_i,
-                                                                            float4* __restrict__ cc_v, int4* __restrict__ cc_i) {
+                                                                            float4* __restrict__ cc_v, int4* __restrict__ cc_i, int dbg) {
   extern __shared__ unsigned char raw[];
   __shared__ C2Bars bars;
   __shared__ uint32_t tmem_slot;
@@ -202,10 +202,12 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           const uint32_t t0 = tmem + ((uint32_t)(q * 32) << 16) + s * 256 + (is_t ? 128 : 0);
           float tm = -INFINITY;
           const bool scan = pass == 1 && own < Pown;
+          const bool skip = (dbg & 1) != 0;
           uint32_t ra[2][16];
-          tmem_ld16_issue(t0, ra[0]);
+          if (!skip) tmem_ld16_issue(t0, ra[0]);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
+            if (skip) break;
             tmem_ld_wait();
             if (ch + 1 < 8) tmem_ld16_issue(t0 + (ch + 1) * 16, ra[(ch + 1) & 1]);
             const int left = nv - ch * 16;
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
             const uint64_t bh = smem_desc_sw128(b0 + kb * 2 * CI_TILE), bl = smem_desc_sw128(b0 + kb * 2 * CI_TILE + CI_TILE);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
+              if (dbg & 4) break;
               const uint64_t o = (uint64_t)(kk * 2);
               const uint32_t accf = (kb | kk) != 0;
               umma_bf16_e(el, d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
@@ -473,7 +476,7 @@ extern "C" int umpr_coattn_fwd_tc(const float* gu, const float* gi, const float*
   const int sm1 = 3 * CI_IMG + 1024;
   cudaError_t e = cudaFuncSetAttribute(coattn_affinity_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm1);
   if (e != cudaSuccess) { set_error("coattn_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
-  coattn_affinity_tc2_kernel<<<B, C2_THREADS, sm1, st>>>(imgA, imgB, n2a, n2b, P, T, meta, rc_v, rc_i, cc_v, cc_i);
+  coattn_affinity_tc2_kernel<<<B, C2_THREADS, sm1, st>>>(imgA, imgB, n2a, n2b, P, T, meta, rc_v, rc_i, cc_v, cc_i, dbg_flags());
   if (int rc = check_launch("coattn_affinity_tc2")) return rc;
   const size_t sm2 = sizeof(float) * (((P + 3) & ~3) + 32) + sizeof(float4) * 8 * 32;
   if (sm2 > 48 * 1024) cudaFuncSetAttribute(coattn_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);

@@ -17,6 +17,8 @@ constexpr int SV = 256;      // saved per (token, direction): r, z, n, (W_hn h +
 void set_error(const char* fmt, ...);
 int fail_arg(const char* fmt, ...);
 int check_launch(const char* what);
+int gather_pack_tc_sides(const float* table, int n_sides, const int64_t* const* ids, const int32_t* const* plan, const int* n_tiles,
+                         const int* n_slabs, const int* L, int E, void* const* xq, void* stream);
 int dbg_flags();      // UMPR_DBG (development only): role-ablation switches of the tile kernels, 0 in normal operation
 // internal form of umpr_cnet_conv_fwd_tc (csrc/cnet_tc.cu): prep = 0 reuses the weight image already in `wimg`
 int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize, const int32_t* table,

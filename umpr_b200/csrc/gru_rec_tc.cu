@@ -187,10 +187,19 @@ __device__ __forceinline__ void gate_step(const int X, const RecArgs& a, const C
 // columns: E embedding values, a 1.0 (bias column), zeros.  fp32 = hi + lo (bf16 each, "3xBF16" operands).  The same image is
 // the A operand of the recurrence's x-part MMA and the (token-major) B operand of the weight-gradient MMA.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
-                                                             const float* __restrict__ dense, Plan p, int L, int E,
-                                                             unsigned char* __restrict__ xq) {
-  const int sl = blockIdx.x;
+// up to three review sides in one launch (the native step: user, item, user->item): blocks [slab0[k], slab0[k+1]) pack side k
+struct GatherSides {
+  const int64_t* ids[3]; Plan plan[3]; unsigned char* xq[3]; int L[3]; int slab0[4]; int n;
+};
+__global__ void __launch_bounds__(256) gather_pack_tc_kernel(const float* __restrict__ table, const float* __restrict__ dense, GatherSides gs,
+                                                             int E) {
+  int side = 0;
+  if (gs.n > 1 && (int)blockIdx.x >= gs.slab0[1]) side = (gs.n > 2 && (int)blockIdx.x >= gs.slab0[2]) ? 2 : 1;
+  const Plan& p = gs.plan[side];
+  const int64_t* __restrict__ ids = gs.ids[side];
+  unsigned char* __restrict__ xq = gs.xq[side];
+  const int L = gs.L[side];
+  const int sl = blockIdx.x - gs.slab0[side];
   const int j = p.slab_tile[sl];
   const int t = sl - p.tile_off[j];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -381,10 +390,34 @@ extern "C" int umpr_gather_pack_tc(const float* table, const int64_t* ids, const
   if ((!table || !ids) && !dense) return fail_arg("gather_pack_tc: need (table, ids) or dense");
   if (E < 1 || E >= KP) return fail_arg("gather_pack_tc: embedding width E=%d must be in [1, %d)", E, KP);
   if (n_slabs == 0) return 0;
-  Plan p = make_plan(plan, n_tiles, n_slabs, RT_R);
-  gather_pack_tc_kernel<<<n_slabs, 256, 0, (cudaStream_t)stream>>>(table, ids, dense, p, L, E, reinterpret_cast<unsigned char*>(xq));
+  GatherSides gs{};
+  gs.n = 1; gs.ids[0] = ids; gs.plan[0] = make_plan(plan, n_tiles, n_slabs, RT_R); gs.xq[0] = reinterpret_cast<unsigned char*>(xq); gs.L[0] = L;
+  gs.slab0[0] = 0; gs.slab0[1] = n_slabs;
+  gather_pack_tc_kernel<<<n_slabs, 256, 0, (cudaStream_t)stream>>>(table, dense, gs, E);
   return check_launch("gather_pack_tc");
 }
+
+namespace umpr {
+// umpr_gather_pack_tc for up to three sides in ONE launch (csrc/step.cu): same table, one plan / id tensor / image buffer per side
+int gather_pack_tc_sides(const float* table, int n_sides, const int64_t* const* ids, const int32_t* const* plan, const int* n_tiles,
+                         const int* n_slabs, const int* L, int E, void* const* xq, void* stream) {
+  if (!table) return fail_arg("gather_pack_tc: table is NULL");
+  if (n_sides < 1 || n_sides > 3) return fail_arg("gather_pack_tc: %d sides", n_sides);
+  if (E < 1 || E >= KP) return fail_arg("gather_pack_tc: embedding width E=%d must be in [1, %d)", E, KP);
+  GatherSides gs{};
+  gs.n = n_sides;
+  int total = 0;
+  for (int k = 0; k < n_sides; ++k) {
+    gs.ids[k] = ids[k]; gs.plan[k] = make_plan(plan[k], n_tiles[k], n_slabs[k], RT_R); gs.xq[k] = reinterpret_cast<unsigned char*>(xq[k]); gs.L[k] = L[k];
+    gs.slab0[k] = total;
+    total += n_slabs[k];
+  }
+  for (int k = n_sides; k < 4; ++k) gs.slab0[k] = total;
+  if (total == 0) return 0;
+  gather_pack_tc_kernel<<<total, 256, 0, (cudaStream_t)stream>>>(table, nullptr, gs, E);
+  return check_launch("gather_pack_tc");
+}
+}  // namespace umpr
 
 extern "C" int umpr_gru_fwd_tc(const umpr_gru_seg* segs, int n_seg, const float* const* w, int E, const int32_t* sched,
                                int n_queues, void* stream) {

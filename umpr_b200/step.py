@@ -217,7 +217,7 @@ class NativeStep:
         _lib.call("umpr_step", C.addressof(m), C.addressof(sides), _lib.ptr(photos), _lib.ptr(labels), _lib.ptr(sr), nq_r, _lib.ptr(sc), nq_c,
                   _lib.ptr(self._zero), _lib.ptr(self._ws), self._ws.numel(), _lib.ptr(pred), _lib.ptr(loss), int(train))
         # kernels launched inside the call (csrc/step.cu), for bench.py's launch count: the call itself was counted as one
-        fwd = (2 + 1 + 1 + 3 + 4 + 1 + 1 + 1) + ((1 + 1 + 12 + 1 + 1 + 2) if self.full else 0)
+        fwd = (1 + 1 + 1 + 3 + 4 + 1 + 1 + 1) + ((1 + 10 + 1 + 1 + 2) if self.full else 0)      # one gather launch; conv: 1 prep + 3 x (conv, fix, head)
         bwd = ((1 + 1 + 1 + 1 + 1 + 1 + 6 + 1 + 1 + 1 + 1) + ((3 + 1 + 1 + 12 + 1 + 1) if self.full else 0)) if train else 0
         _lib.launch_count += fwd + bwd - 1
         if taps is not None:
