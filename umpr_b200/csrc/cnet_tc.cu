@@ -370,10 +370,10 @@ using namespace umpr;
 
 namespace umpr {
 // prep = 0: the weight image (and filter norms) in `wimg` are those of a previous call with the same conv_w (the three C-Net calls of
-// one step share them, csrc/step.cu)
+// one step share them, csrc/step.cu); prep = 2: ONLY build the image
 int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize,
                           const int32_t* table, int table_tiles, void* wimg, int cap, float* cfeat, int32_t* cidx,
-                          int n_ctas, int prep, void* stream) {
+                          int n_ctas, int prep, void* fix_records, void* stream) {
   if (N <= 0) return 0;
   if (ksize != 3) return fail_arg("cnet: kernel_size=%d (only 3 is built)", ksize);
   if (KC < 1 || KC > 128) return fail_arg("cnet: kernel_count=%d must be in [1, 128]", KC);
@@ -384,6 +384,7 @@ int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv
   if (prep) {
     cnet_tc_prep_kernel<<<(CT_KB * 128 * 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(conv_w, KC, reinterpret_cast<unsigned char*>(wimg));
     if (int e = check_launch("cnet_tc_prep")) return e;
+    if (prep == 2) return 0;
   }
   int gs = 128 / (L + 2);
   if (gs > 16) gs = 16;
@@ -398,7 +399,8 @@ int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv
   }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;
-  short* fixrec = reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(wimg) + CT_HDR_BYTES);
+  // the 2-byte records behind the weight image by default; callers that run several sides concurrently pass one buffer per side
+  short* fixrec = fix_records ? reinterpret_cast<short*>(fix_records) : reinterpret_cast<short*>(reinterpret_cast<unsigned char*>(wimg) + CT_HDR_BYTES);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("UMPR_CONV_DBG"); dbg = e ? atoi(e) : 0; }
   cnet_conv_fwd_tc_kernel<<<grid, CT2_THREADS, smem, (cudaStream_t)stream>>>(x, reinterpret_cast<const unsigned char*>(wimg), conv_b, N, L, KC,
@@ -419,5 +421,5 @@ int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv
 extern "C" int umpr_cnet_conv_fwd_tc(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize,
                                      const int32_t* table, int table_tiles, void* wimg, int cap, float* cfeat, int32_t* cidx,
                                      int n_ctas, void* stream) {
-  return cnet_conv_fwd_tc_impl(x, conv_w, conv_b, N, L, KC, ksize, table, table_tiles, wimg, cap, cfeat, cidx, n_ctas, 1, stream);
+  return cnet_conv_fwd_tc_impl(x, conv_w, conv_b, N, L, KC, ksize, table, table_tiles, wimg, cap, cfeat, cidx, n_ctas, 1, nullptr, stream);
 }

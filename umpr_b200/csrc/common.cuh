@@ -20,9 +20,10 @@ int check_launch(const char* what);
 int gather_pack_tc_sides(const float* table, int n_sides, const int64_t* const* ids, const int32_t* const* plan, const int* n_tiles,
                          const int* n_slabs, const int* L, int E, void* const* xq, void* stream);
 int dbg_flags();      // UMPR_DBG (development only): role-ablation switches of the tile kernels, 0 in normal operation
-// internal form of umpr_cnet_conv_fwd_tc (csrc/cnet_tc.cu): prep = 0 reuses the weight image already in `wimg`
+// internal form of umpr_cnet_conv_fwd_tc (csrc/cnet_tc.cu): prep = 0 reuses the weight image already in `wimg`, 2 = only build it;
+// fix_records (optional): 2*N*KC bytes for the re-scoring records instead of the area behind the image
 int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv_b, int N, int L, int KC, int ksize, const int32_t* table,
-                          int table_tiles, void* wimg, int cap, float* cfeat, int32_t* cidx, int n_ctas, int prep, void* stream);
+                          int table_tiles, void* wimg, int cap, float* cfeat, int32_t* cidx, int n_ctas, int prep, void* fix_records, void* stream);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

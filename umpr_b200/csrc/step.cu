@@ -93,6 +93,7 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
                     const int32_t* sched_r, int nq_r, const int32_t* sched_c, int nq_c, const void* zero_img, Arena& a, float* pred_out,
                     float* loss_out, int train, int n_ctas, void* stream) {
   const bool dry = a.base == nullptr;
+  const int order_f[3] = {2, 0, 1};          // the order control_net calls c_net in: ui, user, item
   const bool full = !m.review_net_only;
   const int B = sd[0].B, P = sd[0].S * sd[0].L, V = m.V, KC = m.KC, E = m.E, Dm = 128;
   const int n_sides = full ? 3 : 2;
@@ -148,17 +149,19 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   for (int k = 0; k < n_sides; ++k) Nmax = sd[k].B * sd[k].S > Nmax ? sd[k].B * sd[k].S : Nmax;
   const int cap = ((Nmax * KC + 7) / 8) > 4096 ? ((Nmax * KC + 7) / 8) : 4096;      // one 2-byte re-scoring record per (sentence, filter)
   void* conv_scratch = nullptr; float* s_ui = nullptr; float* senti_ss = nullptr; float* ct_out = nullptr; float* vis_emb = nullptr; float* vis_out = nullptr;
-  void* dx_scratch = nullptr;
+  void* dx_scratch[3] = {nullptr, nullptr, nullptr};
+  void* fix_rec[3] = {nullptr, nullptr, nullptr};
   if (full) {
     long long cb = 0;
     UMPR_TRY(umpr_workspace_bytes("cnet_conv_fwd_tc", cap, 0, &cb));
     conv_scratch = a.get<unsigned char>((size_t)cb);
+    for (int k = 0; k < 3; ++k) fix_rec[k] = a.get<unsigned char>(2 * (size_t)sd[k].B * sd[k].S * KC + 16);      // re-scoring records per side (the sides run concurrently)
     s_ui = a.get<float>((size_t)sd[2].B * sd[2].S * Dm);
     senti_ss = a.get<float>((size_t)sd[2].B * sd[2].S);
     ct_out = a.get<float>(3 * (size_t)B * V);       // score, prefer_pos, prefer_neg
     vis_emb = a.get<float>(2 * (size_t)V);
     vis_out = a.get<float>(5 * (size_t)B * V);      // img_emb, pos_match, neg_match, final_pos, final_neg
-    if (train) dx_scratch = a.get<unsigned char>(196608);
+    if (train) for (int k = 0; k < 3; ++k) dx_scratch[k] = a.get<unsigned char>(196608);
   }
   // backward temporaries
   float* d_pred = nullptr, *g4 = nullptr, *d_repr = nullptr, *d_f = nullptr, *vis_scr = nullptr, *d_c = nullptr, *d_s = nullptr, *d_vp = nullptr,
@@ -202,15 +205,18 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   const bool two = full && !g_single_stream;
   cudaStream_t stc = st;
   void* cstream = stream;
-  static cudaStream_t side = nullptr;
-  static cudaEvent_t ev[4];
+  static cudaStream_t side = nullptr, side3 = nullptr;
+  static cudaEvent_t ev[8];
+  cudaStream_t st3 = st;                     // third stream: the item side of the C-Net tails (convolution, heads) beside ui + user
   if (two) {
     if (!side) {
       if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return fail_arg("step: cannot create the side stream"); }
-      for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking) != cudaSuccess) { side3 = nullptr; return fail_arg("step: cannot create the side stream"); }
+      for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
     }
     stc = side;
     cstream = side;
+    st3 = side3;
     cudaEventRecord(ev[0], st);              // fork: the token images are packed
     cudaStreamWaitEvent(stc, ev[0], 0);
   }
@@ -249,13 +255,22 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
       }
       STEP_CALL_C("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 3, m.cnet_gru, E, sched_c, nq_c, cstream));
     }
-    for (int k = 0; k < 3; ++k) {            // conv + ReLU + max-pool + view head (model.py:118-125)
+    // conv + ReLU + max-pool + view head (model.py:118-125) per side: ui and user on the C-Net stream, item on a third one
+    STEP_CALL_C("umpr_cnet_conv_fwd_tc", cnet_conv_fwd_tc_impl(sb[0].out_c, m.conv_w, m.conv_b, 1, sd[0].L, KC, m.ksize, nullptr, 0, conv_scratch, cap, nullptr, nullptr,
+                                   n_ctas, 2, nullptr, cstream));      // the weight image, once for the three sides
+    if (two) { cudaEventRecord(ev[4], stc); cudaStreamWaitEvent(st3, ev[4], 0); }
+    for (int j = 0; j < 3; ++j) {
+      const int k = order_f[j];
       const int N = sd[k].B * sd[k].S;
-      STEP_CALL_C("umpr_cnet_conv_fwd_tc", cnet_conv_fwd_tc_impl(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
-                                     sb[k].cfeat, sb[k].cidx, n_ctas, k == 0, cstream));      // the weight image of the first call serves all three
-      STEP_CALL_C("umpr_cnet_head_fwd", umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, cstream));
-      if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, stc);
+      cudaStream_t sk = k == 1 ? st3 : stc;
+      { ProfScope ps_("umpr_cnet_conv_fwd_tc", sk);
+        UMPR_TRY(cnet_conv_fwd_tc_impl(sb[k].out_c, m.conv_w, m.conv_b, N, sd[k].L, KC, m.ksize, sd[k].cnet_table, sd[k].cnet_tiles, conv_scratch, cap,
+                                       sb[k].cfeat, sb[k].cidx, n_ctas, 0, fix_rec[k], sk)); }
+      { ProfScope ps_("umpr_cnet_head_fwd", sk);
+        UMPR_TRY(umpr_cnet_head_fwd(sb[k].cfeat, m.clin_w, m.clin_b, m.threshold, sd[k].B, sd[k].S, V, KC, sb[k].view_p, sb[k].fin, sk)); }
+      if (m.routing_cnet[k]) cudaMemcpyAsync(m.routing_cnet[k], sb[k].cidx, (size_t)N * KC * sizeof(int32_t), cudaMemcpyDeviceToDevice, sk);
     }
+    if (two) { cudaEventRecord(ev[5], st3); cudaStreamWaitEvent(st, ev[5], 0); }      // the visual tail needs c_i
     // ControlNet tail (model.py:185-197): S-Net on the user->item review (its `sentiment` output is unused), SSNet + Eq.18 + gates
     STEP_CALL_C("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, s_ui, n_ctas, cstream));
     STEP_CALL_C("umpr_control_tail_fwd", umpr_control_tail_fwd(s_ui, sb[2].view_p, sb[2].fin, m.ss_w, m.ss_b, m.eq18_eps, B, sd[2].S, V, senti_ss, ct_out, ct_out + (size_t)B * V,
@@ -288,15 +303,22 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     // S-Net on the user->item review: only self_atte was used, so d(self_atte) = d_s as it is
     STEP_CALL_C("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[2].out_c, sd[2].snet_table, sd[2].snet_tiles, d_s, m.csnet_Ms, m.csnet_Ws, sd[2].B * sd[2].S, sd[2].L, dx_s_ui,
                               m.g_csnet_Ms, m.g_csnet_Ws, n_ctas, cstream));
-    for (int k = 0; k < 3; ++k) {
+    if (two) cudaStreamWaitEvent(st3, ev[2], 0);                                   // the item side's chain runs on the third stream
+    for (int j = 0; j < 3; ++j) {
+      const int k = order_f[j];
       const int N = sd[k].B * sd[k].S;
+      cudaStream_t sk = k == 1 ? st3 : stc;
       const float* d_view = k == 2 ? d_vp : nullptr;
       const float* d_fin = k == 2 ? d_co : d_c + (size_t)k * B * V;              // c_u, c_i feed the visual tail; c_net_out the control tail
-      STEP_CALL_C("umpr_cnet_head_bwd", umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
-                                  m.g_conv_b, cstream));
-      STEP_CALL_C("umpr_cnet_conv_bwd_dx_tc", umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch, sb[k].dx_c, n_ctas, cstream));
-      STEP_CALL_C("umpr_cnet_conv_bwd_dw_tc", umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, cstream));
+      { ProfScope ps_("umpr_cnet_head_bwd", sk);
+        UMPR_TRY(umpr_cnet_head_bwd(sb[k].cfeat, sb[k].cidx, sb[k].view_p, m.clin_w, d_view, d_fin, sd[k].B, sd[k].S, V, KC, sb[k].dcfeat, m.g_clin_w, m.g_clin_b,
+                                    m.g_conv_b, sk)); }
+      { ProfScope ps_("umpr_cnet_conv_bwd_dx_tc", sk);
+        UMPR_TRY(umpr_cnet_conv_bwd_dx_tc(sb[k].dcfeat, sb[k].cidx, m.conv_w, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, dx_scratch[k], sb[k].dx_c, n_ctas, sk)); }
+      { ProfScope ps_("umpr_cnet_conv_bwd_dw_tc", sk);
+        UMPR_TRY(umpr_cnet_conv_bwd_dw_tc(sb[k].out_c, sb[k].dcfeat, sb[k].cidx, N, sd[k].L, KC, sd[k].cnet_table, sd[k].cnet_tiles, m.g_conv_w, n_ctas, sk)); }
     }
+    if (two) { cudaEventRecord(ev[6], st3); cudaStreamWaitEvent(stc, ev[6], 0); }      // join: the C-Net GRU backward needs all three dx
     {                                        // the user->item GRU output feeds the convolution AND S-Net: sum of both gradients
       const long n4 = (long)(side_tokens_rows(sd[2]) * Dm / 4);
       add_inplace_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stc>>>(reinterpret_cast<float4*>(sb[2].dx_c), reinterpret_cast<const float4*>(dx_s_ui), n4);
