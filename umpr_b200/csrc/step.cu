@@ -201,19 +201,25 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   // (batch 1024: 3.89 -> 3.59 ms per step).
   int tiles_all = 0;
   for (int k = 0; k < n_sides; ++k) tiles_all += sd[k].n_tiles * (k < 2 && full ? 2 : 1);      // user, item tiles are in both launches
-  (void)tiles_all;
+  // the fourth stream pays for its event traffic only when the kernels are long (small batches are bound by the issuing thread)
+  const bool par = !g_single_stream && 2 * tiles_all > n_ctas + n_ctas / 4;
   const bool two = full && !g_single_stream;
   cudaStream_t stc = st;
   void* cstream = stream;
-  static cudaStream_t side = nullptr, side3 = nullptr;
-  static cudaEvent_t ev[8];
+  static cudaStream_t side = nullptr, side3 = nullptr, side4 = nullptr;
+  static cudaEvent_t ev[12];
   cudaStream_t st3 = st;                     // third stream: the item side of the C-Net tails (convolution, heads) beside ui + user
-  if (two) {
+  cudaStream_t st4 = st;                     // fourth: S-Net beside the co-attention (forward), the item side's S-Net backward, dM
+  if (par || two) {
     if (!side) {
       if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) { side = nullptr; return fail_arg("step: cannot create the side stream"); }
       if (cudaStreamCreateWithFlags(&side3, cudaStreamNonBlocking) != cudaSuccess) { side3 = nullptr; return fail_arg("step: cannot create the side stream"); }
-      for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (cudaStreamCreateWithFlags(&side4, cudaStreamNonBlocking) != cudaSuccess) { side4 = nullptr; return fail_arg("step: cannot create the side stream"); }
+      for (int i = 0; i < 12; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
     }
+    if (par) st4 = side4;
+  }
+  if (two) {
     stc = side;
     cstream = side;
     st3 = side3;
@@ -227,6 +233,14 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     STEP_CALL("umpr_gru_fwd_tc", umpr_gru_fwd_tc(segs, 2, m.rnet_gru, E, sched_r, nq_r, stream));
   }
   const float* gu = sb[0].out_r, *gi = sb[1].out_r;
+  // S-Net of each side (model.py:162-163) needs the GRU output only: it runs on the fourth stream beside giM and the co-attention
+  if (par) { cudaEventRecord(ev[7], st); cudaStreamWaitEvent(st4, ev[7], 0); }
+  for (int k = 0; k < 2; ++k) {
+    const float* Ms = k ? m.snet_i_Ms : m.snet_u_Ms, *Ws = k ? m.snet_i_Ws : m.snet_u_Ws;
+    ProfScope ps_("umpr_snet_fwd_tc", st4);
+    UMPR_TRY(umpr_snet_fwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, Ms, Ws, sd[k].B * sd[k].S, sd[k].L, sb[k].self_atte, n_ctas, st4));
+  }
+  if (par) cudaEventRecord(ev[8], st4);
   // co-attention (model.py:50-55): giM = gi · M over the valid rows, flash-style affinity on tcgen05
   if (BP >= 1024)
     STEP_CALL("umpr_tc_gemm_ws", umpr_tc_gemm_ws(gi, Dm, m.M, Dm, giM, Dm, (int)BP, Dm, Dm, 0, nullptr, 0, 1, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
@@ -237,12 +251,9 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   STEP_CALL("umpr_coattn_fwd_tc", umpr_coattn_fwd_tc(gu, gi, giM, B, P, cst_u, sd[0].S, sd[0].L, cst_i, sd[1].S, sd[1].L, pv_max, co_scratch, soft, soft + BP,
                               soft + 2 * BP, soft + 3 * BP, arg, arg + BP, atte, atte + (size_t)B * Dm, stream));
   if (m.routing_coattn) cudaMemcpyAsync(m.routing_coattn, arg, 2 * BP * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-  for (int k = 0; k < 2; ++k) {              // S-Net of each side (model.py:162-163)
-    const float* Ms = k ? m.snet_i_Ms : m.snet_u_Ms, *Ws = k ? m.snet_i_Ws : m.snet_u_Ws;
-    const int N = sd[k].B * sd[k].S;
-    STEP_CALL("umpr_snet_fwd_tc", umpr_snet_fwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, Ms, Ws, N, sd[k].L, sb[k].self_atte, n_ctas, stream));
+  if (par) cudaStreamWaitEvent(st, ev[8], 0);          // join: self_atte of both sides
+  for (int k = 0; k < 2; ++k)
     STEP_CALL("umpr_snet_sentiment_fwd", umpr_snet_sentiment_fwd(sb[k].self_atte, soft + k * BP, B, sd[k].S, sd[k].L, sb[k].wsum, sb[k].senti, stream));
-  }
   STEP_CALL("umpr_text_match_fwd", umpr_text_match_fwd(atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, m.lin_u, m.lin_i, B, repr, stream));      // model.py:166-168
   const float* pp = nullptr, *pn = nullptr, *pm = nullptr, *nm = nullptr, *fpos = nullptr, *fneg = nullptr;
   if (full) {
@@ -336,30 +347,41 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   STEP_CALL("umpr_tanh_bwd", umpr_tanh_bwd(repr, d_repr, (long)B * Dm, dpre, stream));
   STEP_CALL("umpr_text_match_bwd", umpr_text_match_bwd(dpre, m.lin_u, m.lin_i, B, dins, dins + (size_t)B * Dm, dins + 2 * (size_t)B * Dm, dins + 3 * (size_t)B * Dm, stream));
   STEP_CALL("umpr_text_match_wgrad", umpr_text_match_wgrad(dpre, atte, sb[0].senti, atte + (size_t)B * Dm, sb[1].senti, B, m.g_lin_u, m.g_lin_i, stream));
-  for (int k = 0; k < 2; ++k) {              // S-Net of each side; its input gradient is handed to the co-attention backward (add_u / add_i)
+  // S-Net of each side; its input gradient is handed to the co-attention backward (add_u / add_i).  User side here, item side on the
+  // fourth stream
+  if (par) { cudaEventRecord(ev[9], st); cudaStreamWaitEvent(st4, ev[9], 0); }
+  for (int k = 0; k < 2; ++k) {
+    cudaStream_t sk = k ? st4 : st;
     const float* Ms = k ? m.snet_i_Ms : m.snet_u_Ms, *Ws = k ? m.snet_i_Ws : m.snet_u_Ws;
     float* gMs = k ? m.g_snet_i_Ms : m.g_snet_u_Ms, *gWs = k ? m.g_snet_i_Ws : m.g_snet_u_Ws;
     const int N = sd[k].B * sd[k].S;
-    STEP_CALL("umpr_snet_sentiment_bwd", umpr_snet_sentiment_bwd(sb[k].self_atte, sb[k].wsum, dins + (size_t)(2 * k + 1) * B * Dm, nullptr, B, sd[k].S, sb[k].d_sa, sb[k].d_wsum, stream));
-    STEP_CALL("umpr_snet_bwd_tc", umpr_snet_bwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, sb[k].d_sa, Ms, Ws, N, sd[k].L, sb[k].dx_s, gMs, gWs, n_ctas, stream));
+    { ProfScope ps_("umpr_snet_sentiment_bwd", sk);
+      UMPR_TRY(umpr_snet_sentiment_bwd(sb[k].self_atte, sb[k].wsum, dins + (size_t)(2 * k + 1) * B * Dm, nullptr, B, sd[k].S, sb[k].d_sa, sb[k].d_wsum, sk)); }
+    { ProfScope ps_("umpr_snet_bwd_tc", sk);
+      UMPR_TRY(umpr_snet_bwd_tc(sb[k].out_r, sd[k].snet_table, sd[k].snet_tiles, sb[k].d_sa, Ms, Ws, N, sd[k].L, sb[k].dx_s, gMs, gWs, n_ctas, sk)); }
     const long n = (long)N * sd[k].L;        // d(word_soft)[n][l] = d(sum_l word_soft)[n]  (model.py:79)
-    expand_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sb[k].d_wsum, N, sd[k].L, sb[k].d_soft);
+    expand_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sk>>>(sb[k].d_wsum, N, sd[k].L, sb[k].d_soft);
     UMPR_TRY(check_launch("step expand"));
   }
+  if (par) { cudaEventRecord(ev[10], st4); cudaStreamWaitEvent(st, ev[10], 0); }
   STEP_CALL("umpr_coattn_bwd", umpr_coattn_bwd(gu, gi, giM, soft, soft + BP, soft + 2 * BP, soft + 3 * BP, arg, arg + BP, sb[0].d_soft, sb[1].d_soft, dins, dins + 2 * (size_t)B * Dm,
                            B, P, cst_u, sd[0].S, sd[0].L, cst_i, sd[1].S, sd[1].L, sb[0].dx_s, sb[1].dx_s, sb[0].dx_r, sb[1].dx_r, dgiM, stream));
-  // dgi += dgiM · M^T ;  dM = gi^T · dgiM
+  // dgi += dgiM · M^T (feeds the GRU backward) ;  dM = gi^T · dgiM (a parameter gradient only: fourth stream)
+  if (par) { cudaEventRecord(ev[9], st); cudaStreamWaitEvent(st4, ev[9], 0); }
+  if (BP >= 4096) {
+    ProfScope ps_("umpr_tc_gemm_tn", st4);
+    UMPR_TRY(umpr_tc_gemm_tn(gi, Dm, dgiM, Dm, m.g_M, Dm, Dm, Dm, (long)BP, n_ctas, st4));
+  } else {
+    int splits = (int)(BP / 256);
+    splits = splits < 1 ? 1 : (splits > n_ctas ? n_ctas : splits);
+    ProfScope ps_("umpr_sgemm", st4);
+    UMPR_TRY(umpr_sgemm(gi, 1, Dm, dgiM, Dm, 1, m.g_M, Dm, Dm, Dm, (int)BP, splits, 1, nullptr, 0, st4));
+  }
+  if (par) cudaEventRecord(ev[11], st4);
   if (BP >= 1024)
     STEP_CALL("umpr_tc_gemm_ws", umpr_tc_gemm_ws(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
   else
     STEP_CALL("umpr_tc_gemm_nt", umpr_tc_gemm_nt(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, stream));
-  if (BP >= 4096) {
-    STEP_CALL("umpr_tc_gemm_tn", umpr_tc_gemm_tn(gi, Dm, dgiM, Dm, m.g_M, Dm, Dm, Dm, (long)BP, n_ctas, stream));
-  } else {
-    int splits = (int)(BP / 256);
-    splits = splits < 1 ? 1 : (splits > n_ctas ? n_ctas : splits);
-    STEP_CALL("umpr_sgemm", umpr_sgemm(gi, 1, Dm, dgiM, Dm, 1, m.g_M, Dm, Dm, Dm, (int)BP, splits, 1, nullptr, 0, stream));
-  }
   static cudaStream_t comm_st = nullptr;
   static cudaEvent_t cev[3];
   const bool overlap = g_ov.comm != nullptr;
@@ -372,6 +394,7 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     cudaEventRecord(cev[0], st);
     cudaStreamWaitEvent(comm_st, cev[0], 0);
     if (two) { cudaEventRecord(ev[3], stc); cudaStreamWaitEvent(comm_st, ev[3], 0); }
+    if (par) cudaStreamWaitEvent(comm_st, ev[11], 0);      // dM
     UMPR_TRY(umpr_allreduce(g_ov.comm, g_ov.bucket, g_ov.n_early, comm_st));
   }
   {
@@ -386,9 +409,9 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     UMPR_TRY(umpr_allreduce(g_ov.comm, g_ov.bucket + g_ov.n_early, g_ov.n_total - g_ov.n_early, comm_st));
     cudaEventRecord(cev[2], comm_st);
     cudaStreamWaitEvent(st, cev[2], 0);      // whatever follows on the caller's stream (umpr_adam_step) sees the reduced bucket
-  } else if (two) {
-    cudaEventRecord(ev[3], stc);
-    cudaStreamWaitEvent(st, ev[3], 0);       // join: every gradient is in the bucket
+  } else {
+    if (two) { cudaEventRecord(ev[3], stc); cudaStreamWaitEvent(st, ev[3], 0); }      // join: every gradient is in the bucket
+    if (par) cudaStreamWaitEvent(st, ev[11], 0);
   }
   return 0;
 }
