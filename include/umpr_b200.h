@@ -330,6 +330,10 @@ int umpr_step_comm(void* comm /* umpr_comm_init handle, NULL = off */, float* bu
  * (only == NULL) or just the named one.  _end synchronises and returns the totals aggregated by entry-point name. */
 int umpr_step_profile_begin(const char* only);
 int umpr_step_profile_end(int max_entries, char* names /* max_entries x 48 bytes */, float* ms, int* calls, int* n_out);
+/* umpr_step issues independent branches of the step (R-Net / C-Net, the item side of the C-Net tails, S-Net beside the co-attention)
+ * on up to three library streams beside the caller's so that one branch fills the idle SMs of the other's kernel tails.
+ * serialize = 1: everything on the caller's stream (per-kernel timing without co-scheduled kernels); 0: default. */
+int umpr_step_streams(int serialize);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 --json PATH - the per-launch counters bench.py attaches to its roofline objects (profiles/ncu_metrics.json).
 
     python profiles/ncu_table.py gpurun_out/r2_step_full.ncu-rep "title" --json profiles/ncu_metrics.json > profiles/r2_ncu_full_summary.md
+(the first argument may also be the raw-page CSV of a report: `ncu -i REP --page raw --csv > x.csv`)
 """
 import collections
 import csv
@@ -11,7 +12,8 @@ import subprocess
 import sys
 
 rep, title = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a .ncu-rep, or the CSV that `ncu -i REP --page raw --csv` printed on the GPU box (reports of a whole step exceed what comes back)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 col = {h: i for i, h in enumerate(hdr)}

@@ -79,6 +79,7 @@ SIGNATURES = {
     "umpr_step_comm": [P, P, L, L],
     "umpr_step_profile_begin": [C.c_char_p],
     "umpr_step_profile_end": [I, P, P, P, P],
+    "umpr_step_streams": [I],
     "umpr_step": [P, P, P, P, P, I, P, I, P, P, C.c_longlong, P, P, I, P],
     "umpr_ssnet_fwd": [P, P, P, L, P, P],
     "umpr_ssnet_bwd": [P, P, P, P, L, P, P, P, P],

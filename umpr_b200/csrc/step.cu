@@ -37,7 +37,8 @@ static Profiler g_prof;
 // communication stream WHILE that kernel runs; `late` follows when it has finished (two hand-placed buckets)
 struct Overlap { void* comm = nullptr; float* bucket = nullptr; long n_early = 0, n_total = 0; };
 static Overlap g_ov;
-static bool g_single_stream = false;      // UMPR_STEP_SINGLE_STREAM=1: never fork the C-Net branch (debugging / timing)
+static bool g_single_stream = false;      // UMPR_STEP_SINGLE_STREAM=1 / umpr_step_streams(1): never fork (debugging / timing)
+static bool g_streams_set = false;
 struct ProfScope {
   cudaEvent_t e1 = nullptr;
   cudaStream_t st;
@@ -453,7 +454,7 @@ extern "C" int umpr_step(const umpr_step_model* model, const umpr_step_side* sid
   static int n_ctas = 0;
   if (!n_ctas) {
     const char* e = getenv("UMPR_STEP_SINGLE_STREAM");
-    g_single_stream = e && e[0] == '1';
+    if (!g_streams_set) g_single_stream = e && e[0] == '1';
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n_ctas, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_ctas < 1) n_ctas = 148;
@@ -463,6 +464,13 @@ extern "C" int umpr_step(const umpr_step_model* model, const umpr_step_side* sid
 }
 
 // per-entry-point timing of the following umpr_step calls: every entry point (only == NULL) or just the named one
+// serialize = 1: the whole step on the caller's stream (clean per-kernel timing); 0: branches on the library's side streams
+extern "C" int umpr_step_streams(int serialize) {
+  g_single_stream = serialize != 0;
+  g_streams_set = true;
+  return 0;
+}
+
 extern "C" int umpr_step_profile_begin(const char* only) {
   g_prof.on = true;
   g_prof.only = only ? only : "";

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
       }
       const bool acc_c = MODE == 0 && a.accumulate;
       const bool plain = MODE == 1 || (!a.accumulate && !a.bias && a.act == 0);
+      const bool acc_only = MODE == 0 && a.accumulate && !a.bias && a.act == 0;
       // accumulate mode: the C rows of a 32-column chunk are requested one chunk ahead (the first one before the accumulator
       // is even ready), so their latency hides behind the TMEM load / staging of the previous chunk
       float4 cnext[8];
@@ -254,6 +255,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_ws_gemm_kernel(const WsArgs 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 o = *reinterpret_cast<const float4*>(&sw[(j * 4 + (lane >> 3)) * WS_STG_LD + c4]);
+            if (crow[j] && col_ok) *reinterpret_cast<float4*>(crow[j] + c0) = o;
+          }
+        } else if (acc_only) {                                       // C += A·B^T, nothing else (the co-attention backward's dgi)
+          float4 ccur[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ccur[j] = cnext[j];
+          if (c0 + 32 < BN) fetch_c(c0 + 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = *reinterpret_cast<const float4*>(&sw[(j * 4 + (lane >> 3)) * WS_STG_LD + c4]);
+            o.x += ccur[j].x; o.y += ccur[j].y; o.z += ccur[j].z; o.w += ccur[j].w;
             if (crow[j] && col_ok) *reinterpret_cast<float4*>(crow[j] + c0) = o;
           }
         } else {

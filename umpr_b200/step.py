@@ -148,6 +148,13 @@ class NativeStep:
             raise RuntimeError(f"umpr_step_profile_begin: {_lib.last_error()}")
 
     @staticmethod
+    def serialize(on: bool):
+        """Issue the whole step on the caller's stream (``on``) instead of the library's side streams: per-kernel CUDA-event times
+        are then free of co-scheduled kernels."""
+        if _lib.load().umpr_step_streams(int(bool(on))) != 0:
+            raise RuntimeError(f"umpr_step_streams: {_lib.last_error()}")
+
+    @staticmethod
     def profile_end():
         """→ {entry point: dict(calls, ms)}; synchronises."""
         n_max = 64
