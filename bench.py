@@ -60,6 +60,8 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr = None
         try:
+            if os.environ.get("UMPR_BENCH_NO_CLOCKS") == "1":      # diagnostics: no NVML polling during the timed region
+                raise RuntimeError
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -84,7 +86,9 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            # ~6 samples over the ~70 ms timed region of the default run; polling faster costs throughput (NVML takes driver locks:
+            # 2 GPUs, 4 ms interval: 3.62 ms per step against 3.49 ms without any polling)
+            self._stop.wait(0.012)
 
     def start(self):
         if self.nv is not None:
@@ -456,7 +460,7 @@ def main():
                    "step": "zero_grad+fwd+bwd+allreduce+adam",
                    "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                          ("C-ABI NCCL communicator (umpr_comm_*), 2 buckets [head/attention/conv/C-Net | R-Net GRU], the first all-reduced under the last backward kernel"
-                                          if trainer.overlap else ("C-ABI NCCL communicator, after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
+                                          if trainer.overlap else ("C-ABI NCCL communicator (umpr_comm_*): one all-reduce of the flat bucket after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
                    "host_cores_per_rank": len(cores) if cores else None,
                    "host_thread": host_ms, "by_rank": by_rank or None,
                    "issue": ("one native C-ABI call per step (umpr_step: R-Net / C-Net branches, the item side of the C-Net tails and S-Net on side streams) + all-reduce + umpr_adam_step"

@@ -152,8 +152,12 @@ class FlatTrainer:
             from .step import NativeStep
             if isinstance(model, UMPR):
                 self.native = NativeStep(model, with_grads=True)
-        # with both, the exchange overlaps the backward: two buckets all-reduced from inside umpr_step (csrc/step.cu, umpr_step_comm)
-        self.overlap = self.native is not None and self.comm is not None and os.environ.get("UMPR_OVERLAP", "1") == "1"
+        # UMPR_OVERLAP=1: two buckets all-reduced from inside umpr_step (csrc/step.cu, umpr_step_comm), the first on a communication
+        # stream while the R-Net GRU backward runs.  Off by default since the step runs its branches on several streams: the C-Net
+        # branch now ends together with the R-Net GRU backward, so the first bucket is final only at the very end, and NCCL's CTAs wait
+        # for SMs that the persistent kernels of two branches hold (2 GPUs, batch 1024: 3.80 ms per step with, 3.63 ms without; no
+        # exchange at all 3.61 ms - the ~1 MB all-reduce after the backward costs ~0.03 ms).
+        self.overlap = self.native is not None and self.comm is not None and os.environ.get("UMPR_OVERLAP", "0") == "1"
         self._skip_reduce = os.environ.get("UMPR_DIAG_NO_REDUCE", "0") == "1"     # diagnostics only: ranks run unsynchronised (wrong training)
         if self._skip_reduce:
             self.overlap = False
@@ -173,11 +177,14 @@ class FlatTrainer:
                                    "another optimizer used?) - use FlatTrainer.zero_grad()")
 
     def reduce_gradients(self):
-        """The flat bucket (0.57–1.0 MB, latency-bound) as two all-reduces, [early | late] - the same two collectives, in the same
-        order, that the native step issues from inside its backward (a rank without a shard joins them from here)."""
+        """The flat bucket (0.57–1.0 MB, latency-bound): one all-reduce through the library's communicator - or, with UMPR_OVERLAP=1, the
+        two collectives [early | late] in the order the native step issues them from inside its backward."""
         if self.comm is not None:
-            self.comm.all_reduce(self.bucket[:self.n_early])
-            self.comm.all_reduce(self.bucket[self.n_early:])
+            if self.overlap:          # a rank without a shard joins the two collectives the native step issues (same order)
+                self.comm.all_reduce(self.bucket[:self.n_early])
+                self.comm.all_reduce(self.bucket[self.n_early:])
+            else:
+                self.comm.all_reduce(self.bucket)
         elif self.world > 1:
             dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, group=self.pg)
 
