@@ -328,3 +328,35 @@ def test_training_with_more_than_512_valid_positions_vs_oracle(workload, B, L):
     for k, p in model.named_parameters():
         if p.requires_grad:
             _check_grad(k, p.grad if p.grad is not None else torch.zeros_like(p), g_ref[k])
+
+
+@pytest.mark.parametrize("workload,B", [("music_full", 512), ("music_small_r", 256), ("music_full", 48)])
+def test_native_step_on_side_streams_equals_the_single_stream_step(workload, B):
+    """``umpr_step`` issues its independent branches on up to three streams of the library beside the caller's (C-Net beside R-Net, the item
+    side of the C-Net tails, S-Net beside the co-attention; the fourth one only when the batch is large).  ``umpr_step_streams(1)`` puts
+    everything on the caller's stream: same prediction, loss and gradient bucket (to the noise of float atomics)."""
+    from umpr_b200 import synthetic as syn
+    from umpr_b200.step import NativeStep
+    from umpr_b200.train import FlatTrainer
+    table = syn.make_table(5000, seed=2)
+    batch = syn.make_batch(workload, B, vocab=5000, seed=31)
+    res = []
+    try:
+        for serialize in (True, False, False):           # twice on the side streams: the second call reuses streams and events
+            NativeStep.serialize(serialize)
+            model = syn.build_model(workload, table, seed=1, device=DEV)
+            with torch.no_grad():
+                model.review_net.r_net.M.mul_(0.05)
+            tr = FlatTrainer(model)
+            tr.zero_grad()
+            plans = tr.native.plans_of(batch, torch.device(DEV))
+            assert tr.native.supported(batch, plans)
+            pred, loss = tr.native.run(batch, True, plans)
+            torch.cuda.synchronize()
+            res.append((pred.clone(), loss.clone(), tr.grad.clone()))
+    finally:
+        NativeStep.serialize(False)
+    for pred, loss, grad in res[1:]:
+        assert_close(pred, res[0][0], 1e-6, "prediction")
+        assert_close(loss, res[0][1], 1e-6, "loss")
+        assert float((grad - res[0][2]).abs().max() / res[0][2].abs().max()) < 1e-5

@@ -391,11 +391,9 @@ int cnet_conv_fwd_tc_impl(const float* x, const float* conv_w, const float* conv
   if (table && (table_tiles < 1 || table_tiles > N)) return fail_arg("cnet_conv_fwd_tc: tile table inconsistent (n_tiles=%d, N=%d)", table_tiles, N);
   const int n_tiles = table ? table_tiles : (N + gs - 1) / gs;
   const int smem = CT_XIMG + CT_NW * CT_WSTAGE + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(cnet_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = cudaFuncSetAttribute(cnet_conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);      // (per device: every call)
     if (e != cudaSuccess) { set_error("cnet_conv_fwd_tc smem: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
   }
   if (n_ctas < 1) n_ctas = 148;
   const int grid = n_tiles < n_ctas ? n_tiles : n_ctas;

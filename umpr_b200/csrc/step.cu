@@ -207,8 +207,15 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
   const bool two = full && !g_single_stream;
   cudaStream_t stc = st;
   void* cstream = stream;
-  static cudaStream_t side = nullptr, side3 = nullptr, side4 = nullptr;
-  static cudaEvent_t ev[12];
+  // the library's side streams and events belong to a device: one set per device of the process
+  struct DevStreams { cudaStream_t side = nullptr, side3 = nullptr, side4 = nullptr, comm = nullptr; cudaEvent_t ev[12], cev[3]; };
+  static DevStreams dev_streams[64];
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (cur_dev < 0 || cur_dev >= 64) return fail_arg("step: device %d", cur_dev);
+  DevStreams& ds = dev_streams[cur_dev];
+  cudaStream_t& side = ds.side; cudaStream_t& side3 = ds.side3; cudaStream_t& side4 = ds.side4;
+  cudaEvent_t* ev = ds.ev;
   cudaStream_t st3 = st;                     // third stream: the item side of the C-Net tails (convolution, heads) beside ui + user
   cudaStream_t st4 = st;                     // fourth: S-Net beside the co-attention (forward), the item side's S-Net backward, dM
   if (par || two) {
@@ -383,8 +390,8 @@ static int run_step(const umpr_step_model& m, const umpr_step_side* sd, const fl
     STEP_CALL("umpr_tc_gemm_ws", umpr_tc_gemm_ws(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, sd[1].snet_table, sd[1].snet_tiles, sd[1].L, n_ctas, stream));
   else
     STEP_CALL("umpr_tc_gemm_nt", umpr_tc_gemm_nt(dgiM, Dm, m.M, Dm, sb[1].dx_r, Dm, (int)BP, Dm, Dm, 1, nullptr, 0, 0, stream));
-  static cudaStream_t comm_st = nullptr;
-  static cudaEvent_t cev[3];
+  cudaStream_t& comm_st = ds.comm;
+  cudaEvent_t* cev = ds.cev;
   const bool overlap = g_ov.comm != nullptr;
   if (overlap) {
     if (!comm_st) {
