@@ -204,12 +204,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
           const bool scan = pass == 1 && own < Pown;
           const bool skip = (dbg & 1) != 0;
           uint32_t ra[2][16];
+          const int nch = (nv + 15) >> 4;                           // chunks of 16 columns that hold valid entries
           if (!skip) tmem_ld16_issue(t0, ra[0]);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
-            if (skip) break;
+            if (skip || ch >= nch) break;
             tmem_ld_wait();
-            if (ch + 1 < 8) tmem_ld16_issue(t0 + (ch + 1) * 16, ra[(ch + 1) & 1]);
+            if (ch + 1 < nch) tmem_ld16_issue(t0 + (ch + 1) * 16, ra[(ch + 1) & 1]);
             const int left = nv - ch * 16;
             float cm = -INFINITY;                                   // chunk maximum over the valid columns
 #pragma unroll
@@ -262,13 +263,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
   } else {
     // ------------------------------------------------------------------ MMA issuer (whole warp converged, the elected lane issues)
     const uint32_t el = elect_one_sync();
-    constexpr uint32_t idesc = idesc_bf16(128, 128);
     const uint32_t a0 = smem_u32(a_img);
     int n = 0, na = 0;
     for (int pass = 0; pass < 2; ++pass)
       for (int it = 0; it < Ta; ++it, ++na) {
         mbar_wait(&bars.a_full, na & 1);
+        // only the valid columns of a partly filled tile are multiplied (N rounded up to 16; the scans never read beyond them)
+        const uint32_t idesc_t = idesc_bf16(128, (min(128, Pa - it * 128) + 15) & ~15);        // S^T: columns = rows i of this tile
         for (int jt = 0; jt < Tb; ++jt, ++n) {
+          const uint32_t idesc_s = idesc_bf16(128, (min(128, Pb - jt * 128) + 15) & ~15);      // S: columns = rows j of this tile
           const int s = n & 1;
           mbar_wait(&bars.b_full[s], (n >> 1) & 1);
           if (n >= 2) mbar_wait(&bars.acc_empty[s], ((n >> 1) - 1) & 1);
@@ -284,12 +287,12 @@ __global__ void __launch_bounds__(C2_THREADS, 1) coattn_affinity_tc2_kernel(cons
               if (dbg & 4) break;
               const uint64_t o = (uint64_t)(kk * 2);
               const uint32_t accf = (kb | kk) != 0;
-              umma_bf16_e(el, d1, ah + o, bh + o, idesc, accf);      // S   (rows i, cols j)
-              umma_bf16_e(el, d1, ah + o, bl + o, idesc, 1);
-              umma_bf16_e(el, d1, al + o, bh + o, idesc, 1);
-              umma_bf16_e(el, d2, bh + o, ah + o, idesc, accf);      // S^T (rows j, cols i)
-              umma_bf16_e(el, d2, bh + o, al + o, idesc, 1);
-              umma_bf16_e(el, d2, bl + o, ah + o, idesc, 1);
+              umma_bf16_e(el, d1, ah + o, bh + o, idesc_s, accf);      // S   (rows i, cols j)
+              umma_bf16_e(el, d1, ah + o, bl + o, idesc_s, 1);
+              umma_bf16_e(el, d1, al + o, bh + o, idesc_s, 1);
+              umma_bf16_e(el, d2, bh + o, ah + o, idesc_t, accf);      // S^T (rows j, cols i)
+              umma_bf16_e(el, d2, bh + o, al + o, idesc_t, 1);
+              umma_bf16_e(el, d2, bl + o, ah + o, idesc_t, 1);
             }
           }
           umma_commit_e(el, &bars.b_empty[s]);
