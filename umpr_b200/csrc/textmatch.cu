@@ -22,13 +22,22 @@ __global__ void __launch_bounds__(256) text_match_fwd_kernel(const float* __rest
     xs[s][k] = b0 + s < B ? src[(size_t)(b0 + s) * D + c] : 0.f;
   }
   __syncthreads();
+  // the weight row slice of this lane (16 independent loads), fetched one output ahead: the L2 round trip of output n+8 runs under the
+  // 128 FMAs of output n
+  float wn[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wn[j] = Wu[(size_t)warp * 2 * D + lane + 32 * j]; wn[8 + j] = Wi[(size_t)warp * 2 * D + lane + 32 * j]; }
   for (int n = warp; n < D; n += 8) {
     float acc[TM_S];
 #pragma unroll
     for (int s = 0; s < TM_S; ++s) acc[s] = 0.f;
-    float w[16];                                // the whole weight row slice of this lane up front: 16 independent loads in flight
+    float w[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { w[j] = Wu[(size_t)n * 2 * D + lane + 32 * j]; w[8 + j] = Wi[(size_t)n * 2 * D + lane + 32 * j]; }
+    for (int j = 0; j < 16; ++j) w[j] = wn[j];
+    if (n + 8 < D) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { wn[j] = Wu[(size_t)(n + 8) * 2 * D + lane + 32 * j]; wn[8 + j] = Wi[(size_t)(n + 8) * 2 * D + lane + 32 * j]; }
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
 #pragma unroll
@@ -57,7 +66,7 @@ __global__ void __launch_bounds__(512) text_match_bwd_kernel(const float* __rest
   float acc[TM_S];
 #pragma unroll
   for (int s = 0; s < TM_S; ++s) acc[s] = 0.f;
-#pragma unroll 4
+#pragma unroll 16
   for (int n = 0; n < D; ++n) {
     const float w = W[(size_t)n * 2 * D];
 #pragma unroll
