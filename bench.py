@@ -72,6 +72,11 @@ class ClockSampler:
 
     def _run(self):
         nv = self.nv
+        try:
+            from umpr_b200.train import _pin_worker_thread
+            _pin_worker_thread()            # not on the issuing thread's core
+        except Exception:
+            pass
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake": 0x80}
         while not self._stop.is_set():
@@ -282,6 +287,11 @@ def main():
     model = syn.build_model(args.workload, table, seed=0, device=dev)       # identical replicas: same seed on every rank
     trainer = FlatTrainer(model, lr=1e-6, weight_decay=1e-3)
     n_params = trainer.n_params
+    if world > 1:
+        from umpr_b200.train import pin_issuing_thread
+        issue_cpus = pin_issuing_thread()              # (after the communicators exist: their threads keep the rank's whole slice)
+    else:
+        issue_cpus = None
     NB = 4
     host = [syn.make_batch(args.workload, B, seed=1000 * rank + i) for i in range(NB)]
     pin = lambda t: t.pin_memory() if t.numel() else t
@@ -395,7 +405,9 @@ def main():
     feed["it"] = stream_of(devb, K)
     n0 = trainer.native_steps
     host_t.update(wait_batch=0.0, issue=0.0, n=0)
-    ms, clocks = timed(step_resident, K, ClockSampler(local))
+    # clocks and throttle reasons during the timed region: polled by rank 0 only - NVML calls take driver locks that every process on
+    # the box feels (8 ranks polling every 12 ms: 4.31 ms per step against 3.94 ms in the region without polling)
+    ms, clocks = timed(step_resident, K, ClockSampler(local) if rank == 0 else None)
     by_rank = dict(per_rank)
     host_ms = {"wait_for_batch_ms_per_step": round(1e3 * host_t["wait_batch"] / max(1, host_t["n"]), 3),
                "issue_ms_per_step": round(1e3 * host_t["issue"] / max(1, host_t["n"]), 3)}
@@ -461,7 +473,7 @@ def main():
                    "gradient_exchange": ("none (1 GPU)" if world == 1 else
                                          ("C-ABI NCCL communicator (umpr_comm_*), 2 buckets [head/attention/conv/C-Net | R-Net GRU], the first all-reduced under the last backward kernel"
                                           if trainer.overlap else ("C-ABI NCCL communicator (umpr_comm_*): one all-reduce of the flat bucket after the backward" if trainer.comm is not None else "torch.distributed.all_reduce"))),
-                   "host_cores_per_rank": len(cores) if cores else None,
+                   "host_cores_per_rank": len(cores) if cores else None, "issuing_thread_cpus": issue_cpus,
                    "host_thread": host_ms, "by_rank": by_rank or None,
                    "issue": ("one native C-ABI call per step (umpr_step: R-Net / C-Net branches, the item side of the C-Net tails and S-Net on side streams) + all-reduce + umpr_adam_step"
                              if native else "autograd Functions over per-kernel C-ABI calls"),

@@ -90,7 +90,37 @@ def pin_rank_to_cores(local_rank: int, local_world: int):
     # one intra-op thread: the host work of a rank is many small calls (a 20 k-element sort, a few numpy passes) on the issuing
     # thread and the plan workers - extra OpenMP threads per call would only fight them for this rank's few cores
     torch.set_num_threads(1)
+    # the issuing thread gets the first physical core of the slice to itself (pin_issuing_thread), the plan workers the rest
+    global _ISSUE_CPUS, _WORKER_CPUS
+    first = [c for c in groups[[g[0] for g in groups].index(mine[0])] if c in mine] if mine else []
+    rest = [c for c in mine if c not in first]
+    _ISSUE_CPUS, _WORKER_CPUS = (first, rest) if first and rest else (None, None)
     return mine
+
+
+_ISSUE_CPUS = None
+_WORKER_CPUS = None
+
+
+def pin_issuing_thread():
+    """Call from the thread that issues the steps, AFTER the communicators exist (their helper threads inherit the caller's mask at
+    creation and should keep the whole slice): from now on this thread owns one physical core and the plan-prefetch workers run on
+    the others.  With eight ranks on a 32-thread host a rank has two physical cores; the reference's own ``torch.sort`` calls on the
+    workers (~2 ms of CPU per 3.4 ms step) otherwise share a core with the thread whose launches must stay a step ahead of the GPU -
+    the branches of a step only overlap on the GPU when all of them are already queued."""
+    import os
+    if _ISSUE_CPUS:
+        os.sched_setaffinity(0, _ISSUE_CPUS)
+    return _ISSUE_CPUS
+
+
+def _pin_worker_thread():
+    import os
+    if _WORKER_CPUS:
+        try:
+            os.sched_setaffinity(0, _WORKER_CPUS)
+        except OSError:
+            pass
 
 
 class FlatTrainer:
@@ -286,7 +316,7 @@ class PlanPrefetcher:
         import sys
         self._q = queue.Queue(maxsize=depth)
         self._done = object()
-        self._pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="umpr-plan")
+        self._pool = ThreadPoolExecutor(max_workers=max(1, workers), thread_name_prefix="umpr-plan", initializer=_pin_worker_thread)
         # the step is issued by ONE Python thread: with CPython's default 5 ms switch interval a worker in a pure-Python stretch can
         # keep the GIL for as long as a whole step takes.  0.2 ms bounds what the issuing thread can lose to the workers.
         if sys.getswitchinterval() > 2e-4:
@@ -300,7 +330,11 @@ class PlanPrefetcher:
                 self._q.put(e)
             self._q.put(self._done)
 
-        self._thr = threading.Thread(target=feed, daemon=True)
+        def feed_pinned():
+            _pin_worker_thread()
+            feed()
+
+        self._thr = threading.Thread(target=feed_pinned, daemon=True)
         self._thr.start()
 
     def __iter__(self):
