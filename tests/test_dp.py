@@ -89,3 +89,36 @@ def test_flat_trainer_layout_cpu_tensors():
         assert p.grad.data_ptr() == tr.grad.data_ptr() + off * 4
     with pytest.raises(RuntimeError, match="GPU only"):
         tr.optimizer_step()
+
+
+def test_rank_pinning_gives_the_issuing_thread_its_own_cores():
+    """``pin_rank_to_cores`` deals the host's CPUs out to the ranks of a node (disjoint slices); ``pin_issuing_thread`` then keeps one
+    physical core of the slice for the calling thread and leaves the others to the plan workers.  Run in a child process: affinity is
+    process state."""
+    import subprocess
+    import sys
+    code = (
+        "import os, json, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from umpr_b200 import train\n"
+        "all_cpus = sorted(os.sched_getaffinity(0))\n"
+        "out = []\n"
+        "for r in range(2):\n"
+        "    os.sched_setaffinity(0, all_cpus)\n"
+        "    mine = train.pin_rank_to_cores(r, 2)\n"
+        "    issue = train.pin_issuing_thread()\n"
+        "    out.append([mine, issue, train._WORKER_CPUS, sorted(os.sched_getaffinity(0))])\n"
+        "print(json.dumps([all_cpus, out]))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import json
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    all_cpus, out = json.loads(res.stdout.strip().splitlines()[-1])
+    if len(all_cpus) < 4:
+        pytest.skip("needs at least 4 host CPUs")
+    (m0, i0, w0, a0), (m1, i1, w1, a1) = out
+    assert m0 and m1 and not set(m0) & set(m1) and set(m0) | set(m1) <= set(all_cpus)
+    for mine, issue, workers, now in out:
+        if len(mine) >= 2:
+            assert issue and workers and not set(issue) & set(workers) and set(issue) | set(workers) == set(mine)
+            assert now == sorted(issue)          # the calling thread sits on the issuing cores only
